@@ -1,0 +1,210 @@
+/*
+ * exlr.h — C ABI of libexlr_cuda.so, the B200-native (sm_100a) replacement for the
+ * signal-extraction hot path of excord-lr.
+ *
+ * The reference has no FFI seam: its hot path is the body of the per-record loop in
+ * `main()` (reference src/main.rs:158-770).  This header is the seam a host reader
+ * (Rust over `extern "C"`, C++, or Python/ctypes) binds instead of that loop body:
+ *
+ *   reference (src/main.rs)                      this ABI
+ *   -------------------------------------------  -------------------------------------------
+ *   Cli fields used in the loop (:47-96)         exlr_params
+ *   header tid -> contig name (:198)             exlr_create(ref_names, n_ref)
+ *   one `Record` per iteration (:156-158)        exlr_batch_* : a structure-of-arrays batch of records
+ *   loop body :169-768                           exlr_submit / exlr_wait  (kernels 1-4 on the GPU)
+ *   f.write(line) sites :395,420,448,484,515,766 exlr_result.events (ordered) + exlr_format_lines
+ *   utils.rs:196-283 formatters                  exlr_format_lines
+ *   unwrap()/index panics (utils.rs:109,122-135) negative status codes + exlr_result.err_read
+ *
+ * All entry points are plain C: pointers and sizes only, no C++/torch types, no exceptions
+ * cross the boundary.  There is NO CPU fallback: every compute entry point fails with
+ * EXLR_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef EXLR_H
+#define EXLR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EXLR_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------- */
+#define EXLR_OK                 0
+#define EXLR_ERR_ARG           -1   /* bad argument / NULL pointer                                   */
+#define EXLR_ERR_CUDA          -2   /* CUDA runtime error or no usable device (exlr_last_cuda_error) */
+#define EXLR_ERR_NOMEM         -3   /* host or device allocation failed                              */
+#define EXLR_ERR_CAPACITY      -4   /* batch larger than its allocation, or event buffer overflow    */
+#define EXLR_ERR_STATE         -5   /* call sequence error (wait without submit, ...)                */
+/* Per-record conditions on which the reference panics (exit 101).  exlr_result.err_read holds the
+ * smallest offending record index of the batch; events of records < err_read are valid. */
+#define EXLR_ERR_TID          -10   /* kept record with tid<0 or tid>=n_ref (main.rs:198, contig() panics)      */
+#define EXLR_ERR_CIGAR_OP     -11   /* BAM CIGAR op code > 8 (rust-htslib Cigar decode panics; main.rs:243,525) */
+#define EXLR_ERR_SA_FIELDS    -12   /* SA piece with < 6 ','-separated fields (utils.rs:121-130 index panic)    */
+#define EXLR_ERR_SA_POS       -13   /* SA pos not an i64 (utils.rs:122)                                         */
+#define EXLR_ERR_SA_STRAND    -14   /* SA strand not "+" / "-" (utils.rs:123-127,135)                           */
+#define EXLR_ERR_SA_CIGAR     -15   /* SA CIGAR: op with empty/overflowing count (utils.rs:109) or a byte outside
+                                       [0-9MIDNSHP=X] (outside the supported domain)             */
+#define EXLR_ERR_SA_MAPQ      -16   /* SA mapq not a u8 (utils.rs:129)                                          */
+#define EXLR_ERR_SA_NM        -17   /* SA NM not an i64 (utils.rs:130)                                          */
+#define EXLR_ERR_MERGE_DOMAIN -20   /* >2 indel events and the far-edge merge predicate fires (main.rs:673-678):
+                                       the reference panics or duplicates events there           */
+#define EXLR_ERR_SPLIT_COUNT  -21   /* more than 2^24 segments in one record (meta field overflow)              */
+
+/* ---- parameters: the Cli fields read inside the loop (main.rs:47-96) ------------------ */
+typedef struct exlr_params {
+    uint8_t  mapq;               /* -Q  (main.rs:47-48, used :179)                  default 1    */
+    uint8_t  exclude_secondary;  /* -S  (main.rs:55-56, used :169)                  default 0    */
+    uint8_t  exclude_unmapped;   /* -U  (main.rs:59-60, used :174)                  default 0    */
+    uint8_t  split_only;         /* -s  (main.rs:87-88, used :523)                  default 0    */
+    uint16_t exclude_flag;       /* -F  (main.rs:51-52, used :185)                  default 1796 */
+    uint16_t reserved0;
+    uint32_t indel_min;          /* -i  (main.rs:67-68, used :553,569)              default 50   */
+    uint32_t merge_min;          /* -m  (main.rs:71-72, used :615,673-700)          default 5    */
+    uint32_t ins_clip_min;       /* --ins-clip-min (main.rs:75-76, used :347,353,461) default 1000 */
+    uint32_t reserved1;
+    double   max_pct_overlap;    /* -p  (main.rs:91-92, used :351)                  default 0.0  */
+    uint64_t max_supp_alignm;    /* -k  (main.rs:95-96, used :311)                  default 4    */
+} exlr_params;
+
+/* Fills *p with the reference defaults (main.rs:47-96). */
+void exlr_params_default(exlr_params* p);
+
+/* ---- one output line ---------------------------------------------------------------- */
+/* kind: which f.write site produced the line (selects the -v tag, utils.rs:219,263) */
+#define EXLR_KIND_INDEL        0u  /* main.rs:766  "excord-lr-alignment-event"                        */
+#define EXLR_KIND_INS_ONE_SEG  1u  /* main.rs:484  "excord-lr-alignment-event-large-ins"               */
+#define EXLR_KIND_INS_ONE_ALN  2u  /* main.rs:448  "excord-lr-alignment-event-large-ins-one-alignments" */
+#define EXLR_KIND_INS_TWO_ALN  3u  /* main.rs:395,420 "excord-lr-alignment-event-large-ins-two-alignments" */
+#define EXLR_KIND_SPLIT        4u  /* main.rs:515  "excord-lr-split-read"                              */
+
+/* chrom reference: bit31 clear -> tid (header name, "chr" stripped);
+ * bit31 set -> byte offset into the batch's sa_bytes where the (already "chr"-stripped)
+ * SA contig name starts; it ends at the next ','. */
+#define EXLR_CHROM_IS_SA(c)   (((c) >> 31) & 1u)
+#define EXLR_CHROM_SA_OFF(c)  ((c) & 0x7fffffffu)
+
+/* meta: events_num (column 9) | kind | strand signs */
+#define EXLR_EV_NUM(m)      ((m) & 0x00ffffffu)
+#define EXLR_EV_KIND(m)     (((m) >> 24) & 0xfu)
+#define EXLR_EV_LSTRAND(m)  ((((m) >> 28) & 1u) ? -1 : 1)
+#define EXLR_EV_RSTRAND(m)  ((((m) >> 29) & 1u) ? -1 : 1)
+#define EXLR_EV_META(num, kind, lneg, rneg) \
+    (((uint32_t)(num) & 0x00ffffffu) | ((uint32_t)(kind) << 24) | ((uint32_t)((lneg) ? 1 : 0) << 28) | ((uint32_t)((rneg) ? 1 : 0) << 29))
+
+/* 48 bytes.  Coordinates hold the exact value the reference prints: u32-wrapped (zero
+ * extended) for kinds 0-3 (aligments_event.rs:16-21, main.rs:375-380), signed i64 for
+ * kind 4 (split_read_event.rs:5-6). */
+typedef struct exlr_event {
+    int64_t  lstart, lend, rstart, rend;
+    uint32_t read_idx;   /* record index inside the batch */
+    uint32_t lchrom;     /* chrom reference, see above    */
+    uint32_t rchrom;
+    uint32_t meta;
+} exlr_event;
+
+/* ---- batch: structure-of-arrays views in pinned host memory ------------------------- */
+#define EXLR_SA_NONE   0u  /* record.aux("SA") is Err            (main.rs:518)                      */
+#define EXLR_SA_STRING 1u  /* Ok(Aux::String)                     (main.rs:308)                      */
+#define EXLR_SA_OTHER  2u  /* Ok(other aux type): SA arm runs with the record as the only segment    */
+
+typedef struct exlr_batch_views {
+    uint32_t* cigar;      /* [max_ops]  BAM encoding len<<4|op, records back to back (no padding)  */
+    uint64_t* cigar_off;  /* [max_reads+1] op offset of each record; cigar_off[0] must be 0        */
+    int32_t*  pos;        /* [max_reads] 0-based leftmost position (record.pos(), main.rs:199)     */
+    int32_t*  tid;        /* [max_reads] reference id (record.tid())                               */
+    uint16_t* flag;       /* [max_reads] record.flags()                                            */
+    uint8_t*  mapq;       /* [max_reads] record.mapq()                                             */
+    uint8_t*  sa_kind;    /* [max_reads] EXLR_SA_*                                                 */
+    uint32_t* sa_off;     /* [max_reads+1] byte offset of each record's SA string; sa_off[0] = 0   */
+    uint8_t*  sa_bytes;   /* [max_sa_bytes] SA Z-strings back to back, no NUL                      */
+    uint64_t  max_reads, max_ops, max_sa_bytes, max_events;
+} exlr_batch_views;
+
+typedef struct exlr_result {
+    int32_t  status;          /* EXLR_OK or the (negative) code of the first failing record         */
+    uint32_t err_read;        /* smallest failing record index (valid when status <= -10)           */
+    uint64_t n_reads;
+    uint64_t n_events;        /* number of output lines                                             */
+    const exlr_event* events; /* [n_events] in reference output order               */
+    const uint32_t* line_off; /* [n_reads+1] events of record i are [line_off[i], line_off[i+1])    */
+    uint64_t n_kept;          /* records that passed the filters (main.rs:169-190)                  */
+    uint64_t n_sa_reads;      /* kept records with an SA aux                                        */
+    uint64_t n_cap_dropped;   /* kept records skipped by the -k cap (main.rs:311-313)               */
+    uint64_t n_ops;           /* CIGAR ops in the batch                                             */
+} exlr_result;
+
+/* per-stage device times of the last submit, from CUDA events on the batch's stream (ms) */
+typedef struct exlr_timing {
+    float h2d_ms;       /* host->device copies of the SoA sections              */
+    float classify_ms;  /* kernel 0: filter + ordered list of SA records        */
+    float cigar_ms;     /* kernel 1: CIGAR scan / indel events                  */
+    float sa_cigar_ms;  /* kernel 3a: per-op-type sums of SA records' CIGARs    */
+    float sa_parse_ms;  /* kernel 3b: SA parse, sort, large-INS + split events  */
+    float scan_ms;      /* kernel 4a: per-record line counts -> offsets         */
+    float place_ms;     /* kernel 4b: ordered compaction into the event buffer  */
+    float kernels_ms;   /* first kernel start -> last kernel end                */
+    float d2h_ms;       /* device->host copies of the results                   */
+    uint32_t launches;  /* kernels launched by this submit                      */
+    uint32_t reserved;
+} exlr_timing;
+
+typedef struct exlr_ctx exlr_ctx;
+typedef struct exlr_batch exlr_batch;
+
+/* options for exlr_set_option */
+#define EXLR_OPT_CIGAR_KERNEL 1  /* 0 = flat TMA-staged block scan (default), 1 = warp-per-record */
+#define EXLR_OPT_READS_PER_CTA 2 /* 0 = auto */
+
+/* ---- lifecycle ---------------------------------------------------------------------- */
+int  exlr_abi_version(void);
+/* Number of CUDA devices with compute capability 10.x; <0 on CUDA error. */
+int  exlr_device_count(void);
+
+/* ref_names[i] is the header name of tid i (un-stripped; the library strips one leading
+ * "chr" as aligments_event.rs:38-42 / split_read_event.rs:30-34 do). */
+int  exlr_create(const exlr_params* p, int device, const char* const* ref_names, int n_ref, exlr_ctx** out);
+void exlr_destroy(exlr_ctx* ctx);
+int  exlr_set_option(exlr_ctx* ctx, int option, int64_t value);
+
+/* Allocates pinned host staging + device buffers for one batch (own CUDA stream). */
+int  exlr_batch_alloc(exlr_ctx* ctx, uint64_t max_reads, uint64_t max_ops, uint64_t max_sa_bytes,
+                      uint64_t max_events, exlr_batch** out);
+void exlr_batch_free(exlr_batch* b);
+int  exlr_batch_get_views(exlr_batch* b, exlr_batch_views* v);
+
+/* Asynchronous: H2D of the first n_reads records of the pinned views, kernels, result
+ * header D2H, all on the batch's stream.  The views must not be modified until exlr_wait. */
+int  exlr_submit(exlr_batch* b, uint64_t n_reads);
+/* Kernel-only variants for device-resident measurement: exlr_upload copies the views to
+ * the device (synchronous); exlr_submit_resident runs the kernels on the resident copy. */
+int  exlr_upload(exlr_batch* b, uint64_t n_reads);
+int  exlr_submit_resident(exlr_batch* b);
+/* Blocks until the batch is done, copies events + line offsets to pinned host memory and
+ * fills *res (pointers valid until the next submit/free of this batch).  Returns
+ * res->status. */
+int  exlr_wait(exlr_batch* b, exlr_result* res);
+/* Like exlr_wait but leaves events on the device (only the 64-byte result header is read). */
+int  exlr_wait_resident(exlr_batch* b, exlr_result* res);
+int  exlr_get_timing(exlr_batch* b, exlr_timing* t);
+
+/* ---- host formatter: utils.rs:196-283 ------------------------------------------------- */
+/* Writes the lines of events [ev_begin, ev_end) of `res` into out (capacity out_cap) and
+ * returns the number of bytes the lines need (> out_cap means nothing useful was written).
+ * verbose != 0 adds "\t{tag}\t{qname}\tstrand:{s}\tflag:{f}" and needs qnames/qname_off
+ * (qname of record i = qnames[qname_off[i] .. qname_off[i+1])). */
+int64_t exlr_format_lines(const exlr_ctx* ctx, const exlr_batch* b, const exlr_result* res,
+                          uint64_t ev_begin, uint64_t ev_end, int verbose,
+                          const char* qnames, const uint32_t* qname_off,
+                          char* out, uint64_t out_cap);
+
+const char* exlr_strerror(int status);
+const char* exlr_last_cuda_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXLR_H */
