@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — alignments/s and CIGAR ops/s of the signal-extraction hot path on N B200s.
+
+A step = one pass of the hot path (kernels 0-4) over one batch: BASELINE.json configs[1], 1M simulated HiFi
+molecules (~1.04M alignment records, ~5 % carrying SA tags), default parameters + -p 0.8.
+
+  value        alignments/s, inputs resident in HBM, every step timed on the device with the library's CUDA events
+               on the stream its kernels run on (L2 flushed before each step); max over ranks, summed over ranks.
+  e2e          the same metric through the public API with HOST buffers: pinned SoA views -> exlr_submit (H2D +
+               kernels) -> exlr_wait (D2H of events + line offsets), sub-batches pipelined over several streams.
+  roofline     kernel 1 (CIGAR scan), algorithmic bytes 4 B/op + 11 B/record, against the measured HBM copy peak.
+  cpu_baseline the CPU oracle (a port of the reference loop; the Rust reference cannot be built here) on the same batch.
+
+`--impl reference` times that CPU port with every host core (records sharded over threads) instead of the GPU.
+Multi-GPU: reads are independent, so each rank processes its own shard (weak scaling, no collective on the data
+path); torch.distributed is used only for the barrier and the max-over-ranks reduction of the time.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_ev = index, [], set(), None, threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+        while not self._stop_ev.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_ev.set()
+        if self.is_alive():
+            self.join(timeout=1)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def make_workload(config_id, scale, rank):
+    from excord_lr_b200 import synth
+    c = synth.CONFIGS[config_id]
+    n = max(1, int(c["n"] * scale))
+    hb = synth.generate(c["profile"], c["seed"] + 7919 * rank, n, c["chr20"], c["ultra"] if scale >= 1 else 0)
+    return hb, c
+
+
+def split_for_pipeline(hb, parts):
+    n = hb.n_reads
+    bounds = [n * i // parts for i in range(parts + 1)]
+    return [hb.slice(bounds[i], bounds[i + 1]) for i in range(parts)]
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference loop, sharded over every host core."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_c
+    from excord_lr_b200.batch import ExlrParams
+    if rank != 0:
+        return
+    hb, c = make_workload(args.config, args.scale, 0)
+    p = ExlrParams.make(**c["params"])
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        oracle_c.run_sharded(hb, p, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rs = oracle_c.run_sharded(hb, p, cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    assert all(r.status == 0 for r in rs)
+    v = hb.n_reads / dt
+    line = {"impl": "reference", "metric": "alignments_per_sec", "value": v, "unit": "alignments/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "cigar_ops_per_sec": hb.n_ops / dt,
+            "config": {"workload": c["name"], "records": hb.n_reads, "cigar_ops": hb.n_ops, "sa_bytes": hb.n_sa_bytes,
+                       "params": c["params"]},
+            "cpu_baseline": {"value": v, "unit": "alignments/s", "cores": cores, "kind": "port",
+                             "sample": f"whole workload ({hb.n_reads} records) per step, records sharded over {cores} threads; "
+                                       "the reference's own loop is single-threaded (src/main.rs:158)"},
+            "e2e": {"value": v, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs[i]")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--cigar-kernel", type=int, default=0, help="0 flat TMA scan (default), 1 warp per record")
+    ap.add_argument("--reads-per-cta", type=int, default=0)
+    ap.add_argument("--pipeline-parts", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from excord_lr_b200 import api
+    from excord_lr_b200.batch import ExlrParams
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    hb, c = make_workload(args.config, args.scale, rank)
+    p = ExlrParams.make(**c["params"])
+    R, Cops, A = hb.n_reads, hb.n_ops, hb.n_sa_bytes
+
+    ex = api.Extractor(p, hb.ref_names, local_rank)
+    ex.set_option(api.EXLR_OPT_CIGAR_KERNEL, args.cigar_kernel)
+    ex.set_option(api.EXLR_OPT_READS_PER_CTA, args.reads_per_cta)
+
+    # ---------------- device-resident: value + roofline ----------------
+    big = ex.batch_for(hb)
+    big.upload()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+
+    def resident_step():
+        flush.zero_()
+        torch.cuda.synchronize()
+        big.submit_resident()
+        r = big.wait_resident()
+        return r, big.timing()
+
+    for _ in range(args.warmup):
+        r, _t = resident_step()
+    assert r.status == 0, f"status {r.status}"
+    n_events = r.n_events
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step_ms, k1_ms, stage_ms, launches = [], [], {}, 0
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, t = resident_step()
+        step_ms.append(t.kernels_ms + t.d2h_ms + t.classify_ms * 0)       # first kernel start -> result header on the host
+        k1_ms.append(t.cigar_ms)
+        launches += t.launches
+        for k, v in t.as_dict().items():
+            if k.endswith("_ms"):
+                stage_ms[k] = stage_ms.get(k, 0.0) + v / args.steps
+    barrier()
+    wall_resident = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    total_ms = float(np.sum(step_ms))
+
+    # ---------------- end to end through the public API, host buffers ----------------
+    parts = split_for_pipeline(hb, max(1, args.pipeline_parts))
+    pbatches = [ex.batch_for(h) for h in parts]                              # pinned views already hold the packed records
+
+    def e2e_step():
+        for b in pbatches:
+            b.submit()
+        tot = 0
+        for b in pbatches:
+            rr = b.wait(copy=False)
+            tot += rr.n_events
+        return tot
+
+    for _ in range(args.warmup):
+        ne = e2e_step()
+    assert ne == n_events, f"pipelined run produced {ne} lines, resident run {n_events}"
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0)
+    barrier()
+    h2d = 4 * Cops + A + R * (8 + 4 + 4 + 2 + 1 + 1 + 4) + len(parts) * 12
+    d2h = len(parts) * 64 + 4 * (R + len(parts)) + 48 * n_events
+
+    # ---------------- reduce over ranks ----------------
+    tt = torch.tensor([total_ms, e2e_s * 1e3, float(np.sum(k1_ms))], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([R, Cops, n_events], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    total_ms_max, e2e_ms_max, k1_ms_max = tt.tolist()
+    R_all, C_all, E_all = cnt.tolist()
+
+    # ---------------- cpu baseline (rank 0, N=1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_c
+        t0 = time.perf_counter()
+        want = oracle_c.run(hb, p)
+        dt = time.perf_counter() - t0
+        assert want.status == 0 and want.n_events if hasattr(want, "n_events") else True
+        cpu = {"value": R / dt, "unit": "alignments/s", "cores": 1, "kind": "port",
+               "sample": f"the whole workload once ({R} records, {Cops} CIGAR ops, {dt:.2f} s), single thread like the reference loop",
+               "lines": int(len(want.events)), "matches_gpu_line_count": bool(len(want.events) == n_events)}
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        k1_bytes = 4.0 * Cops + 11.0 * R                                  # per launch, this rank
+        k1_avg_s = (float(np.mean(k1_ms)) / 1e3) if k1_ms else float("nan")
+        achieved = k1_bytes / k1_avg_s / 1e9 if k1_avg_s > 0 else 0.0
+        traffic = load_traffic()
+        pipe_bytes = 24.0 * R + 4.0 * Cops + A + 4.0 * R + 48.0 * n_events
+        ms_per_step = total_ms_max / args.steps
+        value = R_all / (total_ms_max / 1e3) * args.steps
+        e2e_value = R_all / (e2e_ms_max / 1e3) * args.steps
+        line = {
+            "metric": "alignments_per_sec", "value": value, "unit": "alignments/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "cigar_ops_per_sec": C_all / (total_ms_max / 1e3) * args.steps,
+            "config": {"workload": c["name"], "records_per_gpu": R, "cigar_ops_per_gpu": Cops, "sa_bytes_per_gpu": A,
+                       "lines_per_gpu": n_events, "params": c["params"], "parallelism": f"dp{world} (record shards, no collective)",
+                       "l2": "flushed (256 MB memset) before every timed step; inputs are also larger than L2",
+                       "cigar_kernel": "flat TMA-staged block scan" if args.cigar_kernel == 0 else "warp per record"},
+            "e2e": {"value": e2e_value, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms_max / args.steps, "pipeline_parts": len(parts),
+                    "h2d_gbs": h2d * args.steps / (e2e_ms_max / 1e3) / 1e9,
+                    "cigar_ops_per_sec": C_all / (e2e_ms_max / 1e3) * args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k1_flat" if args.cigar_kernel == 0 else "k1_warp", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": k1_bytes, "avg_launch_ms": k1_avg_s * 1e3,
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                         "pipeline_achieved_gbs": pipe_bytes / (ms_per_step / 1e3) / 1e9,
+                         "pipeline_frac": pipe_bytes / (ms_per_step / 1e3) / 1e9 / peak},
+            "stage_ms": stage_ms,
+            "clocks": clocks,
+            "wall_s_resident_loop": wall_resident,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+
+    for b in pbatches:
+        b.free()
+    big.free()
+    ex.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

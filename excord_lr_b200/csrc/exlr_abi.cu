@@ -1,0 +1,490 @@
+// exlr_abi.cu — host side of libexlr_cuda.so: the extern "C" entry points of include/exlr.h.
+//
+// One exlr_ctx per GPU; each exlr_batch owns a CUDA stream, pinned host staging for the
+// structure-of-arrays views, the device copies, scratch and result buffers, so several
+// batches can be in flight (H2D of one overlapping the kernels / D2H of another).
+// There is no CPU fallback anywhere in this file: without a usable sm_100 device every
+// compute entry point returns EXLR_ERR_CUDA.
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "exlr_device.cuh"
+
+using namespace exlr;
+
+static thread_local char g_cuda_err[512] = "";
+
+static int cuda_fail(cudaError_t e, const char* what)
+{
+    snprintf(g_cuda_err, sizeof g_cuda_err, "%s: %s", what, cudaGetErrorString(e));
+    return EXLR_ERR_CUDA;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+
+enum { EV_START = 0, EV_H2D, EV_K0, EV_K1, EV_K3A, EV_K3B, EV_K4A, EV_K4B, EV_D2H, EV_COUNT };
+
+struct exlr_ctx {
+    int device = 0;
+    exlr_params params{};
+    DevParams dparams{};
+    std::vector<std::string> ref_stripped;     // "chr" removed (aligments_event.rs:38-42)
+    uint8_t* d_ref_bytes = nullptr; uint32_t* d_ref_off = nullptr; int n_ref = 0;
+    int cigar_kernel = 0;                      // EXLR_OPT_CIGAR_KERNEL
+    uint32_t reads_per_cta = 0;                // EXLR_OPT_READS_PER_CTA (0 = auto)
+};
+
+struct exlr_batch {
+    exlr_ctx* ctx = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_COUNT] = {};
+    exlr_batch_views hv{};                     // pinned host views
+    void* h_slab = nullptr;                    // pinned: inputs
+    void* h_out = nullptr;                     // pinned: ctrl + line_off + events
+    Ctrl* h_ctrl = nullptr; uint32_t* h_line_off = nullptr; exlr_event* h_events = nullptr;
+    void* d_slab = nullptr;                    // one device allocation, carved up below
+    DevBatch dv{};
+    size_t ctrl_bytes = 0;                     // ctrl + both scan status arrays (one memset)
+    uint64_t n_reads = 0, n_ops = 0;
+    bool submitted = false, resident_uploaded = false, have_timing = false;
+    uint32_t launches = 0;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" {
+
+int exlr_abi_version(void) { return EXLR_ABI_VERSION; }
+
+void exlr_params_default(exlr_params* p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->mapq = 1; p->exclude_flag = 1796; p->indel_min = 50; p->merge_min = 5; p->ins_clip_min = 1000;
+    p->max_pct_overlap = 0.0; p->max_supp_alignm = 4;
+}
+
+int exlr_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaGetDeviceCount"); return EXLR_ERR_CUDA; }
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+    }
+    return ok;
+}
+
+const char* exlr_last_cuda_error(void) { return g_cuda_err; }
+
+const char* exlr_strerror(int s)
+{
+    switch (s) {
+    case EXLR_OK: return "ok";
+    case EXLR_ERR_ARG: return "bad argument";
+    case EXLR_ERR_CUDA: return "CUDA error or no usable sm_100 device (no CPU fallback exists)";
+    case EXLR_ERR_NOMEM: return "out of memory";
+    case EXLR_ERR_CAPACITY: return "batch exceeds its allocated capacity";
+    case EXLR_ERR_STATE: return "call sequence error";
+    case EXLR_ERR_TID: return "record passes the filters but has no valid reference id (reference panics in contig())";
+    case EXLR_ERR_CIGAR_OP: return "unknown CIGAR operation code (reference panics)";
+    case EXLR_ERR_SA_FIELDS: return "SA entry with fewer than 6 fields (reference panics)";
+    case EXLR_ERR_SA_POS: return "SA position is not an integer (reference panics)";
+    case EXLR_ERR_SA_STRAND: return "SA strand is not + or - (reference panics)";
+    case EXLR_ERR_SA_CIGAR: return "SA CIGAR is malformed or outside [0-9MIDNSHP=X]";
+    case EXLR_ERR_SA_MAPQ: return "SA mapq is not a u8 (reference panics)";
+    case EXLR_ERR_SA_NM: return "SA NM is not an integer (reference panics)";
+    case EXLR_ERR_MERGE_DOMAIN: return "more than two indel events with merge_min reaching across them: the reference panics or duplicates events here";
+    case EXLR_ERR_SPLIT_COUNT: return "more than 2^24 segments in one record";
+    default: return "unknown status";
+    }
+}
+
+int exlr_create(const exlr_params* p, int device, const char* const* ref_names, int n_ref, exlr_ctx** out)
+{
+    if (!p || !out || n_ref < 0 || (n_ref > 0 && !ref_names)) return EXLR_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return EXLR_ERR_ARG;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        snprintf(g_cuda_err, sizeof g_cuda_err, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return EXLR_ERR_CUDA;
+    }
+    CK(cudaSetDevice(device));
+    CK(configure_kernels(device));
+    exlr_ctx* c = new (std::nothrow) exlr_ctx();
+    if (!c) return EXLR_ERR_NOMEM;
+    c->device = device; c->params = *p; c->n_ref = n_ref;
+    DevParams& d = c->dparams;
+    d.mapq = p->mapq; d.exclude_flag = p->exclude_flag; d.exclude_secondary = p->exclude_secondary;
+    d.exclude_unmapped = p->exclude_unmapped; d.split_only = p->split_only; d.indel_min = p->indel_min;
+    d.merge_min = p->merge_min; d.ins_clip_min = p->ins_clip_min; d.max_pct_overlap = p->max_pct_overlap;
+    d.max_supp_alignm = p->max_supp_alignm;
+    std::vector<uint32_t> off(n_ref + 1, 0);
+    std::string bytes;
+    for (int i = 0; i < n_ref; i++) {
+        std::string s = ref_names[i] ? ref_names[i] : "";
+        if (s.rfind("chr", 0) == 0) s = s.substr(3);
+        c->ref_stripped.push_back(s);
+        off[i] = (uint32_t)bytes.size();
+        bytes += s;
+    }
+    off[n_ref] = (uint32_t)bytes.size();
+    cudaError_t e = cudaMalloc(&c->d_ref_bytes, bytes.size() + 16);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_ref_off, off.size() * 4);
+    if (e == cudaSuccess && !bytes.empty()) e = cudaMemcpy(c->d_ref_bytes, bytes.data(), bytes.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_ref_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { exlr_destroy(c); return cuda_fail(e, "reference name table"); }
+    *out = c;
+    return EXLR_OK;
+}
+
+void exlr_destroy(exlr_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_ref_bytes); cudaFree(c->d_ref_off);
+    delete c;
+}
+
+int exlr_set_option(exlr_ctx* c, int option, int64_t value)
+{
+    if (!c) return EXLR_ERR_ARG;
+    switch (option) {
+    case EXLR_OPT_CIGAR_KERNEL: if (value != 0 && value != 1) return EXLR_ERR_ARG; c->cigar_kernel = (int)value; return EXLR_OK;
+    case EXLR_OPT_READS_PER_CTA: if (value < 0 || value > 256) return EXLR_ERR_ARG; c->reads_per_cta = (uint32_t)value; return EXLR_OK;
+    default: return EXLR_ERR_ARG;
+    }
+}
+
+void exlr_batch_free(exlr_batch* b)
+{
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (auto& e : b->ev) if (e) cudaEventDestroy(e);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    cudaFree(b->d_slab);
+    cudaFreeHost(b->h_slab); cudaFreeHost(b->h_out);
+    delete b;
+}
+
+int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t max_sa_bytes, uint64_t max_events, exlr_batch** out)
+{
+    if (!c || !out) return EXLR_ERR_ARG;
+    *out = nullptr;
+    if (max_reads == 0 || max_reads >= 0xfffffff0ull || max_sa_bytes >= 0x7ffffff0ull || max_events >= 0xfffffff0ull) return EXLR_ERR_ARG;
+    if (max_events == 0) max_events = 2 * max_reads + 1024;
+    CK(cudaSetDevice(c->device));
+    exlr_batch* b = new (std::nothrow) exlr_batch();
+    if (!b) return EXLR_ERR_NOMEM;
+    b->ctx = c;
+    const size_t R = max_reads, A = 256;
+    // ---- pinned host input slab
+    size_t ho = 0;
+    auto hcarve = [&](size_t bytes) { size_t at = ho; ho = align_up(ho + bytes, A); return at; };
+    const size_t h_cigar = hcarve((max_ops + 4) * 4), h_coff = hcarve((R + 1) * 8), h_pos = hcarve(R * 4), h_tid = hcarve(R * 4),
+                 h_flag = hcarve(R * 2), h_mapq = hcarve(R), h_kind = hcarve(R), h_soff = hcarve((R + 1) * 4), h_sab = hcarve(max_sa_bytes + 16);
+    cudaError_t e = cudaHostAlloc(&b->h_slab, ho, cudaHostAllocDefault);
+    if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostAlloc(inputs)"); }
+    char* hs = (char*)b->h_slab;
+    b->hv.cigar = (uint32_t*)(hs + h_cigar); b->hv.cigar_off = (uint64_t*)(hs + h_coff); b->hv.pos = (int32_t*)(hs + h_pos);
+    b->hv.tid = (int32_t*)(hs + h_tid); b->hv.flag = (uint16_t*)(hs + h_flag); b->hv.mapq = (uint8_t*)(hs + h_mapq);
+    b->hv.sa_kind = (uint8_t*)(hs + h_kind); b->hv.sa_off = (uint32_t*)(hs + h_soff); b->hv.sa_bytes = (uint8_t*)(hs + h_sab);
+    b->hv.max_reads = max_reads; b->hv.max_ops = max_ops; b->hv.max_sa_bytes = max_sa_bytes; b->hv.max_events = max_events;
+    b->hv.cigar_off[0] = 0; b->hv.sa_off[0] = 0;
+    // ---- pinned host output slab
+    size_t oo = 0;
+    auto ocarve = [&](size_t bytes) { size_t at = oo; oo = align_up(oo + bytes, A); return at; };
+    const size_t o_ctrl = ocarve(sizeof(Ctrl)), o_loff = ocarve((R + 1) * 4), o_ev = ocarve(max_events * sizeof(exlr_event));
+    e = cudaHostAlloc(&b->h_out, oo, cudaHostAllocDefault);
+    if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostAlloc(outputs)"); }
+    b->h_ctrl = (Ctrl*)((char*)b->h_out + o_ctrl); b->h_line_off = (uint32_t*)((char*)b->h_out + o_loff);
+    b->h_events = (exlr_event*)((char*)b->h_out + o_ev);
+    // ---- device slab
+    const uint32_t tiles = scan_tiles((uint32_t)R);
+    const bool need_pool = c->params.max_supp_alignm + 1 > (uint64_t)kLocalSegs;
+    const size_t pool_cap = need_pool ? (max_sa_bytes / 10 + R + 64) : 0;
+    size_t dof = 0;
+    auto dcarve = [&](size_t bytes) { size_t at = dof; dof = align_up(dof + bytes, A); return at; };
+    const size_t d_ctrl = dcarve(sizeof(Ctrl) + (size_t)tiles * 16);          // ctrl | scan_a | scan_b : one memset
+    const size_t d_cigar = dcarve((max_ops + 4) * 4 + 16), d_coff = dcarve((R + 1) * 8), d_pos = dcarve(R * 4), d_tid = dcarve(R * 4),
+                 d_flag = dcarve(R * 2), d_mapq = dcarve(R), d_kind = dcarve(R), d_soff = dcarve((R + 1) * 4), d_sab = dcarve(max_sa_bytes + 16),
+                 d_k1 = dcarve(R * 8), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
+                 d_raw = dcarve(max_events * sizeof(RawEv)), d_saev = dcarve(max_events * sizeof(exlr_event)),
+                 d_pool = dcarve(pool_cap * sizeof(Seg)), d_loff = dcarve((R + 1) * 4), d_ev = dcarve(max_events * sizeof(exlr_event));
+    e = cudaMalloc(&b->d_slab, dof);
+    if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaMalloc(batch)"); }
+    char* ds = (char*)b->d_slab;
+    DevBatch& v = b->dv;
+    v.ctrl = (Ctrl*)(ds + d_ctrl);
+    v.scan_a = (unsigned long long*)(ds + d_ctrl + sizeof(Ctrl)); v.scan_b = v.scan_a + tiles;
+    b->ctrl_bytes = sizeof(Ctrl) + (size_t)tiles * 16;
+    v.cigar = (uint32_t*)(ds + d_cigar); v.cigar_off = (unsigned long long*)(ds + d_coff); v.pos = (int32_t*)(ds + d_pos);
+    v.tid = (int32_t*)(ds + d_tid); v.flag = (uint16_t*)(ds + d_flag); v.mapq = (uint8_t*)(ds + d_mapq); v.sa_kind = (uint8_t*)(ds + d_kind);
+    v.sa_off = (uint32_t*)(ds + d_soff); v.sa_bytes = (uint8_t*)(ds + d_sab);
+    v.ref_bytes = c->d_ref_bytes; v.ref_off = c->d_ref_off; v.n_ref = c->n_ref;
+    v.k1 = (uint2*)(ds + d_k1); v.csa = (uint32_t*)(ds + d_csa); v.sa_list = (uint32_t*)(ds + d_list); v.sa_base = (uint32_t*)(ds + d_base);
+    v.sa_sum = (SaSum*)(ds + d_sum); v.raw = (RawEv*)(ds + d_raw); v.sa_ev = (exlr_event*)(ds + d_saev);
+    v.seg_pool = (Seg*)(ds + d_pool); v.seg_pool_cap = (uint32_t)pool_cap;
+    v.line_off = (uint32_t*)(ds + d_loff); v.events = (exlr_event*)(ds + d_ev);
+    v.n_reads = 0; v.max_events = (uint32_t)max_events;
+    e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < EV_COUNT && e == cudaSuccess; i++) e = cudaEventCreate(&b->ev[i]);
+    if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "stream/event creation"); }
+    *out = b;
+    return EXLR_OK;
+}
+
+int exlr_batch_get_views(exlr_batch* b, exlr_batch_views* v)
+{
+    if (!b || !v) return EXLR_ERR_ARG;
+    *v = b->hv;
+    return EXLR_OK;
+}
+
+static int check_sizes(exlr_batch* b, uint64_t n_reads)
+{
+    if (n_reads > b->hv.max_reads) return EXLR_ERR_CAPACITY;
+    if (b->hv.cigar_off[0] != 0 || b->hv.sa_off[0] != 0) return EXLR_ERR_ARG;
+    if (b->hv.cigar_off[n_reads] > b->hv.max_ops || b->hv.sa_off[n_reads] > b->hv.max_sa_bytes) return EXLR_ERR_CAPACITY;
+    return EXLR_OK;
+}
+
+static int copy_inputs(exlr_batch* b, uint64_t n)
+{
+    const exlr_batch_views& h = b->hv; DevBatch& d = b->dv; cudaStream_t st = b->stream;
+    const uint64_t ops = h.cigar_off[n], sab = h.sa_off[n];
+    if (ops) CK(cudaMemcpyAsync((void*)d.cigar, h.cigar, ops * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((void*)d.cigar_off, h.cigar_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((void*)d.pos, h.pos, n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((void*)d.tid, h.tid, n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((void*)d.flag, h.flag, n * 2, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((void*)d.mapq, h.mapq, n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((void*)d.sa_kind, h.sa_kind, n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((void*)d.sa_off, h.sa_off, (n + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (sab) CK(cudaMemcpyAsync((void*)d.sa_bytes, h.sa_bytes, sab, cudaMemcpyHostToDevice, st));
+    return EXLR_OK;
+}
+
+static uint32_t auto_rpc(uint64_t n_reads, uint64_t n_ops)
+{
+    // aim at ~12k ops (48 KB of CIGAR) per CTA so short-read batches use full 256-record CTAs and
+    // long-read batches still spread over every SM
+    const uint64_t mean = n_reads ? (n_ops + n_reads - 1) / n_reads : 1;
+    uint64_t rpc = 12288 / (mean ? mean : 1);
+    if (rpc < 1) rpc = 1;
+    if (rpc > 256) rpc = 256;
+    return (uint32_t)rpc;
+}
+
+static int run_kernels(exlr_batch* b)
+{
+    exlr_ctx* c = b->ctx; cudaStream_t st = b->stream; DevBatch& d = b->dv;
+    b->launches = 0;
+    CK(cudaMemsetAsync(d.ctrl, 0, b->ctrl_bytes, st));
+    launch_k0(d, c->dparams, st); b->launches++;
+    CK(cudaEventRecord(b->ev[EV_K0], st));
+    if (!c->params.split_only) {
+        const uint32_t rpc = c->reads_per_cta ? c->reads_per_cta : auto_rpc(b->n_reads, b->n_ops);
+        launch_k1(d, c->dparams, c->cigar_kernel, rpc, st); b->launches++;
+    }
+    CK(cudaEventRecord(b->ev[EV_K1], st));
+    launch_k3a(d, c->dparams, st); b->launches++;
+    CK(cudaEventRecord(b->ev[EV_K3A], st));
+    launch_k3b(d, c->dparams, st); b->launches++;
+    CK(cudaEventRecord(b->ev[EV_K3B], st));
+    launch_k4a(d, c->dparams, st); b->launches++;
+    CK(cudaEventRecord(b->ev[EV_K4A], st));
+    launch_k4b(d, c->dparams, st); b->launches++;
+    CK(cudaEventRecord(b->ev[EV_K4B], st));
+    CK(cudaMemcpyAsync(b->h_ctrl, d.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(b->ev[EV_D2H], st));
+    CK(cudaGetLastError());
+    return EXLR_OK;
+}
+
+int exlr_submit(exlr_batch* b, uint64_t n_reads)
+{
+    if (!b) return EXLR_ERR_ARG;
+    int rc = check_sizes(b, n_reads);
+    if (rc) return rc;
+    CK(cudaSetDevice(b->ctx->device));
+    b->n_reads = n_reads; b->n_ops = b->hv.cigar_off[n_reads]; b->dv.n_reads = (uint32_t)n_reads;
+    b->resident_uploaded = false; b->have_timing = false;
+    if (n_reads == 0) { memset(b->h_ctrl, 0, sizeof(Ctrl)); b->h_line_off[0] = 0; b->submitted = true; return EXLR_OK; }
+    CK(cudaEventRecord(b->ev[EV_START], b->stream));
+    rc = copy_inputs(b, n_reads);
+    if (rc) return rc;
+    CK(cudaEventRecord(b->ev[EV_H2D], b->stream));
+    rc = run_kernels(b);
+    if (rc) return rc;
+    b->submitted = true; b->have_timing = true;
+    return EXLR_OK;
+}
+
+int exlr_upload(exlr_batch* b, uint64_t n_reads)
+{
+    if (!b) return EXLR_ERR_ARG;
+    int rc = check_sizes(b, n_reads);
+    if (rc) return rc;
+    if (n_reads == 0) return EXLR_ERR_ARG;
+    CK(cudaSetDevice(b->ctx->device));
+    b->n_reads = n_reads; b->n_ops = b->hv.cigar_off[n_reads]; b->dv.n_reads = (uint32_t)n_reads;
+    rc = copy_inputs(b, n_reads);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(b->stream));
+    b->resident_uploaded = true; b->submitted = false;
+    return EXLR_OK;
+}
+
+int exlr_submit_resident(exlr_batch* b)
+{
+    if (!b) return EXLR_ERR_ARG;
+    if (!b->resident_uploaded) return EXLR_ERR_STATE;
+    CK(cudaSetDevice(b->ctx->device));
+    CK(cudaEventRecord(b->ev[EV_START], b->stream));
+    CK(cudaEventRecord(b->ev[EV_H2D], b->stream));
+    int rc = run_kernels(b);
+    if (rc) return rc;
+    b->submitted = true; b->have_timing = true;
+    return EXLR_OK;
+}
+
+static int status_of_rank(uint32_t rank)
+{
+    switch (rank) {
+    case RANK_TID: return EXLR_ERR_TID; case RANK_CIGAR_OP: return EXLR_ERR_CIGAR_OP; case RANK_SA_FIELDS: return EXLR_ERR_SA_FIELDS;
+    case RANK_SA_POS: return EXLR_ERR_SA_POS; case RANK_SA_STRAND: return EXLR_ERR_SA_STRAND; case RANK_SA_CIGAR: return EXLR_ERR_SA_CIGAR;
+    case RANK_SA_MAPQ: return EXLR_ERR_SA_MAPQ; case RANK_SA_NM: return EXLR_ERR_SA_NM; case RANK_MERGE_DOMAIN: return EXLR_ERR_MERGE_DOMAIN;
+    default: return EXLR_ERR_SPLIT_COUNT;
+    }
+}
+
+static int finish(exlr_batch* b, exlr_result* res, bool fetch)
+{
+    if (!b || !res) return EXLR_ERR_ARG;
+    if (!b->submitted) return EXLR_ERR_STATE;
+    memset(res, 0, sizeof(*res));
+    res->n_reads = b->n_reads; res->n_ops = b->n_ops; res->err_read = 0xffffffffu;
+    res->events = b->h_events; res->line_off = b->h_line_off;
+    if (b->n_reads == 0) { res->status = EXLR_OK; return EXLR_OK; }
+    CK(cudaSetDevice(b->ctx->device));
+    CK(cudaStreamSynchronize(b->stream));
+    const Ctrl& c = *b->h_ctrl;
+    res->n_events = c.n_events; res->n_kept = c.n_kept; res->n_sa_reads = c.n_sa; res->n_cap_dropped = c.n_dropped;
+    if (c.overflow) { res->status = EXLR_ERR_CAPACITY; res->n_events = 0; return res->status; }
+    if (fetch) {
+        CK(cudaMemcpyAsync(b->h_line_off, b->dv.line_off, (b->n_reads + 1) * 4, cudaMemcpyDeviceToHost, b->stream));
+        if (c.n_events) CK(cudaMemcpyAsync(b->h_events, b->dv.events, (size_t)c.n_events * sizeof(exlr_event), cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+    }
+    if (c.err_key) {
+        const unsigned long long key = ~c.err_key;
+        res->err_read = (uint32_t)(key >> 8);
+        res->status = status_of_rank((uint32_t)(key & 0xff));
+    }
+    return res->status;
+}
+
+int exlr_wait(exlr_batch* b, exlr_result* res) { return finish(b, res, true); }
+int exlr_wait_resident(exlr_batch* b, exlr_result* res) { return finish(b, res, false); }
+
+int exlr_get_timing(exlr_batch* b, exlr_timing* t)
+{
+    if (!b || !t) return EXLR_ERR_ARG;
+    if (!b->have_timing) return EXLR_ERR_STATE;
+    memset(t, 0, sizeof(*t));
+    CK(cudaSetDevice(b->ctx->device));
+    CK(cudaEventSynchronize(b->ev[EV_D2H]));
+    CK(cudaEventElapsedTime(&t->h2d_ms, b->ev[EV_START], b->ev[EV_H2D]));
+    CK(cudaEventElapsedTime(&t->classify_ms, b->ev[EV_H2D], b->ev[EV_K0]));
+    CK(cudaEventElapsedTime(&t->cigar_ms, b->ev[EV_K0], b->ev[EV_K1]));
+    CK(cudaEventElapsedTime(&t->sa_cigar_ms, b->ev[EV_K1], b->ev[EV_K3A]));
+    CK(cudaEventElapsedTime(&t->sa_parse_ms, b->ev[EV_K3A], b->ev[EV_K3B]));
+    CK(cudaEventElapsedTime(&t->scan_ms, b->ev[EV_K3B], b->ev[EV_K4A]));
+    CK(cudaEventElapsedTime(&t->place_ms, b->ev[EV_K4A], b->ev[EV_K4B]));
+    CK(cudaEventElapsedTime(&t->kernels_ms, b->ev[EV_H2D], b->ev[EV_K4B]));
+    CK(cudaEventElapsedTime(&t->d2h_ms, b->ev[EV_K4B], b->ev[EV_D2H]));
+    t->launches = b->launches;
+    return EXLR_OK;
+}
+
+// ---- host formatter (get_alignment_event_record / get_alignment_split_record, utils.rs:196-283) ----
+static inline char* put_i64(char* p, int64_t v)
+{
+    char tmp[24]; int n = 0;
+    uint64_t u = v < 0 ? 0ull - (uint64_t)v : (uint64_t)v;
+    do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) *p++ = '-';
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+static const char* const kTags[5] = {
+    "excord-lr-alignment-event", "excord-lr-alignment-event-large-ins", "excord-lr-alignment-event-large-ins-one-alignments",
+    "excord-lr-alignment-event-large-ins-two-alignments", "excord-lr-split-read"};
+
+int64_t exlr_format_lines(const exlr_ctx* c, const exlr_batch* b, const exlr_result* res, uint64_t ev_begin, uint64_t ev_end,
+                          int verbose, const char* qnames, const uint32_t* qname_off, char* out, uint64_t out_cap)
+{
+    if (!c || !b || !res || ev_begin > ev_end || ev_end > res->n_events) return EXLR_ERR_ARG;
+    if (verbose && (!qnames || !qname_off)) return EXLR_ERR_ARG;
+    const uint8_t* sa = b->hv.sa_bytes;
+    uint64_t w = 0;
+    std::vector<char> line;
+    for (uint64_t i = ev_begin; i < ev_end; i++) {
+        const exlr_event& e = res->events[i];
+        const char* cs[2]; size_t cl[2];
+        const uint32_t refs[2] = {e.lchrom, e.rchrom};
+        for (int s = 0; s < 2; s++) {
+            if (EXLR_CHROM_IS_SA(refs[s])) {
+                const char* p = (const char*)sa + EXLR_CHROM_SA_OFF(refs[s]);
+                size_t n = 0; while (p[n] != ',') n++;
+                cs[s] = p; cl[s] = n;
+            } else {
+                const std::string& nm = c->ref_stripped[refs[s]];
+                cs[s] = nm.data(); cl[s] = nm.size();
+            }
+        }
+        const uint32_t r = e.read_idx, kind = EXLR_EV_KIND(e.meta);
+        const size_t qn = verbose ? (size_t)(qname_off[r + 1] - qname_off[r]) : 0;
+        line.resize(cl[0] + cl[1] + qn + 256);
+        char* p = line.data();
+        memcpy(p, cs[0], cl[0]); p += cl[0]; *p++ = '\t';
+        p = put_i64(p, e.lstart); *p++ = '\t'; p = put_i64(p, e.lend); *p++ = '\t';
+        p = put_i64(p, EXLR_EV_LSTRAND(e.meta)); *p++ = '\t';
+        memcpy(p, cs[1], cl[1]); p += cl[1]; *p++ = '\t';
+        p = put_i64(p, e.rstart); *p++ = '\t'; p = put_i64(p, e.rend); *p++ = '\t';
+        p = put_i64(p, EXLR_EV_RSTRAND(e.meta)); *p++ = '\t';
+        p = put_i64(p, (int64_t)EXLR_EV_NUM(e.meta));
+        if (verbose) {
+            *p++ = '\t';
+            const char* tag = kTags[kind < 5 ? kind : 4]; size_t tl = strlen(tag);
+            memcpy(p, tag, tl); p += tl; *p++ = '\t';
+            memcpy(p, qnames + qname_off[r], qn); p += qn;
+            memcpy(p, "\tstrand:", 8); p += 8;
+            p = put_i64(p, (b->hv.flag[r] & 0x10) ? -1 : 1);
+            memcpy(p, "\tflag:", 6); p += 6;
+            p = put_i64(p, (int64_t)b->hv.flag[r]);
+        }
+        *p++ = '\n';
+        const size_t n = (size_t)(p - line.data());
+        if (w + n <= out_cap && out) memcpy(out + w, line.data(), n);
+        w += n;
+    }
+    return (int64_t)w;
+}
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+// exlr_device.cuh — device-side data layout shared by the kernels and the host ABI layer.
+//
+// Everything here restates, for the GPU, the per-record loop body of excord-lr
+// (reference src/main.rs:158-770).  See DESIGN.md for the kernel map.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/exlr.h"
+
+namespace exlr {
+
+// ---- device error word -----------------------------------------------------------------
+// key = (read_idx << 8) | rank; the smallest key wins: the smallest read, and for one read the
+// condition the reference would hit first (order of main.rs:198, :243, :311-320, :523-742).
+// Ctrl.err_key stores ~key (0 = no error) so one zeroing memset resets the whole block.
+enum ErrRank : uint32_t {
+    RANK_TID = 1, RANK_CIGAR_OP = 2, RANK_SA_FIELDS = 3, RANK_SA_POS = 4, RANK_SA_STRAND = 5, RANK_SA_CIGAR = 6,
+    RANK_SA_MAPQ = 7, RANK_SA_NM = 8, RANK_MERGE_DOMAIN = 9, RANK_SPLIT_COUNT = 10
+};
+
+// ---- result header / control block (one per batch, zeroed by a memset node per submit) --
+struct Ctrl {
+    unsigned long long err_key;     // ~key of the winning error, 0 if none
+    uint32_t n_raw;                 // raw indel events emitted by kernel 1
+    uint32_t n_saev;                // SA-derived events emitted by kernel 3b
+    uint32_t n_sa;                  // kept records with an SA aux (length of sa_list)
+    uint32_t n_kept;
+    uint32_t n_dropped;             // -k cap drops
+    uint32_t n_events;              // total output lines
+    uint32_t overflow;              // 1 = raw / sa / final event buffer too small
+    uint32_t ticket_a, ticket_b;    // dynamic tile ids of the two chained scans
+    uint32_t seg_pool_used;
+    uint32_t pad[4];
+};
+static_assert(sizeof(Ctrl) == 64, "Ctrl is the 64-byte result header");
+
+// raw indel event, kernel 1 -> kernel 4b (32 bytes, two 16-byte stores)
+struct RawEv {
+    uint32_t rid;       // 0xffffffff = tombstone (record did not pass the filters)
+    uint32_t seq;       // index among the record's indel events, CIGAR order
+    uint32_t L;         // left_consume at the op (main.rs:547-600), u32 wrapping
+    uint32_t n_type;    // len | is_del << 31
+    uint32_t prevL;     // L of the record's previous event (for the pair merge, main.rs:612-635)
+    uint32_t pad[3];
+};
+static_assert(sizeof(RawEv) == 32, "RawEv");
+
+// per-record summary written by kernel 1:  x = total_consume (main.rs:528-545), y = info
+static constexpr uint32_t K1_CNT_MASK = 0x0fffffffu;   // number of indel events of the record
+static constexpr uint32_t K1_PAIR_MERGE = 1u << 30;    // 2nd event merges with the 1st (near-edge rule, main.rs:615)
+static constexpr uint32_t K1_FAR_HIT = 1u << 31;       // some adjacent pair satisfies the far-edge rule (main.rs:673-678)
+
+// per-SA-record summary of the record's own CIGAR (kernel 3a -> 3b), the part of
+// cigar_map / first_cigar_str (main.rs:214-306) the later rules read
+struct SaSum {
+    uint32_t S, H;          // wrapping sums of soft / hard clips (main.rs:347,353,461)
+    int64_t refspan;        // D + M + '=' + X, each wrapped to u32 first (split_read_event.rs:23-28)
+    int64_t ffm;            // find_first_match_pos of the rebuilt CIGAR text (utils.rs:12-42)
+    uint32_t pad[2];
+};
+static_assert(sizeof(SaSum) == 32, "SaSum");
+
+static constexpr uint32_t CSA_DROP = 1u << 31;         // -k cap: record skipped entirely (main.rs:311-313)
+static constexpr uint32_t CSA_CNT_MASK = 0x7fffffffu;
+
+// one alignment of a split read (SplitReadEvent, split_read_event.rs:3-11) as kernel 3b keeps it
+struct Seg {
+    int64_t start, end, key;    // key = find_first_match_pos(raw_cigar)
+    uint32_t chrom_ref;         // tid, or sa byte offset | 1<<31 (already past "chr")
+    uint32_t chrom_len;
+    uint32_t clip_big;          // S > ins_clip_min || H > ins_clip_min
+    uint32_t strand_neg;
+};
+static constexpr int kLocalSegs = 10;                  // segments kept in local memory (-k 8 fits); more -> global pool
+
+// ---- kernel argument block ----------------------------------------------------------------
+struct DevBatch {
+    // inputs
+    const uint32_t* cigar; const unsigned long long* cigar_off;
+    const int32_t* pos; const int32_t* tid; const uint16_t* flag; const uint8_t* mapq; const uint8_t* sa_kind;
+    const uint32_t* sa_off; const uint8_t* sa_bytes;
+    // reference names, "chr" stripped: name i = ref_bytes[ref_off[i] .. ref_off[i+1])
+    const uint8_t* ref_bytes; const uint32_t* ref_off; int32_t n_ref;
+    // scratch
+    uint2* k1;              // [R] {total_consume, info}
+    uint32_t* csa;          // [R] SA-derived line count | CSA_DROP
+    uint32_t* sa_list;      // [R] ordered indices of kept records with an SA aux
+    uint32_t* sa_base;      // [R] first temp slot of the SA record's events (indexed like sa_list)
+    SaSum* sa_sum;          // [R] indexed like sa_list
+    RawEv* raw;             // [max_events]
+    exlr_event* sa_ev;      // [max_events] SA-derived events, per record contiguous
+    Seg* seg_pool; uint32_t seg_pool_cap;
+    unsigned long long* scan_a; unsigned long long* scan_b;   // chained-scan tile status
+    Ctrl* ctrl;
+    // outputs
+    uint32_t* line_off;     // [R+1]
+    exlr_event* events;     // [max_events]
+    uint32_t n_reads; uint32_t max_events;
+};
+
+struct DevParams {
+    uint32_t mapq, exclude_flag, exclude_secondary, exclude_unmapped, split_only;
+    uint32_t indel_min, merge_min, ins_clip_min;
+    double max_pct_overlap;
+    unsigned long long max_supp_alignm;
+};
+
+// launchers (exlr_kernels.cu)
+cudaError_t configure_kernels(int device);
+size_t k1_flat_smem_bytes();
+uint32_t scan_tiles(uint32_t n_reads);
+void launch_k0(const DevBatch& B, const DevParams& P, cudaStream_t st);
+void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc, cudaStream_t st);
+void launch_k3a(const DevBatch& B, const DevParams& P, cudaStream_t st);
+void launch_k3b(const DevBatch& B, const DevParams& P, cudaStream_t st);
+void launch_k4a(const DevBatch& B, const DevParams& P, cudaStream_t st);
+void launch_k4b(const DevBatch& B, const DevParams& P, cudaStream_t st);
+
+}  // namespace exlr

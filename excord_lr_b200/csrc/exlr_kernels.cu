@@ -1,0 +1,875 @@
+// exlr_kernels.cu — hand-written sm_100a kernels for excord-lr's signal-extraction hot path.
+//
+//   kernel 0  k0_classify    record filter (main.rs:169-190) + tid check (:198) + ordered list of
+//                            kept records carrying an SA aux (:206), one chained scan
+//   kernel 1  k1_flat        CIGAR scan (main.rs:523-600): the batch's CIGAR stream is staged
+//                            through shared memory by TMA bulk copies (cp.async.bulk + mbarrier,
+//                            3-stage ring) and scanned flat — one block prefix sum of the
+//                            reference-consuming lengths, record boundaries resolved from the
+//                            staged offsets — so load balance does not depend on CIGAR lengths.
+//             k1_warp        warp-per-record variant (kept for A/B measurement)
+//   kernel 3a k3a_sa_cigar   per-op-type sums + first-match offset of SA records' own CIGARs
+//                            (main.rs:214-306, utils.rs:12-42), 8-lane group per record
+//   kernel 3b k3b_sa_events  SA parse (utils.rs:88-139), -k cap (main.rs:311), stable segment sort
+//                            (main.rs:322), large-INS rules (:340-486), split pairs (:488-516)
+//   kernel 4a k4a_line_scan  pair-merge rule (main.rs:612-635) + far-edge domain check (:673-678)
+//                            folded into the per-record line count, chained scan -> line offsets
+//   kernel 4b k4b_place      ordered compaction: every event lands at its reference output
+//                            position as a 48-byte exlr_event
+//
+// HBM-bound integer/byte work: no tensor cores anywhere on this path.
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "exlr_device.cuh"
+
+namespace exlr {
+
+// ======================================================================================
+// small helpers
+// ======================================================================================
+__device__ __forceinline__ bool keep_record(const DevParams& P, uint32_t flag, uint32_t mapq)
+{
+    if (P.exclude_secondary && (flag & 0x100u)) return false;   // main.rs:169
+    if (P.exclude_unmapped && (flag & 0x4u)) return false;      // main.rs:174
+    if (mapq < P.mapq) return false;                            // main.rs:179
+    if (flag & P.exclude_flag) return false;                    // main.rs:185
+    return true;
+}
+
+// The word holds ~key so that a zeroing memset means "no error" and atomicMax keeps the smallest key.
+__device__ __forceinline__ void report(Ctrl* c, uint32_t read, uint32_t rank)
+{
+    atomicMax(&c->err_key, ~(((unsigned long long)read << 8) | rank));
+}
+
+__device__ __forceinline__ uint32_t abs_diff(uint32_t a, uint32_t b) { return a > b ? a - b : b - a; }
+
+// ops consuming the reference in the indel arm: M(0) D(2) N(3) =(7)   (main.rs:528-545, 586-598)
+__device__ __forceinline__ uint32_t consumes_ref(uint32_t op) { return (0x8Du >> op) & 1u; }
+
+__device__ __forceinline__ void store_event(exlr_event* dst, int64_t ls, int64_t le, int64_t rs, int64_t re,
+                                            uint32_t read, uint32_t lc, uint32_t rc, uint32_t meta)
+{
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    d[0] = make_uint4((uint32_t)ls, (uint32_t)((uint64_t)ls >> 32), (uint32_t)le, (uint32_t)((uint64_t)le >> 32));
+    d[1] = make_uint4((uint32_t)rs, (uint32_t)((uint64_t)rs >> 32), (uint32_t)re, (uint32_t)((uint64_t)re >> 32));
+    d[2] = make_uint4(read, lc, rc, meta);
+}
+
+// ---- chained scan (decoupled look-back), one status word per tile: flag<<62 | value ----
+static constexpr int SCAN_THREADS = 256;
+static constexpr int SCAN_ITEMS = 4;
+static constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+static constexpr unsigned long long ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_VALUE = (1ull << 62) - 1;
+
+// thread 0 only: publish this tile's aggregate, return the sum of all previous tiles
+__device__ __forceinline__ uint32_t chained_prefix(unsigned long long* status, uint32_t tile, uint32_t agg)
+{
+    volatile unsigned long long* st = status;
+    if (tile == 0) { st[0] = ST_PREFIX | agg; return 0; }
+    st[tile] = ST_AGG | agg;
+    uint32_t prefix = 0;
+    for (int i = (int)tile - 1;; --i) {
+        unsigned long long s;
+        do { s = st[i]; } while ((s >> 62) == 0);
+        prefix += (uint32_t)(s & ST_VALUE);
+        if ((s >> 62) == 2) break;
+    }
+    st[tile] = ST_PREFIX | (unsigned long long)(agg + prefix);
+    return prefix;
+}
+
+// block-wide exclusive scan of one value per thread (256 threads); returns exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp /*[8]*/, uint32_t* total)
+{
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_THREADS / 32; i++) { uint32_t x = s_warp[i]; if ((uint32_t)i < w) base += x; tot += x; }
+    *total = tot;
+    return base + incl - v;
+}
+
+// ======================================================================================
+// kernel 0: filter + tid check + ordered SA-record list
+// ======================================================================================
+__global__ void __launch_bounds__(SCAN_THREADS) k0_classify(DevBatch B, DevParams P)
+{
+    __shared__ uint32_t s_tile, s_prefix, s_warp[8];
+    if (threadIdx.x == 0) s_tile = atomicAdd(&B.ctrl->ticket_a, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile, n = B.n_reads;
+    const uint32_t r0 = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t is_sa[SCAN_ITEMS], kept = 0, mine = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        const uint32_t r = r0 + i;
+        is_sa[i] = 0;
+        if (r < n) {
+            const uint32_t flag = B.flag[r], mq = B.mapq[r];
+            if (keep_record(P, flag, mq)) {
+                kept++;
+                const int32_t t = B.tid[r];
+                if (t < 0 || t >= B.n_ref) report(B.ctrl, r, RANK_TID);     // record.contig() panics (main.rs:198)
+                else if (B.sa_kind[r] != EXLR_SA_NONE) { is_sa[i] = 1; mine++; }
+            }
+            B.csa[r] = 0;
+            if (P.split_only) B.k1[r] = make_uint2(0u, 0u);                  // kernel 1 does not run (main.rs:523)
+        }
+    }
+    uint32_t total;
+    uint32_t excl = block_excl_scan(mine, s_warp, &total);
+    if (threadIdx.x == 0) s_prefix = chained_prefix(B.scan_a, tile, total);
+    __syncthreads();
+    uint32_t at = s_prefix + excl;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) if (is_sa[i]) B.sa_list[at++] = r0 + i;
+    // kept counter: one atomic per warp
+    for (int d = 16; d; d >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, d);
+    if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&B.ctrl->n_kept, kept);
+    if (threadIdx.x == 0 && tile == (n + SCAN_TILE - 1) / SCAN_TILE - 1) B.ctrl->n_sa = s_prefix + total;
+}
+
+// ======================================================================================
+// kernel 1 (variant B): warp per record
+// ======================================================================================
+__global__ void __launch_bounds__(256) k1_warp(DevBatch B, DevParams P)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < B.n_reads; r += warps) {
+        const uint32_t flag = B.flag[r], mq = B.mapq[r];
+        if (!keep_record(P, flag, mq)) { if (lane == 0) B.k1[r] = make_uint2(0u, 0u); continue; }
+        const unsigned long long o0 = B.cigar_off[r], o1 = B.cigar_off[r + 1];
+        const uint32_t pos2 = (uint32_t)B.pos[r];
+        uint32_t carry = 0, cnt = 0, info = 0;
+        uint32_t pL = 0, pn = 0, pdel = 0;          // previous event of this record (warp-uniform)
+        for (unsigned long long b = o0; b < o1; b += 32) {
+            const bool valid = b + lane < o1;
+            const uint32_t v = valid ? __ldg(B.cigar + b + lane) : 0u;
+            const uint32_t op = v & 15u, len = v >> 4;
+            if (valid && op > 8u) report(B.ctrl, r, RANK_CIGAR_OP);
+            const uint32_t c = (valid && op <= 8u && consumes_ref(op)) ? len : 0u;
+            uint32_t incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+            const uint32_t L = carry + incl - c;
+            const bool isev = valid && (op == 1u || op == 2u) && len >= P.indel_min;
+            const uint32_t bal = __ballot_sync(0xffffffffu, isev);
+            if (bal) {
+                const uint32_t below = bal & ((1u << lane) - 1u);
+                const uint32_t rank = __popc(below);
+                const int src = below ? 31 - __clz(below) : 0;
+                uint32_t qL = __shfl_sync(0xffffffffu, L, src), qn = __shfl_sync(0xffffffffu, len, src),
+                         qdel = __shfl_sync(0xffffffffu, (uint32_t)(op == 2u), src);
+                bool has_prev = below != 0;
+                if (!has_prev && cnt) { qL = pL; qn = pn; qdel = pdel; has_prev = true; }
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&B.ctrl->n_raw, (uint32_t)__popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                uint32_t myflags = 0;
+                if (isev) {
+                    const uint32_t seq = cnt + rank, del = op == 2u;
+                    if (has_prev && del && qdel) {
+                        if (seq == 1 && abs_diff(pos2 + L, pos2 + qL + qn) < P.merge_min) myflags |= K1_PAIR_MERGE;   // main.rs:615
+                        if (abs_diff(pos2 + qL, pos2 + L + len) < P.merge_min) myflags |= K1_FAR_HIT;                 // main.rs:673-678
+                    }
+                    const uint32_t slot = base + rank;
+                    if (slot < B.max_events) {
+                        uint4* d = reinterpret_cast<uint4*>(B.raw + slot);
+                        d[0] = make_uint4(r, seq, L, len | (del << 31));
+                        d[1] = make_uint4(has_prev ? qL : 0u, 0u, 0u, 0u);
+                    } else B.ctrl->overflow = 1;
+                }
+                for (int d = 16; d; d >>= 1) myflags |= __shfl_xor_sync(0xffffffffu, myflags, d);
+                info |= myflags;
+                const int last = 31 - __clz(bal);
+                pL = __shfl_sync(0xffffffffu, L, last); pn = __shfl_sync(0xffffffffu, len, last);
+                pdel = __shfl_sync(0xffffffffu, (uint32_t)(op == 2u), last);
+                cnt += __popc(bal);
+            }
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) B.k1[r] = make_uint2(carry, (cnt & K1_CNT_MASK) | info);
+    }
+}
+
+// ======================================================================================
+// kernel 1 (default): flat TMA-staged block scan over the CIGAR stream
+// ======================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "EXLR_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra EXLR_DONE;\n"
+                 "bra EXLR_WAIT;\n"
+                 "EXLR_DONE:\n"
+                 "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+static constexpr int K1_THREADS = 256;
+static constexpr int K1_SUB = K1_THREADS * 4;          // ops per scan step (one uint4 per thread)
+static constexpr int K1_SUBS_PER_CHUNK = 4;
+static constexpr int K1_CHUNK = K1_SUB * K1_SUBS_PER_CHUNK;   // ops per TMA bulk copy (16 KB)
+static constexpr int K1_STAGES = 3;
+static constexpr int K1_MAX_RPC = 256;                 // records per CTA (thread t owns record t)
+static constexpr int K1_CAP = K1_THREADS;              // staged events per flush (one per thread)
+
+struct __align__(16) K1Stage { uint32_t fp, pexcl, n_type, pad; };
+
+struct __align__(128) K1Smem {
+    uint32_t buf[K1_STAGES][K1_CHUNK];
+    uint32_t lprefix[2][K1_SUB];
+    K1Stage stage[K1_CAP];
+    uint32_t roff[K1_MAX_RPC + 1];
+    uint32_t pstart[K1_MAX_RPC + 1];
+    uint32_t rcnt[K1_MAX_RPC];
+    uint32_t rflags[K1_MAX_RPC];
+    uint32_t fhead[K1_MAX_RPC];
+    uint32_t rkeep[K1_MAX_RPC];
+    uint2 wtot[2][K1_THREADS / 32];
+    K1Stage carry_ev;
+    uint32_t has_carry, gbase;
+    unsigned long long full[K1_STAGES];
+};
+
+// largest i in [0, nr) with roff[i] <= fp (records are back to back; empty records share a start and the
+// last of them owns the ops)
+__device__ __forceinline__ uint32_t k1_find_read(const uint32_t* roff, uint32_t nr, uint32_t fp)
+{
+    uint32_t lo = 0, hi = nr;               // invariant: roff[lo] <= fp, answer in [lo, hi)
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (roff[mid] <= fp) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// Resolve and write out the `m` staged events (m <= K1_CAP, one per thread).  Block-uniform call.
+__device__ __forceinline__ void k1_flush(K1Smem& S, const DevBatch& B, const DevParams& P, uint32_t ra, uint32_t nr, uint32_t m)
+{
+    const uint32_t t = threadIdx.x;
+    if (t == 0) S.gbase = atomicAdd(&B.ctrl->n_raw, m);
+    __syncthreads();                                    // staging, pstart, gbase visible
+    K1Stage ev; uint32_t i = 0; bool has_prev = false; K1Stage pv;
+    pv.fp = 0; pv.pexcl = 0; pv.n_type = 0; pv.pad = 0; ev = pv;
+    if (t < m) {
+        ev = S.stage[t];
+        i = k1_find_read(S.roff, nr, ev.fp);
+        if (t > 0) { pv = S.stage[t - 1]; has_prev = pv.fp >= S.roff[i]; }
+        else if (S.has_carry) { pv = S.carry_ev; has_prev = pv.fp >= S.roff[i]; }
+        if (t == 0 || S.stage[t - 1].fp < S.roff[i]) S.fhead[i] = t;      // first event of record i in this flush
+    }
+    __syncthreads();
+    uint32_t seq = 0;
+    if (t < m) {
+        seq = S.rcnt[i] + t - S.fhead[i];
+        const uint32_t L = ev.pexcl - S.pstart[i];
+        const uint32_t len = ev.n_type & 0x7fffffffu, del = ev.n_type >> 31;
+        uint32_t prevL = 0;
+        if (has_prev) {
+            prevL = pv.pexcl - S.pstart[i];
+            const uint32_t pn = pv.n_type & 0x7fffffffu, pdel = pv.n_type >> 31;
+            if (del && pdel) {
+                const uint32_t pos2 = (uint32_t)B.pos[ra + i];
+                uint32_t fl = 0;
+                if (seq == 1 && abs_diff(pos2 + L, pos2 + prevL + pn) < P.merge_min) fl |= K1_PAIR_MERGE;   // main.rs:615
+                if (abs_diff(pos2 + prevL, pos2 + L + len) < P.merge_min) fl |= K1_FAR_HIT;                 // main.rs:673-678
+                if (fl) atomicOr(&S.rflags[i], fl);
+            }
+        }
+        const uint32_t slot = S.gbase + t;
+        if (slot < B.max_events) {
+            uint4* d = reinterpret_cast<uint4*>(B.raw + slot);
+            d[0] = make_uint4(S.rkeep[i] ? ra + i : 0xffffffffu, seq, L, ev.n_type);
+            d[1] = make_uint4(prevL, 0u, 0u, 0u);
+        } else B.ctrl->overflow = 1;
+    }
+    __syncthreads();                                    // every seq computed before rcnt moves
+    if (t < m) {
+        const bool tail = (t == m - 1) || (S.stage[t + 1].fp >= S.roff[i + 1]);
+        if (tail) S.rcnt[i] = seq + 1;
+        if (t == m - 1) { S.carry_ev = ev; S.has_carry = 1; }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(K1_THREADS) k1_flat(DevBatch B, DevParams P, uint32_t rpc)
+{
+    extern __shared__ __align__(128) unsigned char k1_smem_raw[];
+    K1Smem& S = *reinterpret_cast<K1Smem*>(k1_smem_raw);
+    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const uint32_t ra = blockIdx.x * rpc;
+    if (ra >= B.n_reads) return;
+    const uint32_t nr = min(rpc, B.n_reads - ra);
+    const unsigned long long oa = B.cigar_off[ra], ob = B.cigar_off[ra + nr];
+    const unsigned long long oa4 = oa & ~3ull;
+    const uint32_t span_lo = (uint32_t)(oa - oa4), span_hi = (uint32_t)(ob - oa4);
+    if (ob - oa4 >= 0x80000000ull) { if (t == 0) B.ctrl->overflow = 1; return; }
+    // per-record state
+    for (uint32_t i = t; i <= nr; i += K1_THREADS) S.roff[i] = (uint32_t)(B.cigar_off[ra + i] - oa4);
+    if (t < nr) {
+        S.rkeep[t] = keep_record(P, B.flag[ra + t], B.mapq[ra + t]) ? 1u : 0u;
+        S.rcnt[t] = 0; S.rflags[t] = 0; S.fhead[t] = 0; S.pstart[t] = 0;
+    }
+    if (t == 0) {
+        S.has_carry = 0;
+        for (int s = 0; s < K1_STAGES; s++) mbar_init(&S.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t nchunks = (span_hi + K1_CHUNK - 1) / K1_CHUNK;
+    const uint32_t* gsrc = B.cigar + oa4;
+    auto issue = [&](uint32_t c) {
+        const uint32_t first = c * K1_CHUNK;
+        uint32_t nops = min((uint32_t)K1_CHUNK, span_hi - first);
+        const uint32_t bytes = ((nops * 4u) + 15u) & ~15u;              // the cigar buffer is padded by 16 bytes
+        unsigned long long* bar = &S.full[c % K1_STAGES];
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(S.buf[c % K1_STAGES], gsrc + first, bytes, bar);
+    };
+    if (t == 0) for (uint32_t c = 0; c < nchunks && c < K1_STAGES; c++) issue(c);
+
+    uint32_t carry = 0, staged = 0, g = 0;
+    for (uint32_t c = 0; c < nchunks; c++) {
+        mbar_wait(&S.full[c % K1_STAGES], (c / K1_STAGES) & 1u);
+        const uint32_t* buf = S.buf[c % K1_STAGES];
+        const uint32_t subs = min((uint32_t)K1_SUBS_PER_CHUNK, (span_hi - c * K1_CHUNK + K1_SUB - 1) / K1_SUB);
+        for (uint32_t s = 0; s < subs; s++, g++) {
+            const uint32_t fb = g * K1_SUB;                              // flat position of this step's first op
+            const uint4 q = reinterpret_cast<const uint4*>(buf)[s * K1_THREADS + t];
+            const uint32_t vv[4] = {q.x, q.y, q.z, q.w};
+            uint32_t e[4], evm = 0, tsum = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t fp = fb + t * 4 + k;
+                const bool valid = fp >= span_lo && fp < span_hi;
+                const uint32_t op = vv[k] & 15u, len = vv[k] >> 4;
+                e[k] = tsum;
+                if (valid) {
+                    if (op > 8u) {                                       // rust-htslib panics on an unknown op
+                        const uint32_t i = k1_find_read(S.roff, nr, fp);
+                        if (S.rkeep[i]) report(B.ctrl, ra + i, RANK_CIGAR_OP);
+                    } else {
+                        if (consumes_ref(op)) tsum += len;
+                        if ((op == 1u || op == 2u) && len >= P.indel_min) evm |= 1u << k;
+                    }
+                }
+            }
+            uint32_t wincl = tsum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, wincl, d); if (lane >= (uint32_t)d) wincl += o; }
+            const uint32_t wexcl = wincl - tsum;
+            // events: rank inside the warp (rare path)
+            const uint32_t nev = __popc(evm);
+            const uint32_t anyev = __ballot_sync(0xffffffffu, nev != 0);
+            uint32_t evincl = 0;
+            if (anyev) {
+                evincl = nev;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, evincl, d); if (lane >= (uint32_t)d) evincl += o; }
+            }
+            reinterpret_cast<uint4*>(S.lprefix[g & 1])[t] = make_uint4(wexcl + e[0], wexcl + e[1], wexcl + e[2], wexcl + e[3]);
+            if (lane == 31) S.wtot[g & 1][w] = make_uint2(wincl, evincl);
+            __syncthreads();
+            if (t == 0 && s + 1 == subs && c + K1_STAGES < nchunks) issue(c + K1_STAGES);   // stage c is drained
+            uint32_t wbase = 0, total = 0, evbase = 0, evtotal = 0;
+#pragma unroll
+            for (int k = 0; k < K1_THREADS / 32; k++) {
+                const uint2 x = S.wtot[g & 1][k];
+                if ((uint32_t)k < w) { wbase += x.x; evbase += x.y; }
+                total += x.x; evtotal += x.y;
+            }
+            // record starts inside this step: prefix value at the record's first op
+            if (t < nr) {
+                const uint32_t ro = S.roff[t];
+                if (ro >= fb && ro < fb + K1_SUB && ro < span_hi) {
+                    const uint32_t rel = ro - fb, wp = rel >> 7;
+                    uint32_t b2 = 0;
+                    for (uint32_t k = 0; k < wp; k++) b2 += S.wtot[g & 1][k].x;
+                    S.pstart[t] = carry + b2 + S.lprefix[g & 1][rel];
+                }
+            }
+            if (evtotal) {                                               // block-uniform
+                if (staged + evtotal > K1_CAP && staged) { k1_flush(S, B, P, ra, nr, staged); staged = 0; }
+                const uint32_t my0 = evbase + evincl - nev;              // rank of my first event in this step
+                for (uint32_t round0 = 0; round0 < evtotal; round0 += K1_CAP) {
+                    uint32_t rk = my0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (evm & (1u << k)) {
+                            if (rk >= round0 && rk < round0 + K1_CAP) {
+                                K1Stage x;
+                                x.fp = fb + t * 4 + k;
+                                x.pexcl = carry + wbase + wexcl + e[k];
+                                x.n_type = (vv[k] >> 4) | (((vv[k] & 15u) == 2u) ? 0x80000000u : 0u);
+                                x.pad = 0;
+                                S.stage[staged + rk - round0] = x;
+                            }
+                            rk++;
+                        }
+                    }
+                    const uint32_t nround = min((uint32_t)K1_CAP, evtotal - round0);
+                    if (evtotal > K1_CAP) { k1_flush(S, B, P, ra, nr, staged + nround); staged = 0; }
+                    else staged += nround;
+                }
+            }
+            carry += total;
+        }
+    }
+    if (staged) k1_flush(S, B, P, ra, nr, staged);
+    __syncthreads();
+    for (uint32_t i = t; i <= nr; i += K1_THREADS) if (S.roff[i] >= span_hi) S.pstart[i] = carry;   // trailing empty records + sentinel
+    __syncthreads();
+    if (t < nr) {
+        const uint32_t T = S.pstart[t + 1] - S.pstart[t];
+        const uint32_t info = S.rkeep[t] ? ((S.rcnt[t] & K1_CNT_MASK) | S.rflags[t]) : 0u;
+        B.k1[ra + t] = make_uint2(T, info);
+    }
+}
+
+// ======================================================================================
+// kernel 3a: SA records' own CIGAR -> clip sums, reference span, first-match offset
+// ======================================================================================
+__global__ void __launch_bounds__(256) k3a_sa_cigar(DevBatch B, DevParams P)
+{
+    const uint32_t n_sa = B.ctrl->n_sa;
+    const uint32_t sub = threadIdx.x & 7, grp_in_warp = (threadIdx.x & 31) >> 3;
+    const uint32_t gmask = 0xffu << (grp_in_warp * 8);
+    const uint32_t groups = (gridDim.x * blockDim.x) >> 3;
+    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; j < n_sa; j += groups) {
+        const uint32_t r = B.sa_list[j];
+        const unsigned long long o0 = B.cigar_off[r], o1 = B.cigar_off[r + 1];
+        uint32_t sS = 0, sH = 0, sD = 0, sM = 0, sE = 0, sX = 0;
+        unsigned long long ffm = 0; bool seenM = false;
+        for (unsigned long long b = o0; b < o1; b += 8) {
+            const bool valid = b + sub < o1;
+            const uint32_t v = valid ? __ldg(B.cigar + b + sub) : 0xfu;      // 0xf: not an op
+            const uint32_t op = v & 15u, len = v >> 4;
+            if (valid && op > 8u) report(B.ctrl, r, RANK_CIGAR_OP);
+            sM += op == 0u ? len : 0u; sD += op == 2u ? len : 0u; sS += op == 4u ? len : 0u;
+            sH += op == 5u ? len : 0u; sE += op == 7u ? len : 0u; sX += op == 8u ? len : 0u;
+            const uint32_t mb = (__ballot_sync(gmask, valid && op == 0u) >> (grp_in_warp * 8)) & 0xffu;
+            if (!seenM) {                                                      // utils.rs:28-29 stops at the first M
+                const bool before = (mb & ((1u << sub) - 1u)) == 0u && !(mb & (1u << sub));
+                if (valid && before && (op == 4u || op == 1u || op == 8u || op == 7u)) ffm += len;   // S I X =  (utils.rs:33)
+                if (mb) seenM = true;
+            }
+        }
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            sS += __shfl_xor_sync(gmask, sS, d); sH += __shfl_xor_sync(gmask, sH, d); sD += __shfl_xor_sync(gmask, sD, d);
+            sM += __shfl_xor_sync(gmask, sM, d); sE += __shfl_xor_sync(gmask, sE, d); sX += __shfl_xor_sync(gmask, sX, d);
+            ffm += __shfl_xor_sync(gmask, ffm, d);
+        }
+        if (sub == 0) {
+            SaSum o;
+            o.S = sS; o.H = sH;
+            o.refspan = (int64_t)sD + (int64_t)sM + (int64_t)sE + (int64_t)sX;
+            o.ffm = (int64_t)ffm; o.pad[0] = o.pad[1] = 0;
+            B.sa_sum[j] = o;
+        }
+    }
+}
+
+// ======================================================================================
+// kernel 3b: SA parse, cap, sort, large-INS rules, split pairs
+// ======================================================================================
+__device__ __forceinline__ bool dev_parse_i64(const uint8_t* s, uint32_t b, uint32_t e, int64_t* out)
+{
+    if (b == e) return false;
+    bool neg = false;
+    if (s[b] == '+' || s[b] == '-') { neg = s[b] == '-'; b++; }
+    if (b == e) return false;
+    const unsigned long long lim = neg ? (1ull << 63) : (1ull << 63) - 1;
+    unsigned long long v = 0;
+    for (; b < e; b++) {
+        const uint32_t d = (uint32_t)s[b] - '0';
+        if (d > 9u) return false;
+        if (v > (lim - d) / 10ull) return false;
+        v = v * 10ull + d;
+    }
+    *out = neg ? (int64_t)(0ull - v) : (int64_t)v;
+    return true;
+}
+
+__device__ __forceinline__ bool dev_parse_u8(const uint8_t* s, uint32_t b, uint32_t e)
+{
+    if (b == e) return false;
+    if (s[b] == '+') b++;
+    if (b == e) return false;
+    uint32_t v = 0;
+    for (; b < e; b++) {
+        const uint32_t d = (uint32_t)s[b] - '0';
+        if (d > 9u) return false;
+        v = v * 10u + d;
+        if (v > 255u) return false;
+    }
+    return true;
+}
+
+// parse_supplementary_alignment + parse_cigar + find_first_match_pos (utils.rs:12-42, 88-139)
+__device__ uint32_t dev_parse_piece(const uint8_t* s, uint32_t b, uint32_t e, const DevParams& P, Seg* out)
+{
+    uint32_t fb[6], fe[6], nf = 0, st = b;
+    for (uint32_t i = b; i <= e; i++) {
+        if (i == e || s[i] == ',') {
+            if (nf < 6) { fb[nf] = st; fe[nf] = i; }
+            nf++; st = i + 1;
+        }
+    }
+    if (nf < 6) return RANK_SA_FIELDS;
+    int64_t pos;
+    if (!dev_parse_i64(s, fb[1], fe[1], &pos)) return RANK_SA_POS;
+    if (fe[2] - fb[2] != 1 || (s[fb[2]] != '+' && s[fb[2]] != '-')) return RANK_SA_STRAND;
+    const uint32_t strand_neg = s[fb[2]] == '-';
+    uint32_t sS = 0, sH = 0, sD = 0, sM = 0, sE = 0, sX = 0, ndig = 0;
+    unsigned long long v = 0, key = 0; bool seenM = false;
+    for (uint32_t i = fb[3]; i < fe[3]; i++) {
+        const uint32_t c = s[i], d = c - '0';
+        if (d <= 9u) { v = v * 10ull + d; if (v > 0x1ffffffffull) v = 0x1ffffffffull; ndig++; continue; }
+        const bool isop = c == 'M' || c == 'I' || c == 'D' || c == 'N' || c == 'S' || c == 'H' || c == 'P' || c == '=' || c == 'X';
+        if (!isop || ndig == 0 || v > 0xffffffffull) return RANK_SA_CIGAR;
+        const uint32_t n = (uint32_t)v;
+        if (c == 'S') sS += n; else if (c == 'H') sH += n; else if (c == 'D') sD += n;
+        else if (c == 'M') sM += n; else if (c == '=') sE += n; else if (c == 'X') sX += n;
+        if (!seenM) { if (c == 'M') seenM = true; else if (c == 'S' || c == 'I' || c == 'X' || c == '=') key += n; }
+        v = 0; ndig = 0;
+    }
+    if (!dev_parse_u8(s, fb[4], fe[4])) return RANK_SA_MAPQ;
+    int64_t nm;
+    if (!dev_parse_i64(s, fb[5], fe[5], &nm)) return RANK_SA_NM;
+    uint32_t cb = fb[0], ce = fe[0];
+    if (ce - cb >= 3 && s[cb] == 'c' && s[cb + 1] == 'h' && s[cb + 2] == 'r') cb += 3;
+    out->chrom_ref = 0x80000000u | cb;
+    out->chrom_len = ce - cb;
+    out->start = (int64_t)((unsigned long long)pos - 1ull);
+    out->end = out->start + (int64_t)sD + (int64_t)sM + (int64_t)sE + (int64_t)sX;
+    out->key = (int64_t)key;
+    out->clip_big = (sS > P.ins_clip_min || sH > P.ins_clip_min) ? 1u : 0u;
+    out->strand_neg = strand_neg;
+    return 0;
+}
+
+__device__ __forceinline__ const uint8_t* seg_chrom(const DevBatch& B, const Seg& s)
+{
+    return (s.chrom_ref >> 31) ? B.sa_bytes + (s.chrom_ref & 0x7fffffffu) : B.ref_bytes + B.ref_off[s.chrom_ref];
+}
+
+__device__ __forceinline__ int dev_bytes_cmp(const uint8_t* a, uint32_t an, const uint8_t* b, uint32_t bn)
+{
+    const uint32_t m = an < bn ? an : bn;
+    for (uint32_t i = 0; i < m; i++) { if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1; }
+    return an < bn ? -1 : (an > bn ? 1 : 0);
+}
+
+// overlap (utils.rs:158-194); IEEE f64 divide and compare, like the Rust
+__device__ __forceinline__ bool dev_overlap(int64_t as, int64_t ae, int64_t bs, int64_t be, double p)
+{
+    if (ae < bs || as > be) return false;
+    const int64_t la = ae - as, lb = be - bs;
+    const int64_t ml = la < lb ? la : lb;
+    int64_t num;
+    if (as < bs) num = ae < be ? ae - bs : be - bs;
+    else         num = be < ae ? be - as : ae - as;
+    const double ov = __ddiv_rn((double)num, (double)ml);
+    return ov > p;
+}
+
+__global__ void __launch_bounds__(128) k3b_sa_events(DevBatch B, DevParams P)
+{
+    const uint32_t n_sa = B.ctrl->n_sa;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t n_iter = (n_sa + stride - 1) / stride;
+    Seg local_segs[kLocalSegs];
+    for (uint32_t it = 0; it < n_iter; it++) {
+        const uint32_t j = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool active = j < n_sa;
+        uint32_t r = 0, nseg = 0, n_ins = 0, ins_kind = 0, err = 0;
+        bool dropped = false;
+        Seg* segs = local_segs;
+        int64_t q1 = 0, q2 = 0, q0 = 0;
+        if (active) {
+            r = B.sa_list[j];
+            const SaSum sum = B.sa_sum[j];
+            const uint32_t flag = B.flag[r];
+            const int32_t tid = B.tid[r];
+            const uint8_t* s = B.sa_bytes;
+            const uint32_t b0 = B.sa_off[r], e0 = B.sa_off[r + 1];
+            const bool is_str = B.sa_kind[r] == EXLR_SA_STRING;
+            unsigned long long pieces = 1;
+            if (is_str) {
+                for (uint32_t i = b0; i < e0; i++) pieces += s[i] == ';';
+                if (pieces > P.max_supp_alignm) dropped = true;             // main.rs:311-313: the whole record is skipped
+            }
+            if (!dropped) {
+                if (is_str && pieces + 1 > (unsigned long long)kLocalSegs) {
+                    const uint32_t need = (uint32_t)pieces + 1;
+                    const uint32_t at = atomicAdd(&B.ctrl->seg_pool_used, need);
+                    if ((unsigned long long)at + need <= B.seg_pool_cap) segs = B.seg_pool + at;
+                    else { B.ctrl->overflow = 1; dropped = true; }
+                }
+            }
+            if (!dropped) {
+                Seg& a0 = segs[0];                                            // the record itself (main.rs:299-306)
+                a0.chrom_ref = (uint32_t)tid; a0.chrom_len = B.ref_off[tid + 1] - B.ref_off[tid];
+                a0.start = (int64_t)B.pos[r]; a0.end = a0.start + sum.refspan; a0.key = sum.ffm;
+                a0.clip_big = (sum.S > P.ins_clip_min || sum.H > P.ins_clip_min) ? 1u : 0u;
+                a0.strand_neg = (flag & 0x10u) ? 1u : 0u;
+                nseg = 1;
+                if (is_str) {
+                    uint32_t pb = b0;
+                    for (uint32_t i = b0; i <= e0 && !err; i++) {
+                        if (i == e0 || s[i] == ';') {
+                            if (i > pb) {                                     // filter(|x| x.len() > 0), main.rs:315
+                                err = dev_parse_piece(s, pb, i, P, &segs[nseg]);
+                                if (!err) nseg++;
+                            }
+                            pb = i + 1;
+                        }
+                    }
+                }
+                if (!err && nseg - 1 >= (1u << 24)) err = RANK_SPLIT_COUNT;
+                if (err) { report(B.ctrl, r, err); nseg = 0; }
+                else {
+                    for (uint32_t i = 1; i < nseg; i++) {                     // stable insertion sort by key (main.rs:322)
+                        const Seg x = segs[i]; uint32_t k = i;
+                        while (k > 0 && segs[k - 1].key > x.key) { segs[k] = segs[k - 1]; k--; }
+                        segs[k] = x;
+                    }
+                    if (nseg == 2) {                                          // main.rs:340-451
+                        const Seg& a = segs[0]; const Seg& b = segs[1];
+                        if (a.clip_big) {
+                            const bool same = dev_bytes_cmp(seg_chrom(B, a), a.chrom_len, seg_chrom(B, b), b.chrom_len) == 0;
+                            if (same) {
+                                if (a.strand_neg == b.strand_neg && dev_overlap(a.start, a.end, b.start, b.end, P.max_pct_overlap) && b.clip_big) {
+                                    int64_t q[4] = {a.start, a.end, b.start, b.end};
+#pragma unroll
+                                    for (int x = 1; x < 4; x++) { const int64_t val = q[x]; int y = x; while (y > 0 && q[y - 1] > val) { q[y] = q[y - 1]; y--; } q[y] = val; }
+                                    q0 = q[0]; q1 = q[1]; q2 = q[2];
+                                    n_ins = 2; ins_kind = EXLR_KIND_INS_TWO_ALN;
+                                }
+                            } else { n_ins = 1; ins_kind = EXLR_KIND_INS_ONE_ALN; }
+                        }
+                    } else if (nseg == 1) {                                   // main.rs:459-486
+                        if (segs[0].clip_big) { n_ins = 1; ins_kind = EXLR_KIND_INS_ONE_SEG; }
+                    }
+                }
+            }
+        }
+        // temp slots: one atomic per warp
+        const uint32_t cnt = (active && nseg) ? n_ins + nseg - 1 : 0u;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+        uint32_t base = 0;
+        const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 31 && wtotal) base = atomicAdd(&B.ctrl->n_saev, wtotal);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+        // dropped-by-cap counter
+        const uint32_t dm = __ballot_sync(0xffffffffu, active && dropped);
+        if (lane == 0 && dm) atomicAdd(&B.ctrl->n_dropped, (uint32_t)__popc(dm));
+        if (!active) continue;
+        B.sa_base[j] = base;
+        B.csa[r] = dropped ? CSA_DROP : cnt;
+        if (!cnt) continue;
+        if ((unsigned long long)base + cnt > B.max_events) { B.ctrl->overflow = 1; continue; }
+        exlr_event* dst = B.sa_ev + base;
+        if (n_ins == 2) {
+            const Seg& a = segs[0]; const Seg& b = segs[1];
+            const uint32_t meta = EXLR_EV_META(1u, EXLR_KIND_INS_TWO_ALN, a.strand_neg, b.strand_neg);
+            store_event(dst++, (int64_t)(uint32_t)q0, (int64_t)(uint32_t)q1, (int64_t)(uint32_t)q1, (int64_t)(uint32_t)q1, r, a.chrom_ref, b.chrom_ref, meta);
+            store_event(dst++, (int64_t)(uint32_t)q0, (int64_t)(uint32_t)q2, (int64_t)(uint32_t)q2, (int64_t)(uint32_t)q2, r, a.chrom_ref, b.chrom_ref, meta);
+        } else if (n_ins == 1) {
+            const Seg& a = segs[0];
+            const uint32_t meta = EXLR_EV_META(1u, ins_kind, a.strand_neg, a.strand_neg);
+            store_event(dst++, (int64_t)(uint32_t)a.start, (int64_t)(uint32_t)a.end, (int64_t)(uint32_t)a.end, (int64_t)(uint32_t)a.end, r, a.chrom_ref, a.chrom_ref, meta);
+        }
+        for (uint32_t i = 1; i < nseg; i++) {                                 // main.rs:488-516
+            const Seg* a = &segs[i - 1]; const Seg* b = &segs[i];
+            int c = dev_bytes_cmp(seg_chrom(B, *a), a->chrom_len, seg_chrom(B, *b), b->chrom_len);   // alignment_pos_cmp, utils.rs:75-86
+            if (c == 0) c = a->start < b->start ? -1 : (a->start > b->start ? 1 : 0);
+            if (c > 0) { const Seg* x = a; a = b; b = x; }
+            store_event(dst++, a->start, a->end, b->start, b->end, r, a->chrom_ref, b->chrom_ref,
+                        EXLR_EV_META(nseg - 1, EXLR_KIND_SPLIT, a->strand_neg, b->strand_neg));
+        }
+    }
+}
+
+// ======================================================================================
+// kernel 4a: per-record line count (with the pair merge) -> chained scan -> line offsets
+// ======================================================================================
+__device__ __forceinline__ uint32_t indel_lines(uint32_t info)
+{
+    const uint32_t cnt = info & K1_CNT_MASK;
+    return (cnt == 2u && (info & K1_PAIR_MERGE)) ? 1u : cnt;                  // main.rs:612-635
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k4a_line_scan(DevBatch B, DevParams P)
+{
+    __shared__ uint32_t s_tile, s_prefix, s_warp[8];
+    if (threadIdx.x == 0) s_tile = atomicAdd(&B.ctrl->ticket_b, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile, n = B.n_reads;
+    const uint32_t r0 = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t c[SCAN_ITEMS], mine = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        const uint32_t r = r0 + i;
+        c[i] = 0;
+        if (r < n) {
+            const uint32_t csa = B.csa[r];
+            if (!(csa & CSA_DROP)) {
+                const uint32_t info = B.k1[r].y;
+                if ((info & K1_CNT_MASK) > 2u && (info & K1_FAR_HIT)) report(B.ctrl, r, RANK_MERGE_DOMAIN);
+                c[i] = (csa & CSA_CNT_MASK) + indel_lines(info);
+            }
+            mine += c[i];
+        }
+    }
+    uint32_t total;
+    uint32_t excl = block_excl_scan(mine, s_warp, &total);
+    if (threadIdx.x == 0) s_prefix = chained_prefix(B.scan_b, tile, total);
+    __syncthreads();
+    uint32_t at = s_prefix + excl;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) { if (r0 + i < n) B.line_off[r0 + i] = at; at += c[i]; }
+    if (threadIdx.x == 0 && tile == (n + SCAN_TILE - 1) / SCAN_TILE - 1) {
+        const uint32_t all = s_prefix + total;
+        B.line_off[n] = all;
+        B.ctrl->n_events = all;
+        if (all > B.max_events) B.ctrl->overflow = 1;
+    }
+}
+
+// ======================================================================================
+// kernel 4b: ordered compaction into the output event buffer
+// ======================================================================================
+__global__ void __launch_bounds__(256) k4b_place(DevBatch B, DevParams P)
+{
+    const uint32_t n_raw = min(B.ctrl->n_raw, B.max_events), n_sa = B.ctrl->n_sa;
+    const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    // indel events (AlignmentEvent::new, aligments_event.rs:28-57; merge main.rs:612-635)
+    for (uint32_t x = t0; x < n_raw; x += stride) {
+        const uint4 a = reinterpret_cast<const uint4*>(B.raw + x)[0];
+        const uint32_t r = a.x;
+        if (r == 0xffffffffu) continue;
+        const uint32_t csa = B.csa[r];
+        if (csa & CSA_DROP) continue;
+        const uint2 k1 = B.k1[r];
+        const uint32_t cnt = k1.y & K1_CNT_MASK;
+        const bool merged = cnt == 2u && (k1.y & K1_PAIR_MERGE);
+        uint32_t seq = a.y;
+        const uint32_t L = a.z, len = a.w & 0x7fffffffu, del = a.w >> 31;
+        const uint32_t pos2 = (uint32_t)B.pos[r];
+        uint32_t ls = pos2, le, rs, re;
+        if (merged) {
+            if (seq == 0) continue;
+            const uint32_t prevL = reinterpret_cast<const uint4*>(B.raw + x)[1].x;
+            le = pos2 + prevL; rs = pos2 + L + len; re = pos2 + k1.x; seq = 0;
+        } else if (del) { le = pos2 + L; rs = pos2 + L + len; re = pos2 + k1.x; }      // rend = pos + total_consume
+        else { le = pos2 + L; rs = pos2 + L; re = pos2 + L + len; }                    // Ins: length on the right (main.rs:570-577)
+        const uint32_t dst = B.line_off[r] + (csa & CSA_CNT_MASK) + seq;
+        if (dst >= B.max_events) continue;
+        const uint32_t neg = (B.flag[r] >> 4) & 1u, tid = (uint32_t)B.tid[r];
+        store_event(B.events + dst, (int64_t)ls, (int64_t)le, (int64_t)rs, (int64_t)re, r, tid, tid,
+                    EXLR_EV_META(1u, EXLR_KIND_INDEL, neg, neg));
+    }
+    // SA-derived events: per record contiguous in the temp buffer, they lead the record's lines
+    for (uint32_t j = t0; j < n_sa; j += stride) {
+        const uint32_t r = B.sa_list[j];
+        const uint32_t csa = B.csa[r];
+        if (csa & CSA_DROP) continue;
+        const uint32_t cnt = csa & CSA_CNT_MASK, base = B.sa_base[j], dst = B.line_off[r];
+        if ((unsigned long long)dst + cnt > B.max_events || (unsigned long long)base + cnt > B.max_events) continue;
+        const uint4* src = reinterpret_cast<const uint4*>(B.sa_ev + base);
+        uint4* d = reinterpret_cast<uint4*>(B.events + dst);
+        for (uint32_t k = 0; k < cnt * 3; k++) d[k] = src[k];
+    }
+}
+
+// ======================================================================================
+// launchers (called by the host ABI layer)
+// ======================================================================================
+static int g_sm_count = 148;
+
+size_t k1_flat_smem_bytes() { return sizeof(K1Smem); }
+
+cudaError_t configure_kernels(int device)
+{
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return e;
+    g_sm_count = prop.multiProcessorCount;
+    return cudaFuncSetAttribute(k1_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
+}
+
+void launch_k0(const DevBatch& B, const DevParams& P, cudaStream_t st)
+{
+    const uint32_t tiles = (B.n_reads + SCAN_TILE - 1) / SCAN_TILE;
+    k0_classify<<<tiles, SCAN_THREADS, 0, st>>>(B, P);
+}
+
+void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc, cudaStream_t st)
+{
+    if (variant == 1) {
+        const uint32_t blocks = min((B.n_reads + 7u) / 8u, (uint32_t)g_sm_count * 32u);
+        k1_warp<<<blocks, 256, 0, st>>>(B, P);
+    } else {
+        if (rpc < 1) rpc = 1;
+        if (rpc > K1_MAX_RPC) rpc = K1_MAX_RPC;
+        const uint32_t blocks = (B.n_reads + rpc - 1) / rpc;
+        k1_flat<<<blocks, K1_THREADS, sizeof(K1Smem), st>>>(B, P, rpc);
+    }
+}
+
+void launch_k3a(const DevBatch& B, const DevParams& P, cudaStream_t st)
+{
+    // grid-stride over a device-side count: size for the worst case, cap at a few waves
+    const uint32_t ga = min((B.n_reads + 31u) / 32u, (uint32_t)g_sm_count * 16u);
+    k3a_sa_cigar<<<ga ? ga : 1u, 256, 0, st>>>(B, P);
+}
+
+void launch_k3b(const DevBatch& B, const DevParams& P, cudaStream_t st)
+{
+    const uint32_t gb = min((B.n_reads + 127u) / 128u, (uint32_t)g_sm_count * 16u);
+    k3b_sa_events<<<gb ? gb : 1u, 128, 0, st>>>(B, P);
+}
+
+void launch_k4a(const DevBatch& B, const DevParams& P, cudaStream_t st)
+{
+    const uint32_t tiles = (B.n_reads + SCAN_TILE - 1) / SCAN_TILE;
+    k4a_line_scan<<<tiles, SCAN_THREADS, 0, st>>>(B, P);
+}
+
+void launch_k4b(const DevBatch& B, const DevParams& P, cudaStream_t st)
+{
+    const uint32_t g = min((B.max_events + 255u) / 256u, (uint32_t)g_sm_count * 8u);
+    k4b_place<<<g ? g : 1u, 256, 0, st>>>(B, P);
+}
+
+uint32_t scan_tiles(uint32_t n_reads) { return (n_reads + SCAN_TILE - 1) / SCAN_TILE; }
+
+}  // namespace exlr

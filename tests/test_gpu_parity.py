@@ -1,0 +1,211 @@
+"""Parity of the CUDA path (through the C ABI, host buffers in/out) with the CPU oracle.  Bit-exact:
+every exlr_event field, every line offset, every formatted byte."""
+import numpy as np
+import pytest
+
+import oracle_c
+from excord_lr_b200 import api, synth
+from excord_lr_b200.batch import SA_OTHER, ExlrParams, HostBatch, pack_records
+from gpu_helpers import check_result, gpu_available, gpu_check
+from helpers import py_run
+from ka_vectors import KA, REF_NAMES
+from randrec import clustered_dels, rand_batch, rand_params, REF_NAMES as RREF
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not gpu_available(), reason="needs a B200")]
+
+VARIANTS = [(0, 0), (0, 1), (0, 3), (0, 64), (0, 256), (1, 0)]       # (cigar kernel, records per CTA)
+
+
+@pytest.mark.parametrize("ka", KA, ids=[k[0] for k in KA])
+def test_known_answers(ka):
+    _, over, rec, want = ka
+    hb = pack_records([rec], REF_NAMES)
+    for ck, rpc in ((0, 0), (1, 0)):
+        _, res = gpu_check(hb, ExlrParams.make(**over), ck, rpc, label=f"{ka[0]} k{ck}")
+        assert res.n_events == len(want)
+    res, text = api.extract(hb, ExlrParams.make(**over))
+    assert text.decode() == "".join(w + "\n" for w in want)
+
+
+def test_known_answers_one_batch_verbose():
+    sel = [k for k in KA if not k[1]]
+    hb = pack_records([dict(k[2], qname="read%d" % i) for i, k in enumerate(sel)], REF_NAMES)
+    for ck, rpc in VARIANTS:
+        gpu_check(hb, ExlrParams.make(), ck, rpc, verbose=True, label=f"KA-all k{ck} rpc{rpc}")
+    text, err = py_run(hb, ExlrParams.make(), verbose=True)
+    res, got = api.extract(hb, ExlrParams.make(), verbose=True)
+    assert err is None and got.decode() == text
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_random_default_params(seed):
+    hb = rand_batch(seed, 300, qnames=True)
+    ck, rpc = VARIANTS[seed % len(VARIANTS)]
+    gpu_check(hb, ExlrParams.make(), ck, rpc, verbose=(seed % 4 == 0), label=f"seed{seed} k{ck} rpc{rpc}")
+
+
+@pytest.mark.parametrize("seed", range(60, 160))
+def test_random_params(seed):
+    hb = rand_batch(seed, 300)
+    ck, rpc = VARIANTS[seed % len(VARIANTS)]
+    gpu_check(hb, rand_params(seed), ck, rpc, label=f"seed{seed} k{ck} rpc{rpc}")
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_dense_events_and_merge_rules(variant):
+    # -i 1: every small indel is an event (thousands per CTA: exercises the staged-flush rounds), merge rules at all gaps
+    import random
+    rng = random.Random(77)
+    recs = []
+    for i in range(400):
+        n = rng.choice([2, 2, 3, 5, 40, 300, 3000])
+        recs.append(dict(tid=rng.randrange(len(RREF)), pos=rng.randint(0, 10 ** 8), flag=rng.choice([0, 16]), mapq=60,
+                         cigar=clustered_dels(rng, n, rng.choice([0, 1, 4, 5, 6, 30]), min_len=rng.choice([1, 50]))))
+    hb = pack_records(recs, RREF)
+    for p in (ExlrParams.make(indel_min=1, merge_min=5), ExlrParams.make(indel_min=50, merge_min=5),
+              ExlrParams.make(indel_min=1, merge_min=0), ExlrParams.make(indel_min=50, merge_min=100)):
+        gpu_check(hb, p, *variant, label=f"dense i{p.indel_min} m{p.merge_min} {variant}")
+
+
+def test_empty_and_degenerate_batches():
+    p = ExlrParams.make()
+    # zero records
+    ex = api.Extractor(p, RREF)
+    b = ex.alloc_batch(16, 16, 16)
+    b.n_reads = 0
+    b.submit(0)
+    res = b.wait()
+    assert res.status == 0 and res.n_events == 0 and res.line_off.tolist() == [0]
+    b.free(); ex.close()
+    # records without CIGAR, all filtered, single op, empty SA string, non-string SA
+    recs = [dict(tid=0, pos=5, flag=0, mapq=60, cigar=[]), dict(tid=0, pos=5, flag=4, mapq=0, cigar=[]),
+            dict(tid=1, pos=7, flag=0, mapq=60, cigar="60D"), dict(tid=1, pos=7, flag=0, mapq=60, cigar="60I"),
+            dict(tid=2, pos=9, flag=16, mapq=60, cigar="2000S10M", sa=""),
+            dict(tid=2, pos=9, flag=16, mapq=60, cigar="2000H10M", sa="", sa_kind=SA_OTHER),
+            dict(tid=3, pos=1, flag=0, mapq=60, cigar=[], sa="chr1,5,+,10M,3,0;"),
+            dict(tid=0, pos=2 ** 31 - 1, flag=0, mapq=60, cigar="268435455M268435455D268435455M60D5M")]
+    for k in range(1, len(recs) + 1):
+        hb = pack_records(recs[:k], RREF)
+        for ck, rpc in VARIANTS:
+            gpu_check(hb, p, ck, rpc, label=f"degenerate n={k} k{ck} rpc{rpc}")
+    gpu_check(pack_records(recs, RREF), ExlrParams.make(max_supp_alignm=0, ins_clip_min=0), label="degenerate k0")
+
+
+ERR_CASES = [
+    ("tid", dict(tid=-1, pos=5, flag=0, mapq=60, cigar="10M"), -10),
+    ("tid_hi", dict(tid=len(RREF), pos=5, flag=0, mapq=60, cigar="10M"), -10),
+    ("cigar_op", dict(tid=0, pos=5, flag=0, mapq=60, cigar=[(10 << 4) | 0, (5 << 4) | 9]), -11),
+    ("cigar_op_sa", dict(tid=0, pos=5, flag=0, mapq=60, cigar=[(10 << 4) | 12], sa="chr1,5,+,10M,3,0;"), -11),
+    ("sa_fields", dict(tid=0, pos=5, flag=0, mapq=60, cigar="10M", sa="chr1,5,+,10M,3;"), -12),
+    ("sa_pos", dict(tid=0, pos=5, flag=0, mapq=60, cigar="10M", sa="chr1,5x,+,10M,3,0;"), -13),
+    ("sa_pos_empty", dict(tid=0, pos=5, flag=0, mapq=60, cigar="10M", sa="chr1,,+,10M,3,0;"), -13),
+    ("sa_pos_ovf", dict(tid=0, pos=5, flag=0, mapq=60, cigar="10M", sa="chr1,9223372036854775808,+,10M,3,0;"), -13),
+    ("sa_strand", dict(tid=0, pos=5, flag=0, mapq=60, cigar="10M", sa="chr1,5,*,10M,3,0;"), -14),
+    ("sa_cigar_star", dict(tid=0, pos=5, flag=0, mapq=60, cigar="10M", sa="chr1,5,+,*,3,0;"), -15),
+    ("sa_cigar_empty_num", dict(tid=0, pos=5, flag=0, mapq=60, cigar="10M", sa="chr1,5,+,10MS,3,0;"), -15),
+    ("sa_cigar_ovf", dict(tid=0, pos=5, flag=0, mapq=60, cigar="10M", sa="chr1,5,+,4294967296M,3,0;"), -15),
+    ("sa_mapq", dict(tid=0, pos=5, flag=0, mapq=60, cigar="10M", sa="chr1,5,+,10M,256,0;"), -16),
+    ("sa_mapq_neg", dict(tid=0, pos=5, flag=0, mapq=60, cigar="10M", sa="chr1,5,+,10M,-0,0;"), -16),
+    ("sa_nm", dict(tid=0, pos=5, flag=0, mapq=60, cigar="10M", sa="chr1,5,+,10M,3,;"), -17),
+    ("merge_domain", dict(tid=0, pos=5, flag=0, mapq=60, cigar="10M60D2M60D2M60D10M"), -20),
+]
+
+
+@pytest.mark.parametrize("case", ERR_CASES, ids=[c[0] for c in ERR_CASES])
+def test_reference_panic_conditions(case):
+    name, bad, code = case
+    p = ExlrParams.make(merge_min=200) if name == "merge_domain" else ExlrParams.make()
+    base = rand_batch(4242, 120, merge_clusters=False)
+    good = [dict(tid=int(base.tid[i]), pos=int(base.pos[i]), flag=int(base.flag[i]), mapq=int(base.mapq[i]),
+                 cigar=base.cigar[int(base.cigar_off[i]):int(base.cigar_off[i + 1])].tolist()) for i in range(base.n_reads)]
+    for at in (0, 57, len(good)):
+        recs = good[:at] + [bad] + good[at:]
+        hb = pack_records(recs, RREF)
+        for ck, rpc in ((0, 0), (0, 5), (1, 0)):
+            want, res = gpu_check(hb, p, ck, rpc, label=f"{name}@{at} k{ck}")
+            assert res.status == code and res.err_read == at
+    # the same bad record is harmless when the filters drop it
+    if name not in ("merge_domain",):
+        hb = pack_records([dict(bad, flag=256)], RREF)
+        _, res = gpu_check(hb, p, label=name + " filtered")
+        assert res.status == 0
+
+
+def test_no_error_inside_cap_dropped_record():
+    # -k cap `continue`s before the SA is parsed and before the indel arm (main.rs:311-313): malformed SA and a
+    # merge-domain CIGAR are both invisible there
+    sa = "chr1,5,+,10M,3,0;" * 3 + "chr1,bad,+,*,3;"
+    hb = pack_records([dict(tid=0, pos=5, flag=0, mapq=60, cigar="10M60D2M60D2M60D10M", sa=sa)], RREF)
+    _, res = gpu_check(hb, ExlrParams.make(merge_min=200), label="cap-dropped")
+    assert res.status == 0 and res.n_events == 0 and res.n_cap_dropped == 1
+
+
+def test_many_segments_use_the_pool():
+    # -k 100: more segments than the in-register array holds
+    import random
+    rng = random.Random(5)
+    recs = []
+    for i in range(50):
+        n = rng.choice([9, 10, 11, 30, 99])
+        sa = "".join("%s,%d,%s,%dS%dM,60,1;" % (rng.choice(RREF), rng.randint(1, 10 ** 7), rng.choice("+-"),
+                                                rng.randint(0, 5000), rng.randint(10, 900)) for _ in range(n))
+        recs.append(dict(tid=rng.randrange(len(RREF)), pos=rng.randint(0, 10 ** 7), flag=0, mapq=60, cigar="100S500M2000S", sa=sa))
+    hb = pack_records(recs, RREF)
+    gpu_check(hb, ExlrParams.make(max_supp_alignm=100), label="pool k100")
+    gpu_check(hb, ExlrParams.make(max_supp_alignm=10), label="pool k10")
+    gpu_check(hb, ExlrParams.make(max_supp_alignm=9), label="local k9")
+
+
+def test_event_capacity_overflow_is_reported():
+    hb = synth.config(0, 0.2)
+    p = ExlrParams.make(**synth.CONFIGS[0]["params"])
+    with pytest.raises(api.ExlrError) as e:
+        api.extract(hb, p, max_events=8)
+    assert e.value.status == -4
+
+
+@pytest.mark.parametrize("cfg,scale", [(0, 1.0), (1, 0.05), (2, 0.01), (3, 0.02)])
+def test_baseline_configs(cfg, scale):
+    hb = synth.with_qnames(synth.config(cfg, scale))
+    p = ExlrParams.make(**synth.CONFIGS[cfg]["params"])
+    for ck in (0, 1):
+        want, res = gpu_check(hb, p, ck, 0, verbose=(cfg == 0), label=f"config{cfg} k{ck}")
+    assert res.n_events > 0
+    if cfg == 3:
+        gpu_check(hb, ExlrParams.make(split_only=True, max_supp_alignm=8), label="config3 k8")
+    if cfg == 2:
+        assert int(np.diff(hb.cigar_off.astype(np.int64)).max()) > 65535       # a CIGAR beyond the BAM 16-bit op count
+
+
+def test_batch_reuse_and_two_in_flight():
+    p = ExlrParams.make()
+    a, b = rand_batch(1, 500), rand_batch(2, 800)
+    ex = api.Extractor(p, a.ref_names)
+    cap = lambda *hs: (max(h.n_reads for h in hs), max(h.n_ops for h in hs), max(h.n_sa_bytes for h in hs))
+    b1, b2 = ex.alloc_batch(*cap(a, b)), ex.alloc_batch(*cap(a, b))
+    for rnd in range(3):
+        x, y = (a, b) if rnd % 2 == 0 else (b, a)
+        b1.fill(x); b2.fill(y)
+        b1.submit(); b2.submit()
+        r1, r2 = b1.wait(), b2.wait()
+        check_result(x, p, r1, b1.format_lines(r1, False, None, 0, r1.n_events if r1.status == 0 else int(r1.line_off[r1.err_read])), label=f"reuse{rnd}a")
+        check_result(y, p, r2, b2.format_lines(r2, False, None, 0, r2.n_events if r2.status == 0 else int(r2.line_off[r2.err_read])), label=f"reuse{rnd}b")
+        t = b1.timing()
+        assert t.launches == 6 and t.kernels_ms > 0
+    # resident path gives the same header
+    b1.fill(a); b1.upload(); b1.submit_resident()
+    rr = b1.wait_resident()
+    b1.submit(); rh = b1.wait()
+    assert (rr.n_events, rr.n_kept, rr.status) == (rh.n_events, rh.n_kept, rh.status)
+    b1.free(); b2.free(); ex.close()
+
+
+def test_full_size_config1_checksums():
+    # BASELINE.json configs[1] at full size (1M molecules): whole-output comparison with the oracle
+    hb = synth.config(1, 1.0)
+    p = ExlrParams.make(**synth.CONFIGS[1]["params"])
+    want, res = gpu_check(hb, p, 0, 0, label="config1 full")
+    # size-independent properties: offsets are a prefix sum, events are grouped by ascending record
+    assert res.line_off[0] == 0 and res.line_off[-1] == res.n_events
+    assert (np.diff(res.events["read_idx"].astype(np.int64)) >= 0).all()
+    assert np.array_equal(np.bincount(res.events["read_idx"], minlength=hb.n_reads), np.diff(res.line_off.astype(np.int64)))
