@@ -30,6 +30,14 @@ class ExlrError(RuntimeError):
         self.status, self.err_read = status, err_read
 
 
+class ExlrCapacityError(ExlrError):
+    """EXLR_ERR_CAPACITY from exlr_wait; .needed = the max_events that would have sufficed."""
+
+    def __init__(self, needed: int):
+        super().__init__(-4, f"event buffers too small, need max_events >= {needed}")
+        self.needed = needed
+
+
 class _Views(C.Structure):
     _fields_ = [("cigar", C.c_void_p), ("cigar_off", C.c_void_p), ("pos", C.c_void_p), ("tid", C.c_void_p),
                 ("flag", C.c_void_p), ("mapq", C.c_void_p), ("sa_kind", C.c_void_p), ("sa_off", C.c_void_p),
@@ -177,6 +185,8 @@ class DeviceBatch:
     def wait(self, copy: bool = True, raise_on_record_error: bool = False) -> Result:
         raw = _Result()
         rc = self.lib.exlr_wait(self.handle, C.byref(raw))
+        if rc == -4:                                    # event buffers too small: n_events = capacity needed
+            raise ExlrCapacityError(int(raw.n_events))
         if rc != 0 and (rc > -10 or raise_on_record_error):
             _check(rc, int(raw.err_read) if rc <= -10 else -1)
         return Result(raw, copy)
@@ -261,24 +271,30 @@ class Extractor:
 
 
 def extract(hb: HostBatch, params: ExlrParams, device: int = 0, cigar_kernel: int = CIGAR_KERNEL_FLAT,
-            reads_per_cta: int = 0, verbose: bool = False, max_events: int = 0):
-    """One-shot: host batch -> (Result, formatted lines).  Host buffers in, host buffers out."""
+            reads_per_cta: int = 0, verbose: bool = False, max_events: int = 0, grow: bool = True):
+    """One-shot: host batch -> (Result, formatted lines).  Host buffers in, host buffers out.
+    If the event buffers turn out too small the batch is re-run once with the size the device reported."""
     ex = Extractor(params, hb.ref_names, device)
     try:
         ex.set_option(EXLR_OPT_CIGAR_KERNEL, cigar_kernel)
         ex.set_option(EXLR_OPT_READS_PER_CTA, reads_per_cta)
-        b = ex.batch_for(hb, max_events)
-        try:
-            b.submit()
-            res = b.wait()
-            if res.status != 0 and res.status > -10:
-                _check(res.status)
-            k = res.n_events
-            if res.status <= -10:
-                k = int(res.line_off[res.err_read])     # lines of the records before the failing one
-            text = b.format_lines(res, verbose, hb.qnames, 0, k)
-            return res, text
-        finally:
-            b.free()
+        for attempt in range(2):
+            b = ex.batch_for(hb, max_events)
+            try:
+                b.submit()
+                try:
+                    res = b.wait()
+                except ExlrCapacityError as e:
+                    if not grow or attempt:
+                        raise
+                    max_events = e.needed + 16
+                    continue
+                k = res.n_events
+                if res.status <= -10:
+                    k = int(res.line_off[res.err_read])     # lines of the records before the failing one
+                text = b.format_lines(res, verbose, hb.qnames, 0, k)
+                return res, text
+            finally:
+                b.free()
     finally:
         ex.close()

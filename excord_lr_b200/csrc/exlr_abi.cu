@@ -384,7 +384,11 @@ static int finish(exlr_batch* b, exlr_result* res, bool fetch)
     CK(cudaStreamSynchronize(b->stream));
     const Ctrl& c = *b->h_ctrl;
     res->n_events = c.n_events; res->n_kept = c.n_kept; res->n_sa_reads = c.n_sa; res->n_cap_dropped = c.n_dropped;
-    if (c.overflow) { res->status = EXLR_ERR_CAPACITY; res->n_events = 0; return res->status; }
+    if (c.overflow) {
+        // n_events = the max_events that would have sufficed (all three counters keep counting past the capacity)
+        uint32_t need = c.n_events; if (c.n_raw > need) need = c.n_raw; if (c.n_saev > need) need = c.n_saev;
+        res->status = EXLR_ERR_CAPACITY; res->n_events = need; return res->status;
+    }
     if (fetch) {
         CK(cudaMemcpyAsync(b->h_line_off, b->dv.line_off, (b->n_reads + 1) * 4, cudaMemcpyDeviceToHost, b->stream));
         if (c.n_events) CK(cudaMemcpyAsync(b->h_events, b->dv.events, (size_t)c.n_events * sizeof(exlr_event), cudaMemcpyDeviceToHost, b->stream));

@@ -58,25 +58,44 @@ __device__ __forceinline__ void store_event(exlr_event* dst, int64_t ls, int64_t
 }
 
 // ---- chained scan (decoupled look-back), one status word per tile: flag<<62 | value ----
+// 256 threads x 16 records = 4096 records per tile; the look-back is done by a whole warp, 32 tiles at a time.
 static constexpr int SCAN_THREADS = 256;
-static constexpr int SCAN_ITEMS = 4;
+static constexpr int SCAN_ITEMS = 16;
 static constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 static constexpr unsigned long long ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_VALUE = (1ull << 62) - 1;
 
-// thread 0 only: publish this tile's aggregate, return the sum of all previous tiles
+// warp 0 only (all 32 lanes): publish this tile's aggregate, return the sum of all previous tiles
 __device__ __forceinline__ uint32_t chained_prefix(unsigned long long* status, uint32_t tile, uint32_t agg)
 {
     volatile unsigned long long* st = status;
-    if (tile == 0) { st[0] = ST_PREFIX | agg; return 0; }
-    st[tile] = ST_AGG | agg;
+    const uint32_t lane = threadIdx.x & 31;
+    if (tile == 0) { if (lane == 0) st[0] = ST_PREFIX | agg; return 0; }
+    if (lane == 0) st[tile] = ST_AGG | agg;
     uint32_t prefix = 0;
-    for (int i = (int)tile - 1;; --i) {
-        unsigned long long s;
-        do { s = st[i]; } while ((s >> 62) == 0);
-        prefix += (uint32_t)(s & ST_VALUE);
-        if ((s >> 62) == 2) break;
+    int base = (int)tile - 1;
+    for (;;) {
+        const int idx = base - (int)lane;
+        unsigned long long s = 2ull << 62;                                     // tiles before 0: prefix 0
+        if (idx >= 0) s = st[idx];
+        const uint32_t flag = (uint32_t)(s >> 62);
+        const uint32_t pmask = __ballot_sync(0xffffffffu, flag == 2u);
+        const uint32_t zmask = __ballot_sync(0xffffffffu, flag == 0u);
+        if (pmask) {
+            const int fp = __ffs(pmask) - 1;                                   // nearest tile holding an inclusive prefix
+            const uint32_t need = fp == 31 ? 0xffffffffu : ((1u << (fp + 1)) - 1u);
+            if (zmask & need) continue;                                        // a nearer tile has not published yet
+            uint32_t v = (int)lane <= fp ? (uint32_t)(s & ST_VALUE) : 0u;
+            for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            prefix += v;
+            break;
+        }
+        if (zmask) continue;
+        uint32_t v = (uint32_t)(s & ST_VALUE);
+        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        prefix += v;
+        base -= 32;
     }
-    st[tile] = ST_PREFIX | (unsigned long long)(agg + prefix);
+    if (lane == 0) st[tile] = ST_PREFIX | (unsigned long long)(agg + prefix);
     return prefix;
 }
 
@@ -96,6 +115,21 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
     return base + incl - v;
 }
 
+// tile prefix: block scan + chained look-back; returns this thread's exclusive prefix over the whole batch
+__device__ __forceinline__ uint32_t tile_excl_scan(unsigned long long* status, uint32_t tile, uint32_t mine,
+                                                   uint32_t* s_warp, uint32_t* s_prefix, uint32_t* grand_total_if_last)
+{
+    uint32_t total;
+    const uint32_t excl = block_excl_scan(mine, s_warp, &total);
+    if (threadIdx.x < 32) {
+        const uint32_t p = chained_prefix(status, tile, total);
+        if (threadIdx.x == 0) *s_prefix = p;
+    }
+    __syncthreads();
+    *grand_total_if_last = *s_prefix + total;
+    return *s_prefix + excl;
+}
+
 // ======================================================================================
 // kernel 0: filter + tid check + ordered SA-record list
 // ======================================================================================
@@ -106,35 +140,56 @@ __global__ void __launch_bounds__(SCAN_THREADS) k0_classify(DevBatch B, DevParam
     __syncthreads();
     const uint32_t tile = s_tile, n = B.n_reads;
     const uint32_t r0 = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    uint32_t is_sa[SCAN_ITEMS], kept = 0, mine = 0;
+    uint32_t sa_mask = 0, kept = 0;
+    if (r0 + SCAN_ITEMS <= n) {
+        // 16 consecutive records per thread: 128-bit loads of every per-record array
+        union { uint4 v[2]; uint16_t h[16]; } fl;
+        union { uint4 v; uint8_t b[16]; } mq, kd;
+        union { uint4 v[4]; int32_t i[16]; } td;
+        fl.v[0] = __ldg(reinterpret_cast<const uint4*>(B.flag + r0)); fl.v[1] = __ldg(reinterpret_cast<const uint4*>(B.flag + r0) + 1);
+        mq.v = __ldg(reinterpret_cast<const uint4*>(B.mapq + r0));
+        kd.v = __ldg(reinterpret_cast<const uint4*>(B.sa_kind + r0));
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        const uint32_t r = r0 + i;
-        is_sa[i] = 0;
-        if (r < n) {
-            const uint32_t flag = B.flag[r], mq = B.mapq[r];
-            if (keep_record(P, flag, mq)) {
+        for (int k = 0; k < 4; k++) td.v[k] = __ldg(reinterpret_cast<const uint4*>(B.tid + r0) + k);
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            if (keep_record(P, fl.h[i], mq.b[i])) {
+                kept++;
+                const int32_t t = td.i[i];
+                if (t < 0 || t >= B.n_ref) report(B.ctrl, r0 + i, RANK_TID);     // record.contig() panics (main.rs:198)
+                else if (kd.b[i] != EXLR_SA_NONE) sa_mask |= 1u << i;
+            }
+        }
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int k = 0; k < 4; k++) reinterpret_cast<uint4*>(B.csa + r0)[k] = z;
+        if (P.split_only) {                                                      // kernel 1 does not run (main.rs:523)
+#pragma unroll
+            for (int k = 0; k < 8; k++) reinterpret_cast<uint4*>(B.k1 + r0)[k] = z;
+        }
+    } else {
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            const uint32_t r = r0 + i;
+            if (r >= n) break;
+            if (keep_record(P, B.flag[r], B.mapq[r])) {
                 kept++;
                 const int32_t t = B.tid[r];
-                if (t < 0 || t >= B.n_ref) report(B.ctrl, r, RANK_TID);     // record.contig() panics (main.rs:198)
-                else if (B.sa_kind[r] != EXLR_SA_NONE) { is_sa[i] = 1; mine++; }
+                if (t < 0 || t >= B.n_ref) report(B.ctrl, r, RANK_TID);
+                else if (B.sa_kind[r] != EXLR_SA_NONE) sa_mask |= 1u << i;
             }
             B.csa[r] = 0;
-            if (P.split_only) B.k1[r] = make_uint2(0u, 0u);                  // kernel 1 does not run (main.rs:523)
+            if (P.split_only) B.k1[r] = make_uint2(0u, 0u);
         }
     }
-    uint32_t total;
-    uint32_t excl = block_excl_scan(mine, s_warp, &total);
-    if (threadIdx.x == 0) s_prefix = chained_prefix(B.scan_a, tile, total);
-    __syncthreads();
-    uint32_t at = s_prefix + excl;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) if (is_sa[i]) B.sa_list[at++] = r0 + i;
+    uint32_t grand;
+    uint32_t at = tile_excl_scan(B.scan_a, tile, (uint32_t)__popc(sa_mask), s_warp, &s_prefix, &grand);
+    while (sa_mask) { const int i = __ffs(sa_mask) - 1; sa_mask &= sa_mask - 1; B.sa_list[at++] = r0 + i; }
     // kept counter: one atomic per warp
     for (int d = 16; d; d >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, d);
     if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&B.ctrl->n_kept, kept);
-    if (threadIdx.x == 0 && tile == (n + SCAN_TILE - 1) / SCAN_TILE - 1) B.ctrl->n_sa = s_prefix + total;
+    if (threadIdx.x == 0 && tile == (n + SCAN_TILE - 1) / SCAN_TILE - 1) B.ctrl->n_sa = grand;
 }
+
 
 // ======================================================================================
 // kernel 1 (variant B): warp per record
@@ -230,9 +285,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 }
 
 static constexpr int K1_THREADS = 256;
-static constexpr int K1_SUB = K1_THREADS * 4;          // ops per scan step (one uint4 per thread)
-static constexpr int K1_SUBS_PER_CHUNK = 4;
-static constexpr int K1_CHUNK = K1_SUB * K1_SUBS_PER_CHUNK;   // ops per TMA bulk copy (16 KB)
+static constexpr int K1_V = 16;                        // consecutive ops per thread per scan step
+static constexpr int K1_CHUNK = K1_THREADS * K1_V;     // ops per TMA bulk copy = per scan step (16 KB)
 static constexpr int K1_STAGES = 3;
 static constexpr int K1_MAX_RPC = 256;                 // records per CTA (thread t owns record t)
 static constexpr int K1_CAP = K1_THREADS;              // staged events per flush (one per thread)
@@ -240,8 +294,7 @@ static constexpr int K1_CAP = K1_THREADS;              // staged events per flus
 struct __align__(16) K1Stage { uint32_t fp, pexcl, n_type, pad; };
 
 struct __align__(128) K1Smem {
-    uint32_t buf[K1_STAGES][K1_CHUNK];
-    uint32_t lprefix[2][K1_SUB];
+    uint32_t buf[K1_STAGES][K1_CHUNK];                 // CIGAR ops as landed by TMA; overwritten in place by per-op prefixes
     K1Stage stage[K1_CAP];
     uint32_t roff[K1_MAX_RPC + 1];
     uint32_t pstart[K1_MAX_RPC + 1];
@@ -249,7 +302,8 @@ struct __align__(128) K1Smem {
     uint32_t rflags[K1_MAX_RPC];
     uint32_t fhead[K1_MAX_RPC];
     uint32_t rkeep[K1_MAX_RPC];
-    uint2 wtot[2][K1_THREADS / 32];
+    uint32_t wtot[2][K1_THREADS / 32];
+    uint32_t evcnt[K1_THREADS / 32];
     K1Stage carry_ev;
     uint32_t has_carry, gbase;
     unsigned long long full[K1_STAGES];
@@ -265,10 +319,12 @@ __device__ __forceinline__ uint32_t k1_find_read(const uint32_t* roff, uint32_t 
 }
 
 // Resolve and write out the `m` staged events (m <= K1_CAP, one per thread).  Block-uniform call.
-__device__ __forceinline__ void k1_flush(K1Smem& S, const DevBatch& B, const DevParams& P, uint32_t ra, uint32_t nr, uint32_t m)
+struct K1Out { RawEv* raw; Ctrl* ctrl; const int32_t* pos; uint32_t max_events, merge_min; };
+
+__device__ __noinline__ void k1_flush(K1Smem& S, K1Out O, uint32_t ra, uint32_t nr, uint32_t m)
 {
     const uint32_t t = threadIdx.x;
-    if (t == 0) S.gbase = atomicAdd(&B.ctrl->n_raw, m);
+    if (t == 0) S.gbase = atomicAdd(&O.ctrl->n_raw, m);
     __syncthreads();                                    // staging, pstart, gbase visible
     K1Stage ev; uint32_t i = 0; bool has_prev = false; K1Stage pv;
     pv.fp = 0; pv.pexcl = 0; pv.n_type = 0; pv.pad = 0; ev = pv;
@@ -290,19 +346,19 @@ __device__ __forceinline__ void k1_flush(K1Smem& S, const DevBatch& B, const Dev
             prevL = pv.pexcl - S.pstart[i];
             const uint32_t pn = pv.n_type & 0x7fffffffu, pdel = pv.n_type >> 31;
             if (del && pdel) {
-                const uint32_t pos2 = (uint32_t)B.pos[ra + i];
+                const uint32_t pos2 = (uint32_t)O.pos[ra + i];
                 uint32_t fl = 0;
-                if (seq == 1 && abs_diff(pos2 + L, pos2 + prevL + pn) < P.merge_min) fl |= K1_PAIR_MERGE;   // main.rs:615
-                if (abs_diff(pos2 + prevL, pos2 + L + len) < P.merge_min) fl |= K1_FAR_HIT;                 // main.rs:673-678
+                if (seq == 1 && abs_diff(pos2 + L, pos2 + prevL + pn) < O.merge_min) fl |= K1_PAIR_MERGE;   // main.rs:615
+                if (abs_diff(pos2 + prevL, pos2 + L + len) < O.merge_min) fl |= K1_FAR_HIT;                 // main.rs:673-678
                 if (fl) atomicOr(&S.rflags[i], fl);
             }
         }
         const uint32_t slot = S.gbase + t;
-        if (slot < B.max_events) {
-            uint4* d = reinterpret_cast<uint4*>(B.raw + slot);
+        if (slot < O.max_events) {
+            uint4* d = reinterpret_cast<uint4*>(O.raw + slot);
             d[0] = make_uint4(S.rkeep[i] ? ra + i : 0xffffffffu, seq, L, ev.n_type);
             d[1] = make_uint4(prevL, 0u, 0u, 0u);
-        } else B.ctrl->overflow = 1;
+        } else O.ctrl->overflow = 1;
     }
     __syncthreads();                                    // every seq computed before rcnt moves
     if (t < m) {
@@ -313,7 +369,47 @@ __device__ __forceinline__ void k1_flush(K1Smem& S, const DevBatch& B, const Dev
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(K1_THREADS) k1_flat(DevBatch B, DevParams P, uint32_t rpc)
+// Rare path of one scan step: rank this step's events over the CTA and stage them (flushing as needed).
+// Block-uniform call.  evm: bit k set = my k-th op is an event.
+__device__ __forceinline__ uint32_t k1_stage_events(K1Smem& S, const K1Out& O, uint32_t ra, uint32_t nr,
+                                                 uint32_t staged, uint32_t evm, const uint32_t* v, const uint32_t* e,
+                                                 uint32_t fp0, uint32_t pbase)
+{
+    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const uint32_t nev = __popc(evm);
+    uint32_t evincl = nev;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, evincl, d); if (lane >= (uint32_t)d) evincl += o; }
+    if (lane == 31) S.evcnt[w] = evincl;
+    __syncthreads();
+    uint32_t evbase = 0, evtotal = 0;
+#pragma unroll
+    for (int k = 0; k < K1_THREADS / 32; k++) { const uint32_t x = S.evcnt[k]; if ((uint32_t)k < w) evbase += x; evtotal += x; }
+    if (staged + evtotal > K1_CAP && staged) { k1_flush(S, O, ra, nr, staged); staged = 0; }
+    const uint32_t my0 = evbase + evincl - nev;                      // rank of my first event in this step
+    for (uint32_t round0 = 0; round0 < evtotal; round0 += K1_CAP) {
+        uint32_t rk = my0;
+#pragma unroll
+        for (int k = 0; k < K1_V; k++) {                                 // static indices keep v[] / e[] in registers
+            if (!(evm & (1u << k))) continue;
+            if (rk >= round0 && rk < round0 + K1_CAP) {
+                K1Stage x;
+                x.fp = fp0 + k;
+                x.pexcl = pbase + e[k];
+                x.n_type = (v[k] >> 4) | (((v[k] & 15u) == 2u) ? 0x80000000u : 0u);
+                x.pad = 0;
+                S.stage[staged + rk - round0] = x;
+            }
+            rk++;
+        }
+        const uint32_t nround = min((uint32_t)K1_CAP, evtotal - round0);
+        if (evtotal > K1_CAP) { k1_flush(S, O, ra, nr, staged + nround); staged = 0; }
+        else staged += nround;
+    }
+    return staged;
+}
+
+__global__ void __launch_bounds__(K1_THREADS, 3) k1_flat(DevBatch B, DevParams P, uint32_t rpc)
 {
     extern __shared__ __align__(128) unsigned char k1_smem_raw[];
     K1Smem& S = *reinterpret_cast<K1Smem*>(k1_smem_raw);
@@ -325,120 +421,102 @@ __global__ void __launch_bounds__(K1_THREADS) k1_flat(DevBatch B, DevParams P, u
     const unsigned long long oa4 = oa & ~3ull;
     const uint32_t span_lo = (uint32_t)(oa - oa4), span_hi = (uint32_t)(ob - oa4);
     if (ob - oa4 >= 0x80000000ull) { if (t == 0) B.ctrl->overflow = 1; return; }
-    // per-record state
-    for (uint32_t i = t; i <= nr; i += K1_THREADS) S.roff[i] = (uint32_t)(B.cigar_off[ra + i] - oa4);
-    if (t < nr) {
-        S.rkeep[t] = keep_record(P, B.flag[ra + t], B.mapq[ra + t]) ? 1u : 0u;
-        S.rcnt[t] = 0; S.rflags[t] = 0; S.fhead[t] = 0; S.pstart[t] = 0;
-    }
-    if (t == 0) {
-        S.has_carry = 0;
-        for (int s = 0; s < K1_STAGES; s++) mbar_init(&S.full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-
     const uint32_t nchunks = (span_hi + K1_CHUNK - 1) / K1_CHUNK;
     const uint32_t* gsrc = B.cigar + oa4;
     auto issue = [&](uint32_t c) {
         const uint32_t first = c * K1_CHUNK;
-        uint32_t nops = min((uint32_t)K1_CHUNK, span_hi - first);
+        const uint32_t nops = min((uint32_t)K1_CHUNK, span_hi - first);
         const uint32_t bytes = ((nops * 4u) + 15u) & ~15u;              // the cigar buffer is padded by 16 bytes
         unsigned long long* bar = &S.full[c % K1_STAGES];
         mbar_expect_tx(bar, bytes);
         tma_load_1d(S.buf[c % K1_STAGES], gsrc + first, bytes, bar);
     };
-    if (t == 0) for (uint32_t c = 0; c < nchunks && c < K1_STAGES; c++) issue(c);
+    if (t == 0) {
+        S.has_carry = 0;
+        for (int s = 0; s < K1_STAGES; s++) mbar_init(&S.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (uint32_t c = 0; c < nchunks && c < K1_STAGES; c++) issue(c);       // CIGAR bytes start moving first
+    }
+    // per-record state (overlaps the bulk copies)
+    for (uint32_t i = t; i <= nr; i += K1_THREADS) S.roff[i] = (uint32_t)(B.cigar_off[ra + i] - oa4);
+    if (t < nr) {
+        S.rkeep[t] = keep_record(P, B.flag[ra + t], B.mapq[ra + t]) ? 1u : 0u;
+        S.rcnt[t] = 0; S.rflags[t] = 0; S.fhead[t] = 0; S.pstart[t] = 0;
+    }
+    __syncthreads();
 
-    uint32_t carry = 0, staged = 0, g = 0;
+    const uint32_t imin16 = P.indel_min >= (1u << 28) ? 0xffffffffu : (P.indel_min << 4);
+    const K1Out O{B.raw, B.ctrl, B.pos, B.max_events, P.merge_min};
+    uint32_t carry = 0, staged = 0;
     for (uint32_t c = 0; c < nchunks; c++) {
         mbar_wait(&S.full[c % K1_STAGES], (c / K1_STAGES) & 1u);
-        const uint32_t* buf = S.buf[c % K1_STAGES];
-        const uint32_t subs = min((uint32_t)K1_SUBS_PER_CHUNK, (span_hi - c * K1_CHUNK + K1_SUB - 1) / K1_SUB);
-        for (uint32_t s = 0; s < subs; s++, g++) {
-            const uint32_t fb = g * K1_SUB;                              // flat position of this step's first op
-            const uint4 q = reinterpret_cast<const uint4*>(buf)[s * K1_THREADS + t];
-            const uint32_t vv[4] = {q.x, q.y, q.z, q.w};
-            uint32_t e[4], evm = 0, tsum = 0;
+        uint32_t* buf = S.buf[c % K1_STAGES];
+        const uint32_t fp0 = c * K1_CHUNK + t * K1_V;                    // flat position of my first op
+        uint32_t v[K1_V];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t fp = fb + t * 4 + k;
-                const bool valid = fp >= span_lo && fp < span_hi;
-                const uint32_t op = vv[k] & 15u, len = vv[k] >> 4;
-                e[k] = tsum;
-                if (valid) {
-                    if (op > 8u) {                                       // rust-htslib panics on an unknown op
-                        const uint32_t i = k1_find_read(S.roff, nr, fp);
-                        if (S.rkeep[i]) report(B.ctrl, ra + i, RANK_CIGAR_OP);
-                    } else {
-                        if (consumes_ref(op)) tsum += len;
-                        if ((op == 1u || op == 2u) && len >= P.indel_min) evm |= 1u << k;
-                    }
-                }
-            }
-            uint32_t wincl = tsum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, wincl, d); if (lane >= (uint32_t)d) wincl += o; }
-            const uint32_t wexcl = wincl - tsum;
-            // events: rank inside the warp (rare path)
-            const uint32_t nev = __popc(evm);
-            const uint32_t anyev = __ballot_sync(0xffffffffu, nev != 0);
-            uint32_t evincl = 0;
-            if (anyev) {
-                evincl = nev;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, evincl, d); if (lane >= (uint32_t)d) evincl += o; }
-            }
-            reinterpret_cast<uint4*>(S.lprefix[g & 1])[t] = make_uint4(wexcl + e[0], wexcl + e[1], wexcl + e[2], wexcl + e[3]);
-            if (lane == 31) S.wtot[g & 1][w] = make_uint2(wincl, evincl);
-            __syncthreads();
-            if (t == 0 && s + 1 == subs && c + K1_STAGES < nchunks) issue(c + K1_STAGES);   // stage c is drained
-            uint32_t wbase = 0, total = 0, evbase = 0, evtotal = 0;
-#pragma unroll
-            for (int k = 0; k < K1_THREADS / 32; k++) {
-                const uint2 x = S.wtot[g & 1][k];
-                if ((uint32_t)k < w) { wbase += x.x; evbase += x.y; }
-                total += x.x; evtotal += x.y;
-            }
-            // record starts inside this step: prefix value at the record's first op
-            if (t < nr) {
-                const uint32_t ro = S.roff[t];
-                if (ro >= fb && ro < fb + K1_SUB && ro < span_hi) {
-                    const uint32_t rel = ro - fb, wp = rel >> 7;
-                    uint32_t b2 = 0;
-                    for (uint32_t k = 0; k < wp; k++) b2 += S.wtot[g & 1][k].x;
-                    S.pstart[t] = carry + b2 + S.lprefix[g & 1][rel];
-                }
-            }
-            if (evtotal) {                                               // block-uniform
-                if (staged + evtotal > K1_CAP && staged) { k1_flush(S, B, P, ra, nr, staged); staged = 0; }
-                const uint32_t my0 = evbase + evincl - nev;              // rank of my first event in this step
-                for (uint32_t round0 = 0; round0 < evtotal; round0 += K1_CAP) {
-                    uint32_t rk = my0;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        if (evm & (1u << k)) {
-                            if (rk >= round0 && rk < round0 + K1_CAP) {
-                                K1Stage x;
-                                x.fp = fb + t * 4 + k;
-                                x.pexcl = carry + wbase + wexcl + e[k];
-                                x.n_type = (vv[k] >> 4) | (((vv[k] & 15u) == 2u) ? 0x80000000u : 0u);
-                                x.pad = 0;
-                                S.stage[staged + rk - round0] = x;
-                            }
-                            rk++;
-                        }
-                    }
-                    const uint32_t nround = min((uint32_t)K1_CAP, evtotal - round0);
-                    if (evtotal > K1_CAP) { k1_flush(S, B, P, ra, nr, staged + nround); staged = 0; }
-                    else staged += nround;
-                }
-            }
-            carry += total;
+        for (int k = 0; k < K1_V / 4; k++) {
+            const uint4 q = reinterpret_cast<const uint4*>(buf)[t * (K1_V / 4) + k];
+            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
         }
+        if (fp0 < span_lo || fp0 + K1_V > span_hi) {                     // CTA edge: blank the ops outside my records
+#pragma unroll
+            for (int k = 0; k < K1_V; k++) if (fp0 + k < span_lo || fp0 + k >= span_hi) v[k] = 0u;
+        }
+        // decode: reference-consuming length, event and unknown-op bits (masks indexed by the 4-bit op code)
+        uint32_t e[K1_V], tsum = 0, evm = 0, bad = 0;
+#pragma unroll
+        for (int k = 0; k < K1_V; k++) {
+            const uint32_t op = v[k] & 15u, len = v[k] >> 4;
+            e[k] = tsum;
+            tsum += ((0x8Du >> op) & 1u) * len;                         // M D N =  (main.rs:528-545)
+            if (v[k] >= imin16) evm |= ((0x6u << k) >> op) & (1u << k); // I or D with len >= indel_min (main.rs:553,569)
+            bad |= 0xFE00u >> op;                                       // op code 9..15
+        }
+        uint32_t wincl = tsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, wincl, d); if (lane >= (uint32_t)d) wincl += o; }
+        const uint32_t wexcl = wincl - tsum;
+        // per-op prefixes (warp-relative) replace the ops in shared memory: record starts read them below
+#pragma unroll
+        for (int k = 0; k < K1_V / 4; k++)
+            reinterpret_cast<uint4*>(buf)[t * (K1_V / 4) + k] =
+                make_uint4(wexcl + e[4 * k], wexcl + e[4 * k + 1], wexcl + e[4 * k + 2], wexcl + e[4 * k + 3]);
+        if (lane == 31) S.wtot[c & 1][w] = wincl;
+        const int any_ev = __syncthreads_or(evm != 0u);
+        // the stage read two steps ago is free now: every thread is past its prefix look-ups
+        if (t == 0 && c >= 1 && c - 1 + K1_STAGES < nchunks) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(c - 1 + K1_STAGES);
+        }
+        // cross-warp prefix: lanes 0..7 scan the eight warp totals
+        uint32_t x = lane < K1_THREADS / 32 ? S.wtot[c & 1][lane] : 0u;
+#pragma unroll
+        for (int d = 1; d < K1_THREADS / 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += o; }
+        const uint32_t total = __shfl_sync(0xffffffffu, x, K1_THREADS / 32 - 1);
+        uint32_t wbase = __shfl_sync(0xffffffffu, x, (w - 1u) & 31u);
+        if (w == 0) wbase = 0;
+        // record starts inside this step: prefix value at the record's first op
+        {
+            const uint32_t ro = t < nr ? S.roff[t] : 0xffffffffu;
+            const uint32_t fb = c * K1_CHUNK;
+            const bool mine = ro >= fb && ro < fb + K1_CHUNK && ro < span_hi;
+            const uint32_t rel = mine ? ro - fb : 0u, wp = rel / (32u * K1_V);
+            uint32_t b2 = __shfl_sync(0xffffffffu, x, (wp - 1u) & 31u);
+            if (wp == 0) b2 = 0;
+            if (mine) S.pstart[t] = carry + b2 + buf[rel];
+        }
+        if (bad & 1u) {                                                  // rust-htslib panics on an unknown op
+#pragma unroll
+            for (int k = 0; k < K1_V; k++) if ((v[k] & 15u) > 8u) {
+                const uint32_t i = k1_find_read(S.roff, nr, fp0 + k);
+                if (S.rkeep[i]) report(B.ctrl, ra + i, RANK_CIGAR_OP);
+            }
+        }
+        if (any_ev) staged = k1_stage_events(S, O, ra, nr, staged, evm, v, e, fp0, carry + wbase + wexcl);
+        carry += total;
     }
-    if (staged) k1_flush(S, B, P, ra, nr, staged);
+    if (staged) k1_flush(S, O, ra, nr, staged);
     __syncthreads();
     for (uint32_t i = t; i <= nr; i += K1_THREADS) if (S.roff[i] >= span_hi) S.pstart[i] = carry;   // trailing empty records + sentinel
     __syncthreads();
@@ -495,17 +573,37 @@ __global__ void __launch_bounds__(256) k3a_sa_cigar(DevBatch B, DevParams P)
 
 // ======================================================================================
 // kernel 3b: SA parse, cap, sort, large-INS rules, split pairs
+//
+// The SA list is ordered and only SA records own SA bytes, so the SA strings of 128 consecutive
+// list entries are one contiguous byte range: a CTA stages it into shared memory with coalesced
+// 128-bit loads and each thread then parses its own record's string out of shared memory
+// (falls back to reading global memory when the range does not fit).
 // ======================================================================================
-__device__ __forceinline__ bool dev_parse_i64(const uint8_t* s, uint32_t b, uint32_t e, int64_t* out)
+static constexpr int K3B_THREADS = 128;
+static constexpr uint32_t K3B_STAGE_BYTES = 32 * 1024;
+static constexpr uint32_t K3B_MAXP = 768;              // segments (records + SA pieces) per tile in the staged layout
+
+struct SmemBytes {            // byte i of sa_bytes, served from the staged copy
+    const uint8_t* p; uint32_t bias;
+    __device__ __forceinline__ uint32_t operator[](uint32_t i) const { return p[i - bias]; }
+};
+struct GlobalBytes {
+    const uint8_t* p;
+    __device__ __forceinline__ uint32_t operator[](uint32_t i) const { return __ldg(p + i); }
+};
+
+template <class Bytes>
+__device__ __forceinline__ bool dev_parse_i64(const Bytes& s, uint32_t b, uint32_t e, int64_t* out)
 {
     if (b == e) return false;
     bool neg = false;
-    if (s[b] == '+' || s[b] == '-') { neg = s[b] == '-'; b++; }
+    const uint32_t c0 = s[b];
+    if (c0 == '+' || c0 == '-') { neg = c0 == '-'; b++; }
     if (b == e) return false;
     const unsigned long long lim = neg ? (1ull << 63) : (1ull << 63) - 1;
     unsigned long long v = 0;
     for (; b < e; b++) {
-        const uint32_t d = (uint32_t)s[b] - '0';
+        const uint32_t d = s[b] - '0';
         if (d > 9u) return false;
         if (v > (lim - d) / 10ull) return false;
         v = v * 10ull + d;
@@ -514,14 +612,15 @@ __device__ __forceinline__ bool dev_parse_i64(const uint8_t* s, uint32_t b, uint
     return true;
 }
 
-__device__ __forceinline__ bool dev_parse_u8(const uint8_t* s, uint32_t b, uint32_t e)
+template <class Bytes>
+__device__ __forceinline__ bool dev_parse_u8(const Bytes& s, uint32_t b, uint32_t e)
 {
     if (b == e) return false;
     if (s[b] == '+') b++;
     if (b == e) return false;
     uint32_t v = 0;
     for (; b < e; b++) {
-        const uint32_t d = (uint32_t)s[b] - '0';
+        const uint32_t d = s[b] - '0';
         if (d > 9u) return false;
         v = v * 10u + d;
         if (v > 255u) return false;
@@ -530,7 +629,8 @@ __device__ __forceinline__ bool dev_parse_u8(const uint8_t* s, uint32_t b, uint3
 }
 
 // parse_supplementary_alignment + parse_cigar + find_first_match_pos (utils.rs:12-42, 88-139)
-__device__ uint32_t dev_parse_piece(const uint8_t* s, uint32_t b, uint32_t e, const DevParams& P, Seg* out)
+template <class Bytes>
+__device__ uint32_t dev_parse_piece(const Bytes& s, uint32_t b, uint32_t e, const DevParams& P, Seg* out)
 {
     uint32_t fb[6], fe[6], nf = 0, st = b;
     for (uint32_t i = b; i <= e; i++) {
@@ -542,8 +642,9 @@ __device__ uint32_t dev_parse_piece(const uint8_t* s, uint32_t b, uint32_t e, co
     if (nf < 6) return RANK_SA_FIELDS;
     int64_t pos;
     if (!dev_parse_i64(s, fb[1], fe[1], &pos)) return RANK_SA_POS;
-    if (fe[2] - fb[2] != 1 || (s[fb[2]] != '+' && s[fb[2]] != '-')) return RANK_SA_STRAND;
-    const uint32_t strand_neg = s[fb[2]] == '-';
+    const uint32_t sc = fe[2] - fb[2] == 1 ? s[fb[2]] : 0u;
+    if (sc != '+' && sc != '-') return RANK_SA_STRAND;
+    const uint32_t strand_neg = sc == '-';
     uint32_t sS = 0, sH = 0, sD = 0, sM = 0, sE = 0, sX = 0, ndig = 0;
     unsigned long long v = 0, key = 0; bool seenM = false;
     for (uint32_t i = fb[3]; i < fe[3]; i++) {
@@ -560,7 +661,8 @@ __device__ uint32_t dev_parse_piece(const uint8_t* s, uint32_t b, uint32_t e, co
     if (!dev_parse_u8(s, fb[4], fe[4])) return RANK_SA_MAPQ;
     int64_t nm;
     if (!dev_parse_i64(s, fb[5], fe[5], &nm)) return RANK_SA_NM;
-    uint32_t cb = fb[0], ce = fe[0];
+    uint32_t cb = fb[0];
+    const uint32_t ce = fe[0];
     if (ce - cb >= 3 && s[cb] == 'c' && s[cb + 1] == 'h' && s[cb + 2] == 'r') cb += 3;
     out->chrom_ref = 0x80000000u | cb;
     out->chrom_len = ce - cb;
@@ -572,16 +674,22 @@ __device__ uint32_t dev_parse_piece(const uint8_t* s, uint32_t b, uint32_t e, co
     return 0;
 }
 
-__device__ __forceinline__ const uint8_t* seg_chrom(const DevBatch& B, const Seg& s)
+template <class Bytes>
+__device__ __forceinline__ uint32_t chrom_byte(const DevBatch& B, const Bytes& s, const Seg& g, uint32_t i)
 {
-    return (s.chrom_ref >> 31) ? B.sa_bytes + (s.chrom_ref & 0x7fffffffu) : B.ref_bytes + B.ref_off[s.chrom_ref];
+    return (g.chrom_ref >> 31) ? s[(g.chrom_ref & 0x7fffffffu) + i] : (uint32_t)__ldg(B.ref_bytes + B.ref_off[g.chrom_ref] + i);
 }
 
-__device__ __forceinline__ int dev_bytes_cmp(const uint8_t* a, uint32_t an, const uint8_t* b, uint32_t bn)
+// String::cmp / as_bytes().cmp (utils.rs:76-77) on the "chr"-stripped names
+template <class Bytes>
+__device__ __forceinline__ int dev_chrom_cmp(const DevBatch& B, const Bytes& s, const Seg& a, const Seg& b)
 {
-    const uint32_t m = an < bn ? an : bn;
-    for (uint32_t i = 0; i < m; i++) { if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1; }
-    return an < bn ? -1 : (an > bn ? 1 : 0);
+    const uint32_t m = a.chrom_len < b.chrom_len ? a.chrom_len : b.chrom_len;
+    for (uint32_t i = 0; i < m; i++) {
+        const uint32_t x = chrom_byte(B, s, a, i), y = chrom_byte(B, s, b, i);
+        if (x != y) return x < y ? -1 : 1;
+    }
+    return a.chrom_len < b.chrom_len ? -1 : (a.chrom_len > b.chrom_len ? 1 : 0);
 }
 
 // overlap (utils.rs:158-194); IEEE f64 divide and compare, like the Rust
@@ -597,124 +705,231 @@ __device__ __forceinline__ bool dev_overlap(int64_t as, int64_t ae, int64_t bs, 
     return ov > p;
 }
 
-__global__ void __launch_bounds__(128) k3b_sa_events(DevBatch B, DevParams P)
+// Second half of a record's SA arm, shared by the fast and the fallback path: stable sort of the segments
+// (main.rs:322), large-INS rules (main.rs:340-486), slot allocation, event emission (main.rs:488-516).
+// Must be called by every lane of the warp (the slot allocation is warp-aggregated).
+template <class Bytes>
+__device__ __forceinline__ void k3b_finish(const DevBatch& B, const DevParams& P, const Bytes& s, uint32_t j, bool active,
+                                           uint32_t r, bool dropped, Seg* segs, uint32_t nseg)
 {
-    const uint32_t n_sa = B.ctrl->n_sa;
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t n_iter = (n_sa + stride - 1) / stride;
-    Seg local_segs[kLocalSegs];
-    for (uint32_t it = 0; it < n_iter; it++) {
-        const uint32_t j = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        const bool active = j < n_sa;
-        uint32_t r = 0, nseg = 0, n_ins = 0, ins_kind = 0, err = 0;
-        bool dropped = false;
-        Seg* segs = local_segs;
-        int64_t q1 = 0, q2 = 0, q0 = 0;
-        if (active) {
-            r = B.sa_list[j];
-            const SaSum sum = B.sa_sum[j];
-            const uint32_t flag = B.flag[r];
-            const int32_t tid = B.tid[r];
-            const uint8_t* s = B.sa_bytes;
-            const uint32_t b0 = B.sa_off[r], e0 = B.sa_off[r + 1];
-            const bool is_str = B.sa_kind[r] == EXLR_SA_STRING;
-            unsigned long long pieces = 1;
-            if (is_str) {
-                for (uint32_t i = b0; i < e0; i++) pieces += s[i] == ';';
-                if (pieces > P.max_supp_alignm) dropped = true;             // main.rs:311-313: the whole record is skipped
-            }
-            if (!dropped) {
-                if (is_str && pieces + 1 > (unsigned long long)kLocalSegs) {
-                    const uint32_t need = (uint32_t)pieces + 1;
-                    const uint32_t at = atomicAdd(&B.ctrl->seg_pool_used, need);
-                    if ((unsigned long long)at + need <= B.seg_pool_cap) segs = B.seg_pool + at;
-                    else { B.ctrl->overflow = 1; dropped = true; }
-                }
-            }
-            if (!dropped) {
-                Seg& a0 = segs[0];                                            // the record itself (main.rs:299-306)
-                a0.chrom_ref = (uint32_t)tid; a0.chrom_len = B.ref_off[tid + 1] - B.ref_off[tid];
-                a0.start = (int64_t)B.pos[r]; a0.end = a0.start + sum.refspan; a0.key = sum.ffm;
-                a0.clip_big = (sum.S > P.ins_clip_min || sum.H > P.ins_clip_min) ? 1u : 0u;
-                a0.strand_neg = (flag & 0x10u) ? 1u : 0u;
-                nseg = 1;
-                if (is_str) {
-                    uint32_t pb = b0;
-                    for (uint32_t i = b0; i <= e0 && !err; i++) {
-                        if (i == e0 || s[i] == ';') {
-                            if (i > pb) {                                     // filter(|x| x.len() > 0), main.rs:315
-                                err = dev_parse_piece(s, pb, i, P, &segs[nseg]);
-                                if (!err) nseg++;
-                            }
-                            pb = i + 1;
-                        }
-                    }
-                }
-                if (!err && nseg - 1 >= (1u << 24)) err = RANK_SPLIT_COUNT;
-                if (err) { report(B.ctrl, r, err); nseg = 0; }
-                else {
-                    for (uint32_t i = 1; i < nseg; i++) {                     // stable insertion sort by key (main.rs:322)
-                        const Seg x = segs[i]; uint32_t k = i;
-                        while (k > 0 && segs[k - 1].key > x.key) { segs[k] = segs[k - 1]; k--; }
-                        segs[k] = x;
-                    }
-                    if (nseg == 2) {                                          // main.rs:340-451
-                        const Seg& a = segs[0]; const Seg& b = segs[1];
-                        if (a.clip_big) {
-                            const bool same = dev_bytes_cmp(seg_chrom(B, a), a.chrom_len, seg_chrom(B, b), b.chrom_len) == 0;
-                            if (same) {
-                                if (a.strand_neg == b.strand_neg && dev_overlap(a.start, a.end, b.start, b.end, P.max_pct_overlap) && b.clip_big) {
-                                    int64_t q[4] = {a.start, a.end, b.start, b.end};
-#pragma unroll
-                                    for (int x = 1; x < 4; x++) { const int64_t val = q[x]; int y = x; while (y > 0 && q[y - 1] > val) { q[y] = q[y - 1]; y--; } q[y] = val; }
-                                    q0 = q[0]; q1 = q[1]; q2 = q[2];
-                                    n_ins = 2; ins_kind = EXLR_KIND_INS_TWO_ALN;
-                                }
-                            } else { n_ins = 1; ins_kind = EXLR_KIND_INS_ONE_ALN; }
-                        }
-                    } else if (nseg == 1) {                                   // main.rs:459-486
-                        if (segs[0].clip_big) { n_ins = 1; ins_kind = EXLR_KIND_INS_ONE_SEG; }
-                    }
-                }
-            }
+    uint32_t n_ins = 0, ins_kind = 0;
+    int64_t q1 = 0, q2 = 0, q0 = 0;
+    if (active && nseg) {
+        for (uint32_t i = 1; i < nseg; i++) {                             // stable insertion sort by key (main.rs:322)
+            const Seg x = segs[i]; uint32_t k = i;
+            while (k > 0 && segs[k - 1].key > x.key) { segs[k] = segs[k - 1]; k--; }
+            segs[k] = x;
         }
-        // temp slots: one atomic per warp
-        const uint32_t cnt = (active && nseg) ? n_ins + nseg - 1 : 0u;
-        uint32_t incl = cnt;
+        if (nseg == 2) {                                                  // main.rs:340-451
+            const Seg& a = segs[0]; const Seg& b = segs[1];
+            if (a.clip_big) {
+                if (dev_chrom_cmp(B, s, a, b) == 0) {
+                    if (a.strand_neg == b.strand_neg && dev_overlap(a.start, a.end, b.start, b.end, P.max_pct_overlap) && b.clip_big) {
+                        int64_t q[4] = {a.start, a.end, b.start, b.end};
+#pragma unroll
+                        for (int x = 1; x < 4; x++) { const int64_t val = q[x]; int y = x; while (y > 0 && q[y - 1] > val) { q[y] = q[y - 1]; y--; } q[y] = val; }
+                        q0 = q[0]; q1 = q[1]; q2 = q[2];
+                        n_ins = 2; ins_kind = EXLR_KIND_INS_TWO_ALN;
+                    }
+                } else { n_ins = 1; ins_kind = EXLR_KIND_INS_ONE_ALN; }
+            }
+        } else if (nseg == 1) {                                           // main.rs:459-486
+            if (segs[0].clip_big) { n_ins = 1; ins_kind = EXLR_KIND_INS_ONE_SEG; }
+        }
+    }
+    // temp slots: one atomic per warp
+    const uint32_t cnt = (active && nseg) ? n_ins + nseg - 1 : 0u;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+    uint32_t base = 0;
+    const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 31 && wtotal) base = atomicAdd(&B.ctrl->n_saev, wtotal);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+    const uint32_t dm = __ballot_sync(0xffffffffu, active && dropped);
+    if (lane == 0 && dm) atomicAdd(&B.ctrl->n_dropped, (uint32_t)__popc(dm));
+    if (!active) return;
+    B.sa_base[j] = base;
+    B.csa[r] = dropped ? CSA_DROP : cnt;
+    if (!cnt) return;
+    if ((unsigned long long)base + cnt > B.max_events) { B.ctrl->overflow = 1; return; }
+    exlr_event* dst = B.sa_ev + base;
+    if (n_ins == 2) {
+        const Seg& a = segs[0]; const Seg& b = segs[1];
+        const uint32_t meta = EXLR_EV_META(1u, EXLR_KIND_INS_TWO_ALN, a.strand_neg, b.strand_neg);
+        store_event(dst++, (int64_t)(uint32_t)q0, (int64_t)(uint32_t)q1, (int64_t)(uint32_t)q1, (int64_t)(uint32_t)q1, r, a.chrom_ref, b.chrom_ref, meta);
+        store_event(dst++, (int64_t)(uint32_t)q0, (int64_t)(uint32_t)q2, (int64_t)(uint32_t)q2, (int64_t)(uint32_t)q2, r, a.chrom_ref, b.chrom_ref, meta);
+    } else if (n_ins == 1) {
+        const Seg& a = segs[0];
+        const uint32_t meta = EXLR_EV_META(1u, ins_kind, a.strand_neg, a.strand_neg);
+        store_event(dst++, (int64_t)(uint32_t)a.start, (int64_t)(uint32_t)a.end, (int64_t)(uint32_t)a.end, (int64_t)(uint32_t)a.end, r, a.chrom_ref, a.chrom_ref, meta);
+    }
+    for (uint32_t i = 1; i < nseg; i++) {                                 // main.rs:488-516
+        const Seg* a = &segs[i - 1]; const Seg* b = &segs[i];
+        int c = dev_chrom_cmp(B, s, *a, *b);                               // alignment_pos_cmp, utils.rs:75-86
+        if (c == 0) c = a->start < b->start ? -1 : (a->start > b->start ? 1 : 0);
+        if (c > 0) { const Seg* x = a; a = b; b = x; }
+        store_event(dst++, a->start, a->end, b->start, b->end, r, a->chrom_ref, b->chrom_ref,
+                    EXLR_EV_META(nseg - 1, EXLR_KIND_SPLIT, a->strand_neg, b->strand_neg));
+    }
+}
+
+// the record's own alignment as segment 0 (main.rs:299-306)
+__device__ __forceinline__ void k3b_record_seg(const DevBatch& B, const DevParams& P, uint32_t j, uint32_t r, Seg* out)
+{
+    const SaSum sum = B.sa_sum[j];
+    const int32_t tid = B.tid[r];
+    out->chrom_ref = (uint32_t)tid; out->chrom_len = B.ref_off[tid + 1] - B.ref_off[tid];
+    out->start = (int64_t)B.pos[r]; out->end = out->start + sum.refspan; out->key = sum.ffm;
+    out->clip_big = (sum.S > P.ins_clip_min || sum.H > P.ins_clip_min) ? 1u : 0u;
+    out->strand_neg = (B.flag[r] & 0x10u) ? 1u : 0u;
+}
+
+// Fallback: one SA record parsed start to finish by one thread (used when a tile's SA bytes or segment count do
+// not fit the staged layout, e.g. -k far above the default).  Must be called by every lane of the warp.
+template <class Bytes>
+__device__ __noinline__ void k3b_record(const DevBatch& B, const DevParams& P, const Bytes& s, uint32_t j, bool active, Seg* local_segs)
+{
+    uint32_t r = 0, nseg = 0, err = 0;
+    bool dropped = false;
+    Seg* segs = local_segs;
+    if (active) {
+        r = B.sa_list[j];
+        const uint32_t b0 = B.sa_off[r], e0 = B.sa_off[r + 1];
+        const bool is_str = B.sa_kind[r] == EXLR_SA_STRING;
+        unsigned long long pieces = 1;
+        if (is_str) {
+            for (uint32_t i = b0; i < e0; i++) pieces += s[i] == ';';
+            if (pieces > P.max_supp_alignm) dropped = true;                 // main.rs:311-313: the whole record is skipped
+        }
+        if (!dropped && is_str && pieces + 1 > (unsigned long long)kLocalSegs) {
+            const uint32_t need = (uint32_t)pieces + 1;
+            const uint32_t at = atomicAdd(&B.ctrl->seg_pool_used, need);
+            if ((unsigned long long)at + need <= B.seg_pool_cap) segs = B.seg_pool + at;
+            else { B.ctrl->overflow = 1; dropped = true; }
+        }
+        if (!dropped) {
+            k3b_record_seg(B, P, j, r, &segs[0]);
+            nseg = 1;
+            if (is_str) {
+                uint32_t pb = b0;
+                for (uint32_t i = b0; i <= e0 && !err; i++) {
+                    if (i == e0 || s[i] == ';') {
+                        if (i > pb) {                                         // filter(|x| x.len() > 0), main.rs:315
+                            err = dev_parse_piece(s, pb, i, P, &segs[nseg]);
+                            if (!err) nseg++;
+                        }
+                        pb = i + 1;
+                    }
+                }
+            }
+            if (!err && nseg - 1 >= (1u << 24)) err = RANK_SPLIT_COUNT;
+            if (err) { report(B.ctrl, r, err); nseg = 0; }
+        }
+    }
+    k3b_finish(B, P, s, j, active, r, dropped, segs, nseg);
+}
+
+// Fast path layout: the tile's SA bytes, its piece list and its segments all live in shared memory, and the work
+// is re-flattened between phases so that the lanes of a warp always run the same loop:
+//   phase 1  thread per record : count ';' (the -k cap) and non-empty pieces          -> slots per record, block scan
+//   phase 1b thread per record : write the [begin,end) of every piece into the piece list
+//   phase 2  thread per PIECE  : parse_supplementary_alignment on homogeneous pieces   -> Seg
+//   phase 3  thread per record : record segment, sort, rules, emit
+struct __align__(16) K3bSmem {
+    uint8_t bytes[K3B_STAGE_BYTES];
+    Seg segs[K3B_MAXP];
+    uint32_t pb[K3B_MAXP], pe[K3B_MAXP];
+    uint32_t rerr[K3B_THREADS];
+    uint32_t sbase[K3B_THREADS + 1];
+    uint32_t wsum[K3B_THREADS / 32];
+    uint8_t pread[K3B_MAXP];
+};
+
+__global__ void __launch_bounds__(K3B_THREADS) k3b_sa_events(DevBatch B, DevParams P)
+{
+    extern __shared__ __align__(16) unsigned char k3b_smem_raw[];
+    K3bSmem& S = *reinterpret_cast<K3bSmem*>(k3b_smem_raw);
+    const uint32_t n_sa = B.ctrl->n_sa;
+    const uint32_t n_tiles = (n_sa + K3B_THREADS - 1) / K3B_THREADS;
+    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+    Seg local_segs[kLocalSegs];
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t j0 = tile * K3B_THREADS, j1 = min(j0 + (uint32_t)K3B_THREADS, n_sa);
+        const uint32_t span_b = B.sa_off[B.sa_list[j0]], span_e = B.sa_off[B.sa_list[j1 - 1] + 1];
+        const uint32_t a0 = span_b & ~15u;
+        const bool staged = span_e - a0 <= K3B_STAGE_BYTES;                   // block-uniform
+        const uint32_t j = j0 + t;
+        const bool active = j < j1;
+        __syncthreads();                                                      // the previous tile's readers are done
+        if (!staged) {
+            GlobalBytes s{B.sa_bytes};
+            k3b_record(B, P, s, j, active, local_segs);
+            continue;
+        }
+        for (uint32_t o = a0 + t * 16u; o < span_e; o += K3B_THREADS * 16u)
+            *reinterpret_cast<uint4*>(S.bytes + (o - a0)) = __ldg(reinterpret_cast<const uint4*>(B.sa_bytes + o));
+        // phase 1: pieces per record
+        uint32_t r = 0, b0 = 0, e0 = 0, slots = 0;
+        bool dropped = false, is_str = false;
+        if (active) { r = B.sa_list[j]; b0 = B.sa_off[r]; e0 = B.sa_off[r + 1]; is_str = B.sa_kind[r] == EXLR_SA_STRING; }
+        __syncthreads();
+        SmemBytes s{S.bytes, a0};
+        if (active) {
+            unsigned long long pieces = 1; uint32_t nonempty = 0, pbeg = b0;
+            if (is_str) {
+                for (uint32_t i = b0; i < e0; i++) if (s[i] == ';') { pieces++; nonempty += i > pbeg; pbeg = i + 1; }
+                nonempty += e0 > pbeg;
+                if (pieces > P.max_supp_alignm) dropped = true;               // main.rs:311-313
+            }
+            slots = dropped ? 0u : 1u + nonempty;
+            S.rerr[t] = 0xffffffffu;
+        }
+        uint32_t incl = slots;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
-        uint32_t base = 0;
-        const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
-        if (lane == 31 && wtotal) base = atomicAdd(&B.ctrl->n_saev, wtotal);
-        base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
-        // dropped-by-cap counter
-        const uint32_t dm = __ballot_sync(0xffffffffu, active && dropped);
-        if (lane == 0 && dm) atomicAdd(&B.ctrl->n_dropped, (uint32_t)__popc(dm));
-        if (!active) continue;
-        B.sa_base[j] = base;
-        B.csa[r] = dropped ? CSA_DROP : cnt;
-        if (!cnt) continue;
-        if ((unsigned long long)base + cnt > B.max_events) { B.ctrl->overflow = 1; continue; }
-        exlr_event* dst = B.sa_ev + base;
-        if (n_ins == 2) {
-            const Seg& a = segs[0]; const Seg& b = segs[1];
-            const uint32_t meta = EXLR_EV_META(1u, EXLR_KIND_INS_TWO_ALN, a.strand_neg, b.strand_neg);
-            store_event(dst++, (int64_t)(uint32_t)q0, (int64_t)(uint32_t)q1, (int64_t)(uint32_t)q1, (int64_t)(uint32_t)q1, r, a.chrom_ref, b.chrom_ref, meta);
-            store_event(dst++, (int64_t)(uint32_t)q0, (int64_t)(uint32_t)q2, (int64_t)(uint32_t)q2, (int64_t)(uint32_t)q2, r, a.chrom_ref, b.chrom_ref, meta);
-        } else if (n_ins == 1) {
-            const Seg& a = segs[0];
-            const uint32_t meta = EXLR_EV_META(1u, ins_kind, a.strand_neg, a.strand_neg);
-            store_event(dst++, (int64_t)(uint32_t)a.start, (int64_t)(uint32_t)a.end, (int64_t)(uint32_t)a.end, (int64_t)(uint32_t)a.end, r, a.chrom_ref, a.chrom_ref, meta);
+        if (lane == 31) S.wsum[w] = incl;
+        __syncthreads();
+        uint32_t sb = incl - slots, total = 0;
+#pragma unroll
+        for (int k = 0; k < K3B_THREADS / 32; k++) { const uint32_t x = S.wsum[k]; if ((uint32_t)k < w) sb += x; total += x; }
+        if (total > K3B_MAXP) {                                               // block-uniform: too many segments for the staged layout
+            k3b_record(B, P, s, j, active, local_segs);
+            continue;
         }
-        for (uint32_t i = 1; i < nseg; i++) {                                 // main.rs:488-516
-            const Seg* a = &segs[i - 1]; const Seg* b = &segs[i];
-            int c = dev_bytes_cmp(seg_chrom(B, *a), a->chrom_len, seg_chrom(B, *b), b->chrom_len);   // alignment_pos_cmp, utils.rs:75-86
-            if (c == 0) c = a->start < b->start ? -1 : (a->start > b->start ? 1 : 0);
-            if (c > 0) { const Seg* x = a; a = b; b = x; }
-            store_event(dst++, a->start, a->end, b->start, b->end, r, a->chrom_ref, b->chrom_ref,
-                        EXLR_EV_META(nseg - 1, EXLR_KIND_SPLIT, a->strand_neg, b->strand_neg));
+        // phase 1b: piece list
+        if (active && !dropped) {
+            S.pb[sb] = 0xffffffffu; S.pread[sb] = (uint8_t)t;                 // slot 0 of the record: its own alignment
+            if (is_str) {
+                uint32_t at = sb + 1, pbeg = b0;
+                for (uint32_t i = b0; i <= e0; i++) {
+                    if (i == e0 || s[i] == ';') {
+                        if (i > pbeg) { S.pb[at] = pbeg; S.pe[at] = i; S.pread[at] = (uint8_t)t; at++; }
+                        pbeg = i + 1;
+                    }
+                }
+            }
         }
+        __syncthreads();
+        // phase 2: one thread per piece
+        for (uint32_t x = t; x < total; x += K3B_THREADS) {
+            const uint32_t pbeg = S.pb[x];
+            if (pbeg == 0xffffffffu) continue;
+            const uint32_t err = dev_parse_piece(s, pbeg, S.pe[x], P, &S.segs[x]);
+            if (err) atomicMin(&S.rerr[S.pread[x]], (x << 8) | err);          // the first failing piece in SA order wins
+        }
+        __syncthreads();
+        // phase 3: one thread per record
+        uint32_t nseg = 0;
+        if (active && !dropped) {
+            uint32_t err = S.rerr[t];
+            nseg = slots;
+            if (err == 0xffffffffu && nseg - 1 >= (1u << 24)) err = RANK_SPLIT_COUNT;
+            if (err != 0xffffffffu) { report(B.ctrl, r, err & 0xffu); nseg = 0; }
+            else k3b_record_seg(B, P, j, r, &S.segs[sb]);
+        }
+        k3b_finish(B, P, s, j, active, r, dropped, &S.segs[sb < K3B_MAXP ? sb : 0], nseg);
     }
 }
 
@@ -727,6 +942,13 @@ __device__ __forceinline__ uint32_t indel_lines(uint32_t info)
     return (cnt == 2u && (info & K1_PAIR_MERGE)) ? 1u : cnt;                  // main.rs:612-635
 }
 
+__device__ __forceinline__ uint32_t record_lines(const DevBatch& B, uint32_t r, uint32_t csa, uint32_t info)
+{
+    if (csa & CSA_DROP) return 0u;                                            // -k cap: no lines at all (main.rs:311-313)
+    if ((info & K1_CNT_MASK) > 2u && (info & K1_FAR_HIT)) report(B.ctrl, r, RANK_MERGE_DOMAIN);
+    return (csa & CSA_CNT_MASK) + indel_lines(info);
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS) k4a_line_scan(DevBatch B, DevParams P)
 {
     __shared__ uint32_t s_tile, s_prefix, s_warp[8];
@@ -735,34 +957,43 @@ __global__ void __launch_bounds__(SCAN_THREADS) k4a_line_scan(DevBatch B, DevPar
     const uint32_t tile = s_tile, n = B.n_reads;
     const uint32_t r0 = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint32_t c[SCAN_ITEMS], mine = 0;
+    const bool full = r0 + SCAN_ITEMS <= n;
+    if (full) {
+        union { uint4 v[4]; uint32_t u[16]; } cs;
+        union { uint4 v[8]; uint2 p[16]; } k1;
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        const uint32_t r = r0 + i;
-        c[i] = 0;
-        if (r < n) {
-            const uint32_t csa = B.csa[r];
-            if (!(csa & CSA_DROP)) {
-                const uint32_t info = B.k1[r].y;
-                if ((info & K1_CNT_MASK) > 2u && (info & K1_FAR_HIT)) report(B.ctrl, r, RANK_MERGE_DOMAIN);
-                c[i] = (csa & CSA_CNT_MASK) + indel_lines(info);
-            }
+        for (int k = 0; k < 4; k++) cs.v[k] = reinterpret_cast<const uint4*>(B.csa + r0)[k];
+#pragma unroll
+        for (int k = 0; k < 8; k++) k1.v[k] = reinterpret_cast<const uint4*>(B.k1 + r0)[k];
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) { c[i] = record_lines(B, r0 + i, cs.u[i], k1.p[i].y); mine += c[i]; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            const uint32_t r = r0 + i;
+            c[i] = r < n ? record_lines(B, r, B.csa[r], B.k1[r].y) : 0u;
             mine += c[i];
         }
     }
-    uint32_t total;
-    uint32_t excl = block_excl_scan(mine, s_warp, &total);
-    if (threadIdx.x == 0) s_prefix = chained_prefix(B.scan_b, tile, total);
-    __syncthreads();
-    uint32_t at = s_prefix + excl;
+    uint32_t grand;
+    uint32_t at = tile_excl_scan(B.scan_b, tile, mine, s_warp, &s_prefix, &grand);
+    if (full) {
+        union { uint4 v[4]; uint32_t u[16]; } o;
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) { if (r0 + i < n) B.line_off[r0 + i] = at; at += c[i]; }
+        for (int i = 0; i < SCAN_ITEMS; i++) { o.u[i] = at; at += c[i]; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) reinterpret_cast<uint4*>(B.line_off + r0)[k] = o.v[k];
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) { if (r0 + i < n) B.line_off[r0 + i] = at; at += c[i]; }
+    }
     if (threadIdx.x == 0 && tile == (n + SCAN_TILE - 1) / SCAN_TILE - 1) {
-        const uint32_t all = s_prefix + total;
-        B.line_off[n] = all;
-        B.ctrl->n_events = all;
-        if (all > B.max_events) B.ctrl->overflow = 1;
+        B.line_off[n] = grand;
+        B.ctrl->n_events = grand;
+        if (grand > B.max_events) B.ctrl->overflow = 1;
     }
 }
+
 
 // ======================================================================================
 // kernel 4b: ordered compaction into the output event buffer
@@ -823,7 +1054,9 @@ cudaError_t configure_kernels(int device)
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) return e;
     g_sm_count = prop.multiProcessorCount;
-    return cudaFuncSetAttribute(k1_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
+    e = cudaFuncSetAttribute(k1_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k3b_sa_events, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3bSmem));
 }
 
 void launch_k0(const DevBatch& B, const DevParams& P, cudaStream_t st)
@@ -854,8 +1087,8 @@ void launch_k3a(const DevBatch& B, const DevParams& P, cudaStream_t st)
 
 void launch_k3b(const DevBatch& B, const DevParams& P, cudaStream_t st)
 {
-    const uint32_t gb = min((B.n_reads + 127u) / 128u, (uint32_t)g_sm_count * 16u);
-    k3b_sa_events<<<gb ? gb : 1u, 128, 0, st>>>(B, P);
+    const uint32_t gb = min((B.n_reads + 127u) / 128u, (uint32_t)g_sm_count * 3u);
+    k3b_sa_events<<<gb ? gb : 1u, K3B_THREADS, sizeof(K3bSmem), st>>>(B, P);
 }
 
 void launch_k4a(const DevBatch& B, const DevParams& P, cudaStream_t st)

@@ -128,7 +128,7 @@ typedef struct exlr_result {
     int32_t  status;          /* EXLR_OK or the (negative) code of the first failing record         */
     uint32_t err_read;        /* smallest failing record index (valid when status <= -10)           */
     uint64_t n_reads;
-    uint64_t n_events;        /* number of output lines                                             */
+    uint64_t n_events;        /* number of output lines (on EXLR_ERR_CAPACITY: the max_events needed) */
     const exlr_event* events; /* [n_events] in reference output order               */
     const uint32_t* line_off; /* [n_reads+1] events of record i are [line_off[i], line_off[i+1])    */
     uint64_t n_kept;          /* records that passed the filters (main.rs:169-190)                  */

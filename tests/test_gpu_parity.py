@@ -118,7 +118,9 @@ def test_reference_panic_conditions(case):
     base = rand_batch(4242, 120, merge_clusters=False)
     good = [dict(tid=int(base.tid[i]), pos=int(base.pos[i]), flag=int(base.flag[i]), mapq=int(base.mapq[i]),
                  cigar=base.cigar[int(base.cigar_off[i]):int(base.cigar_off[i + 1])].tolist()) for i in range(base.n_reads)]
-    for at in (0, 57, len(good)):
+    if name == "merge_domain":      # keep the other records free of indel events so the injected one is the first offender
+        good = [g for g in good if all((v >> 4) < 50 for v in g["cigar"])]
+    for at in (0, min(57, len(good) // 2), len(good)):
         recs = good[:at] + [bad] + good[at:]
         hb = pack_records(recs, RREF)
         for ck, rpc in ((0, 0), (0, 5), (1, 0)):
@@ -159,9 +161,11 @@ def test_many_segments_use_the_pool():
 def test_event_capacity_overflow_is_reported():
     hb = synth.config(0, 0.2)
     p = ExlrParams.make(**synth.CONFIGS[0]["params"])
-    with pytest.raises(api.ExlrError) as e:
-        api.extract(hb, p, max_events=8)
-    assert e.value.status == -4
+    with pytest.raises(api.ExlrCapacityError) as e:
+        api.extract(hb, p, max_events=8, grow=False)
+    assert e.value.status == -4 and e.value.needed > 8
+    # and the one-shot helper grows the buffers to exactly what the device asked for
+    gpu_check(hb, p, max_events=8, label="grown")
 
 
 @pytest.mark.parametrize("cfg,scale", [(0, 1.0), (1, 0.05), (2, 0.01), (3, 0.02)])
@@ -182,7 +186,7 @@ def test_batch_reuse_and_two_in_flight():
     a, b = rand_batch(1, 500), rand_batch(2, 800)
     ex = api.Extractor(p, a.ref_names)
     cap = lambda *hs: (max(h.n_reads for h in hs), max(h.n_ops for h in hs), max(h.n_sa_bytes for h in hs))
-    b1, b2 = ex.alloc_batch(*cap(a, b)), ex.alloc_batch(*cap(a, b))
+    b1, b2 = ex.alloc_batch(*cap(a, b), 20000), ex.alloc_batch(*cap(a, b), 20000)
     for rnd in range(3):
         x, y = (a, b) if rnd % 2 == 0 else (b, a)
         b1.fill(x); b2.fill(y)
