@@ -278,14 +278,14 @@ def extract(hb: HostBatch, params: ExlrParams, device: int = 0, cigar_kernel: in
     try:
         ex.set_option(EXLR_OPT_CIGAR_KERNEL, cigar_kernel)
         ex.set_option(EXLR_OPT_READS_PER_CTA, reads_per_cta)
-        for attempt in range(2):
+        for attempt in range(5):
             b = ex.batch_for(hb, max_events)
             try:
                 b.submit()
                 try:
                     res = b.wait()
                 except ExlrCapacityError as e:
-                    if not grow or attempt:
+                    if not grow or attempt == 4:
                         raise
                     max_events = e.needed + 16
                     continue

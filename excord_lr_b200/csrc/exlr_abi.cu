@@ -163,7 +163,7 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
     if (!c) return EXLR_ERR_ARG;
     switch (option) {
     case EXLR_OPT_CIGAR_KERNEL: if (value != 0 && value != 1) return EXLR_ERR_ARG; c->cigar_kernel = (int)value; return EXLR_OK;
-    case EXLR_OPT_READS_PER_CTA: if (value < 0 || value > 256) return EXLR_ERR_ARG; c->reads_per_cta = (uint32_t)value; return EXLR_OK;
+    case EXLR_OPT_READS_PER_CTA: if (value < 0 || value > 128) return EXLR_ERR_ARG; c->reads_per_cta = (uint32_t)value; return EXLR_OK;
     default: return EXLR_ERR_ARG;
     }
 }
@@ -221,7 +221,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     const size_t d_ctrl = dcarve(sizeof(Ctrl) + (size_t)tiles * 16);          // ctrl | scan_a | scan_b : one memset
     const size_t d_cigar = dcarve((max_ops + 4) * 4 + 16), d_coff = dcarve((R + 1) * 8), d_pos = dcarve(R * 4), d_tid = dcarve(R * 4),
                  d_flag = dcarve(R * 2), d_mapq = dcarve(R), d_kind = dcarve(R), d_soff = dcarve((R + 1) * 4), d_sab = dcarve(max_sa_bytes + 16),
-                 d_k1 = dcarve(R * 8), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
+                 d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
                  d_raw = dcarve(max_events * sizeof(RawEv)), d_saev = dcarve(max_events * sizeof(exlr_event)),
                  d_pool = dcarve(pool_cap * sizeof(Seg)), d_loff = dcarve((R + 1) * 4), d_ev = dcarve(max_events * sizeof(exlr_event));
     e = cudaMalloc(&b->d_slab, dof);
@@ -235,6 +235,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     v.tid = (int32_t*)(ds + d_tid); v.flag = (uint16_t*)(ds + d_flag); v.mapq = (uint8_t*)(ds + d_mapq); v.sa_kind = (uint8_t*)(ds + d_kind);
     v.sa_off = (uint32_t*)(ds + d_soff); v.sa_bytes = (uint8_t*)(ds + d_sab);
     v.ref_bytes = c->d_ref_bytes; v.ref_off = c->d_ref_off; v.n_ref = c->n_ref;
+    v.tile_cnt = (uint32_t*)(ds + d_tcnt); v.raw_cap = (uint32_t)max_events;
     v.k1 = (uint2*)(ds + d_k1); v.csa = (uint32_t*)(ds + d_csa); v.sa_list = (uint32_t*)(ds + d_list); v.sa_base = (uint32_t*)(ds + d_base);
     v.sa_sum = (SaSum*)(ds + d_sum); v.raw = (RawEv*)(ds + d_raw); v.sa_ev = (exlr_event*)(ds + d_saev);
     v.seg_pool = (Seg*)(ds + d_pool); v.seg_pool_cap = (uint32_t)pool_cap;
@@ -280,12 +281,12 @@ static int copy_inputs(exlr_batch* b, uint64_t n)
 
 static uint32_t auto_rpc(uint64_t n_reads, uint64_t n_ops)
 {
-    // aim at ~12k ops (48 KB of CIGAR) per CTA so short-read batches use full 256-record CTAs and
-    // long-read batches still spread over every SM
+    // kernel 1 scans 2048 ops per step: aim just under two steps of CIGAR per CTA for short-read batches (full
+    // 128-record CTAs), one record per CTA once records are longer than that
     const uint64_t mean = n_reads ? (n_ops + n_reads - 1) / n_reads : 1;
-    uint64_t rpc = 12288 / (mean ? mean : 1);
+    uint64_t rpc = 3900 / (mean ? mean : 1);
     if (rpc < 1) rpc = 1;
-    if (rpc > 256) rpc = 256;
+    if (rpc > 128) rpc = 128;
     return (uint32_t)rpc;
 }
 
@@ -296,8 +297,11 @@ static int run_kernels(exlr_batch* b)
     CK(cudaMemsetAsync(d.ctrl, 0, b->ctrl_bytes, st));
     launch_k0(d, c->dparams, st); b->launches++;
     CK(cudaEventRecord(b->ev[EV_K0], st));
+    d.prim_slots = 0; d.capt_log2 = 0;
     if (!c->params.split_only) {
         const uint32_t rpc = c->reads_per_cta ? c->reads_per_cta : auto_rpc(b->n_reads, b->n_ops);
+        uint32_t n_tiles = 0;
+        plan_k1(d, c->cigar_kernel, rpc, &n_tiles);
         launch_k1(d, c->dparams, c->cigar_kernel, rpc, st); b->launches++;
     }
     CK(cudaEventRecord(b->ev[EV_K1], st));
@@ -386,7 +390,8 @@ static int finish(exlr_batch* b, exlr_result* res, bool fetch)
     res->n_events = c.n_events; res->n_kept = c.n_kept; res->n_sa_reads = c.n_sa; res->n_cap_dropped = c.n_dropped;
     if (c.overflow) {
         // n_events = the max_events that would have sufficed (all three counters keep counting past the capacity)
-        uint32_t need = c.n_events; if (c.n_raw > need) need = c.n_raw; if (c.n_saev > need) need = c.n_saev;
+        uint64_t need = c.n_events; if (c.n_saev > need) need = c.n_saev;
+        if (c.n_raw) { const uint64_t r = (uint64_t)b->dv.raw_cap + 2ull * c.n_raw; if (r > need) need = r; }
         res->status = EXLR_ERR_CAPACITY; res->n_events = need; return res->status;
     }
     if (fetch) {

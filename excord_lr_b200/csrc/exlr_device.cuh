@@ -88,7 +88,9 @@ struct DevBatch {
     uint32_t* sa_list;      // [R] ordered indices of kept records with an SA aux
     uint32_t* sa_base;      // [R] first temp slot of the SA record's events (indexed like sa_list)
     SaSum* sa_sum;          // [R] indexed like sa_list
-    RawEv* raw;             // [max_events]
+    RawEv* raw;             // [raw_cap]: per-tile slices [0, prim_slots), then the overflow region
+    uint32_t* tile_cnt;     // [R] events in each tile's slice
+    uint32_t raw_cap, prim_slots, capt_log2;
     exlr_event* sa_ev;      // [max_events] SA-derived events, per record contiguous
     Seg* seg_pool; uint32_t seg_pool_cap;
     unsigned long long* scan_a; unsigned long long* scan_b;   // chained-scan tile status
@@ -111,6 +113,7 @@ cudaError_t configure_kernels(int device);
 size_t k1_flat_smem_bytes();
 uint32_t scan_tiles(uint32_t n_reads);
 void launch_k0(const DevBatch& B, const DevParams& P, cudaStream_t st);
+void plan_k1(DevBatch& B, int variant, uint32_t rpc, uint32_t* tiles_out);
 void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc, cudaStream_t st);
 void launch_k3a(const DevBatch& B, const DevParams& P, cudaStream_t st);
 void launch_k3b(const DevBatch& B, const DevParams& P, cudaStream_t st);

@@ -235,8 +235,8 @@ __global__ void __launch_bounds__(256) k1_warp(DevBatch B, DevParams P)
                         if (seq == 1 && abs_diff(pos2 + L, pos2 + qL + qn) < P.merge_min) myflags |= K1_PAIR_MERGE;   // main.rs:615
                         if (abs_diff(pos2 + qL, pos2 + L + len) < P.merge_min) myflags |= K1_FAR_HIT;                 // main.rs:673-678
                     }
-                    const uint32_t slot = base + rank;
-                    if (slot < B.max_events) {
+                    const uint32_t slot = B.prim_slots + base + rank;
+                    if (slot < B.raw_cap) {
                         uint4* d = reinterpret_cast<uint4*>(B.raw + slot);
                         d[0] = make_uint4(r, seq, L, len | (del << 31));
                         d[1] = make_uint4(has_prev ? qL : 0u, 0u, 0u, 0u);
@@ -284,28 +284,33 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
                  "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-static constexpr int K1_THREADS = 256;
+static constexpr int K1_THREADS = 128;
+static constexpr int K1_WARPS = K1_THREADS / 32;
 static constexpr int K1_V = 16;                        // consecutive ops per thread per scan step
-static constexpr int K1_CHUNK = K1_THREADS * K1_V;     // ops per TMA bulk copy = per scan step (16 KB)
-static constexpr int K1_STAGES = 3;
-static constexpr int K1_MAX_RPC = 256;                 // records per CTA (thread t owns record t)
+static constexpr int K1_CHUNK = K1_THREADS * K1_V;     // ops per TMA bulk copy = per scan step (8 KB)
+static constexpr int K1_STAGES = 5;                    // ring of bulk-copy stages (40 KB), kept full across tiles
+static constexpr int K1_MAX_RPC = K1_THREADS;          // records per tile (thread t owns record t)
 static constexpr int K1_CAP = K1_THREADS;              // staged events per flush (one per thread)
+static constexpr int K1_MAX_TILES = 256;               // tiles per CTA
 
 struct __align__(16) K1Stage { uint32_t fp, pexcl, n_type, pad; };
 
 struct __align__(128) K1Smem {
     uint32_t buf[K1_STAGES][K1_CHUNK];                 // CIGAR ops as landed by TMA; overwritten in place by per-op prefixes
     K1Stage stage[K1_CAP];
+    unsigned long long tb[K1_MAX_TILES][2];            // [first, last) op offset of every tile of this CTA
+    uint32_t rpos[K1_MAX_RPC];                         // record.pos() as u32 (aligments_event.rs:43)
     uint32_t roff[K1_MAX_RPC + 1];
     uint32_t pstart[K1_MAX_RPC + 1];
     uint32_t rcnt[K1_MAX_RPC];
     uint32_t rflags[K1_MAX_RPC];
     uint32_t fhead[K1_MAX_RPC];
     uint32_t rkeep[K1_MAX_RPC];
-    uint32_t wtot[2][K1_THREADS / 32];
-    uint32_t evcnt[K1_THREADS / 32];
+    uint32_t tpre[2][K1_THREADS];                      // warp-relative exclusive prefix of each thread's 16 ops
+    uint32_t wtot[2][K1_WARPS];
+    uint32_t evcnt[K1_WARPS];
     K1Stage carry_ev;
-    uint32_t has_carry, gbase;
+    uint32_t has_carry, gbase, flushes, in_slab;
     unsigned long long full[K1_STAGES];
 };
 
@@ -318,13 +323,26 @@ __device__ __forceinline__ uint32_t k1_find_read(const uint32_t* roff, uint32_t 
     return lo;
 }
 
-// Resolve and write out the `m` staged events (m <= K1_CAP, one per thread).  Block-uniform call.
-struct K1Out { RawEv* raw; Ctrl* ctrl; const int32_t* pos; uint32_t max_events, merge_min; };
+// Where a tile's raw events go: the tile's first flush lands in its own fixed slice of the raw buffer
+// (no atomic, no round trip); anything beyond goes to the shared overflow region behind the slices.
+struct K1Out { RawEv* raw; Ctrl* ctrl; uint32_t* tile_cnt; uint32_t raw_cap, merge_min, prim_slots, capt_log2; };
 
-__device__ __noinline__ void k1_flush(K1Smem& S, K1Out O, uint32_t ra, uint32_t nr, uint32_t m)
+// Resolve and write out the `m` staged events (m <= K1_CAP, one per thread).  Block-uniform call.
+// `spare` (meaningful in thread 0 only) is an overflow slab of K1_CAP slots reserved ahead of time, so that no flush
+// ever waits for an atomic: the flush that consumes it immediately reserves the next one.
+__device__ __forceinline__ void k1_flush(K1Smem& S, const K1Out& O, uint32_t tile, uint32_t ra, uint32_t nr, uint32_t m, uint32_t& spare)
 {
     const uint32_t t = threadIdx.x;
-    if (t == 0) S.gbase = atomicAdd(&O.ctrl->n_raw, m);
+    if (t == 0) {
+        const uint32_t capt = O.prim_slots ? (1u << O.capt_log2) : 0u;
+        if (S.flushes == 0 && m <= capt) { S.gbase = tile << O.capt_log2; O.tile_cnt[tile] = m; S.in_slab = 0; }
+        else {
+            if (S.flushes == 0) O.tile_cnt[tile] = 0;                     // slice unused: everything of this tile overflows
+            S.gbase = O.prim_slots + spare; S.in_slab = 1;
+            spare = atomicAdd(&O.ctrl->n_raw, (uint32_t)K1_CAP);          // not needed before the next overflowing flush
+        }
+        S.flushes++;
+    }
     __syncthreads();                                    // staging, pstart, gbase visible
     K1Stage ev; uint32_t i = 0; bool has_prev = false; K1Stage pv;
     pv.fp = 0; pv.pexcl = 0; pv.n_type = 0; pv.pad = 0; ev = pv;
@@ -337,6 +355,7 @@ __device__ __noinline__ void k1_flush(K1Smem& S, K1Out O, uint32_t ra, uint32_t 
     }
     __syncthreads();
     uint32_t seq = 0;
+    const uint32_t slot = S.gbase + t;
     if (t < m) {
         seq = S.rcnt[i] + t - S.fhead[i];
         const uint32_t L = ev.pexcl - S.pstart[i];
@@ -346,19 +365,20 @@ __device__ __noinline__ void k1_flush(K1Smem& S, K1Out O, uint32_t ra, uint32_t 
             prevL = pv.pexcl - S.pstart[i];
             const uint32_t pn = pv.n_type & 0x7fffffffu, pdel = pv.n_type >> 31;
             if (del && pdel) {
-                const uint32_t pos2 = (uint32_t)O.pos[ra + i];
+                const uint32_t pos2 = S.rpos[i];
                 uint32_t fl = 0;
                 if (seq == 1 && abs_diff(pos2 + L, pos2 + prevL + pn) < O.merge_min) fl |= K1_PAIR_MERGE;   // main.rs:615
                 if (abs_diff(pos2 + prevL, pos2 + L + len) < O.merge_min) fl |= K1_FAR_HIT;                 // main.rs:673-678
                 if (fl) atomicOr(&S.rflags[i], fl);
             }
         }
-        const uint32_t slot = S.gbase + t;
-        if (slot < O.max_events) {
+        if (slot < O.raw_cap) {
             uint4* d = reinterpret_cast<uint4*>(O.raw + slot);
             d[0] = make_uint4(S.rkeep[i] ? ra + i : 0xffffffffu, seq, L, ev.n_type);
             d[1] = make_uint4(prevL, 0u, 0u, 0u);
         } else O.ctrl->overflow = 1;
+    } else if (S.in_slab && slot < O.raw_cap) {
+        reinterpret_cast<uint4*>(O.raw + slot)[0] = make_uint4(0xffffffffu, 0u, 0u, 0u);   // unused slab slot
     }
     __syncthreads();                                    // every seq computed before rcnt moves
     if (t < m) {
@@ -370,10 +390,10 @@ __device__ __noinline__ void k1_flush(K1Smem& S, K1Out O, uint32_t ra, uint32_t 
 }
 
 // Rare path of one scan step: rank this step's events over the CTA and stage them (flushing as needed).
-// Block-uniform call.  evm: bit k set = my k-th op is an event.
-__device__ __forceinline__ uint32_t k1_stage_events(K1Smem& S, const K1Out& O, uint32_t ra, uint32_t nr,
-                                                 uint32_t staged, uint32_t evm, const uint32_t* v, const uint32_t* e,
-                                                 uint32_t fp0, uint32_t pbase)
+// Block-uniform call.  evm: bit k set = my k-th op is an event; the per-op prefixes are read back from `pre`.
+__device__ __forceinline__ uint32_t k1_stage_events(K1Smem& S, const K1Out& O, uint32_t tile, uint32_t ra, uint32_t nr,
+                                                    uint32_t staged, uint32_t evm, const uint32_t* v, const uint32_t* pre,
+                                                    uint32_t fp0, uint32_t pbase, uint32_t& spare)
 {
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
     const uint32_t nev = __popc(evm);
@@ -384,147 +404,217 @@ __device__ __forceinline__ uint32_t k1_stage_events(K1Smem& S, const K1Out& O, u
     __syncthreads();
     uint32_t evbase = 0, evtotal = 0;
 #pragma unroll
-    for (int k = 0; k < K1_THREADS / 32; k++) { const uint32_t x = S.evcnt[k]; if ((uint32_t)k < w) evbase += x; evtotal += x; }
-    if (staged + evtotal > K1_CAP && staged) { k1_flush(S, O, ra, nr, staged); staged = 0; }
+    for (int k = 0; k < K1_WARPS; k++) { const uint32_t x = S.evcnt[k]; if ((uint32_t)k < w) evbase += x; evtotal += x; }
+    if (staged + evtotal > K1_CAP && staged) { k1_flush(S, O, tile, ra, nr, staged, spare); staged = 0; }
     const uint32_t my0 = evbase + evincl - nev;                      // rank of my first event in this step
-    for (uint32_t round0 = 0; round0 < evtotal; round0 += K1_CAP) {
+    if (evtotal <= K1_CAP) {                                          // the usual case: everything fits the staging area
+        if (evm) {
+            uint32_t at = staged + my0;
+#pragma unroll
+            for (int k = 0; k < K1_V; k++) {                             // static indices keep v[] in registers
+                if (evm & (1u << k)) {
+                    K1Stage x;
+                    x.fp = fp0 + k; x.pexcl = pbase + pre[k];
+                    x.n_type = (v[k] >> 4) | (((v[k] & 15u) == 2u) ? 0x80000000u : 0u);
+                    x.pad = 0;
+                    S.stage[at++] = x;
+                }
+            }
+        }
+        return staged + evtotal;
+    }
+    for (uint32_t round0 = 0; round0 < evtotal; round0 += K1_CAP) {  // event-dense step: K1_CAP events at a time
         uint32_t rk = my0;
 #pragma unroll
-        for (int k = 0; k < K1_V; k++) {                                 // static indices keep v[] / e[] in registers
+        for (int k = 0; k < K1_V; k++) {
             if (!(evm & (1u << k))) continue;
             if (rk >= round0 && rk < round0 + K1_CAP) {
                 K1Stage x;
-                x.fp = fp0 + k;
-                x.pexcl = pbase + e[k];
+                x.fp = fp0 + k; x.pexcl = pbase + pre[k];
                 x.n_type = (v[k] >> 4) | (((v[k] & 15u) == 2u) ? 0x80000000u : 0u);
                 x.pad = 0;
                 S.stage[staged + rk - round0] = x;
             }
             rk++;
         }
-        const uint32_t nround = min((uint32_t)K1_CAP, evtotal - round0);
-        if (evtotal > K1_CAP) { k1_flush(S, O, ra, nr, staged + nround); staged = 0; }
-        else staged += nround;
+        k1_flush(S, O, tile, ra, nr, staged + min((uint32_t)K1_CAP, evtotal - round0), spare);
+        staged = 0;
     }
     return staged;
 }
 
-__global__ void __launch_bounds__(K1_THREADS, 3) k1_flat(DevBatch B, DevParams P, uint32_t rpc)
+// op code -> flag byte, looked up with one PRMT (selector nibble 0 = op code):
+//   bit0 = consumes the reference in the indel arm (M D N =, main.rs:528-545)   bit1 = I or D (event candidate)
+// Bytes 1..7 carry bit7 so that selectors 9..15 (PRMT sign-replicate mode) read 0xff: bit6 then flags an unknown
+// op code; selector 8 (X) replicates the clear msb of byte 0 and reads 0x00: X neither consumes nor is an event.
+static constexpr uint32_t K1_LUT_LO = 0x81838201u;     // N D I M
+static constexpr uint32_t K1_LUT_HI = 0x81808080u;     // = P H S
+
+// Persistent: CTA b scans tiles b, b + gridDim, b + 2 gridDim, ... (`rpc` records each; interleaved so that a
+// run of event-dense tiles is spread over many CTAs).  All its tile boundaries are fetched up front, so thread 0
+// keeps the TMA ring K1_STAGES chunks ahead of the scan ACROSS tile boundaries; the next tile's per-record
+// offsets, positions and filter inputs are prefetched into registers while the current tile is scanned.
+__global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P, uint32_t rpc, uint32_t n_tiles)
 {
     extern __shared__ __align__(128) unsigned char k1_smem_raw[];
     K1Smem& S = *reinterpret_cast<K1Smem*>(k1_smem_raw);
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const uint32_t ra = blockIdx.x * rpc;
-    if (ra >= B.n_reads) return;
-    const uint32_t nr = min(rpc, B.n_reads - ra);
-    const unsigned long long oa = B.cigar_off[ra], ob = B.cigar_off[ra + nr];
-    const unsigned long long oa4 = oa & ~3ull;
-    const uint32_t span_lo = (uint32_t)(oa - oa4), span_hi = (uint32_t)(ob - oa4);
-    if (ob - oa4 >= 0x80000000ull) { if (t == 0) B.ctrl->overflow = 1; return; }
-    const uint32_t nchunks = (span_hi + K1_CHUNK - 1) / K1_CHUNK;
-    const uint32_t* gsrc = B.cigar + oa4;
-    auto issue = [&](uint32_t c) {
-        const uint32_t first = c * K1_CHUNK;
-        const uint32_t nops = min((uint32_t)K1_CHUNK, span_hi - first);
-        const uint32_t bytes = ((nops * 4u) + 15u) & ~15u;              // the cigar buffer is padded by 16 bytes
-        unsigned long long* bar = &S.full[c % K1_STAGES];
-        mbar_expect_tx(bar, bytes);
-        tma_load_1d(S.buf[c % K1_STAGES], gsrc + first, bytes, bar);
-    };
+    if (blockIdx.x >= n_tiles) return;
+    const uint32_t ntile = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;         // <= K1_MAX_TILES (host)
+    for (uint32_t k = t; k < 2 * ntile; k += K1_THREADS) {
+        const unsigned long long rec = (unsigned long long)(blockIdx.x + (k >> 1) * gridDim.x) * rpc + ((k & 1) ? rpc : 0u);
+        S.tb[k >> 1][k & 1] = B.cigar_off[min(rec, (unsigned long long)B.n_reads)];
+    }
+    uint32_t spare = 0;                                    // thread 0: reserved overflow slab (see k1_flush)
     if (t == 0) {
-        S.has_carry = 0;
         for (int s = 0; s < K1_STAGES; s++) mbar_init(&S.full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (uint32_t c = 0; c < nchunks && c < K1_STAGES; c++) issue(c);       // CIGAR bytes start moving first
+        spare = atomicAdd(&B.ctrl->n_raw, (uint32_t)K1_CAP);
     }
-    // per-record state (overlaps the bulk copies)
-    for (uint32_t i = t; i <= nr; i += K1_THREADS) S.roff[i] = (uint32_t)(B.cigar_off[ra + i] - oa4);
-    if (t < nr) {
-        S.rkeep[t] = keep_record(P, B.flag[ra + t], B.mapq[ra + t]) ? 1u : 0u;
-        S.rcnt[t] = 0; S.rflags[t] = 0; S.fhead[t] = 0; S.pstart[t] = 0;
+    // first tile's per-record inputs straight from global memory; later tiles arrive through the register prefetch
+    unsigned long long pre_off = 0; uint32_t pre_flag = 0, pre_mapq = 0, pre_pos = 0;
+    {
+        const uint32_t ra = blockIdx.x * rpc, nr = min(rpc, B.n_reads - ra);
+        if (t < nr) { pre_off = B.cigar_off[ra + t]; pre_flag = B.flag[ra + t]; pre_mapq = B.mapq[ra + t]; pre_pos = (uint32_t)B.pos[ra + t]; }
     }
     __syncthreads();
 
+    // issue cursor (thread 0): next chunk to request = chunk ic of tile it_i; gi = chunks requested so far
+    uint32_t it_i = 0, ic = 0, gi = 0;
+    auto issue_upto = [&](uint32_t limit) {                // request chunks while fewer than `limit` have been requested
+        while (gi < limit && it_i < ntile) {
+            const unsigned long long oa4 = S.tb[it_i][0] & ~3ull;
+            const uint32_t span_hi = (uint32_t)(S.tb[it_i][1] - oa4);
+            const uint32_t nch = (span_hi + K1_CHUNK - 1) / K1_CHUNK;
+            if (ic >= nch) { it_i++; ic = 0; continue; }
+            const uint32_t first = ic * K1_CHUNK;
+            const uint32_t nops = min((uint32_t)K1_CHUNK, span_hi - first);
+            const uint32_t bytes = ((nops * 4u) + 15u) & ~15u;          // the cigar buffer is padded by 16 bytes
+            unsigned long long* bar = &S.full[gi % K1_STAGES];
+            mbar_expect_tx(bar, bytes);
+            tma_load_1d(S.buf[gi % K1_STAGES], B.cigar + oa4 + first, bytes, bar);
+            gi++; ic++;
+        }
+    };
+    if (t == 0) issue_upto(K1_STAGES);
+
     const uint32_t imin16 = P.indel_min >= (1u << 28) ? 0xffffffffu : (P.indel_min << 4);
-    const K1Out O{B.raw, B.ctrl, B.pos, B.max_events, P.merge_min};
-    uint32_t carry = 0, staged = 0;
-    for (uint32_t c = 0; c < nchunks; c++) {
-        mbar_wait(&S.full[c % K1_STAGES], (c / K1_STAGES) & 1u);
-        uint32_t* buf = S.buf[c % K1_STAGES];
-        const uint32_t fp0 = c * K1_CHUNK + t * K1_V;                    // flat position of my first op
-        uint32_t v[K1_V];
-#pragma unroll
-        for (int k = 0; k < K1_V / 4; k++) {
-            const uint4 q = reinterpret_cast<const uint4*>(buf)[t * (K1_V / 4) + k];
-            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    const K1Out O{B.raw, B.ctrl, B.tile_cnt, B.raw_cap, P.merge_min, B.prim_slots, B.capt_log2};
+    uint32_t gs = 0;                                       // scan steps done by this CTA (= chunks consumed)
+    for (uint32_t it = 0; it < ntile; it++) {
+        const uint32_t tile = blockIdx.x + it * gridDim.x;
+        const uint32_t ra = tile * rpc, nr = min(rpc, B.n_reads - ra);
+        const unsigned long long oa = S.tb[it][0], ob = S.tb[it][1], oa4 = oa & ~3ull;
+        const uint32_t span_lo = (uint32_t)(oa - oa4), span_hi = (uint32_t)(ob - oa4);
+        if (ob - oa4 >= 0x80000000ull) { if (t == 0) B.ctrl->overflow = 1; return; }    // block-uniform
+        const uint32_t nchunks = (span_hi + K1_CHUNK - 1) / K1_CHUNK;
+        // tile state from the prefetched registers
+        if (t < nr) {
+            S.roff[t] = (uint32_t)(pre_off - oa4); S.rkeep[t] = keep_record(P, pre_flag, pre_mapq) ? 1u : 0u; S.rpos[t] = pre_pos;
+            S.rcnt[t] = 0; S.rflags[t] = 0; S.fhead[t] = 0; S.pstart[t] = 0;
         }
-        if (fp0 < span_lo || fp0 + K1_V > span_hi) {                     // CTA edge: blank the ops outside my records
-#pragma unroll
-            for (int k = 0; k < K1_V; k++) if (fp0 + k < span_lo || fp0 + k >= span_hi) v[k] = 0u;
+        if (t == 0) { S.roff[nr] = span_hi; S.has_carry = 0; S.flushes = 0; }
+        __syncthreads();
+        if (it + 1 < ntile) {                              // next tile: loads fly while this tile is scanned
+            const uint32_t ra2 = ra + gridDim.x * rpc, nr2 = min(rpc, B.n_reads - ra2);
+            if (t < nr2) { pre_off = B.cigar_off[ra2 + t]; pre_flag = B.flag[ra2 + t]; pre_mapq = B.mapq[ra2 + t]; pre_pos = (uint32_t)B.pos[ra2 + t]; }
         }
-        // decode: reference-consuming length, event and unknown-op bits (masks indexed by the 4-bit op code)
-        uint32_t e[K1_V], tsum = 0, evm = 0, bad = 0;
+        uint32_t carry = 0, staged = 0;
+        for (uint32_t c = 0; c < nchunks; c++, gs++) {
+            mbar_wait(&S.full[gs % K1_STAGES], (gs / K1_STAGES) & 1u);
+            uint32_t* buf = S.buf[gs % K1_STAGES];
+            uint4* mine4 = reinterpret_cast<uint4*>(buf) + t * (K1_V / 4);
+            const uint32_t fp0 = c * K1_CHUNK + t * K1_V;                // flat position of my first op
+            uint32_t v[K1_V];
 #pragma unroll
-        for (int k = 0; k < K1_V; k++) {
-            const uint32_t op = v[k] & 15u, len = v[k] >> 4;
-            e[k] = tsum;
-            tsum += ((0x8Du >> op) & 1u) * len;                         // M D N =  (main.rs:528-545)
-            if (v[k] >= imin16) evm |= ((0x6u << k) >> op) & (1u << k); // I or D with len >= indel_min (main.rs:553,569)
-            bad |= 0xFE00u >> op;                                       // op code 9..15
-        }
-        uint32_t wincl = tsum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, wincl, d); if (lane >= (uint32_t)d) wincl += o; }
-        const uint32_t wexcl = wincl - tsum;
-        // per-op prefixes (warp-relative) replace the ops in shared memory: record starts read them below
-#pragma unroll
-        for (int k = 0; k < K1_V / 4; k++)
-            reinterpret_cast<uint4*>(buf)[t * (K1_V / 4) + k] =
-                make_uint4(wexcl + e[4 * k], wexcl + e[4 * k + 1], wexcl + e[4 * k + 2], wexcl + e[4 * k + 3]);
-        if (lane == 31) S.wtot[c & 1][w] = wincl;
-        const int any_ev = __syncthreads_or(evm != 0u);
-        // the stage read two steps ago is free now: every thread is past its prefix look-ups
-        if (t == 0 && c >= 1 && c - 1 + K1_STAGES < nchunks) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(c - 1 + K1_STAGES);
-        }
-        // cross-warp prefix: lanes 0..7 scan the eight warp totals
-        uint32_t x = lane < K1_THREADS / 32 ? S.wtot[c & 1][lane] : 0u;
-#pragma unroll
-        for (int d = 1; d < K1_THREADS / 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += o; }
-        const uint32_t total = __shfl_sync(0xffffffffu, x, K1_THREADS / 32 - 1);
-        uint32_t wbase = __shfl_sync(0xffffffffu, x, (w - 1u) & 31u);
-        if (w == 0) wbase = 0;
-        // record starts inside this step: prefix value at the record's first op
-        {
-            const uint32_t ro = t < nr ? S.roff[t] : 0xffffffffu;
-            const uint32_t fb = c * K1_CHUNK;
-            const bool mine = ro >= fb && ro < fb + K1_CHUNK && ro < span_hi;
-            const uint32_t rel = mine ? ro - fb : 0u, wp = rel / (32u * K1_V);
-            uint32_t b2 = __shfl_sync(0xffffffffu, x, (wp - 1u) & 31u);
-            if (wp == 0) b2 = 0;
-            if (mine) S.pstart[t] = carry + b2 + buf[rel];
-        }
-        if (bad & 1u) {                                                  // rust-htslib panics on an unknown op
-#pragma unroll
-            for (int k = 0; k < K1_V; k++) if ((v[k] & 15u) > 8u) {
-                const uint32_t i = k1_find_read(S.roff, nr, fp0 + k);
-                if (S.rkeep[i]) report(B.ctrl, ra + i, RANK_CIGAR_OP);
+            for (int k = 0; k < K1_V / 4; k++) {
+                const uint4 q = mine4[k];
+                v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
             }
+            if (fp0 < span_lo || fp0 + K1_V > span_hi) {                 // tile edge: blank the ops outside my records
+#pragma unroll
+                for (int k = 0; k < K1_V; k++) if (fp0 + k < span_lo || fp0 + k >= span_hi) v[k] = 0u;
+            }
+            // decode; the thread-local exclusive prefixes replace the ops in shared memory as we go
+            uint32_t tsum = 0, evm = 0, flags = 0;
+#pragma unroll
+            for (int g = 0; g < K1_V / 4; g++) {
+                uint32_t e[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int k = 4 * g + q;
+                    uint32_t f;                                          // prmt.b32, not __byte_perm: the intrinsic masks selector bit 3
+                    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(f) : "r"(K1_LUT_LO), "r"(K1_LUT_HI), "r"(v[k]));
+                    e[q] = tsum;
+                    // tsum += consumes ? len : 0 as one multiply-add; evm |= (I or D) && len >= indel_min (main.rs:553,569)
+                    // as one compare + one predicated LOP3.  Spelled in PTX so the 0/1 multiply is not turned into compare+select.
+                    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(tsum) : "r"(f & 1u), "r"(v[k] >> 4));
+                    const uint32_t bit = k ? (f << (k - 1)) : (f >> 1); // bit k <- "I or D"
+                    asm("{\n.reg .pred p;\nsetp.ge.u32 p, %1, %2;\n@p lop3.b32 %0, %3, %4, %0, 0xEA;\n}"
+                        : "+r"(evm) : "r"(v[k]), "r"(imin16), "r"(bit), "r"(1u << k));
+                    flags |= f;
+                }
+                mine4[g] = make_uint4(e[0], e[1], e[2], e[3]);
+            }
+            uint32_t wincl = tsum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, wincl, d); if (lane >= (uint32_t)d) wincl += o; }
+            const uint32_t wexcl = wincl - tsum;
+            S.tpre[gs & 1][t] = wexcl;
+            if (lane == 31) S.wtot[gs & 1][w] = wincl;
+            const int any_ev = __syncthreads_or(evm != 0u);
+            // every stage before this step's is free now (all threads are past their prefix look-ups): top the ring up
+            if (t == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_upto(gs + K1_STAGES);
+            }
+            // cross-warp prefix: the first lanes scan the warp totals
+            uint32_t x = lane < K1_WARPS ? S.wtot[gs & 1][lane] : 0u;
+#pragma unroll
+            for (int d = 1; d < K1_WARPS; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += o; }
+            const uint32_t total = __shfl_sync(0xffffffffu, x, K1_WARPS - 1);
+            uint32_t wbase = __shfl_sync(0xffffffffu, x, (w - 1u) & 31u);
+            if (w == 0) wbase = 0;
+            // record starts inside this step: prefix value at the record's first op
+            {
+                const uint32_t ro = t < nr ? S.roff[t] : 0xffffffffu;
+                const uint32_t fb = c * K1_CHUNK;
+                const bool mine = ro >= fb && ro < fb + K1_CHUNK && ro < span_hi;
+                const uint32_t rel = mine ? ro - fb : 0u, owner = rel / K1_V, wp = owner >> 5;
+                uint32_t b2 = __shfl_sync(0xffffffffu, x, (wp - 1u) & 31u);
+                if (wp == 0) b2 = 0;
+                if (mine) S.pstart[t] = carry + b2 + S.tpre[gs & 1][owner] + buf[rel];
+            }
+            if (flags & 0x40u) {                                         // rust-htslib panics on an unknown op
+#pragma unroll
+                for (int k = 0; k < K1_V; k++) if ((v[k] & 15u) > 8u) {
+                    const uint32_t i = k1_find_read(S.roff, nr, fp0 + k);
+                    if (S.rkeep[i]) report(B.ctrl, ra + i, RANK_CIGAR_OP);
+                }
+            }
+            if (any_ev) staged = k1_stage_events(S, O, tile, ra, nr, staged, evm, v, buf + t * K1_V, fp0, carry + wbase + wexcl, spare);
+            carry += total;
         }
-        if (any_ev) staged = k1_stage_events(S, O, ra, nr, staged, evm, v, e, fp0, carry + wbase + wexcl);
-        carry += total;
+        if (staged) k1_flush(S, O, tile, ra, nr, staged, spare);
+        __syncthreads();
+        for (uint32_t i = t; i <= nr; i += K1_THREADS) if (S.roff[i] >= span_hi) S.pstart[i] = carry;   // trailing empty records + sentinel
+        if (t == 0 && S.flushes == 0) B.tile_cnt[tile] = 0;
+        __syncthreads();
+        if (t < nr) {
+            const uint32_t T = S.pstart[t + 1] - S.pstart[t];
+            const uint32_t info = S.rkeep[t] ? ((S.rcnt[t] & K1_CNT_MASK) | S.rflags[t]) : 0u;
+            B.k1[ra + t] = make_uint2(T, info);
+        }
+        __syncthreads();                                   // the next tile re-initialises the per-record arrays
     }
-    if (staged) k1_flush(S, O, ra, nr, staged);
+    // the slab still held in reserve was never used: blank it
+    const uint32_t last = __shfl_sync(0xffffffffu, spare, 0);
+    __shared__ uint32_t s_last;
+    if (t == 0) s_last = last;
     __syncthreads();
-    for (uint32_t i = t; i <= nr; i += K1_THREADS) if (S.roff[i] >= span_hi) S.pstart[i] = carry;   // trailing empty records + sentinel
-    __syncthreads();
-    if (t < nr) {
-        const uint32_t T = S.pstart[t + 1] - S.pstart[t];
-        const uint32_t info = S.rkeep[t] ? ((S.rcnt[t] & K1_CNT_MASK) | S.rflags[t]) : 0u;
-        B.k1[ra + t] = make_uint2(T, info);
-    }
+    const uint32_t slot = B.prim_slots + s_last + t;
+    if (slot < B.raw_cap) reinterpret_cast<uint4*>(B.raw + slot)[0] = make_uint4(0xffffffffu, 0u, 0u, 0u);
 }
 
 // ======================================================================================
@@ -580,8 +670,9 @@ __global__ void __launch_bounds__(256) k3a_sa_cigar(DevBatch B, DevParams P)
 // (falls back to reading global memory when the range does not fit).
 // ======================================================================================
 static constexpr int K3B_THREADS = 128;
-static constexpr uint32_t K3B_STAGE_BYTES = 32 * 1024;
-static constexpr uint32_t K3B_MAXP = 768;              // segments (records + SA pieces) per tile in the staged layout
+static constexpr int K3B_TILE = 64;                     // SA records per CTA (pieces are then spread over all 128 threads)
+static constexpr uint32_t K3B_STAGE_BYTES = 16 * 1024;
+static constexpr uint32_t K3B_MAXP = 384;              // segments (records + SA pieces) per tile in the staged layout
 
 struct SmemBytes {            // byte i of sa_bytes, served from the staged copy
     const uint8_t* p; uint32_t bias;
@@ -600,13 +691,21 @@ __device__ __forceinline__ bool dev_parse_i64(const Bytes& s, uint32_t b, uint32
     const uint32_t c0 = s[b];
     if (c0 == '+' || c0 == '-') { neg = c0 == '-'; b++; }
     if (b == e) return false;
-    const unsigned long long lim = neg ? (1ull << 63) : (1ull << 63) - 1;
     unsigned long long v = 0;
-    for (; b < e; b++) {
-        const uint32_t d = s[b] - '0';
-        if (d > 9u) return false;
-        if (v > (lim - d) / 10ull) return false;
-        v = v * 10ull + d;
+    if (e - b <= 18u) {                                  // < 10^18: cannot overflow an i64, no per-digit range check
+        for (; b < e; b++) {
+            const uint32_t d = s[b] - '0';
+            if (d > 9u) return false;
+            v = v * 10ull + d;
+        }
+    } else {
+        const unsigned long long lim = neg ? (1ull << 63) : (1ull << 63) - 1;
+        for (; b < e; b++) {
+            const uint32_t d = s[b] - '0';
+            if (d > 9u) return false;
+            if (v > (lim - d) / 10ull) return false;
+            v = v * 10ull + d;
+        }
     }
     *out = neg ? (int64_t)(0ull - v) : (int64_t)v;
     return true;
@@ -650,12 +749,17 @@ __device__ uint32_t dev_parse_piece(const Bytes& s, uint32_t b, uint32_t e, cons
     for (uint32_t i = fb[3]; i < fe[3]; i++) {
         const uint32_t c = s[i], d = c - '0';
         if (d <= 9u) { v = v * 10ull + d; if (v > 0x1ffffffffull) v = 0x1ffffffffull; ndig++; continue; }
-        const bool isop = c == 'M' || c == 'I' || c == 'D' || c == 'N' || c == 'S' || c == 'H' || c == 'P' || c == '=' || c == 'X';
+        // op letters as bits of (c - '='):  = D H I M N P S X  ->  0 7 11 12 16 17 19 22 27
+        const uint32_t x = c - '=';
+        const bool isop = x < 28u && ((0x84B1881u >> x) & 1u);
         if (!isop || ndig == 0 || v > 0xffffffffull) return RANK_SA_CIGAR;
         const uint32_t n = (uint32_t)v;
-        if (c == 'S') sS += n; else if (c == 'H') sH += n; else if (c == 'D') sD += n;
-        else if (c == 'M') sM += n; else if (c == '=') sE += n; else if (c == 'X') sX += n;
-        if (!seenM) { if (c == 'M') seenM = true; else if (c == 'S' || c == 'I' || c == 'X' || c == '=') key += n; }
+        if (c == 'M') { sM += n; seenM = true; }
+        else {
+            if (c == 'S') sS += n; else if (c == 'D') sD += n; else if (c == 'H') sH += n;
+            else if (c == '=') sE += n; else if (c == 'X') sX += n;
+            if (!seenM && ((0x8401001u >> x) & 1u)) key += n;             // = I S X before the first M (utils.rs:33)
+        }
         v = 0; ndig = 0;
     }
     if (!dev_parse_u8(s, fb[4], fe[4])) return RANK_SA_MAPQ;
@@ -841,8 +945,7 @@ struct __align__(16) K3bSmem {
     uint8_t bytes[K3B_STAGE_BYTES];
     Seg segs[K3B_MAXP];
     uint32_t pb[K3B_MAXP], pe[K3B_MAXP];
-    uint32_t rerr[K3B_THREADS];
-    uint32_t sbase[K3B_THREADS + 1];
+    uint32_t rerr[K3B_TILE];
     uint32_t wsum[K3B_THREADS / 32];
     uint8_t pread[K3B_MAXP];
 };
@@ -852,16 +955,16 @@ __global__ void __launch_bounds__(K3B_THREADS) k3b_sa_events(DevBatch B, DevPara
     extern __shared__ __align__(16) unsigned char k3b_smem_raw[];
     K3bSmem& S = *reinterpret_cast<K3bSmem*>(k3b_smem_raw);
     const uint32_t n_sa = B.ctrl->n_sa;
-    const uint32_t n_tiles = (n_sa + K3B_THREADS - 1) / K3B_THREADS;
+    const uint32_t n_tiles = (n_sa + K3B_TILE - 1) / K3B_TILE;
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
     Seg local_segs[kLocalSegs];
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t j0 = tile * K3B_THREADS, j1 = min(j0 + (uint32_t)K3B_THREADS, n_sa);
+        const uint32_t j0 = tile * K3B_TILE, j1 = min(j0 + (uint32_t)K3B_TILE, n_sa);
         const uint32_t span_b = B.sa_off[B.sa_list[j0]], span_e = B.sa_off[B.sa_list[j1 - 1] + 1];
         const uint32_t a0 = span_b & ~15u;
         const bool staged = span_e - a0 <= K3B_STAGE_BYTES;                   // block-uniform
         const uint32_t j = j0 + t;
-        const bool active = j < j1;
+        const bool active = t < K3B_TILE && j < j1;                           // threads 64..127 only help with the pieces
         __syncthreads();                                                      // the previous tile's readers are done
         if (!staged) {
             GlobalBytes s{B.sa_bytes};
@@ -925,7 +1028,6 @@ __global__ void __launch_bounds__(K3B_THREADS) k3b_sa_events(DevBatch B, DevPara
         if (active && !dropped) {
             uint32_t err = S.rerr[t];
             nseg = slots;
-            if (err == 0xffffffffu && nseg - 1 >= (1u << 24)) err = RANK_SPLIT_COUNT;
             if (err != 0xffffffffu) { report(B.ctrl, r, err & 0xffu); nseg = 0; }
             else k3b_record_seg(B, P, j, r, &S.segs[sb]);
         }
@@ -998,36 +1100,45 @@ __global__ void __launch_bounds__(SCAN_THREADS) k4a_line_scan(DevBatch B, DevPar
 // ======================================================================================
 // kernel 4b: ordered compaction into the output event buffer
 // ======================================================================================
+// one raw indel event -> its output line (AlignmentEvent::new, aligments_event.rs:28-57; pair merge main.rs:612-635)
+__device__ __forceinline__ void k4b_indel(const DevBatch& B, const RawEv* src)
+{
+    const uint4 a = reinterpret_cast<const uint4*>(src)[0];
+    const uint32_t r = a.x;
+    if (r == 0xffffffffu) return;
+    const uint32_t csa = B.csa[r];
+    if (csa & CSA_DROP) return;
+    const uint2 k1 = B.k1[r];
+    const uint32_t cnt = k1.y & K1_CNT_MASK;
+    const bool merged = cnt == 2u && (k1.y & K1_PAIR_MERGE);
+    uint32_t seq = a.y;
+    const uint32_t L = a.z, len = a.w & 0x7fffffffu, del = a.w >> 31;
+    const uint32_t pos2 = (uint32_t)B.pos[r];
+    uint32_t ls = pos2, le, rs, re;
+    if (merged) {
+        if (seq == 0) return;
+        const uint32_t prevL = reinterpret_cast<const uint4*>(src)[1].x;
+        le = pos2 + prevL; rs = pos2 + L + len; re = pos2 + k1.x; seq = 0;
+    } else if (del) { le = pos2 + L; rs = pos2 + L + len; re = pos2 + k1.x; }      // rend = pos + total_consume
+    else { le = pos2 + L; rs = pos2 + L; re = pos2 + L + len; }                    // Ins: length on the right (main.rs:570-577)
+    const uint32_t dst = B.line_off[r] + (csa & CSA_CNT_MASK) + seq;
+    if (dst >= B.max_events) return;
+    const uint32_t neg = (B.flag[r] >> 4) & 1u, tid = (uint32_t)B.tid[r];
+    store_event(B.events + dst, (int64_t)ls, (int64_t)le, (int64_t)rs, (int64_t)re, r, tid, tid,
+                EXLR_EV_META(1u, EXLR_KIND_INDEL, neg, neg));
+}
+
 __global__ void __launch_bounds__(256) k4b_place(DevBatch B, DevParams P)
 {
-    const uint32_t n_raw = min(B.ctrl->n_raw, B.max_events), n_sa = B.ctrl->n_sa;
+    const uint32_t n_sa = B.ctrl->n_sa;
     const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    // indel events (AlignmentEvent::new, aligments_event.rs:28-57; merge main.rs:612-635)
-    for (uint32_t x = t0; x < n_raw; x += stride) {
-        const uint4 a = reinterpret_cast<const uint4*>(B.raw + x)[0];
-        const uint32_t r = a.x;
-        if (r == 0xffffffffu) continue;
-        const uint32_t csa = B.csa[r];
-        if (csa & CSA_DROP) continue;
-        const uint2 k1 = B.k1[r];
-        const uint32_t cnt = k1.y & K1_CNT_MASK;
-        const bool merged = cnt == 2u && (k1.y & K1_PAIR_MERGE);
-        uint32_t seq = a.y;
-        const uint32_t L = a.z, len = a.w & 0x7fffffffu, del = a.w >> 31;
-        const uint32_t pos2 = (uint32_t)B.pos[r];
-        uint32_t ls = pos2, le, rs, re;
-        if (merged) {
-            if (seq == 0) continue;
-            const uint32_t prevL = reinterpret_cast<const uint4*>(B.raw + x)[1].x;
-            le = pos2 + prevL; rs = pos2 + L + len; re = pos2 + k1.x; seq = 0;
-        } else if (del) { le = pos2 + L; rs = pos2 + L + len; re = pos2 + k1.x; }      // rend = pos + total_consume
-        else { le = pos2 + L; rs = pos2 + L; re = pos2 + L + len; }                    // Ins: length on the right (main.rs:570-577)
-        const uint32_t dst = B.line_off[r] + (csa & CSA_CNT_MASK) + seq;
-        if (dst >= B.max_events) continue;
-        const uint32_t neg = (B.flag[r] >> 4) & 1u, tid = (uint32_t)B.tid[r];
-        store_event(B.events + dst, (int64_t)ls, (int64_t)le, (int64_t)rs, (int64_t)re, r, tid, tid,
-                    EXLR_EV_META(1u, EXLR_KIND_INDEL, neg, neg));
-    }
+    // indel events, per-tile slices first (slice of tile i = raw[i << capt_log2 ..], tile_cnt[i] entries used) ...
+    const uint32_t capt_mask = (1u << B.capt_log2) - 1u;
+    for (uint32_t x = t0; x < B.prim_slots; x += stride)
+        if ((x & capt_mask) < B.tile_cnt[x >> B.capt_log2]) k4b_indel(B, B.raw + x);
+    // ... then the shared overflow region
+    const uint32_t room = B.raw_cap - B.prim_slots, n_ovf = min(B.ctrl->n_raw, room);
+    for (uint32_t x = t0; x < n_ovf; x += stride) k4b_indel(B, B.raw + B.prim_slots + x);
     // SA-derived events: per record contiguous in the temp buffer, they lead the record's lines
     for (uint32_t j = t0; j < n_sa; j += stride) {
         const uint32_t r = B.sa_list[j];
@@ -1065,6 +1176,22 @@ void launch_k0(const DevBatch& B, const DevParams& P, cudaStream_t st)
     k0_classify<<<tiles, SCAN_THREADS, 0, st>>>(B, P);
 }
 
+// Raw-event layout for this submit: tile slices of 2^capt_log2 slots in the first half of the raw buffer at most,
+// the rest is the atomically allocated overflow region.  Must be applied to the DevBatch before kernels 1 and 4b.
+void plan_k1(DevBatch& B, int variant, uint32_t rpc, uint32_t* tiles_out)
+{
+    if (rpc < 1) rpc = 1;
+    if (rpc > K1_MAX_RPC) rpc = K1_MAX_RPC;
+    const uint32_t n_tiles = (B.n_reads + rpc - 1) / rpc;
+    B.prim_slots = 0; B.capt_log2 = 0;
+    if (variant == 0) {
+        int lg = 7;                                                       // up to K1_CAP = 128 slots per tile
+        while (lg >= 0 && ((unsigned long long)n_tiles << lg) > B.raw_cap / 2) lg--;
+        if (lg >= 0) { B.capt_log2 = (uint32_t)lg; B.prim_slots = n_tiles << lg; }
+    }
+    *tiles_out = n_tiles;
+}
+
 void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc, cudaStream_t st)
 {
     if (variant == 1) {
@@ -1073,8 +1200,10 @@ void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc,
     } else {
         if (rpc < 1) rpc = 1;
         if (rpc > K1_MAX_RPC) rpc = K1_MAX_RPC;
-        const uint32_t blocks = (B.n_reads + rpc - 1) / rpc;
-        k1_flat<<<blocks, K1_THREADS, sizeof(K1Smem), st>>>(B, P, rpc);
+        const uint32_t n_tiles = (B.n_reads + rpc - 1) / rpc;
+        uint32_t grid = min(n_tiles, (uint32_t)g_sm_count * 4u);
+        if ((n_tiles + grid - 1) / grid > K1_MAX_TILES) grid = (n_tiles + K1_MAX_TILES - 1) / K1_MAX_TILES;
+        k1_flat<<<grid, K1_THREADS, sizeof(K1Smem), st>>>(B, P, rpc, n_tiles);
     }
 }
 
@@ -1087,7 +1216,8 @@ void launch_k3a(const DevBatch& B, const DevParams& P, cudaStream_t st)
 
 void launch_k3b(const DevBatch& B, const DevParams& P, cudaStream_t st)
 {
-    const uint32_t gb = min((B.n_reads + 127u) / 128u, (uint32_t)g_sm_count * 3u);
+    // one CTA per tile of 64 SA records; the count lives on the device, so size for the batch and let spare CTAs exit
+    const uint32_t gb = min((B.n_reads + K3B_TILE - 1u) / K3B_TILE, 65535u * 16u);
     k3b_sa_events<<<gb ? gb : 1u, K3B_THREADS, sizeof(K3bSmem), st>>>(B, P);
 }
 

@@ -13,7 +13,7 @@ from randrec import clustered_dels, rand_batch, rand_params, REF_NAMES as RREF
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not gpu_available(), reason="needs a B200")]
 
-VARIANTS = [(0, 0), (0, 1), (0, 3), (0, 64), (0, 256), (1, 0)]       # (cigar kernel, records per CTA)
+VARIANTS = [(0, 0), (0, 1), (0, 3), (0, 64), (0, 128), (1, 0)]       # (cigar kernel, records per CTA)
 
 
 @pytest.mark.parametrize("ka", KA, ids=[k[0] for k in KA])
