@@ -893,7 +893,7 @@ __device__ __forceinline__ void k3b_record_seg(const DevBatch& B, const DevParam
 // Fallback: one SA record parsed start to finish by one thread (used when a tile's SA bytes or segment count do
 // not fit the staged layout, e.g. -k far above the default).  Must be called by every lane of the warp.
 template <class Bytes>
-__device__ __noinline__ void k3b_record(const DevBatch& B, const DevParams& P, const Bytes& s, uint32_t j, bool active, Seg* local_segs)
+__device__ __forceinline__ void k3b_record(const DevBatch& B, const DevParams& P, const Bytes& s, uint32_t j, bool active, Seg* local_segs)
 {
     uint32_t r = 0, nseg = 0, err = 0;
     bool dropped = false;

@@ -1,0 +1,218 @@
+// bam_reader.hpp — minimal multi-threaded BGZF/BAM reader for the record packer.
+//
+// Plays the role rust-htslib/htslib play for the reference (`bam::Reader::from_path`, `set_threads`, `bam.read(&mut record)`:
+// reference src/main.rs:137,155,158): BGZF blocks are inflated on worker threads (zlib), records are walked touching only
+// what the hot path reads — the fixed header (refID, pos, mapq, flag), the CIGAR (with the CG:B,I long-CIGAR restore htslib
+// performs inside bam_read1), the SA aux field and, for -v, the read name.  SEQ/QUAL are skipped.
+#pragma once
+#include <zlib.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace exlr_host {
+
+struct BamRecordView {
+    int32_t tid, pos;
+    uint16_t flag;
+    uint8_t mapq;
+    const uint32_t* cigar; uint32_t n_cigar;     // points into the decompressed stream (or into cg_restore)
+    uint8_t sa_kind;                             // 0 none, 1 Z string, 2 other aux type (include/exlr.h EXLR_SA_*)
+    const uint8_t* sa; uint32_t sa_len;
+    const char* qname; uint32_t qname_len;       // without the trailing NUL
+};
+
+class BamReader {
+public:
+    std::vector<std::string> ref_names;
+    std::vector<int64_t> ref_lens;
+    std::string error;
+
+    ~BamReader() { if (fp_) fclose(fp_); }
+
+    bool open(const std::string& path, int threads)
+    {
+        fp_ = fopen(path.c_str(), "rb");
+        if (!fp_) { error = "cannot open " + path; return false; }
+        threads_ = threads < 1 ? 1 : threads;
+        if (!fill()) { if (error.empty()) error = "empty or truncated BAM"; return false; }
+        return read_header();
+    }
+
+    // Next record; false at EOF or on a read error (the reference stops silently on a read error too: src/main.rs:165-168).
+    bool next(BamRecordView& r)
+    {
+        for (;;) {
+            if (avail() >= 4) {
+                uint32_t bs; memcpy(&bs, cur(), 4);
+                if (bs < 32) { error = "corrupt BAM record"; return false; }
+                if (avail() >= 4 + (size_t)bs) return parse(cur() + 4, bs, r);
+            }
+            if (!fill()) { if (avail() != 0 && error.empty()) error = "truncated BAM"; return false; }
+        }
+    }
+
+private:
+    FILE* fp_ = nullptr;
+    int threads_ = 1;
+    std::vector<uint8_t> buf_;        // decompressed stream window
+    size_t off_ = 0;                  // read cursor inside buf_
+    bool eof_ = false;
+    std::vector<uint32_t> cg_restore_;
+    std::vector<uint8_t> comp_;       // compressed superblock
+    struct Blk { size_t coff, clen, uoff, ulen; };
+
+    const uint8_t* cur() const { return buf_.data() + off_; }
+    size_t avail() const { return buf_.size() - off_; }
+
+    // Read up to ~256 BGZF blocks per thread, inflate them on threads_ workers, append to the stream window.
+    // A truncated or corrupt block ends the stream after the blocks before it (the reference, too, keeps what it had read).
+    bool fill()
+    {
+        if (eof_) return false;
+        if (off_ > 0) { buf_.erase(buf_.begin(), buf_.begin() + (ptrdiff_t)off_); off_ = 0; }
+        comp_.clear();
+        std::vector<Blk> blks;
+        size_t utotal = 0;
+        const size_t kMaxBlocks = 256 * (size_t)threads_;
+        while (blks.size() < kMaxBlocks) {
+            uint8_t h[18];
+            size_t n = fread(h, 1, 18, fp_);
+            if (n == 0) { eof_ = true; break; }
+            if (n < 18 || h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { error = "not a BGZF block"; eof_ = true; break; }
+            // extra subfields: find BC
+            uint16_t xlen; memcpy(&xlen, h + 10, 2);
+            if (xlen < 6) { error = "BGZF block without BC field"; eof_ = true; break; }
+            std::vector<uint8_t> extra(xlen);
+            memcpy(extra.data(), h + 12, xlen < 6 ? xlen : 6);
+            if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, fp_) != (size_t)xlen - 6) { error = "truncated BGZF header"; eof_ = true; break; }
+            int bsize = -1;
+            for (size_t i = 0; i + 4 <= extra.size();) {
+                uint16_t slen; memcpy(&slen, &extra[i + 2], 2);
+                if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2 && i + 6 <= extra.size()) { uint16_t b; memcpy(&b, &extra[i + 4], 2); bsize = b; }
+                i += 4 + slen;
+            }
+            if (bsize < 0) { error = "BGZF block without BC field"; eof_ = true; break; }
+            const size_t total = (size_t)bsize + 1, head = 12 + (size_t)xlen;
+            if (total < head + 8) { error = "corrupt BGZF block size"; eof_ = true; break; }
+            const size_t body = total - head;                     // deflate data + crc32 + isize
+            const size_t at = comp_.size();
+            comp_.resize(at + body);
+            if (fread(comp_.data() + at, 1, body, fp_) != body) { error = "truncated BGZF block"; eof_ = true; break; }
+            uint32_t isize; memcpy(&isize, comp_.data() + at + body - 4, 4);
+            if (isize > 65536) { error = "corrupt BGZF isize"; eof_ = true; break; }
+            blks.push_back({at, body - 8, utotal, isize});
+            utotal += isize;
+        }
+        if (blks.empty()) return false;
+        const size_t base = buf_.size();
+        buf_.resize(base + utotal);
+        std::atomic<size_t> next{0};
+        std::atomic<bool> ok{true};
+        auto work = [&]() {
+            z_stream zs;
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= blks.size()) break;
+                const Blk& b = blks[i];
+                if (b.ulen == 0) continue;
+                memset(&zs, 0, sizeof zs);
+                if (inflateInit2(&zs, -15) != Z_OK) { ok = false; break; }
+                zs.next_in = comp_.data() + b.coff; zs.avail_in = (uInt)b.clen;
+                zs.next_out = buf_.data() + base + b.uoff; zs.avail_out = (uInt)b.ulen;
+                const int rc = inflate(&zs, Z_FINISH);
+                inflateEnd(&zs);
+                if (rc != Z_STREAM_END || zs.avail_out != 0) { ok = false; break; }
+            }
+        };
+        const int nt = (int)std::min<size_t>((size_t)threads_, blks.size());
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+        if (!ok) { error = "BGZF inflate failed"; eof_ = true; buf_.resize(base); return false; }
+        return true;
+    }
+
+    bool need(size_t n) { while (avail() < n) if (!fill()) return false; return true; }
+
+    bool read_header()
+    {
+        if (!need(12)) { error = "truncated BAM header"; return false; }
+        if (memcmp(cur(), "BAM\1", 4) != 0) { error = "not a BAM file (SAM text and CRAM are not supported by this reader)"; return false; }
+        int32_t l_text; memcpy(&l_text, cur() + 4, 4);
+        if (l_text < 0 || !need(12 + (size_t)l_text)) { error = "truncated BAM header"; return false; }
+        int32_t n_ref; memcpy(&n_ref, cur() + 8 + l_text, 4);
+        off_ += 12 + (size_t)l_text;
+        for (int i = 0; i < n_ref; i++) {
+            if (!need(4)) { error = "truncated BAM header"; return false; }
+            int32_t l_name; memcpy(&l_name, cur(), 4);
+            if (l_name < 1 || !need(8 + (size_t)l_name)) { error = "truncated BAM header"; return false; }
+            ref_names.emplace_back((const char*)cur() + 4, (size_t)l_name - 1);
+            int32_t l_ref; memcpy(&l_ref, cur() + 4 + l_name, 4);
+            ref_lens.push_back(l_ref);
+            off_ += 8 + (size_t)l_name;
+        }
+        return true;
+    }
+
+    static size_t aux_size(uint8_t type)
+    {
+        switch (type) { case 'A': case 'c': case 'C': return 1; case 's': case 'S': return 2; case 'i': case 'I': case 'f': return 4; default: return 0; }
+    }
+
+    bool parse(const uint8_t* p, uint32_t bs, BamRecordView& r)
+    {
+        int32_t tid, pos; uint32_t bin_mq_nl, flag_nc, l_seq;
+        memcpy(&tid, p, 4); memcpy(&pos, p + 4, 4); memcpy(&bin_mq_nl, p + 8, 4); memcpy(&flag_nc, p + 12, 4); memcpy(&l_seq, p + 16, 4);
+        const uint32_t l_name = bin_mq_nl & 0xff, n_cigar = flag_nc & 0xffff;
+        r.tid = tid; r.pos = pos; r.mapq = (uint8_t)((bin_mq_nl >> 8) & 0xff); r.flag = (uint16_t)(flag_nc >> 16);
+        size_t o = 32;
+        const size_t fixed = o + l_name + 4 * (size_t)n_cigar + (l_seq + 1) / 2 + l_seq;
+        if (fixed > bs || l_name == 0) { error = "corrupt BAM record"; return false; }
+        r.qname = (const char*)p + o; r.qname_len = l_name - 1; o += l_name;
+        r.cigar = (const uint32_t*)(p + o); r.n_cigar = n_cigar; o += 4 * (size_t)n_cigar;   // 4-byte alignment is not guaranteed: copied below
+        o += (l_seq + 1) / 2 + l_seq;
+        // aux walk: SA (first occurrence, like bam_aux_get) and CG
+        r.sa_kind = 0; r.sa = nullptr; r.sa_len = 0;
+        const uint8_t* cg = nullptr; uint32_t cg_n = 0; bool cg_seen = false;
+        while (o + 3 <= bs) {
+            const uint8_t t0 = p[o], t1 = p[o + 1], ty = p[o + 2];
+            size_t v = o + 3, len;
+            if (ty == 'Z' || ty == 'H') { size_t e = v; while (e < bs && p[e]) e++; if (e >= bs) { error = "corrupt aux"; return false; } len = e - v + 1; }
+            else if (ty == 'B') {
+                if (v + 5 > bs) { error = "corrupt aux"; return false; }
+                const size_t es = aux_size(p[v]); uint32_t cnt; memcpy(&cnt, p + v + 1, 4);
+                if (!es) { error = "corrupt aux"; return false; }
+                len = 5 + es * (size_t)cnt;
+                if (t0 == 'C' && t1 == 'G' && !cg_seen) { cg_seen = true; if (p[v] == 'I' || p[v] == 'i') { cg = p + v + 5; cg_n = cnt; } }
+            } else { len = aux_size(ty); if (!len) { error = "corrupt aux"; return false; } }
+            if (v + len > bs) { error = "corrupt aux"; return false; }
+            if (t0 == 'S' && t1 == 'A' && r.sa_kind == 0) {
+                if (ty == 'Z') { r.sa_kind = 1; r.sa = p + v; r.sa_len = (uint32_t)(len - 1); }
+                else r.sa_kind = 2;
+            }
+            o = v + len;
+        }
+        // CIGAR bytes are only 4-byte aligned by luck: always hand out an aligned copy
+        const uint8_t* src = (const uint8_t*)r.cigar; uint32_t n = n_cigar;
+        // long-CIGAR convention (SAM spec 4.2.2).  Same test as htslib's bam_tag2cigar, which runs inside bam_read1 before the
+        // reference ever sees the record: first op is <l_seq>S, the record is placed, and a CG:B,I (or B,i) aux exists.
+        if (cg && n_cigar > 0 && tid >= 0 && pos >= 0) {
+            uint32_t c0; memcpy(&c0, src, 4);
+            if ((c0 & 15) == 4 && (c0 >> 4) == l_seq) { src = cg; n = cg_n; }
+        }
+        cg_restore_.resize(n);
+        if (n) memcpy(cg_restore_.data(), src, 4 * (size_t)n);
+        r.cigar = cg_restore_.data(); r.n_cigar = n;
+        off_ += 4 + (size_t)bs;
+        return true;
+    }
+};
+
+}  // namespace exlr_host

@@ -1,0 +1,264 @@
+// exlr_main.cpp — `excord-lr-b200`: the reference CLI (reference src/main.rs:29-156) in front of libexlr_cuda.so.
+//
+//   reader thread : BGZF/BAM (-t inflate threads) -> packer -> exlr_submit, batches round-robin over the GPUs
+//   writer thread : exlr_wait in batch order -> exlr_format_lines -> output file (record order)
+//
+// Same flags, same startup messages/exit codes, same output bytes as the reference for BAM input.  There is no CPU
+// path: without a B200 the program exits with the library's error.
+#include <algorithm>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <sys/stat.h>
+#include <thread>
+#include <unistd.h>
+#include <vector>
+
+#include "../../include/exlr.h"
+#include "bam_reader.hpp"
+#include "packer.hpp"
+
+using namespace exlr_host;
+
+struct Cli {
+    std::string bam, out, reference; bool has_reference = false;
+    exlr_params p{};
+    unsigned long long thread = 8;
+    bool not_merge = false, debug = false, verbose = false;
+    int gpus = 0;                       // 0 = all visible
+    unsigned long long batch_reads = 131072, batch_ops = 0, batch_sa = 0;
+};
+
+static void usage(FILE* f)
+{
+    fputs("\nExtract Structural Variation Signals from Long-Read BAMs (B200 build of the signal-extraction path)\n\n"
+          "Usage: excord-lr-b200 [OPTIONS] --bam <BAM> --out <OUT>\n\nOptions:\n"
+          "  -b, --bam <BAM>                          Path to BAM file\n"
+          "  -r, --reference <REFERENCE>              Path to reference, used for CRAM file\n"
+          "  -Q, --mapq <MAPQ>                        Minimal MapQ [default: 1]\n"
+          "  -F, --exclude-flag <EXCLUDE_FLAG>        Exclude Flags [default: 1796]\n"
+          "  -S, --exclude-secondary                  Exclude Secondary Alignment\n"
+          "  -U, --exclude-unmapped                   Exclude Unmapped Alignment\n"
+          "  -t, --thread <THREAD>                    Threads [default: 8]\n"
+          "  -i, --indel-min <INDEL_MIN>              Minimal length to define an SV events in CIGAR [default: 50]\n"
+          "  -m, --merge-min <MERGE_MIN>              Threshold to merge two adjacent events [default: 5]\n"
+          "      --ins-clip-min <INS_CLIP_MIN>        Minimal length of hard-clip and soft-clip to define a large insertion signal [default: 1000]\n"
+          "  -n, --not-merge                          Not merge (accepted and ignored, as in the reference)\n"
+          "  -o, --out <OUT>                          Output file name\n"
+          "  -s, --split-only                         Only report split-read event\n"
+          "  -p, --max-pct-overlap <MAX_PCT_OVERLAP>  Percent of overlap to discard a potential false positive record [default: 0] (alias: --pct-overlap)\n"
+          "  -k, --max-supp-alignm <MAX_SUPP_ALIGNM>  Maximal number of SA to include a record [default: 4]\n"
+          "  -d, --debug                              Debug\n"
+          "  -v, --verbose                            Verbose output\n"
+          "      --gpus <N>                           GPUs to shard batches over [default: all visible]\n"
+          "      --batch-reads <N>                    Records per GPU batch [default: 131072]\n"
+          "  -h, --help                               Print help\n"
+          "  -V, --version                            Print version\n", f);
+}
+
+static bool parse_u(const char* s, unsigned long long max, unsigned long long* out)
+{
+    if (!s || !*s) return false;
+    char* e = nullptr;
+    if (*s == '-') return false;
+    unsigned long long v = strtoull(s, &e, 10);
+    if (*e || v > max) return false;
+    *out = v; return true;
+}
+
+static int parse_cli(int argc, char** argv, Cli& c)
+{
+    exlr_params_default(&c.p);
+    bool have_bam = false, have_out = false;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i], val; bool has_val = false;
+        if (a.rfind("--", 0) == 0) { size_t eq = a.find('='); if (eq != std::string::npos) { val = a.substr(eq + 1); a = a.substr(0, eq); has_val = true; } }
+        else if (a.size() > 2 && a[0] == '-' ) { val = a.substr(2); a = a.substr(0, 2); has_val = true; }      // -Q1
+        auto value = [&](const char** out) -> bool { if (has_val) { *out = val.c_str(); return true; } if (i + 1 < argc) { *out = argv[++i]; return true; } return false; };
+        auto flagopt = [&](bool* b) -> bool { if (has_val && a.size() == 2) { fprintf(stderr, "error: unexpected value for '%s'\n", a.c_str()); return false; } *b = true; return true; };
+        const char* v = nullptr; unsigned long long u = 0;
+#define NEEDV() do { if (!value(&v)) { fprintf(stderr, "error: a value is required for '%s'\n", a.c_str()); return 2; } } while (0)
+#define NUM(max) do { NEEDV(); if (!parse_u(v, (max), &u)) { fprintf(stderr, "error: invalid value '%s' for '%s'\n", v, a.c_str()); return 2; } } while (0)
+        if (a == "-b" || a == "--bam") { NEEDV(); c.bam = v; have_bam = true; }
+        else if (a == "-o" || a == "--out") { NEEDV(); c.out = v; have_out = true; }
+        else if (a == "-r" || a == "--reference") { NEEDV(); c.reference = v; c.has_reference = true; }
+        else if (a == "-Q" || a == "--mapq") { NUM(255); c.p.mapq = (uint8_t)u; }
+        else if (a == "-F" || a == "--exclude-flag") { NUM(65535); c.p.exclude_flag = (uint16_t)u; }
+        else if (a == "-S" || a == "--exclude-secondary") { bool b; if (!flagopt(&b)) return 2; c.p.exclude_secondary = 1; }
+        else if (a == "-U" || a == "--exclude-unmapped") { bool b; if (!flagopt(&b)) return 2; c.p.exclude_unmapped = 1; }
+        else if (a == "-t" || a == "--thread") { NUM(~0ull); c.thread = u; }
+        else if (a == "-i" || a == "--indel-min") { NUM(0xffffffffull); c.p.indel_min = (uint32_t)u; }      // -i belongs to indel_min
+        else if (a == "-m" || a == "--merge-min") { NUM(0xffffffffull); c.p.merge_min = (uint32_t)u; }
+        else if (a == "--ins-clip-min") { NUM(0xffffffffull); c.p.ins_clip_min = (uint32_t)u; }
+        else if (a == "-n" || a == "--not-merge") { if (!flagopt(&c.not_merge)) return 2; }                   // never read by the reference
+        else if (a == "-s" || a == "--split-only") { bool b; if (!flagopt(&b)) return 2; c.p.split_only = 1; }
+        else if (a == "-p" || a == "--max-pct-overlap" || a == "--pct-overlap") {
+            NEEDV(); char* e = nullptr; double d = strtod(v, &e);
+            if (e == v || *e) { fprintf(stderr, "error: invalid value '%s' for '%s'\n", v, a.c_str()); return 2; }
+            c.p.max_pct_overlap = d;
+        }
+        else if (a == "-k" || a == "--max-supp-alignm") { NUM(~0ull); c.p.max_supp_alignm = u; }
+        else if (a == "-d" || a == "--debug") { if (!flagopt(&c.debug)) return 2; }
+        else if (a == "-v" || a == "--verbose") { if (!flagopt(&c.verbose)) return 2; }
+        else if (a == "--gpus") { NUM(64); c.gpus = (int)u; }
+        else if (a == "--batch-reads") { NUM(1ull << 30); c.batch_reads = u ? u : 1; }
+        else if (a == "-h" || a == "--help") { usage(stdout); return -1; }
+        else if (a == "-V" || a == "--version") { puts("excord-LR 0.1.17"); return -1; }
+        else { fprintf(stderr, "error: unexpected argument '%s' found\n\nFor more information, try '--help'.\n", argv[i]); return 2; }
+    }
+    if (!have_bam || !have_out) {
+        fprintf(stderr, "error: the following required arguments were not provided:\n%s%s\nFor more information, try '--help'.\n",
+                have_bam ? "" : "  --bam <BAM>\n", have_out ? "" : "  --out <OUT>\n");
+        return 2;
+    }
+    return 0;
+}
+
+static bool is_file(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode); }
+static bool is_dir(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode); }
+
+struct Slot {
+    exlr_batch* b = nullptr; PackedBatch pk; int gpu = 0;
+};
+
+int main(int argc, char** argv)
+{
+    Cli cli;
+    int rc = parse_cli(argc, argv, cli);
+    if (rc < 0) return 0;
+    if (rc) return rc;
+    if (cli.debug)          // println!("{:?}", &cli)  (src/main.rs:109-111)
+        printf("Cli { bam: \"%s\", reference: %s%s%s, mapq: %u, exclude_flag: %u, exclude_secondary: %s, exclude_unmapped: %s, thread: %llu, "
+               "indel_min: %u, merge_min: %u, ins_clip_min: %u, not_merge: %s, out: \"%s\", split_only: %s, max_pct_overlap: %.1f, "
+               "max_supp_alignm: %llu, debug: true, verbose: %s }\n",
+               cli.bam.c_str(), cli.has_reference ? "Some(\"" : "None", cli.has_reference ? cli.reference.c_str() : "", cli.has_reference ? "\")" : "",
+               cli.p.mapq, cli.p.exclude_flag, cli.p.exclude_secondary ? "true" : "false", cli.p.exclude_unmapped ? "true" : "false", cli.thread,
+               cli.p.indel_min, cli.p.merge_min, cli.p.ins_clip_min, cli.not_merge ? "true" : "false", cli.out.c_str(),
+               cli.p.split_only ? "true" : "false", cli.p.max_pct_overlap, (unsigned long long)cli.p.max_supp_alignm, cli.verbose ? "true" : "false");
+    // startup checks: messages on stdout, exit 1 (src/main.rs:113-151)
+    if (!is_file(cli.bam)) { printf("Ivalid BAM file path: %s \n", cli.bam.c_str()); return 1; }
+    {
+        std::string parent;
+        size_t sl = cli.out.find_last_of('/');
+        parent = sl == std::string::npos ? "" : (sl == 0 ? "/" : cli.out.substr(0, sl));
+        std::string abs = parent;
+        if (parent.empty() || parent[0] != '/') { char cwd[4096]; if (getcwd(cwd, sizeof cwd)) abs = std::string(cwd) + (parent.empty() ? "" : "/" + parent); }
+        if (!is_dir(abs)) { printf("Output directory does not exists: %s \n", abs.c_str()); return 1; }
+    }
+    FILE* fo = fopen(cli.out.c_str(), "wb");                 // created before the BAM is opened (src/main.rs:135 vs 137)
+    if (!fo) { fprintf(stderr, "cannot create %s\n", cli.out.c_str()); return 101; }
+    {
+        std::string low = cli.bam; std::transform(low.begin(), low.end(), low.begin(), ::tolower);
+        if (low.find(".cram") != std::string::npos) {
+            if (!cli.has_reference) { puts("excord-lr is running on CRAM file, reference(-r) is required."); return 1; }
+            fputs("CRAM input is not supported by this build (BAM only)\n", stderr); return 1;
+        }
+    }
+    if (cli.thread == 0) { fputs("thread pool of 0 threads: the reference panics here\n", stderr); return 101; }
+
+    BamReader rd;
+    if (!rd.open(cli.bam, (int)std::min<unsigned long long>(cli.thread, 256))) { fprintf(stderr, "%s\n", rd.error.c_str()); return 101; }
+
+    int ndev = exlr_device_count();
+    if (ndev <= 0) { fprintf(stderr, "no usable B200: %s (%s)\n", exlr_strerror(EXLR_ERR_CUDA), exlr_last_cuda_error()); return 3; }
+    if (cli.gpus > 0) ndev = std::min(ndev, cli.gpus);
+    std::vector<const char*> names; for (auto& s : rd.ref_names) names.push_back(s.c_str());
+    std::vector<exlr_ctx*> ctx(ndev, nullptr);
+    for (int g = 0; g < ndev; g++) {
+        rc = exlr_create(&cli.p, g, names.data(), (int)names.size(), &ctx[g]);
+        if (rc) { fprintf(stderr, "exlr_create(device %d): %s (%s)\n", g, exlr_strerror(rc), exlr_last_cuda_error()); return 3; }
+    }
+    const unsigned long long R = cli.batch_reads;
+    const unsigned long long OPS = cli.batch_ops ? cli.batch_ops : std::max<unsigned long long>(R * 64, 4ull << 20);
+    const unsigned long long SAB = cli.batch_sa ? cli.batch_sa : std::max<unsigned long long>(R * 64, 1ull << 20);
+    const int per_gpu = 3;
+    std::vector<Slot> slots((size_t)ndev * per_gpu);
+    for (size_t i = 0; i < slots.size(); i++) {
+        slots[i].gpu = (int)(i % ndev);
+        rc = exlr_batch_alloc(ctx[slots[i].gpu], R, OPS, SAB, 4 * R + 4096, &slots[i].b);
+        if (rc) { fprintf(stderr, "exlr_batch_alloc: %s (%s)\n", exlr_strerror(rc), exlr_last_cuda_error()); return 3; }
+        exlr_batch_get_views(slots[i].b, &slots[i].pk.v);
+        slots[i].pk.keep_qnames = cli.verbose;
+        slots[i].pk.reset();
+    }
+
+    // submitted batches travel to the writer in submission order; free slots travel back
+    std::mutex mu; std::condition_variable cv;
+    std::deque<int> inflight, freeq; bool done = false; int fatal = 0;
+    for (size_t i = 0; i < slots.size(); i++) freeq.push_back((int)i);
+
+    std::thread writer([&]() {
+        std::vector<char> text;
+        for (;;) {
+            int si;
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !inflight.empty() || done; }); if (inflight.empty()) return; si = inflight.front(); inflight.pop_front(); }
+            Slot& s = slots[si];
+            exlr_result res;
+            int st = exlr_wait(s.b, &res);
+            if (st != 0 && st > -10) { fprintf(stderr, "exlr_wait: %s (%s)\n", exlr_strerror(st), exlr_last_cuda_error()); std::lock_guard<std::mutex> lk(mu); fatal = 3; cv.notify_all(); return; }
+            uint64_t n_ev = res.n_events;
+            if (st <= -10) n_ev = res.line_off[res.err_read];            // the lines of the records before the failing one
+            const char* qn = cli.verbose ? s.pk.qnames.data() : nullptr;
+            static const char kEmpty = 0;
+            if (cli.verbose && !qn) qn = &kEmpty;
+            int64_t need = exlr_format_lines(ctx[s.gpu], s.b, &res, 0, n_ev, cli.verbose, qn, cli.verbose ? s.pk.qname_off.data() : nullptr, nullptr, 0);
+            if (need > 0) {
+                text.resize((size_t)need);
+                exlr_format_lines(ctx[s.gpu], s.b, &res, 0, n_ev, cli.verbose, qn, cli.verbose ? s.pk.qname_off.data() : nullptr, text.data(), (uint64_t)need);
+                fwrite(text.data(), 1, (size_t)need, fo);
+            }
+            if (st <= -10) {
+                fflush(fo);
+                fprintf(stderr, "excord-lr-b200: record %u of a batch: %s\n", res.err_read, exlr_strerror(st));
+                std::lock_guard<std::mutex> lk(mu); fatal = 101; cv.notify_all(); return;
+            }
+            { std::lock_guard<std::mutex> lk(mu); freeq.push_back(si); }
+            cv.notify_all();
+        }
+    });
+
+    auto acquire = [&]() -> int {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !freeq.empty() || fatal; });
+        if (fatal) return -1;
+        int si = freeq.front(); freeq.pop_front(); return si;
+    };
+    auto submit = [&](int si) -> bool {
+        Slot& s = slots[si];
+        int st = exlr_submit(s.b, s.pk.n);
+        if (st) { fprintf(stderr, "exlr_submit: %s (%s)\n", exlr_strerror(st), exlr_last_cuda_error()); std::lock_guard<std::mutex> lk(mu); fatal = 3; cv.notify_all(); return false; }
+        { std::lock_guard<std::mutex> lk(mu); inflight.push_back(si); }
+        cv.notify_all();
+        return true;
+    };
+
+    // free slots come back in submission order, and slot i always belongs to GPU i % ndev: batches alternate over the GPUs
+    int cur = acquire();
+    BamRecordView r;
+    uint64_t n_rec = 0;
+    while (cur >= 0 && rd.next(r)) {
+        n_rec++;
+        PackedBatch* pk = &slots[cur].pk;
+        if (!pk->fits(r)) {
+            if (pk->n == 0 || !pk->can_ever_fit(r)) { fprintf(stderr, "record %llu does not fit a batch (CIGAR ops %u, SA bytes %u): raise --batch-reads\n", (unsigned long long)n_rec, r.n_cigar, r.sa_len); std::lock_guard<std::mutex> lk(mu); fatal = 3; break; }
+            if (!submit(cur)) break;
+            cur = acquire();
+            if (cur < 0) break;
+            pk = &slots[cur].pk; pk->reset();
+        }
+        pk->push(r);
+    }
+    if (cur >= 0 && !fatal && slots[cur].pk.n) submit(cur);
+    { std::lock_guard<std::mutex> lk(mu); done = true; }
+    cv.notify_all();
+    writer.join();
+    fclose(fo);
+    for (auto& s : slots) exlr_batch_free(s.b);
+    for (auto c : ctx) exlr_destroy(c);
+    return fatal;
+}

@@ -1,0 +1,67 @@
+"""Reader + packer (host C++, no GPU): synthetic batch -> BAM (Python writer) -> exlr_bam_dump -> identical batch."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from excord_lr_b200 import bamio, synth
+from excord_lr_b200.batch import pack_records
+from randrec import rand_batch, REF_NAMES
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DUMP = os.path.join(ROOT, "excord_lr_b200", "host", "exlr_bam_dump")
+
+
+def _build():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "excord_lr_b200", "host"), "exlr_bam_dump"], stdout=subprocess.DEVNULL)
+
+
+def _roundtrip(hb, tmp_path, threads=4, **kw):
+    _build()
+    bam, out = str(tmp_path / "x.bam"), str(tmp_path / "x.bin")
+    bamio.write_bam(hb, bam, **kw)
+    subprocess.check_call([DUMP, bam, out, str(threads)])
+    got = bamio.load_dump(out)
+    for f in ("cigar", "cigar_off", "pos", "tid", "flag", "mapq", "sa_kind", "sa_off", "sa_bytes"):
+        assert np.array_equal(getattr(got, f), getattr(hb, f)), f
+    assert got.ref_names == hb.ref_names
+    return got
+
+
+def test_roundtrip_config0(tmp_path):
+    hb = synth.with_qnames(synth.config(0, 0.2))
+    got = _roundtrip(hb, tmp_path, ref_lens=synth.ref_lens())
+    assert got.qnames == hb.qnames
+
+
+def test_roundtrip_random_records_with_seq_and_threads(tmp_path):
+    hb = rand_batch(11, 400, qnames=True)
+    hb.tid[hb.tid >= len(REF_NAMES)] = 0
+    _roundtrip(hb, tmp_path, threads=1, seq_len=37, block=4000)      # small blocks: records straddle BGZF blocks
+    _roundtrip(hb, tmp_path, threads=8, seq_len=0, level=6)
+
+
+def test_long_cigar_cg_tag_restore(tmp_path):
+    # > 65 535 ops: written as <l_seq>S<reflen>N + CG:B,I, restored by the reader like htslib's bam_read1
+    rng = np.random.default_rng(3)
+    ops = ((rng.integers(1, 30, 70000).astype(np.uint32) << 4) | rng.choice([0, 1, 2], 70000).astype(np.uint32)).tolist()
+    hb = pack_records([dict(tid=0, pos=100, flag=0, mapq=60, cigar=ops, sa="chr1,5,+,10M,3,0;"),
+                       dict(tid=1, pos=7, flag=16, mapq=1, cigar="5S10M")], REF_NAMES)
+    got = _roundtrip(hb, tmp_path)
+    assert int(got.cigar_off[1]) == 70000
+
+
+def test_truncated_bam_stops_quietly(tmp_path):
+    # the reference breaks out of its loop on a read error and exits 0 with what it had (src/main.rs:165-168)
+    _build()
+    hb = synth.config(0, 0.2)
+    bam = str(tmp_path / "t.bam")
+    bamio.write_bam(hb, bam, block=8000)
+    data = open(bam, "rb").read()
+    open(bam, "wb").write(data[: len(data) * 2 // 3])
+    rc = subprocess.call([DUMP, bam, str(tmp_path / "t.bin"), "2"], stderr=subprocess.DEVNULL)
+    assert rc == 4
+    got = bamio.load_dump(str(tmp_path / "t.bin"))
+    n = got.n_reads
+    assert 0 < n < hb.n_reads and np.array_equal(got.pos, hb.pos[:n])

@@ -1,0 +1,92 @@
+"""The CLI front end (host C++).  Startup behaviour is checked without a GPU; the full BAM -> event file runs are GPU tests
+and must reproduce the oracle's bytes exactly."""
+import os
+import subprocess
+
+import pytest
+
+import oracle_c
+from excord_lr_b200 import bamio, synth
+from excord_lr_b200.batch import ExlrParams, pack_records
+from gpu_helpers import gpu_available
+from randrec import REF_NAMES
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "excord_lr_b200", "host", "excord-lr-b200")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "excord_lr_b200", "host")], stdout=subprocess.DEVNULL)
+
+
+def run(args, **kw):
+    return subprocess.run([EXE] + args, capture_output=True, text=True, **kw)
+
+
+def test_startup_messages_and_exit_codes(tmp_path):
+    # reference src/main.rs:113-134: messages go to stdout, exit code 1
+    r = run(["-b", str(tmp_path / "nope.bam"), "-o", str(tmp_path / "o.txt")])
+    assert r.returncode == 1 and r.stdout == f"Ivalid BAM file path: {tmp_path / 'nope.bam'} \n"
+    bam = tmp_path / "x.bam"
+    bam.write_bytes(b"")
+    r = run(["-b", str(bam), "-o", str(tmp_path / "missing_dir" / "o.txt")])
+    assert r.returncode == 1 and r.stdout == f"Output directory does not exists: {tmp_path / 'missing_dir'} \n"
+    cram = tmp_path / "x.cram"
+    cram.write_bytes(b"")
+    r = run(["-b", str(cram), "-o", str(tmp_path / "o.txt")])
+    assert r.returncode == 1 and r.stdout == "excord-lr is running on CRAM file, reference(-r) is required.\n"
+    assert (tmp_path / "o.txt").exists()            # the output file is created before the input is opened (main.rs:135)
+    assert run(["-V"]).stdout == "excord-LR 0.1.17\n"
+    assert run(["--help"]).returncode == 0
+    assert run(["-o", "x"]).returncode == 2 and run(["-b", "x", "-o", "y", "--bogus"]).returncode == 2
+
+
+def test_debug_prints_parsed_cli(tmp_path):
+    r = run(["-d", "-b", str(tmp_path / "nope.bam"), "-o", str(tmp_path / "o.txt"), "-Q", "3", "-i", "30", "-n", "-p", "0.8", "-k8"])
+    assert r.stdout.startswith('Cli { bam: "') and "mapq: 3" in r.stdout and "indel_min: 30" in r.stdout
+    assert "not_merge: true" in r.stdout and "max_pct_overlap: 0.8" in r.stdout and "max_supp_alignm: 8" in r.stdout
+
+
+gpu = [pytest.mark.gpu, pytest.mark.skipif(not gpu_available(), reason="needs a B200")]
+
+
+def _expect(hb, p, verbose=False):
+    r = oracle_c.run(hb, p)
+    return r, oracle_c.format_lines(hb, r.events if r.status == 0 else r.events[:int(r.line_off[r.err_read])], verbose)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not gpu_available(), reason="needs a B200")
+@pytest.mark.parametrize("extra,params,verbose", [
+    (["-p", "0.8"], dict(max_pct_overlap=0.8), False),
+    (["-p", "0.8", "-v", "--batch-reads", "777"], dict(max_pct_overlap=0.8), True),
+    (["--pct-overlap=0.8", "-s", "-k", "8", "-t", "2", "--batch-reads", "100"], dict(max_pct_overlap=0.8, split_only=True, max_supp_alignm=8), False),
+    (["-i", "30", "-n", "-Q", "0", "-F", "0", "-S", "-U", "--ins-clip-min", "40"], dict(indel_min=30, mapq=0, exclude_flag=0, exclude_secondary=True, exclude_unmapped=True, ins_clip_min=40), True),
+])
+def test_bam_to_event_file_matches_oracle(tmp_path, extra, params, verbose):
+    hb = synth.with_qnames(synth.config(0, 1.0))
+    if params.get("exclude_flag") == 0:
+        hb.tid[hb.tid < 0] = 0                      # with -F 0 an unplaced record would reach contig() and panic
+    bam, out = str(tmp_path / "c1.bam"), str(tmp_path / "c1.txt")
+    bamio.write_bam(hb, bam, ref_lens=synth.ref_lens(), seq_len=11)
+    r = run(["-b", bam, "-o", out] + extra)
+    assert r.returncode == 0, r.stderr
+    want_r, want = _expect(hb, ExlrParams.make(**params), verbose)
+    assert want_r.status == 0 and len(want) > 1000
+    assert open(out, "rb").read() == want
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not gpu_available(), reason="needs a B200")
+def test_reference_panic_gives_partial_output_and_exit_101(tmp_path):
+    recs = [dict(tid=0, pos=100 + i, flag=0, mapq=60, cigar="100M60D200M", qname="a%d" % i) for i in range(500)]
+    recs[321] = dict(tid=0, pos=5, flag=0, mapq=60, cigar="10M", sa="chr1,5,*,10M,3,0;", qname="bad")
+    hb = pack_records(recs, REF_NAMES)
+    bam, out = str(tmp_path / "p.bam"), str(tmp_path / "p.txt")
+    bamio.write_bam(hb, bam)
+    r = run(["-b", bam, "-o", out, "--batch-reads", "64"])
+    assert r.returncode == 101 and "strand" in r.stderr
+    want_r, want = _expect(hb, ExlrParams.make())
+    assert want_r.status == -14 and want_r.err_read == 321
+    assert open(out, "rb").read() == want

@@ -213,3 +213,15 @@ def test_full_size_config1_checksums():
     assert res.line_off[0] == 0 and res.line_off[-1] == res.n_events
     assert (np.diff(res.events["read_idx"].astype(np.int64)) >= 0).all()
     assert np.array_equal(np.bincount(res.events["read_idx"], minlength=hb.n_reads), np.diff(res.line_off.astype(np.int64)))
+
+
+def test_round_robin_shards_reassemble_in_order():
+    # the N-GPU host logic with the real extractor as the runner (two "ranks" emulated on one device)
+    from excord_lr_b200 import shard
+    hb = synth.config(0, 0.5)
+    p = ExlrParams.make(**synth.CONFIGS[0]["params"])
+    plan = shard.plan_batches(hb.n_reads, 611)
+    runner = lambda h: api.extract(h, p)[1]
+    parts = [shard.run_rank(hb, plan, r, 2, runner) for r in range(2)]
+    want = oracle_c.run(hb, p)
+    assert shard.merge_ordered(parts) == oracle_c.format_lines(hb, want.events)
