@@ -215,6 +215,16 @@ def main():
     clocks = sampler.stop()
     total_ms = float(np.sum(step_ms))
 
+    # ---------------- PCIe ceiling: one pinned 256 MB host->device copy, best of 10 ----------------
+    pin = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    dev = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pcie_h2d = 0.0
+    for _ in range(10):
+        e0.record(); dev.copy_(pin, non_blocking=True); e1.record(); torch.cuda.synchronize()
+        pcie_h2d = max(pcie_h2d, (256 << 20) / (e0.elapsed_time(e1) / 1e3) / 1e9)
+    del pin, dev
+
     # ---------------- end to end through the public API, host buffers ----------------
     parts = split_for_pipeline(hb, max(1, args.pipeline_parts))
     pbatches = [ex.batch_for(h) for h in parts]                              # pinned views already hold the packed records
@@ -284,7 +294,8 @@ def main():
                        "cigar_kernel": "flat TMA-staged block scan" if args.cigar_kernel == 0 else "warp per record"},
             "e2e": {"value": e2e_value, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms_max / args.steps, "pipeline_parts": len(parts),
-                    "h2d_gbs": h2d * args.steps / (e2e_ms_max / 1e3) / 1e9,
+                    "h2d_gbs": h2d * args.steps / (e2e_ms_max / 1e3) / 1e9, "pcie_h2d_peak_gbs": pcie_h2d,
+                    "frac_of_pcie": (h2d * args.steps / (e2e_ms_max / 1e3) / 1e9) / pcie_h2d if pcie_h2d else None,
                     "cigar_ops_per_sec": C_all / (e2e_ms_max / 1e3) * args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k1_flat" if args.cigar_kernel == 0 else "k1_warp", "achieved": achieved,

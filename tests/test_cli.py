@@ -62,7 +62,7 @@ def _expect(hb, p, verbose=False):
     (["-p", "0.8"], dict(max_pct_overlap=0.8), False),
     (["-p", "0.8", "-v", "--batch-reads", "777"], dict(max_pct_overlap=0.8), True),
     (["--pct-overlap=0.8", "-s", "-k", "8", "-t", "2", "--batch-reads", "100"], dict(max_pct_overlap=0.8, split_only=True, max_supp_alignm=8), False),
-    (["-i", "30", "-n", "-Q", "0", "-F", "0", "-S", "-U", "--ins-clip-min", "40"], dict(indel_min=30, mapq=0, exclude_flag=0, exclude_secondary=True, exclude_unmapped=True, ins_clip_min=40), True),
+    (["-i", "30", "-n", "-Q", "0", "-F", "0", "-S", "-U", "--ins-clip-min", "40", "--verbose"], dict(indel_min=30, mapq=0, exclude_flag=0, exclude_secondary=True, exclude_unmapped=True, ins_clip_min=40), True),
 ])
 def test_bam_to_event_file_matches_oracle(tmp_path, extra, params, verbose):
     hb = synth.with_qnames(synth.config(0, 1.0))
