@@ -56,6 +56,10 @@ struct exlr_batch {
     uint32_t launches = 0;
 };
 
+// kernel 1 reserves overflow slabs of 128 raw slots ahead of use (one spare per persistent CTA, see k1_flush): room for
+// them on top of the caller's max_events so that only real events can exhaust the buffer
+static constexpr size_t kRawHeadroom = 256 * 1024;
+
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 extern "C" {
@@ -184,7 +188,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
 {
     if (!c || !out) return EXLR_ERR_ARG;
     *out = nullptr;
-    if (max_reads == 0 || max_reads >= 0xfffffff0ull || max_sa_bytes >= 0x7ffffff0ull || max_events >= 0xfffffff0ull) return EXLR_ERR_ARG;
+    if (max_reads == 0 || max_reads >= 0xfffffff0ull || max_sa_bytes >= 0x7ffffff0ull || max_events >= 0xfff00000ull) return EXLR_ERR_ARG;
     if (max_events == 0) max_events = 2 * max_reads + 1024;
     CK(cudaSetDevice(c->device));
     exlr_batch* b = new (std::nothrow) exlr_batch();
@@ -222,7 +226,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     const size_t d_cigar = dcarve((max_ops + 4) * 4 + 16), d_coff = dcarve((R + 1) * 8), d_pos = dcarve(R * 4), d_tid = dcarve(R * 4),
                  d_flag = dcarve(R * 2), d_mapq = dcarve(R), d_kind = dcarve(R), d_soff = dcarve((R + 1) * 4), d_sab = dcarve(max_sa_bytes + 16),
                  d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
-                 d_raw = dcarve(max_events * sizeof(RawEv)), d_saev = dcarve(max_events * sizeof(exlr_event)),
+                 d_raw = dcarve((max_events + kRawHeadroom) * sizeof(RawEv)), d_saev = dcarve(max_events * sizeof(exlr_event)),
                  d_pool = dcarve(pool_cap * sizeof(Seg)), d_loff = dcarve((R + 1) * 4), d_ev = dcarve(max_events * sizeof(exlr_event));
     e = cudaMalloc(&b->d_slab, dof);
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaMalloc(batch)"); }
@@ -235,7 +239,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     v.tid = (int32_t*)(ds + d_tid); v.flag = (uint16_t*)(ds + d_flag); v.mapq = (uint8_t*)(ds + d_mapq); v.sa_kind = (uint8_t*)(ds + d_kind);
     v.sa_off = (uint32_t*)(ds + d_soff); v.sa_bytes = (uint8_t*)(ds + d_sab);
     v.ref_bytes = c->d_ref_bytes; v.ref_off = c->d_ref_off; v.n_ref = c->n_ref;
-    v.tile_cnt = (uint32_t*)(ds + d_tcnt); v.raw_cap = (uint32_t)max_events;
+    v.tile_cnt = (uint32_t*)(ds + d_tcnt); v.raw_cap = (uint32_t)(max_events + kRawHeadroom);
     v.k1 = (uint2*)(ds + d_k1); v.csa = (uint32_t*)(ds + d_csa); v.sa_list = (uint32_t*)(ds + d_list); v.sa_base = (uint32_t*)(ds + d_base);
     v.sa_sum = (SaSum*)(ds + d_sum); v.raw = (RawEv*)(ds + d_raw); v.sa_ev = (exlr_event*)(ds + d_saev);
     v.seg_pool = (Seg*)(ds + d_pool); v.seg_pool_cap = (uint32_t)pool_cap;

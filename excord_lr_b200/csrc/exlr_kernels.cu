@@ -288,7 +288,7 @@ static constexpr int K1_THREADS = 128;
 static constexpr int K1_WARPS = K1_THREADS / 32;
 static constexpr int K1_V = 16;                        // consecutive ops per thread per scan step
 static constexpr int K1_CHUNK = K1_THREADS * K1_V;     // ops per TMA bulk copy = per scan step (8 KB)
-static constexpr int K1_STAGES = 5;                    // ring of bulk-copy stages (40 KB), kept full across tiles
+static constexpr int K1_STAGES = 3;                    // ring of bulk-copy stages (24 KB), kept full across tiles
 static constexpr int K1_MAX_RPC = K1_THREADS;          // records per tile (thread t owns record t)
 static constexpr int K1_CAP = K1_THREADS;              // staged events per flush (one per thread)
 static constexpr int K1_MAX_TILES = 256;               // tiles per CTA
@@ -454,7 +454,7 @@ static constexpr uint32_t K1_LUT_HI = 0x81808080u;     // = P H S
 // run of event-dense tiles is spread over many CTAs).  All its tile boundaries are fetched up front, so thread 0
 // keeps the TMA ring K1_STAGES chunks ahead of the scan ACROSS tile boundaries; the next tile's per-record
 // offsets, positions and filter inputs are prefetched into registers while the current tile is scanned.
-__global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P, uint32_t rpc, uint32_t n_tiles)
+__global__ void __launch_bounds__(K1_THREADS, 6) k1_flat(DevBatch B, DevParams P, uint32_t rpc, uint32_t n_tiles)
 {
     extern __shared__ __align__(128) unsigned char k1_smem_raw[];
     K1Smem& S = *reinterpret_cast<K1Smem*>(k1_smem_raw);
@@ -620,43 +620,85 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
 // ======================================================================================
 // kernel 3a: SA records' own CIGAR -> clip sums, reference span, first-match offset
 // ======================================================================================
-__global__ void __launch_bounds__(256) k3a_sa_cigar(DevBatch B, DevParams P)
+// One record's CIGAR walked by a group of G lanes (G = 8: a quarter warp per short record; G = 32: the whole warp for a
+// long one).  Returns the reduced sums in every lane of the group.
+struct K3aAcc { uint32_t S, H, D, M, E, X; unsigned long long ffm; };
+
+template <int G>
+__device__ __forceinline__ K3aAcc k3a_walk(const DevBatch& B, uint32_t r, unsigned long long o0, unsigned long long o1, uint32_t gmask, uint32_t gshift)
 {
-    const uint32_t n_sa = B.ctrl->n_sa;
-    const uint32_t sub = threadIdx.x & 7, grp_in_warp = (threadIdx.x & 31) >> 3;
-    const uint32_t gmask = 0xffu << (grp_in_warp * 8);
-    const uint32_t groups = (gridDim.x * blockDim.x) >> 3;
-    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; j < n_sa; j += groups) {
-        const uint32_t r = B.sa_list[j];
-        const unsigned long long o0 = B.cigar_off[r], o1 = B.cigar_off[r + 1];
-        uint32_t sS = 0, sH = 0, sD = 0, sM = 0, sE = 0, sX = 0;
-        unsigned long long ffm = 0; bool seenM = false;
-        for (unsigned long long b = o0; b < o1; b += 8) {
-            const bool valid = b + sub < o1;
-            const uint32_t v = valid ? __ldg(B.cigar + b + sub) : 0xfu;      // 0xf: not an op
+    const uint32_t sub = threadIdx.x & (G - 1);
+    K3aAcc a{0, 0, 0, 0, 0, 0, 0};
+    bool seenM = false;
+    constexpr int U = G == 32 ? 8 : 1;                                         // loads in flight per lane on the long path
+    for (unsigned long long b = o0; b < o1; b += (unsigned long long)G * U) {
+        uint32_t vv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const unsigned long long at = b + (unsigned long long)u * G + sub;
+            vv[u] = at < o1 ? __ldg(B.cigar + at) : 0xfu;                     // 0xf: not an op
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool valid = b + (unsigned long long)u * G + sub < o1;
+            const uint32_t v = vv[u];
             const uint32_t op = v & 15u, len = v >> 4;
             if (valid && op > 8u) report(B.ctrl, r, RANK_CIGAR_OP);
-            sM += op == 0u ? len : 0u; sD += op == 2u ? len : 0u; sS += op == 4u ? len : 0u;
-            sH += op == 5u ? len : 0u; sE += op == 7u ? len : 0u; sX += op == 8u ? len : 0u;
-            const uint32_t mb = (__ballot_sync(gmask, valid && op == 0u) >> (grp_in_warp * 8)) & 0xffu;
+            a.M += op == 0u ? len : 0u; a.D += op == 2u ? len : 0u; a.S += op == 4u ? len : 0u;
+            a.H += op == 5u ? len : 0u; a.E += op == 7u ? len : 0u; a.X += op == 8u ? len : 0u;
             if (!seenM) {                                                      // utils.rs:28-29 stops at the first M
-                const bool before = (mb & ((1u << sub) - 1u)) == 0u && !(mb & (1u << sub));
-                if (valid && before && (op == 4u || op == 1u || op == 8u || op == 7u)) ffm += len;   // S I X =  (utils.rs:33)
+                const uint32_t mb = (__ballot_sync(gmask, valid && op == 0u) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+                const bool before = (mb & ((2u << sub) - 1u)) == 0u;          // no M at or before my lane
+                if (valid && before && (op == 4u || op == 1u || op == 8u || op == 7u)) a.ffm += len;   // S I X =  (utils.rs:33)
                 if (mb) seenM = true;
             }
         }
+    }
 #pragma unroll
-        for (int d = 1; d < 8; d <<= 1) {
-            sS += __shfl_xor_sync(gmask, sS, d); sH += __shfl_xor_sync(gmask, sH, d); sD += __shfl_xor_sync(gmask, sD, d);
-            sM += __shfl_xor_sync(gmask, sM, d); sE += __shfl_xor_sync(gmask, sE, d); sX += __shfl_xor_sync(gmask, sX, d);
-            ffm += __shfl_xor_sync(gmask, ffm, d);
+    for (int d = 1; d < G; d <<= 1) {
+        a.S += __shfl_xor_sync(gmask, a.S, d); a.H += __shfl_xor_sync(gmask, a.H, d); a.D += __shfl_xor_sync(gmask, a.D, d);
+        a.M += __shfl_xor_sync(gmask, a.M, d); a.E += __shfl_xor_sync(gmask, a.E, d); a.X += __shfl_xor_sync(gmask, a.X, d);
+        a.ffm += __shfl_xor_sync(gmask, a.ffm, d);
+    }
+    return a;
+}
+
+__device__ __forceinline__ void k3a_store(const DevBatch& B, uint32_t j, const K3aAcc& a)
+{
+    SaSum o;
+    o.S = a.S; o.H = a.H;
+    o.refspan = (int64_t)a.D + (int64_t)a.M + (int64_t)a.E + (int64_t)a.X;
+    o.ffm = (int64_t)a.ffm; o.pad[0] = o.pad[1] = 0;
+    B.sa_sum[j] = o;
+}
+
+static constexpr uint32_t K3A_LONG = 96;       // CIGARs longer than this are walked by the whole warp
+
+// Each warp takes four consecutive SA-list entries: short CIGARs are walked by the four 8-lane groups side by side,
+// long ones (ONT: 10^3..10^5 ops) by all 32 lanes one after the other, so the loads stay 128-byte coalesced.
+__global__ void __launch_bounds__(256) k3a_sa_cigar(DevBatch B, DevParams P)
+{
+    const uint32_t n_sa = B.ctrl->n_sa;
+    const uint32_t lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+    const uint32_t gmask = 0xffu << (grp * 8);
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t j0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4; j0 < n_sa; j0 += warps * 4) {
+        const uint32_t j = j0 + grp;
+        const bool have = j < n_sa;
+        uint32_t r = 0; unsigned long long o0 = 0, o1 = 0;
+        if (have) { r = B.sa_list[j]; o0 = B.cigar_off[r]; o1 = B.cigar_off[r + 1]; }
+        const bool is_long = have && (o1 - o0) > K3A_LONG;
+        if (have && !is_long) {
+            const K3aAcc a = k3a_walk<8>(B, r, o0, o1, gmask, grp * 8);
+            if (sub == 0) k3a_store(B, j, a);
         }
-        if (sub == 0) {
-            SaSum o;
-            o.S = sS; o.H = sH;
-            o.refspan = (int64_t)sD + (int64_t)sM + (int64_t)sE + (int64_t)sX;
-            o.ffm = (int64_t)ffm; o.pad[0] = o.pad[1] = 0;
-            B.sa_sum[j] = o;
+        uint32_t longs = __ballot_sync(0xffffffffu, is_long && sub == 0);     // one bit per group (lanes 0, 8, 16, 24)
+        while (longs) {
+            const int src = __ffs(longs) - 1; longs &= longs - 1;
+            const uint32_t rr = __shfl_sync(0xffffffffu, r, src);
+            const unsigned long long a0 = __shfl_sync(0xffffffffu, o0, src), a1 = __shfl_sync(0xffffffffu, o1, src);
+            const K3aAcc a = k3a_walk<32>(B, rr, a0, a1, 0xffffffffu, 0);
+            if (lane == 0) k3a_store(B, j0 + (src >> 3), a);
         }
     }
 }
@@ -1178,6 +1220,8 @@ void launch_k0(const DevBatch& B, const DevParams& P, cudaStream_t st)
 
 // Raw-event layout for this submit: tile slices of 2^capt_log2 slots in the first half of the raw buffer at most,
 // the rest is the atomically allocated overflow region.  Must be applied to the DevBatch before kernels 1 and 4b.
+static constexpr uint32_t kRawSlabHeadroom = 256 * 1024;   // = kRawHeadroom in exlr_abi.cu
+
 void plan_k1(DevBatch& B, int variant, uint32_t rpc, uint32_t* tiles_out)
 {
     if (rpc < 1) rpc = 1;
@@ -1186,7 +1230,7 @@ void plan_k1(DevBatch& B, int variant, uint32_t rpc, uint32_t* tiles_out)
     B.prim_slots = 0; B.capt_log2 = 0;
     if (variant == 0) {
         int lg = 7;                                                       // up to K1_CAP = 128 slots per tile
-        while (lg >= 0 && ((unsigned long long)n_tiles << lg) > B.raw_cap / 2) lg--;
+        while (lg >= 0 && ((unsigned long long)n_tiles << lg) > (B.raw_cap - kRawSlabHeadroom) / 2) lg--;
         if (lg >= 0) { B.capt_log2 = (uint32_t)lg; B.prim_slots = n_tiles << lg; }
     }
     *tiles_out = n_tiles;
@@ -1201,7 +1245,7 @@ void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc,
         if (rpc < 1) rpc = 1;
         if (rpc > K1_MAX_RPC) rpc = K1_MAX_RPC;
         const uint32_t n_tiles = (B.n_reads + rpc - 1) / rpc;
-        uint32_t grid = min(n_tiles, (uint32_t)g_sm_count * 4u);
+        uint32_t grid = min(n_tiles, (uint32_t)g_sm_count * 6u);
         if ((n_tiles + grid - 1) / grid > K1_MAX_TILES) grid = (n_tiles + K1_MAX_TILES - 1) / K1_MAX_TILES;
         k1_flat<<<grid, K1_THREADS, sizeof(K1Smem), st>>>(B, P, rpc, n_tiles);
     }
