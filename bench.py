@@ -146,6 +146,8 @@ def main():
     ap.add_argument("--reads-per-cta", type=int, default=0)
     ap.add_argument("--pipeline-parts", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run kernel 1 on the same stream as the SA branch")
+    ap.add_argument("--k1-ctas", type=int, default=0, help="persistent CTAs of kernel 1 per SM (1..4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -180,6 +182,10 @@ def main():
     ex = api.Extractor(p, hb.ref_names, local_rank)
     ex.set_option(api.EXLR_OPT_CIGAR_KERNEL, args.cigar_kernel)
     ex.set_option(api.EXLR_OPT_READS_PER_CTA, args.reads_per_cta)
+    if args.no_overlap:
+        ex.set_option(api.EXLR_OPT_OVERLAP, 0)
+    if args.k1_ctas:
+        ex.set_option(api.EXLR_OPT_K1_CTAS_PER_SM, args.k1_ctas)
 
     # ---------------- device-resident: value + roofline ----------------
     big = ex.batch_for(hb)

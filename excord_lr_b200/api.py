@@ -21,6 +21,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libexlr_cuda.so")
 
 EXLR_OPT_CIGAR_KERNEL = 1
 EXLR_OPT_READS_PER_CTA = 2
+EXLR_OPT_OVERLAP = 3
+EXLR_OPT_K1_CTAS_PER_SM = 4
 CIGAR_KERNEL_FLAT, CIGAR_KERNEL_WARP = 0, 1
 
 

@@ -37,13 +37,15 @@ struct exlr_ctx {
     std::vector<std::string> ref_stripped;     // "chr" removed (aligments_event.rs:38-42)
     uint8_t* d_ref_bytes = nullptr; uint32_t* d_ref_off = nullptr; int n_ref = 0;
     int cigar_kernel = 0;                      // EXLR_OPT_CIGAR_KERNEL
+    int overlap = 1;                           // EXLR_OPT_OVERLAP: kernel 1 on a second stream beside the SA branch
     uint32_t reads_per_cta = 0;                // EXLR_OPT_READS_PER_CTA (0 = auto)
 };
 
 struct exlr_batch {
     exlr_ctx* ctx = nullptr;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: kernel 1 runs beside the SA branch (kernels 0, 3a, 3b)
     cudaEvent_t ev[EV_COUNT] = {};
+    cudaEvent_t ev_fork = nullptr, ev_k1_begin = nullptr, ev_k1_end = nullptr;
     exlr_batch_views hv{};                     // pinned host views
     void* h_slab = nullptr;                    // pinned: inputs
     void* h_out = nullptr;                     // pinned: ctrl + line_off + events
@@ -168,6 +170,8 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
     switch (option) {
     case EXLR_OPT_CIGAR_KERNEL: if (value != 0 && value != 1) return EXLR_ERR_ARG; c->cigar_kernel = (int)value; return EXLR_OK;
     case EXLR_OPT_READS_PER_CTA: if (value < 0 || value > 128) return EXLR_ERR_ARG; c->reads_per_cta = (uint32_t)value; return EXLR_OK;
+    case EXLR_OPT_OVERLAP: c->overlap = value != 0; return EXLR_OK;
+    case EXLR_OPT_K1_CTAS_PER_SM: if (value < 1 || value > 4) return EXLR_ERR_ARG; set_k1_ctas_per_sm((int)value); return EXLR_OK;
     default: return EXLR_ERR_ARG;
     }
 }
@@ -178,6 +182,10 @@ void exlr_batch_free(exlr_batch* b)
     cudaSetDevice(b->ctx->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (auto& e : b->ev) if (e) cudaEventDestroy(e);
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_k1_begin) cudaEventDestroy(b->ev_k1_begin);
+    if (b->ev_k1_end) cudaEventDestroy(b->ev_k1_end);
+    if (b->stream2) cudaStreamDestroy(b->stream2);
     if (b->stream) cudaStreamDestroy(b->stream);
     cudaFree(b->d_slab);
     cudaFreeHost(b->h_slab); cudaFreeHost(b->h_out);
@@ -246,6 +254,10 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     v.line_off = (uint32_t*)(ds + d_loff); v.events = (exlr_event*)(ds + d_ev);
     v.n_reads = 0; v.max_events = (uint32_t)max_events;
     e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev_fork);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev_k1_begin);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev_k1_end);
     for (int i = 0; i < EV_COUNT && e == cudaSuccess; i++) e = cudaEventCreate(&b->ev[i]);
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "stream/event creation"); }
     *out = b;
@@ -299,20 +311,35 @@ static int run_kernels(exlr_batch* b)
     exlr_ctx* c = b->ctx; cudaStream_t st = b->stream; DevBatch& d = b->dv;
     b->launches = 0;
     CK(cudaMemsetAsync(d.ctrl, 0, b->ctrl_bytes, st));
-    launch_k0(d, c->dparams, st); b->launches++;
-    CK(cudaEventRecord(b->ev[EV_K0], st));
+    // kernel 1 needs nothing from kernel 0, so it runs on a second stream beside the SA branch (0 -> 3a -> 3b); 4a joins them
     d.prim_slots = 0; d.capt_log2 = 0;
+    const bool overlap = c->overlap && !c->params.split_only;
     if (!c->params.split_only) {
         const uint32_t rpc = c->reads_per_cta ? c->reads_per_cta : auto_rpc(b->n_reads, b->n_ops);
         uint32_t n_tiles = 0;
         plan_k1(d, c->cigar_kernel, rpc, &n_tiles);
+        if (overlap) {
+            CK(cudaEventRecord(b->ev_fork, st));
+            CK(cudaStreamWaitEvent(b->stream2, b->ev_fork, 0));
+            CK(cudaEventRecord(b->ev_k1_begin, b->stream2));
+            launch_k1(d, c->dparams, c->cigar_kernel, rpc, b->stream2); b->launches++;
+            CK(cudaEventRecord(b->ev_k1_end, b->stream2));
+        }
+    }
+    launch_k0(d, c->dparams, st); b->launches++;
+    CK(cudaEventRecord(b->ev[EV_K0], st));
+    if (!c->params.split_only && !overlap) {
+        const uint32_t rpc = c->reads_per_cta ? c->reads_per_cta : auto_rpc(b->n_reads, b->n_ops);
+        CK(cudaEventRecord(b->ev_k1_begin, st));
         launch_k1(d, c->dparams, c->cigar_kernel, rpc, st); b->launches++;
+        CK(cudaEventRecord(b->ev_k1_end, st));
     }
     CK(cudaEventRecord(b->ev[EV_K1], st));
     launch_k3a(d, c->dparams, st); b->launches++;
     CK(cudaEventRecord(b->ev[EV_K3A], st));
     launch_k3b(d, c->dparams, st); b->launches++;
     CK(cudaEventRecord(b->ev[EV_K3B], st));
+    if (overlap) CK(cudaStreamWaitEvent(st, b->ev_k1_end, 0));
     launch_k4a(d, c->dparams, st); b->launches++;
     CK(cudaEventRecord(b->ev[EV_K4A], st));
     launch_k4b(d, c->dparams, st); b->launches++;
@@ -423,7 +450,7 @@ int exlr_get_timing(exlr_batch* b, exlr_timing* t)
     CK(cudaEventSynchronize(b->ev[EV_D2H]));
     CK(cudaEventElapsedTime(&t->h2d_ms, b->ev[EV_START], b->ev[EV_H2D]));
     CK(cudaEventElapsedTime(&t->classify_ms, b->ev[EV_H2D], b->ev[EV_K0]));
-    CK(cudaEventElapsedTime(&t->cigar_ms, b->ev[EV_K0], b->ev[EV_K1]));
+    if (b->ctx->params.split_only) t->cigar_ms = 0.f; else CK(cudaEventElapsedTime(&t->cigar_ms, b->ev_k1_begin, b->ev_k1_end));
     CK(cudaEventElapsedTime(&t->sa_cigar_ms, b->ev[EV_K1], b->ev[EV_K3A]));
     CK(cudaEventElapsedTime(&t->sa_parse_ms, b->ev[EV_K3A], b->ev[EV_K3B]));
     CK(cudaEventElapsedTime(&t->scan_ms, b->ev[EV_K3B], b->ev[EV_K4A]));

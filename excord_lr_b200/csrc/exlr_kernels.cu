@@ -288,7 +288,7 @@ static constexpr int K1_THREADS = 128;
 static constexpr int K1_WARPS = K1_THREADS / 32;
 static constexpr int K1_V = 16;                        // consecutive ops per thread per scan step
 static constexpr int K1_CHUNK = K1_THREADS * K1_V;     // ops per TMA bulk copy = per scan step (8 KB)
-static constexpr int K1_STAGES = 3;                    // ring of bulk-copy stages (24 KB), kept full across tiles
+static constexpr int K1_STAGES = 5;                    // ring of bulk-copy stages (40 KB), kept full across tiles
 static constexpr int K1_MAX_RPC = K1_THREADS;          // records per tile (thread t owns record t)
 static constexpr int K1_CAP = K1_THREADS;              // staged events per flush (one per thread)
 static constexpr int K1_MAX_TILES = 256;               // tiles per CTA
@@ -454,7 +454,7 @@ static constexpr uint32_t K1_LUT_HI = 0x81808080u;     // = P H S
 // run of event-dense tiles is spread over many CTAs).  All its tile boundaries are fetched up front, so thread 0
 // keeps the TMA ring K1_STAGES chunks ahead of the scan ACROSS tile boundaries; the next tile's per-record
 // offsets, positions and filter inputs are prefetched into registers while the current tile is scanned.
-__global__ void __launch_bounds__(K1_THREADS, 6) k1_flat(DevBatch B, DevParams P, uint32_t rpc, uint32_t n_tiles)
+__global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P, uint32_t rpc, uint32_t n_tiles)
 {
     extern __shared__ __align__(128) unsigned char k1_smem_raw[];
     K1Smem& S = *reinterpret_cast<K1Smem*>(k1_smem_raw);
@@ -1198,6 +1198,8 @@ __global__ void __launch_bounds__(256) k4b_place(DevBatch B, DevParams P)
 // launchers (called by the host ABI layer)
 // ======================================================================================
 static int g_sm_count = 148;
+static int g_k1_ctas_per_sm = 4;
+void set_k1_ctas_per_sm(int n) { g_k1_ctas_per_sm = n < 1 ? 1 : (n > 4 ? 4 : n); }
 
 size_t k1_flat_smem_bytes() { return sizeof(K1Smem); }
 
@@ -1245,7 +1247,7 @@ void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc,
         if (rpc < 1) rpc = 1;
         if (rpc > K1_MAX_RPC) rpc = K1_MAX_RPC;
         const uint32_t n_tiles = (B.n_reads + rpc - 1) / rpc;
-        uint32_t grid = min(n_tiles, (uint32_t)g_sm_count * 6u);
+        uint32_t grid = min(n_tiles, (uint32_t)g_sm_count * (uint32_t)g_k1_ctas_per_sm);
         if ((n_tiles + grid - 1) / grid > K1_MAX_TILES) grid = (n_tiles + K1_MAX_TILES - 1) / K1_MAX_TILES;
         k1_flat<<<grid, K1_THREADS, sizeof(K1Smem), st>>>(B, P, rpc, n_tiles);
     }
