@@ -144,7 +144,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--cigar-kernel", type=int, default=0, help="0 flat TMA scan (default), 1 warp per record")
     ap.add_argument("--reads-per-cta", type=int, default=0)
-    ap.add_argument("--pipeline-parts", type=int, default=8)
+    ap.add_argument("--pipeline-parts", type=int, default=2, help="sub-batches in flight for the e2e measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run kernel 1 on the same stream as the SA branch")
     ap.add_argument("--k1-ctas", type=int, default=0, help="persistent CTAs of kernel 1 per SM (1..4)")

@@ -284,6 +284,13 @@ static int copy_inputs(exlr_batch* b, uint64_t n)
     const exlr_batch_views& h = b->hv; DevBatch& d = b->dv; cudaStream_t st = b->stream;
     const uint64_t ops = h.cigar_off[n], sab = h.sa_off[n];
     if (ops) CK(cudaMemcpyAsync((void*)d.cigar, h.cigar, ops * 4, cudaMemcpyHostToDevice, st));
+    if (n == h.max_reads) {
+        // a full batch: cigar_off .. sa_off are carved back to back with the same relative offsets on both sides, one copy moves them all
+        const size_t bytes = (size_t)((const char*)(h.sa_off + n + 1) - (const char*)h.cigar_off);
+        CK(cudaMemcpyAsync((void*)d.cigar_off, h.cigar_off, bytes, cudaMemcpyHostToDevice, st));
+        if (sab) CK(cudaMemcpyAsync((void*)d.sa_bytes, h.sa_bytes, sab, cudaMemcpyHostToDevice, st));
+        return EXLR_OK;
+    }
     CK(cudaMemcpyAsync((void*)d.cigar_off, h.cigar_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync((void*)d.pos, h.pos, n * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync((void*)d.tid, h.tid, n * 4, cudaMemcpyHostToDevice, st));

@@ -716,14 +716,33 @@ static constexpr int K3B_TILE = 64;                     // SA records per CTA (p
 static constexpr uint32_t K3B_STAGE_BYTES = 16 * 1024;
 static constexpr uint32_t K3B_MAXP = 384;              // segments (records + SA pieces) per tile in the staged layout
 
-struct SmemBytes {            // byte i of sa_bytes, served from the staged copy
+struct SmemBytes {            // byte i of sa_bytes, served from the staged copy (bias is a multiple of 16)
+    static constexpr bool kWords = true;
     const uint8_t* p; uint32_t bias;
     __device__ __forceinline__ uint32_t operator[](uint32_t i) const { return p[i - bias]; }
+    // the aligned 32-bit word holding byte i (little endian: byte i is bits 8*(i&3)..)
+    __device__ __forceinline__ uint32_t word(uint32_t i) const { return *reinterpret_cast<const uint32_t*>(p + ((i - bias) & ~3u)); }
 };
 struct GlobalBytes {
+    static constexpr bool kWords = false;
     const uint8_t* p;
     __device__ __forceinline__ uint32_t operator[](uint32_t i) const { return __ldg(p + i); }
+    __device__ __forceinline__ uint32_t word(uint32_t i) const { return 0u; }
 };
+
+// SWAR: 0x80 in every byte of x that equals c (exact: no carries cross byte lanes)
+__device__ __forceinline__ uint32_t swar_eq(uint32_t x, uint32_t c4)
+{
+    const uint32_t y = x ^ c4;
+    return ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y | 0x7f7f7f7fu);
+}
+// keep only the flag bits of the bytes whose absolute index is in [lo, hi); w0 = absolute index of the word's byte 0
+__device__ __forceinline__ uint32_t swar_clip(uint32_t z, uint32_t w0, uint32_t lo, uint32_t hi)
+{
+    if (w0 < lo) z &= 0xffffffffu << (8u * (lo - w0));
+    if (w0 + 4u > hi) z &= 0xffffffffu >> (8u * (w0 + 4u - hi));
+    return z;
+}
 
 template <class Bytes>
 __device__ __forceinline__ bool dev_parse_i64(const Bytes& s, uint32_t b, uint32_t e, int64_t* out)
@@ -774,10 +793,24 @@ template <class Bytes>
 __device__ uint32_t dev_parse_piece(const Bytes& s, uint32_t b, uint32_t e, const DevParams& P, Seg* out)
 {
     uint32_t fb[6], fe[6], nf = 0, st = b;
-    for (uint32_t i = b; i <= e; i++) {
-        if (i == e || s[i] == ',') {
-            if (nf < 6) { fb[nf] = st; fe[nf] = i; }
-            nf++; st = i + 1;
+    if constexpr (Bytes::kWords) {                       // four bytes per step: find the commas with SWAR compares
+        for (uint32_t w0 = b & ~3u; w0 < e; w0 += 4u) {
+            uint32_t z = swar_clip(swar_eq(s.word(w0), 0x2c2c2c2cu), w0, b, e);
+            while (z) {
+                const uint32_t i = w0 + ((uint32_t)(__ffs((int)z) - 1) >> 3);
+                z &= z - 1u;
+                if (nf < 6) { fb[nf] = st; fe[nf] = i; }
+                nf++; st = i + 1;
+            }
+        }
+        if (nf < 6) { fb[nf] = st; fe[nf] = e; }
+        nf++;
+    } else {
+        for (uint32_t i = b; i <= e; i++) {
+            if (i == e || s[i] == ',') {
+                if (nf < 6) { fb[nf] = st; fe[nf] = i; }
+                nf++; st = i + 1;
+            }
         }
     }
     if (nf < 6) return RANK_SA_FIELDS;
@@ -1022,10 +1055,20 @@ __global__ void __launch_bounds__(K3B_THREADS) k3b_sa_events(DevBatch B, DevPara
         __syncthreads();
         SmemBytes s{S.bytes, a0};
         if (active) {
-            unsigned long long pieces = 1; uint32_t nonempty = 0, pbeg = b0;
+            unsigned long long pieces = 1; uint32_t nonempty = 0;
             if (is_str) {
-                for (uint32_t i = b0; i < e0; i++) if (s[i] == ';') { pieces++; nonempty += i > pbeg; pbeg = i + 1; }
-                nonempty += e0 > pbeg;
+                // pieces = #';' + 1; a piece is empty when its ';' follows another ';' or starts the string, or when it is the
+                // (missing) piece after a trailing ';'.  Four bytes per step.
+                uint32_t empties = (e0 == b0 || s[e0 - 1] == ';') ? 1u : 0u, carry = 0;
+                for (uint32_t w0 = b0 & ~3u; w0 < e0; w0 += 4u) {
+                    const uint32_t zz = swar_clip(swar_eq(s.word(w0), 0x3b3b3b3bu), w0, b0, e0) >> 7;     // 0x01 per ';'
+                    uint32_t prev = (zz << 8) | carry;
+                    if (w0 <= b0) prev |= 1u << (8u * (b0 - w0));            // the first byte follows the start of the string
+                    pieces += __popc(zz);
+                    empties += __popc(zz & prev);
+                    carry = zz >> 24;
+                }
+                nonempty = (uint32_t)pieces - empties;
                 if (pieces > P.max_supp_alignm) dropped = true;               // main.rs:311-313
             }
             slots = dropped ? 0u : 1u + nonempty;
@@ -1048,12 +1091,16 @@ __global__ void __launch_bounds__(K3B_THREADS) k3b_sa_events(DevBatch B, DevPara
             S.pb[sb] = 0xffffffffu; S.pread[sb] = (uint8_t)t;                 // slot 0 of the record: its own alignment
             if (is_str) {
                 uint32_t at = sb + 1, pbeg = b0;
-                for (uint32_t i = b0; i <= e0; i++) {
-                    if (i == e0 || s[i] == ';') {
+                for (uint32_t w0 = b0 & ~3u; w0 < e0; w0 += 4u) {
+                    uint32_t z = swar_clip(swar_eq(s.word(w0), 0x3b3b3b3bu), w0, b0, e0);
+                    while (z) {
+                        const uint32_t i = w0 + ((uint32_t)(__ffs((int)z) - 1) >> 3);
+                        z &= z - 1u;
                         if (i > pbeg) { S.pb[at] = pbeg; S.pe[at] = i; S.pread[at] = (uint8_t)t; at++; }
                         pbeg = i + 1;
                     }
                 }
+                if (e0 > pbeg) { S.pb[at] = pbeg; S.pe[at] = e0; S.pread[at] = (uint8_t)t; at++; }
             }
         }
         __syncthreads();
