@@ -79,3 +79,28 @@ def load_dump(path: str) -> HostBatch:
     ref = [names[noff[i]:noff[i + 1]].decode() for i in range(len(noff) - 1)]
     qnames = [qn[qoff[i]:qoff[i + 1]].decode() for i in range(len(qoff) - 1)]
     return HostBatch(cigar, cigar_off, pos, tid, flag, mapq, sa_kind, sa_off, sa_bytes, ref, qnames)
+
+
+def write_sam(hb: HostBatch, path: str, ref_lens: Optional[Sequence[int]] = None) -> None:
+    """The same records as SAM text (what `samtools view -h` would print, SEQ/QUAL '*')."""
+    names = hb.ref_names
+    lens = list(ref_lens) if ref_lens is not None else [2 ** 31 - 1] * len(names)
+    qn = hb.qnames if hb.qnames is not None else ["r%09d" % i for i in range(hb.n_reads)]
+    co, so = hb.cigar_off.tolist(), hb.sa_off.tolist()
+    sab = hb.sa_bytes.tobytes()
+    with open(path, "w") as f:
+        f.write("@HD\tVN:1.6\tSO:coordinate\n")
+        for n, l in zip(names, lens):
+            f.write(f"@SQ\tSN:{n}\tLN:{l}\n")
+        for i in range(hb.n_reads):
+            ops = hb.cigar[co[i]:co[i + 1]].tolist()
+            cig = "".join("%d%s" % (v >> 4, "MIDNSHP=X"[v & 15]) for v in ops) or "*"
+            t = int(hb.tid[i])
+            cols = [qn[i], str(int(hb.flag[i])), names[t] if t >= 0 else "*", str(int(hb.pos[i]) + 1), str(int(hb.mapq[i])), cig,
+                    "*", "0", "0", "*", "*", "NM:i:5"]
+            k = int(hb.sa_kind[i])
+            if k == SA_STRING:
+                cols.append("SA:Z:" + sab[so[i]:so[i + 1]].decode("latin-1"))
+            elif k == SA_OTHER:
+                cols.append("SA:i:7")
+            f.write("\t".join(cols) + "\n")

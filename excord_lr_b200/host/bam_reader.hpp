@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -35,18 +36,27 @@ public:
 
     ~BamReader() { if (fp_) fclose(fp_); }
 
+    // BAM, or SAM text (plain or BGZF-compressed): htslib auto-detects the same way and the reference's Makefile feeds it
+    // a .sam (reference Makefile:73-74).
     bool open(const std::string& path, int threads)
     {
         fp_ = fopen(path.c_str(), "rb");
         if (!fp_) { error = "cannot open " + path; return false; }
         threads_ = threads < 1 ? 1 : threads;
-        if (!fill()) { if (error.empty()) error = "empty or truncated BAM"; return false; }
-        return read_header();
+        uint8_t magic[2] = {0, 0};
+        const size_t got = fread(magic, 1, 2, fp_);
+        rewind(fp_);
+        plain_ = !(got == 2 && magic[0] == 31 && magic[1] == 139);
+        if (!fill()) { if (error.empty()) error = "empty or truncated input"; return false; }
+        if (!plain_ && avail() >= 4 && memcmp(cur(), "BAM\1", 4) == 0) return read_header();
+        sam_ = true;
+        return read_sam_header();
     }
 
     // Next record; false at EOF or on a read error (the reference stops silently on a read error too: src/main.rs:165-168).
     bool next(BamRecordView& r)
     {
+        if (sam_) return next_sam(r);
         for (;;) {
             if (avail() >= 4) {
                 uint32_t bs; memcpy(&bs, cur(), 4);
@@ -62,7 +72,7 @@ private:
     int threads_ = 1;
     std::vector<uint8_t> buf_;        // decompressed stream window
     size_t off_ = 0;                  // read cursor inside buf_
-    bool eof_ = false;
+    bool eof_ = false, plain_ = false, sam_ = false;
     std::vector<uint32_t> cg_restore_;
     std::vector<uint8_t> comp_;       // compressed superblock
     struct Blk { size_t coff, clen, uoff, ulen; };
@@ -76,6 +86,14 @@ private:
     {
         if (eof_) return false;
         if (off_ > 0) { buf_.erase(buf_.begin(), buf_.begin() + (ptrdiff_t)off_); off_ = 0; }
+        if (plain_) {
+            const size_t base = buf_.size(), chunk = 4u << 20;
+            buf_.resize(base + chunk);
+            const size_t n = fread(buf_.data() + base, 1, chunk, fp_);
+            buf_.resize(base + n);
+            if (n == 0) { eof_ = true; return false; }
+            return true;
+        }
         comp_.clear();
         std::vector<Blk> blks;
         size_t utotal = 0;
@@ -158,6 +176,98 @@ private:
             ref_lens.push_back(l_ref);
             off_ += 8 + (size_t)l_name;
         }
+        return true;
+    }
+
+    // one text line [cur(), cur()+len) without the newline; false at EOF.  A last line without '\n' is still returned.
+    bool sam_line(size_t* len)
+    {
+        for (;;) {
+            const uint8_t* p = cur();
+            const void* nl = avail() ? memchr(p, '\n', avail()) : nullptr;
+            if (nl) { *len = (size_t)((const uint8_t*)nl - p); return true; }
+            if (!fill()) { if (avail() == 0) return false; *len = avail(); return true; }
+        }
+    }
+    void sam_consume(size_t len) { off_ += len; if (avail() && *cur() == '\n') off_++; }
+
+    bool read_sam_header()
+    {
+        size_t len;
+        while (avail() || !eof_) {
+            if (!avail() && !fill()) break;
+            if (*cur() != '@') break;
+            if (!sam_line(&len)) break;
+            std::string line((const char*)cur(), len);
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            if (line.rfind("@SQ", 0) == 0) {
+                std::string name; int64_t ln = 0;
+                size_t b = 3;
+                while (b < line.size()) {
+                    size_t e = line.find('\t', b + 1); if (e == std::string::npos) e = line.size();
+                    const std::string f = line.substr(b + 1, e - b - 1);
+                    if (f.rfind("SN:", 0) == 0) name = f.substr(3);
+                    else if (f.rfind("LN:", 0) == 0) ln = atoll(f.c_str() + 3);
+                    b = e;
+                }
+                ref_names.push_back(name); ref_lens.push_back(ln);
+            }
+            sam_consume(len);
+        }
+        return true;
+    }
+
+    bool next_sam(BamRecordView& r)
+    {
+        size_t len;
+        for (;;) {
+            if (!sam_line(&len)) return false;
+            if (len == 0 || *cur() == '@') { sam_consume(len); continue; }
+            break;
+        }
+        const char* p = (const char*)cur();
+        size_t n = len;
+        if (n && p[n - 1] == '\r') n--;
+        const char* f[12]; size_t fl[12]; int nf = 0; size_t b = 0, aux_at = n;
+        for (size_t i = 0; i <= n && nf < 11; i++) {
+            if (i == n || p[i] == '\t') { f[nf] = p + b; fl[nf] = i - b; nf++; b = i + 1; if (nf == 11) aux_at = b <= n ? b : n; }
+        }
+        if (nf < 11) { error = "corrupt SAM record"; return false; }
+        auto num = [](const char* s, size_t l, long long* out) { if (!l) return false; char* e; std::string t(s, l); *out = strtoll(t.c_str(), &e, 10); return *e == 0; };
+        long long flag, pos, mapq;
+        if (!num(f[1], fl[1], &flag) || !num(f[3], fl[3], &pos) || !num(f[4], fl[4], &mapq)) { error = "corrupt SAM record"; return false; }
+        r.qname = f[0]; r.qname_len = (uint32_t)fl[0];
+        r.flag = (uint16_t)flag; r.pos = (int32_t)(pos - 1); r.mapq = (uint8_t)mapq;
+        r.tid = -1;
+        if (!(fl[2] == 1 && f[2][0] == '*')) {
+            for (size_t i = 0; i < ref_names.size(); i++) if (ref_names[i].size() == fl[2] && memcmp(ref_names[i].data(), f[2], fl[2]) == 0) { r.tid = (int32_t)i; break; }
+            if (r.tid < 0) { error = "SAM record on a contig that is not in the header"; return false; }
+        }
+        cg_restore_.clear();
+        if (!(fl[5] == 1 && f[5][0] == '*')) {
+            uint64_t v = 0; bool have = false;
+            for (size_t i = 0; i < fl[5]; i++) {
+                const char c = f[5][i];
+                if (c >= '0' && c <= '9') { v = v * 10 + (uint64_t)(c - '0'); have = true; if (v >= (1ull << 28)) { error = "CIGAR length out of range"; return false; } continue; }
+                static const char ops[] = "MIDNSHP=XB";
+                const char* q = (const char*)memchr(ops, c, 10);
+                if (!q || !have) { error = "corrupt CIGAR"; return false; }
+                cg_restore_.push_back((uint32_t)(v << 4) | (uint32_t)(q - ops));
+                v = 0; have = false;
+            }
+            if (have) { error = "corrupt CIGAR"; return false; }
+        }
+        r.cigar = cg_restore_.data(); r.n_cigar = (uint32_t)cg_restore_.size();
+        r.sa_kind = 0; r.sa = nullptr; r.sa_len = 0;
+        for (size_t i = aux_at; i < n;) {
+            size_t e = i; while (e < n && p[e] != '\t') e++;
+            if (e - i >= 5 && p[i] == 'S' && p[i + 1] == 'A' && p[i + 2] == ':' && p[i + 4] == ':' && r.sa_kind == 0) {
+                if (p[i + 3] == 'Z') { r.sa_kind = 1; r.sa = (const uint8_t*)p + i + 5; r.sa_len = (uint32_t)(e - i - 5); }
+                else r.sa_kind = 2;
+            }
+            i = e + 1;
+        }
+        sam_consume(len);
         return true;
     }
 

@@ -65,3 +65,21 @@ def test_truncated_bam_stops_quietly(tmp_path):
     got = bamio.load_dump(str(tmp_path / "t.bin"))
     n = got.n_reads
     assert 0 < n < hb.n_reads and np.array_equal(got.pos, hb.pos[:n])
+
+
+def test_sam_text_input(tmp_path):
+    # SAM text is accepted like BAM (the reference reads .sam through htslib's auto-detection, reference Makefile:73-74)
+    _build()
+    hb = synth.with_qnames(synth.config(0, 0.1))
+    hb2 = rand_batch(5, 200, qnames=True)
+    hb2.tid[hb2.tid >= len(REF_NAMES)] = 0
+    for k, h in enumerate((hb, hb2)):
+        valid = (h.cigar & 15) <= 8
+        assert valid.all()
+        sam, out = str(tmp_path / f"x{k}.sam"), str(tmp_path / f"x{k}.bin")
+        bamio.write_sam(h, sam)
+        subprocess.check_call([DUMP, sam, out, "2"])
+        got = bamio.load_dump(out)
+        for f in ("cigar", "cigar_off", "pos", "tid", "flag", "mapq", "sa_kind", "sa_off", "sa_bytes"):
+            assert np.array_equal(getattr(got, f), getattr(h, f)), f
+        assert got.qnames == h.qnames and got.ref_names == h.ref_names
