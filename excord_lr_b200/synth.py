@@ -94,7 +94,7 @@ CONFIGS = {
             params=dict(mapq=1, exclude_flag=1796, indel_min=50, merge_min=5, max_pct_overlap=0.8, max_supp_alignm=4)),
     2: dict(name="c3_ont_500k", profile=PROFILE_ONT, seed=1003, n=500_000, chr20=False, ultra=100,
             params=dict(indel_min=30)),
-    3: dict(name="c4_split_2M", profile=PROFILE_SPLIT, seed=1004, n=500_000, chr20=False, ultra=0,
+    3: dict(name="c4_split_2M", profile=PROFILE_SPLIT, seed=1004, n=670_000, chr20=False, ultra=0,
             params=dict(split_only=True, max_supp_alignm=4)),
     4: dict(name="c5_hifi_6M", profile=PROFILE_HIFI, seed=1005, n=6_000_000, chr20=False, ultra=0,
             params=dict(mapq=1, exclude_flag=1796, indel_min=50, merge_min=5, max_pct_overlap=0.8, max_supp_alignm=4)),

@@ -225,3 +225,15 @@ def test_round_robin_shards_reassemble_in_order():
     parts = [shard.run_rank(hb, plan, r, 2, runner) for r in range(2)]
     want = oracle_c.run(hb, p)
     assert shard.merge_ordered(parts) == oracle_c.format_lines(hb, want.events)
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("cfg", [2, 3, 4])
+def test_full_size_configs_bit_exact(cfg):
+    # BASELINE.json configs[2..4] at their full sizes (ONT 0.5M records / 1.7e9 ops; 2M split records; 6M HiFi records):
+    # the whole output compared with the oracle, plus the size-independent structure checks
+    hb = synth.config(cfg, 1.0)
+    p = ExlrParams.make(**synth.CONFIGS[cfg]["params"])
+    want, res = gpu_check(hb, p, 0, 0, label=f"config{cfg} full size")
+    assert res.status == 0 and res.line_off[-1] == res.n_events == len(want.events)
+    assert (np.diff(res.events["read_idx"].astype(np.int64)) >= 0).all()
