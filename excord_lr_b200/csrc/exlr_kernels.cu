@@ -292,6 +292,7 @@ static constexpr int K1_STAGES = 5;                    // ring of bulk-copy stag
 static constexpr int K1_MAX_RPC = K1_THREADS;          // records per tile (thread t owns record t)
 static constexpr int K1_CAP = K1_THREADS;              // staged events per flush (one per thread)
 static constexpr int K1_MAX_TILES = 256;               // tiles per CTA
+static constexpr uint32_t K1_SCREEN_CHUNKS = 2;         // tiles resident in at most this many stages are screened for events first
 
 struct __align__(16) K1Stage { uint32_t fp, pexcl, n_type, pad; };
 
@@ -472,12 +473,8 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         spare = atomicAdd(&B.ctrl->n_raw, (uint32_t)K1_CAP);
     }
-    // first tile's per-record inputs straight from global memory; later tiles arrive through the register prefetch
-    unsigned long long pre_off = 0; uint32_t pre_flag = 0, pre_mapq = 0, pre_pos = 0;
-    {
-        const uint32_t ra = blockIdx.x * rpc, nr = min(rpc, B.n_reads - ra);
-        if (t < nr) { pre_off = B.cigar_off[ra + t]; pre_flag = B.flag[ra + t]; pre_mapq = B.mapq[ra + t]; pre_pos = (uint32_t)B.pos[ra + t]; }
-    }
+    // per-record inputs of the next tile that is known to need the full scan, prefetched into registers (see the tile loop)
+    unsigned long long pre_off = 0; uint32_t pre_flag = 0, pre_mapq = 0, pre_pos = 0, pre_tile = 0xffffffffu;
     __syncthreads();
 
     // issue cursor (thread 0): next chunk to request = chunk ic of tile it_i; gi = chunks requested so far
@@ -509,16 +506,58 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
         const uint32_t span_lo = (uint32_t)(oa - oa4), span_hi = (uint32_t)(ob - oa4);
         if (ob - oa4 >= 0x80000000ull) { if (t == 0) B.ctrl->overflow = 1; return; }    // block-uniform
         const uint32_t nchunks = (span_hi + K1_CHUNK - 1) / K1_CHUNK;
-        // tile state from the prefetched registers
+        // ---- event-free tiles leave early ------------------------------------------------------------------------
+        // total_consume and the prefixes are only ever read for records that have an indel event (kernel 4b), and events
+        // (I/D >= indel_min) are sparse: a tile that is fully resident (<= 2 stages) is first screened with 4 instructions per op
+        // -- table look-up, OR, compare, predicated OR.  A clean tile gets zeroed summaries and is done; anything suspicious
+        // (event candidate, unknown op code) takes the full scan below, which re-reads the same, untouched stages.
+        if (nchunks <= K1_SCREEN_CHUNKS) {
+            uint32_t sus = 0, flags = 0;
+            for (uint32_t c = 0; c < nchunks; c++) {
+                mbar_wait(&S.full[(gs + c) % K1_STAGES], ((gs + c) / K1_STAGES) & 1u);
+                const uint4* m4 = reinterpret_cast<const uint4*>(S.buf[(gs + c) % K1_STAGES]) + t * (K1_V / 4);
+                const uint32_t fp0 = c * K1_CHUNK + t * K1_V;
+                const bool edge = fp0 < span_lo || fp0 + K1_V > span_hi;
+#pragma unroll
+                for (int k = 0; k < K1_V / 4; k++) {
+                    const uint4 q = m4[k];
+                    uint32_t vv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (edge && (fp0 + 4 * k + j < span_lo || fp0 + 4 * k + j >= span_hi)) vv[j] = 0u;
+                        uint32_t f;
+                        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(f) : "r"(K1_LUT_LO), "r"(K1_LUT_HI), "r"(vv[j]));
+                        flags |= f;
+                        asm("{\n.reg .pred p;\nsetp.ge.u32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(sus) : "r"(vv[j]), "r"(imin16), "r"(f));
+                    }
+                }
+            }
+            if (!__syncthreads_or((sus & 2u) | (flags & 0x40u))) {
+                if (t < nr) B.k1[ra + t] = make_uint2(0u, 0u);
+                if (t == 0) B.tile_cnt[tile] = 0;
+                gs += nchunks;
+                if (t == 0) issue_upto(gs + K1_STAGES);
+                continue;
+            }
+        }
+        // per-record state of the tile: from the register prefetch when this tile was known to need the scan (long records),
+        // straight from global memory otherwise (a screened tile that turned out to hold events)
+        if (pre_tile != it && t < nr) {
+            pre_off = B.cigar_off[ra + t]; pre_flag = B.flag[ra + t]; pre_mapq = B.mapq[ra + t]; pre_pos = (uint32_t)B.pos[ra + t];
+        }
         if (t < nr) {
             S.roff[t] = (uint32_t)(pre_off - oa4); S.rkeep[t] = keep_record(P, pre_flag, pre_mapq) ? 1u : 0u; S.rpos[t] = pre_pos;
             S.rcnt[t] = 0; S.rflags[t] = 0; S.fhead[t] = 0; S.pstart[t] = 0;
         }
         if (t == 0) { S.roff[nr] = span_hi; S.has_carry = 0; S.flushes = 0; }
         __syncthreads();
-        if (it + 1 < ntile) {                              // next tile: loads fly while this tile is scanned
-            const uint32_t ra2 = ra + gridDim.x * rpc, nr2 = min(rpc, B.n_reads - ra2);
-            if (t < nr2) { pre_off = B.cigar_off[ra2 + t]; pre_flag = B.flag[ra2 + t]; pre_mapq = B.mapq[ra2 + t]; pre_pos = (uint32_t)B.pos[ra2 + t]; }
+        if (it + 1 < ntile) {                              // next tile needs the scan for sure (long records): prefetch its inputs
+            const unsigned long long na4 = S.tb[it + 1][0] & ~3ull;
+            if ((uint32_t)((S.tb[it + 1][1] - na4 + K1_CHUNK - 1) / K1_CHUNK) > K1_SCREEN_CHUNKS) {
+                const uint32_t ra2 = ra + gridDim.x * rpc, nr2 = min(rpc, B.n_reads - ra2);
+                if (t < nr2) { pre_off = B.cigar_off[ra2 + t]; pre_flag = B.flag[ra2 + t]; pre_mapq = B.mapq[ra2 + t]; pre_pos = (uint32_t)B.pos[ra2 + t]; }
+                pre_tile = it + 1;
+            }
         }
         uint32_t carry = 0, staged = 0;
         for (uint32_t c = 0; c < nchunks; c++, gs++) {
