@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run kernel 1 on the same stream as the SA branch")
     ap.add_argument("--k1-ctas", type=int, default=0, help="persistent CTAs of kernel 1 per SM (1..4)")
+    ap.add_argument("--k1-waves", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -186,6 +187,8 @@ def main():
         ex.set_option(api.EXLR_OPT_OVERLAP, 0)
     if args.k1_ctas:
         ex.set_option(api.EXLR_OPT_K1_CTAS_PER_SM, args.k1_ctas)
+    if args.k1_waves:
+        ex.set_option(api.EXLR_OPT_K1_WAVES, args.k1_waves)
 
     # ---------------- device-resident: value + roofline ----------------
     big = ex.batch_for(hb)

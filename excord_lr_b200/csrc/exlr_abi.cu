@@ -171,6 +171,7 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
     case EXLR_OPT_CIGAR_KERNEL: if (value != 0 && value != 1) return EXLR_ERR_ARG; c->cigar_kernel = (int)value; return EXLR_OK;
     case EXLR_OPT_READS_PER_CTA: if (value < 0 || value > 128) return EXLR_ERR_ARG; c->reads_per_cta = (uint32_t)value; return EXLR_OK;
     case EXLR_OPT_OVERLAP: c->overlap = value != 0; return EXLR_OK;
+    case EXLR_OPT_K1_WAVES: if (value < 1 || value > 16) return EXLR_ERR_ARG; set_k1_waves((int)value); return EXLR_OK;
     case EXLR_OPT_K1_CTAS_PER_SM: if (value < 1 || value > 4) return EXLR_ERR_ARG; set_k1_ctas_per_sm((int)value); return EXLR_OK;
     default: return EXLR_ERR_ARG;
     }

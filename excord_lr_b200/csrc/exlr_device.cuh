@@ -111,6 +111,7 @@ struct DevParams {
 // launchers (exlr_kernels.cu)
 cudaError_t configure_kernels(int device);
 void set_k1_ctas_per_sm(int n);
+void set_k1_waves(int n);
 size_t k1_flat_smem_bytes();
 uint32_t scan_tiles(uint32_t n_reads);
 void launch_k0(const DevBatch& B, const DevParams& P, cudaStream_t st);

@@ -518,18 +518,19 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
                 const uint4* m4 = reinterpret_cast<const uint4*>(S.buf[(gs + c) % K1_STAGES]) + t * (K1_V / 4);
                 const uint32_t fp0 = c * K1_CHUNK + t * K1_V;
                 const bool edge = fp0 < span_lo || fp0 + K1_V > span_hi;
+                uint32_t vv[K1_V];
 #pragma unroll
-                for (int k = 0; k < K1_V / 4; k++) {
-                    const uint4 q = m4[k];
-                    uint32_t vv[4] = {q.x, q.y, q.z, q.w};
+                for (int k = 0; k < K1_V / 4; k++) { const uint4 q = m4[k]; vv[4 * k] = q.x; vv[4 * k + 1] = q.y; vv[4 * k + 2] = q.z; vv[4 * k + 3] = q.w; }
+                if (edge) {                                                  // first / last thread of the tile only
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        if (edge && (fp0 + 4 * k + j < span_lo || fp0 + 4 * k + j >= span_hi)) vv[j] = 0u;
-                        uint32_t f;
-                        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(f) : "r"(K1_LUT_LO), "r"(K1_LUT_HI), "r"(vv[j]));
-                        flags |= f;
-                        asm("{\n.reg .pred p;\nsetp.ge.u32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(sus) : "r"(vv[j]), "r"(imin16), "r"(f));
-                    }
+                    for (int k = 0; k < K1_V; k++) if (fp0 + k < span_lo || fp0 + k >= span_hi) vv[k] = 0u;
+                }
+#pragma unroll
+                for (int k = 0; k < K1_V; k++) {
+                    uint32_t f;
+                    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(f) : "r"(K1_LUT_LO), "r"(K1_LUT_HI), "r"(vv[k]));
+                    flags |= f;
+                    asm("{\n.reg .pred p;\nsetp.ge.u32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(sus) : "r"(vv[k]), "r"(imin16), "r"(f));
                 }
             }
             if (!__syncthreads_or((sus & 2u) | (flags & 0x40u))) {
@@ -1285,6 +1286,8 @@ __global__ void __launch_bounds__(256) k4b_place(DevBatch B, DevParams P)
 // ======================================================================================
 static int g_sm_count = 148;
 static int g_k1_ctas_per_sm = 4;
+static int g_k1_waves = 3;                 // grid = SMs x CTAs/SM x waves: > 1 trades prefetch depth for dynamic balance
+void set_k1_waves(int n) { g_k1_waves = n < 1 ? 1 : (n > 16 ? 16 : n); }
 void set_k1_ctas_per_sm(int n) { g_k1_ctas_per_sm = n < 1 ? 1 : (n > 4 ? 4 : n); }
 
 size_t k1_flat_smem_bytes() { return sizeof(K1Smem); }
@@ -1333,7 +1336,7 @@ void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc,
         if (rpc < 1) rpc = 1;
         if (rpc > K1_MAX_RPC) rpc = K1_MAX_RPC;
         const uint32_t n_tiles = (B.n_reads + rpc - 1) / rpc;
-        uint32_t grid = min(n_tiles, (uint32_t)g_sm_count * (uint32_t)g_k1_ctas_per_sm);
+        uint32_t grid = min(n_tiles, (uint32_t)g_sm_count * (uint32_t)g_k1_ctas_per_sm * (uint32_t)g_k1_waves);
         if ((n_tiles + grid - 1) / grid > K1_MAX_TILES) grid = (n_tiles + K1_MAX_TILES - 1) / K1_MAX_TILES;
         k1_flat<<<grid, K1_THREADS, sizeof(K1Smem), st>>>(B, P, rpc, n_tiles);
     }
