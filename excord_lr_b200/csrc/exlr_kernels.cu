@@ -670,7 +670,7 @@ __device__ __forceinline__ K3aAcc k3a_walk(const DevBatch& B, uint32_t r, unsign
     const uint32_t sub = threadIdx.x & (G - 1);
     K3aAcc a{0, 0, 0, 0, 0, 0, 0};
     bool seenM = false;
-    constexpr int U = G == 32 ? 8 : 1;                                         // loads in flight per lane on the long path
+    constexpr int U = G == 32 ? 8 : 4;                                         // independent loads in flight per lane
     for (unsigned long long b = o0; b < o1; b += (unsigned long long)G * U) {
         uint32_t vv[U];
 #pragma unroll
@@ -779,6 +779,7 @@ __device__ __forceinline__ uint32_t swar_eq(uint32_t x, uint32_t c4)
 // keep only the flag bits of the bytes whose absolute index is in [lo, hi); w0 = absolute index of the word's byte 0
 __device__ __forceinline__ uint32_t swar_clip(uint32_t z, uint32_t w0, uint32_t lo, uint32_t hi)
 {
+    if (w0 >= lo && w0 + 4u <= hi) return z;             // interior word: the common case costs one predicate
     if (w0 < lo) z &= 0xffffffffu << (8u * (lo - w0));
     if (w0 + 4u > hi) z &= 0xffffffffu >> (8u * (w0 + 4u - hi));
     return z;
@@ -1257,24 +1258,23 @@ __device__ __forceinline__ void k4b_indel(const DevBatch& B, const RawEv* src)
                 EXLR_EV_META(1u, EXLR_KIND_INDEL, neg, neg));
 }
 
+// One thread per raw slot / overflow entry / SA record (no grid-stride loop: every chain of dependent loads runs beside all
+// the others; threads without work leave at once).
 __global__ void __launch_bounds__(256) k4b_place(DevBatch B, DevParams P)
 {
-    const uint32_t n_sa = B.ctrl->n_sa;
-    const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
     // indel events, per-tile slices first (slice of tile i = raw[i << capt_log2 ..], tile_cnt[i] entries used) ...
-    const uint32_t capt_mask = (1u << B.capt_log2) - 1u;
-    for (uint32_t x = t0; x < B.prim_slots; x += stride)
-        if ((x & capt_mask) < B.tile_cnt[x >> B.capt_log2]) k4b_indel(B, B.raw + x);
+    if (x < B.prim_slots && (x & ((1u << B.capt_log2) - 1u)) < B.tile_cnt[x >> B.capt_log2]) k4b_indel(B, B.raw + x);
     // ... then the shared overflow region
     const uint32_t room = B.raw_cap - B.prim_slots, n_ovf = min(B.ctrl->n_raw, room);
-    for (uint32_t x = t0; x < n_ovf; x += stride) k4b_indel(B, B.raw + B.prim_slots + x);
+    if (x < n_ovf) k4b_indel(B, B.raw + B.prim_slots + x);
     // SA-derived events: per record contiguous in the temp buffer, they lead the record's lines
-    for (uint32_t j = t0; j < n_sa; j += stride) {
-        const uint32_t r = B.sa_list[j];
+    if (x < B.ctrl->n_sa) {
+        const uint32_t j = x, r = B.sa_list[j];
         const uint32_t csa = B.csa[r];
-        if (csa & CSA_DROP) continue;
+        if (csa & CSA_DROP) return;
         const uint32_t cnt = csa & CSA_CNT_MASK, base = B.sa_base[j], dst = B.line_off[r];
-        if ((unsigned long long)dst + cnt > B.max_events || (unsigned long long)base + cnt > B.max_events) continue;
+        if ((unsigned long long)dst + cnt > B.max_events || (unsigned long long)base + cnt > B.max_events) return;
         const uint4* src = reinterpret_cast<const uint4*>(B.sa_ev + base);
         uint4* d = reinterpret_cast<uint4*>(B.events + dst);
         for (uint32_t k = 0; k < cnt * 3; k++) d[k] = src[k];
@@ -1364,8 +1364,11 @@ void launch_k4a(const DevBatch& B, const DevParams& P, cudaStream_t st)
 
 void launch_k4b(const DevBatch& B, const DevParams& P, cudaStream_t st)
 {
-    const uint32_t g = min((B.max_events + 255u) / 256u, (uint32_t)g_sm_count * 8u);
-    k4b_place<<<g ? g : 1u, 256, 0, st>>>(B, P);
+    // the overflow count and the SA-record count live on the device: cover the largest they can be
+    uint32_t n = B.prim_slots > B.n_reads ? B.prim_slots : B.n_reads;
+    const uint32_t room = B.raw_cap - B.prim_slots;
+    if (room > n) n = room;
+    k4b_place<<<(n + 255u) / 256u, 256, 0, st>>>(B, P);
 }
 
 uint32_t scan_tiles(uint32_t n_reads) { return (n_reads + SCAN_TILE - 1) / SCAN_TILE; }
