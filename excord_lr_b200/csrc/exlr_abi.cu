@@ -38,6 +38,7 @@ struct exlr_ctx {
     uint8_t* d_ref_bytes = nullptr; uint32_t* d_ref_off = nullptr; int n_ref = 0;
     int cigar_kernel = 0;                      // EXLR_OPT_CIGAR_KERNEL
     int overlap = 1;                           // EXLR_OPT_OVERLAP: kernel 1 on a second stream beside the SA branch
+    int k1_ctas = 0;                           // EXLR_OPT_K1_CTAS_PER_SM (0 = 3 when overlapping, which leaves room for the SA branch, else 4)
     uint32_t reads_per_cta = 0;                // EXLR_OPT_READS_PER_CTA (0 = auto)
 };
 
@@ -172,7 +173,7 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
     case EXLR_OPT_READS_PER_CTA: if (value < 0 || value > 128) return EXLR_ERR_ARG; c->reads_per_cta = (uint32_t)value; return EXLR_OK;
     case EXLR_OPT_OVERLAP: c->overlap = value != 0; return EXLR_OK;
     case EXLR_OPT_K1_WAVES: if (value < 1 || value > 16) return EXLR_ERR_ARG; set_k1_waves((int)value); return EXLR_OK;
-    case EXLR_OPT_K1_CTAS_PER_SM: if (value < 1 || value > 4) return EXLR_ERR_ARG; set_k1_ctas_per_sm((int)value); return EXLR_OK;
+    case EXLR_OPT_K1_CTAS_PER_SM: if (value < 0 || value > 4) return EXLR_ERR_ARG; c->k1_ctas = (int)value; return EXLR_OK;
     default: return EXLR_ERR_ARG;
     }
 }
@@ -254,8 +255,12 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     v.seg_pool = (Seg*)(ds + d_pool); v.seg_pool_cap = (uint32_t)pool_cap;
     v.line_off = (uint32_t*)(ds + d_loff); v.events = (exlr_event*)(ds + d_ev);
     v.n_reads = 0; v.max_events = (uint32_t)max_events;
-    e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream2, cudaStreamNonBlocking);
+    // the SA branch (kernels 0, 3a, 3b) is the longer chain: its stream gets the higher priority so its CTAs are placed first
+    // whenever kernel 1 (stream2) frees a slot
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    e = cudaStreamCreateWithPriority(&b->stream, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&b->stream2, cudaStreamNonBlocking, prio_lo);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_fork);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_k1_begin);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_k1_end);
@@ -322,25 +327,22 @@ static int run_kernels(exlr_batch* b)
     // kernel 1 needs nothing from kernel 0, so it runs on a second stream beside the SA branch (0 -> 3a -> 3b); 4a joins them
     d.prim_slots = 0; d.capt_log2 = 0;
     const bool overlap = c->overlap && !c->params.split_only;
+    set_k1_ctas_per_sm(c->k1_ctas ? c->k1_ctas : (overlap ? 3 : 4));
+    uint32_t rpc = 0;
     if (!c->params.split_only) {
-        const uint32_t rpc = c->reads_per_cta ? c->reads_per_cta : auto_rpc(b->n_reads, b->n_ops);
+        rpc = c->reads_per_cta ? c->reads_per_cta : auto_rpc(b->n_reads, b->n_ops);
         uint32_t n_tiles = 0;
         plan_k1(d, c->cigar_kernel, rpc, &n_tiles);
-        if (overlap) {
-            CK(cudaEventRecord(b->ev_fork, st));
-            CK(cudaStreamWaitEvent(b->stream2, b->ev_fork, 0));
-            CK(cudaEventRecord(b->ev_k1_begin, b->stream2));
-            launch_k1(d, c->dparams, c->cigar_kernel, rpc, b->stream2); b->launches++;
-            CK(cudaEventRecord(b->ev_k1_end, b->stream2));
-        }
+        if (overlap) CK(cudaEventRecord(b->ev_fork, st));                  // after the memset
     }
     launch_k0(d, c->dparams, st); b->launches++;
     CK(cudaEventRecord(b->ev[EV_K0], st));
-    if (!c->params.split_only && !overlap) {
-        const uint32_t rpc = c->reads_per_cta ? c->reads_per_cta : auto_rpc(b->n_reads, b->n_ops);
-        CK(cudaEventRecord(b->ev_k1_begin, st));
-        launch_k1(d, c->dparams, c->cigar_kernel, rpc, st); b->launches++;
-        CK(cudaEventRecord(b->ev_k1_end, st));
+    if (!c->params.split_only) {
+        cudaStream_t s1 = overlap ? b->stream2 : st;
+        if (overlap) CK(cudaStreamWaitEvent(s1, b->ev_fork, 0));
+        CK(cudaEventRecord(b->ev_k1_begin, s1));
+        launch_k1(d, c->dparams, c->cigar_kernel, rpc, s1); b->launches++;
+        CK(cudaEventRecord(b->ev_k1_end, s1));
     }
     CK(cudaEventRecord(b->ev[EV_K1], st));
     launch_k3a(d, c->dparams, st); b->launches++;

@@ -159,7 +159,7 @@ typedef struct exlr_batch exlr_batch;
 #define EXLR_OPT_CIGAR_KERNEL 1  /* 0 = flat TMA-staged block scan (default), 1 = warp-per-record */
 #define EXLR_OPT_READS_PER_CTA 2 /* 0 = auto */
 #define EXLR_OPT_OVERLAP 3       /* 1 (default) = kernel 1 runs on a second stream beside kernels 0/3a/3b */
-#define EXLR_OPT_K1_CTAS_PER_SM 4 /* 1..4 persistent CTAs of kernel 1 per SM (default 4) */
+#define EXLR_OPT_K1_CTAS_PER_SM 4 /* 1..4 CTAs of kernel 1 per SM; 0 (default) = 3 when overlapping, else 4 */
 #define EXLR_OPT_K1_WAVES 5       /* kernel 1 grid = SMs x CTAs/SM x waves (default 3) */
 
 /* ---- lifecycle ---------------------------------------------------------------------- */
