@@ -6,6 +6,7 @@
 // Same flags, same startup messages/exit codes, same output bytes as the reference for BAM input.  There is no CPU
 // path: without a B200 the program exits with the library's error.
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <cstdio>
@@ -31,6 +32,7 @@ struct Cli {
     unsigned long long thread = 8;
     bool not_merge = false, debug = false, verbose = false;
     int gpus = 0;                       // 0 = all visible
+    bool stats = false;                 // --stats: stage times on stderr
     unsigned long long batch_reads = 131072, batch_ops = 0, batch_sa = 0;
 };
 
@@ -57,6 +59,7 @@ static void usage(FILE* f)
           "  -v, --verbose                            Verbose output\n"
           "      --gpus <N>                           GPUs to shard batches over [default: all visible]\n"
           "      --batch-reads <N>                    Records per GPU batch [default: 131072]\n"
+          "      --stats                              Print stage times to stderr\n"
           "  -h, --help                               Print help\n"
           "  -V, --version                            Print version\n", f);
 }
@@ -107,6 +110,7 @@ static int parse_cli(int argc, char** argv, Cli& c)
         else if (a == "-v" || a == "--verbose") { if (!flagopt(&c.verbose)) return 2; }
         else if (a == "--gpus") { NUM(64); c.gpus = (int)u; }
         else if (a == "--batch-reads") { NUM(1ull << 30); c.batch_reads = u ? u : 1; }
+        else if (a == "--stats") { if (!flagopt(&c.stats)) return 2; }
         else if (a == "-h" || a == "--help") { usage(stdout); return -1; }
         else if (a == "-V" || a == "--version") { puts("excord-LR 0.1.17"); return -1; }
         else { fprintf(stderr, "error: unexpected argument '%s' found\n\nFor more information, try '--help'.\n", argv[i]); return 2; }
@@ -192,6 +196,10 @@ int main(int argc, char** argv)
     std::deque<int> inflight, freeq; bool done = false; int fatal = 0;
     for (size_t i = 0; i < slots.size(); i++) freeq.push_back((int)i);
 
+    using clk = std::chrono::steady_clock;
+    auto secs = [](clk::duration d) { return std::chrono::duration<double>(d).count(); };
+    const auto t_begin = clk::now();
+    double t_wait = 0, t_format = 0, t_write = 0; uint64_t n_lines = 0, n_batches = 0;
     std::thread writer([&]() {
         std::vector<char> text;
         for (;;) {
@@ -199,19 +207,25 @@ int main(int argc, char** argv)
             { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !inflight.empty() || done; }); if (inflight.empty()) return; si = inflight.front(); inflight.pop_front(); }
             Slot& s = slots[si];
             exlr_result res;
+            auto t0 = clk::now();
             int st = exlr_wait(s.b, &res);
+            t_wait += secs(clk::now() - t0); n_batches++;
             if (st != 0 && st > -10) { fprintf(stderr, "exlr_wait: %s (%s)\n", exlr_strerror(st), exlr_last_cuda_error()); std::lock_guard<std::mutex> lk(mu); fatal = 3; cv.notify_all(); return; }
             uint64_t n_ev = res.n_events;
             if (st <= -10) n_ev = res.line_off[res.err_read];            // the lines of the records before the failing one
             const char* qn = cli.verbose ? s.pk.qnames.data() : nullptr;
             static const char kEmpty = 0;
             if (cli.verbose && !qn) qn = &kEmpty;
+            t0 = clk::now();
             int64_t need = exlr_format_lines(ctx[s.gpu], s.b, &res, 0, n_ev, cli.verbose, qn, cli.verbose ? s.pk.qname_off.data() : nullptr, nullptr, 0);
             if (need > 0) {
                 text.resize((size_t)need);
                 exlr_format_lines(ctx[s.gpu], s.b, &res, 0, n_ev, cli.verbose, qn, cli.verbose ? s.pk.qname_off.data() : nullptr, text.data(), (uint64_t)need);
+                t_format += secs(clk::now() - t0); t0 = clk::now();
                 fwrite(text.data(), 1, (size_t)need, fo);
+                t_write += secs(clk::now() - t0);
             }
+            n_lines += n_ev;
             if (st <= -10) {
                 fflush(fo);
                 fprintf(stderr, "excord-lr-b200: record %u of a batch: %s\n", res.err_read, exlr_strerror(st));
@@ -258,6 +272,10 @@ int main(int argc, char** argv)
     cv.notify_all();
     writer.join();
     fclose(fo);
+    if (cli.stats)
+        fprintf(stderr, "excord-lr-b200: %llu records, %llu lines, %llu batches on %d GPU(s); total %.3f s (writer thread: waiting for the GPU %.3f s, "
+                "formatting %.3f s, writing %.3f s; the reader thread inflates, parses and packs for the whole run)\n",
+                (unsigned long long)n_rec, (unsigned long long)n_lines, (unsigned long long)n_batches, ndev, secs(clk::now() - t_begin), t_wait, t_format, t_write);
     for (auto& s : slots) exlr_batch_free(s.b);
     for (auto c : ctx) exlr_destroy(c);
     return fatal;
