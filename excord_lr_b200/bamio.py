@@ -23,7 +23,7 @@ def _bgzf_block(data: bytes, level: int) -> bytes:
 
 
 def write_bam(hb: HostBatch, path: str, ref_lens: Optional[Sequence[int]] = None, level: int = 1, block: int = 0xFF00,
-              seq_len: int = 0, extra_aux: bytes = b"NM\x43\x05") -> None:
+              seq_len: int = 0, extra_aux: bytes = b"NM\x43\x05", random_seq: bool = False) -> None:
     """Writes `hb` as a coordinate-order BAM.  seq_len > 0 adds that many bases of SEQ/QUAL per record (the reader must skip them)."""
     names = hb.ref_names
     lens = list(ref_lens) if ref_lens is not None else [2 ** 31 - 1] * len(names)
@@ -38,6 +38,7 @@ def write_bam(hb: HostBatch, path: str, ref_lens: Optional[Sequence[int]] = None
     cig = hb.cigar
     sab = hb.sa_bytes.tobytes()
     seq = b"\x12" * ((seq_len + 1) // 2) + b"\x1e" * seq_len
+    rng = np.random.default_rng(7)
     with open(path, "wb") as f:
         for i in range(hb.n_reads):
             ops = cig[co[i]:co[i + 1]]
@@ -50,6 +51,9 @@ def write_bam(hb: HostBatch, path: str, ref_lens: Optional[Sequence[int]] = None
                 aux += b"CGBI" + struct.pack("<I", n_ops) + cig_bytes
                 cig_bytes = struct.pack("<II", (seq_len << 4) | 4, (min(reflen, (1 << 28) - 1) << 4) | 3)
                 n_ops = 2
+            if random_seq and seq_len:      # incompressible-ish bases, HiFi-like qualities: realistic BGZF ratios
+                seq = (rng.integers(0, 256, (seq_len + 1) // 2, dtype=np.uint8).tobytes() +
+                       rng.integers(20, 42, seq_len, dtype=np.uint8).tobytes())
             k = int(hb.sa_kind[i])
             if k == SA_STRING:
                 aux += b"SAZ" + sab[so[i]:so[i + 1]] + b"\x00"

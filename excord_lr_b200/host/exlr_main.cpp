@@ -132,6 +132,7 @@ struct Slot {
 
 int main(int argc, char** argv)
 {
+    const auto t_start = std::chrono::steady_clock::now();
     Cli cli;
     int rc = parse_cli(argc, argv, cli);
     if (rc < 0) return 0;
@@ -199,6 +200,7 @@ int main(int argc, char** argv)
     using clk = std::chrono::steady_clock;
     auto secs = [](clk::duration d) { return std::chrono::duration<double>(d).count(); };
     const auto t_begin = clk::now();
+    const double t_setup = secs(t_begin - t_start);
     double t_wait = 0, t_format = 0, t_write = 0; uint64_t n_lines = 0, n_batches = 0;
     std::thread writer([&]() {
         std::vector<char> text;
@@ -273,9 +275,10 @@ int main(int argc, char** argv)
     writer.join();
     fclose(fo);
     if (cli.stats)
-        fprintf(stderr, "excord-lr-b200: %llu records, %llu lines, %llu batches on %d GPU(s); total %.3f s (writer thread: waiting for the GPU %.3f s, "
-                "formatting %.3f s, writing %.3f s; the reader thread inflates, parses and packs for the whole run)\n",
-                (unsigned long long)n_rec, (unsigned long long)n_lines, (unsigned long long)n_batches, ndev, secs(clk::now() - t_begin), t_wait, t_format, t_write);
+        fprintf(stderr, "excord-lr-b200: %llu records, %llu lines, %llu batches on %d GPU(s); setup (CUDA context, pinned + device buffers, BAM header) %.3f s; "
+                "stream %.3f s (writer thread: waiting for the GPU %.3f s, formatting %.3f s, writing %.3f s; the reader thread inflates, parses and packs "
+                "for the whole stream)\n",
+                (unsigned long long)n_rec, (unsigned long long)n_lines, (unsigned long long)n_batches, ndev, t_setup, secs(clk::now() - t_begin), t_wait, t_format, t_write);
     for (auto& s : slots) exlr_batch_free(s.b);
     for (auto c : ctx) exlr_destroy(c);
     return fatal;

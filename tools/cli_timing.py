@@ -21,13 +21,13 @@ args = ap.parse_args()
 exe = os.path.join(ROOT, "excord_lr_b200", "host", "excord-lr-b200")
 subprocess.check_call(["make", "-C", os.path.join(ROOT, "excord_lr_b200", "host")], stdout=subprocess.DEVNULL)
 
-cases = [("c2 HiFi 1M molecules, no SEQ/QUAL in the BAM", 1, 1.0, 0), ("c2 HiFi 50k molecules with 15 kb SEQ/QUAL per record", 1, 0.05, 15000)]
+cases = [("c2 HiFi 1M molecules, no SEQ/QUAL in the BAM", 1, 1.0, 0), ("c2 HiFi 30k molecules with 15 kb random SEQ/QUAL per record", 1, 0.03, 15000)]
 with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
     for name, cfg, scale, seq_len in cases:
         hb = synth.config(cfg, scale)
         bam, out = os.path.join(d, "x.bam"), os.path.join(d, "x.txt")
         t0 = time.time()
-        bamio.write_bam(hb, bam, ref_lens=synth.ref_lens(), seq_len=seq_len)
+        bamio.write_bam(hb, bam, ref_lens=synth.ref_lens(), seq_len=seq_len, random_seq=seq_len > 0)
         tw = time.time() - t0
         size = os.path.getsize(bam)
         best = None
