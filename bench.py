@@ -89,10 +89,17 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def make_workload(config_id, scale, rank):
-    from excord_lr_b200 import synth
+def make_workload(config_id, scale, rank, world=1, strong=False):
+    """weak scaling (default): every rank gets its own batch of the config's size (seed + rank).
+    strong: ONE dataset, cut into 64k-record batches that go round robin to the ranks; rank r keeps its share."""
+    from excord_lr_b200 import shard, synth
+    from excord_lr_b200.batch import HostBatch
     c = synth.CONFIGS[config_id]
     n = max(1, int(c["n"] * scale))
+    if strong and world > 1:
+        hb = synth.generate(c["profile"], c["seed"], n, c["chr20"], c["ultra"] if scale >= 1 else 0)
+        mine = shard.rank_batches(shard.plan_batches(hb.n_reads, 65536), rank, world)
+        return HostBatch.concat([hb.slice(a, b) for _, a, b in mine]), c
     hb = synth.generate(c["profile"], c["seed"] + 7919 * rank, n, c["chr20"], c["ultra"] if scale >= 1 else 0)
     return hb, c
 
@@ -146,6 +153,7 @@ def main():
     ap.add_argument("--reads-per-cta", type=int, default=0)
     ap.add_argument("--pipeline-parts", type=int, default=2, help="sub-batches in flight for the e2e measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="one dataset sharded round robin over the ranks instead of one batch per rank")
     ap.add_argument("--no-overlap", action="store_true", help="run kernel 1 on the same stream as the SA branch")
     ap.add_argument("--k1-ctas", type=int, default=0, help="persistent CTAs of kernel 1 per SM (1..4)")
     ap.add_argument("--k1-waves", type=int, default=0)
@@ -176,7 +184,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    hb, c = make_workload(args.config, args.scale, rank)
+    hb, c = make_workload(args.config, args.scale, rank, world, args.strong)
     p = ExlrParams.make(**c["params"])
     R, Cops, A = hb.n_reads, hb.n_ops, hb.n_sa_bytes
 
@@ -310,7 +318,7 @@ def main():
         e2e_value = R_all / (e2e_ms_max / 1e3) * args.steps
         line = {
             "metric": "alignments_per_sec", "value": value, "unit": "alignments/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "cigar_ops_per_sec": C_all / (total_ms_max / 1e3) * args.steps,
             "config": {"workload": c["name"], "records_per_gpu": R, "cigar_ops_per_gpu": Cops, "sa_bytes_per_gpu": A,

@@ -73,6 +73,22 @@ class HostBatch:
                          self.sa_bytes[int(so[a]):int(so[b])].copy(), self.ref_names,
                          None if self.qnames is None else self.qnames[a:b])
 
+    @staticmethod
+    def concat(parts: Sequence["HostBatch"]) -> "HostBatch":
+        """Batches back to back (offsets rebased); used to build one rank's shard from its round-robin batches."""
+        if not parts:
+            raise ValueError("nothing to concatenate")
+        co, so, cbase, sbase = [np.zeros(1, np.uint64)], [np.zeros(1, np.uint32)], 0, 0
+        for p in parts:
+            co.append(p.cigar_off[1:] + np.uint64(cbase))
+            so.append((p.sa_off[1:].astype(np.uint64) + sbase).astype(np.uint32))
+            cbase += p.n_ops
+            sbase += p.n_sa_bytes
+        cat = lambda f: np.concatenate([getattr(p, f) for p in parts])
+        qn = None if any(p.qnames is None for p in parts) else [q for p in parts for q in p.qnames]
+        return HostBatch(cat("cigar"), np.concatenate(co), cat("pos"), cat("tid"), cat("flag"), cat("mapq"), cat("sa_kind"),
+                         np.concatenate(so), cat("sa_bytes"), parts[0].ref_names, qn)
+
     def qname_blob(self):
         """(bytes, u32 offsets[n+1]) for the verbose formatter."""
         names = self.qnames if self.qnames is not None else ["r%09d" % i for i in range(self.n_reads)]
