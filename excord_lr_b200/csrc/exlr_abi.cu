@@ -345,7 +345,7 @@ static int run_kernels(exlr_batch* b)
         CK(cudaEventRecord(b->ev_k1_end, s1));
     }
     CK(cudaEventRecord(b->ev[EV_K1], st));
-    launch_k3a(d, c->dparams, st); b->launches++;
+    launch_k3a(d, c->dparams, (uint32_t)(b->n_reads ? b->n_ops / b->n_reads : 0), st); b->launches++;
     CK(cudaEventRecord(b->ev[EV_K3A], st));
     launch_k3b(d, c->dparams, st); b->launches++;
     CK(cudaEventRecord(b->ev[EV_K3B], st));

@@ -90,7 +90,7 @@ struct DevBatch {
     SaSum* sa_sum;          // [R] indexed like sa_list
     RawEv* raw;             // [raw_cap]: per-tile slices [0, prim_slots), then the overflow region
     uint32_t* tile_cnt;     // [R] events in each tile's slice
-    uint32_t raw_cap, prim_slots, capt_log2;
+    uint32_t raw_cap, prim_slots, capt_log2, slab;
     exlr_event* sa_ev;      // [max_events] SA-derived events, per record contiguous
     Seg* seg_pool; uint32_t seg_pool_cap;
     unsigned long long* scan_a; unsigned long long* scan_b;   // chained-scan tile status
@@ -117,7 +117,7 @@ uint32_t scan_tiles(uint32_t n_reads);
 void launch_k0(const DevBatch& B, const DevParams& P, cudaStream_t st);
 void plan_k1(DevBatch& B, int variant, uint32_t rpc, uint32_t* tiles_out);
 void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc, cudaStream_t st);
-void launch_k3a(const DevBatch& B, const DevParams& P, cudaStream_t st);
+void launch_k3a(const DevBatch& B, const DevParams& P, uint32_t mean_ops, cudaStream_t st);
 void launch_k3b(const DevBatch& B, const DevParams& P, cudaStream_t st);
 void launch_k4a(const DevBatch& B, const DevParams& P, cudaStream_t st);
 void launch_k4b(const DevBatch& B, const DevParams& P, cudaStream_t st);

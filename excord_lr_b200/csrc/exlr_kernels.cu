@@ -326,7 +326,7 @@ __device__ __forceinline__ uint32_t k1_find_read(const uint32_t* roff, uint32_t 
 
 // Where a tile's raw events go: the tile's first flush lands in its own fixed slice of the raw buffer
 // (no atomic, no round trip); anything beyond goes to the shared overflow region behind the slices.
-struct K1Out { RawEv* raw; Ctrl* ctrl; uint32_t* tile_cnt; uint32_t raw_cap, merge_min, prim_slots, capt_log2; };
+struct K1Out { RawEv* raw; Ctrl* ctrl; uint32_t* tile_cnt; uint32_t raw_cap, merge_min, prim_slots, capt_log2, slab; };
 
 // Resolve and write out the `m` staged events (m <= K1_CAP, one per thread).  Block-uniform call.
 // `spare` (meaningful in thread 0 only) is an overflow slab of K1_CAP slots reserved ahead of time, so that no flush
@@ -339,8 +339,12 @@ __device__ __forceinline__ void k1_flush(K1Smem& S, const K1Out& O, uint32_t til
         if (S.flushes == 0 && m <= capt) { S.gbase = tile << O.capt_log2; O.tile_cnt[tile] = m; S.in_slab = 0; }
         else {
             if (S.flushes == 0) O.tile_cnt[tile] = 0;                     // slice unused: everything of this tile overflows
-            S.gbase = O.prim_slots + spare; S.in_slab = 1;
-            spare = atomicAdd(&O.ctrl->n_raw, (uint32_t)K1_CAP);          // not needed before the next overflowing flush
+            if (m <= O.slab) {
+                S.gbase = O.prim_slots + spare; S.in_slab = 1;
+                spare = atomicAdd(&O.ctrl->n_raw, O.slab);                // not needed before the next overflowing flush
+            } else {                                                      // larger than a slab: exact, synchronous reservation
+                S.gbase = O.prim_slots + atomicAdd(&O.ctrl->n_raw, m); S.in_slab = 0;
+            }
         }
         S.flushes++;
     }
@@ -378,7 +382,7 @@ __device__ __forceinline__ void k1_flush(K1Smem& S, const K1Out& O, uint32_t til
             d[0] = make_uint4(S.rkeep[i] ? ra + i : 0xffffffffu, seq, L, ev.n_type);
             d[1] = make_uint4(prevL, 0u, 0u, 0u);
         } else O.ctrl->overflow = 1;
-    } else if (S.in_slab && slot < O.raw_cap) {
+    } else if (S.in_slab && t < O.slab && slot < O.raw_cap) {
         reinterpret_cast<uint4*>(O.raw + slot)[0] = make_uint4(0xffffffffu, 0u, 0u, 0u);   // unused slab slot
     }
     __syncthreads();                                    // every seq computed before rcnt moves
@@ -471,7 +475,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
         for (int s = 0; s < K1_STAGES; s++) mbar_init(&S.full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        spare = atomicAdd(&B.ctrl->n_raw, (uint32_t)K1_CAP);
+        spare = atomicAdd(&B.ctrl->n_raw, B.slab);
     }
     // per-record inputs of the next tile that is known to need the full scan, prefetched into registers (see the tile loop)
     unsigned long long pre_off = 0; uint32_t pre_flag = 0, pre_mapq = 0, pre_pos = 0, pre_tile = 0xffffffffu;
@@ -497,7 +501,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
     if (t == 0) issue_upto(K1_STAGES);
 
     const uint32_t imin16 = P.indel_min >= (1u << 28) ? 0xffffffffu : (P.indel_min << 4);
-    const K1Out O{B.raw, B.ctrl, B.tile_cnt, B.raw_cap, P.merge_min, B.prim_slots, B.capt_log2};
+    const K1Out O{B.raw, B.ctrl, B.tile_cnt, B.raw_cap, P.merge_min, B.prim_slots, B.capt_log2, B.slab};
     uint32_t gs = 0;                                       // scan steps done by this CTA (= chunks consumed)
     for (uint32_t it = 0; it < ntile; it++) {
         const uint32_t tile = blockIdx.x + it * gridDim.x;
@@ -654,7 +658,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
     if (t == 0) s_last = last;
     __syncthreads();
     const uint32_t slot = B.prim_slots + s_last + t;
-    if (slot < B.raw_cap) reinterpret_cast<uint4*>(B.raw + slot)[0] = make_uint4(0xffffffffu, 0u, 0u, 0u);
+    if (t < B.slab && slot < B.raw_cap) reinterpret_cast<uint4*>(B.raw + slot)[0] = make_uint4(0xffffffffu, 0u, 0u, 0u);
 }
 
 // ======================================================================================
@@ -670,7 +674,7 @@ __device__ __forceinline__ K3aAcc k3a_walk(const DevBatch& B, uint32_t r, unsign
     const uint32_t sub = threadIdx.x & (G - 1);
     K3aAcc a{0, 0, 0, 0, 0, 0, 0};
     bool seenM = false;
-    constexpr int U = G == 32 ? 8 : 4;                                         // independent loads in flight per lane
+    constexpr int U = G == 32 ? 8 : (G == 8 ? 4 : 8);                          // independent loads in flight per lane
     for (unsigned long long b = o0; b < o1; b += (unsigned long long)G * U) {
         uint32_t vv[U];
 #pragma unroll
@@ -714,31 +718,34 @@ __device__ __forceinline__ void k3a_store(const DevBatch& B, uint32_t j, const K
 
 static constexpr uint32_t K3A_LONG = 96;       // CIGARs longer than this are walked by the whole warp
 
-// Each warp takes four consecutive SA-list entries: short CIGARs are walked by the four 8-lane groups side by side,
-// long ones (ONT: 10^3..10^5 ops) by all 32 lanes one after the other, so the loads stay 128-byte coalesced.
+// Each warp takes 32/G consecutive SA-list entries: short CIGARs are walked by the G-lane groups side by side, long ones
+// (ONT: 10^3..10^5 ops) by all 32 lanes one after the other, so the loads stay 128-byte coalesced.  G is picked by the host
+// from the batch's mean CIGAR length (2 lanes for the few-op records of split-heavy batches, 8 for HiFi-like CIGARs).
+template <int G>
 __global__ void __launch_bounds__(256) k3a_sa_cigar(DevBatch B, DevParams P)
 {
+    constexpr uint32_t PER_WARP = 32 / G;
     const uint32_t n_sa = B.ctrl->n_sa;
-    const uint32_t lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
-    const uint32_t gmask = 0xffu << (grp * 8);
+    const uint32_t lane = threadIdx.x & 31, sub = lane & (G - 1), grp = lane / G;
+    const uint32_t gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (grp * G);
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t j0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4; j0 < n_sa; j0 += warps * 4) {
+    for (uint32_t j0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * PER_WARP; j0 < n_sa; j0 += warps * PER_WARP) {
         const uint32_t j = j0 + grp;
         const bool have = j < n_sa;
         uint32_t r = 0; unsigned long long o0 = 0, o1 = 0;
         if (have) { r = B.sa_list[j]; o0 = B.cigar_off[r]; o1 = B.cigar_off[r + 1]; }
         const bool is_long = have && (o1 - o0) > K3A_LONG;
         if (have && !is_long) {
-            const K3aAcc a = k3a_walk<8>(B, r, o0, o1, gmask, grp * 8);
+            const K3aAcc a = k3a_walk<G>(B, r, o0, o1, gmask, grp * G);
             if (sub == 0) k3a_store(B, j, a);
         }
-        uint32_t longs = __ballot_sync(0xffffffffu, is_long && sub == 0);     // one bit per group (lanes 0, 8, 16, 24)
+        uint32_t longs = __ballot_sync(0xffffffffu, is_long && sub == 0);     // one bit per group (its lane 0)
         while (longs) {
             const int src = __ffs(longs) - 1; longs &= longs - 1;
             const uint32_t rr = __shfl_sync(0xffffffffu, r, src);
             const unsigned long long a0 = __shfl_sync(0xffffffffu, o0, src), a1 = __shfl_sync(0xffffffffu, o1, src);
             const K3aAcc a = k3a_walk<32>(B, rr, a0, a1, 0xffffffffu, 0);
-            if (lane == 0) k3a_store(B, j0 + (src >> 3), a);
+            if (lane == 0) k3a_store(B, j0 + (uint32_t)src / G, a);
         }
     }
 }
@@ -1319,6 +1326,7 @@ void plan_k1(DevBatch& B, int variant, uint32_t rpc, uint32_t* tiles_out)
     if (rpc > K1_MAX_RPC) rpc = K1_MAX_RPC;
     const uint32_t n_tiles = (B.n_reads + rpc - 1) / rpc;
     B.prim_slots = 0; B.capt_log2 = 0;
+    B.slab = rpc >= 32 ? (uint32_t)K1_CAP : 16u;                         // overflow slab: small when tiles hold few records
     if (variant == 0) {
         int lg = 7;                                                       // up to K1_CAP = 128 slots per tile
         while (lg >= 0 && ((unsigned long long)n_tiles << lg) > (B.raw_cap - kRawSlabHeadroom) / 2) lg--;
@@ -1342,11 +1350,16 @@ void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc,
     }
 }
 
-void launch_k3a(const DevBatch& B, const DevParams& P, cudaStream_t st)
+void launch_k3a(const DevBatch& B, const DevParams& P, uint32_t mean_ops, cudaStream_t st)
 {
     // grid-stride over a device-side count: size for the worst case, cap at a few waves
-    const uint32_t ga = min((B.n_reads + 31u) / 32u, (uint32_t)g_sm_count * 16u);
-    k3a_sa_cigar<<<ga ? ga : 1u, 256, 0, st>>>(B, P);
+    if (mean_ops <= 16) {
+        const uint32_t g = min((B.n_reads + 127u) / 128u, (uint32_t)g_sm_count * 16u);
+        k3a_sa_cigar<2><<<g ? g : 1u, 256, 0, st>>>(B, P);
+    } else {
+        const uint32_t g = min((B.n_reads + 31u) / 32u, (uint32_t)g_sm_count * 16u);
+        k3a_sa_cigar<8><<<g ? g : 1u, 256, 0, st>>>(B, P);
+    }
 }
 
 void launch_k3b(const DevBatch& B, const DevParams& P, cudaStream_t st)
