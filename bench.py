@@ -210,6 +210,9 @@ def main():
         r = big.wait_resident()
         return r, big.timing()
 
+    # the timed steps run without the per-stage events (they cost a few microseconds of launch gap each); stage times and the
+    # roofline kernel's duration are taken in extra, untimed-for-`value` steps below
+    ex.set_option(api.EXLR_OPT_STAGE_TIMING, 0)
     for _ in range(args.warmup):
         r, _t = resident_step()
     assert r.status == 0, f"status {r.status}"
@@ -217,36 +220,39 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    step_ms, k1_ms, stage_ms, launches = [], [], {}, 0
+    step_ms, launches = [], 0
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         r, t = resident_step()
-        step_ms.append(t.kernels_ms + t.d2h_ms + t.classify_ms * 0)       # first kernel start -> result header on the host
-        k1_ms.append(t.cigar_ms)
+        step_ms.append(t.kernels_ms + t.d2h_ms)                            # first kernel start -> result header on the host
         launches += t.launches
-        for k, v in t.as_dict().items():
-            if k.endswith("_ms"):
-                stage_ms[k] = stage_ms.get(k, 0.0) + v / args.steps
     barrier()
     wall_resident = time.perf_counter() - wall0
-    clocks = sampler.stop()
     total_ms = float(np.sum(step_ms))
-    # the dominant kernel on its own: the same steps with every kernel on one stream, so that kernel 1's launch duration is
-    # not stretched by the SA branch running beside it (that overlap is what `value` measures)
-    k1_overlapped_ms = float(np.mean(k1_ms)) if k1_ms else float("nan")
-    if not args.no_overlap and not c["params"].get("split_only"):
-        ex.set_option(api.EXLR_OPT_OVERLAP, 0)
-        k1_ms, solo_stage = [], {}
-        for i in range(3 + min(args.steps, 20)):
-            r, t = resident_step()
+
+    def diag(n):
+        acc, k1 = {}, []
+        for i in range(3 + n):
+            _r, t = resident_step()
             if i >= 3:
-                k1_ms.append(t.cigar_ms)
+                k1.append(t.cigar_ms)
                 for k, v in t.as_dict().items():
                     if k.endswith("_ms"):
-                        solo_stage[k] = solo_stage.get(k, 0.0) + v / min(args.steps, 20)
+                        acc[k] = acc.get(k, 0.0) + v / n
+        return acc, k1
+    ex.set_option(api.EXLR_OPT_STAGE_TIMING, 1)
+    nd = min(args.steps, 20)
+    stage_ms, k1_beside = diag(nd)                                         # as configured (kernel 1 beside the SA branch)
+    k1_overlapped_ms = float(np.mean(k1_beside)) if k1_beside else float("nan")
+    # the dominant kernel on its own: every kernel on one stream, so kernel 1's launch duration is not stretched by the SA branch
+    if not args.no_overlap and not c["params"].get("split_only"):
+        ex.set_option(api.EXLR_OPT_OVERLAP, 0)
+        solo_stage, k1_ms = diag(nd)
         ex.set_option(api.EXLR_OPT_OVERLAP, 1)
     else:
-        solo_stage = dict(stage_ms)
+        solo_stage, k1_ms = dict(stage_ms), k1_beside
+    ex.set_option(api.EXLR_OPT_STAGE_TIMING, 0)
+    clocks = sampler.stop()
 
     # ---------------- PCIe ceiling: one pinned 256 MB host->device copy, best of 10 ----------------
     pin = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()

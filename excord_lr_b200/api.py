@@ -24,6 +24,7 @@ EXLR_OPT_READS_PER_CTA = 2
 EXLR_OPT_OVERLAP = 3
 EXLR_OPT_K1_CTAS_PER_SM = 4
 EXLR_OPT_K1_WAVES = 5
+EXLR_OPT_STAGE_TIMING = 6
 CIGAR_KERNEL_FLAT, CIGAR_KERNEL_WARP = 0, 1
 
 

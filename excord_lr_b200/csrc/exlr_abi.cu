@@ -38,6 +38,7 @@ struct exlr_ctx {
     uint8_t* d_ref_bytes = nullptr; uint32_t* d_ref_off = nullptr; int n_ref = 0;
     int cigar_kernel = 0;                      // EXLR_OPT_CIGAR_KERNEL
     int overlap = 1;                           // EXLR_OPT_OVERLAP: kernel 1 on a second stream beside the SA branch
+    int stage_timing = 1;                      // EXLR_OPT_STAGE_TIMING: CUDA events between the kernels (exlr_timing per stage)
     int k1_ctas = 0;                           // EXLR_OPT_K1_CTAS_PER_SM (0 = 3 when overlapping, which leaves room for the SA branch, else 4)
     uint32_t reads_per_cta = 0;                // EXLR_OPT_READS_PER_CTA (0 = auto)
 };
@@ -55,7 +56,7 @@ struct exlr_batch {
     DevBatch dv{};
     size_t ctrl_bytes = 0;                     // ctrl + both scan status arrays (one memset)
     uint64_t n_reads = 0, n_ops = 0;
-    bool submitted = false, resident_uploaded = false, have_timing = false;
+    bool submitted = false, resident_uploaded = false, have_timing = false, stage_timed = false;
     uint32_t launches = 0;
 };
 
@@ -172,6 +173,7 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
     case EXLR_OPT_CIGAR_KERNEL: if (value != 0 && value != 1) return EXLR_ERR_ARG; c->cigar_kernel = (int)value; return EXLR_OK;
     case EXLR_OPT_READS_PER_CTA: if (value < 0 || value > 128) return EXLR_ERR_ARG; c->reads_per_cta = (uint32_t)value; return EXLR_OK;
     case EXLR_OPT_OVERLAP: c->overlap = value != 0; return EXLR_OK;
+    case EXLR_OPT_STAGE_TIMING: c->stage_timing = value != 0; return EXLR_OK;
     case EXLR_OPT_K1_WAVES: if (value < 1 || value > 16) return EXLR_ERR_ARG; set_k1_waves((int)value); return EXLR_OK;
     case EXLR_OPT_K1_CTAS_PER_SM: if (value < 0 || value > 4) return EXLR_ERR_ARG; c->k1_ctas = (int)value; return EXLR_OK;
     default: return EXLR_ERR_ARG;
@@ -322,7 +324,7 @@ static uint32_t auto_rpc(uint64_t n_reads, uint64_t n_ops)
 static int run_kernels(exlr_batch* b)
 {
     exlr_ctx* c = b->ctx; cudaStream_t st = b->stream; DevBatch& d = b->dv;
-    b->launches = 0;
+    b->launches = 0; b->stage_timed = c->stage_timing != 0;
     CK(cudaMemsetAsync(d.ctrl, 0, b->ctrl_bytes, st));
     // kernel 1 needs nothing from kernel 0, so it runs on a second stream beside the SA branch (0 -> 3a -> 3b); 4a joins them
     d.prim_slots = 0; d.capt_log2 = 0;
@@ -336,22 +338,22 @@ static int run_kernels(exlr_batch* b)
         if (overlap) CK(cudaEventRecord(b->ev_fork, st));                  // after the memset
     }
     launch_k0(d, c->dparams, st); b->launches++;
-    CK(cudaEventRecord(b->ev[EV_K0], st));
+    if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K0], st));
     if (!c->params.split_only) {
         cudaStream_t s1 = overlap ? b->stream2 : st;
         if (overlap) CK(cudaStreamWaitEvent(s1, b->ev_fork, 0));
-        CK(cudaEventRecord(b->ev_k1_begin, s1));
+        if (c->stage_timing) CK(cudaEventRecord(b->ev_k1_begin, s1));
         launch_k1(d, c->dparams, c->cigar_kernel, rpc, s1); b->launches++;
         CK(cudaEventRecord(b->ev_k1_end, s1));
     }
-    CK(cudaEventRecord(b->ev[EV_K1], st));
+    if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K1], st));
     launch_k3a(d, c->dparams, (uint32_t)(b->n_reads ? b->n_ops / b->n_reads : 0), st); b->launches++;
-    CK(cudaEventRecord(b->ev[EV_K3A], st));
+    if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K3A], st));
     launch_k3b(d, c->dparams, st); b->launches++;
-    CK(cudaEventRecord(b->ev[EV_K3B], st));
+    if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K3B], st));
     if (overlap) CK(cudaStreamWaitEvent(st, b->ev_k1_end, 0));
     launch_k4a(d, c->dparams, st); b->launches++;
-    CK(cudaEventRecord(b->ev[EV_K4A], st));
+    if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K4A], st));
     launch_k4b(d, c->dparams, st); b->launches++;
     CK(cudaEventRecord(b->ev[EV_K4B], st));
     CK(cudaMemcpyAsync(b->h_ctrl, d.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
@@ -459,12 +461,14 @@ int exlr_get_timing(exlr_batch* b, exlr_timing* t)
     CK(cudaSetDevice(b->ctx->device));
     CK(cudaEventSynchronize(b->ev[EV_D2H]));
     CK(cudaEventElapsedTime(&t->h2d_ms, b->ev[EV_START], b->ev[EV_H2D]));
-    CK(cudaEventElapsedTime(&t->classify_ms, b->ev[EV_H2D], b->ev[EV_K0]));
-    if (b->ctx->params.split_only) t->cigar_ms = 0.f; else CK(cudaEventElapsedTime(&t->cigar_ms, b->ev_k1_begin, b->ev_k1_end));
-    CK(cudaEventElapsedTime(&t->sa_cigar_ms, b->ev[EV_K1], b->ev[EV_K3A]));
-    CK(cudaEventElapsedTime(&t->sa_parse_ms, b->ev[EV_K3A], b->ev[EV_K3B]));
-    CK(cudaEventElapsedTime(&t->scan_ms, b->ev[EV_K3B], b->ev[EV_K4A]));
-    CK(cudaEventElapsedTime(&t->place_ms, b->ev[EV_K4A], b->ev[EV_K4B]));
+    if (b->stage_timed) {
+        CK(cudaEventElapsedTime(&t->classify_ms, b->ev[EV_H2D], b->ev[EV_K0]));
+        if (b->ctx->params.split_only) t->cigar_ms = 0.f; else CK(cudaEventElapsedTime(&t->cigar_ms, b->ev_k1_begin, b->ev_k1_end));
+        CK(cudaEventElapsedTime(&t->sa_cigar_ms, b->ev[EV_K1], b->ev[EV_K3A]));
+        CK(cudaEventElapsedTime(&t->sa_parse_ms, b->ev[EV_K3A], b->ev[EV_K3B]));
+        CK(cudaEventElapsedTime(&t->scan_ms, b->ev[EV_K3B], b->ev[EV_K4A]));
+        CK(cudaEventElapsedTime(&t->place_ms, b->ev[EV_K4A], b->ev[EV_K4B]));
+    }
     CK(cudaEventElapsedTime(&t->kernels_ms, b->ev[EV_H2D], b->ev[EV_K4B]));
     CK(cudaEventElapsedTime(&t->d2h_ms, b->ev[EV_K4B], b->ev[EV_D2H]));
     t->launches = b->launches;

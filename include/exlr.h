@@ -160,6 +160,7 @@ typedef struct exlr_batch exlr_batch;
 #define EXLR_OPT_READS_PER_CTA 2 /* 0 = auto */
 #define EXLR_OPT_OVERLAP 3       /* 1 (default) = kernel 1 runs on a second stream beside kernels 0/3a/3b */
 #define EXLR_OPT_K1_CTAS_PER_SM 4 /* 1..4 CTAs of kernel 1 per SM; 0 (default) = 3 when overlapping, else 4 */
+#define EXLR_OPT_STAGE_TIMING 6   /* 1 (default) = CUDA events between the kernels, so exlr_get_timing has per-stage times */
 #define EXLR_OPT_K1_WAVES 5       /* kernel 1 grid = SMs x CTAs/SM x waves (default 3) */
 
 /* ---- lifecycle ---------------------------------------------------------------------- */
