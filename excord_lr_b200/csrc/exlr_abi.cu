@@ -38,6 +38,7 @@ struct exlr_ctx {
     uint8_t* d_ref_bytes = nullptr; uint32_t* d_ref_off = nullptr; int n_ref = 0;
     int cigar_kernel = 0;                      // EXLR_OPT_CIGAR_KERNEL
     int overlap = 1;                           // EXLR_OPT_OVERLAP: kernel 1 on a second stream beside the SA branch
+    int trace = 0;                             // EXLR_OPT_TRACE: kernel 1 writes a per-CTA timeline (debug)
     int stage_timing = 1;                      // EXLR_OPT_STAGE_TIMING: CUDA events between the kernels (exlr_timing per stage)
     int k1_ctas = 0;                           // EXLR_OPT_K1_CTAS_PER_SM (0 = 3 when overlapping, which leaves room for the SA branch, else 4)
     uint32_t reads_per_cta = 0;                // EXLR_OPT_READS_PER_CTA (0 = auto)
@@ -58,6 +59,7 @@ struct exlr_batch {
     uint64_t n_reads = 0, n_ops = 0;
     bool submitted = false, resident_uploaded = false, have_timing = false, stage_timed = false;
     uint32_t launches = 0;
+    unsigned long long* d_dbg = nullptr;
 };
 
 // kernel 1 reserves overflow slabs of 128 raw slots ahead of use (one spare per persistent CTA, see k1_flush): room for
@@ -173,6 +175,7 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
     case EXLR_OPT_CIGAR_KERNEL: if (value != 0 && value != 1) return EXLR_ERR_ARG; c->cigar_kernel = (int)value; return EXLR_OK;
     case EXLR_OPT_READS_PER_CTA: if (value < 0 || value > 128) return EXLR_ERR_ARG; c->reads_per_cta = (uint32_t)value; return EXLR_OK;
     case EXLR_OPT_OVERLAP: c->overlap = value != 0; return EXLR_OK;
+    case EXLR_OPT_TRACE: c->trace = value != 0; return EXLR_OK;
     case EXLR_OPT_STAGE_TIMING: c->stage_timing = value != 0; return EXLR_OK;
     case EXLR_OPT_K1_WAVES: if (value < 1 || value > 16) return EXLR_ERR_ARG; set_k1_waves((int)value); return EXLR_OK;
     case EXLR_OPT_K1_CTAS_PER_SM: if (value < 0 || value > 4) return EXLR_ERR_ARG; c->k1_ctas = (int)value; return EXLR_OK;
@@ -239,7 +242,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
                  d_flag = dcarve(R * 2), d_mapq = dcarve(R), d_kind = dcarve(R), d_soff = dcarve((R + 1) * 4), d_sab = dcarve(max_sa_bytes + 16),
                  d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
                  d_raw = dcarve((max_events + kRawHeadroom) * sizeof(RawEv)), d_saev = dcarve(max_events * sizeof(exlr_event)),
-                 d_pool = dcarve(pool_cap * sizeof(Seg)), d_loff = dcarve((R + 1) * 4), d_ev = dcarve(max_events * sizeof(exlr_event));
+                 d_pool = dcarve(pool_cap * sizeof(Seg)), d_dbg = dcarve(8192 * 32), d_loff = dcarve((R + 1) * 4), d_ev = dcarve(max_events * sizeof(exlr_event));
     e = cudaMalloc(&b->d_slab, dof);
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaMalloc(batch)"); }
     char* ds = (char*)b->d_slab;
@@ -255,6 +258,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     v.k1 = (uint2*)(ds + d_k1); v.csa = (uint32_t*)(ds + d_csa); v.sa_list = (uint32_t*)(ds + d_list); v.sa_base = (uint32_t*)(ds + d_base);
     v.sa_sum = (SaSum*)(ds + d_sum); v.raw = (RawEv*)(ds + d_raw); v.sa_ev = (exlr_event*)(ds + d_saev);
     v.seg_pool = (Seg*)(ds + d_pool); v.seg_pool_cap = (uint32_t)pool_cap;
+    b->d_dbg = (unsigned long long*)(ds + d_dbg); v.dbg = nullptr;
     v.line_off = (uint32_t*)(ds + d_loff); v.events = (exlr_event*)(ds + d_ev);
     v.n_reads = 0; v.max_events = (uint32_t)max_events;
     // the SA branch (kernels 0, 3a, 3b) is the longer chain: its stream gets the higher priority so its CTAs are placed first
@@ -325,6 +329,7 @@ static int run_kernels(exlr_batch* b)
 {
     exlr_ctx* c = b->ctx; cudaStream_t st = b->stream; DevBatch& d = b->dv;
     b->launches = 0; b->stage_timed = c->stage_timing != 0;
+    d.dbg = c->trace ? b->d_dbg : nullptr;
     CK(cudaMemsetAsync(d.ctrl, 0, b->ctrl_bytes, st));
     // kernel 1 needs nothing from kernel 0, so it runs on a second stream beside the SA branch (0 -> 3a -> 3b); 4a joins them
     d.prim_slots = 0; d.capt_log2 = 0;
@@ -472,6 +477,15 @@ int exlr_get_timing(exlr_batch* b, exlr_timing* t)
     CK(cudaEventElapsedTime(&t->kernels_ms, b->ev[EV_H2D], b->ev[EV_K4B]));
     CK(cudaEventElapsedTime(&t->d2h_ms, b->ev[EV_K4B], b->ev[EV_D2H]));
     t->launches = b->launches;
+    return EXLR_OK;
+}
+
+int exlr_get_trace(exlr_batch* b, unsigned long long* out, uint32_t n_ctas)
+{
+    if (!b || !out || n_ctas > 8192) return EXLR_ERR_ARG;
+    CK(cudaSetDevice(b->ctx->device));
+    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaMemcpy(out, b->d_dbg, (size_t)n_ctas * 32, cudaMemcpyDeviceToHost));
     return EXLR_OK;
 }
 

@@ -99,6 +99,7 @@ struct DevBatch {
     uint32_t* line_off;     // [R+1]
     exlr_event* events;     // [max_events]
     uint32_t n_reads; uint32_t max_events;
+    unsigned long long* dbg;    // optional per-CTA trace of kernel 1 (EXLR_OPT_TRACE): {start, first data, end, tiles | scanned tiles << 32}
 };
 
 struct DevParams {

@@ -44,6 +44,7 @@ __device__ __forceinline__ void report(Ctrl* c, uint32_t read, uint32_t rank)
 }
 
 __device__ __forceinline__ uint32_t abs_diff(uint32_t a, uint32_t b) { return a > b ? a - b : b - a; }
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 // ops consuming the reference in the indel arm: M(0) D(2) N(3) =(7)   (main.rs:528-545, 586-598)
 __device__ __forceinline__ uint32_t consumes_ref(uint32_t op) { return (0x8Du >> op) & 1u; }
@@ -465,6 +466,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
     K1Smem& S = *reinterpret_cast<K1Smem*>(k1_smem_raw);
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (blockIdx.x >= n_tiles) return;
+    const unsigned long long tr_start = B.dbg ? gtimer() : 0ull; unsigned long long tr_first = 0; uint32_t tr_scanned = 0;
     const uint32_t ntile = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;         // <= K1_MAX_TILES (host)
     for (uint32_t k = t; k < 2 * ntile; k += K1_THREADS) {
         const unsigned long long rec = (unsigned long long)(blockIdx.x + (k >> 1) * gridDim.x) * rpc + ((k & 1) ? rpc : 0u);
@@ -537,6 +539,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
                     asm("{\n.reg .pred p;\nsetp.ge.u32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(sus) : "r"(vv[k]), "r"(imin16), "r"(f));
                 }
             }
+            if (B.dbg && !tr_first) tr_first = gtimer();
             if (!__syncthreads_or((sus & 2u) | (flags & 0x40u))) {
                 if (t < nr) B.k1[ra + t] = make_uint2(0u, 0u);
                 if (t == 0) B.tile_cnt[tile] = 0;
@@ -545,6 +548,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
                 continue;
             }
         }
+        tr_scanned++;
         // per-record state of the tile: from the register prefetch when this tile was known to need the scan (long records),
         // straight from global memory otherwise (a screened tile that turned out to hold events)
         if (pre_tile != it && t < nr) {
@@ -651,6 +655,10 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
             B.k1[ra + t] = make_uint2(T, info);
         }
         __syncthreads();                                   // the next tile re-initialises the per-record arrays
+    }
+    if (B.dbg && t == 0) {
+        unsigned long long* d = B.dbg + 4ull * blockIdx.x;
+        d[0] = tr_start; d[1] = tr_first; d[2] = gtimer(); d[3] = (unsigned long long)ntile | ((unsigned long long)tr_scanned << 32);
     }
     // the slab still held in reserve was never used: blank it
     const uint32_t last = __shfl_sync(0xffffffffu, spare, 0);

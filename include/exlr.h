@@ -160,6 +160,7 @@ typedef struct exlr_batch exlr_batch;
 #define EXLR_OPT_READS_PER_CTA 2 /* 0 = auto */
 #define EXLR_OPT_OVERLAP 3       /* 1 (default) = kernel 1 runs on a second stream beside kernels 0/3a/3b */
 #define EXLR_OPT_K1_CTAS_PER_SM 4 /* 1..4 CTAs of kernel 1 per SM; 0 (default) = 3 when overlapping, else 4 */
+#define EXLR_OPT_TRACE 7          /* debug: kernel 1 records a per-CTA timeline, read back with exlr_get_trace */
 #define EXLR_OPT_STAGE_TIMING 6   /* 1 (default) = CUDA events between the kernels, so exlr_get_timing has per-stage times */
 #define EXLR_OPT_K1_WAVES 5       /* kernel 1 grid = SMs x CTAs/SM x waves (default 3) */
 
@@ -194,6 +195,8 @@ int  exlr_wait(exlr_batch* b, exlr_result* res);
 /* Like exlr_wait but leaves events on the device (only the 64-byte result header is read). */
 int  exlr_wait_resident(exlr_batch* b, exlr_result* res);
 int  exlr_get_timing(exlr_batch* b, exlr_timing* t);
+/* debug (EXLR_OPT_TRACE): 4 x u64 per CTA of kernel 1 {globaltimer at start, at first data, at end, tiles | scanned tiles << 32} */
+int  exlr_get_trace(exlr_batch* b, unsigned long long* out, uint32_t n_ctas);
 
 /* ---- host formatter: utils.rs:196-283 ------------------------------------------------- */
 /* Writes the lines of events [ev_begin, ev_end) of `res` into out (capacity out_cap) and
