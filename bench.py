@@ -36,11 +36,11 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+def load_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), if any."""
     try:
-        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
-            return json.load(f)
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
     except Exception:
         return None
 
@@ -149,9 +149,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs[i]")
     ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--cigar-kernel", type=int, default=0, help="0 flat TMA scan (default), 1 warp per record")
+    ap.add_argument("--cigar-kernel", type=int, default=0, help="0 auto (default), 1 warp per record, 2 flat block scan, 3 streaming screen + thread per record")
     ap.add_argument("--reads-per-cta", type=int, default=0)
-    ap.add_argument("--pipeline-parts", type=int, default=2, help="sub-batches in flight for the e2e measurement")
+    ap.add_argument("--pipeline-parts", type=int, default=3, help="sub-batches in flight for the e2e measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strong", action="store_true", help="one dataset sharded round robin over the ranks instead of one batch per rank")
     ap.add_argument("--no-overlap", action="store_true", help="run kernel 1 on the same stream as the SA branch")
@@ -231,26 +231,27 @@ def main():
     total_ms = float(np.sum(step_ms))
 
     def diag(n):
-        acc, k1 = {}, []
+        acc, k1, k1a = {}, [], []
         for i in range(3 + n):
             _r, t = resident_step()
             if i >= 3:
                 k1.append(t.cigar_ms)
+                k1a.append(t.screen_ms)
                 for k, v in t.as_dict().items():
                     if k.endswith("_ms"):
                         acc[k] = acc.get(k, 0.0) + v / n
-        return acc, k1
+        return acc, k1, k1a
     ex.set_option(api.EXLR_OPT_STAGE_TIMING, 1)
     nd = min(args.steps, 20)
-    stage_ms, k1_beside = diag(nd)                                         # as configured (kernel 1 beside the SA branch)
+    stage_ms, k1_beside, _ = diag(nd)                                      # as configured (kernel 1 beside the SA branch)
     k1_overlapped_ms = float(np.mean(k1_beside)) if k1_beside else float("nan")
     # the dominant kernel on its own: every kernel on one stream, so kernel 1's launch duration is not stretched by the SA branch
     if not args.no_overlap and not c["params"].get("split_only"):
         ex.set_option(api.EXLR_OPT_OVERLAP, 0)
-        solo_stage, k1_ms = diag(nd)
+        solo_stage, k1_ms, k1a_ms = diag(nd)
         ex.set_option(api.EXLR_OPT_OVERLAP, 1)
     else:
-        solo_stage, k1_ms = dict(stage_ms), k1_beside
+        solo_stage, k1_ms, k1a_ms = dict(stage_ms), k1_beside, [0.0]
     ex.set_option(api.EXLR_OPT_STAGE_TIMING, 0)
     clocks = sampler.stop()
 
@@ -268,35 +269,41 @@ def main():
     parts = split_for_pipeline(hb, max(1, args.pipeline_parts))
     pbatches = [ex.batch_for(h) for h in parts]                              # pinned views already hold the packed records
 
-    def e2e_step():
-        for b in pbatches:
-            b.submit()
-        tot = 0
-        for b in pbatches:
-            rr = b.wait(copy=False)
-            tot += rr.n_events
+    def e2e_steps(k):
+        """k steps through exlr_submit / exlr_wait the way a streaming caller (the CLI) uses them: a ring of sub-batches, each
+        waited (events + line offsets read back to the host) right before its buffers are re-submitted with the next step's
+        records, so the H2D engine never idles between steps.  Every step's inputs cross PCIe and every step's result is read."""
+        tot, busy = 0, [False] * len(pbatches)
+        for _ in range(k):
+            for i, b in enumerate(pbatches):
+                if busy[i]:
+                    tot += b.wait(copy=False).n_events
+                b.submit()
+                busy[i] = True
+        for i, b in enumerate(pbatches):
+            if busy[i]:
+                tot += b.wait(copy=False).n_events
         return tot
 
-    for _ in range(args.warmup):
-        ne = e2e_step()
-    assert ne == n_events, f"pipelined run produced {ne} lines, resident run {n_events}"
+    ne = e2e_steps(args.warmup)
+    assert ne == n_events * args.warmup, f"pipelined run produced {ne} lines, resident run {n_events} per step"
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    ne = e2e_steps(args.steps)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0)
     barrier()
+    assert ne == n_events * args.steps
     h2d = 4 * Cops + A + R * (8 + 4 + 4 + 2 + 1 + 1 + 4) + len(parts) * 12
     d2h = len(parts) * 64 + 4 * (R + len(parts)) + 48 * n_events
 
     # ---------------- reduce over ranks ----------------
-    tt = torch.tensor([total_ms, e2e_s * 1e3, float(np.sum(k1_ms))], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([total_ms, e2e_s * 1e3, float(np.sum(k1_ms)), float(np.sum(k1a_ms))], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([R, Cops, n_events], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    total_ms_max, e2e_ms_max, k1_ms_max = tt.tolist()
+    total_ms_max, e2e_ms_max, k1_ms_max, k1a_ms_max = tt.tolist()
     R_all, C_all, E_all = cnt.tolist()
 
     # ---------------- cpu baseline (rank 0, N=1 only) ----------------
@@ -315,10 +322,21 @@ def main():
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        k1_bytes = 4.0 * Cops + 11.0 * R                                  # per launch, this rank
-        k1_avg_s = (float(np.mean(k1_ms)) / 1e3) if k1_ms else float("nan")
+        # The CIGAR path of a short-record batch is kernel 1a (streaming event screen: reads every op once, writes every record's
+        # 8-byte summary and one flag per 512 ops) followed by kernel 1b on the records around the flagged steps; long-record
+        # batches get kernel 1 (flat block scan of everything).  The roofline entry is the kernel that moves the bytes.
+        screened = bool(k1a_ms) and float(np.mean(k1a_ms)) > 0
+        path_bytes = 4.0 * Cops + 11.0 * R                                # 4 B/op + offset 8 + flag 2 + mapq 1 per record
+        path_s = float(np.mean(k1_ms)) / 1e3 if k1_ms else float("nan")
+        if screened:
+            rk_name = "k1a_screen"
+            k1_bytes = 4.0 * Cops + 8.0 * R                               # every op read once + an 8-byte summary written per record
+            k1_avg_s = float(np.mean(k1a_ms)) / 1e3
+        else:
+            rk_name = "k1_flat" if args.cigar_kernel != 1 else "k1_warp"
+            k1_bytes, k1_avg_s = path_bytes, path_s
         achieved = k1_bytes / k1_avg_s / 1e9 if k1_avg_s > 0 else 0.0
-        traffic = load_traffic()
+        traffic = load_traffic(rk_name)
         pipe_bytes = 24.0 * R + 4.0 * Cops + A + 4.0 * R + 48.0 * n_events
         ms_per_step = total_ms_max / args.steps
         value = R_all / (total_ms_max / 1e3) * args.steps
@@ -331,18 +349,23 @@ def main():
             "config": {"workload": c["name"], "records_per_gpu": R, "cigar_ops_per_gpu": Cops, "sa_bytes_per_gpu": A,
                        "lines_per_gpu": n_events, "params": c["params"], "parallelism": f"dp{world} (record shards, no collective)",
                        "l2": "flushed (256 MB read) before every timed step; inputs are also larger than L2",
-                       "cigar_kernel": "flat TMA-staged block scan" if args.cigar_kernel == 0 else "warp per record"},
+                       "cigar_kernel": {0: "auto: streaming screen + thread per record around the candidates (short records) / flat TMA-staged block scan (long records)",
+                                        1: "warp per record", 2: "flat TMA-staged block scan", 3: "streaming screen + thread per record"}[args.cigar_kernel]},
             "e2e": {"value": e2e_value, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms_max / args.steps, "pipeline_parts": len(parts),
                     "h2d_gbs": h2d * args.steps / (e2e_ms_max / 1e3) / 1e9, "pcie_h2d_peak_gbs": pcie_h2d,
                     "frac_of_pcie": (h2d * args.steps / (e2e_ms_max / 1e3) / 1e9) / pcie_h2d if pcie_h2d else None,
                     "cigar_ops_per_sec": C_all / (e2e_ms_max / 1e3) * args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k1_flat" if args.cigar_kernel == 0 else "k1_warp", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": rk_name, "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k1_bytes, "avg_launch_ms": k1_avg_s * 1e3,
-                         "measured": "live CUDA events in bench.py, same-stream steps (kernel 1 alone on the GPU)",
-                         "avg_launch_ms_beside_sa_branch": k1_overlapped_ms,
+                         "measured": "live CUDA events in bench.py, same-stream steps (the kernel alone on the GPU)",
+                         "cigar_path": {"kernels": "k1a_screen + k1b_steps" if screened else rk_name,
+                                        "algorithmic_bytes": path_bytes, "ms": path_s * 1e3,
+                                        "achieved": path_bytes / path_s / 1e9 if path_s > 0 else 0.0,
+                                        "frac": (path_bytes / path_s / 1e9 / peak) if path_s > 0 else 0.0,
+                                        "ms_beside_sa_branch": k1_overlapped_ms},
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"),
                          "pipeline_achieved_gbs": pipe_bytes / (ms_per_step / 1e3) / 1e9,
                          "pipeline_frac": pipe_bytes / (ms_per_step / 1e3) / 1e9 / peak},

@@ -25,7 +25,8 @@ EXLR_OPT_OVERLAP = 3
 EXLR_OPT_K1_CTAS_PER_SM = 4
 EXLR_OPT_K1_WAVES = 5
 EXLR_OPT_STAGE_TIMING = 6
-CIGAR_KERNEL_FLAT, CIGAR_KERNEL_WARP = 0, 1
+# see EXLR_OPT_CIGAR_KERNEL in include/exlr.h
+CIGAR_KERNEL_AUTO, CIGAR_KERNEL_WARP, CIGAR_KERNEL_FLAT, CIGAR_KERNEL_SCREEN = 0, 1, 2, 3
 
 
 class ExlrError(RuntimeError):
@@ -58,10 +59,10 @@ class _Result(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("classify_ms", C.c_float), ("cigar_ms", C.c_float), ("sa_cigar_ms", C.c_float),
                 ("sa_parse_ms", C.c_float), ("scan_ms", C.c_float), ("place_ms", C.c_float), ("kernels_ms", C.c_float),
-                ("d2h_ms", C.c_float), ("launches", C.c_uint32), ("reserved", C.c_uint32)]
+                ("d2h_ms", C.c_float), ("launches", C.c_uint32), ("screen_ms", C.c_float)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 _lib = None
@@ -274,7 +275,7 @@ class Extractor:
             pass
 
 
-def extract(hb: HostBatch, params: ExlrParams, device: int = 0, cigar_kernel: int = CIGAR_KERNEL_FLAT,
+def extract(hb: HostBatch, params: ExlrParams, device: int = 0, cigar_kernel: int = CIGAR_KERNEL_AUTO,
             reads_per_cta: int = 0, verbose: bool = False, max_events: int = 0, grow: bool = True):
     """One-shot: host batch -> (Result, formatted lines).  Host buffers in, host buffers out.
     If the event buffers turn out too small the batch is re-run once with the size the device reported."""

@@ -36,7 +36,7 @@ struct exlr_ctx {
     DevParams dparams{};
     std::vector<std::string> ref_stripped;     // "chr" removed (aligments_event.rs:38-42)
     uint8_t* d_ref_bytes = nullptr; uint32_t* d_ref_off = nullptr; int n_ref = 0;
-    int cigar_kernel = 0;                      // EXLR_OPT_CIGAR_KERNEL
+    int cigar_kernel = 0;                      // EXLR_OPT_CIGAR_KERNEL (0 auto, 1 warp, 2 flat scan, 3 screen + thread per record)
     int overlap = 1;                           // EXLR_OPT_OVERLAP: kernel 1 on a second stream beside the SA branch
     int trace = 0;                             // EXLR_OPT_TRACE: kernel 1 writes a per-CTA timeline (debug)
     int stage_timing = 1;                      // EXLR_OPT_STAGE_TIMING: CUDA events between the kernels (exlr_timing per stage)
@@ -48,7 +48,8 @@ struct exlr_batch {
     exlr_ctx* ctx = nullptr;
     cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: kernel 1 runs beside the SA branch (kernels 0, 3a, 3b)
     cudaEvent_t ev[EV_COUNT] = {};
-    cudaEvent_t ev_fork = nullptr, ev_k1_begin = nullptr, ev_k1_end = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_k1_begin = nullptr, ev_k1_mid = nullptr, ev_k1_end = nullptr;
+    bool screened = false;                     // the last submit ran kernels 1a + 1b instead of kernel 1
     exlr_batch_views hv{};                     // pinned host views
     void* h_slab = nullptr;                    // pinned: inputs
     void* h_out = nullptr;                     // pinned: ctrl + line_off + events
@@ -172,10 +173,10 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
 {
     if (!c) return EXLR_ERR_ARG;
     switch (option) {
-    case EXLR_OPT_CIGAR_KERNEL: if (value != 0 && value != 1) return EXLR_ERR_ARG; c->cigar_kernel = (int)value; return EXLR_OK;
+    case EXLR_OPT_CIGAR_KERNEL: if (value < 0 || value > 3) return EXLR_ERR_ARG; c->cigar_kernel = (int)value; return EXLR_OK;
     case EXLR_OPT_READS_PER_CTA: if (value < 0 || value > 128) return EXLR_ERR_ARG; c->reads_per_cta = (uint32_t)value; return EXLR_OK;
     case EXLR_OPT_OVERLAP: c->overlap = value != 0; return EXLR_OK;
-    case EXLR_OPT_TRACE: c->trace = value != 0; return EXLR_OK;
+    case EXLR_OPT_TRACE: if (value < 0 || value > 6) return EXLR_ERR_ARG; c->trace = (int)value; return EXLR_OK;
     case EXLR_OPT_STAGE_TIMING: c->stage_timing = value != 0; return EXLR_OK;
     case EXLR_OPT_K1_WAVES: if (value < 1 || value > 16) return EXLR_ERR_ARG; set_k1_waves((int)value); return EXLR_OK;
     case EXLR_OPT_K1_CTAS_PER_SM: if (value < 0 || value > 4) return EXLR_ERR_ARG; c->k1_ctas = (int)value; return EXLR_OK;
@@ -191,6 +192,7 @@ void exlr_batch_free(exlr_batch* b)
     for (auto& e : b->ev) if (e) cudaEventDestroy(e);
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_k1_begin) cudaEventDestroy(b->ev_k1_begin);
+    if (b->ev_k1_mid) cudaEventDestroy(b->ev_k1_mid);
     if (b->ev_k1_end) cudaEventDestroy(b->ev_k1_end);
     if (b->stream2) cudaStreamDestroy(b->stream2);
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -237,10 +239,11 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     const size_t pool_cap = need_pool ? (max_sa_bytes / 10 + R + 64) : 0;
     size_t dof = 0;
     auto dcarve = [&](size_t bytes) { size_t at = dof; dof = align_up(dof + bytes, A); return at; };
-    const size_t d_ctrl = dcarve(sizeof(Ctrl) + (size_t)tiles * 16);          // ctrl | scan_a | scan_b : one memset
+    const size_t bits_bytes = align_up((R + 31) / 32 * 4, 16);
+    const size_t d_ctrl = dcarve(sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes);   // ctrl | scan_a | scan_b | dirty_bits : one memset
     const size_t d_cigar = dcarve((max_ops + 4) * 4 + 16), d_coff = dcarve((R + 1) * 8), d_pos = dcarve(R * 4), d_tid = dcarve(R * 4),
                  d_flag = dcarve(R * 2), d_mapq = dcarve(R), d_kind = dcarve(R), d_soff = dcarve((R + 1) * 4), d_sab = dcarve(max_sa_bytes + 16),
-                 d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
+                 d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_slist = dcarve((max_ops / 512 + 16) * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
                  d_raw = dcarve((max_events + kRawHeadroom) * sizeof(RawEv)), d_saev = dcarve(max_events * sizeof(exlr_event)),
                  d_pool = dcarve(pool_cap * sizeof(Seg)), d_dbg = dcarve(8192 * 32), d_loff = dcarve((R + 1) * 4), d_ev = dcarve(max_events * sizeof(exlr_event));
     e = cudaMalloc(&b->d_slab, dof);
@@ -249,7 +252,8 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     DevBatch& v = b->dv;
     v.ctrl = (Ctrl*)(ds + d_ctrl);
     v.scan_a = (unsigned long long*)(ds + d_ctrl + sizeof(Ctrl)); v.scan_b = v.scan_a + tiles;
-    b->ctrl_bytes = sizeof(Ctrl) + (size_t)tiles * 16;
+    v.dirty_bits = (uint32_t*)(v.scan_b + tiles); v.step_list = (uint32_t*)(ds + d_slist);
+    b->ctrl_bytes = sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes;
     v.cigar = (uint32_t*)(ds + d_cigar); v.cigar_off = (unsigned long long*)(ds + d_coff); v.pos = (int32_t*)(ds + d_pos);
     v.tid = (int32_t*)(ds + d_tid); v.flag = (uint16_t*)(ds + d_flag); v.mapq = (uint8_t*)(ds + d_mapq); v.sa_kind = (uint8_t*)(ds + d_kind);
     v.sa_off = (uint32_t*)(ds + d_soff); v.sa_bytes = (uint8_t*)(ds + d_sab);
@@ -269,6 +273,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&b->stream2, cudaStreamNonBlocking, prio_lo);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_fork);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_k1_begin);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev_k1_mid);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_k1_end);
     for (int i = 0; i < EV_COUNT && e == cudaSuccess; i++) e = cudaEventCreate(&b->ev[i]);
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "stream/event creation"); }
@@ -314,6 +319,9 @@ static int copy_inputs(exlr_batch* b, uint64_t n)
     return EXLR_OK;
 }
 
+// batches whose mean CIGAR is at most this long get the screen pass (kernel 1a) in front of kernel 1
+static constexpr uint64_t kScreenMaxMeanOps = 512;
+
 static uint32_t auto_rpc(uint64_t n_reads, uint64_t n_ops)
 {
     // kernel 1 scans 2048 ops per step: aim just under two steps of CIGAR per CTA for short-read batches (full
@@ -329,17 +337,25 @@ static int run_kernels(exlr_batch* b)
 {
     exlr_ctx* c = b->ctx; cudaStream_t st = b->stream; DevBatch& d = b->dv;
     b->launches = 0; b->stage_timed = c->stage_timing != 0;
-    d.dbg = c->trace ? b->d_dbg : nullptr;
+    d.dbg = c->trace ? b->d_dbg : nullptr; d.dbg_sel = (uint32_t)c->trace;
+    if (c->trace) CK(cudaMemsetAsync(b->d_dbg, 0, 8192 * 32, st));
     CK(cudaMemsetAsync(d.ctrl, 0, b->ctrl_bytes, st));
     // kernel 1 needs nothing from kernel 0, so it runs on a second stream beside the SA branch (0 -> 3a -> 3b); 4a joins them
     d.prim_slots = 0; d.capt_log2 = 0;
     const bool overlap = c->overlap && !c->params.split_only;
     set_k1_ctas_per_sm(c->k1_ctas ? c->k1_ctas : (overlap ? 3 : 4));
     uint32_t rpc = 0;
+    const int variant = c->cigar_kernel == 1 ? 1 : 0;
+    b->screened = false;
     if (!c->params.split_only) {
         rpc = c->reads_per_cta ? c->reads_per_cta : auto_rpc(b->n_reads, b->n_ops);
+        // short records (HiFi-like): events are sparse, so the CIGAR stream is screened at streaming speed (kernel 1a) and only the
+        // records around an event candidate are walked (kernel 1b); long records (ONT-like) nearly all carry one: scan everything.
+        // (kernel 1a indexes the CIGAR array by 32-bit vector numbers)
+        const bool short_records = b->n_ops / b->n_reads <= kScreenMaxMeanOps;
+        b->screened = (c->cigar_kernel == 3 || (c->cigar_kernel == 0 && short_records)) && b->n_ops < (1ull << 32) && b->n_ops > 0;
         uint32_t n_tiles = 0;
-        plan_k1(d, c->cigar_kernel, rpc, &n_tiles);
+        plan_k1(d, b->screened ? 1 : variant, rpc, &n_tiles);               // screened: raw events all go to the atomically allocated region
         if (overlap) CK(cudaEventRecord(b->ev_fork, st));                  // after the memset
     }
     launch_k0(d, c->dparams, st); b->launches++;
@@ -348,7 +364,13 @@ static int run_kernels(exlr_batch* b)
         cudaStream_t s1 = overlap ? b->stream2 : st;
         if (overlap) CK(cudaStreamWaitEvent(s1, b->ev_fork, 0));
         if (c->stage_timing) CK(cudaEventRecord(b->ev_k1_begin, s1));
-        launch_k1(d, c->dparams, c->cigar_kernel, rpc, s1); b->launches++;
+        if (b->screened) {
+            launch_k1a(d, c->dparams, b->n_ops, s1); b->launches++;
+            if (c->stage_timing) CK(cudaEventRecord(b->ev_k1_mid, s1));
+            launch_k1b(d, c->dparams, b->n_ops, s1); b->launches++;
+        } else {
+            launch_k1(d, c->dparams, variant, rpc, s1); b->launches++;
+        }
         CK(cudaEventRecord(b->ev_k1_end, s1));
     }
     if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K1], st));
@@ -469,6 +491,7 @@ int exlr_get_timing(exlr_batch* b, exlr_timing* t)
     if (b->stage_timed) {
         CK(cudaEventElapsedTime(&t->classify_ms, b->ev[EV_H2D], b->ev[EV_K0]));
         if (b->ctx->params.split_only) t->cigar_ms = 0.f; else CK(cudaEventElapsedTime(&t->cigar_ms, b->ev_k1_begin, b->ev_k1_end));
+        if (b->screened && !b->ctx->params.split_only) CK(cudaEventElapsedTime(&t->screen_ms, b->ev_k1_begin, b->ev_k1_mid));
         CK(cudaEventElapsedTime(&t->sa_cigar_ms, b->ev[EV_K1], b->ev[EV_K3A]));
         CK(cudaEventElapsedTime(&t->sa_parse_ms, b->ev[EV_K3A], b->ev[EV_K3B]));
         CK(cudaEventElapsedTime(&t->scan_ms, b->ev[EV_K3B], b->ev[EV_K4A]));

@@ -31,7 +31,8 @@ struct Ctrl {
     uint32_t overflow;              // 1 = raw / sa / final event buffer too small
     uint32_t ticket_a, ticket_b;    // dynamic tile ids of the two chained scans
     uint32_t seg_pool_used;
-    uint32_t pad[4];
+    uint32_t n_flagged;             // 512-op steps of the CIGAR stream kernel 1a found an event candidate in (length of step_list)
+    uint32_t pad[3];
 };
 static_assert(sizeof(Ctrl) == 64, "Ctrl is the 64-byte result header");
 
@@ -90,6 +91,8 @@ struct DevBatch {
     SaSum* sa_sum;          // [R] indexed like sa_list
     RawEv* raw;             // [raw_cap]: per-tile slices [0, prim_slots), then the overflow region
     uint32_t* tile_cnt;     // [R] events in each tile's slice
+    uint32_t* dirty_bits;   // [R/32] one bit per record: claimed by a thread of kernel 1b (zeroed with ctrl)
+    uint32_t* step_list;    // [max_ops/512 + 1] kernel 1a: the 512-op steps of the CIGAR stream that hold an event candidate, any order
     uint32_t raw_cap, prim_slots, capt_log2, slab;
     exlr_event* sa_ev;      // [max_events] SA-derived events, per record contiguous
     Seg* seg_pool; uint32_t seg_pool_cap;
@@ -99,7 +102,8 @@ struct DevBatch {
     uint32_t* line_off;     // [R+1]
     exlr_event* events;     // [max_events]
     uint32_t n_reads; uint32_t max_events;
-    unsigned long long* dbg;    // optional per-CTA trace of kernel 1 (EXLR_OPT_TRACE): {start, first data, end, tiles | scanned tiles << 32}
+    unsigned long long* dbg;    // optional per-CTA trace (EXLR_OPT_TRACE), 4 x u64 per entry; kernel 1: {start, first data, end, tiles | scanned tiles << 32}
+    uint32_t dbg_sel;           // which kernel writes the trace: 1 = kernel 1 / 1b, 2 = k0, 3 = k3a, 4 = k3b, 5 = k4a, 6 = k4b ({start, mid, end, 0})
 };
 
 struct DevParams {
@@ -118,6 +122,9 @@ uint32_t scan_tiles(uint32_t n_reads);
 void launch_k0(const DevBatch& B, const DevParams& P, cudaStream_t st);
 void plan_k1(DevBatch& B, int variant, uint32_t rpc, uint32_t* tiles_out);
 void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc, cudaStream_t st);
+uint32_t k1a_steps(unsigned long long n_ops);
+void launch_k1a(const DevBatch& B, const DevParams& P, unsigned long long n_ops, cudaStream_t st);
+void launch_k1b(const DevBatch& B, const DevParams& P, unsigned long long n_ops, cudaStream_t st);
 void launch_k3a(const DevBatch& B, const DevParams& P, uint32_t mean_ops, cudaStream_t st);
 void launch_k3b(const DevBatch& B, const DevParams& P, cudaStream_t st);
 void launch_k4a(const DevBatch& B, const DevParams& P, cudaStream_t st);

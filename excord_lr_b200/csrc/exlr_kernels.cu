@@ -44,6 +44,11 @@ __device__ __forceinline__ void report(Ctrl* c, uint32_t read, uint32_t rank)
 }
 
 __device__ __forceinline__ uint32_t abs_diff(uint32_t a, uint32_t b) { return a > b ? a - b : b - a; }
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may be placed on the
+// SMs while its predecessor in the stream is still draining; griddep_wait() returns once the predecessor has completed and its
+// writes are visible, so every global access of such a kernel comes after it.  griddep_launch() lets the successor be placed.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 // ops consuming the reference in the indel arm: M(0) D(2) N(3) =(7)   (main.rs:528-545, 586-598)
@@ -58,6 +63,14 @@ __device__ __forceinline__ void store_event(exlr_event* dst, int64_t ls, int64_t
     d[2] = make_uint4(read, lc, rc, meta);
 }
 
+// EXLR_OPT_TRACE for the small kernels: {CTA start, a mid point, CTA end} by thread 0, entry blockIdx.x (mod 8192)
+struct CtaTrace {
+    unsigned long long* d; unsigned long long t0, t1;
+    __device__ __forceinline__ CtaTrace(const DevBatch& B, uint32_t sel) : d(B.dbg && B.dbg_sel == sel ? B.dbg + 4ull * (blockIdx.x & 8191u) : nullptr), t0(0), t1(0) { if (d) t0 = gtimer(); }
+    __device__ __forceinline__ void mid() { if (d && !t1) t1 = gtimer(); }
+    __device__ __forceinline__ void end() { if (d && threadIdx.x == 0) { d[0] = t0; d[1] = t1; d[2] = gtimer(); d[3] = 0; } }
+};
+
 // ---- chained scan (decoupled look-back), one status word per tile: flag<<62 | value ----
 // 256 threads x 16 records = 4096 records per tile; the look-back is done by a whole warp, 32 tiles at a time.
 static constexpr int SCAN_THREADS = 256;
@@ -65,38 +78,35 @@ static constexpr int SCAN_ITEMS = 16;
 static constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 static constexpr unsigned long long ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_VALUE = (1ull << 62) - 1;
 
-// warp 0 only (all 32 lanes): publish this tile's aggregate, return the sum of all previous tiles
-__device__ __forceinline__ uint32_t chained_prefix(unsigned long long* status, uint32_t tile, uint32_t agg)
+// All SCAN_THREADS threads: publish this tile's aggregate, return the sum of all previous tiles.
+// The look-back window is the whole CTA (256 predecessors per probe, every status word fetched by its own thread), so a
+// batch of a few hundred tiles resolves in one L2 round trip instead of a serial walk of 32-tile windows.
+// Tile ids come from a ticket, so every predecessor is running or done and publishes without waiting for anybody.
+__device__ __forceinline__ uint32_t chained_prefix(unsigned long long* status, uint32_t tile, uint32_t agg,
+                                                   uint32_t* s_sum /*[8]*/, uint32_t* s_has /*[8]*/)
 {
     volatile unsigned long long* st = status;
-    const uint32_t lane = threadIdx.x & 31;
-    if (tile == 0) { if (lane == 0) st[0] = ST_PREFIX | agg; return 0; }
-    if (lane == 0) st[tile] = ST_AGG | agg;
+    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (tile == 0) { if (t == 0) st[0] = ST_PREFIX | agg; return 0; }
+    if (t == 0) st[tile] = ST_AGG | agg;
     uint32_t prefix = 0;
-    int base = (int)tile - 1;
-    for (;;) {
-        const int idx = base - (int)lane;
-        unsigned long long s = 2ull << 62;                                     // tiles before 0: prefix 0
-        if (idx >= 0) s = st[idx];
-        const uint32_t flag = (uint32_t)(s >> 62);
-        const uint32_t pmask = __ballot_sync(0xffffffffu, flag == 2u);
-        const uint32_t zmask = __ballot_sync(0xffffffffu, flag == 0u);
-        if (pmask) {
-            const int fp = __ffs(pmask) - 1;                                   // nearest tile holding an inclusive prefix
-            const uint32_t need = fp == 31 ? 0xffffffffu : ((1u << (fp + 1)) - 1u);
-            if (zmask & need) continue;                                        // a nearer tile has not published yet
-            uint32_t v = (int)lane <= fp ? (uint32_t)(s & ST_VALUE) : 0u;
-            for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-            prefix += v;
-            break;
-        }
-        if (zmask) continue;
-        uint32_t v = (uint32_t)(s & ST_VALUE);
+    for (int base = (int)tile - 1;; base -= SCAN_THREADS) {
+        const int idx = base - (int)t;
+        unsigned long long s = ST_PREFIX;                                      // tiles before 0: prefix 0
+        if (idx >= 0) { do { s = st[idx]; } while ((s >> 62) == 0ull); }
+        const uint32_t pm = __ballot_sync(0xffffffffu, (uint32_t)(s >> 62) == 2u);
+        const uint32_t fp = pm ? (uint32_t)(__ffs(pm) - 1) : 31u;             // nearest inclusive prefix inside this warp's window
+        uint32_t v = lane <= fp ? (uint32_t)(s & ST_VALUE) : 0u;
         for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        prefix += v;
-        base -= 32;
+        if (lane == 0) { s_sum[w] = v; s_has[w] = pm != 0u; }
+        __syncthreads();
+        bool found = false;
+#pragma unroll
+        for (int k = 0; k < SCAN_THREADS / 32; k++) { if (!found) { prefix += s_sum[k]; found = s_has[k] != 0u; } }
+        __syncthreads();                                                       // s_sum / s_has are reused by the next window
+        if (found) break;
     }
-    if (lane == 0) st[tile] = ST_PREFIX | (unsigned long long)(agg + prefix);
+    if (t == 0) st[tile] = ST_PREFIX | (unsigned long long)(agg + prefix);
     return prefix;
 }
 
@@ -118,17 +128,14 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
 
 // tile prefix: block scan + chained look-back; returns this thread's exclusive prefix over the whole batch
 __device__ __forceinline__ uint32_t tile_excl_scan(unsigned long long* status, uint32_t tile, uint32_t mine,
-                                                   uint32_t* s_warp, uint32_t* s_prefix, uint32_t* grand_total_if_last)
+                                                   uint32_t* s_warp /*[16]*/, uint32_t* grand_total_if_last)
 {
     uint32_t total;
     const uint32_t excl = block_excl_scan(mine, s_warp, &total);
-    if (threadIdx.x < 32) {
-        const uint32_t p = chained_prefix(status, tile, total);
-        if (threadIdx.x == 0) *s_prefix = p;
-    }
-    __syncthreads();
-    *grand_total_if_last = *s_prefix + total;
-    return *s_prefix + excl;
+    __syncthreads();                                                           // s_warp is reused by the look-back
+    const uint32_t p = chained_prefix(status, tile, total, s_warp, s_warp + 8);
+    *grand_total_if_last = p + total;
+    return p + excl;
 }
 
 // ======================================================================================
@@ -136,7 +143,9 @@ __device__ __forceinline__ uint32_t tile_excl_scan(unsigned long long* status, u
 // ======================================================================================
 __global__ void __launch_bounds__(SCAN_THREADS) k0_classify(DevBatch B, DevParams P)
 {
-    __shared__ uint32_t s_tile, s_prefix, s_warp[8];
+    __shared__ uint32_t s_tile, s_warp[16];
+    griddep_launch();                                  // kernel 3a may be placed; it waits for this grid before it reads anything
+    CtaTrace tr(B, 2);
     if (threadIdx.x == 0) s_tile = atomicAdd(&B.ctrl->ticket_a, 1u);
     __syncthreads();
     const uint32_t tile = s_tile, n = B.n_reads;
@@ -183,77 +192,83 @@ __global__ void __launch_bounds__(SCAN_THREADS) k0_classify(DevBatch B, DevParam
         }
     }
     uint32_t grand;
-    uint32_t at = tile_excl_scan(B.scan_a, tile, (uint32_t)__popc(sa_mask), s_warp, &s_prefix, &grand);
+    tr.mid();
+    uint32_t at = tile_excl_scan(B.scan_a, tile, (uint32_t)__popc(sa_mask), s_warp, &grand);
     while (sa_mask) { const int i = __ffs(sa_mask) - 1; sa_mask &= sa_mask - 1; B.sa_list[at++] = r0 + i; }
     // kept counter: one atomic per warp
     for (int d = 16; d; d >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, d);
     if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&B.ctrl->n_kept, kept);
     if (threadIdx.x == 0 && tile == (n + SCAN_TILE - 1) / SCAN_TILE - 1) B.ctrl->n_sa = grand;
+    tr.end();
 }
 
 
 // ======================================================================================
 // kernel 1 (variant B): warp per record
 // ======================================================================================
-__global__ void __launch_bounds__(256) k1_warp(DevBatch B, DevParams P)
+// One record scanned by the 32 lanes of a warp, 32 ops per step (all lanes of the warp must call).
+__device__ __forceinline__ void k1_warp_record(const DevBatch& B, const DevParams& P, uint32_t r)
 {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < B.n_reads; r += warps) {
-        const uint32_t flag = B.flag[r], mq = B.mapq[r];
-        if (!keep_record(P, flag, mq)) { if (lane == 0) B.k1[r] = make_uint2(0u, 0u); continue; }
-        const unsigned long long o0 = B.cigar_off[r], o1 = B.cigar_off[r + 1];
-        const uint32_t pos2 = (uint32_t)B.pos[r];
-        uint32_t carry = 0, cnt = 0, info = 0;
-        uint32_t pL = 0, pn = 0, pdel = 0;          // previous event of this record (warp-uniform)
-        for (unsigned long long b = o0; b < o1; b += 32) {
-            const bool valid = b + lane < o1;
-            const uint32_t v = valid ? __ldg(B.cigar + b + lane) : 0u;
-            const uint32_t op = v & 15u, len = v >> 4;
-            if (valid && op > 8u) report(B.ctrl, r, RANK_CIGAR_OP);
-            const uint32_t c = (valid && op <= 8u && consumes_ref(op)) ? len : 0u;
-            uint32_t incl = c;
+    const uint32_t flag = B.flag[r], mq = B.mapq[r];
+    if (!keep_record(P, flag, mq)) { if (lane == 0) B.k1[r] = make_uint2(0u, 0u); return; }
+    const unsigned long long o0 = B.cigar_off[r], o1 = B.cigar_off[r + 1];
+    const uint32_t pos2 = (uint32_t)B.pos[r];
+    uint32_t carry = 0, cnt = 0, info = 0;
+    uint32_t pL = 0, pn = 0, pdel = 0;          // previous event of this record (warp-uniform)
+    for (unsigned long long b = o0; b < o1; b += 32) {
+        const bool valid = b + lane < o1;
+        const uint32_t v = valid ? __ldg(B.cigar + b + lane) : 0u;
+        const uint32_t op = v & 15u, len = v >> 4;
+        if (valid && op > 8u) report(B.ctrl, r, RANK_CIGAR_OP);
+        const uint32_t c = (valid && op <= 8u && consumes_ref(op)) ? len : 0u;
+        uint32_t incl = c;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
-            const uint32_t L = carry + incl - c;
-            const bool isev = valid && (op == 1u || op == 2u) && len >= P.indel_min;
-            const uint32_t bal = __ballot_sync(0xffffffffu, isev);
-            if (bal) {
-                const uint32_t below = bal & ((1u << lane) - 1u);
-                const uint32_t rank = __popc(below);
-                const int src = below ? 31 - __clz(below) : 0;
-                uint32_t qL = __shfl_sync(0xffffffffu, L, src), qn = __shfl_sync(0xffffffffu, len, src),
-                         qdel = __shfl_sync(0xffffffffu, (uint32_t)(op == 2u), src);
-                bool has_prev = below != 0;
-                if (!has_prev && cnt) { qL = pL; qn = pn; qdel = pdel; has_prev = true; }
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&B.ctrl->n_raw, (uint32_t)__popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                uint32_t myflags = 0;
-                if (isev) {
-                    const uint32_t seq = cnt + rank, del = op == 2u;
-                    if (has_prev && del && qdel) {
-                        if (seq == 1 && abs_diff(pos2 + L, pos2 + qL + qn) < P.merge_min) myflags |= K1_PAIR_MERGE;   // main.rs:615
-                        if (abs_diff(pos2 + qL, pos2 + L + len) < P.merge_min) myflags |= K1_FAR_HIT;                 // main.rs:673-678
-                    }
-                    const uint32_t slot = B.prim_slots + base + rank;
-                    if (slot < B.raw_cap) {
-                        uint4* d = reinterpret_cast<uint4*>(B.raw + slot);
-                        d[0] = make_uint4(r, seq, L, len | (del << 31));
-                        d[1] = make_uint4(has_prev ? qL : 0u, 0u, 0u, 0u);
-                    } else B.ctrl->overflow = 1;
+        for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+        const uint32_t L = carry + incl - c;
+        const bool isev = valid && (op == 1u || op == 2u) && len >= P.indel_min;
+        const uint32_t bal = __ballot_sync(0xffffffffu, isev);
+        if (bal) {
+            const uint32_t below = bal & ((1u << lane) - 1u);
+            const uint32_t rank = __popc(below);
+            const int src = below ? 31 - __clz(below) : 0;
+            uint32_t qL = __shfl_sync(0xffffffffu, L, src), qn = __shfl_sync(0xffffffffu, len, src),
+                     qdel = __shfl_sync(0xffffffffu, (uint32_t)(op == 2u), src);
+            bool has_prev = below != 0;
+            if (!has_prev && cnt) { qL = pL; qn = pn; qdel = pdel; has_prev = true; }
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&B.ctrl->n_raw, (uint32_t)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            uint32_t myflags = 0;
+            if (isev) {
+                const uint32_t seq = cnt + rank, del = op == 2u;
+                if (has_prev && del && qdel) {
+                    if (seq == 1 && abs_diff(pos2 + L, pos2 + qL + qn) < P.merge_min) myflags |= K1_PAIR_MERGE;   // main.rs:615
+                    if (abs_diff(pos2 + qL, pos2 + L + len) < P.merge_min) myflags |= K1_FAR_HIT;                 // main.rs:673-678
                 }
-                for (int d = 16; d; d >>= 1) myflags |= __shfl_xor_sync(0xffffffffu, myflags, d);
-                info |= myflags;
-                const int last = 31 - __clz(bal);
-                pL = __shfl_sync(0xffffffffu, L, last); pn = __shfl_sync(0xffffffffu, len, last);
-                pdel = __shfl_sync(0xffffffffu, (uint32_t)(op == 2u), last);
-                cnt += __popc(bal);
+                const uint32_t slot = B.prim_slots + base + rank;
+                if (slot < B.raw_cap) {
+                    uint4* d = reinterpret_cast<uint4*>(B.raw + slot);
+                    d[0] = make_uint4(r, seq, L, len | (del << 31));
+                    d[1] = make_uint4(has_prev ? qL : 0u, 0u, 0u, 0u);
+                } else B.ctrl->overflow = 1;
             }
-            carry += __shfl_sync(0xffffffffu, incl, 31);
+            for (int d = 16; d; d >>= 1) myflags |= __shfl_xor_sync(0xffffffffu, myflags, d);
+            info |= myflags;
+            const int last = 31 - __clz(bal);
+            pL = __shfl_sync(0xffffffffu, L, last); pn = __shfl_sync(0xffffffffu, len, last);
+            pdel = __shfl_sync(0xffffffffu, (uint32_t)(op == 2u), last);
+            cnt += __popc(bal);
         }
-        if (lane == 0) B.k1[r] = make_uint2(carry, (cnt & K1_CNT_MASK) | info);
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
+    if (lane == 0) B.k1[r] = make_uint2(carry, (cnt & K1_CNT_MASK) | info);
+}
+
+__global__ void __launch_bounds__(256) k1_warp(DevBatch B, DevParams P)
+{
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < B.n_reads; r += warps) k1_warp_record(B, P, r);
 }
 
 // ======================================================================================
@@ -466,7 +481,8 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
     K1Smem& S = *reinterpret_cast<K1Smem*>(k1_smem_raw);
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (blockIdx.x >= n_tiles) return;
-    const unsigned long long tr_start = B.dbg ? gtimer() : 0ull; unsigned long long tr_first = 0; uint32_t tr_scanned = 0;
+    const bool trace = B.dbg && B.dbg_sel == 1u;
+    const unsigned long long tr_start = trace ? gtimer() : 0ull; unsigned long long tr_first = 0; uint32_t tr_scanned = 0;
     const uint32_t ntile = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;         // <= K1_MAX_TILES (host)
     for (uint32_t k = t; k < 2 * ntile; k += K1_THREADS) {
         const unsigned long long rec = (unsigned long long)(blockIdx.x + (k >> 1) * gridDim.x) * rpc + ((k & 1) ? rpc : 0u);
@@ -539,7 +555,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
                     asm("{\n.reg .pred p;\nsetp.ge.u32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(sus) : "r"(vv[k]), "r"(imin16), "r"(f));
                 }
             }
-            if (B.dbg && !tr_first) tr_first = gtimer();
+            if (trace && !tr_first) tr_first = gtimer();
             if (!__syncthreads_or((sus & 2u) | (flags & 0x40u))) {
                 if (t < nr) B.k1[ra + t] = make_uint2(0u, 0u);
                 if (t == 0) B.tile_cnt[tile] = 0;
@@ -656,7 +672,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
         }
         __syncthreads();                                   // the next tile re-initialises the per-record arrays
     }
-    if (B.dbg && t == 0) {
+    if (trace && t == 0) {
         unsigned long long* d = B.dbg + 4ull * blockIdx.x;
         d[0] = tr_start; d[1] = tr_first; d[2] = gtimer(); d[3] = (unsigned long long)ntile | ((unsigned long long)tr_scanned << 32);
     }
@@ -667,6 +683,242 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
     __syncthreads();
     const uint32_t slot = B.prim_slots + s_last + t;
     if (t < B.slab && slot < B.raw_cap) reinterpret_cast<uint4*>(B.raw + slot)[0] = make_uint4(0xffffffffu, 0u, 0u, 0u);
+}
+
+// ======================================================================================
+// kernel 1a: event screen over the flat CIGAR stream (short-record batches)
+//
+// I/D >= indel_min are sparse in HiFi-like batches, and total_consume / the prefixes are only ever read for records that
+// have such an event (kernel 4b).  So the whole CIGAR stream is first streamed once at full width -- plain coalesced 128-bit
+// loads, four per thread in flight, four instructions per op (table look-up, OR, compare, predicated OR), no record
+// structure at all -- and all it leaves behind is the list of 512-op steps with an event candidate or an unknown op code in
+// them.  Kernel 1b resolves the listed steps to records.  Every record's summary starts out as "no event" here.
+// (Measured: resolving candidates to records inside this kernel -- a 4-level search per flagged step -- cost 12 of 39 us.)
+// ======================================================================================
+static constexpr int K1A_THREADS = 256;
+static constexpr int K1A_VEC = 4;                      // 128-bit loads per thread per step: a warp step covers 2 KB = 512 ops
+static constexpr int K1A_CTAS = 8;                     // CTAs per SM: full occupancy (32 registers) measured faster than fewer warps with deeper prefetch
+static constexpr uint32_t K1A_STEP_OPS = 32 * K1A_VEC * 4;
+
+// One warp step: screen the 512 ops held in q; true (warp-uniform) when some lane saw an event candidate or an unknown op.
+__device__ __forceinline__ bool k1a_step(uint32_t imin16, uint32_t lut_lo, uint32_t lut_hi, const uint4 (&q)[K1A_VEC])
+{
+    uint32_t sus = 0, flags = 0;
+#pragma unroll
+    for (int k = 0; k < K1A_VEC; k++) {
+        const uint32_t vv[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t f;
+            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(f) : "r"(lut_lo), "r"(lut_hi), "r"(vv[j]));
+            flags |= f;
+            asm("{\n.reg .pred p;\nsetp.ge.u32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(sus) : "r"(vv[j]), "r"(imin16), "r"(f));
+        }
+    }
+    return __any_sync(0xffffffffu, ((sus & 2u) | (flags & 0x40u)) != 0u);
+}
+
+__global__ void __launch_bounds__(K1A_THREADS, K1A_CTAS) k1a_screen(DevBatch B, DevParams P, unsigned long long n_ops)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t nthreads = gridDim.x * K1A_THREADS, gt = blockIdx.x * K1A_THREADS + threadIdx.x;
+    griddep_launch();                                  // kernel 1b may be placed; it waits for this grid before it reads anything
+    {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);      // the array is padded to 256 bytes, so whole 16-byte stores are fine
+        uint4* k1 = reinterpret_cast<uint4*>(B.k1);
+        for (uint32_t i = gt, n = (B.n_reads + 1u) / 2u; i < n; i += nthreads) k1[i] = z;
+    }
+    const uint32_t imin16 = P.indel_min >= (1u << 28) ? 0xffffffffu : (P.indel_min << 4);
+    const uint32_t nvec = (uint32_t)((n_ops + 3ull) / 4ull);               // < 2^30 (host); the cigar buffer is padded by 16 bytes
+    const uint4* cig = reinterpret_cast<const uint4*>(B.cigar);
+    // Warp steps are dealt round robin over all warps of the grid (event-dense genome regions are contiguous in the array).
+    // The last vector may hold padding past the last op: a false flag there only costs kernel 1b a look.
+    const uint32_t wstep = (nthreads >> 5) * (32 * K1A_VEC);
+    uint32_t lut_lo, lut_hi;                                                // the op table, pinned in two registers
+    asm volatile("mov.u32 %0, %2;\n\tmov.u32 %1, %3;" : "=r"(lut_lo), "=r"(lut_hi) : "n"(K1_LUT_LO), "n"(K1_LUT_HI));
+    // flagged steps are remembered in a per-warp bit mask and appended to the step list 32 iterations at a time (one atomic
+    // per warp for a typical batch, at its very end): nothing in the streaming loop waits for memory it does not stream
+    const uint32_t gw = gt >> 5, nw = nthreads >> 5;
+    auto append = [&](uint32_t mask, uint32_t it0) {
+        const uint32_t n = __popc(mask);
+        if (!n) return;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&B.ctrl->n_flagged, n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < n) B.step_list[base + lane] = gw + (it0 + __fns(mask, 0, lane + 1)) * nw;
+    };
+    uint32_t hitmask = 0, it = 0;
+    for (uint32_t v0 = gw * (32 * K1A_VEC); v0 < nvec; v0 += wstep, it++) {
+        const uint4* p = cig + v0 + lane;
+        uint4 q[K1A_VEC];
+        if (v0 + 32 * K1A_VEC <= nvec) {
+#pragma unroll
+            for (int k = 0; k < K1A_VEC; k++) q[k] = __ldg(p + 32 * k);
+        } else {
+#pragma unroll
+            for (int k = 0; k < K1A_VEC; k++) q[k] = v0 + 32 * k + lane < nvec ? __ldg(p + 32 * k) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        hitmask |= (k1a_step(imin16, lut_lo, lut_hi, q) ? 1u : 0u) << (it & 31u);
+        if ((it & 31u) == 31u) { append(hitmask, it - 31u); hitmask = 0; }
+    }
+    append(hitmask, it & ~31u);
+}
+
+// largest r in [0, n_reads) with cigar_off[r] <= fp, for fp < cigar_off[n_reads]: a 33-ary search done by the whole warp
+// (32 probes per step, 4 steps for a million records)
+__device__ __forceinline__ uint32_t k1b_find_read(const unsigned long long* off, uint32_t n_reads, unsigned long long fp)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t lo = 0, hi = n_reads;                     // invariant: off[lo] <= fp < off[hi]
+    while (hi - lo > 1u) {
+        const uint32_t n = hi - lo;
+        uint32_t probe; bool valid = true;
+        if (n <= 33u) { probe = lo + 1u + lane; valid = probe < hi; }
+        else probe = lo + (uint32_t)(((unsigned long long)n * (lane + 1u)) / 33ull);       // strictly increasing, inside (lo, hi)
+        const bool le = valid && off[valid ? probe : lo] <= fp;
+        const uint32_t k = __popc(__ballot_sync(0xffffffffu, le));                     // sorted offsets: the true lanes are 0..k-1
+        const uint32_t below = __shfl_sync(0xffffffffu, probe, (k + 31u) & 31u);
+        const uint32_t above = __shfl_sync(0xffffffffu, probe, k & 31u);
+        const uint32_t above_ok = __shfl_sync(0xffffffffu, (uint32_t)valid, k & 31u);
+        if (k < 32u && above_ok) hi = above;
+        if (k) lo = below;
+    }
+    return lo;
+}
+
+// ======================================================================================
+// kernel 1b: the flagged steps of kernel 1a, one warp per step, one thread per record
+//
+// A warp takes a step off the list, finds the records that overlap its 512 ops (one search for the first, then consecutive
+// offsets), and every such record is claimed by exactly one thread on the device (atomic bit per record: a record can
+// overlap several flagged steps) which walks the whole record: left_consume, total_consume, the event sequence and the two
+// merge predicates are all thread-local (main.rs:523-600, 612-635, 673-678); no staging, no block scan.  The walk reads
+// aligned 128-bit vectors, four in flight; the records of a step are neighbours, so the sectors their walks touch are shared,
+// and the stream has just been through L2 for kernel 1a.  Events are parked in shared memory during the walk (a short
+// divergent branch) and written out afterwards with one reservation per warp.  A record too long for one thread is
+// scanned by the whole warp (k1_warp_record).  Raw events go to the atomically allocated region (no tile slices here).
+// The grid is one resident wave (measured: launching a warp per step, flagged or not, took 16 us for 7.8k CTAs).
+// ======================================================================================
+static constexpr int K1B_THREADS = 256;
+static constexpr int K1B_CTAS = 5;                     // CTAs per SM
+static constexpr uint32_t K1B_LONG = 256;              // ops; longer records are scanned by the warp
+static constexpr uint32_t K1B_EV = 4;                  // events per record parked in shared memory during the walk
+static constexpr int K1B_VEC = 4;                      // 128-bit loads in flight per walking thread
+
+__global__ void __launch_bounds__(K1B_THREADS, K1B_CTAS) k1b_steps(DevBatch B, DevParams P, unsigned long long n_ops)
+{
+    __shared__ uint2 s_ev[K1B_THREADS][K1B_EV + 1];    // {left_consume, op word}; the last slot is a dummy
+    const uint32_t t = threadIdx.x, lane = t & 31;
+    griddep_wait();                                    // kernel 1a's step list and zeroed summaries
+    const uint32_t n_list = B.ctrl->n_flagged, nw = (gridDim.x * K1B_THREADS) >> 5;
+    const uint32_t imin16 = P.indel_min >= (1u << 28) ? 0xffffffffu : (P.indel_min << 4);
+    const uint4* cig4 = reinterpret_cast<const uint4*>(B.cigar);
+    for (uint32_t li = (blockIdx.x * K1B_THREADS + t) >> 5; li < n_list; li += nw) {
+        const bool trace = B.dbg && B.dbg_sel == 1u;
+        const unsigned long long tr0 = trace ? gtimer() : 0ull;
+        unsigned long long tr1 = 0, tr2 = 0;
+        const uint32_t st = B.step_list[li];
+        const unsigned long long lo_op = (unsigned long long)st * K1A_STEP_OPS, hi_op = min(lo_op + K1A_STEP_OPS, n_ops);
+        if (lo_op >= hi_op) continue;
+        const uint32_t r_first = k1b_find_read(B.cigar_off, B.n_reads, lo_op);
+        if (trace) tr1 = gtimer();
+        for (uint32_t rb = r_first;; rb += 32) {                              // records overlapping the step, 32 at a time
+            const uint32_t r = rb + lane;
+            unsigned long long o0 = 0, o1 = 0;
+            uint32_t flag = 0, mapq = 0, pos2 = 0;
+            const bool in = r < B.n_reads;
+            if (in) { o0 = B.cigar_off[r]; o1 = B.cigar_off[r + 1]; flag = B.flag[r]; mapq = B.mapq[r]; pos2 = (uint32_t)B.pos[r]; }
+            const bool overlaps = in && o0 < hi_op;                           // (o1 > lo_op holds from r_first on, empty records aside)
+            bool mine = overlaps && o1 > o0 && o1 > lo_op && keep_record(P, flag, mapq);
+            bool is_long = mine && o1 - o0 > K1B_LONG;
+            // the record's first vectors are requested before the claim is known: both round trips overlap
+            const unsigned long long a0 = o0 & ~3ull;
+            const uint32_t nv = mine && !is_long ? (uint32_t)((((o1 + 3ull) & ~3ull) - a0) >> 2) : 0u;   // aligned vectors spanned
+            const uint32_t head = (uint32_t)(o0 - a0), nops = (uint32_t)(o1 - o0);
+            const uint4* c4 = cig4 + (a0 >> 2);
+            uint4 q[K1B_VEC];
+#pragma unroll
+            for (int k = 0; k < K1B_VEC; k++) q[k] = (uint32_t)k < nv ? __ldg(c4 + k) : make_uint4(0u, 0u, 0u, 0u);
+            {   // one owner per record on the whole device.  The 32 records of the warp share at most two words of the claim bitmap:
+                // two atomics per warp instead of one per lane
+                const uint32_t cb = __ballot_sync(0xffffffffu, mine), sh = rb & 31u;
+                const uint32_t lo_bits = cb << sh, hi_bits = sh ? cb >> (32u - sh) : 0u;
+                uint32_t old = 0;
+                if (lane == 0 && lo_bits) old = atomicOr(&B.dirty_bits[rb >> 5], lo_bits);
+                if (lane == 1 && hi_bits) old = atomicOr(&B.dirty_bits[(rb >> 5) + 1u], hi_bits);
+                const uint32_t old_lo = __shfl_sync(0xffffffffu, old, 0), old_hi = __shfl_sync(0xffffffffu, old, 1);
+                const uint32_t p = sh + lane;
+                if ((p < 32u ? old_lo >> p : old_hi >> (p - 32u)) & 1u) mine = false;
+            }
+            // ---- the walk.  Lanes walk different records, so the loop body is kept free of branches: an op outside the record
+            // reads as 0M, an event only parks {left_consume, op} in shared memory (slot K1B_EV is a dummy that every
+            // non-event writes to); the merge predicates are evaluated on the parked events afterwards.
+            uint32_t cnt = 0, L = 0, flags = 0;
+            if (mine && !is_long) {
+                for (uint32_t vb = 0; vb < nv; vb += K1B_VEC) {
+                    if (vb) {
+#pragma unroll
+                        for (int k = 0; k < K1B_VEC; k++) q[k] = vb + k < nv ? __ldg(c4 + vb + k) : make_uint4(0u, 0u, 0u, 0u);
+                    }
+#pragma unroll
+                    for (int k = 0; k < K1B_VEC; k++) {
+                        const uint32_t vv[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t e = (vb + k) * 4u + j;                 // element index counted from a0
+                            const uint32_t v = (e - head) < nops ? vv[j] : 0u;
+                            uint32_t f;
+                            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(f) : "r"(K1_LUT_LO), "r"(K1_LUT_HI), "r"(v));
+                            flags |= f;
+                            const bool isev = (f & 2u) && v >= imin16;               // I/D >= indel_min (main.rs:553,569)
+                            s_ev[t][isev ? min(cnt, K1B_EV) : K1B_EV] = make_uint2(L, v);
+                            cnt += isev ? 1u : 0u;
+                            L += (f & 1u) ? (v >> 4) : 0u;                          // M D N = consume the reference (main.rs:528-545)
+                        }
+                    }
+                }
+                if (flags & 0x40u) report(B.ctrl, r, RANK_CIGAR_OP);                                // rust-htslib panics on an unknown op
+                if (cnt > K1B_EV) is_long = true;                                                   // more events than parking space: the warp does it
+                else {
+                    uint32_t info = 0;
+                    for (uint32_t j = 1; j < cnt; j++) {
+                        const uint2 x = s_ev[t][j - 1], y = s_ev[t][j];
+                        if ((x.y & 15u) == 2u && (y.y & 15u) == 2u) {
+                            if (j == 1u && abs_diff(pos2 + y.x, pos2 + x.x + (x.y >> 4)) < P.merge_min) info |= K1_PAIR_MERGE;   // main.rs:615
+                            if (abs_diff(pos2 + x.x, pos2 + y.x + (y.y >> 4)) < P.merge_min) info |= K1_FAR_HIT;                  // main.rs:673-678
+                        }
+                    }
+                    B.k1[r] = make_uint2(L, (cnt & K1_CNT_MASK) | info);
+                }
+            }
+            if (trace && !tr2) { __syncwarp(); tr2 = gtimer(); }
+            // parked events: warp scan of the counts, one reservation, every lane writes its own
+            const uint32_t parked = mine && !is_long ? cnt : 0u;
+            uint32_t incl = parked;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t base = 0;
+            if (lane == 0 && total) base = atomicAdd(&B.ctrl->n_raw, total);
+            base = B.prim_slots + __shfl_sync(0xffffffffu, base, 0) + incl - parked;
+            for (uint32_t j = 0; j < parked; j++) {
+                if (base + j < B.raw_cap) {
+                    const uint2 e = s_ev[t][j];
+                    uint4* d = reinterpret_cast<uint4*>(B.raw + base + j);
+                    d[0] = make_uint4(r, j, e.x, (e.y >> 4) | ((e.y & 15u) == 2u ? 0x80000000u : 0u));
+                    d[1] = make_uint4(j ? s_ev[t][j - 1].x : 0u, 0u, 0u, 0u);
+                } else B.ctrl->overflow = 1;
+            }
+            for (uint32_t lm = __ballot_sync(0xffffffffu, mine && is_long); lm; lm &= lm - 1u)
+                k1_warp_record(B, P, __shfl_sync(0xffffffffu, r, __ffs((int)lm) - 1));
+            // the next 32 records matter only if the last one of these still ends inside the step
+            if (!__shfl_sync(0xffffffffu, (uint32_t)(overlaps && o1 < hi_op), 31)) break;
+        }
+        if (trace && lane == 0) {                                             // EXLR_OPT_TRACE: {start, search done, first walk done | end}
+            unsigned long long* d = B.dbg + 4ull * (li & 8191u);
+            d[0] = tr0; d[1] = tr1; d[2] = tr2; d[3] = gtimer();
+        }
+    }
 }
 
 // ======================================================================================
@@ -733,7 +985,11 @@ template <int G>
 __global__ void __launch_bounds__(256) k3a_sa_cigar(DevBatch B, DevParams P)
 {
     constexpr uint32_t PER_WARP = 32 / G;
+    griddep_wait();                                    // kernel 0's list and count
+    griddep_launch();
+    CtaTrace tr(B, 3);
     const uint32_t n_sa = B.ctrl->n_sa;
+    tr.mid();
     const uint32_t lane = threadIdx.x & 31, sub = lane & (G - 1), grp = lane / G;
     const uint32_t gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (grp * G);
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -756,6 +1012,7 @@ __global__ void __launch_bounds__(256) k3a_sa_cigar(DevBatch B, DevParams P)
             if (lane == 0) k3a_store(B, j0 + (uint32_t)src / G, a);
         }
     }
+    tr.end();
 }
 
 // ======================================================================================
@@ -766,10 +1023,12 @@ __global__ void __launch_bounds__(256) k3a_sa_cigar(DevBatch B, DevParams P)
 // 128-bit loads and each thread then parses its own record's string out of shared memory
 // (falls back to reading global memory when the range does not fit).
 // ======================================================================================
-static constexpr int K3B_THREADS = 128;
-static constexpr int K3B_TILE = 64;                     // SA records per CTA (pieces are then spread over all 128 threads)
-static constexpr uint32_t K3B_STAGE_BYTES = 16 * 1024;
-static constexpr uint32_t K3B_MAXP = 384;              // segments (records + SA pieces) per tile in the staged layout
+static constexpr int K3B_THREADS = 192;                 // the usual tile (64 records, ~140 pieces + 64 own segments) parses in one round
+static constexpr int K3B_TILE = 64;                     // SA records per tile (pieces are then spread over all threads)
+static constexpr int K3B_CTAS = 7;                      // CTAs per SM: 30 KB of shared memory and 48 registers x 192 threads each
+static constexpr uint32_t K3B_STAGE_BYTES = 12 * 1024;
+static constexpr uint32_t K3B_SEMI = 8;                // ';' positions kept per record by phase 1; more -> phase 1b rescans
+static constexpr uint32_t K3B_MAXP = 320;              // segments (records + SA pieces) per tile in the staged layout
 
 struct SmemBytes {            // byte i of sa_bytes, served from the staged copy (bias is a multiple of 16)
     static constexpr bool kWords = true;
@@ -907,6 +1166,94 @@ __device__ uint32_t dev_parse_piece(const Bytes& s, uint32_t b, uint32_t e, cons
     out->clip_big = (sS > P.ins_clip_min || sH > P.ins_clip_min) ? 1u : 0u;
     out->strand_neg = strand_neg;
     return 0;
+}
+
+// Fast path of parse_supplementary_alignment (utils.rs:119-139) for the regular form every aligner writes,
+//     chrom,<1-9 digits>,<+|->,(<1-9 digits><op>)+,<1-3 digits <= 255>,<1-9 digits>
+// in ONE pass over the bytes.  Anything else -- signs, longer numbers, missing or extra fields, odd bytes, trailing digits in
+// the CIGAR -- returns false and the caller runs the exact dev_parse_piece above, which also yields the reference's panics.
+// For the accepted form both produce the same Seg: same field boundaries, u32-wrapping sums, u64 key.
+// Written for warp convergence: one simple loop per field, no early exit (a failed check only clears `ok`), and the lanes
+// of `m` (the lanes of the warp that hold a piece) re-join after every loop -- with early returns and nested digit loops
+// the lanes drifted apart and the parser ran at a quarter of the warp width.
+__device__ __forceinline__ bool dev_parse_piece_fast(const uint8_t* p /* staged bytes */, uint32_t bias /* sa offset of p[0] */,
+                                                     uint32_t b, uint32_t e, const DevParams& P, Seg* out, uint32_t m)
+{
+    b -= bias; e -= bias;
+    bool ok = true;
+    uint32_t i = b;
+    while (i < e && p[i] != ',') i++;                                          // chrom
+    __syncwarp(m);
+    const uint32_t ce = i;
+    ok &= i < e;
+    i++;
+    uint32_t pos = 0, nd = 0;                                                  // pos
+    while (i < e) { const uint32_t d = (uint32_t)p[i] - '0'; if (d > 9u) break; pos = pos * 10u + d; nd++; i++; }
+    __syncwarp(m);
+    ok &= nd - 1u < 9u && i < e && p[min(i, e - 1u)] == ',';
+    i++;
+    const uint32_t sc = i < e ? (uint32_t)p[i] : 0u, sc2 = i + 1u < e ? (uint32_t)p[i + 1] : 0u;   // strand
+    ok &= (sc == '+' || sc == '-') && sc2 == ',';
+    i += 2;
+    // CIGAR text (utils.rs:88-117, 12-42): the same step for every byte up to the comma
+    uint32_t sS = 0, sH = 0, sD = 0, sM = 0, sE = 0, sX = 0, nops = 0, n = 0, bad = 0;
+    unsigned long long key = 0; bool seenM = false;
+    nd = 0;
+    while (i < e) {
+        const uint32_t c = p[i];
+        if (c == ',') break;
+        const uint32_t d = c - '0';
+        if (d <= 9u) { n = n * 10u + d; nd++; }
+        else {
+            const uint32_t x = c - '=';                                         // = D H I M N P S X  ->  0 7 11 12 16 17 19 22 27
+            bad |= (x >= 28u || !((0x84B1881u >> (x & 31u)) & 1u) || nd - 1u >= 9u) ? 1u : 0u;
+            sM += c == 'M' ? n : 0u; sS += c == 'S' ? n : 0u; sD += c == 'D' ? n : 0u;
+            sH += c == 'H' ? n : 0u; sE += c == '=' ? n : 0u; sX += c == 'X' ? n : 0u;
+            if (!seenM && x < 28u && ((0x8401001u >> x) & 1u)) key += n;        // = I S X before the first M (utils.rs:33)
+            seenM |= c == 'M';
+            n = 0; nd = 0; nops++;
+        }
+        i++;
+    }
+    __syncwarp(m);
+    ok &= !bad && nd == 0u && nops != 0u && i < e;                             // ends at the comma, right after an op
+    i++;
+    uint32_t mq = 0;                                                           // mapq: u8
+    nd = 0;
+    while (i < e) { const uint32_t d = (uint32_t)p[i] - '0'; if (d > 9u) break; mq = mq * 10u + d; nd++; i++; }
+    __syncwarp(m);
+    ok &= nd - 1u < 3u && mq <= 255u && i < e && p[min(i, e - 1u)] == ',';
+    i++;
+    nd = 0;                                                                    // NM: parsed, value unused (utils.rs:135)
+    while (i < e) { if ((uint32_t)p[i] - '0' > 9u) break; nd++; i++; }
+    __syncwarp(m);
+    ok &= nd - 1u < 9u && i == e;
+    if (!ok) return false;
+    uint32_t cb = b;
+    if (ce - cb >= 3u && p[cb] == 'c' && p[cb + 1] == 'h' && p[cb + 2] == 'r') cb += 3;
+    out->chrom_ref = 0x80000000u | (cb + bias);
+    out->chrom_len = ce - cb;
+    out->start = (int64_t)pos - 1;
+    out->end = out->start + (int64_t)sD + (int64_t)sM + (int64_t)sE + (int64_t)sX;
+    out->key = (int64_t)key;
+    out->clip_big = (sS > P.ins_clip_min || sH > P.ins_clip_min) ? 1u : 0u;
+    out->strand_neg = sc == '-';
+    return true;
+}
+
+// Calls f(w0, z) for every aligned word of bytes [b0, e0): z has 0x80 in each byte that equals the byte replicated in c4,
+// bytes outside the range masked off (only the first and the last word pay for the masking).
+template <class F>
+__device__ __forceinline__ void swar_scan(const SmemBytes& s, uint32_t b0, uint32_t e0, uint32_t c4, F f)
+{
+    if (b0 >= e0) return;
+    uint32_t w0 = b0 & ~3u;
+    const uint32_t last = (e0 - 1u) & ~3u;
+    uint32_t z = swar_eq(s.word(w0), c4) & (0xffffffffu << (8u * (b0 - w0)));
+    if (w0 == last) { f(w0, z & (0xffffffffu >> (8u * (w0 + 4u - e0)))); return; }
+    f(w0, z);
+    for (w0 += 4u; w0 < last; w0 += 4u) f(w0, swar_eq(s.word(w0), c4));
+    f(last, swar_eq(s.word(last), c4) & (0xffffffffu >> (8u * (last + 4u - e0))));
 }
 
 template <class Bytes>
@@ -1077,14 +1424,17 @@ struct __align__(16) K3bSmem {
     Seg segs[K3B_MAXP];
     uint32_t pb[K3B_MAXP], pe[K3B_MAXP];
     uint32_t rerr[K3B_TILE];
+    uint32_t semi[K3B_TILE][K3B_SEMI];                 // positions of the first ';' of every record (phase 1 -> 1b)
     uint32_t wsum[K3B_THREADS / 32];
     uint8_t pread[K3B_MAXP];
 };
 
-__global__ void __launch_bounds__(K3B_THREADS) k3b_sa_events(DevBatch B, DevParams P)
+__global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch B, DevParams P)
 {
     extern __shared__ __align__(16) unsigned char k3b_smem_raw[];
     K3bSmem& S = *reinterpret_cast<K3bSmem*>(k3b_smem_raw);
+    griddep_wait();                                    // kernel 3a's summaries
+    CtaTrace tr(B, 4);
     const uint32_t n_sa = B.ctrl->n_sa;
     const uint32_t n_tiles = (n_sa + K3B_TILE - 1) / K3B_TILE;
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -1095,7 +1445,7 @@ __global__ void __launch_bounds__(K3B_THREADS) k3b_sa_events(DevBatch B, DevPara
         const uint32_t a0 = span_b & ~15u;
         const bool staged = span_e - a0 <= K3B_STAGE_BYTES;                   // block-uniform
         const uint32_t j = j0 + t;
-        const bool active = t < K3B_TILE && j < j1;                           // threads 64..127 only help with the pieces
+        const bool active = t < K3B_TILE && j < j1;                           // the other threads only help with the pieces
         __syncthreads();                                                      // the previous tile's readers are done
         if (!staged) {
             GlobalBytes s{B.sa_bytes};
@@ -1110,22 +1460,25 @@ __global__ void __launch_bounds__(K3B_THREADS) k3b_sa_events(DevBatch B, DevPara
         if (active) { r = B.sa_list[j]; b0 = B.sa_off[r]; e0 = B.sa_off[r + 1]; is_str = B.sa_kind[r] == EXLR_SA_STRING; }
         __syncthreads();
         SmemBytes s{S.bytes, a0};
+        uint32_t nsemi = 0;
         if (active) {
-            unsigned long long pieces = 1; uint32_t nonempty = 0;
+            uint32_t nonempty = 0;
             if (is_str) {
-                // pieces = #';' + 1; a piece is empty when its ';' follows another ';' or starts the string, or when it is the
-                // (missing) piece after a trailing ';'.  Four bytes per step.
-                uint32_t empties = (e0 == b0 || s[e0 - 1] == ';') ? 1u : 0u, carry = 0;
-                for (uint32_t w0 = b0 & ~3u; w0 < e0; w0 += 4u) {
-                    const uint32_t zz = swar_clip(swar_eq(s.word(w0), 0x3b3b3b3bu), w0, b0, e0) >> 7;     // 0x01 per ';'
-                    uint32_t prev = (zz << 8) | carry;
-                    if (w0 <= b0) prev |= 1u << (8u * (b0 - w0));            // the first byte follows the start of the string
-                    pieces += __popc(zz);
-                    empties += __popc(zz & prev);
-                    carry = zz >> 24;
-                }
-                nonempty = (uint32_t)pieces - empties;
-                if (pieces > P.max_supp_alignm) dropped = true;               // main.rs:311-313
+                // one pass, four bytes per step: every ';' closes a piece (empty when it directly follows the previous ';' or the
+                // start of the string); the last piece runs to the end of the string.  pieces = #';' + 1 (main.rs:309).
+                uint32_t pbeg = b0;
+                swar_scan(s, b0, e0, 0x3b3b3b3bu, [&](uint32_t w0, uint32_t z) {
+                    while (z) {
+                        const uint32_t i = w0 + ((uint32_t)(__ffs((int)z) - 1) >> 3);
+                        z &= z - 1u;
+                        if (nsemi < K3B_SEMI) S.semi[t][nsemi] = i;
+                        nsemi++;
+                        nonempty += i > pbeg;
+                        pbeg = i + 1u;
+                    }
+                });
+                nonempty += e0 > pbeg;
+                if ((unsigned long long)nsemi + 1ull > P.max_supp_alignm) dropped = true;   // main.rs:311-313
             }
             slots = dropped ? 0u : 1u + nonempty;
             S.rerr[t] = 0xffffffffu;
@@ -1147,27 +1500,35 @@ __global__ void __launch_bounds__(K3B_THREADS) k3b_sa_events(DevBatch B, DevPara
             S.pb[sb] = 0xffffffffu; S.pread[sb] = (uint8_t)t;                 // slot 0 of the record: its own alignment
             if (is_str) {
                 uint32_t at = sb + 1, pbeg = b0;
-                for (uint32_t w0 = b0 & ~3u; w0 < e0; w0 += 4u) {
-                    uint32_t z = swar_clip(swar_eq(s.word(w0), 0x3b3b3b3bu), w0, b0, e0);
-                    while (z) {
-                        const uint32_t i = w0 + ((uint32_t)(__ffs((int)z) - 1) >> 3);
-                        z &= z - 1u;
-                        if (i > pbeg) { S.pb[at] = pbeg; S.pe[at] = i; S.pread[at] = (uint8_t)t; at++; }
-                        pbeg = i + 1;
-                    }
+                auto piece_end = [&](uint32_t i) {
+                    if (i > pbeg) { S.pb[at] = pbeg; S.pe[at] = i; S.pread[at] = (uint8_t)t; at++; }   // filter(|x| x.len() > 0), main.rs:315
+                    pbeg = i + 1u;
+                };
+                if (nsemi <= K3B_SEMI) {
+                    for (uint32_t k = 0; k < nsemi; k++) piece_end(S.semi[t][k]);
+                } else {                                                       // more ';' than phase 1 kept (large -k): rescan
+                    swar_scan(s, b0, e0, 0x3b3b3b3bu, [&](uint32_t w0, uint32_t z) {
+                        while (z) { piece_end(w0 + ((uint32_t)(__ffs((int)z) - 1) >> 3)); z &= z - 1u; }
+                    });
                 }
-                if (e0 > pbeg) { S.pb[at] = pbeg; S.pe[at] = e0; S.pread[at] = (uint8_t)t; at++; }
+                if (e0 > pbeg) piece_end(e0);
             }
         }
         __syncthreads();
         // phase 2: one thread per piece
-        for (uint32_t x = t; x < total; x += K3B_THREADS) {
-            const uint32_t pbeg = S.pb[x];
-            if (pbeg == 0xffffffffu) continue;
-            const uint32_t err = dev_parse_piece(s, pbeg, S.pe[x], P, &S.segs[x]);
+        for (uint32_t x0 = 0; x0 < total; x0 += K3B_THREADS) {               // block-uniform trip count
+            const uint32_t x = x0 + t;
+            const uint32_t pbeg = x < total ? S.pb[x] : 0xffffffffu;
+            const bool has = pbeg != 0xffffffffu;
+            const uint32_t m = __ballot_sync(0xffffffffu, has);
+            if (!has) continue;
+            const uint32_t pend = S.pe[x];
+            if (dev_parse_piece_fast(S.bytes, a0, pbeg, pend, P, &S.segs[x], m)) continue;
+            const uint32_t err = dev_parse_piece(s, pbeg, pend, P, &S.segs[x]);   // irregular piece: the exact parser decides
             if (err) atomicMin(&S.rerr[S.pread[x]], (x << 8) | err);          // the first failing piece in SA order wins
         }
         __syncthreads();
+        tr.mid();
         // phase 3: one thread per record
         uint32_t nseg = 0;
         if (active && !dropped) {
@@ -1178,6 +1539,7 @@ __global__ void __launch_bounds__(K3B_THREADS) k3b_sa_events(DevBatch B, DevPara
         }
         k3b_finish(B, P, s, j, active, r, dropped, &S.segs[sb < K3B_MAXP ? sb : 0], nseg);
     }
+    tr.end();
 }
 
 // ======================================================================================
@@ -1198,7 +1560,9 @@ __device__ __forceinline__ uint32_t record_lines(const DevBatch& B, uint32_t r, 
 
 __global__ void __launch_bounds__(SCAN_THREADS) k4a_line_scan(DevBatch B, DevParams P)
 {
-    __shared__ uint32_t s_tile, s_prefix, s_warp[8];
+    __shared__ uint32_t s_tile, s_warp[16];
+    griddep_launch();                                  // kernel 4b may be placed; it waits for this grid before it reads anything
+    CtaTrace tr(B, 5);
     if (threadIdx.x == 0) s_tile = atomicAdd(&B.ctrl->ticket_b, 1u);
     __syncthreads();
     const uint32_t tile = s_tile, n = B.n_reads;
@@ -1223,7 +1587,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k4a_line_scan(DevBatch B, DevPar
         }
     }
     uint32_t grand;
-    uint32_t at = tile_excl_scan(B.scan_b, tile, mine, s_warp, &s_prefix, &grand);
+    tr.mid();
+    uint32_t at = tile_excl_scan(B.scan_b, tile, mine, s_warp, &grand);
     if (full) {
         union { uint4 v[4]; uint32_t u[16]; } o;
 #pragma unroll
@@ -1239,6 +1604,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k4a_line_scan(DevBatch B, DevPar
         B.ctrl->n_events = grand;
         if (grand > B.max_events) B.ctrl->overflow = 1;
     }
+    tr.end();
 }
 
 
@@ -1273,27 +1639,34 @@ __device__ __forceinline__ void k4b_indel(const DevBatch& B, const RawEv* src)
                 EXLR_EV_META(1u, EXLR_KIND_INDEL, neg, neg));
 }
 
-// One thread per raw slot / overflow entry / SA record (no grid-stride loop: every chain of dependent loads runs beside all
-// the others; threads without work leave at once).
+// One thread per raw slot / overflow entry / SA record.  The overflow and SA-record counts live on the device, so the grid
+// is one resident wave striding over the largest of the three ranges (measured: a grid sized for the worst case launched
+// 7-9k CTAs, most of them empty, and the launch alone took ~15 us).
 __global__ void __launch_bounds__(256) k4b_place(DevBatch B, DevParams P)
 {
-    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-    // indel events, per-tile slices first (slice of tile i = raw[i << capt_log2 ..], tile_cnt[i] entries used) ...
-    if (x < B.prim_slots && (x & ((1u << B.capt_log2) - 1u)) < B.tile_cnt[x >> B.capt_log2]) k4b_indel(B, B.raw + x);
-    // ... then the shared overflow region
-    const uint32_t room = B.raw_cap - B.prim_slots, n_ovf = min(B.ctrl->n_raw, room);
-    if (x < n_ovf) k4b_indel(B, B.raw + B.prim_slots + x);
-    // SA-derived events: per record contiguous in the temp buffer, they lead the record's lines
-    if (x < B.ctrl->n_sa) {
-        const uint32_t j = x, r = B.sa_list[j];
-        const uint32_t csa = B.csa[r];
-        if (csa & CSA_DROP) return;
-        const uint32_t cnt = csa & CSA_CNT_MASK, base = B.sa_base[j], dst = B.line_off[r];
-        if ((unsigned long long)dst + cnt > B.max_events || (unsigned long long)base + cnt > B.max_events) return;
-        const uint4* src = reinterpret_cast<const uint4*>(B.sa_ev + base);
-        uint4* d = reinterpret_cast<uint4*>(B.events + dst);
-        for (uint32_t k = 0; k < cnt * 3; k++) d[k] = src[k];
+    griddep_wait();                                    // kernel 4a's line offsets
+    CtaTrace tr(B, 6);
+    const uint32_t room = B.raw_cap - B.prim_slots, n_ovf = min(B.ctrl->n_raw, room), n_sa = B.ctrl->n_sa;
+    tr.mid();
+    const uint32_t limit = max(B.prim_slots, max(n_ovf, n_sa)), stride = gridDim.x * blockDim.x;
+    for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < limit; x += stride) {
+        // indel events, per-tile slices first (slice of tile i = raw[i << capt_log2 ..], tile_cnt[i] entries used) ...
+        if (x < B.prim_slots && (x & ((1u << B.capt_log2) - 1u)) < B.tile_cnt[x >> B.capt_log2]) k4b_indel(B, B.raw + x);
+        // ... then the shared overflow region
+        if (x < n_ovf) k4b_indel(B, B.raw + B.prim_slots + x);
+        // SA-derived events: per record contiguous in the temp buffer, they lead the record's lines
+        if (x < n_sa) {
+            const uint32_t j = x, r = B.sa_list[j];
+            const uint32_t csa = B.csa[r];
+            if (csa & CSA_DROP) continue;
+            const uint32_t cnt = csa & CSA_CNT_MASK, base = B.sa_base[j], dst = B.line_off[r];
+            if ((unsigned long long)dst + cnt > B.max_events || (unsigned long long)base + cnt > B.max_events) continue;
+            const uint4* src = reinterpret_cast<const uint4*>(B.sa_ev + base);
+            uint4* d = reinterpret_cast<uint4*>(B.events + dst);
+            for (uint32_t k = 0; k < cnt * 3; k++) d[k] = src[k];
+        }
     }
+    tr.end();
 }
 
 // ======================================================================================
@@ -1316,6 +1689,20 @@ cudaError_t configure_kernels(int device)
     e = cudaFuncSetAttribute(k1_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k3b_sa_events, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3bSmem));
+}
+
+// Launch with the programmatic-stream-serialization attribute: the kernel may be placed while its predecessor in the stream
+// drains (it calls griddep_wait() before touching memory).  After anything but a kernel the attribute changes nothing.
+template <class... KArgs, class... Args>
+static void launch_dependent(void (*kernel)(KArgs...), uint32_t grid, uint32_t block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 void launch_k0(const DevBatch& B, const DevParams& P, cudaStream_t st)
@@ -1358,23 +1745,51 @@ void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc,
     }
 }
 
+// the screen pass (kernel 1a) and the resolution of its flagged steps (kernel 1b); n_ops < 2^32
+uint32_t k1a_steps(unsigned long long n_ops) { return (uint32_t)((n_ops + K1A_STEP_OPS - 1) / K1A_STEP_OPS); }
+
+void launch_k1a(const DevBatch& B, const DevParams& P, unsigned long long n_ops, cudaStream_t st)
+{
+    const uint32_t steps = k1a_steps(n_ops);
+    uint32_t grid = (steps + K1A_THREADS / 32 - 1) / (K1A_THREADS / 32);
+    const uint32_t cap = (uint32_t)g_sm_count * K1A_CTAS;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    k1a_screen<<<grid, K1A_THREADS, 0, st>>>(B, P, n_ops);
+}
+
+void launch_k1b(const DevBatch& B, const DevParams& P, unsigned long long n_ops, cudaStream_t st)
+{
+    // the number of flagged steps lives on the device: one resident wave of warps strides over the list
+    const uint32_t steps = k1a_steps(n_ops);
+    const uint32_t grid = min((steps + K1B_THREADS / 32 - 1) / (K1B_THREADS / 32), (uint32_t)g_sm_count * K1B_CTAS);
+    launch_dependent(k1b_steps, grid ? grid : 1u, K1B_THREADS, 0, st, B, P, n_ops);
+}
+
 void launch_k3a(const DevBatch& B, const DevParams& P, uint32_t mean_ops, cudaStream_t st)
 {
-    // grid-stride over a device-side count: size for the worst case, cap at a few waves
+    // grid-stride over a device-side count: size for the worst case, cap at one resident wave (spare CTAs cost launch time).
+    // Lanes per record by the batch's mean CIGAR length: the more records a warp walks side by side, the fewer waves.
+    const uint32_t cap = (uint32_t)g_sm_count * 8u;
     if (mean_ops <= 16) {
-        const uint32_t g = min((B.n_reads + 127u) / 128u, (uint32_t)g_sm_count * 16u);
-        k3a_sa_cigar<2><<<g ? g : 1u, 256, 0, st>>>(B, P);
+        const uint32_t g = min((B.n_reads + 127u) / 128u, cap);
+        launch_dependent(k3a_sa_cigar<2>, g ? g : 1u, 256, 0, st, B, P);
+    } else if (mean_ops <= 48) {
+        const uint32_t g = min((B.n_reads + 63u) / 64u, cap);
+        launch_dependent(k3a_sa_cigar<4>, g ? g : 1u, 256, 0, st, B, P);
     } else {
-        const uint32_t g = min((B.n_reads + 31u) / 32u, (uint32_t)g_sm_count * 16u);
-        k3a_sa_cigar<8><<<g ? g : 1u, 256, 0, st>>>(B, P);
+        const uint32_t g = min((B.n_reads + 31u) / 32u, cap);
+        launch_dependent(k3a_sa_cigar<8>, g ? g : 1u, 256, 0, st, B, P);
     }
 }
 
 void launch_k3b(const DevBatch& B, const DevParams& P, cudaStream_t st)
 {
-    // one CTA per tile of 64 SA records; the count lives on the device, so size for the batch and let spare CTAs exit
-    const uint32_t gb = min((B.n_reads + K3B_TILE - 1u) / K3B_TILE, 65535u * 16u);
-    k3b_sa_events<<<gb ? gb : 1u, K3B_THREADS, sizeof(K3bSmem), st>>>(B, P);
+    // tiles of 64 SA records, grid-stride; the SA-record count lives on the device, so the grid is sized from the batch but
+    // capped at the CTAs that are resident at once: spare CTAs of an over-sized grid cost a launch slot each just to read the
+    // count and leave, and a CTA with a second tile doubles the kernel's span
+    const uint32_t gb = min((B.n_reads + K3B_TILE - 1u) / K3B_TILE, (uint32_t)g_sm_count * K3B_CTAS);
+    launch_dependent(k3b_sa_events, gb ? gb : 1u, K3B_THREADS, sizeof(K3bSmem), st, B, P);
 }
 
 void launch_k4a(const DevBatch& B, const DevParams& P, cudaStream_t st)
@@ -1385,11 +1800,12 @@ void launch_k4a(const DevBatch& B, const DevParams& P, cudaStream_t st)
 
 void launch_k4b(const DevBatch& B, const DevParams& P, cudaStream_t st)
 {
-    // the overflow count and the SA-record count live on the device: cover the largest they can be
+    // the overflow count and the SA-record count live on the device: cover the largest they can be, capped at one resident wave
     uint32_t n = B.prim_slots > B.n_reads ? B.prim_slots : B.n_reads;
     const uint32_t room = B.raw_cap - B.prim_slots;
     if (room > n) n = room;
-    k4b_place<<<(n + 255u) / 256u, 256, 0, st>>>(B, P);
+    const uint32_t grid = min((n + 255u) / 256u, (uint32_t)g_sm_count * 8u);
+    launch_dependent(k4b_place, grid ? grid : 1u, 256, 0, st, B, P);
 }
 
 uint32_t scan_tiles(uint32_t n_reads) { return (n_reads + SCAN_TILE - 1) / SCAN_TILE; }

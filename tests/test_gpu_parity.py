@@ -13,14 +13,15 @@ from randrec import clustered_dels, rand_batch, rand_params, REF_NAMES as RREF
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not gpu_available(), reason="needs a B200")]
 
-VARIANTS = [(0, 0), (0, 1), (0, 3), (0, 64), (0, 128), (1, 0)]       # (cigar kernel, records per CTA)
+# (cigar kernel, records per CTA); kernels: 0 auto, 1 warp per record, 2 flat block scan, 3 streaming screen + thread per record
+VARIANTS = [(0, 0), (2, 1), (2, 3), (2, 64), (2, 128), (1, 0), (3, 0), (2, 0)]
 
 
 @pytest.mark.parametrize("ka", KA, ids=[k[0] for k in KA])
 def test_known_answers(ka):
     _, over, rec, want = ka
     hb = pack_records([rec], REF_NAMES)
-    for ck, rpc in ((0, 0), (1, 0)):
+    for ck, rpc in ((0, 0), (1, 0), (2, 0), (3, 0)):
         _, res = gpu_check(hb, ExlrParams.make(**over), ck, rpc, label=f"{ka[0]} k{ck}")
         assert res.n_events == len(want)
     res, text = api.extract(hb, ExlrParams.make(**over))
@@ -172,7 +173,7 @@ def test_event_capacity_overflow_is_reported():
 def test_baseline_configs(cfg, scale):
     hb = synth.with_qnames(synth.config(cfg, scale))
     p = ExlrParams.make(**synth.CONFIGS[cfg]["params"])
-    for ck in (0, 1):
+    for ck in (0, 1, 2, 3):
         want, res = gpu_check(hb, p, ck, 0, verbose=(cfg == 0), label=f"config{cfg} k{ck}")
     assert res.n_events > 0
     if cfg == 3:
@@ -195,7 +196,7 @@ def test_batch_reuse_and_two_in_flight():
         check_result(x, p, r1, b1.format_lines(r1, False, None, 0, r1.n_events if r1.status == 0 else int(r1.line_off[r1.err_read])), label=f"reuse{rnd}a")
         check_result(y, p, r2, b2.format_lines(r2, False, None, 0, r2.n_events if r2.status == 0 else int(r2.line_off[r2.err_read])), label=f"reuse{rnd}b")
         t = b1.timing()
-        assert t.launches == 6 and t.kernels_ms > 0
+        assert t.launches == 7 and t.kernels_ms > 0 and t.screen_ms > 0      # short records: kernels 1a + 1b instead of kernel 1
     # resident path gives the same header
     b1.fill(a); b1.upload(); b1.submit_resident()
     rr = b1.wait_resident()
