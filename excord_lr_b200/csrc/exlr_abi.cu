@@ -42,6 +42,7 @@ struct exlr_ctx {
     int stage_timing = 1;                      // EXLR_OPT_STAGE_TIMING: CUDA events between the kernels (exlr_timing per stage)
     int k1_ctas = 0;                           // EXLR_OPT_K1_CTAS_PER_SM (0 = 3 when overlapping, which leaves room for the SA branch, else 4)
     uint32_t reads_per_cta = 0;                // EXLR_OPT_READS_PER_CTA (0 = auto)
+    int skip_screen = 0;                       // auto mode: batches left to run without the screen pass (the last screened one was event-dense)
 };
 
 struct exlr_batch {
@@ -243,7 +244,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     const size_t d_ctrl = dcarve(sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes);   // ctrl | scan_a | scan_b | dirty_bits : one memset
     const size_t d_cigar = dcarve((max_ops + 4) * 4 + 16), d_coff = dcarve((R + 1) * 8), d_pos = dcarve(R * 4), d_tid = dcarve(R * 4),
                  d_flag = dcarve(R * 2), d_mapq = dcarve(R), d_kind = dcarve(R), d_soff = dcarve((R + 1) * 4), d_sab = dcarve(max_sa_bytes + 16),
-                 d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_slist = dcarve((max_ops / 512 + 16) * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
+                 d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_slist = dcarve((max_ops / 512 + 16) * 4), d_llist = dcarve(R * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
                  d_raw = dcarve((max_events + kRawHeadroom) * sizeof(RawEv)), d_saev = dcarve(max_events * sizeof(exlr_event)),
                  d_pool = dcarve(pool_cap * sizeof(Seg)), d_dbg = dcarve(8192 * 32), d_loff = dcarve((R + 1) * 4), d_ev = dcarve(max_events * sizeof(exlr_event));
     e = cudaMalloc(&b->d_slab, dof);
@@ -252,7 +253,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     DevBatch& v = b->dv;
     v.ctrl = (Ctrl*)(ds + d_ctrl);
     v.scan_a = (unsigned long long*)(ds + d_ctrl + sizeof(Ctrl)); v.scan_b = v.scan_a + tiles;
-    v.dirty_bits = (uint32_t*)(v.scan_b + tiles); v.step_list = (uint32_t*)(ds + d_slist);
+    v.dirty_bits = (uint32_t*)(v.scan_b + tiles); v.step_list = (uint32_t*)(ds + d_slist); v.long_list = (uint32_t*)(ds + d_llist);
     b->ctrl_bytes = sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes;
     v.cigar = (uint32_t*)(ds + d_cigar); v.cigar_off = (unsigned long long*)(ds + d_coff); v.pos = (int32_t*)(ds + d_pos);
     v.tid = (int32_t*)(ds + d_tid); v.flag = (uint16_t*)(ds + d_flag); v.mapq = (uint8_t*)(ds + d_mapq); v.sa_kind = (uint8_t*)(ds + d_kind);
@@ -319,9 +320,6 @@ static int copy_inputs(exlr_batch* b, uint64_t n)
     return EXLR_OK;
 }
 
-// batches whose mean CIGAR is at most this long get the screen pass (kernel 1a) in front of kernel 1
-static constexpr uint64_t kScreenMaxMeanOps = 512;
-
 static uint32_t auto_rpc(uint64_t n_reads, uint64_t n_ops)
 {
     // kernel 1 scans 2048 ops per step: aim just under two steps of CIGAR per CTA for short-read batches (full
@@ -349,11 +347,14 @@ static int run_kernels(exlr_batch* b)
     b->screened = false;
     if (!c->params.split_only) {
         rpc = c->reads_per_cta ? c->reads_per_cta : auto_rpc(b->n_reads, b->n_ops);
-        // short records (HiFi-like): events are sparse, so the CIGAR stream is screened at streaming speed (kernel 1a) and only the
-        // records around an event candidate are walked (kernel 1b); long records (ONT-like) nearly all carry one: scan everything.
+        // Events (I/D >= indel_min) are sparse in HiFi and ONT batches alike (~10 % of the records hold one), so by default the
+        // CIGAR stream is screened at streaming speed (kernel 1a) and only the records around an event candidate are scanned
+        // (kernels 1b, 1c).  A batch where most 512-op steps held a candidate (e.g. -i 1) is better off with the flat scan of
+        // everything: after such a batch the next few run unscreened, then the screen is tried again.
         // (kernel 1a indexes the CIGAR array by 32-bit vector numbers)
-        const bool short_records = b->n_ops / b->n_reads <= kScreenMaxMeanOps;
-        b->screened = (c->cigar_kernel == 3 || (c->cigar_kernel == 0 && short_records)) && b->n_ops < (1ull << 32) && b->n_ops > 0;
+        bool want = c->cigar_kernel == 3;
+        if (c->cigar_kernel == 0) { if (c->skip_screen > 0) c->skip_screen--; else want = true; }
+        b->screened = want && b->n_ops < (1ull << 33) && b->n_ops > 0;
         uint32_t n_tiles = 0;
         plan_k1(d, b->screened ? 1 : variant, rpc, &n_tiles);               // screened: raw events all go to the atomically allocated region
         if (overlap) CK(cudaEventRecord(b->ev_fork, st));                  // after the memset
@@ -368,6 +369,7 @@ static int run_kernels(exlr_batch* b)
             launch_k1a(d, c->dparams, b->n_ops, s1); b->launches++;
             if (c->stage_timing) CK(cudaEventRecord(b->ev_k1_mid, s1));
             launch_k1b(d, c->dparams, b->n_ops, s1); b->launches++;
+            launch_k1c(d, c->dparams, s1); b->launches++;
         } else {
             launch_k1(d, c->dparams, variant, rpc, s1); b->launches++;
         }
@@ -457,6 +459,7 @@ static int finish(exlr_batch* b, exlr_result* res, bool fetch)
     CK(cudaSetDevice(b->ctx->device));
     CK(cudaStreamSynchronize(b->stream));
     const Ctrl& c = *b->h_ctrl;
+    if (b->screened && (uint64_t)c.n_flagged * 2 > (uint64_t)k1a_steps(b->n_ops)) b->ctx->skip_screen = 8;   // event-dense: see run_kernels
     res->n_events = c.n_events; res->n_kept = c.n_kept; res->n_sa_reads = c.n_sa; res->n_cap_dropped = c.n_dropped;
     if (c.overflow) {
         // n_events = the max_events that would have sufficed (all three counters keep counting past the capacity)

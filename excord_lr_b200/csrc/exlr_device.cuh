@@ -32,7 +32,8 @@ struct Ctrl {
     uint32_t ticket_a, ticket_b;    // dynamic tile ids of the two chained scans
     uint32_t seg_pool_used;
     uint32_t n_flagged;             // 512-op steps of the CIGAR stream kernel 1a found an event candidate in (length of step_list)
-    uint32_t pad[3];
+    uint32_t n_long;                // records kernel 1b passed on to kernel 1c (length of long_list)
+    uint32_t pad[2];
 };
 static_assert(sizeof(Ctrl) == 64, "Ctrl is the 64-byte result header");
 
@@ -92,6 +93,7 @@ struct DevBatch {
     RawEv* raw;             // [raw_cap]: per-tile slices [0, prim_slots), then the overflow region
     uint32_t* tile_cnt;     // [R] events in each tile's slice
     uint32_t* dirty_bits;   // [R/32] one bit per record: claimed by a thread of kernel 1b (zeroed with ctrl)
+    uint32_t* long_list;    // [R] kernel 1b: claimed records too long for one thread, any order (ctrl->n_long entries)
     uint32_t* step_list;    // [max_ops/512 + 1] kernel 1a: the 512-op steps of the CIGAR stream that hold an event candidate, any order
     uint32_t raw_cap, prim_slots, capt_log2, slab;
     exlr_event* sa_ev;      // [max_events] SA-derived events, per record contiguous
@@ -125,6 +127,7 @@ void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc,
 uint32_t k1a_steps(unsigned long long n_ops);
 void launch_k1a(const DevBatch& B, const DevParams& P, unsigned long long n_ops, cudaStream_t st);
 void launch_k1b(const DevBatch& B, const DevParams& P, unsigned long long n_ops, cudaStream_t st);
+void launch_k1c(const DevBatch& B, const DevParams& P, cudaStream_t st);
 void launch_k3a(const DevBatch& B, const DevParams& P, uint32_t mean_ops, cudaStream_t st);
 void launch_k3b(const DevBatch& B, const DevParams& P, cudaStream_t st);
 void launch_k4a(const DevBatch& B, const DevParams& P, cudaStream_t st);

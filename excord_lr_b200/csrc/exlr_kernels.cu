@@ -316,6 +316,7 @@ struct __align__(128) K1Smem {
     uint32_t buf[K1_STAGES][K1_CHUNK];                 // CIGAR ops as landed by TMA; overwritten in place by per-op prefixes
     K1Stage stage[K1_CAP];
     unsigned long long tb[K1_MAX_TILES][2];            // [first, last) op offset of every tile of this CTA
+    uint32_t tidx[K1_MAX_TILES];                       // tile ids of this CTA: b, b + grid, ... or its share of the long-record list
     uint32_t rpos[K1_MAX_RPC];                         // record.pos() as u32 (aligments_event.rs:43)
     uint32_t roff[K1_MAX_RPC + 1];
     uint32_t pstart[K1_MAX_RPC + 1];
@@ -475,18 +476,25 @@ static constexpr uint32_t K1_LUT_HI = 0x81808080u;     // = P H S
 // run of event-dense tiles is spread over many CTAs).  All its tile boundaries are fetched up front, so thread 0
 // keeps the TMA ring K1_STAGES chunks ahead of the scan ACROSS tile boundaries; the next tile's per-record
 // offsets, positions and filter inputs are prefetched into registers while the current tile is scanned.
-__global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P, uint32_t rpc, uint32_t n_tiles)
+__global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P, uint32_t rpc, uint32_t n_tiles, const uint32_t* list)
 {
     extern __shared__ __align__(128) unsigned char k1_smem_raw[];
     K1Smem& S = *reinterpret_cast<K1Smem*>(k1_smem_raw);
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+    // listed mode (kernel 1c): the tiles are the long records kernel 1b put on its list, one record each (rpc = 1);
+    // every one of them holds an event candidate, so nothing is screened
+    if (list) { griddep_wait(); n_tiles = B.ctrl->n_long; }
     if (blockIdx.x >= n_tiles) return;
-    const bool trace = B.dbg && B.dbg_sel == 1u;
+    const bool trace = B.dbg && B.dbg_sel == 1u && !list;
     const unsigned long long tr_start = trace ? gtimer() : 0ull; unsigned long long tr_first = 0; uint32_t tr_scanned = 0;
     const uint32_t ntile = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;         // <= K1_MAX_TILES (host)
-    for (uint32_t k = t; k < 2 * ntile; k += K1_THREADS) {
-        const unsigned long long rec = (unsigned long long)(blockIdx.x + (k >> 1) * gridDim.x) * rpc + ((k & 1) ? rpc : 0u);
-        S.tb[k >> 1][k & 1] = B.cigar_off[min(rec, (unsigned long long)B.n_reads)];
+    for (uint32_t k = t; k < ntile; k += K1_THREADS) {
+        const uint32_t id = blockIdx.x + k * gridDim.x;
+        const uint32_t tile = list ? list[id] : id;
+        S.tidx[k] = tile;
+        const unsigned long long r0 = (unsigned long long)tile * rpc;
+        S.tb[k][0] = B.cigar_off[min(r0, (unsigned long long)B.n_reads)];
+        S.tb[k][1] = B.cigar_off[min(r0 + rpc, (unsigned long long)B.n_reads)];
     }
     uint32_t spare = 0;                                    // thread 0: reserved overflow slab (see k1_flush)
     if (t == 0) {
@@ -522,7 +530,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
     const K1Out O{B.raw, B.ctrl, B.tile_cnt, B.raw_cap, P.merge_min, B.prim_slots, B.capt_log2, B.slab};
     uint32_t gs = 0;                                       // scan steps done by this CTA (= chunks consumed)
     for (uint32_t it = 0; it < ntile; it++) {
-        const uint32_t tile = blockIdx.x + it * gridDim.x;
+        const uint32_t tile = S.tidx[it];
         const uint32_t ra = tile * rpc, nr = min(rpc, B.n_reads - ra);
         const unsigned long long oa = S.tb[it][0], ob = S.tb[it][1], oa4 = oa & ~3ull;
         const uint32_t span_lo = (uint32_t)(oa - oa4), span_hi = (uint32_t)(ob - oa4);
@@ -533,7 +541,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
         // (I/D >= indel_min) are sparse: a tile that is fully resident (<= 2 stages) is first screened with 4 instructions per op
         // -- table look-up, OR, compare, predicated OR.  A clean tile gets zeroed summaries and is done; anything suspicious
         // (event candidate, unknown op code) takes the full scan below, which re-reads the same, untouched stages.
-        if (nchunks <= K1_SCREEN_CHUNKS) {
+        if (nchunks <= K1_SCREEN_CHUNKS && !list) {
             uint32_t sus = 0, flags = 0;
             for (uint32_t c = 0; c < nchunks; c++) {
                 mbar_wait(&S.full[(gs + c) % K1_STAGES], ((gs + c) / K1_STAGES) & 1u);
@@ -576,10 +584,10 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
         }
         if (t == 0) { S.roff[nr] = span_hi; S.has_carry = 0; S.flushes = 0; }
         __syncthreads();
-        if (it + 1 < ntile) {                              // next tile needs the scan for sure (long records): prefetch its inputs
+        if (it + 1 < ntile) {                              // next tile needs the scan for sure (long records, or listed): prefetch its inputs
             const unsigned long long na4 = S.tb[it + 1][0] & ~3ull;
-            if ((uint32_t)((S.tb[it + 1][1] - na4 + K1_CHUNK - 1) / K1_CHUNK) > K1_SCREEN_CHUNKS) {
-                const uint32_t ra2 = ra + gridDim.x * rpc, nr2 = min(rpc, B.n_reads - ra2);
+            if (list || (uint32_t)((S.tb[it + 1][1] - na4 + K1_CHUNK - 1) / K1_CHUNK) > K1_SCREEN_CHUNKS) {
+                const uint32_t ra2 = S.tidx[it + 1] * rpc, nr2 = min(rpc, B.n_reads - ra2);
                 if (t < nr2) { pre_off = B.cigar_off[ra2 + t]; pre_flag = B.flag[ra2 + t]; pre_mapq = B.mapq[ra2 + t]; pre_pos = (uint32_t)B.pos[ra2 + t]; }
                 pre_tile = it + 1;
             }
@@ -795,8 +803,10 @@ __device__ __forceinline__ uint32_t k1b_find_read(const unsigned long long* off,
 // merge predicates are all thread-local (main.rs:523-600, 612-635, 673-678); no staging, no block scan.  The walk reads
 // aligned 128-bit vectors, four in flight; the records of a step are neighbours, so the sectors their walks touch are shared,
 // and the stream has just been through L2 for kernel 1a.  Events are parked in shared memory during the walk (a short
-// divergent branch) and written out afterwards with one reservation per warp.  A record too long for one thread is
-// scanned by the whole warp (k1_warp_record).  Raw events go to the atomically allocated region (no tile slices here).
+// divergent branch) and written out afterwards with one reservation per warp.  A record too long (or with too many events)
+// for one thread goes on the list of kernel 1c: the flat block scan (k1_flat), one listed record per tile, which is balanced
+// for CIGARs of any length (ONT batches: ~10 % of the records hold an event, and those are 10^3..10^5 ops long).
+// Raw events go to the atomically allocated region (no tile slices here).
 // The grid is one resident wave (measured: launching a warp per step, flagged or not, took 16 us for 7.8k CTAs).
 // ======================================================================================
 static constexpr int K1B_THREADS = 256;
@@ -810,6 +820,7 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_CTAS) k1b_steps(DevBatch B, D
     __shared__ uint2 s_ev[K1B_THREADS][K1B_EV + 1];    // {left_consume, op word}; the last slot is a dummy
     const uint32_t t = threadIdx.x, lane = t & 31;
     griddep_wait();                                    // kernel 1a's step list and zeroed summaries
+    griddep_launch();                                  // kernel 1c may be placed
     const uint32_t n_list = B.ctrl->n_flagged, nw = (gridDim.x * K1B_THREADS) >> 5;
     const uint32_t imin16 = P.indel_min >= (1u << 28) ? 0xffffffffu : (P.indel_min << 4);
     const uint4* cig4 = reinterpret_cast<const uint4*>(B.cigar);
@@ -878,7 +889,7 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_CTAS) k1b_steps(DevBatch B, D
                     }
                 }
                 if (flags & 0x40u) report(B.ctrl, r, RANK_CIGAR_OP);                                // rust-htslib panics on an unknown op
-                if (cnt > K1B_EV) is_long = true;                                                   // more events than parking space: the warp does it
+                if (cnt > K1B_EV) is_long = true;                                                   // more events than parking space: kernel 1c does it
                 else {
                     uint32_t info = 0;
                     for (uint32_t j = 1; j < cnt; j++) {
@@ -909,8 +920,15 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_CTAS) k1b_steps(DevBatch B, D
                     d[1] = make_uint4(j ? s_ev[t][j - 1].x : 0u, 0u, 0u, 0u);
                 } else B.ctrl->overflow = 1;
             }
-            for (uint32_t lm = __ballot_sync(0xffffffffu, mine && is_long); lm; lm &= lm - 1u)
-                k1_warp_record(B, P, __shfl_sync(0xffffffffu, r, __ffs((int)lm) - 1));
+            {   // records too long (or too eventful) for one thread: on to the list of kernel 1c, which scans them block-wide
+                const uint32_t lm = __ballot_sync(0xffffffffu, mine && is_long);
+                if (lm) {
+                    uint32_t lbase = 0;
+                    if (lane == 0) lbase = atomicAdd(&B.ctrl->n_long, (uint32_t)__popc(lm));
+                    lbase = __shfl_sync(0xffffffffu, lbase, 0);
+                    if (mine && is_long) B.long_list[lbase + __popc(lm & ((1u << lane) - 1u))] = r;
+                }
+            }
             // the next 32 records matter only if the last one of these still ends inside the step
             if (!__shfl_sync(0xffffffffu, (uint32_t)(overlaps && o1 < hi_op), 31)) break;
         }
@@ -1741,8 +1759,17 @@ void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc,
         const uint32_t n_tiles = (B.n_reads + rpc - 1) / rpc;
         uint32_t grid = min(n_tiles, (uint32_t)g_sm_count * (uint32_t)g_k1_ctas_per_sm * (uint32_t)g_k1_waves);
         if ((n_tiles + grid - 1) / grid > K1_MAX_TILES) grid = (n_tiles + K1_MAX_TILES - 1) / K1_MAX_TILES;
-        k1_flat<<<grid, K1_THREADS, sizeof(K1Smem), st>>>(B, P, rpc, n_tiles);
+        k1_flat<<<grid, K1_THREADS, sizeof(K1Smem), st>>>(B, P, rpc, n_tiles, nullptr);
     }
+}
+
+// kernel 1c: the flat block scan over the long records kernel 1b listed, one record per tile.  The length of the list lives
+// on the device; the grid covers the case that every record is on it.
+void launch_k1c(const DevBatch& B, const DevParams& P, cudaStream_t st)
+{
+    uint32_t grid = min(B.n_reads, (uint32_t)g_sm_count * (uint32_t)g_k1_ctas_per_sm * (uint32_t)g_k1_waves);
+    if ((B.n_reads + grid - 1) / grid > K1_MAX_TILES) grid = (B.n_reads + K1_MAX_TILES - 1) / K1_MAX_TILES;
+    launch_dependent(k1_flat, grid ? grid : 1u, K1_THREADS, sizeof(K1Smem), st, B, P, 1u, B.n_reads, (const uint32_t*)B.long_list);
 }
 
 // the screen pass (kernel 1a) and the resolution of its flagged steps (kernel 1b); n_ops < 2^32
