@@ -244,7 +244,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     const size_t d_ctrl = dcarve(sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes);   // ctrl | scan_a | scan_b | dirty_bits : one memset
     const size_t d_cigar = dcarve((max_ops + 4) * 4 + 16), d_coff = dcarve((R + 1) * 8), d_pos = dcarve(R * 4), d_tid = dcarve(R * 4),
                  d_flag = dcarve(R * 2), d_mapq = dcarve(R), d_kind = dcarve(R), d_soff = dcarve((R + 1) * 4), d_sab = dcarve(max_sa_bytes + 16),
-                 d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_slist = dcarve((max_ops / 512 + 16) * 4), d_llist = dcarve(R * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
+                 d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_slist = dcarve((max_ops / 512 + 16) * 4), d_llist = dcarve(R * 4), d_shlist = dcarve(R * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
                  d_raw = dcarve((max_events + kRawHeadroom) * sizeof(RawEv)), d_saev = dcarve(max_events * sizeof(exlr_event)),
                  d_pool = dcarve(pool_cap * sizeof(Seg)), d_dbg = dcarve(8192 * 32), d_loff = dcarve((R + 1) * 4), d_ev = dcarve(max_events * sizeof(exlr_event));
     e = cudaMalloc(&b->d_slab, dof);
@@ -253,7 +253,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     DevBatch& v = b->dv;
     v.ctrl = (Ctrl*)(ds + d_ctrl);
     v.scan_a = (unsigned long long*)(ds + d_ctrl + sizeof(Ctrl)); v.scan_b = v.scan_a + tiles;
-    v.dirty_bits = (uint32_t*)(v.scan_b + tiles); v.step_list = (uint32_t*)(ds + d_slist); v.long_list = (uint32_t*)(ds + d_llist);
+    v.dirty_bits = (uint32_t*)(v.scan_b + tiles); v.step_list = (uint32_t*)(ds + d_slist); v.long_list = (uint32_t*)(ds + d_llist); v.short_list = (uint32_t*)(ds + d_shlist);
     b->ctrl_bytes = sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes;
     v.cigar = (uint32_t*)(ds + d_cigar); v.cigar_off = (unsigned long long*)(ds + d_coff); v.pos = (int32_t*)(ds + d_pos);
     v.tid = (int32_t*)(ds + d_tid); v.flag = (uint16_t*)(ds + d_flag); v.mapq = (uint8_t*)(ds + d_mapq); v.sa_kind = (uint8_t*)(ds + d_kind);
@@ -368,7 +368,7 @@ static int run_kernels(exlr_batch* b)
         if (b->screened) {
             launch_k1a(d, c->dparams, b->n_ops, s1); b->launches++;
             if (c->stage_timing) CK(cudaEventRecord(b->ev_k1_mid, s1));
-            launch_k1b(d, c->dparams, b->n_ops, s1); b->launches++;
+            launch_k1b(d, c->dparams, b->n_ops, s1); b->launches += 2;
             launch_k1c(d, c->dparams, s1); b->launches++;
         } else {
             launch_k1(d, c->dparams, variant, rpc, s1); b->launches++;

@@ -33,7 +33,8 @@ struct Ctrl {
     uint32_t seg_pool_used;
     uint32_t n_flagged;             // 512-op steps of the CIGAR stream kernel 1a found an event candidate in (length of step_list)
     uint32_t n_long;                // records kernel 1b passed on to kernel 1c (length of long_list)
-    uint32_t pad[2];
+    uint32_t n_short;               // records kernel 1b walks itself (length of short_list)
+    uint32_t pad[1];
 };
 static_assert(sizeof(Ctrl) == 64, "Ctrl is the 64-byte result header");
 
@@ -93,6 +94,7 @@ struct DevBatch {
     RawEv* raw;             // [raw_cap]: per-tile slices [0, prim_slots), then the overflow region
     uint32_t* tile_cnt;     // [R] events in each tile's slice
     uint32_t* dirty_bits;   // [R/32] one bit per record: claimed by a thread of kernel 1b (zeroed with ctrl)
+    uint32_t* short_list;   // [R] k1b_claim: claimed records walked by one thread each, any order (ctrl->n_short entries)
     uint32_t* long_list;    // [R] kernel 1b: claimed records too long for one thread, any order (ctrl->n_long entries)
     uint32_t* step_list;    // [max_ops/512 + 1] kernel 1a: the 512-op steps of the CIGAR stream that hold an event candidate, any order
     uint32_t raw_cap, prim_slots, capt_log2, slab;

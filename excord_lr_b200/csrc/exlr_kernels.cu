@@ -795,39 +795,38 @@ __device__ __forceinline__ uint32_t k1b_find_read(const unsigned long long* off,
 }
 
 // ======================================================================================
-// kernel 1b: the flagged steps of kernel 1a, one warp per step, one thread per record
+// kernel 1b: from flagged steps to records, then one thread per record
 //
-// A warp takes a step off the list, finds the records that overlap its 512 ops (one search for the first, then consecutive
-// offsets), and every such record is claimed by exactly one thread on the device (atomic bit per record: a record can
-// overlap several flagged steps) which walks the whole record: left_consume, total_consume, the event sequence and the two
-// merge predicates are all thread-local (main.rs:523-600, 612-635, 673-678); no staging, no block scan.  The walk reads
-// aligned 128-bit vectors, four in flight; the records of a step are neighbours, so the sectors their walks touch are shared,
-// and the stream has just been through L2 for kernel 1a.  Events are parked in shared memory during the walk (a short
-// divergent branch) and written out afterwards with one reservation per warp.  A record too long (or with too many events)
-// for one thread goes on the list of kernel 1c: the flat block scan (k1_flat), one listed record per tile, which is balanced
-// for CIGARs of any length (ONT batches: ~10 % of the records hold an event, and those are 10^3..10^5 ops long).
+// k1b_claim: a warp takes a step off kernel 1a's list, finds the records that overlap its 512 ops (one search for the first,
+// then consecutive offsets) and claims every kept one exactly once on the device (atomic bit per record: a record can overlap
+// several flagged steps).  Claimed records go on one of two lists: short ones (walked by a thread each, below) and long
+// ones (kernel 1c: the flat block scan, one record per tile, which is balanced for CIGARs of any length -- in ONT batches
+// ~10 % of the records hold an event and those are 10^3..10^5 ops long).
+// k1b_walk: one thread per short record, warps full.  left_consume, total_consume, the event sequence and the two merge
+// predicates are all thread-local (main.rs:523-600, 612-635, 673-678); no staging, no block scan.  The walk reads aligned
+// 128-bit vectors, four in flight; neighbouring threads walk neighbouring records, so the sectors they touch are shared, and
+// the stream has just been through L2 for kernel 1a.  The loop body is branch-free (lanes walk different records): an event
+// is parked in shared memory by a predicated store, the merge predicates are evaluated on the parked events afterwards, the
+// events are written out with one reservation per warp.  A record with more events than parking space joins the long list.
 // Raw events go to the atomically allocated region (no tile slices here).
-// The grid is one resident wave (measured: launching a warp per step, flagged or not, took 16 us for 7.8k CTAs).
+// Both grids are one resident wave (measured: a warp per step, flagged or not, was 7.8k CTAs and 16 us of CTA turnover; and
+// walking inside the per-step warps ran at a third of the warp width, since most of a step's records belong to a neighbour).
 // ======================================================================================
 static constexpr int K1B_THREADS = 256;
-static constexpr int K1B_CTAS = 5;                     // CTAs per SM
-static constexpr uint32_t K1B_LONG = 256;              // ops; longer records are scanned by the warp
+static constexpr uint32_t K1B_LONG = 256;              // ops; longer records go to kernel 1c
 static constexpr uint32_t K1B_EV = 4;                  // events per record parked in shared memory during the walk
 static constexpr int K1B_VEC = 4;                      // 128-bit loads in flight per walking thread
 
-__global__ void __launch_bounds__(K1B_THREADS, K1B_CTAS) k1b_steps(DevBatch B, DevParams P, unsigned long long n_ops)
+__global__ void __launch_bounds__(K1B_THREADS) k1b_claim(DevBatch B, DevParams P, unsigned long long n_ops)
 {
-    __shared__ uint2 s_ev[K1B_THREADS][K1B_EV + 1];    // {left_consume, op word}; the last slot is a dummy
     const uint32_t t = threadIdx.x, lane = t & 31;
     griddep_wait();                                    // kernel 1a's step list and zeroed summaries
-    griddep_launch();                                  // kernel 1c may be placed
+    griddep_launch();
     const uint32_t n_list = B.ctrl->n_flagged, nw = (gridDim.x * K1B_THREADS) >> 5;
-    const uint32_t imin16 = P.indel_min >= (1u << 28) ? 0xffffffffu : (P.indel_min << 4);
-    const uint4* cig4 = reinterpret_cast<const uint4*>(B.cigar);
     for (uint32_t li = (blockIdx.x * K1B_THREADS + t) >> 5; li < n_list; li += nw) {
         const bool trace = B.dbg && B.dbg_sel == 1u;
         const unsigned long long tr0 = trace ? gtimer() : 0ull;
-        unsigned long long tr1 = 0, tr2 = 0;
+        unsigned long long tr1 = 0;
         const uint32_t st = B.step_list[li];
         const unsigned long long lo_op = (unsigned long long)st * K1A_STEP_OPS, hi_op = min(lo_op + K1A_STEP_OPS, n_ops);
         if (lo_op >= hi_op) continue;
@@ -836,22 +835,12 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_CTAS) k1b_steps(DevBatch B, D
         for (uint32_t rb = r_first;; rb += 32) {                              // records overlapping the step, 32 at a time
             const uint32_t r = rb + lane;
             unsigned long long o0 = 0, o1 = 0;
-            uint32_t flag = 0, mapq = 0, pos2 = 0;
+            uint32_t flag = 0, mapq = 0;
             const bool in = r < B.n_reads;
-            if (in) { o0 = B.cigar_off[r]; o1 = B.cigar_off[r + 1]; flag = B.flag[r]; mapq = B.mapq[r]; pos2 = (uint32_t)B.pos[r]; }
+            if (in) { o0 = B.cigar_off[r]; o1 = B.cigar_off[r + 1]; flag = B.flag[r]; mapq = B.mapq[r]; }
             const bool overlaps = in && o0 < hi_op;                           // (o1 > lo_op holds from r_first on, empty records aside)
             bool mine = overlaps && o1 > o0 && o1 > lo_op && keep_record(P, flag, mapq);
-            bool is_long = mine && o1 - o0 > K1B_LONG;
-            // the record's first vectors are requested before the claim is known: both round trips overlap
-            const unsigned long long a0 = o0 & ~3ull;
-            const uint32_t nv = mine && !is_long ? (uint32_t)((((o1 + 3ull) & ~3ull) - a0) >> 2) : 0u;   // aligned vectors spanned
-            const uint32_t head = (uint32_t)(o0 - a0), nops = (uint32_t)(o1 - o0);
-            const uint4* c4 = cig4 + (a0 >> 2);
-            uint4 q[K1B_VEC];
-#pragma unroll
-            for (int k = 0; k < K1B_VEC; k++) q[k] = (uint32_t)k < nv ? __ldg(c4 + k) : make_uint4(0u, 0u, 0u, 0u);
-            {   // one owner per record on the whole device.  The 32 records of the warp share at most two words of the claim bitmap:
-                // two atomics per warp instead of one per lane
+            {   // the 32 records of the warp share at most two words of the claim bitmap: two atomics per warp, not one per lane
                 const uint32_t cb = __ballot_sync(0xffffffffu, mine), sh = rb & 31u;
                 const uint32_t lo_bits = cb << sh, hi_bits = sh ? cb >> (32u - sh) : 0u;
                 uint32_t old = 0;
@@ -861,80 +850,115 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_CTAS) k1b_steps(DevBatch B, D
                 const uint32_t p = sh + lane;
                 if ((p < 32u ? old_lo >> p : old_hi >> (p - 32u)) & 1u) mine = false;
             }
-            // ---- the walk.  Lanes walk different records, so the loop body is kept free of branches: an op outside the record
-            // reads as 0M, an event only parks {left_consume, op} in shared memory (slot K1B_EV is a dummy that every
-            // non-event writes to); the merge predicates are evaluated on the parked events afterwards.
-            uint32_t cnt = 0, L = 0, flags = 0;
-            if (mine && !is_long) {
-                for (uint32_t vb = 0; vb < nv; vb += K1B_VEC) {
-                    if (vb) {
-#pragma unroll
-                        for (int k = 0; k < K1B_VEC; k++) q[k] = vb + k < nv ? __ldg(c4 + vb + k) : make_uint4(0u, 0u, 0u, 0u);
-                    }
-#pragma unroll
-                    for (int k = 0; k < K1B_VEC; k++) {
-                        const uint32_t vv[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const uint32_t e = (vb + k) * 4u + j;                 // element index counted from a0
-                            const uint32_t v = (e - head) < nops ? vv[j] : 0u;
-                            uint32_t f;
-                            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(f) : "r"(K1_LUT_LO), "r"(K1_LUT_HI), "r"(v));
-                            flags |= f;
-                            const bool isev = (f & 2u) && v >= imin16;               // I/D >= indel_min (main.rs:553,569)
-                            s_ev[t][isev ? min(cnt, K1B_EV) : K1B_EV] = make_uint2(L, v);
-                            cnt += isev ? 1u : 0u;
-                            L += (f & 1u) ? (v >> 4) : 0u;                          // M D N = consume the reference (main.rs:528-545)
-                        }
-                    }
-                }
-                if (flags & 0x40u) report(B.ctrl, r, RANK_CIGAR_OP);                                // rust-htslib panics on an unknown op
-                if (cnt > K1B_EV) is_long = true;                                                   // more events than parking space: kernel 1c does it
-                else {
-                    uint32_t info = 0;
-                    for (uint32_t j = 1; j < cnt; j++) {
-                        const uint2 x = s_ev[t][j - 1], y = s_ev[t][j];
-                        if ((x.y & 15u) == 2u && (y.y & 15u) == 2u) {
-                            if (j == 1u && abs_diff(pos2 + y.x, pos2 + x.x + (x.y >> 4)) < P.merge_min) info |= K1_PAIR_MERGE;   // main.rs:615
-                            if (abs_diff(pos2 + x.x, pos2 + y.x + (y.y >> 4)) < P.merge_min) info |= K1_FAR_HIT;                  // main.rs:673-678
-                        }
-                    }
-                    B.k1[r] = make_uint2(L, (cnt & K1_CNT_MASK) | info);
-                }
-            }
-            if (trace && !tr2) { __syncwarp(); tr2 = gtimer(); }
-            // parked events: warp scan of the counts, one reservation, every lane writes its own
-            const uint32_t parked = mine && !is_long ? cnt : 0u;
-            uint32_t incl = parked;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            uint32_t base = 0;
-            if (lane == 0 && total) base = atomicAdd(&B.ctrl->n_raw, total);
-            base = B.prim_slots + __shfl_sync(0xffffffffu, base, 0) + incl - parked;
-            for (uint32_t j = 0; j < parked; j++) {
-                if (base + j < B.raw_cap) {
-                    const uint2 e = s_ev[t][j];
-                    uint4* d = reinterpret_cast<uint4*>(B.raw + base + j);
-                    d[0] = make_uint4(r, j, e.x, (e.y >> 4) | ((e.y & 15u) == 2u ? 0x80000000u : 0u));
-                    d[1] = make_uint4(j ? s_ev[t][j - 1].x : 0u, 0u, 0u, 0u);
-                } else B.ctrl->overflow = 1;
-            }
-            {   // records too long (or too eventful) for one thread: on to the list of kernel 1c, which scans them block-wide
-                const uint32_t lm = __ballot_sync(0xffffffffu, mine && is_long);
-                if (lm) {
-                    uint32_t lbase = 0;
-                    if (lane == 0) lbase = atomicAdd(&B.ctrl->n_long, (uint32_t)__popc(lm));
-                    lbase = __shfl_sync(0xffffffffu, lbase, 0);
-                    if (mine && is_long) B.long_list[lbase + __popc(lm & ((1u << lane) - 1u))] = r;
-                }
-            }
+            const bool is_long = mine && o1 - o0 > K1B_LONG;
+            const uint32_t sm = __ballot_sync(0xffffffffu, mine && !is_long), lm = __ballot_sync(0xffffffffu, is_long);
+            uint32_t sbase = 0, lbase = 0;
+            if (lane == 0 && sm) sbase = atomicAdd(&B.ctrl->n_short, (uint32_t)__popc(sm));
+            if (lane == 1 && lm) lbase = atomicAdd(&B.ctrl->n_long, (uint32_t)__popc(lm));
+            sbase = __shfl_sync(0xffffffffu, sbase, 0); lbase = __shfl_sync(0xffffffffu, lbase, 1);
+            const uint32_t below = (1u << lane) - 1u;
+            if (mine && !is_long) B.short_list[sbase + __popc(sm & below)] = r;
+            if (is_long) B.long_list[lbase + __popc(lm & below)] = r;
             // the next 32 records matter only if the last one of these still ends inside the step
             if (!__shfl_sync(0xffffffffu, (uint32_t)(overlaps && o1 < hi_op), 31)) break;
         }
-        if (trace && lane == 0) {                                             // EXLR_OPT_TRACE: {start, search done, first walk done | end}
+        if (trace && lane == 0) {                                             // EXLR_OPT_TRACE: {start, search done, end, 0}
             unsigned long long* d = B.dbg + 4ull * (li & 8191u);
-            d[0] = tr0; d[1] = tr1; d[2] = tr2; d[3] = gtimer();
+            d[0] = tr0; d[1] = tr1; d[2] = gtimer(); d[3] = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(K1B_THREADS) k1b_walk(DevBatch B, DevParams P)
+{
+    __shared__ uint2 s_ev[K1B_THREADS][K1B_EV + 1];    // {left_consume, op word}; the extra slot tells "more than K1B_EV"
+    const uint32_t t = threadIdx.x, lane = t & 31;
+    griddep_wait();                                    // k1b_claim's lists
+    griddep_launch();
+    const uint32_t n_list = B.ctrl->n_short, stride = gridDim.x * K1B_THREADS;
+    const uint32_t imin16 = P.indel_min >= (1u << 28) ? 0xffffffffu : (P.indel_min << 4);
+    const uint4* cig4 = reinterpret_cast<const uint4*>(B.cigar);
+    const uint32_t ev0 = smem_u32(&s_ev[t][0]), ev_end = ev0 + (K1B_EV + 1) * 8u;
+    for (uint32_t i0 = blockIdx.x * K1B_THREADS + (t & ~31u); i0 < n_list; i0 += stride) {     // warp-uniform trip count
+        const uint32_t i = i0 + lane;
+        const bool have = i < n_list;
+        uint32_t r = 0, pos2 = 0, nv = 0, head = 0, nops = 0;
+        const uint4* c4 = cig4;
+        if (have) {
+            r = B.short_list[i];
+            const unsigned long long o0 = B.cigar_off[r], o1 = B.cigar_off[r + 1], a0 = o0 & ~3ull;
+            pos2 = (uint32_t)B.pos[r];
+            nv = (uint32_t)((((o1 + 3ull) & ~3ull) - a0) >> 2);                // aligned vectors spanned (<= 65)
+            head = (uint32_t)(o0 - a0); nops = (uint32_t)(o1 - o0);
+            c4 = cig4 + (a0 >> 2);
+        }
+        uint32_t L = 0, flags = 0, evp = ev0;
+        for (uint32_t vb = 0; vb < nv; vb += K1B_VEC) {
+            uint4 q[K1B_VEC];
+#pragma unroll
+            for (int k = 0; k < K1B_VEC; k++) q[k] = vb + k < nv ? __ldg(c4 + vb + k) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int k = 0; k < K1B_VEC; k++) {
+                const uint32_t vv[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t e = (vb + k) * 4u + j;                     // element index counted from the aligned base
+                    const uint32_t v = (e - head) < nops ? vv[j] : 0u;         // outside the record: reads as 0M
+                    uint32_t f;
+                    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(f) : "r"(K1_LUT_LO), "r"(K1_LUT_HI), "r"(v));
+                    flags |= f;
+                    // an event (I/D >= indel_min, main.rs:553,569) parks {left_consume, op} and bumps the parking pointer, all predicated
+                    asm volatile("{\n.reg .pred p, q;\n"
+                                 "setp.ne.u32 q, %3, 0;\n"
+                                 "setp.ge.and.u32 p, %2, %4, q;\n"
+                                 "setp.lt.and.u32 p, %0, %5, p;\n"
+                                 "@p st.shared.v2.u32 [%0], {%1, %2};\n"
+                                 "@p add.u32 %0, %0, 8;\n}"
+                                 : "+r"(evp) : "r"(L), "r"(v), "r"(f & 2u), "r"(imin16), "r"(ev_end) : "memory");
+                    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(L) : "r"(f & 1u), "r"(v >> 4));   // M D N = consume the reference (main.rs:528-545)
+                }
+            }
+        }
+        const uint32_t cnt = (evp - ev0) >> 3;
+        bool is_long = false;
+        if (have) {
+            if (flags & 0x40u) report(B.ctrl, r, RANK_CIGAR_OP);                                    // rust-htslib panics on an unknown op
+            if (cnt > K1B_EV) is_long = true;                                                       // more events than parking space: kernel 1c does it
+            else {
+                uint32_t info = 0;
+                for (uint32_t j = 1; j < cnt; j++) {
+                    const uint2 x = s_ev[t][j - 1], y = s_ev[t][j];
+                    if ((x.y & 15u) == 2u && (y.y & 15u) == 2u) {
+                        if (j == 1u && abs_diff(pos2 + y.x, pos2 + x.x + (x.y >> 4)) < P.merge_min) info |= K1_PAIR_MERGE;   // main.rs:615
+                        if (abs_diff(pos2 + x.x, pos2 + y.x + (y.y >> 4)) < P.merge_min) info |= K1_FAR_HIT;                  // main.rs:673-678
+                    }
+                }
+                B.k1[r] = make_uint2(L, (cnt & K1_CNT_MASK) | info);
+            }
+        }
+        // parked events: warp scan of the counts, one reservation, every lane writes its own
+        const uint32_t parked = have && !is_long ? cnt : 0u;
+        uint32_t incl = parked;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t base = 0;
+        if (lane == 0 && total) base = atomicAdd(&B.ctrl->n_raw, total);
+        base = B.prim_slots + __shfl_sync(0xffffffffu, base, 0) + incl - parked;
+        for (uint32_t j = 0; j < parked; j++) {
+            if (base + j < B.raw_cap) {
+                const uint2 e = s_ev[t][j];
+                uint4* d = reinterpret_cast<uint4*>(B.raw + base + j);
+                d[0] = make_uint4(r, j, e.x, (e.y >> 4) | ((e.y & 15u) == 2u ? 0x80000000u : 0u));
+                d[1] = make_uint4(j ? s_ev[t][j - 1].x : 0u, 0u, 0u, 0u);
+            } else B.ctrl->overflow = 1;
+        }
+        const uint32_t lm = __ballot_sync(0xffffffffu, is_long);
+        if (lm) {
+            uint32_t lbase = 0;
+            if (lane == 0) lbase = atomicAdd(&B.ctrl->n_long, (uint32_t)__popc(lm));
+            lbase = __shfl_sync(0xffffffffu, lbase, 0);
+            if (is_long) B.long_list[lbase + __popc(lm & ((1u << lane) - 1u))] = r;
         }
     }
 }
@@ -1767,7 +1791,8 @@ void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc,
 // on the device; the grid covers the case that every record is on it.
 void launch_k1c(const DevBatch& B, const DevParams& P, cudaStream_t st)
 {
-    uint32_t grid = min(B.n_reads, (uint32_t)g_sm_count * (uint32_t)g_k1_ctas_per_sm * (uint32_t)g_k1_waves);
+    // one resident wave (the list is usually short or empty, and every CTA of a larger grid costs a launch slot just to see that)
+    uint32_t grid = min(B.n_reads, (uint32_t)g_sm_count * (uint32_t)g_k1_ctas_per_sm);
     if ((B.n_reads + grid - 1) / grid > K1_MAX_TILES) grid = (B.n_reads + K1_MAX_TILES - 1) / K1_MAX_TILES;
     launch_dependent(k1_flat, grid ? grid : 1u, K1_THREADS, sizeof(K1Smem), st, B, P, 1u, B.n_reads, (const uint32_t*)B.long_list);
 }
@@ -1787,10 +1812,12 @@ void launch_k1a(const DevBatch& B, const DevParams& P, unsigned long long n_ops,
 
 void launch_k1b(const DevBatch& B, const DevParams& P, unsigned long long n_ops, cudaStream_t st)
 {
-    // the number of flagged steps lives on the device: one resident wave of warps strides over the list
+    // the numbers of flagged steps and of claimed records live on the device: one resident wave strides over each list
     const uint32_t steps = k1a_steps(n_ops);
-    const uint32_t grid = min((steps + K1B_THREADS / 32 - 1) / (K1B_THREADS / 32), (uint32_t)g_sm_count * K1B_CTAS);
-    launch_dependent(k1b_steps, grid ? grid : 1u, K1B_THREADS, 0, st, B, P, n_ops);
+    const uint32_t g1 = min((steps + K1B_THREADS / 32 - 1) / (K1B_THREADS / 32), (uint32_t)g_sm_count * 8u);
+    launch_dependent(k1b_claim, g1 ? g1 : 1u, K1B_THREADS, 0, st, B, P, n_ops);
+    const uint32_t g2 = min((B.n_reads + K1B_THREADS - 1) / K1B_THREADS, (uint32_t)g_sm_count * 8u);
+    launch_dependent(k1b_walk, g2 ? g2 : 1u, K1B_THREADS, 0, st, B, P);
 }
 
 void launch_k3a(const DevBatch& B, const DevParams& P, uint32_t mean_ops, cudaStream_t st)
