@@ -25,6 +25,8 @@ EXLR_OPT_OVERLAP = 3
 EXLR_OPT_K1_CTAS_PER_SM = 4
 EXLR_OPT_K1_WAVES = 5
 EXLR_OPT_STAGE_TIMING = 6
+EXLR_OPT_TRACE = 7
+EXLR_OPT_DEVICE_FORMAT = 8
 # see EXLR_OPT_CIGAR_KERNEL in include/exlr.h
 CIGAR_KERNEL_AUTO, CIGAR_KERNEL_WARP, CIGAR_KERNEL_FLAT, CIGAR_KERNEL_SCREEN = 0, 1, 2, 3
 
@@ -92,6 +94,7 @@ def load_library() -> C.CDLL:
     lib.exlr_submit_resident.argtypes = [vp]
     lib.exlr_wait.argtypes = [vp, C.POINTER(_Result)]
     lib.exlr_wait_resident.argtypes = [vp, C.POINTER(_Result)]
+    lib.exlr_wait_text.argtypes = [vp, C.POINTER(_Result), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.exlr_get_timing.argtypes = [vp, C.POINTER(Timing)]
     lib.exlr_format_lines.restype = C.c_int64
     lib.exlr_format_lines.argtypes = [vp, vp, C.POINTER(_Result), u64, u64, i32, C.c_char_p, vp, vp, u64]
@@ -99,7 +102,7 @@ def load_library() -> C.CDLL:
     lib.exlr_strerror.argtypes = [i32]
     lib.exlr_last_cuda_error.restype = C.c_char_p
     for f in ("exlr_create", "exlr_set_option", "exlr_batch_alloc", "exlr_batch_get_views", "exlr_submit", "exlr_upload",
-              "exlr_submit_resident", "exlr_wait", "exlr_wait_resident", "exlr_get_timing"):
+              "exlr_submit_resident", "exlr_wait", "exlr_wait_resident", "exlr_wait_text", "exlr_get_timing"):
         getattr(lib, f).restype = i32
     _lib = lib
     return lib
@@ -196,6 +199,16 @@ class DeviceBatch:
             _check(rc, int(raw.err_read) if rc <= -10 else -1)
         return Result(raw, copy)
 
+    def wait_text(self):
+        """With EXLR_OPT_DEVICE_FORMAT: (Result without events, the formatted non-verbose lines as bytes)."""
+        raw, ptr, n = _Result(), C.c_void_p(), C.c_uint64()
+        rc = self.lib.exlr_wait_text(self.handle, C.byref(raw), C.byref(ptr), C.byref(n))
+        if rc == -4:
+            raise ExlrCapacityError(int(raw.n_events))
+        if rc != 0 and rc > -10:
+            _check(rc)
+        return Result(raw, False, resident=True), (C.string_at(ptr.value, n.value) if n.value else b"")
+
     def wait_resident(self) -> Result:
         raw = _Result()
         rc = self.lib.exlr_wait_resident(self.handle, C.byref(raw))
@@ -276,19 +289,23 @@ class Extractor:
 
 
 def extract(hb: HostBatch, params: ExlrParams, device: int = 0, cigar_kernel: int = CIGAR_KERNEL_AUTO,
-            reads_per_cta: int = 0, verbose: bool = False, max_events: int = 0, grow: bool = True):
+            reads_per_cta: int = 0, verbose: bool = False, max_events: int = 0, grow: bool = True, device_format: bool = False):
     """One-shot: host batch -> (Result, formatted lines).  Host buffers in, host buffers out.
-    If the event buffers turn out too small the batch is re-run once with the size the device reported."""
+    If the event buffers turn out too small the batch is re-run once with the size the device reported.
+    device_format: also format the (non-verbose) lines on the device; they come back as Result.device_text."""
     ex = Extractor(params, hb.ref_names, device)
     try:
         ex.set_option(EXLR_OPT_CIGAR_KERNEL, cigar_kernel)
         ex.set_option(EXLR_OPT_READS_PER_CTA, reads_per_cta)
+        ex.set_option(EXLR_OPT_DEVICE_FORMAT, int(device_format))
         for attempt in range(5):
             b = ex.batch_for(hb, max_events)
             try:
                 b.submit()
                 try:
+                    dtext = b.wait_text()[1] if device_format else None
                     res = b.wait()
+                    res.device_text = dtext
                 except ExlrCapacityError as e:
                     if not grow or attempt == 4:
                         raise

@@ -42,6 +42,7 @@ struct exlr_ctx {
     int stage_timing = 1;                      // EXLR_OPT_STAGE_TIMING: CUDA events between the kernels (exlr_timing per stage)
     int k1_ctas = 0;                           // EXLR_OPT_K1_CTAS_PER_SM (0 = 3 when overlapping, which leaves room for the SA branch, else 4)
     uint32_t reads_per_cta = 0;                // EXLR_OPT_READS_PER_CTA (0 = auto)
+    int device_format = 0;                     // EXLR_OPT_DEVICE_FORMAT: kernels 5a/5b write the output lines; read with exlr_wait_text
     int skip_screen = 0;                       // auto mode: batches left to run without the screen pass (the last screened one was event-dense)
 };
 
@@ -55,6 +56,8 @@ struct exlr_batch {
     void* h_slab = nullptr;                    // pinned: inputs
     void* h_out = nullptr;                     // pinned: ctrl + line_off + events
     Ctrl* h_ctrl = nullptr; uint32_t* h_line_off = nullptr; exlr_event* h_events = nullptr;
+    char* h_text = nullptr;                    // pinned: formatted lines (allocated with the batch when EXLR_OPT_DEVICE_FORMAT is set)
+    bool formatted = false;                    // the last submit ran kernels 5a/5b
     void* d_slab = nullptr;                    // one device allocation, carved up below
     DevBatch dv{};
     size_t ctrl_bytes = 0;                     // ctrl + both scan status arrays (one memset)
@@ -67,6 +70,9 @@ struct exlr_batch {
 // kernel 1 reserves overflow slabs of 128 raw slots ahead of use (one spare per persistent CTA, see k1_flush): room for
 // them on top of the caller's max_events so that only real events can exhaust the buffer
 static constexpr size_t kRawHeadroom = 256 * 1024;
+// EXLR_OPT_DEVICE_FORMAT: room for the formatted lines, per max_events entry (a typical line is 40-60 bytes; when a batch needs
+// more, exlr_wait_text says so and the caller formats on the host)
+static constexpr size_t kTextBytesPerLine = 96;
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -116,6 +122,7 @@ const char* exlr_strerror(int s)
     case EXLR_ERR_SA_NM: return "SA NM is not an integer (reference panics)";
     case EXLR_ERR_MERGE_DOMAIN: return "more than two indel events with merge_min reaching across them: the reference panics or duplicates events here";
     case EXLR_ERR_SPLIT_COUNT: return "more than 2^24 segments in one record";
+    case EXLR_ERR_TEXT_CAPACITY: return "formatted lines exceed the batch's text buffer; use exlr_wait + exlr_format_lines";
     default: return "unknown status";
     }
 }
@@ -177,6 +184,7 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
     case EXLR_OPT_CIGAR_KERNEL: if (value < 0 || value > 3) return EXLR_ERR_ARG; c->cigar_kernel = (int)value; return EXLR_OK;
     case EXLR_OPT_READS_PER_CTA: if (value < 0 || value > 128) return EXLR_ERR_ARG; c->reads_per_cta = (uint32_t)value; return EXLR_OK;
     case EXLR_OPT_OVERLAP: c->overlap = value != 0; return EXLR_OK;
+    case EXLR_OPT_DEVICE_FORMAT: c->device_format = value != 0; return EXLR_OK;
     case EXLR_OPT_TRACE: if (value < 0 || value > 6) return EXLR_ERR_ARG; c->trace = (int)value; return EXLR_OK;
     case EXLR_OPT_STAGE_TIMING: c->stage_timing = value != 0; return EXLR_OK;
     case EXLR_OPT_K1_WAVES: if (value < 1 || value > 16) return EXLR_ERR_ARG; set_k1_waves((int)value); return EXLR_OK;
@@ -198,7 +206,7 @@ void exlr_batch_free(exlr_batch* b)
     if (b->stream2) cudaStreamDestroy(b->stream2);
     if (b->stream) cudaStreamDestroy(b->stream);
     cudaFree(b->d_slab);
-    cudaFreeHost(b->h_slab); cudaFreeHost(b->h_out);
+    cudaFreeHost(b->h_slab); cudaFreeHost(b->h_out); cudaFreeHost(b->h_text);
     delete b;
 }
 
@@ -234,6 +242,10 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostAlloc(outputs)"); }
     b->h_ctrl = (Ctrl*)((char*)b->h_out + o_ctrl); b->h_line_off = (uint32_t*)((char*)b->h_out + o_loff);
     b->h_events = (exlr_event*)((char*)b->h_out + o_ev);
+    if (c->device_format) {
+        e = cudaHostAlloc((void**)&b->h_text, max_events * kTextBytesPerLine + 16, cudaHostAllocDefault);
+        if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostAlloc(text)"); }
+    }
     // ---- device slab
     const uint32_t tiles = scan_tiles((uint32_t)R);
     const bool need_pool = c->params.max_supp_alignm + 1 > (uint64_t)kLocalSegs;
@@ -241,12 +253,15 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     size_t dof = 0;
     auto dcarve = [&](size_t bytes) { size_t at = dof; dof = align_up(dof + bytes, A); return at; };
     const size_t bits_bytes = align_up((R + 31) / 32 * 4, 16);
-    const size_t d_ctrl = dcarve(sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes);   // ctrl | scan_a | scan_b | dirty_bits : one memset
+    const uint32_t ttiles = c->device_format ? text_scan_tiles((uint32_t)max_events) : 0;
+    const size_t text_cap = c->device_format ? max_events * kTextBytesPerLine : 0;
+    if (text_cap >= 0xfffffff0ull) { exlr_batch_free(b); return EXLR_ERR_ARG; }
+    const size_t d_ctrl = dcarve(sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes + (size_t)ttiles * 8);   // ctrl | scan_a | scan_b | dirty_bits | scan_c : one memset
     const size_t d_cigar = dcarve((max_ops + 4) * 4 + 16), d_coff = dcarve((R + 1) * 8), d_pos = dcarve(R * 4), d_tid = dcarve(R * 4),
                  d_flag = dcarve(R * 2), d_mapq = dcarve(R), d_kind = dcarve(R), d_soff = dcarve((R + 1) * 4), d_sab = dcarve(max_sa_bytes + 16),
                  d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_slist = dcarve((max_ops / 512 + 16) * 4), d_llist = dcarve(R * 4), d_shlist = dcarve(R * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
                  d_raw = dcarve((max_events + kRawHeadroom) * sizeof(RawEv)), d_saev = dcarve(max_events * sizeof(exlr_event)),
-                 d_pool = dcarve(pool_cap * sizeof(Seg)), d_dbg = dcarve(8192 * 32), d_loff = dcarve((R + 1) * 4), d_ev = dcarve(max_events * sizeof(exlr_event));
+                 d_pool = dcarve(pool_cap * sizeof(Seg)), d_dbg = dcarve(8192 * 32), d_toff = dcarve(c->device_format ? (max_events + 1) * 4 : 0), d_text = dcarve(text_cap + 16), d_loff = dcarve((R + 1) * 4), d_ev = dcarve(max_events * sizeof(exlr_event));
     e = cudaMalloc(&b->d_slab, dof);
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaMalloc(batch)"); }
     char* ds = (char*)b->d_slab;
@@ -254,7 +269,9 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     v.ctrl = (Ctrl*)(ds + d_ctrl);
     v.scan_a = (unsigned long long*)(ds + d_ctrl + sizeof(Ctrl)); v.scan_b = v.scan_a + tiles;
     v.dirty_bits = (uint32_t*)(v.scan_b + tiles); v.step_list = (uint32_t*)(ds + d_slist); v.long_list = (uint32_t*)(ds + d_llist); v.short_list = (uint32_t*)(ds + d_shlist);
-    b->ctrl_bytes = sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes;
+    v.scan_c = (unsigned long long*)((char*)v.dirty_bits + bits_bytes);
+    v.text_off = c->device_format ? (uint32_t*)(ds + d_toff) : nullptr; v.text = (uint8_t*)(ds + d_text); v.text_cap = (uint32_t)text_cap;
+    b->ctrl_bytes = sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes + (size_t)ttiles * 8;
     v.cigar = (uint32_t*)(ds + d_cigar); v.cigar_off = (unsigned long long*)(ds + d_coff); v.pos = (int32_t*)(ds + d_pos);
     v.tid = (int32_t*)(ds + d_tid); v.flag = (uint16_t*)(ds + d_flag); v.mapq = (uint8_t*)(ds + d_mapq); v.sa_kind = (uint8_t*)(ds + d_kind);
     v.sa_off = (uint32_t*)(ds + d_soff); v.sa_bytes = (uint8_t*)(ds + d_sab);
@@ -385,6 +402,8 @@ static int run_kernels(exlr_batch* b)
     if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K4A], st));
     launch_k4b(d, c->dparams, st); b->launches++;
     CK(cudaEventRecord(b->ev[EV_K4B], st));
+    b->formatted = d.text_off != nullptr;
+    if (b->formatted) { launch_k5(d, st); b->launches += 2; }
     CK(cudaMemcpyAsync(b->h_ctrl, d.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(b->ev[EV_D2H], st));
     CK(cudaGetLastError());
@@ -481,6 +500,33 @@ static int finish(exlr_batch* b, exlr_result* res, bool fetch)
 }
 
 int exlr_wait(exlr_batch* b, exlr_result* res) { return finish(b, res, true); }
+
+int exlr_wait_text(exlr_batch* b, exlr_result* res, const char** text, uint64_t* n_bytes)
+{
+    if (!text || !n_bytes) return EXLR_ERR_ARG;
+    *text = nullptr; *n_bytes = 0;
+    int rc = finish(b, res, false);
+    if (rc != EXLR_OK && rc > -10) return rc;                           // no usable result at all
+    if (!b->formatted || b->n_reads == 0) return b->n_reads == 0 ? rc : EXLR_ERR_STATE;
+    const Ctrl& c = *b->h_ctrl;
+    if (c.text_bytes > b->dv.text_cap) return EXLR_ERR_TEXT_CAPACITY;    // exlr_wait + exlr_format_lines still work
+    uint64_t nb = c.text_bytes;
+    if (rc <= -10) {
+        // a record on which the reference panics: the lines of the records before it stand (its BufWriter is flushed on unwind)
+        uint32_t first_line = 0, off = 0;
+        CK(cudaMemcpyAsync(&first_line, b->dv.line_off + res->err_read, 4, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+        CK(cudaMemcpyAsync(&off, b->dv.text_off + first_line, 4, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+        nb = off;
+    }
+    if (nb) {
+        CK(cudaMemcpyAsync(b->h_text, b->dv.text, nb, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+    }
+    *text = b->h_text; *n_bytes = nb;
+    return rc;
+}
 int exlr_wait_resident(exlr_batch* b, exlr_result* res) { return finish(b, res, false); }
 
 int exlr_get_timing(exlr_batch* b, exlr_timing* t)

@@ -34,9 +34,11 @@ struct Ctrl {
     uint32_t n_flagged;             // 512-op steps of the CIGAR stream kernel 1a found an event candidate in (length of step_list)
     uint32_t n_long;                // records kernel 1b passed on to kernel 1c (length of long_list)
     uint32_t n_short;               // records kernel 1b walks itself (length of short_list)
-    uint32_t pad[1];
+    uint32_t ticket_c;              // dynamic tile ids of kernel 5a's chained scan
+    uint32_t text_bytes;            // kernel 5a: bytes of the formatted lines
+    uint32_t pad[15];
 };
-static_assert(sizeof(Ctrl) == 64, "Ctrl is the 64-byte result header");
+static_assert(sizeof(Ctrl) == 128, "Ctrl is the 128-byte result header");
 
 // raw indel event, kernel 1 -> kernel 4b (32 bytes, two 16-byte stores)
 struct RawEv {
@@ -101,10 +103,14 @@ struct DevBatch {
     exlr_event* sa_ev;      // [max_events] SA-derived events, per record contiguous
     Seg* seg_pool; uint32_t seg_pool_cap;
     unsigned long long* scan_a; unsigned long long* scan_b;   // chained-scan tile status
+    unsigned long long* scan_c;                                // ... of kernel 5a (one word per 256 events)
     Ctrl* ctrl;
     // outputs
     uint32_t* line_off;     // [R+1]
     exlr_event* events;     // [max_events]
+    uint32_t* text_off;     // [max_events+1] byte offset of every line (kernel 5a); null unless EXLR_OPT_DEVICE_FORMAT
+    uint8_t* text;          // [text_cap] the formatted lines (kernel 5b)
+    uint32_t text_cap;
     uint32_t n_reads; uint32_t max_events;
     unsigned long long* dbg;    // optional per-CTA trace (EXLR_OPT_TRACE), 4 x u64 per entry; kernel 1: {start, first data, end, tiles | scanned tiles << 32}
     uint32_t dbg_sel;           // which kernel writes the trace: 1 = kernel 1 / 1b, 2 = k0, 3 = k3a, 4 = k3b, 5 = k4a, 6 = k4b ({start, mid, end, 0})
@@ -123,6 +129,8 @@ void set_k1_ctas_per_sm(int n);
 void set_k1_waves(int n);
 size_t k1_flat_smem_bytes();
 uint32_t scan_tiles(uint32_t n_reads);
+uint32_t text_scan_tiles(uint32_t max_events);
+void launch_k5(const DevBatch& B, cudaStream_t st);
 void launch_k0(const DevBatch& B, const DevParams& P, cudaStream_t st);
 void plan_k1(DevBatch& B, int variant, uint32_t rpc, uint32_t* tiles_out);
 void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc, cudaStream_t st);

@@ -1687,6 +1687,7 @@ __device__ __forceinline__ void k4b_indel(const DevBatch& B, const RawEv* src)
 __global__ void __launch_bounds__(256) k4b_place(DevBatch B, DevParams P)
 {
     griddep_wait();                                    // kernel 4a's line offsets
+    griddep_launch();
     CtaTrace tr(B, 6);
     const uint32_t room = B.raw_cap - B.prim_slots, n_ovf = min(B.ctrl->n_raw, room), n_sa = B.ctrl->n_sa;
     tr.mid();
@@ -1709,6 +1710,101 @@ __global__ void __launch_bounds__(256) k4b_place(DevBatch B, DevParams P)
         }
     }
     tr.end();
+}
+
+// ======================================================================================
+// kernels 5a / 5b: the output lines themselves (optional; EXLR_OPT_DEVICE_FORMAT)
+//
+// get_alignment_event_record / get_alignment_split_record without -v (utils.rs:225-236, 269-280):
+//   lchrom \t lstart \t lend \t lstrand \t rchrom \t rstart \t rend \t rstrand \t events_num \n
+// 5a: one thread per event computes the byte length of its line; a chained scan turns the lengths into byte offsets.
+// 5b: one thread per event writes its line at its offset -- the lines of consecutive events are consecutive in memory, so
+// the byte stores of a warp fall into the same few sectors and merge in L2.
+// With this the device-to-host copy carries the final bytes and the host formatter (the slowest host stage after BGZF
+// inflate) is not needed; -v lines carry the read name, which never travels to the device: those stay with the host.
+// ======================================================================================
+__device__ __forceinline__ uint32_t dec_len(int64_t v)
+{
+    unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    uint32_t n = v < 0 ? 2u : 1u;
+    while (u >= 10ull) { u /= 10ull; n++; }
+    return n;
+}
+
+__device__ __forceinline__ uint8_t* put_dec(uint8_t* p, int64_t v)
+{
+    unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    uint8_t tmp[20]; int n = 0;
+    do { tmp[n++] = (uint8_t)('0' + (uint32_t)(u % 10ull)); u /= 10ull; } while (u);
+    if (v < 0) *p++ = '-';
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+// name of a chrom reference (exlr.h): header name by tid, or the bytes of the SA string up to the next ','
+__device__ __forceinline__ const uint8_t* chrom_name(const DevBatch& B, uint32_t ref, uint32_t* len)
+{
+    if (ref >> 31) {
+        const uint8_t* p = B.sa_bytes + (ref & 0x7fffffffu);
+        uint32_t n = 0;
+        while (p[n] != ',') n++;
+        *len = n;
+        return p;
+    }
+    const uint32_t a = B.ref_off[ref];
+    *len = B.ref_off[ref + 1] - a;
+    return B.ref_bytes + a;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k5a_line_bytes(DevBatch B)
+{
+    __shared__ uint32_t s_tile, s_warp[16];
+    griddep_wait();                                    // kernel 4b's events
+    griddep_launch();
+    const uint32_t n = min(B.ctrl->n_events, B.max_events), n_tiles = (n + SCAN_THREADS - 1) / SCAN_THREADS;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&B.ctrl->ticket_c, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= n_tiles) break;
+        const uint32_t i = tile * SCAN_THREADS + threadIdx.x;
+        uint32_t len = 0;
+        if (i < n) {
+            const exlr_event e = B.events[i];
+            uint32_t a, b;
+            chrom_name(B, e.lchrom, &a); chrom_name(B, e.rchrom, &b);
+            len = a + b + dec_len(e.lstart) + dec_len(e.lend) + dec_len(e.rstart) + dec_len(e.rend)
+                  + (EXLR_EV_LSTRAND(e.meta) < 0 ? 2u : 1u) + (EXLR_EV_RSTRAND(e.meta) < 0 ? 2u : 1u)
+                  + dec_len((int64_t)EXLR_EV_NUM(e.meta)) + 9u;                 // 8 tabs and the newline
+        }
+        uint32_t grand;
+        const uint32_t at = tile_excl_scan(B.scan_c, tile, len, s_warp, &grand);
+        if (i < n) B.text_off[i] = at;
+        if (threadIdx.x == 0 && tile == n_tiles - 1) { B.text_off[n] = grand; B.ctrl->text_bytes = grand; }
+    }
+    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) { B.text_off[0] = 0; B.ctrl->text_bytes = 0; }
+}
+
+__global__ void __launch_bounds__(256) k5b_format(DevBatch B)
+{
+    griddep_wait();                                    // kernel 5a's offsets
+    const uint32_t n = min(B.ctrl->n_events, B.max_events), stride = gridDim.x * blockDim.x;
+    if (B.ctrl->text_bytes > B.text_cap) return;        // the host falls back to its own formatter
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const exlr_event e = B.events[i];
+        uint8_t* p = B.text + B.text_off[i];
+        uint32_t len;
+        const uint8_t* nm = chrom_name(B, e.lchrom, &len);
+        for (uint32_t k = 0; k < len; k++) *p++ = nm[k];
+        *p++ = '\t'; p = put_dec(p, e.lstart); *p++ = '\t'; p = put_dec(p, e.lend); *p++ = '\t';
+        p = put_dec(p, EXLR_EV_LSTRAND(e.meta)); *p++ = '\t';
+        nm = chrom_name(B, e.rchrom, &len);
+        for (uint32_t k = 0; k < len; k++) *p++ = nm[k];
+        *p++ = '\t'; p = put_dec(p, e.rstart); *p++ = '\t'; p = put_dec(p, e.rend); *p++ = '\t';
+        p = put_dec(p, EXLR_EV_RSTRAND(e.meta)); *p++ = '\t';
+        p = put_dec(p, (int64_t)EXLR_EV_NUM(e.meta)); *p++ = '\n';
+    }
 }
 
 // ======================================================================================
@@ -1863,5 +1959,15 @@ void launch_k4b(const DevBatch& B, const DevParams& P, cudaStream_t st)
 }
 
 uint32_t scan_tiles(uint32_t n_reads) { return (n_reads + SCAN_TILE - 1) / SCAN_TILE; }
+uint32_t text_scan_tiles(uint32_t max_events) { return (max_events + SCAN_THREADS - 1) / SCAN_THREADS + 1; }
+
+void launch_k5(const DevBatch& B, cudaStream_t st)
+{
+    // the line count lives on the device: both kernels are one resident wave (5a draws its tiles from a ticket)
+    const uint32_t ga = min((B.max_events + SCAN_THREADS - 1) / SCAN_THREADS, (uint32_t)g_sm_count * 8u);
+    launch_dependent(k5a_line_bytes, ga ? ga : 1u, SCAN_THREADS, 0, st, B);
+    const uint32_t gb = min((B.max_events + 255u) / 256u, (uint32_t)g_sm_count * 8u);
+    launch_dependent(k5b_format, gb ? gb : 1u, 256, 0, st, B);
+}
 
 }  // namespace exlr

@@ -1,7 +1,8 @@
 // exlr_main.cpp — `excord-lr-b200`: the reference CLI (reference src/main.rs:29-156) in front of libexlr_cuda.so.
 //
 //   reader thread : BGZF/BAM (-t inflate threads) -> packer -> exlr_submit, batches round-robin over the GPUs
-//   writer thread : exlr_wait in batch order -> exlr_format_lines -> output file (record order)
+//   writer thread : in batch order, exlr_wait_text (lines formatted on the device) or, with -v, exlr_wait + exlr_format_lines
+//                   -> output file (record order)
 //
 // Same flags, same startup messages/exit codes, same output bytes as the reference for BAM input.  There is no CPU
 // path: without a B200 the program exits with the library's error.
@@ -177,6 +178,9 @@ int main(int argc, char** argv)
     for (int g = 0; g < ndev; g++) {
         rc = exlr_create(&cli.p, g, names.data(), (int)names.size(), &ctx[g]);
         if (rc) { fprintf(stderr, "exlr_create(device %d): %s (%s)\n", g, exlr_strerror(rc), exlr_last_cuda_error()); return 3; }
+        // without -v the lines are formatted on the device (kernels 5a/5b) and the D2H copy carries the final bytes;
+        // -v lines carry the read name, which stays on the host: those are formatted here
+        exlr_set_option(ctx[g], EXLR_OPT_DEVICE_FORMAT, cli.verbose ? 0 : 1);
     }
     const unsigned long long R = cli.batch_reads;
     const unsigned long long OPS = cli.batch_ops ? cli.batch_ops : std::max<unsigned long long>(R * 64, 4ull << 20);
@@ -210,21 +214,30 @@ int main(int argc, char** argv)
             Slot& s = slots[si];
             exlr_result res;
             auto t0 = clk::now();
-            int st = exlr_wait(s.b, &res);
+            const char* dtext = nullptr; uint64_t dbytes = 0;
+            int st = cli.verbose ? exlr_wait(s.b, &res) : exlr_wait_text(s.b, &res, &dtext, &dbytes);
+            bool host_format = cli.verbose;
+            if (st == EXLR_ERR_TEXT_CAPACITY) { st = exlr_wait(s.b, &res); host_format = true; }   // unusually long lines: format here
             t_wait += secs(clk::now() - t0); n_batches++;
             if (st != 0 && st > -10) { fprintf(stderr, "exlr_wait: %s (%s)\n", exlr_strerror(st), exlr_last_cuda_error()); std::lock_guard<std::mutex> lk(mu); fatal = 3; cv.notify_all(); return; }
             uint64_t n_ev = res.n_events;
-            if (st <= -10) n_ev = res.line_off[res.err_read];            // the lines of the records before the failing one
-            const char* qn = cli.verbose ? s.pk.qnames.data() : nullptr;
-            static const char kEmpty = 0;
-            if (cli.verbose && !qn) qn = &kEmpty;
-            t0 = clk::now();
-            int64_t need = exlr_format_lines(ctx[s.gpu], s.b, &res, 0, n_ev, cli.verbose, qn, cli.verbose ? s.pk.qname_off.data() : nullptr, nullptr, 0);
-            if (need > 0) {
-                text.resize((size_t)need);
-                exlr_format_lines(ctx[s.gpu], s.b, &res, 0, n_ev, cli.verbose, qn, cli.verbose ? s.pk.qname_off.data() : nullptr, text.data(), (uint64_t)need);
-                t_format += secs(clk::now() - t0); t0 = clk::now();
-                fwrite(text.data(), 1, (size_t)need, fo);
+            if (host_format) {
+                if (st <= -10) n_ev = res.line_off[res.err_read];        // the lines of the records before the failing one
+                const char* qn = cli.verbose ? s.pk.qnames.data() : nullptr;
+                static const char kEmpty = 0;
+                if (cli.verbose && !qn) qn = &kEmpty;
+                t0 = clk::now();
+                int64_t need = exlr_format_lines(ctx[s.gpu], s.b, &res, 0, n_ev, cli.verbose, qn, cli.verbose ? s.pk.qname_off.data() : nullptr, nullptr, 0);
+                if (need > 0) {
+                    text.resize((size_t)need);
+                    exlr_format_lines(ctx[s.gpu], s.b, &res, 0, n_ev, cli.verbose, qn, cli.verbose ? s.pk.qname_off.data() : nullptr, text.data(), (uint64_t)need);
+                    t_format += secs(clk::now() - t0); t0 = clk::now();
+                    fwrite(text.data(), 1, (size_t)need, fo);
+                    t_write += secs(clk::now() - t0);
+                }
+            } else if (dbytes) {                                          // (on a failing record: already cut to the lines before it)
+                t0 = clk::now();
+                fwrite(dtext, 1, (size_t)dbytes, fo);
                 t_write += secs(clk::now() - t0);
             }
             n_lines += n_ev;

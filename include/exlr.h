@@ -39,6 +39,7 @@ extern "C" {
 #define EXLR_ERR_NOMEM         -3   /* host or device allocation failed                              */
 #define EXLR_ERR_CAPACITY      -4   /* batch larger than its allocation, or event buffer overflow    */
 #define EXLR_ERR_STATE         -5   /* call sequence error (wait without submit, ...)                */
+#define EXLR_ERR_TEXT_CAPACITY -6   /* exlr_wait_text: the lines need more than the batch's text buffer; format on the host */
 /* Per-record conditions on which the reference panics (exit 101).  exlr_result.err_read holds the
  * smallest offending record index of the batch; events of records < err_read are valid. */
 #define EXLR_ERR_TID          -10   /* kept record with tid<0 or tid>=n_ref (main.rs:198, contig() panics)      */
@@ -166,6 +167,8 @@ typedef struct exlr_batch exlr_batch;
 #define EXLR_OPT_TRACE 7          /* debug: kernel 1 records a per-CTA timeline, read back with exlr_get_trace */
 #define EXLR_OPT_STAGE_TIMING 6   /* 1 (default) = CUDA events between the kernels, so exlr_get_timing has per-stage times */
 #define EXLR_OPT_K1_WAVES 5       /* kernel 1 grid = SMs x CTAs/SM x waves (default 3) */
+#define EXLR_OPT_DEVICE_FORMAT 8  /* 1 = batches allocated from now on also format the non-verbose output lines on the device
+                                     (kernels 5a/5b, utils.rs:225-236, 269-280); read them with exlr_wait_text */
 
 /* ---- lifecycle ---------------------------------------------------------------------- */
 int  exlr_abi_version(void);
@@ -195,7 +198,12 @@ int  exlr_submit_resident(exlr_batch* b);
  * fills *res (pointers valid until the next submit/free of this batch).  Returns
  * res->status. */
 int  exlr_wait(exlr_batch* b, exlr_result* res);
-/* Like exlr_wait but leaves events on the device (only the 64-byte result header is read). */
+/* With EXLR_OPT_DEVICE_FORMAT: blocks until the batch is done and copies the formatted lines (no -v columns) to pinned host
+ * memory: *text / *n_bytes are exactly the bytes the reference writes for this batch (for a record the reference panics on:
+ * the lines of the records before it).  res->events / res->line_off are NOT fetched.  EXLR_ERR_TEXT_CAPACITY: the lines do
+ * not fit the text buffer (96 bytes per max_events entry); exlr_wait + exlr_format_lines still work for the batch. */
+int  exlr_wait_text(exlr_batch* b, exlr_result* res, const char** text, uint64_t* n_bytes);
+/* Like exlr_wait but leaves events on the device (only the result header is read). */
 int  exlr_wait_resident(exlr_batch* b, exlr_result* res);
 int  exlr_get_timing(exlr_batch* b, exlr_timing* t);
 /* debug (EXLR_OPT_TRACE): 4 x u64 per CTA of kernel 1 {globaltimer at start, at first data, at end, tiles | scanned tiles << 32} */

@@ -23,15 +23,15 @@ for r in D:
     if len(r) > vi:
         per.setdefault(r[ki].split("(")[0], []).append(float(r[vi].replace(",", "")) / 1000.0)
 with open(os.path.join(HERE, f"{tag}_launches_summary.txt"), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none, bench.py --steps 3 --warmup 3 --pipeline-parts 2\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none, bench.py --steps 3 --warmup 3\n")
     f.write("# cold-cache, serialised launches: compare SHARES, not absolutes.  Times in microseconds.\n")
-    f.write("# Launches with the larger time belong to the 1M-record resident steps, the smaller ones to the half-size e2e parts.\n")
+    f.write("# Launches with the larger time belong to the 1M-record resident steps, the smaller ones to the e2e sub-batches.\n")
     f.write(f"{'kernel':44s} {'n':>4s} {'min':>9s} {'median':>9s} {'max':>9s}\n")
     big = {}
     for k, v in per.items():
         s = sorted(v)
         f.write(f"{k:44s} {len(v):4d} {s[0]:9.1f} {s[len(s) // 2]:9.1f} {s[-1]:9.1f}\n")
-        if k.startswith("exlr::"):
+        if k.startswith("exlr::") or k.startswith("k") or k.startswith("void k"):
             big[k] = s[-1]
     tot = sum(big.values())
     f.write("\n# share of one 1M-record step (largest launch of each of our kernels)\n")
@@ -68,10 +68,17 @@ with open(os.path.join(HERE, f"{tag}_kernels.csv"), "w") as f:
             return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
         traffic[name] = {"dram_bytes_read": num("dram__bytes_read.sum"), "dram_bytes_write": num("dram__bytes_write.sum"),
                          "duration_us_under_ncu": float(r[H.index("gpu__time_duration.sum")].replace(",", ""))}
-k1 = traffic.get("k1_flat")
-if k1:
-    json.dump({"kernel": "k1_flat", "source": f"profiles/{tag}_kernels.csv (ncu --set full, one launch on the 1M-record batch)",
-               "dram_bytes_per_launch": k1["dram_bytes_read"] + k1["dram_bytes_write"], **k1},
-              open(os.path.join(HERE, "k1_traffic.json"), "w"), indent=1)
+# DRAM bytes per launch of every kernel: bench.py reads the roofline kernel's entry into roofline.traffic
+out = {}
+for name, t in traffic.items():
+    out[name.replace("void ", "").split("<")[0]] = {"source": f"profiles/{tag}_kernels.csv (ncu --set full, one launch on the 1M-record batch)",
+                                                     "dram_bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"], **t}
+path = os.path.join(HERE, "traffic.json")
+try:
+    old = json.load(open(path))
+except Exception:
+    old = {}
+old.update(out)
+json.dump(old, open(path, "w"), indent=1)
 print(open(os.path.join(HERE, f"{tag}_launches_summary.txt")).read())
 print(open(os.path.join(HERE, f"{tag}_kernels.csv")).read()[:3000])

@@ -54,9 +54,12 @@ def check_result(hb: HostBatch, p: ExlrParams, res, text: bytes, verbose=False, 
         raise AssertionError(f"{label} events differ at {d} (gpu n={len(got_ev)}, oracle n={len(want_ev)}):\n gpu   ={g}\n oracle={w}\n" + describe_read(hb, r))
     want_text = oracle_c.format_lines(hb, want_ev, verbose)
     assert text == want_text, f"{label} formatted text differs"
+    if getattr(res, "device_text", None) is not None:                  # kernels 5a/5b: the same bytes without the host formatter
+        want_plain = want_text if not verbose else oracle_c.format_lines(hb, want_ev, False)
+        assert res.device_text == want_plain, f"{label} device-formatted text differs"
     return want
 
 
 def gpu_check(hb: HostBatch, p: ExlrParams, cigar_kernel=0, reads_per_cta=0, verbose=False, label="", max_events=0):
-    res, text = api.extract(hb, p, 0, cigar_kernel, reads_per_cta, verbose, max_events)
+    res, text = api.extract(hb, p, 0, cigar_kernel, reads_per_cta, verbose, max_events, device_format=True)
     return check_result(hb, p, res, text, verbose, label), res
