@@ -2,21 +2,30 @@
 //
 //   kernel 0  k0_classify    record filter (main.rs:169-190) + tid check (:198) + ordered list of
 //                            kept records carrying an SA aux (:206), one chained scan
-//   kernel 1  k1_flat        CIGAR scan (main.rs:523-600): the batch's CIGAR stream is staged
-//                            through shared memory by TMA bulk copies (cp.async.bulk + mbarrier,
-//                            3-stage ring) and scanned flat — one block prefix sum of the
-//                            reference-consuming lengths, record boundaries resolved from the
+//   kernel 1a k1a_screen     streams the CIGAR array once at HBM speed and lists the 512-op steps that
+//                            hold an I/D >= indel_min (main.rs:553,569) or an unknown op code
+//   kernel 1b k1b_claim      listed steps -> records (one owner per record), short / long lists
+//             k1b_walk       one thread per short record: the CIGAR scan of main.rs:523-600 and the
+//                            merge predicates of :612-635, :673-678, all thread-local
+//   kernel 1c k1_flat(list)  the long records, one per tile, by the flat block scan below
+//   kernel 1  k1_flat        CIGAR scan of everything (event-dense batches, EXLR_OPT_CIGAR_KERNEL=2): the
+//                            CIGAR stream is staged through shared memory by TMA bulk copies
+//                            (cp.async.bulk + mbarrier, 5-stage ring) and scanned flat — one block prefix
+//                            sum of the reference-consuming lengths, record boundaries resolved from the
 //                            staged offsets — so load balance does not depend on CIGAR lengths.
 //             k1_warp        warp-per-record variant (kept for A/B measurement)
 //   kernel 3a k3a_sa_cigar   per-op-type sums + first-match offset of SA records' own CIGARs
-//                            (main.rs:214-306, utils.rs:12-42), 8-lane group per record
+//                            (main.rs:214-306, utils.rs:12-42), 2/4/8-lane group per record
 //   kernel 3b k3b_sa_events  SA parse (utils.rs:88-139), -k cap (main.rs:311), stable segment sort
 //                            (main.rs:322), large-INS rules (:340-486), split pairs (:488-516)
 //   kernel 4a k4a_line_scan  pair-merge rule (main.rs:612-635) + far-edge domain check (:673-678)
 //                            folded into the per-record line count, chained scan -> line offsets
 //   kernel 4b k4b_place      ordered compaction: every event lands at its reference output
 //                            position as a 48-byte exlr_event
+//   kernel 5a k5a_line_bytes byte length of every output line -> chained scan -> byte offsets  (optional)
+//   kernel 5b k5b_format     the lines themselves (utils.rs:225-236, 269-280)                  (optional)
 //
+// Consecutive kernels of a chain use programmatic dependent launch (griddep_wait / griddep_launch below).
 // HBM-bound integer/byte work: no tensor cores anywhere on this path.
 #include <cstdint>
 #include <cuda_runtime.h>
