@@ -185,7 +185,8 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
     case EXLR_OPT_READS_PER_CTA: if (value < 0 || value > 128) return EXLR_ERR_ARG; c->reads_per_cta = (uint32_t)value; return EXLR_OK;
     case EXLR_OPT_OVERLAP: c->overlap = value != 0; return EXLR_OK;
     case EXLR_OPT_DEVICE_FORMAT: c->device_format = value != 0; return EXLR_OK;
-    case EXLR_OPT_TRACE: if (value < 0 || value > 6) return EXLR_ERR_ARG; c->trace = (int)value; return EXLR_OK;
+    case EXLR_OPT_K1A_CTAS_PER_SM: if (value < 1 || value > 8) return EXLR_ERR_ARG; set_k1a_ctas_per_sm((int)value); return EXLR_OK;
+    case EXLR_OPT_TRACE: if (value < 0 || value > 7) return EXLR_ERR_ARG; c->trace = (int)value; return EXLR_OK;
     case EXLR_OPT_STAGE_TIMING: c->stage_timing = value != 0; return EXLR_OK;
     case EXLR_OPT_K1_WAVES: if (value < 1 || value > 16) return EXLR_ERR_ARG; set_k1_waves((int)value); return EXLR_OK;
     case EXLR_OPT_K1_CTAS_PER_SM: if (value < 0 || value > 4) return EXLR_ERR_ARG; c->k1_ctas = (int)value; return EXLR_OK;
@@ -337,6 +338,9 @@ static int copy_inputs(exlr_batch* b, uint64_t n)
     return EXLR_OK;
 }
 
+// batches whose mean CIGAR is longer than this run kernel 1c behind kernel 1b
+static constexpr uint64_t kLongRecordMeanOps = 512;
+
 static uint32_t auto_rpc(uint64_t n_reads, uint64_t n_ops)
 {
     // kernel 1 scans 2048 ops per step: aim just under two steps of CIGAR per CTA for short-read batches (full
@@ -385,8 +389,11 @@ static int run_kernels(exlr_batch* b)
         if (b->screened) {
             launch_k1a(d, c->dparams, b->n_ops, s1); b->launches++;
             if (c->stage_timing) CK(cudaEventRecord(b->ev_k1_mid, s1));
-            launch_k1b(d, c->dparams, b->n_ops, s1); b->launches += 2;
-            launch_k1c(d, c->dparams, s1); b->launches++;
+            // kernel 1c (flat block scan of the long records) is only launched for batches of long records; in a batch of short ones
+            // the odd long record is scanned by a warp of kernel 1b, and the chain is one launch shorter
+            const bool use_k1c = b->n_ops / b->n_reads > kLongRecordMeanOps;
+            launch_k1b(d, c->dparams, b->n_ops, use_k1c, s1); b->launches += 2;
+            if (use_k1c) { launch_k1c(d, c->dparams, s1); b->launches++; }
         } else {
             launch_k1(d, c->dparams, variant, rpc, s1); b->launches++;
         }
@@ -401,9 +408,9 @@ static int run_kernels(exlr_batch* b)
     launch_k4a(d, c->dparams, st); b->launches++;
     if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K4A], st));
     launch_k4b(d, c->dparams, st); b->launches++;
-    CK(cudaEventRecord(b->ev[EV_K4B], st));
     b->formatted = d.text_off != nullptr;
-    if (b->formatted) { launch_k5(d, st); b->launches += 2; }
+    if (b->formatted) { launch_k5(d, st); b->launches += 2; }      // (no event in between: 5a is placed while 4b drains)
+    CK(cudaEventRecord(b->ev[EV_K4B], st));
     CK(cudaMemcpyAsync(b->h_ctrl, d.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(b->ev[EV_D2H], st));
     CK(cudaGetLastError());

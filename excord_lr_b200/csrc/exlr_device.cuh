@@ -127,6 +127,7 @@ struct DevParams {
 cudaError_t configure_kernels(int device);
 void set_k1_ctas_per_sm(int n);
 void set_k1_waves(int n);
+void set_k1a_ctas_per_sm(int n);
 size_t k1_flat_smem_bytes();
 uint32_t scan_tiles(uint32_t n_reads);
 uint32_t text_scan_tiles(uint32_t max_events);
@@ -136,7 +137,7 @@ void plan_k1(DevBatch& B, int variant, uint32_t rpc, uint32_t* tiles_out);
 void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc, cudaStream_t st);
 uint32_t k1a_steps(unsigned long long n_ops);
 void launch_k1a(const DevBatch& B, const DevParams& P, unsigned long long n_ops, cudaStream_t st);
-void launch_k1b(const DevBatch& B, const DevParams& P, unsigned long long n_ops, cudaStream_t st);
+void launch_k1b(const DevBatch& B, const DevParams& P, unsigned long long n_ops, bool use_k1c, cudaStream_t st);
 void launch_k1c(const DevBatch& B, const DevParams& P, cudaStream_t st);
 void launch_k3a(const DevBatch& B, const DevParams& P, uint32_t mean_ops, cudaStream_t st);
 void launch_k3b(const DevBatch& B, const DevParams& P, cudaStream_t st);

@@ -72,12 +72,27 @@ __device__ __forceinline__ void store_event(exlr_event* dst, int64_t ls, int64_t
     d[2] = make_uint4(read, lc, rc, meta);
 }
 
-// EXLR_OPT_TRACE for the small kernels: {CTA start, a mid point, CTA end} by thread 0, entry blockIdx.x (mod 8192)
+// EXLR_OPT_TRACE for the small kernels: {CTA start, a mid point, CTA end} by thread 0, entry blockIdx.x (mod 8192).
+// EXLR_OPT_TRACE = 7 is the timeline mode: every kernel folds its CTAs' start / end into entry `id` with atomicMin / atomicMax
+// ({~first CTA start, last CTA end, -, CTAs}; the buffer is zeroed per submit), which shows the gaps and overlaps of a whole step
+// (tools/timeline.py).
 struct CtaTrace {
-    unsigned long long* d; unsigned long long t0, t1;
-    __device__ __forceinline__ CtaTrace(const DevBatch& B, uint32_t sel) : d(B.dbg && B.dbg_sel == sel ? B.dbg + 4ull * (blockIdx.x & 8191u) : nullptr), t0(0), t1(0) { if (d) t0 = gtimer(); }
+    unsigned long long* d; unsigned long long t0, t1; bool tl;
+    __device__ __forceinline__ CtaTrace(const DevBatch& B, uint32_t sel) : d(nullptr), t0(0), t1(0), tl(false)
+    {
+        if (!B.dbg) return;
+        if (B.dbg_sel == 7u) { d = B.dbg + 4ull * sel; tl = true; }
+        else if (B.dbg_sel == sel) d = B.dbg + 4ull * (blockIdx.x & 8191u);
+        if (d) t0 = gtimer();
+    }
     __device__ __forceinline__ void mid() { if (d && !t1) t1 = gtimer(); }
-    __device__ __forceinline__ void end() { if (d && threadIdx.x == 0) { d[0] = t0; d[1] = t1; d[2] = gtimer(); d[3] = 0; } }
+    __device__ __forceinline__ void end()
+    {
+        if (!d || threadIdx.x != 0) return;
+        const unsigned long long t2 = gtimer();
+        if (tl) { atomicMax(d, ~t0); atomicMax(d + 1, t2); atomicAdd(d + 3, 1ull); }
+        else { d[0] = t0; d[1] = t1; d[2] = t2; d[3] = 0; }
+    }
 };
 
 // ---- chained scan (decoupled look-back), one status word per tile: flag<<62 | value ----
@@ -494,6 +509,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
     // every one of them holds an event candidate, so nothing is screened
     if (list) { griddep_wait(); n_tiles = B.ctrl->n_long; }
     if (blockIdx.x >= n_tiles) return;
+    CtaTrace tr(B, 11);
     const bool trace = B.dbg && B.dbg_sel == 1u && !list;
     const unsigned long long tr_start = trace ? gtimer() : 0ull; unsigned long long tr_first = 0; uint32_t tr_scanned = 0;
     const uint32_t ntile = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;         // <= K1_MAX_TILES (host)
@@ -693,6 +709,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
         unsigned long long* d = B.dbg + 4ull * blockIdx.x;
         d[0] = tr_start; d[1] = tr_first; d[2] = gtimer(); d[3] = (unsigned long long)ntile | ((unsigned long long)tr_scanned << 32);
     }
+    tr.end();
     // the slab still held in reserve was never used: blank it
     const uint32_t last = __shfl_sync(0xffffffffu, spare, 0);
     __shared__ uint32_t s_last;
@@ -740,6 +757,7 @@ __global__ void __launch_bounds__(K1A_THREADS, K1A_CTAS) k1a_screen(DevBatch B, 
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t nthreads = gridDim.x * K1A_THREADS, gt = blockIdx.x * K1A_THREADS + threadIdx.x;
     griddep_launch();                                  // kernel 1b may be placed; it waits for this grid before it reads anything
+    CtaTrace tr(B, 8);
     {
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);      // the array is padded to 256 bytes, so whole 16-byte stores are fine
         uint4* k1 = reinterpret_cast<uint4*>(B.k1);
@@ -779,6 +797,7 @@ __global__ void __launch_bounds__(K1A_THREADS, K1A_CTAS) k1a_screen(DevBatch B, 
         if ((it & 31u) == 31u) { append(hitmask, it - 31u); hitmask = 0; }
     }
     append(hitmask, it & ~31u);
+    tr.end();
 }
 
 // largest r in [0, n_reads) with cigar_off[r] <= fp, for fp < cigar_off[n_reads]: a 33-ary search done by the whole warp
@@ -826,11 +845,12 @@ static constexpr uint32_t K1B_LONG = 256;              // ops; longer records go
 static constexpr uint32_t K1B_EV = 4;                  // events per record parked in shared memory during the walk
 static constexpr int K1B_VEC = 4;                      // 128-bit loads in flight per walking thread
 
-__global__ void __launch_bounds__(K1B_THREADS) k1b_claim(DevBatch B, DevParams P, unsigned long long n_ops)
+__global__ void __launch_bounds__(K1B_THREADS) k1b_claim(DevBatch B, DevParams P, unsigned long long n_ops, uint32_t use_k1c)
 {
     const uint32_t t = threadIdx.x, lane = t & 31;
     griddep_wait();                                    // kernel 1a's step list and zeroed summaries
     griddep_launch();
+    CtaTrace tr(B, 9);
     const uint32_t n_list = B.ctrl->n_flagged, nw = (gridDim.x * K1B_THREADS) >> 5;
     for (uint32_t li = (blockIdx.x * K1B_THREADS + t) >> 5; li < n_list; li += nw) {
         const bool trace = B.dbg && B.dbg_sel == 1u;
@@ -859,14 +879,16 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_claim(DevBatch B, DevParams P
                 const uint32_t p = sh + lane;
                 if ((p < 32u ? old_lo >> p : old_hi >> (p - 32u)) & 1u) mine = false;
             }
-            const bool is_long = mine && o1 - o0 > K1B_LONG;
+            // long records: kernel 1c's list, or (batches of short records, where kernel 1c is not launched) the short list with bit 31
+            // set: k1b_walk then scans them with a whole warp
+            const bool is_big = mine && o1 - o0 > K1B_LONG, is_long = is_big && use_k1c;
             const uint32_t sm = __ballot_sync(0xffffffffu, mine && !is_long), lm = __ballot_sync(0xffffffffu, is_long);
             uint32_t sbase = 0, lbase = 0;
             if (lane == 0 && sm) sbase = atomicAdd(&B.ctrl->n_short, (uint32_t)__popc(sm));
             if (lane == 1 && lm) lbase = atomicAdd(&B.ctrl->n_long, (uint32_t)__popc(lm));
             sbase = __shfl_sync(0xffffffffu, sbase, 0); lbase = __shfl_sync(0xffffffffu, lbase, 1);
             const uint32_t below = (1u << lane) - 1u;
-            if (mine && !is_long) B.short_list[sbase + __popc(sm & below)] = r;
+            if (mine && !is_long) B.short_list[sbase + __popc(sm & below)] = r | (is_big ? 0x80000000u : 0u);
             if (is_long) B.long_list[lbase + __popc(lm & below)] = r;
             // the next 32 records matter only if the last one of these still ends inside the step
             if (!__shfl_sync(0xffffffffu, (uint32_t)(overlaps && o1 < hi_op), 31)) break;
@@ -876,14 +898,16 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_claim(DevBatch B, DevParams P
             d[0] = tr0; d[1] = tr1; d[2] = gtimer(); d[3] = 0;
         }
     }
+    tr.end();
 }
 
-__global__ void __launch_bounds__(K1B_THREADS) k1b_walk(DevBatch B, DevParams P)
+__global__ void __launch_bounds__(K1B_THREADS) k1b_walk(DevBatch B, DevParams P, uint32_t use_k1c)
 {
     __shared__ uint2 s_ev[K1B_THREADS][K1B_EV + 1];    // {left_consume, op word}; the extra slot tells "more than K1B_EV"
     const uint32_t t = threadIdx.x, lane = t & 31;
     griddep_wait();                                    // k1b_claim's lists
     griddep_launch();
+    CtaTrace tr(B, 10);
     const uint32_t n_list = B.ctrl->n_short, stride = gridDim.x * K1B_THREADS;
     const uint32_t imin16 = P.indel_min >= (1u << 28) ? 0xffffffffu : (P.indel_min << 4);
     const uint4* cig4 = reinterpret_cast<const uint4*>(B.cigar);
@@ -893,8 +917,9 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_walk(DevBatch B, DevParams P)
         const bool have = i < n_list;
         uint32_t r = 0, pos2 = 0, nv = 0, head = 0, nops = 0;
         const uint4* c4 = cig4;
-        if (have) {
-            r = B.short_list[i];
+        bool is_long = false;                                                  // not for one thread: too long, or too many events
+        if (have) { r = B.short_list[i]; is_long = r >> 31; r &= 0x7fffffffu; }
+        if (have && !is_long) {
             const unsigned long long o0 = B.cigar_off[r], o1 = B.cigar_off[r + 1], a0 = o0 & ~3ull;
             pos2 = (uint32_t)B.pos[r];
             nv = (uint32_t)((((o1 + 3ull) & ~3ull) - a0) >> 2);                // aligned vectors spanned (<= 65)
@@ -929,10 +954,9 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_walk(DevBatch B, DevParams P)
             }
         }
         const uint32_t cnt = (evp - ev0) >> 3;
-        bool is_long = false;
-        if (have) {
+        if (have && !is_long) {
             if (flags & 0x40u) report(B.ctrl, r, RANK_CIGAR_OP);                                    // rust-htslib panics on an unknown op
-            if (cnt > K1B_EV) is_long = true;                                                       // more events than parking space: kernel 1c does it
+            if (cnt > K1B_EV) is_long = true;                                                       // more events than parking space
             else {
                 uint32_t info = 0;
                 for (uint32_t j = 1; j < cnt; j++) {
@@ -962,14 +986,17 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_walk(DevBatch B, DevParams P)
                 d[1] = make_uint4(j ? s_ev[t][j - 1].x : 0u, 0u, 0u, 0u);
             } else B.ctrl->overflow = 1;
         }
-        const uint32_t lm = __ballot_sync(0xffffffffu, is_long);
-        if (lm) {
+        uint32_t lm = __ballot_sync(0xffffffffu, is_long);
+        if (lm && use_k1c) {                                                   // on to kernel 1c's list
             uint32_t lbase = 0;
             if (lane == 0) lbase = atomicAdd(&B.ctrl->n_long, (uint32_t)__popc(lm));
             lbase = __shfl_sync(0xffffffffu, lbase, 0);
             if (is_long) B.long_list[lbase + __popc(lm & ((1u << lane) - 1u))] = r;
+        } else {
+            for (; lm; lm &= lm - 1u) k1_warp_record(B, P, __shfl_sync(0xffffffffu, r, __ffs((int)lm) - 1));   // the whole warp scans it
         }
     }
+    tr.end();
 }
 
 // ======================================================================================
@@ -1770,6 +1797,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k5a_line_bytes(DevBatch B)
     __shared__ uint32_t s_tile, s_warp[16];
     griddep_wait();                                    // kernel 4b's events
     griddep_launch();
+    CtaTrace tr(B, 12);
     const uint32_t n = min(B.ctrl->n_events, B.max_events), n_tiles = (n + SCAN_THREADS - 1) / SCAN_THREADS;
     for (;;) {
         __syncthreads();
@@ -1793,27 +1821,67 @@ __global__ void __launch_bounds__(SCAN_THREADS) k5a_line_bytes(DevBatch B)
         if (threadIdx.x == 0 && tile == n_tiles - 1) { B.text_off[n] = grand; B.ctrl->text_bytes = grand; }
     }
     if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) { B.text_off[0] = 0; B.ctrl->text_bytes = 0; }
+    tr.end();
 }
+
+// one line into p (any address space); returns the end
+__device__ __forceinline__ uint8_t* k5_put_line(const DevBatch& B, const exlr_event& e, uint8_t* p)
+{
+    uint32_t len;
+    const uint8_t* nm = chrom_name(B, e.lchrom, &len);
+    for (uint32_t k = 0; k < len; k++) *p++ = nm[k];
+    *p++ = '\t'; p = put_dec(p, e.lstart); *p++ = '\t'; p = put_dec(p, e.lend); *p++ = '\t';
+    p = put_dec(p, EXLR_EV_LSTRAND(e.meta)); *p++ = '\t';
+    nm = chrom_name(B, e.rchrom, &len);
+    for (uint32_t k = 0; k < len; k++) *p++ = nm[k];
+    *p++ = '\t'; p = put_dec(p, e.rstart); *p++ = '\t'; p = put_dec(p, e.rend); *p++ = '\t';
+    p = put_dec(p, EXLR_EV_RSTRAND(e.meta)); *p++ = '\t';
+    p = put_dec(p, (int64_t)EXLR_EV_NUM(e.meta)); *p++ = '\n';
+    return p;
+}
+
+// A warp takes 32 consecutive events: their lines are one contiguous byte range of the output (~1.6 KB).  Every lane formats
+// its line into the warp's shared-memory stage at the line's offset inside that range; the stage is laid out with the same
+// alignment (mod 16) as the destination, so the warp then writes the range out with coalesced 128-bit stores (bytes only at
+// the two ragged ends).  Measured: one thread writing its line straight to global memory, byte by byte, took 92 us for 268k lines.
+static constexpr uint32_t K5B_STAGE = 4096;             // bytes of stage per warp (a range that does not fit goes out byte-wise)
 
 __global__ void __launch_bounds__(256) k5b_format(DevBatch B)
 {
+    __shared__ __align__(16) uint8_t s_stage[8][K5B_STAGE];
     griddep_wait();                                    // kernel 5a's offsets
-    const uint32_t n = min(B.ctrl->n_events, B.max_events), stride = gridDim.x * blockDim.x;
+    CtaTrace tr(B, 13);
+    const uint32_t n = min(B.ctrl->n_events, B.max_events), lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
     if (B.ctrl->text_bytes > B.text_cap) return;        // the host falls back to its own formatter
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const exlr_event e = B.events[i];
-        uint8_t* p = B.text + B.text_off[i];
-        uint32_t len;
-        const uint8_t* nm = chrom_name(B, e.lchrom, &len);
-        for (uint32_t k = 0; k < len; k++) *p++ = nm[k];
-        *p++ = '\t'; p = put_dec(p, e.lstart); *p++ = '\t'; p = put_dec(p, e.lend); *p++ = '\t';
-        p = put_dec(p, EXLR_EV_LSTRAND(e.meta)); *p++ = '\t';
-        nm = chrom_name(B, e.rchrom, &len);
-        for (uint32_t k = 0; k < len; k++) *p++ = nm[k];
-        *p++ = '\t'; p = put_dec(p, e.rstart); *p++ = '\t'; p = put_dec(p, e.rend); *p++ = '\t';
-        p = put_dec(p, EXLR_EV_RSTRAND(e.meta)); *p++ = '\t';
-        p = put_dec(p, (int64_t)EXLR_EV_NUM(e.meta)); *p++ = '\n';
+    for (uint32_t i0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; i0 < n; i0 += nw * 32u) {
+        const uint32_t i = i0 + lane, i1 = min(i0 + 32u, n);
+        const uint32_t lo = B.text_off[i0], hi = B.text_off[i1];          // the warp's byte range
+        const uint32_t skew = lo & 15u;
+        const bool have = i < n;
+        exlr_event e;
+        uint32_t off = 0;
+        if (have) { e = B.events[i]; off = B.text_off[i]; }
+        if (hi - lo + skew <= K5B_STAGE) {
+            uint8_t* st = s_stage[w];
+            if (have) k5_put_line(B, e, st + skew + (off - lo));
+            __syncwarp();
+            uint8_t* dst = B.text + (lo - skew);                           // 16-byte aligned; stage byte k <-> dst byte k
+            const uint32_t end = skew + (hi - lo);
+            const uint32_t v0 = skew ? 16u : 0u, v1 = end & ~15u;           // [v0, v1) is whole vectors
+            if (v1 > v0) {
+                for (uint32_t k = v0 + lane * 16u; k < v1; k += 512u) *reinterpret_cast<uint4*>(dst + k) = *reinterpret_cast<const uint4*>(st + k);
+                if (skew) { const uint32_t k = skew + lane; if (k < 16u) dst[k] = st[k]; }
+                { const uint32_t k = v1 + lane; if (k < end) dst[k] = st[k]; }
+            } else {
+                for (uint32_t k = skew + lane; k < end; k += 32u) dst[k] = st[k];
+            }
+            __syncwarp();                                                  // the stage is reused by the next range
+        } else if (have) {
+            k5_put_line(B, e, B.text + off);
+        }
     }
+    tr.end();
 }
 
 // ======================================================================================
@@ -1821,6 +1889,8 @@ __global__ void __launch_bounds__(256) k5b_format(DevBatch B)
 // ======================================================================================
 static int g_sm_count = 148;
 static int g_k1_ctas_per_sm = 4;
+static int g_k1a_ctas_per_sm = 8;          // resident CTAs of the screen kernel per SM (fewer leave room for the SA branch beside it)
+void set_k1a_ctas_per_sm(int n) { g_k1a_ctas_per_sm = n < 1 ? 1 : (n > 8 ? 8 : n); }
 static int g_k1_waves = 3;                 // grid = SMs x CTAs/SM x waves: > 1 trades prefetch depth for dynamic balance
 void set_k1_waves(int n) { g_k1_waves = n < 1 ? 1 : (n > 16 ? 16 : n); }
 void set_k1_ctas_per_sm(int n) { g_k1_ctas_per_sm = n < 1 ? 1 : (n > 4 ? 4 : n); }
@@ -1909,20 +1979,20 @@ void launch_k1a(const DevBatch& B, const DevParams& P, unsigned long long n_ops,
 {
     const uint32_t steps = k1a_steps(n_ops);
     uint32_t grid = (steps + K1A_THREADS / 32 - 1) / (K1A_THREADS / 32);
-    const uint32_t cap = (uint32_t)g_sm_count * K1A_CTAS;
+    const uint32_t cap = (uint32_t)g_sm_count * (uint32_t)g_k1a_ctas_per_sm;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     k1a_screen<<<grid, K1A_THREADS, 0, st>>>(B, P, n_ops);
 }
 
-void launch_k1b(const DevBatch& B, const DevParams& P, unsigned long long n_ops, cudaStream_t st)
+void launch_k1b(const DevBatch& B, const DevParams& P, unsigned long long n_ops, bool use_k1c, cudaStream_t st)
 {
     // the numbers of flagged steps and of claimed records live on the device: one resident wave strides over each list
     const uint32_t steps = k1a_steps(n_ops);
     const uint32_t g1 = min((steps + K1B_THREADS / 32 - 1) / (K1B_THREADS / 32), (uint32_t)g_sm_count * 8u);
-    launch_dependent(k1b_claim, g1 ? g1 : 1u, K1B_THREADS, 0, st, B, P, n_ops);
+    launch_dependent(k1b_claim, g1 ? g1 : 1u, K1B_THREADS, 0, st, B, P, n_ops, use_k1c ? 1u : 0u);
     const uint32_t g2 = min((B.n_reads + K1B_THREADS - 1) / K1B_THREADS, (uint32_t)g_sm_count * 8u);
-    launch_dependent(k1b_walk, g2 ? g2 : 1u, K1B_THREADS, 0, st, B, P);
+    launch_dependent(k1b_walk, g2 ? g2 : 1u, K1B_THREADS, 0, st, B, P, use_k1c ? 1u : 0u);
 }
 
 void launch_k3a(const DevBatch& B, const DevParams& P, uint32_t mean_ops, cudaStream_t st)

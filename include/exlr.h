@@ -164,9 +164,11 @@ typedef struct exlr_batch exlr_batch;
 #define EXLR_OPT_READS_PER_CTA 2 /* 0 = auto */
 #define EXLR_OPT_OVERLAP 3       /* 1 (default) = kernel 1 runs on a second stream beside kernels 0/3a/3b */
 #define EXLR_OPT_K1_CTAS_PER_SM 4 /* 1..4 CTAs of kernel 1 per SM; 0 (default) = 3 when overlapping, else 4 */
-#define EXLR_OPT_TRACE 7          /* debug: kernel 1 records a per-CTA timeline, read back with exlr_get_trace */
+#define EXLR_OPT_TRACE 7          /* debug: %globaltimer traces, read back with exlr_get_trace.  1 = kernel 1 / 1b per CTA / step, 2..6 = k0, k3a,
+                                     k3b, k4a, k4b per CTA {start, mid, end}, 7 = timeline: entry k = {~first start, last end, -, CTAs} of kernel k */
 #define EXLR_OPT_STAGE_TIMING 6   /* 1 (default) = CUDA events between the kernels, so exlr_get_timing has per-stage times */
 #define EXLR_OPT_K1_WAVES 5       /* kernel 1 grid = SMs x CTAs/SM x waves (default 3) */
+#define EXLR_OPT_K1A_CTAS_PER_SM 9 /* resident CTAs of kernel 1a per SM, 1..8 (default 8) */
 #define EXLR_OPT_DEVICE_FORMAT 8  /* 1 = batches allocated from now on also format the non-verbose output lines on the device
                                      (kernels 5a/5b, utils.rs:225-236, 269-280); read them with exlr_wait_text */
 
