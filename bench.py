@@ -334,7 +334,7 @@ def main():
         path_s = float(np.mean(k1_ms)) / 1e3 if k1_ms else float("nan")
         if screened:
             rk_name = "k1a_screen"
-            k1_bytes = 4.0 * Cops + 8.0 * R                               # every op read once + an 8-byte summary written per record
+            k1_bytes = 4.0 * Cops                                         # every op read once (the list of flagged steps is a few KB)
             k1_avg_s = float(np.mean(k1a_ms)) / 1e3
         else:
             rk_name = "k1_flat" if args.cigar_kernel != 1 else "k1_warp"

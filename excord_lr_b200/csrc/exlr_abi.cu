@@ -360,7 +360,7 @@ static int run_kernels(exlr_batch* b)
     if (c->trace) CK(cudaMemsetAsync(b->d_dbg, 0, 8192 * 32, st));
     CK(cudaMemsetAsync(d.ctrl, 0, b->ctrl_bytes, st));
     // kernel 1 needs nothing from kernel 0, so it runs on a second stream beside the SA branch (0 -> 3a -> 3b); 4a joins them
-    d.prim_slots = 0; d.capt_log2 = 0;
+    d.prim_slots = 0; d.capt_log2 = 0; d.k1_gated = 0;
     const bool overlap = c->overlap && !c->params.split_only;
     set_k1_ctas_per_sm(c->k1_ctas ? c->k1_ctas : (overlap ? 3 : 4));
     uint32_t rpc = 0;
@@ -377,6 +377,7 @@ static int run_kernels(exlr_batch* b)
         if (c->cigar_kernel == 0) { if (c->skip_screen > 0) c->skip_screen--; else want = true; }
         b->screened = want && b->n_ops < (1ull << 33) && b->n_ops > 0;
         uint32_t n_tiles = 0;
+        d.k1_gated = b->screened ? 1u : 0u;
         plan_k1(d, b->screened ? 1 : variant, rpc, &n_tiles);               // screened: raw events all go to the atomically allocated region
         if (overlap) CK(cudaEventRecord(b->ev_fork, st));                  // after the memset
     }

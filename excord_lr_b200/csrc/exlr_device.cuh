@@ -88,7 +88,8 @@ struct DevBatch {
     // reference names, "chr" stripped: name i = ref_bytes[ref_off[i] .. ref_off[i+1])
     const uint8_t* ref_bytes; const uint32_t* ref_off; int32_t n_ref;
     // scratch
-    uint2* k1;              // [R] {total_consume, info}
+    uint2* k1;              // [R] {total_consume, info}; with k1_gated only the entries of claimed records (dirty_bits) are valid
+    uint32_t k1_gated;      // 1 = screened CIGAR path
     uint32_t* csa;          // [R] SA-derived line count | CSA_DROP
     uint32_t* sa_list;      // [R] ordered indices of kept records with an SA aux
     uint32_t* sa_base;      // [R] first temp slot of the SA record's events (indexed like sa_list)

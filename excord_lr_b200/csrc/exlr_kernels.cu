@@ -726,7 +726,8 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_flat(DevBatch B, DevParams P
 // have such an event (kernel 4b).  So the whole CIGAR stream is first streamed once at full width -- plain coalesced 128-bit
 // loads, four per thread in flight, four instructions per op (table look-up, OR, compare, predicated OR), no record
 // structure at all -- and all it leaves behind is the list of 512-op steps with an event candidate or an unknown op code in
-// them.  Kernel 1b resolves the listed steps to records.  Every record's summary starts out as "no event" here.
+// them.  Kernel 1b resolves the listed steps to records.  It writes nothing per record: a record has an indel summary only
+// if kernel 1b claims it (k4a reads the claim bitmap first).
 // (Measured: resolving candidates to records inside this kernel -- a 4-level search per flagged step -- cost 12 of 39 us.)
 // ======================================================================================
 static constexpr int K1A_THREADS = 256;
@@ -758,11 +759,6 @@ __global__ void __launch_bounds__(K1A_THREADS, K1A_CTAS) k1a_screen(DevBatch B, 
     const uint32_t nthreads = gridDim.x * K1A_THREADS, gt = blockIdx.x * K1A_THREADS + threadIdx.x;
     griddep_launch();                                  // kernel 1b may be placed; it waits for this grid before it reads anything
     CtaTrace tr(B, 8);
-    {
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);      // the array is padded to 256 bytes, so whole 16-byte stores are fine
-        uint4* k1 = reinterpret_cast<uint4*>(B.k1);
-        for (uint32_t i = gt, n = (B.n_reads + 1u) / 2u; i < n; i += nthreads) k1[i] = z;
-    }
     const uint32_t imin16 = P.indel_min >= (1u << 28) ? 0xffffffffu : (P.indel_min << 4);
     const uint32_t nvec = (uint32_t)((n_ops + 3ull) / 4ull);               // < 2^30 (host); the cigar buffer is padded by 16 bytes
     const uint4* cig = reinterpret_cast<const uint4*>(B.cigar);
@@ -1647,7 +1643,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) k4a_line_scan(DevBatch B, DevPar
     const uint32_t r0 = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint32_t c[SCAN_ITEMS], mine = 0;
     const bool full = r0 + SCAN_ITEMS <= n;
-    if (full) {
+    if (full && B.k1_gated) {
+        // screened CIGAR path: a record has an indel summary only if kernel 1b claimed it (its bit in the claim bitmap);
+        // everything else is "no event" without ever having been written -- 16 records share one 16-bit slice of the bitmap
+        union { uint4 v[4]; uint32_t u[16]; } cs;
+#pragma unroll
+        for (int k = 0; k < 4; k++) cs.v[k] = reinterpret_cast<const uint4*>(B.csa + r0)[k];
+        const uint32_t bits = (B.dirty_bits[r0 >> 5] >> (r0 & 31u)) & 0xffffu;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            const uint32_t info = (bits >> i) & 1u ? B.k1[r0 + i].y : 0u;
+            c[i] = record_lines(B, r0 + i, cs.u[i], info); mine += c[i];
+        }
+    } else if (full) {
         union { uint4 v[4]; uint32_t u[16]; } cs;
         union { uint4 v[8]; uint2 p[16]; } k1;
 #pragma unroll
@@ -1660,7 +1668,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k4a_line_scan(DevBatch B, DevPar
 #pragma unroll
         for (int i = 0; i < SCAN_ITEMS; i++) {
             const uint32_t r = r0 + i;
-            c[i] = r < n ? record_lines(B, r, B.csa[r], B.k1[r].y) : 0u;
+            uint32_t info = 0;
+            if (r < n && (!B.k1_gated || ((B.dirty_bits[r >> 5] >> (r & 31u)) & 1u))) info = B.k1[r].y;
+            c[i] = r < n ? record_lines(B, r, B.csa[r], info) : 0u;
             mine += c[i];
         }
     }
