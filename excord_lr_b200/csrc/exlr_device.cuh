@@ -124,7 +124,7 @@ struct DevParams {
     unsigned long long max_supp_alignm;
 };
 
-// launchers (exlr_kernels.cu)
+// launchers (exlr_cigar.cu, exlr_sa.cu, exlr_order.cu)
 cudaError_t configure_kernels(int device);
 void set_k1_ctas_per_sm(int n);
 void set_k1_waves(int n);

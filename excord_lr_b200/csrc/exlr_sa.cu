@@ -1,0 +1,663 @@
+// exlr_sa.cu — the SA arm (reference src/main.rs:206-519, src/utils.rs, src/split_read_event.rs):
+//
+//   kernel 3a k3a_sa_cigar   per-op-type sums + first-match offset of SA records' own CIGARs
+//                            (main.rs:214-306, utils.rs:12-42), 2/4/8-lane group per record
+//   kernel 3b k3b_sa_events  SA parse (utils.rs:88-139), -k cap (main.rs:311), stable segment sort
+//                            (main.rs:322), large-INS rules (:340-486), split pairs (:488-516)
+#include "exlr_common.cuh"
+
+namespace exlr {
+
+// ======================================================================================
+// kernel 3a: SA records' own CIGAR -> clip sums, reference span, first-match offset
+// ======================================================================================
+// One record's CIGAR walked by a group of G lanes (G = 8: a quarter warp per short record; G = 32: the whole warp for a
+// long one).  Returns the reduced sums in every lane of the group.
+struct K3aAcc { uint32_t S, H, D, M, E, X; unsigned long long ffm; };
+
+template <int G>
+__device__ __forceinline__ K3aAcc k3a_walk(const DevBatch& B, uint32_t r, unsigned long long o0, unsigned long long o1, uint32_t gmask, uint32_t gshift)
+{
+    const uint32_t sub = threadIdx.x & (G - 1);
+    K3aAcc a{0, 0, 0, 0, 0, 0, 0};
+    bool seenM = false;
+    constexpr int U = G == 32 ? 8 : (G == 8 ? 4 : 8);                          // independent loads in flight per lane
+    for (unsigned long long b = o0; b < o1; b += (unsigned long long)G * U) {
+        uint32_t vv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const unsigned long long at = b + (unsigned long long)u * G + sub;
+            vv[u] = at < o1 ? __ldg(B.cigar + at) : 0xfu;                     // 0xf: not an op
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool valid = b + (unsigned long long)u * G + sub < o1;
+            const uint32_t v = vv[u];
+            const uint32_t op = v & 15u, len = v >> 4;
+            if (valid && op > 8u) report(B.ctrl, r, RANK_CIGAR_OP);
+            a.M += op == 0u ? len : 0u; a.D += op == 2u ? len : 0u; a.S += op == 4u ? len : 0u;
+            a.H += op == 5u ? len : 0u; a.E += op == 7u ? len : 0u; a.X += op == 8u ? len : 0u;
+            if (!seenM) {                                                      // utils.rs:28-29 stops at the first M
+                const uint32_t mb = (__ballot_sync(gmask, valid && op == 0u) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+                const bool before = (mb & ((2u << sub) - 1u)) == 0u;          // no M at or before my lane
+                if (valid && before && (op == 4u || op == 1u || op == 8u || op == 7u)) a.ffm += len;   // S I X =  (utils.rs:33)
+                if (mb) seenM = true;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+        a.S += __shfl_xor_sync(gmask, a.S, d); a.H += __shfl_xor_sync(gmask, a.H, d); a.D += __shfl_xor_sync(gmask, a.D, d);
+        a.M += __shfl_xor_sync(gmask, a.M, d); a.E += __shfl_xor_sync(gmask, a.E, d); a.X += __shfl_xor_sync(gmask, a.X, d);
+        a.ffm += __shfl_xor_sync(gmask, a.ffm, d);
+    }
+    return a;
+}
+
+__device__ __forceinline__ void k3a_store(const DevBatch& B, uint32_t j, const K3aAcc& a)
+{
+    SaSum o;
+    o.S = a.S; o.H = a.H;
+    o.refspan = (int64_t)a.D + (int64_t)a.M + (int64_t)a.E + (int64_t)a.X;
+    o.ffm = (int64_t)a.ffm; o.pad[0] = o.pad[1] = 0;
+    B.sa_sum[j] = o;
+}
+
+static constexpr uint32_t K3A_LONG = 96;       // CIGARs longer than this are walked by the whole warp
+
+// Each warp takes 32/G consecutive SA-list entries: short CIGARs are walked by the G-lane groups side by side, long ones
+// (ONT: 10^3..10^5 ops) by all 32 lanes one after the other, so the loads stay 128-byte coalesced.  G is picked by the host
+// from the batch's mean CIGAR length (2 lanes for the few-op records of split-heavy batches, 8 for HiFi-like CIGARs).
+template <int G>
+__global__ void __launch_bounds__(256) k3a_sa_cigar(DevBatch B, DevParams P)
+{
+    constexpr uint32_t PER_WARP = 32 / G;
+    griddep_wait();                                    // kernel 0's list and count
+    griddep_launch();
+    CtaTrace tr(B, 3);
+    const uint32_t n_sa = B.ctrl->n_sa;
+    tr.mid();
+    const uint32_t lane = threadIdx.x & 31, sub = lane & (G - 1), grp = lane / G;
+    const uint32_t gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (grp * G);
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t j0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * PER_WARP; j0 < n_sa; j0 += warps * PER_WARP) {
+        const uint32_t j = j0 + grp;
+        const bool have = j < n_sa;
+        uint32_t r = 0; unsigned long long o0 = 0, o1 = 0;
+        if (have) { r = B.sa_list[j]; o0 = B.cigar_off[r]; o1 = B.cigar_off[r + 1]; }
+        const bool is_long = have && (o1 - o0) > K3A_LONG;
+        if (have && !is_long) {
+            const K3aAcc a = k3a_walk<G>(B, r, o0, o1, gmask, grp * G);
+            if (sub == 0) k3a_store(B, j, a);
+        }
+        uint32_t longs = __ballot_sync(0xffffffffu, is_long && sub == 0);     // one bit per group (its lane 0)
+        while (longs) {
+            const int src = __ffs(longs) - 1; longs &= longs - 1;
+            const uint32_t rr = __shfl_sync(0xffffffffu, r, src);
+            const unsigned long long a0 = __shfl_sync(0xffffffffu, o0, src), a1 = __shfl_sync(0xffffffffu, o1, src);
+            const K3aAcc a = k3a_walk<32>(B, rr, a0, a1, 0xffffffffu, 0);
+            if (lane == 0) k3a_store(B, j0 + (uint32_t)src / G, a);
+        }
+    }
+    tr.end();
+}
+
+// ======================================================================================
+// kernel 3b: SA parse, cap, sort, large-INS rules, split pairs
+//
+// The SA list is ordered and only SA records own SA bytes, so the SA strings of 128 consecutive
+// list entries are one contiguous byte range: a CTA stages it into shared memory with coalesced
+// 128-bit loads and each thread then parses its own record's string out of shared memory
+// (falls back to reading global memory when the range does not fit).
+// ======================================================================================
+static constexpr int K3B_THREADS = 192;                 // the usual tile (64 records, ~140 pieces + 64 own segments) parses in one round
+static constexpr int K3B_TILE = 64;                     // SA records per tile (pieces are then spread over all threads)
+static constexpr int K3B_CTAS = 7;                      // CTAs per SM: 30 KB of shared memory and 48 registers x 192 threads each
+static constexpr uint32_t K3B_STAGE_BYTES = 12 * 1024;
+static constexpr uint32_t K3B_SEMI = 8;                // ';' positions kept per record by phase 1; more -> phase 1b rescans
+static constexpr uint32_t K3B_MAXP = 320;              // segments (records + SA pieces) per tile in the staged layout
+
+struct SmemBytes {            // byte i of sa_bytes, served from the staged copy (bias is a multiple of 16)
+    static constexpr bool kWords = true;
+    const uint8_t* p; uint32_t bias;
+    __device__ __forceinline__ uint32_t operator[](uint32_t i) const { return p[i - bias]; }
+    // the aligned 32-bit word holding byte i (little endian: byte i is bits 8*(i&3)..)
+    __device__ __forceinline__ uint32_t word(uint32_t i) const { return *reinterpret_cast<const uint32_t*>(p + ((i - bias) & ~3u)); }
+};
+struct GlobalBytes {
+    static constexpr bool kWords = false;
+    const uint8_t* p;
+    __device__ __forceinline__ uint32_t operator[](uint32_t i) const { return __ldg(p + i); }
+    __device__ __forceinline__ uint32_t word(uint32_t i) const { return 0u; }
+};
+
+// SWAR: 0x80 in every byte of x that equals c (exact: no carries cross byte lanes)
+__device__ __forceinline__ uint32_t swar_eq(uint32_t x, uint32_t c4)
+{
+    const uint32_t y = x ^ c4;
+    return ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y | 0x7f7f7f7fu);
+}
+// keep only the flag bits of the bytes whose absolute index is in [lo, hi); w0 = absolute index of the word's byte 0
+__device__ __forceinline__ uint32_t swar_clip(uint32_t z, uint32_t w0, uint32_t lo, uint32_t hi)
+{
+    if (w0 >= lo && w0 + 4u <= hi) return z;             // interior word: the common case costs one predicate
+    if (w0 < lo) z &= 0xffffffffu << (8u * (lo - w0));
+    if (w0 + 4u > hi) z &= 0xffffffffu >> (8u * (w0 + 4u - hi));
+    return z;
+}
+
+template <class Bytes>
+__device__ __forceinline__ bool dev_parse_i64(const Bytes& s, uint32_t b, uint32_t e, int64_t* out)
+{
+    if (b == e) return false;
+    bool neg = false;
+    const uint32_t c0 = s[b];
+    if (c0 == '+' || c0 == '-') { neg = c0 == '-'; b++; }
+    if (b == e) return false;
+    unsigned long long v = 0;
+    if (e - b <= 18u) {                                  // < 10^18: cannot overflow an i64, no per-digit range check
+        for (; b < e; b++) {
+            const uint32_t d = s[b] - '0';
+            if (d > 9u) return false;
+            v = v * 10ull + d;
+        }
+    } else {
+        const unsigned long long lim = neg ? (1ull << 63) : (1ull << 63) - 1;
+        for (; b < e; b++) {
+            const uint32_t d = s[b] - '0';
+            if (d > 9u) return false;
+            if (v > (lim - d) / 10ull) return false;
+            v = v * 10ull + d;
+        }
+    }
+    *out = neg ? (int64_t)(0ull - v) : (int64_t)v;
+    return true;
+}
+
+template <class Bytes>
+__device__ __forceinline__ bool dev_parse_u8(const Bytes& s, uint32_t b, uint32_t e)
+{
+    if (b == e) return false;
+    if (s[b] == '+') b++;
+    if (b == e) return false;
+    uint32_t v = 0;
+    for (; b < e; b++) {
+        const uint32_t d = s[b] - '0';
+        if (d > 9u) return false;
+        v = v * 10u + d;
+        if (v > 255u) return false;
+    }
+    return true;
+}
+
+// parse_supplementary_alignment + parse_cigar + find_first_match_pos (utils.rs:12-42, 88-139)
+template <class Bytes>
+__device__ uint32_t dev_parse_piece(const Bytes& s, uint32_t b, uint32_t e, const DevParams& P, Seg* out)
+{
+    uint32_t fb[6], fe[6], nf = 0, st = b;
+    if constexpr (Bytes::kWords) {                       // four bytes per step: find the commas with SWAR compares
+        for (uint32_t w0 = b & ~3u; w0 < e; w0 += 4u) {
+            uint32_t z = swar_clip(swar_eq(s.word(w0), 0x2c2c2c2cu), w0, b, e);
+            while (z) {
+                const uint32_t i = w0 + ((uint32_t)(__ffs((int)z) - 1) >> 3);
+                z &= z - 1u;
+                if (nf < 6) { fb[nf] = st; fe[nf] = i; }
+                nf++; st = i + 1;
+            }
+        }
+        if (nf < 6) { fb[nf] = st; fe[nf] = e; }
+        nf++;
+    } else {
+        for (uint32_t i = b; i <= e; i++) {
+            if (i == e || s[i] == ',') {
+                if (nf < 6) { fb[nf] = st; fe[nf] = i; }
+                nf++; st = i + 1;
+            }
+        }
+    }
+    if (nf < 6) return RANK_SA_FIELDS;
+    int64_t pos;
+    if (!dev_parse_i64(s, fb[1], fe[1], &pos)) return RANK_SA_POS;
+    const uint32_t sc = fe[2] - fb[2] == 1 ? s[fb[2]] : 0u;
+    if (sc != '+' && sc != '-') return RANK_SA_STRAND;
+    const uint32_t strand_neg = sc == '-';
+    uint32_t sS = 0, sH = 0, sD = 0, sM = 0, sE = 0, sX = 0, ndig = 0;
+    unsigned long long v = 0, key = 0; bool seenM = false;
+    for (uint32_t i = fb[3]; i < fe[3]; i++) {
+        const uint32_t c = s[i], d = c - '0';
+        if (d <= 9u) { v = v * 10ull + d; if (v > 0x1ffffffffull) v = 0x1ffffffffull; ndig++; continue; }
+        // op letters as bits of (c - '='):  = D H I M N P S X  ->  0 7 11 12 16 17 19 22 27
+        const uint32_t x = c - '=';
+        const bool isop = x < 28u && ((0x84B1881u >> x) & 1u);
+        if (!isop || ndig == 0 || v > 0xffffffffull) return RANK_SA_CIGAR;
+        const uint32_t n = (uint32_t)v;
+        if (c == 'M') { sM += n; seenM = true; }
+        else {
+            if (c == 'S') sS += n; else if (c == 'D') sD += n; else if (c == 'H') sH += n;
+            else if (c == '=') sE += n; else if (c == 'X') sX += n;
+            if (!seenM && ((0x8401001u >> x) & 1u)) key += n;             // = I S X before the first M (utils.rs:33)
+        }
+        v = 0; ndig = 0;
+    }
+    if (!dev_parse_u8(s, fb[4], fe[4])) return RANK_SA_MAPQ;
+    int64_t nm;
+    if (!dev_parse_i64(s, fb[5], fe[5], &nm)) return RANK_SA_NM;
+    uint32_t cb = fb[0];
+    const uint32_t ce = fe[0];
+    if (ce - cb >= 3 && s[cb] == 'c' && s[cb + 1] == 'h' && s[cb + 2] == 'r') cb += 3;
+    out->chrom_ref = 0x80000000u | cb;
+    out->chrom_len = ce - cb;
+    out->start = (int64_t)((unsigned long long)pos - 1ull);
+    out->end = out->start + (int64_t)sD + (int64_t)sM + (int64_t)sE + (int64_t)sX;
+    out->key = (int64_t)key;
+    out->clip_big = (sS > P.ins_clip_min || sH > P.ins_clip_min) ? 1u : 0u;
+    out->strand_neg = strand_neg;
+    return 0;
+}
+
+// Fast path of parse_supplementary_alignment (utils.rs:119-139) for the regular form every aligner writes,
+//     chrom,<1-9 digits>,<+|->,(<1-9 digits><op>)+,<1-3 digits <= 255>,<1-9 digits>
+// in ONE pass over the bytes.  Anything else -- signs, longer numbers, missing or extra fields, odd bytes, trailing digits in
+// the CIGAR -- returns false and the caller runs the exact dev_parse_piece above, which also yields the reference's panics.
+// For the accepted form both produce the same Seg: same field boundaries, u32-wrapping sums, u64 key.
+// Written for warp convergence: one simple loop per field, no early exit (a failed check only clears `ok`), and the lanes
+// of `m` (the lanes of the warp that hold a piece) re-join after every loop -- with early returns and nested digit loops
+// the lanes drifted apart and the parser ran at a quarter of the warp width.
+__device__ __forceinline__ bool dev_parse_piece_fast(const uint8_t* p /* staged bytes */, uint32_t bias /* sa offset of p[0] */,
+                                                     uint32_t b, uint32_t e, const DevParams& P, Seg* out, uint32_t m)
+{
+    b -= bias; e -= bias;
+    bool ok = true;
+    uint32_t i = b;
+    while (i < e && p[i] != ',') i++;                                          // chrom
+    __syncwarp(m);
+    const uint32_t ce = i;
+    ok &= i < e;
+    i++;
+    uint32_t pos = 0, nd = 0;                                                  // pos
+    while (i < e) { const uint32_t d = (uint32_t)p[i] - '0'; if (d > 9u) break; pos = pos * 10u + d; nd++; i++; }
+    __syncwarp(m);
+    ok &= nd - 1u < 9u && i < e && p[min(i, e - 1u)] == ',';
+    i++;
+    const uint32_t sc = i < e ? (uint32_t)p[i] : 0u, sc2 = i + 1u < e ? (uint32_t)p[i + 1] : 0u;   // strand
+    ok &= (sc == '+' || sc == '-') && sc2 == ',';
+    i += 2;
+    // CIGAR text (utils.rs:88-117, 12-42): the same step for every byte up to the comma
+    uint32_t sS = 0, sH = 0, sD = 0, sM = 0, sE = 0, sX = 0, nops = 0, n = 0, bad = 0;
+    unsigned long long key = 0; bool seenM = false;
+    nd = 0;
+    while (i < e) {
+        const uint32_t c = p[i];
+        if (c == ',') break;
+        const uint32_t d = c - '0';
+        if (d <= 9u) { n = n * 10u + d; nd++; }
+        else {
+            const uint32_t x = c - '=';                                         // = D H I M N P S X  ->  0 7 11 12 16 17 19 22 27
+            bad |= (x >= 28u || !((0x84B1881u >> (x & 31u)) & 1u) || nd - 1u >= 9u) ? 1u : 0u;
+            sM += c == 'M' ? n : 0u; sS += c == 'S' ? n : 0u; sD += c == 'D' ? n : 0u;
+            sH += c == 'H' ? n : 0u; sE += c == '=' ? n : 0u; sX += c == 'X' ? n : 0u;
+            if (!seenM && x < 28u && ((0x8401001u >> x) & 1u)) key += n;        // = I S X before the first M (utils.rs:33)
+            seenM |= c == 'M';
+            n = 0; nd = 0; nops++;
+        }
+        i++;
+    }
+    __syncwarp(m);
+    ok &= !bad && nd == 0u && nops != 0u && i < e;                             // ends at the comma, right after an op
+    i++;
+    uint32_t mq = 0;                                                           // mapq: u8
+    nd = 0;
+    while (i < e) { const uint32_t d = (uint32_t)p[i] - '0'; if (d > 9u) break; mq = mq * 10u + d; nd++; i++; }
+    __syncwarp(m);
+    ok &= nd - 1u < 3u && mq <= 255u && i < e && p[min(i, e - 1u)] == ',';
+    i++;
+    nd = 0;                                                                    // NM: parsed, value unused (utils.rs:135)
+    while (i < e) { if ((uint32_t)p[i] - '0' > 9u) break; nd++; i++; }
+    __syncwarp(m);
+    ok &= nd - 1u < 9u && i == e;
+    if (!ok) return false;
+    uint32_t cb = b;
+    if (ce - cb >= 3u && p[cb] == 'c' && p[cb + 1] == 'h' && p[cb + 2] == 'r') cb += 3;
+    out->chrom_ref = 0x80000000u | (cb + bias);
+    out->chrom_len = ce - cb;
+    out->start = (int64_t)pos - 1;
+    out->end = out->start + (int64_t)sD + (int64_t)sM + (int64_t)sE + (int64_t)sX;
+    out->key = (int64_t)key;
+    out->clip_big = (sS > P.ins_clip_min || sH > P.ins_clip_min) ? 1u : 0u;
+    out->strand_neg = sc == '-';
+    return true;
+}
+
+// Calls f(w0, z) for every aligned word of bytes [b0, e0): z has 0x80 in each byte that equals the byte replicated in c4,
+// bytes outside the range masked off (only the first and the last word pay for the masking).
+template <class F>
+__device__ __forceinline__ void swar_scan(const SmemBytes& s, uint32_t b0, uint32_t e0, uint32_t c4, F f)
+{
+    if (b0 >= e0) return;
+    uint32_t w0 = b0 & ~3u;
+    const uint32_t last = (e0 - 1u) & ~3u;
+    uint32_t z = swar_eq(s.word(w0), c4) & (0xffffffffu << (8u * (b0 - w0)));
+    if (w0 == last) { f(w0, z & (0xffffffffu >> (8u * (w0 + 4u - e0)))); return; }
+    f(w0, z);
+    for (w0 += 4u; w0 < last; w0 += 4u) f(w0, swar_eq(s.word(w0), c4));
+    f(last, swar_eq(s.word(last), c4) & (0xffffffffu >> (8u * (last + 4u - e0))));
+}
+
+template <class Bytes>
+__device__ __forceinline__ uint32_t chrom_byte(const DevBatch& B, const Bytes& s, const Seg& g, uint32_t i)
+{
+    return (g.chrom_ref >> 31) ? s[(g.chrom_ref & 0x7fffffffu) + i] : (uint32_t)__ldg(B.ref_bytes + B.ref_off[g.chrom_ref] + i);
+}
+
+// String::cmp / as_bytes().cmp (utils.rs:76-77) on the "chr"-stripped names
+template <class Bytes>
+__device__ __forceinline__ int dev_chrom_cmp(const DevBatch& B, const Bytes& s, const Seg& a, const Seg& b)
+{
+    const uint32_t m = a.chrom_len < b.chrom_len ? a.chrom_len : b.chrom_len;
+    for (uint32_t i = 0; i < m; i++) {
+        const uint32_t x = chrom_byte(B, s, a, i), y = chrom_byte(B, s, b, i);
+        if (x != y) return x < y ? -1 : 1;
+    }
+    return a.chrom_len < b.chrom_len ? -1 : (a.chrom_len > b.chrom_len ? 1 : 0);
+}
+
+// overlap (utils.rs:158-194); IEEE f64 divide and compare, like the Rust
+__device__ __forceinline__ bool dev_overlap(int64_t as, int64_t ae, int64_t bs, int64_t be, double p)
+{
+    if (ae < bs || as > be) return false;
+    const int64_t la = ae - as, lb = be - bs;
+    const int64_t ml = la < lb ? la : lb;
+    int64_t num;
+    if (as < bs) num = ae < be ? ae - bs : be - bs;
+    else         num = be < ae ? be - as : ae - as;
+    const double ov = __ddiv_rn((double)num, (double)ml);
+    return ov > p;
+}
+
+// Second half of a record's SA arm, shared by the fast and the fallback path: stable sort of the segments
+// (main.rs:322), large-INS rules (main.rs:340-486), slot allocation, event emission (main.rs:488-516).
+// Must be called by every lane of the warp (the slot allocation is warp-aggregated).
+template <class Bytes>
+__device__ __forceinline__ void k3b_finish(const DevBatch& B, const DevParams& P, const Bytes& s, uint32_t j, bool active,
+                                           uint32_t r, bool dropped, Seg* segs, uint32_t nseg)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t n_ins = 0, ins_kind = 0;
+    int64_t q1 = 0, q2 = 0, q0 = 0;
+    if (active && nseg) {
+        for (uint32_t i = 1; i < nseg; i++) {                             // stable insertion sort by key (main.rs:322)
+            const Seg x = segs[i]; uint32_t k = i;
+            while (k > 0 && segs[k - 1].key > x.key) { segs[k] = segs[k - 1]; k--; }
+            segs[k] = x;
+        }
+        if (nseg == 2) {                                                  // main.rs:340-451
+            const Seg& a = segs[0]; const Seg& b = segs[1];
+            if (a.clip_big) {
+                if (dev_chrom_cmp(B, s, a, b) == 0) {
+                    if (a.strand_neg == b.strand_neg && dev_overlap(a.start, a.end, b.start, b.end, P.max_pct_overlap) && b.clip_big) {
+                        int64_t q[4] = {a.start, a.end, b.start, b.end};
+#pragma unroll
+                        for (int x = 1; x < 4; x++) { const int64_t val = q[x]; int y = x; while (y > 0 && q[y - 1] > val) { q[y] = q[y - 1]; y--; } q[y] = val; }
+                        q0 = q[0]; q1 = q[1]; q2 = q[2];
+                        n_ins = 2; ins_kind = EXLR_KIND_INS_TWO_ALN;
+                    }
+                } else { n_ins = 1; ins_kind = EXLR_KIND_INS_ONE_ALN; }
+            }
+        } else if (nseg == 1) {                                           // main.rs:459-486
+            if (segs[0].clip_big) { n_ins = 1; ins_kind = EXLR_KIND_INS_ONE_SEG; }
+        }
+    }
+    // temp slots: one atomic per warp
+    const uint32_t cnt = (active && nseg) ? n_ins + nseg - 1 : 0u;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+    uint32_t base = 0;
+    const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 31 && wtotal) base = atomicAdd(&B.ctrl->n_saev, wtotal);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+    const uint32_t dm = __ballot_sync(0xffffffffu, active && dropped);
+    if (lane == 0 && dm) atomicAdd(&B.ctrl->n_dropped, (uint32_t)__popc(dm));
+    if (!active) return;
+    B.sa_base[j] = base;
+    B.csa[r] = dropped ? CSA_DROP : cnt;
+    if (!cnt) return;
+    if ((unsigned long long)base + cnt > B.max_events) { B.ctrl->overflow = 1; return; }
+    exlr_event* dst = B.sa_ev + base;
+    if (n_ins == 2) {
+        const Seg& a = segs[0]; const Seg& b = segs[1];
+        const uint32_t meta = EXLR_EV_META(1u, EXLR_KIND_INS_TWO_ALN, a.strand_neg, b.strand_neg);
+        store_event(dst++, (int64_t)(uint32_t)q0, (int64_t)(uint32_t)q1, (int64_t)(uint32_t)q1, (int64_t)(uint32_t)q1, r, a.chrom_ref, b.chrom_ref, meta);
+        store_event(dst++, (int64_t)(uint32_t)q0, (int64_t)(uint32_t)q2, (int64_t)(uint32_t)q2, (int64_t)(uint32_t)q2, r, a.chrom_ref, b.chrom_ref, meta);
+    } else if (n_ins == 1) {
+        const Seg& a = segs[0];
+        const uint32_t meta = EXLR_EV_META(1u, ins_kind, a.strand_neg, a.strand_neg);
+        store_event(dst++, (int64_t)(uint32_t)a.start, (int64_t)(uint32_t)a.end, (int64_t)(uint32_t)a.end, (int64_t)(uint32_t)a.end, r, a.chrom_ref, a.chrom_ref, meta);
+    }
+    for (uint32_t i = 1; i < nseg; i++) {                                 // main.rs:488-516
+        const Seg* a = &segs[i - 1]; const Seg* b = &segs[i];
+        int c = dev_chrom_cmp(B, s, *a, *b);                               // alignment_pos_cmp, utils.rs:75-86
+        if (c == 0) c = a->start < b->start ? -1 : (a->start > b->start ? 1 : 0);
+        if (c > 0) { const Seg* x = a; a = b; b = x; }
+        store_event(dst++, a->start, a->end, b->start, b->end, r, a->chrom_ref, b->chrom_ref,
+                    EXLR_EV_META(nseg - 1, EXLR_KIND_SPLIT, a->strand_neg, b->strand_neg));
+    }
+}
+
+// the record's own alignment as segment 0 (main.rs:299-306)
+__device__ __forceinline__ void k3b_record_seg(const DevBatch& B, const DevParams& P, uint32_t j, uint32_t r, Seg* out)
+{
+    const SaSum sum = B.sa_sum[j];
+    const int32_t tid = B.tid[r];
+    out->chrom_ref = (uint32_t)tid; out->chrom_len = B.ref_off[tid + 1] - B.ref_off[tid];
+    out->start = (int64_t)B.pos[r]; out->end = out->start + sum.refspan; out->key = sum.ffm;
+    out->clip_big = (sum.S > P.ins_clip_min || sum.H > P.ins_clip_min) ? 1u : 0u;
+    out->strand_neg = (B.flag[r] & 0x10u) ? 1u : 0u;
+}
+
+// Fallback: one SA record parsed start to finish by one thread (used when a tile's SA bytes or segment count do
+// not fit the staged layout, e.g. -k far above the default).  Must be called by every lane of the warp.
+template <class Bytes>
+__device__ __forceinline__ void k3b_record(const DevBatch& B, const DevParams& P, const Bytes& s, uint32_t j, bool active, Seg* local_segs)
+{
+    uint32_t r = 0, nseg = 0, err = 0;
+    bool dropped = false;
+    Seg* segs = local_segs;
+    if (active) {
+        r = B.sa_list[j];
+        const uint32_t b0 = B.sa_off[r], e0 = B.sa_off[r + 1];
+        const bool is_str = B.sa_kind[r] == EXLR_SA_STRING;
+        unsigned long long pieces = 1;
+        if (is_str) {
+            for (uint32_t i = b0; i < e0; i++) pieces += s[i] == ';';
+            if (pieces > P.max_supp_alignm) dropped = true;                 // main.rs:311-313: the whole record is skipped
+        }
+        if (!dropped && is_str && pieces + 1 > (unsigned long long)kLocalSegs) {
+            const uint32_t need = (uint32_t)pieces + 1;
+            const uint32_t at = atomicAdd(&B.ctrl->seg_pool_used, need);
+            if ((unsigned long long)at + need <= B.seg_pool_cap) segs = B.seg_pool + at;
+            else { B.ctrl->overflow = 1; dropped = true; }
+        }
+        if (!dropped) {
+            k3b_record_seg(B, P, j, r, &segs[0]);
+            nseg = 1;
+            if (is_str) {
+                uint32_t pb = b0;
+                for (uint32_t i = b0; i <= e0 && !err; i++) {
+                    if (i == e0 || s[i] == ';') {
+                        if (i > pb) {                                         // filter(|x| x.len() > 0), main.rs:315
+                            err = dev_parse_piece(s, pb, i, P, &segs[nseg]);
+                            if (!err) nseg++;
+                        }
+                        pb = i + 1;
+                    }
+                }
+            }
+            if (!err && nseg - 1 >= (1u << 24)) err = RANK_SPLIT_COUNT;
+            if (err) { report(B.ctrl, r, err); nseg = 0; }
+        }
+    }
+    k3b_finish(B, P, s, j, active, r, dropped, segs, nseg);
+}
+
+// Fast path layout: the tile's SA bytes, its piece list and its segments all live in shared memory, and the work
+// is re-flattened between phases so that the lanes of a warp always run the same loop:
+//   phase 1  thread per record : count ';' (the -k cap) and non-empty pieces          -> slots per record, block scan
+//   phase 1b thread per record : write the [begin,end) of every piece into the piece list
+//   phase 2  thread per PIECE  : parse_supplementary_alignment on homogeneous pieces   -> Seg
+//   phase 3  thread per record : record segment, sort, rules, emit
+struct __align__(16) K3bSmem {
+    uint8_t bytes[K3B_STAGE_BYTES];
+    Seg segs[K3B_MAXP];
+    uint32_t pb[K3B_MAXP], pe[K3B_MAXP];
+    uint32_t rerr[K3B_TILE];
+    uint32_t semi[K3B_TILE][K3B_SEMI];                 // positions of the first ';' of every record (phase 1 -> 1b)
+    uint32_t wsum[K3B_THREADS / 32];
+    uint8_t pread[K3B_MAXP];
+};
+
+__global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch B, DevParams P)
+{
+    extern __shared__ __align__(16) unsigned char k3b_smem_raw[];
+    K3bSmem& S = *reinterpret_cast<K3bSmem*>(k3b_smem_raw);
+    griddep_wait();                                    // kernel 3a's summaries
+    CtaTrace tr(B, 4);
+    const uint32_t n_sa = B.ctrl->n_sa;
+    const uint32_t n_tiles = (n_sa + K3B_TILE - 1) / K3B_TILE;
+    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+    Seg local_segs[kLocalSegs];
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t j0 = tile * K3B_TILE, j1 = min(j0 + (uint32_t)K3B_TILE, n_sa);
+        const uint32_t span_b = B.sa_off[B.sa_list[j0]], span_e = B.sa_off[B.sa_list[j1 - 1] + 1];
+        const uint32_t a0 = span_b & ~15u;
+        const bool staged = span_e - a0 <= K3B_STAGE_BYTES;                   // block-uniform
+        const uint32_t j = j0 + t;
+        const bool active = t < K3B_TILE && j < j1;                           // the other threads only help with the pieces
+        __syncthreads();                                                      // the previous tile's readers are done
+        if (!staged) {
+            GlobalBytes s{B.sa_bytes};
+            k3b_record(B, P, s, j, active, local_segs);
+            continue;
+        }
+        for (uint32_t o = a0 + t * 16u; o < span_e; o += K3B_THREADS * 16u)
+            *reinterpret_cast<uint4*>(S.bytes + (o - a0)) = __ldg(reinterpret_cast<const uint4*>(B.sa_bytes + o));
+        // phase 1: pieces per record
+        uint32_t r = 0, b0 = 0, e0 = 0, slots = 0;
+        bool dropped = false, is_str = false;
+        if (active) { r = B.sa_list[j]; b0 = B.sa_off[r]; e0 = B.sa_off[r + 1]; is_str = B.sa_kind[r] == EXLR_SA_STRING; }
+        __syncthreads();
+        SmemBytes s{S.bytes, a0};
+        uint32_t nsemi = 0;
+        if (active) {
+            uint32_t nonempty = 0;
+            if (is_str) {
+                // one pass, four bytes per step: every ';' closes a piece (empty when it directly follows the previous ';' or the
+                // start of the string); the last piece runs to the end of the string.  pieces = #';' + 1 (main.rs:309).
+                uint32_t pbeg = b0;
+                swar_scan(s, b0, e0, 0x3b3b3b3bu, [&](uint32_t w0, uint32_t z) {
+                    while (z) {
+                        const uint32_t i = w0 + ((uint32_t)(__ffs((int)z) - 1) >> 3);
+                        z &= z - 1u;
+                        if (nsemi < K3B_SEMI) S.semi[t][nsemi] = i;
+                        nsemi++;
+                        nonempty += i > pbeg;
+                        pbeg = i + 1u;
+                    }
+                });
+                nonempty += e0 > pbeg;
+                if ((unsigned long long)nsemi + 1ull > P.max_supp_alignm) dropped = true;   // main.rs:311-313
+            }
+            slots = dropped ? 0u : 1u + nonempty;
+            S.rerr[t] = 0xffffffffu;
+        }
+        uint32_t incl = slots;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+        if (lane == 31) S.wsum[w] = incl;
+        __syncthreads();
+        uint32_t sb = incl - slots, total = 0;
+#pragma unroll
+        for (int k = 0; k < K3B_THREADS / 32; k++) { const uint32_t x = S.wsum[k]; if ((uint32_t)k < w) sb += x; total += x; }
+        if (total > K3B_MAXP) {                                               // block-uniform: too many segments for the staged layout
+            k3b_record(B, P, s, j, active, local_segs);
+            continue;
+        }
+        // phase 1b: piece list
+        if (active && !dropped) {
+            S.pb[sb] = 0xffffffffu; S.pread[sb] = (uint8_t)t;                 // slot 0 of the record: its own alignment
+            if (is_str) {
+                uint32_t at = sb + 1, pbeg = b0;
+                auto piece_end = [&](uint32_t i) {
+                    if (i > pbeg) { S.pb[at] = pbeg; S.pe[at] = i; S.pread[at] = (uint8_t)t; at++; }   // filter(|x| x.len() > 0), main.rs:315
+                    pbeg = i + 1u;
+                };
+                if (nsemi <= K3B_SEMI) {
+                    for (uint32_t k = 0; k < nsemi; k++) piece_end(S.semi[t][k]);
+                } else {                                                       // more ';' than phase 1 kept (large -k): rescan
+                    swar_scan(s, b0, e0, 0x3b3b3b3bu, [&](uint32_t w0, uint32_t z) {
+                        while (z) { piece_end(w0 + ((uint32_t)(__ffs((int)z) - 1) >> 3)); z &= z - 1u; }
+                    });
+                }
+                if (e0 > pbeg) piece_end(e0);
+            }
+        }
+        __syncthreads();
+        // phase 2: one thread per piece
+        for (uint32_t x0 = 0; x0 < total; x0 += K3B_THREADS) {               // block-uniform trip count
+            const uint32_t x = x0 + t;
+            const uint32_t pbeg = x < total ? S.pb[x] : 0xffffffffu;
+            const bool has = pbeg != 0xffffffffu;
+            const uint32_t m = __ballot_sync(0xffffffffu, has);
+            if (!has) continue;
+            const uint32_t pend = S.pe[x];
+            if (dev_parse_piece_fast(S.bytes, a0, pbeg, pend, P, &S.segs[x], m)) continue;
+            const uint32_t err = dev_parse_piece(s, pbeg, pend, P, &S.segs[x]);   // irregular piece: the exact parser decides
+            if (err) atomicMin(&S.rerr[S.pread[x]], (x << 8) | err);          // the first failing piece in SA order wins
+        }
+        __syncthreads();
+        tr.mid();
+        // phase 3: one thread per record
+        uint32_t nseg = 0;
+        if (active && !dropped) {
+            uint32_t err = S.rerr[t];
+            nseg = slots;
+            if (err != 0xffffffffu) { report(B.ctrl, r, err & 0xffu); nseg = 0; }
+            else k3b_record_seg(B, P, j, r, &S.segs[sb]);
+        }
+        k3b_finish(B, P, s, j, active, r, dropped, &S.segs[sb < K3B_MAXP ? sb : 0], nseg);
+    }
+    tr.end();
+}
+
+// ======================================================================================
+// launchers
+// ======================================================================================
+cudaError_t configure_sa_kernels() { return cudaFuncSetAttribute(k3b_sa_events, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3bSmem)); }
+
+void launch_k3a(const DevBatch& B, const DevParams& P, uint32_t mean_ops, cudaStream_t st)
+{
+    // grid-stride over a device-side count: size for the worst case, cap at one resident wave (spare CTAs cost launch time).
+    // Lanes per record by the batch's mean CIGAR length: the more records a warp walks side by side, the fewer waves.
+    const uint32_t cap = (uint32_t)sm_count() * 8u;
+    if (mean_ops <= 16) {
+        const uint32_t g = min((B.n_reads + 127u) / 128u, cap);
+        launch_dependent(k3a_sa_cigar<2>, g ? g : 1u, 256, 0, st, B, P);
+    } else if (mean_ops <= 48) {
+        const uint32_t g = min((B.n_reads + 63u) / 64u, cap);
+        launch_dependent(k3a_sa_cigar<4>, g ? g : 1u, 256, 0, st, B, P);
+    } else {
+        const uint32_t g = min((B.n_reads + 31u) / 32u, cap);
+        launch_dependent(k3a_sa_cigar<8>, g ? g : 1u, 256, 0, st, B, P);
+    }
+}
+
+void launch_k3b(const DevBatch& B, const DevParams& P, cudaStream_t st)
+{
+    // tiles of 64 SA records, grid-stride; the SA-record count lives on the device, so the grid is sized from the batch but
+    // capped at the CTAs that are resident at once: spare CTAs of an over-sized grid cost a launch slot each just to read the
+    // count and leave, and a CTA with a second tile doubles the kernel's span
+    const uint32_t gb = min((B.n_reads + K3B_TILE - 1u) / K3B_TILE, (uint32_t)sm_count() * K3B_CTAS);
+    launch_dependent(k3b_sa_events, gb ? gb : 1u, K3B_THREADS, sizeof(K3bSmem), st, B, P);
+}
+
+}  // namespace exlr
