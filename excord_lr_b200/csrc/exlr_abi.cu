@@ -260,7 +260,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     const size_t d_ctrl = dcarve(sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes + (size_t)ttiles * 8);   // ctrl | scan_a | scan_b | dirty_bits | scan_c : one memset
     const size_t d_cigar = dcarve((max_ops + 4) * 4 + 16), d_coff = dcarve((R + 1) * 8), d_pos = dcarve(R * 4), d_tid = dcarve(R * 4),
                  d_flag = dcarve(R * 2), d_mapq = dcarve(R), d_kind = dcarve(R), d_soff = dcarve((R + 1) * 4), d_sab = dcarve(max_sa_bytes + 16),
-                 d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_slist = dcarve((max_ops / 512 + 16) * 4), d_llist = dcarve(R * 4), d_shlist = dcarve(R * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
+                 d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_slist = dcarve((max_ops / 512 + 16) * 4), d_llist = dcarve(R * 4), d_shlist = dcarve(R * 4), d_wlist = dcarve(R * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
                  d_raw = dcarve((max_events + kRawHeadroom) * sizeof(RawEv)), d_saev = dcarve(max_events * sizeof(exlr_event)),
                  d_pool = dcarve(pool_cap * sizeof(Seg)), d_dbg = dcarve(8192 * 32), d_toff = dcarve(c->device_format ? (max_events + 1) * 4 : 0), d_text = dcarve(text_cap + 16), d_loff = dcarve((R + 1) * 4), d_ev = dcarve(max_events * sizeof(exlr_event));
     e = cudaMalloc(&b->d_slab, dof);
@@ -269,7 +269,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     DevBatch& v = b->dv;
     v.ctrl = (Ctrl*)(ds + d_ctrl);
     v.scan_a = (unsigned long long*)(ds + d_ctrl + sizeof(Ctrl)); v.scan_b = v.scan_a + tiles;
-    v.dirty_bits = (uint32_t*)(v.scan_b + tiles); v.step_list = (uint32_t*)(ds + d_slist); v.long_list = (uint32_t*)(ds + d_llist); v.short_list = (uint32_t*)(ds + d_shlist);
+    v.dirty_bits = (uint32_t*)(v.scan_b + tiles); v.step_list = (uint32_t*)(ds + d_slist); v.long_list = (uint32_t*)(ds + d_llist); v.short_list = (uint32_t*)(ds + d_shlist); v.warp_list = (uint32_t*)(ds + d_wlist);
     v.scan_c = (unsigned long long*)((char*)v.dirty_bits + bits_bytes);
     v.text_off = c->device_format ? (uint32_t*)(ds + d_toff) : nullptr; v.text = (uint8_t*)(ds + d_text); v.text_cap = (uint32_t)text_cap;
     b->ctrl_bytes = sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes + (size_t)ttiles * 8;

@@ -625,7 +625,7 @@ __device__ __forceinline__ uint32_t k1b_find_read(const unsigned long long* off,
 // walking inside the per-step warps ran at a third of the warp width, since most of a step's records belong to a neighbour).
 // ======================================================================================
 static constexpr int K1B_THREADS = 256;
-static constexpr uint32_t K1B_LONG = 256;              // ops; longer records go to kernel 1c
+static constexpr uint32_t K1B_LONG = 256;              // ops; longer records are scanned by kernel 1c or by a warp
 static constexpr uint32_t K1B_EV = 4;                  // events per record parked in shared memory during the walk
 static constexpr int K1B_VEC = 4;                      // 128-bit loads in flight per walking thread
 
@@ -663,17 +663,22 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_claim(DevBatch B, DevParams P
                 const uint32_t p = sh + lane;
                 if ((p < 32u ? old_lo >> p : old_hi >> (p - 32u)) & 1u) mine = false;
             }
-            // long records: kernel 1c's list, or (batches of short records, where kernel 1c is not launched) the short list with bit 31
-            // set: k1b_walk then scans them with a whole warp
-            const bool is_big = mine && o1 - o0 > K1B_LONG, is_long = is_big && use_k1c;
-            const uint32_t sm = __ballot_sync(0xffffffffu, mine && !is_long), lm = __ballot_sync(0xffffffffu, is_long);
-            uint32_t sbase = 0, lbase = 0;
-            if (lane == 0 && sm) sbase = atomicAdd(&B.ctrl->n_short, (uint32_t)__popc(sm));
-            if (lane == 1 && lm) lbase = atomicAdd(&B.ctrl->n_long, (uint32_t)__popc(lm));
-            sbase = __shfl_sync(0xffffffffu, sbase, 0); lbase = __shfl_sync(0xffffffffu, lbase, 1);
+            // by CIGAR length: a thread walks it (short_list); longer ones are scanned block-wide by kernel 1c (long_list) in
+            // batches of long records, and by a warp each (warp_list) in batches of short records, where kernel 1c is not
+            // launched.  (Measured on the ONT config: a warp per 3k-op record is latency-bound at ~1.8 us per 32 ops -- 1.1 ms for
+            // the 58k records kernel 1c scans in 0.5 ms.)
+            const unsigned long long len = o1 - o0;
+            const bool c_long = mine && len > K1B_LONG && use_k1c, c_warp = mine && len > K1B_LONG && !use_k1c, c_short = mine && len <= K1B_LONG;
+            const uint32_t sm = __ballot_sync(0xffffffffu, c_short), wm = __ballot_sync(0xffffffffu, c_warp), lm = __ballot_sync(0xffffffffu, c_long);
+            uint32_t base = 0;
+            if (lane == 0 && sm) base = atomicAdd(&B.ctrl->n_short, (uint32_t)__popc(sm));
+            if (lane == 1 && wm) base = atomicAdd(&B.ctrl->n_warp, (uint32_t)__popc(wm));
+            if (lane == 2 && lm) base = atomicAdd(&B.ctrl->n_long, (uint32_t)__popc(lm));
+            const uint32_t sbase = __shfl_sync(0xffffffffu, base, 0), wbase = __shfl_sync(0xffffffffu, base, 1), lbase = __shfl_sync(0xffffffffu, base, 2);
             const uint32_t below = (1u << lane) - 1u;
-            if (mine && !is_long) B.short_list[sbase + __popc(sm & below)] = r | (is_big ? 0x80000000u : 0u);
-            if (is_long) B.long_list[lbase + __popc(lm & below)] = r;
+            if (c_short) B.short_list[sbase + __popc(sm & below)] = r;
+            if (c_warp) B.warp_list[wbase + __popc(wm & below)] = r;
+            if (c_long) B.long_list[lbase + __popc(lm & below)] = r;
             // the next 32 records matter only if the last one of these still ends inside the step
             if (!__shfl_sync(0xffffffffu, (uint32_t)(overlaps && o1 < hi_op), 31)) break;
         }
@@ -685,7 +690,7 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_claim(DevBatch B, DevParams P
     tr.end();
 }
 
-__global__ void __launch_bounds__(K1B_THREADS) k1b_walk(DevBatch B, DevParams P, uint32_t use_k1c)
+__global__ void __launch_bounds__(K1B_THREADS) k1b_walk(DevBatch B, DevParams P)
 {
     __shared__ uint2 s_ev[K1B_THREADS][K1B_EV + 1];    // {left_consume, op word}; the extra slot tells "more than K1B_EV"
     const uint32_t t = threadIdx.x, lane = t & 31;
@@ -701,9 +706,9 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_walk(DevBatch B, DevParams P,
         const bool have = i < n_list;
         uint32_t r = 0, pos2 = 0, nv = 0, head = 0, nops = 0;
         const uint4* c4 = cig4;
-        bool is_long = false;                                                  // not for one thread: too long, or too many events
-        if (have) { r = B.short_list[i]; is_long = r >> 31; r &= 0x7fffffffu; }
-        if (have && !is_long) {
+        bool is_long = false;                                                  // more events than parking space
+        if (have) {
+            r = B.short_list[i];
             const unsigned long long o0 = B.cigar_off[r], o1 = B.cigar_off[r + 1], a0 = o0 & ~3ull;
             pos2 = (uint32_t)B.pos[r];
             nv = (uint32_t)((((o1 + 3ull) & ~3ull) - a0) >> 2);                // aligned vectors spanned (<= 65)
@@ -738,7 +743,7 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_walk(DevBatch B, DevParams P,
             }
         }
         const uint32_t cnt = (evp - ev0) >> 3;
-        if (have && !is_long) {
+        if (have) {
             if (flags & 0x40u) report(B.ctrl, r, RANK_CIGAR_OP);                                    // rust-htslib panics on an unknown op
             if (cnt > K1B_EV) is_long = true;                                                       // more events than parking space
             else {
@@ -770,16 +775,12 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_walk(DevBatch B, DevParams P,
                 d[1] = make_uint4(j ? s_ev[t][j - 1].x : 0u, 0u, 0u, 0u);
             } else B.ctrl->overflow = 1;
         }
-        uint32_t lm = __ballot_sync(0xffffffffu, is_long);
-        if (lm && use_k1c) {                                                   // on to kernel 1c's list
-            uint32_t lbase = 0;
-            if (lane == 0) lbase = atomicAdd(&B.ctrl->n_long, (uint32_t)__popc(lm));
-            lbase = __shfl_sync(0xffffffffu, lbase, 0);
-            if (is_long) B.long_list[lbase + __popc(lm & ((1u << lane) - 1u))] = r;
-        } else {
-            for (; lm; lm &= lm - 1u) k1_warp_record(B, P, __shfl_sync(0xffffffffu, r, __ffs((int)lm) - 1));   // the whole warp scans it
-        }
+        for (uint32_t lm = __ballot_sync(0xffffffffu, is_long); lm; lm &= lm - 1u)          // rare: the whole warp scans such a record
+            k1_warp_record(B, P, __shfl_sync(0xffffffffu, r, __ffs((int)lm) - 1));
     }
+    // the medium-length records: one warp each, 32 ops per step with a shuffle scan
+    const uint32_t n_warp = B.ctrl->n_warp, nw = (gridDim.x * K1B_THREADS) >> 5;
+    for (uint32_t i = (blockIdx.x * K1B_THREADS + t) >> 5; i < n_warp; i += nw) k1_warp_record(B, P, B.warp_list[i]);
     tr.end();
 }
 
@@ -860,7 +861,7 @@ void launch_k1b(const DevBatch& B, const DevParams& P, unsigned long long n_ops,
     const uint32_t g1 = min((steps + K1B_THREADS / 32 - 1) / (K1B_THREADS / 32), (uint32_t)sm_count() * 8u);
     launch_dependent(k1b_claim, g1 ? g1 : 1u, K1B_THREADS, 0, st, B, P, n_ops, use_k1c ? 1u : 0u);
     const uint32_t g2 = min((B.n_reads + K1B_THREADS - 1) / K1B_THREADS, (uint32_t)sm_count() * 8u);
-    launch_dependent(k1b_walk, g2 ? g2 : 1u, K1B_THREADS, 0, st, B, P, use_k1c ? 1u : 0u);
+    launch_dependent(k1b_walk, g2 ? g2 : 1u, K1B_THREADS, 0, st, B, P);
 }
 
 }  // namespace exlr

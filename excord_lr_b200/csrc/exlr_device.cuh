@@ -36,7 +36,8 @@ struct Ctrl {
     uint32_t n_short;               // records kernel 1b walks itself (length of short_list)
     uint32_t ticket_c;              // dynamic tile ids of kernel 5a's chained scan
     uint32_t text_bytes;            // kernel 5a: bytes of the formatted lines
-    uint32_t pad[15];
+    uint32_t n_warp;                // records kernel 1b scans with a warp each (length of warp_list)
+    uint32_t pad[14];
 };
 static_assert(sizeof(Ctrl) == 128, "Ctrl is the 128-byte result header");
 
@@ -98,6 +99,7 @@ struct DevBatch {
     uint32_t* tile_cnt;     // [R] events in each tile's slice
     uint32_t* dirty_bits;   // [R/32] one bit per record: claimed by a thread of kernel 1b (zeroed with ctrl)
     uint32_t* short_list;   // [R] k1b_claim: claimed records walked by one thread each, any order (ctrl->n_short entries)
+    uint32_t* warp_list;    // [R] k1b_claim: claimed records of medium length, scanned by one warp each (ctrl->n_warp entries)
     uint32_t* long_list;    // [R] kernel 1b: claimed records too long for one thread, any order (ctrl->n_long entries)
     uint32_t* step_list;    // [max_ops/512 + 1] kernel 1a: the 512-op steps of the CIGAR stream that hold an event candidate, any order
     uint32_t raw_cap, prim_slots, capt_log2, slab;
