@@ -56,6 +56,7 @@ struct exlr_batch {
     void* h_slab = nullptr;                    // pinned: inputs
     void* h_out = nullptr;                     // pinned: ctrl + line_off + events
     Ctrl* h_ctrl = nullptr; uint32_t* h_line_off = nullptr; exlr_event* h_events = nullptr;
+    Ctrl* h_ctrl_dev = nullptr;                // device address of h_ctrl (mapped pinned memory): the result header is stored there by a kernel
     char* h_text = nullptr;                    // pinned: formatted lines (allocated with the batch when EXLR_OPT_DEVICE_FORMAT is set)
     bool formatted = false;                    // the last submit ran kernels 5a/5b
     void* d_slab = nullptr;                    // one device allocation, carved up below
@@ -239,10 +240,12 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     size_t oo = 0;
     auto ocarve = [&](size_t bytes) { size_t at = oo; oo = align_up(oo + bytes, A); return at; };
     const size_t o_ctrl = ocarve(sizeof(Ctrl)), o_loff = ocarve((R + 1) * 4), o_ev = ocarve(max_events * sizeof(exlr_event));
-    e = cudaHostAlloc(&b->h_out, oo, cudaHostAllocDefault);
+    e = cudaHostAlloc(&b->h_out, oo, cudaHostAllocMapped);
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostAlloc(outputs)"); }
     b->h_ctrl = (Ctrl*)((char*)b->h_out + o_ctrl); b->h_line_off = (uint32_t*)((char*)b->h_out + o_loff);
     b->h_events = (exlr_event*)((char*)b->h_out + o_ev);
+    e = cudaHostGetDevicePointer((void**)&b->h_ctrl_dev, b->h_ctrl, 0);
+    if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostGetDevicePointer"); }
     if (c->device_format) {
         e = cudaHostAlloc((void**)&b->h_text, max_events * kTextBytesPerLine + 16, cudaHostAllocDefault);
         if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostAlloc(text)"); }
@@ -411,8 +414,8 @@ static int run_kernels(exlr_batch* b)
     launch_k4b(d, c->dparams, st); b->launches++;
     b->formatted = d.text_off != nullptr;
     if (b->formatted) { launch_k5(d, st); b->launches += 2; }      // (no event in between: 5a is placed while 4b drains)
+    launch_header(d, b->h_ctrl_dev, st); b->launches++;            // the result header, stored straight into pinned host memory
     CK(cudaEventRecord(b->ev[EV_K4B], st));
-    CK(cudaMemcpyAsync(b->h_ctrl, d.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(b->ev[EV_D2H], st));
     CK(cudaGetLastError());
     return EXLR_OK;

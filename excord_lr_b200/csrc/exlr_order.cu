@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(256) k5b_format(DevBatch B)
 {
     __shared__ __align__(16) uint8_t s_stage[8][K5B_STAGE];
     griddep_wait();                                    // kernel 5a's offsets
+    griddep_launch();
     CtaTrace tr(B, 13);
     const uint32_t n = min(B.ctrl->n_events, B.max_events), lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
@@ -353,6 +354,17 @@ __global__ void __launch_bounds__(256) k5b_format(DevBatch B)
         }
     }
     tr.end();
+}
+
+// ======================================================================================
+// result header: the 128-byte control block goes to (mapped, pinned) host memory by eight 16-byte stores of one warp, placed
+// while the last kernel drains -- a cudaMemcpyAsync of 128 bytes costs ~9 us of stream time, this ~3
+// ======================================================================================
+__global__ void __launch_bounds__(32) k6_header(const Ctrl* ctrl, Ctrl* host_ctrl)
+{
+    griddep_wait();
+    if (threadIdx.x < sizeof(Ctrl) / 16) reinterpret_cast<uint4*>(host_ctrl)[threadIdx.x] = reinterpret_cast<const uint4*>(ctrl)[threadIdx.x];
+    __threadfence_system();
 }
 
 // ======================================================================================
@@ -396,6 +408,8 @@ void launch_k4b(const DevBatch& B, const DevParams& P, cudaStream_t st)
     const uint32_t grid = min((n + 255u) / 256u, (uint32_t)sm_count() * 8u);
     launch_dependent(k4b_place, grid ? grid : 1u, 256, 0, st, B, P);
 }
+
+void launch_header(const DevBatch& B, Ctrl* host_ctrl_dev, cudaStream_t st) { launch_dependent(k6_header, 1u, 32u, 0, st, (const Ctrl*)B.ctrl, host_ctrl_dev); }
 
 uint32_t scan_tiles(uint32_t n_reads) { return (n_reads + SCAN_TILE - 1) / SCAN_TILE; }
 uint32_t text_scan_tiles(uint32_t max_events) { return (max_events + SCAN_THREADS - 1) / SCAN_THREADS + 1; }

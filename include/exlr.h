@@ -147,8 +147,8 @@ typedef struct exlr_timing {
     float sa_parse_ms;  /* kernel 3b: SA parse, sort, large-INS + split events  */
     float scan_ms;      /* kernel 4a: per-record line counts -> offsets         */
     float place_ms;     /* kernel 4b: ordered compaction into the event buffer  */
-    float kernels_ms;   /* first kernel start -> last kernel end                */
-    float d2h_ms;       /* device->host copies of the results                   */
+    float kernels_ms;   /* first kernel start -> last kernel end (the last kernel stores the result header in pinned host memory) */
+    float d2h_ms;       /* what the stream still does after the last kernel (nothing but the closing event since the header is a kernel) */
     uint32_t launches;  /* kernels launched by this submit                      */
     float screen_ms;    /* kernel 1a (event screen in front of kernel 1), part of cigar_ms; 0 when it did not run */
 } exlr_timing;
