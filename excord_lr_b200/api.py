@@ -27,6 +27,8 @@ EXLR_OPT_K1_WAVES = 5
 EXLR_OPT_STAGE_TIMING = 6
 EXLR_OPT_TRACE = 7
 EXLR_OPT_DEVICE_FORMAT = 8
+EXLR_OPT_K1A_CTAS_PER_SM = 9
+EXLR_OPT_LONG_RECORDS = 10
 # see EXLR_OPT_CIGAR_KERNEL in include/exlr.h
 CIGAR_KERNEL_AUTO, CIGAR_KERNEL_WARP, CIGAR_KERNEL_FLAT, CIGAR_KERNEL_SCREEN = 0, 1, 2, 3
 
@@ -289,7 +291,7 @@ class Extractor:
 
 
 def extract(hb: HostBatch, params: ExlrParams, device: int = 0, cigar_kernel: int = CIGAR_KERNEL_AUTO,
-            reads_per_cta: int = 0, verbose: bool = False, max_events: int = 0, grow: bool = True, device_format: bool = False):
+            reads_per_cta: int = 0, verbose: bool = False, max_events: int = 0, grow: bool = True, device_format: bool = False, long_records: int = 0):
     """One-shot: host batch -> (Result, formatted lines).  Host buffers in, host buffers out.
     If the event buffers turn out too small the batch is re-run once with the size the device reported.
     device_format: also format the (non-verbose) lines on the device; they come back as Result.device_text."""
@@ -298,6 +300,7 @@ def extract(hb: HostBatch, params: ExlrParams, device: int = 0, cigar_kernel: in
         ex.set_option(EXLR_OPT_CIGAR_KERNEL, cigar_kernel)
         ex.set_option(EXLR_OPT_READS_PER_CTA, reads_per_cta)
         ex.set_option(EXLR_OPT_DEVICE_FORMAT, int(device_format))
+        ex.set_option(EXLR_OPT_LONG_RECORDS, long_records)
         for attempt in range(5):
             b = ex.batch_for(hb, max_events)
             try:

@@ -43,6 +43,7 @@ struct exlr_ctx {
     int k1_ctas = 0;                           // EXLR_OPT_K1_CTAS_PER_SM (0 = 3 when overlapping, which leaves room for the SA branch, else 4)
     uint32_t reads_per_cta = 0;                // EXLR_OPT_READS_PER_CTA (0 = auto)
     int device_format = 0;                     // EXLR_OPT_DEVICE_FORMAT: kernels 5a/5b write the output lines; read with exlr_wait_text
+    int long_records = 0;                      // EXLR_OPT_LONG_RECORDS: 0 auto (by mean CIGAR length), 1 never, 2 kernel 1c, 3 kernel 1d
     int skip_screen = 0;                       // auto mode: batches left to run without the screen pass (the last screened one was event-dense)
 };
 
@@ -186,6 +187,7 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
     case EXLR_OPT_READS_PER_CTA: if (value < 0 || value > 128) return EXLR_ERR_ARG; c->reads_per_cta = (uint32_t)value; return EXLR_OK;
     case EXLR_OPT_OVERLAP: c->overlap = value != 0; return EXLR_OK;
     case EXLR_OPT_DEVICE_FORMAT: c->device_format = value != 0; return EXLR_OK;
+    case EXLR_OPT_LONG_RECORDS: if (value < 0 || value > 3) return EXLR_ERR_ARG; c->long_records = (int)value; return EXLR_OK;
     case EXLR_OPT_K1A_CTAS_PER_SM: if (value < 1 || value > 8) return EXLR_ERR_ARG; set_k1a_ctas_per_sm((int)value); return EXLR_OK;
     case EXLR_OPT_TRACE: if (value < 0 || value > 7) return EXLR_ERR_ARG; c->trace = (int)value; return EXLR_OK;
     case EXLR_OPT_STAGE_TIMING: c->stage_timing = value != 0; return EXLR_OK;
@@ -263,7 +265,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     const size_t d_ctrl = dcarve(sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes + (size_t)ttiles * 8);   // ctrl | scan_a | scan_b | dirty_bits | scan_c : one memset
     const size_t d_cigar = dcarve((max_ops + 4) * 4 + 16), d_coff = dcarve((R + 1) * 8), d_pos = dcarve(R * 4), d_tid = dcarve(R * 4),
                  d_flag = dcarve(R * 2), d_mapq = dcarve(R), d_kind = dcarve(R), d_soff = dcarve((R + 1) * 4), d_sab = dcarve(max_sa_bytes + 16),
-                 d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_slist = dcarve((max_ops / 512 + 16) * 4), d_llist = dcarve(R * 4), d_shlist = dcarve(R * 4), d_wlist = dcarve(R * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
+                 d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_slist = dcarve((max_ops / 512 + 16) * 4), d_ssum = dcarve((max_ops / 512 + 16) * 4), d_sflag = dcarve(max_ops / 512 + 16), d_llist = dcarve(R * 4), d_shlist = dcarve(R * 4), d_wlist = dcarve(R * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
                  d_raw = dcarve((max_events + kRawHeadroom) * sizeof(RawEv)), d_saev = dcarve(max_events * sizeof(exlr_event)),
                  d_pool = dcarve(pool_cap * sizeof(Seg)), d_dbg = dcarve(8192 * 32), d_toff = dcarve(c->device_format ? (max_events + 1) * 4 : 0), d_text = dcarve(text_cap + 16), d_loff = dcarve((R + 1) * 4), d_ev = dcarve(max_events * sizeof(exlr_event));
     e = cudaMalloc(&b->d_slab, dof);
@@ -272,7 +274,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     DevBatch& v = b->dv;
     v.ctrl = (Ctrl*)(ds + d_ctrl);
     v.scan_a = (unsigned long long*)(ds + d_ctrl + sizeof(Ctrl)); v.scan_b = v.scan_a + tiles;
-    v.dirty_bits = (uint32_t*)(v.scan_b + tiles); v.step_list = (uint32_t*)(ds + d_slist); v.long_list = (uint32_t*)(ds + d_llist); v.short_list = (uint32_t*)(ds + d_shlist); v.warp_list = (uint32_t*)(ds + d_wlist);
+    v.dirty_bits = (uint32_t*)(v.scan_b + tiles); v.step_list = (uint32_t*)(ds + d_slist); v.step_sum = (uint32_t*)(ds + d_ssum); v.step_flag = (uint8_t*)(ds + d_sflag); v.long_list = (uint32_t*)(ds + d_llist); v.short_list = (uint32_t*)(ds + d_shlist); v.warp_list = (uint32_t*)(ds + d_wlist);
     v.scan_c = (unsigned long long*)((char*)v.dirty_bits + bits_bytes);
     v.text_off = c->device_format ? (uint32_t*)(ds + d_toff) : nullptr; v.text = (uint8_t*)(ds + d_text); v.text_cap = (uint32_t)text_cap;
     b->ctrl_bytes = sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes + (size_t)ttiles * 8;
@@ -391,13 +393,15 @@ static int run_kernels(exlr_batch* b)
         if (overlap) CK(cudaStreamWaitEvent(s1, b->ev_fork, 0));
         if (c->stage_timing) CK(cudaEventRecord(b->ev_k1_begin, s1));
         if (b->screened) {
-            launch_k1a(d, c->dparams, b->n_ops, s1); b->launches++;
+            // Batches of long records (ONT-like): kernel 1a also leaves per-step sums, and the long records behind it are resolved by
+            // kernel 1d from those sums (EXLR_OPT_LONG_RECORDS=2: by kernel 1c, the flat block scan of the listed records).  In a
+            // batch of short records the odd long one is scanned by a warp of kernel 1b, and the chain is one launch shorter.
+            const bool long_batch = c->long_records ? c->long_records >= 2 : b->n_ops / b->n_reads > kLongRecordMeanOps;
+            const bool two_level = long_batch && c->long_records != 2;
+            launch_k1a(d, c->dparams, b->n_ops, two_level, s1); b->launches++;
             if (c->stage_timing) CK(cudaEventRecord(b->ev_k1_mid, s1));
-            // kernel 1c (flat block scan of the long records) is only launched for batches of long records; in a batch of short ones
-            // the odd long record is scanned by a warp of kernel 1b, and the chain is one launch shorter
-            const bool use_k1c = b->n_ops / b->n_reads > kLongRecordMeanOps;
-            launch_k1b(d, c->dparams, b->n_ops, use_k1c, s1); b->launches += 2;
-            if (use_k1c) { launch_k1c(d, c->dparams, s1); b->launches++; }
+            launch_k1b(d, c->dparams, b->n_ops, long_batch, s1); b->launches += 2;
+            if (long_batch) { if (two_level) launch_k1d(d, c->dparams, s1); else launch_k1c(d, c->dparams, s1); b->launches++; }
         } else {
             launch_k1(d, c->dparams, variant, rpc, s1); b->launches++;
         }

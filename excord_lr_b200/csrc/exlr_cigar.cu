@@ -524,9 +524,12 @@ static constexpr int K1A_CTAS = 8;                     // CTAs per SM: full occu
 static constexpr uint32_t K1A_STEP_OPS = 32 * K1A_VEC * 4;
 
 // One warp step: screen the 512 ops held in q; true (warp-uniform) when some lane saw an event candidate or an unknown op.
-__device__ __forceinline__ bool k1a_step(uint32_t imin16, uint32_t lut_lo, uint32_t lut_hi, const uint4 (&q)[K1A_VEC])
+// SUMS: also the step's reference-consuming length (u32 wrapping, main.rs:528-545) -- what lets kernel 1d place an event of a
+// long record without rescanning the record.
+template <bool SUMS>
+__device__ __forceinline__ bool k1a_step(uint32_t imin16, uint32_t lut_lo, uint32_t lut_hi, const uint4 (&q)[K1A_VEC], uint32_t* step_sum)
 {
-    uint32_t sus = 0, flags = 0;
+    uint32_t sus = 0, flags = 0, tsum = 0;
 #pragma unroll
     for (int k = 0; k < K1A_VEC; k++) {
         const uint32_t vv[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
@@ -536,11 +539,18 @@ __device__ __forceinline__ bool k1a_step(uint32_t imin16, uint32_t lut_lo, uint3
             asm("prmt.b32 %0, %1, %2, %3;" : "=r"(f) : "r"(lut_lo), "r"(lut_hi), "r"(vv[j]));
             flags |= f;
             asm("{\n.reg .pred p;\nsetp.ge.u32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(sus) : "r"(vv[j]), "r"(imin16), "r"(f));
+            if (SUMS) asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(tsum) : "r"(f & 1u), "r"(vv[j] >> 4));
         }
+    }
+    if (SUMS) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, d);
+        *step_sum = tsum;
     }
     return __any_sync(0xffffffffu, ((sus & 2u) | (flags & 0x40u)) != 0u);
 }
 
+template <bool SUMS>
 __global__ void __launch_bounds__(K1A_THREADS, K1A_CTAS) k1a_screen(DevBatch B, DevParams P, unsigned long long n_ops)
 {
     const uint32_t lane = threadIdx.x & 31;
@@ -548,10 +558,9 @@ __global__ void __launch_bounds__(K1A_THREADS, K1A_CTAS) k1a_screen(DevBatch B, 
     griddep_launch();                                  // kernel 1b may be placed; it waits for this grid before it reads anything
     CtaTrace tr(B, 8);
     const uint32_t imin16 = P.indel_min >= (1u << 28) ? 0xffffffffu : (P.indel_min << 4);
-    const uint32_t nvec = (uint32_t)((n_ops + 3ull) / 4ull);               // < 2^30 (host); the cigar buffer is padded by 16 bytes
+    const uint32_t nvec = (uint32_t)((n_ops + 3ull) / 4ull);               // < 2^31 (host); the cigar buffer is padded by 16 bytes
     const uint4* cig = reinterpret_cast<const uint4*>(B.cigar);
     // Warp steps are dealt round robin over all warps of the grid (event-dense genome regions are contiguous in the array).
-    // The last vector may hold padding past the last op: a false flag there only costs kernel 1b a look.
     const uint32_t wstep = (nthreads >> 5) * (32 * K1A_VEC);
     uint32_t lut_lo, lut_hi;                                                // the op table, pinned in two registers
     asm volatile("mov.u32 %0, %2;\n\tmov.u32 %1, %3;" : "=r"(lut_lo), "=r"(lut_hi) : "n"(K1_LUT_LO), "n"(K1_LUT_HI));
@@ -570,14 +579,25 @@ __global__ void __launch_bounds__(K1A_THREADS, K1A_CTAS) k1a_screen(DevBatch B, 
     for (uint32_t v0 = gw * (32 * K1A_VEC); v0 < nvec; v0 += wstep, it++) {
         const uint4* p = cig + v0 + lane;
         uint4 q[K1A_VEC];
-        if (v0 + 32 * K1A_VEC <= nvec) {
+        if ((unsigned long long)(v0 + 32 * K1A_VEC) * 4ull <= n_ops) {      // every op of the step exists
 #pragma unroll
             for (int k = 0; k < K1A_VEC; k++) q[k] = __ldg(p + 32 * k);
-        } else {
+        } else {                                                            // the last step: what lies past the last op reads as 0M
 #pragma unroll
-            for (int k = 0; k < K1A_VEC; k++) q[k] = v0 + 32 * k + lane < nvec ? __ldg(p + 32 * k) : make_uint4(0u, 0u, 0u, 0u);
+            for (int k = 0; k < K1A_VEC; k++) {
+                const uint32_t vi = v0 + 32 * k + lane;
+                q[k] = vi < nvec ? __ldg(p + 32 * k) : make_uint4(0u, 0u, 0u, 0u);
+                const unsigned long long e0 = (unsigned long long)vi * 4ull;
+                if (e0 + 1 > n_ops) q[k].x = 0u;
+                if (e0 + 2 > n_ops) q[k].y = 0u;
+                if (e0 + 3 > n_ops) q[k].z = 0u;
+                if (e0 + 4 > n_ops) q[k].w = 0u;
+            }
         }
-        hitmask |= (k1a_step(imin16, lut_lo, lut_hi, q) ? 1u : 0u) << (it & 31u);
+        uint32_t ssum = 0;
+        const bool hit = k1a_step<SUMS>(imin16, lut_lo, lut_hi, q, &ssum);
+        if (SUMS && lane == 0) { const uint32_t st = v0 / (32 * K1A_VEC); B.step_sum[st] = ssum; B.step_flag[st] = hit ? 1 : 0; }
+        hitmask |= (hit ? 1u : 0u) << (it & 31u);
         if ((it & 31u) == 31u) { append(hitmask, it - 31u); hitmask = 0; }
     }
     append(hitmask, it & ~31u);
@@ -785,6 +805,151 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_walk(DevBatch B, DevParams P)
 }
 
 // ======================================================================================
+// kernel 1d: the long records of a long-record batch, one warp each, WITHOUT rescanning them
+//
+// Kernel 1a<SUMS> left two things per 512-op step: its reference-consuming length and whether it holds an event candidate.  For a
+// record that spans steps s0..s1 that is all that is needed: left_consume of an event = (partial sum of s0 inside the record) +
+// (sums of the whole steps in between) + (prefix inside the event's own step); total_consume likewise.  So a warp scans only the
+// record's two ragged end steps and its flagged steps (for an ONT record with one event: ~3 of its ~7..200 steps), 512 ops per
+// scan with four 128-bit loads per lane, and events come out in CIGAR order with their sequence numbers and merge predicates
+// (main.rs:523-600, 612-635, 673-678).  Measured on the ONT config: the flat block scan of the same records (kernel 1c) took 527 us.
+// ======================================================================================
+struct K1dState { uint32_t cnt, info, has_prev, pL, pn, pdel; };   // warp-uniform: events so far, flags, the previous event
+
+// Scan the part of step `s` that lies inside the record's ops [o0, o1).  Lane l holds ops s*512 + 16 l .. + 15.
+// Returns the reference-consuming length of that part.  EMIT: also writes the raw events of the part, in order, with
+// `carry` = left_consume at the part's first op.
+template <bool EMIT>
+__device__ __noinline__ uint32_t k1d_scan_step(const DevBatch& B, const DevParams& P, uint32_t imin16, uint32_t s, unsigned long long o0,
+                                                  unsigned long long o1, uint32_t carry, uint32_t pos2, uint32_t r, K1dState& S)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const unsigned long long sb = (unsigned long long)s * K1A_STEP_OPS;                       // the step's first op
+    // the record's part of the step as op numbers inside the step, [lo, hi) within 0..512
+    const uint32_t lo = o0 > sb ? (uint32_t)(o0 - sb) : 0u, hi = o1 < sb + K1A_STEP_OPS ? (uint32_t)(o1 - sb) : K1A_STEP_OPS;
+    const uint32_t e0 = lane * 16u;                                                             // my first op inside the step
+    const uint4* c4 = reinterpret_cast<const uint4*>(B.cigar) + (sb >> 2) + lane * 4u;
+    uint32_t v[16];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const bool any = e0 + 4u * k < hi && e0 + 4u * k + 4u > lo;                            // the vector overlaps the record
+        const uint4 q = any ? __ldg(c4 + k) : make_uint4(0u, 0u, 0u, 0u);
+        v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
+    uint32_t tot = 0, evm = 0, flags = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        if (e0 + i - lo >= hi - lo) v[i] = 0u;                                                  // outside the record: reads as 0M
+        uint32_t f;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(f) : "r"(K1_LUT_LO), "r"(K1_LUT_HI), "r"(v[i]));
+        flags |= f;
+        tot += (f & 1u) ? (v[i] >> 4) : 0u;
+        if ((f & 2u) && v[i] >= imin16) evm |= 1u << i;
+    }
+    uint32_t incl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+    const uint32_t part = __shfl_sync(0xffffffffu, incl, 31);
+    if (!EMIT) return part;
+    if (__any_sync(0xffffffffu, (flags & 0x40u) != 0u)) { if (flags & 0x40u) report(B.ctrl, r, RANK_CIGAR_OP); }   // rust-htslib panics on an unknown op
+    const uint32_t em = __ballot_sync(0xffffffffu, evm != 0u);
+    if (!em) return part;
+    // ranks and raw slots
+    const uint32_t mine = __popc(evm);
+    uint32_t rincl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, rincl, d); if (lane >= (uint32_t)d) rincl += o; }
+    const uint32_t n_ev = __shfl_sync(0xffffffffu, rincl, 31);
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&B.ctrl->n_raw, n_ev);
+    base = B.prim_slots + __shfl_sync(0xffffffffu, base, 0) + rincl - mine;
+    // first walk: my last event, for the lane above me; second walk: emit with the previous-event chain
+    uint32_t L = carry + incl - tot, lL = 0, ln = 0, ldel = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        uint32_t f;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(f) : "r"(K1_LUT_LO), "r"(K1_LUT_HI), "r"(v[i]));
+        if (evm & (1u << i)) { lL = L; ln = v[i] >> 4; ldel = (v[i] & 15u) == 2u; }
+        L += (f & 1u) ? (v[i] >> 4) : 0u;
+    }
+    const uint32_t lower = em & ((1u << lane) - 1u);
+    const int src = lower ? 31 - __clz(lower) : 0;
+    uint32_t pL = __shfl_sync(0xffffffffu, lL, src), pn = __shfl_sync(0xffffffffu, ln, src), pdel = __shfl_sync(0xffffffffu, ldel, src);
+    bool has_prev = lower != 0u;
+    if (!has_prev && S.has_prev) { pL = S.pL; pn = S.pn; pdel = S.pdel; has_prev = true; }
+    uint32_t seq = S.cnt + rincl - mine, info = 0, slot = base;
+    L = carry + incl - tot;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        uint32_t f;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(f) : "r"(K1_LUT_LO), "r"(K1_LUT_HI), "r"(v[i]));
+        if (evm & (1u << i)) {
+            const uint32_t len = v[i] >> 4, del = (v[i] & 15u) == 2u;
+            if (has_prev && del && pdel) {
+                if (seq == 1u && abs_diff(pos2 + L, pos2 + pL + pn) < P.merge_min) info |= K1_PAIR_MERGE;   // main.rs:615
+                if (abs_diff(pos2 + pL, pos2 + L + len) < P.merge_min) info |= K1_FAR_HIT;                  // main.rs:673-678
+            }
+            if (slot < B.raw_cap) {
+                uint4* d = reinterpret_cast<uint4*>(B.raw + slot);
+                d[0] = make_uint4(r, seq, L, len | (del << 31));
+                d[1] = make_uint4(has_prev ? pL : 0u, 0u, 0u, 0u);
+            } else B.ctrl->overflow = 1;
+            pL = L; pn = len; pdel = del; has_prev = true; seq++; slot++;
+        }
+        L += (f & 1u) ? (v[i] >> 4) : 0u;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) info |= __shfl_xor_sync(0xffffffffu, info, d);
+    const int top = 31 - __clz(em);                                                             // the step's last event becomes "previous"
+    S.pL = __shfl_sync(0xffffffffu, lL, top); S.pn = __shfl_sync(0xffffffffu, ln, top); S.pdel = __shfl_sync(0xffffffffu, ldel, top);
+    S.has_prev = 1; S.cnt += n_ev; S.info |= info;
+    return part;
+}
+
+__global__ void __launch_bounds__(256, 3) k1d_long(DevBatch B, DevParams P)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    griddep_wait();                                    // k1b's long list
+    griddep_launch();
+    CtaTrace tr(B, 11);
+    const uint32_t n_list = B.ctrl->n_long, nw = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t imin16 = P.indel_min >= (1u << 28) ? 0xffffffffu : (P.indel_min << 4);
+    for (uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; li < n_list; li += nw) {
+        const uint32_t r = B.long_list[li];
+        const unsigned long long o0 = B.cigar_off[r], o1 = B.cigar_off[r + 1];
+        const uint32_t pos2 = (uint32_t)B.pos[r];
+        const uint32_t s0 = (uint32_t)(o0 / K1A_STEP_OPS), s1 = (uint32_t)((o1 - 1ull) / K1A_STEP_OPS);       // o1 > o0: long records are not empty
+        K1dState S{0u, 0u, 0u, 0u, 0u, 0u};
+        uint32_t T;
+        if (s0 == s1) T = k1d_scan_step<true>(B, P, imin16, s0, o0, o1, 0u, pos2, r, S);
+        else {
+            const uint32_t first = k1d_scan_step<false>(B, P, imin16, s0, o0, o1, 0u, pos2, r, S);
+            const uint32_t last = k1d_scan_step<false>(B, P, imin16, s1, o0, o1, 0u, pos2, r, S);
+            uint32_t carry = 0;
+            for (uint32_t w0 = s0; w0 <= s1; w0 += 32u) {                                        // the record's steps, 32 at a time
+                const uint32_t s = w0 + lane;
+                const bool in = s <= s1;
+                const uint32_t val = !in ? 0u : (s == s0 ? first : (s == s1 ? last : B.step_sum[s]));
+                const bool flagged = in && B.step_flag[s] != 0;
+                uint32_t incl = val;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+                for (uint32_t m = __ballot_sync(0xffffffffu, flagged); m; m &= m - 1u) {            // only the flagged steps are looked at
+                    const int b = __ffs((int)m) - 1;
+                    const uint32_t at = carry + __shfl_sync(0xffffffffu, incl - val, b);
+                    k1d_scan_step<true>(B, P, imin16, w0 + (uint32_t)b, o0, o1, at, pos2, r, S);
+                }
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+                if (w0 + 32u < w0) break;                                                        // (u32 wrap guard)
+            }
+            T = carry;
+        }
+        if (lane == 0) B.k1[r] = make_uint2(T, (S.cnt & K1_CNT_MASK) | S.info);
+    }
+    tr.end();
+}
+
+// ======================================================================================
 // launchers
 // ======================================================================================
 static int g_k1_ctas_per_sm = 4;
@@ -841,17 +1006,25 @@ void launch_k1c(const DevBatch& B, const DevParams& P, cudaStream_t st)
     launch_dependent(k1_flat, grid ? grid : 1u, K1_THREADS, sizeof(K1Smem), st, B, P, 1u, B.n_reads, (const uint32_t*)B.long_list);
 }
 
+// kernel 1d: one warp per listed long record, one resident wave
+void launch_k1d(const DevBatch& B, const DevParams& P, cudaStream_t st)
+{
+    const uint32_t grid = min((B.n_reads + 7u) / 8u, (uint32_t)sm_count() * 8u);
+    launch_dependent(k1d_long, grid ? grid : 1u, 256u, 0, st, B, P);
+}
+
 // the screen pass (kernel 1a) and the resolution of its flagged steps (kernel 1b); n_ops < 2^33
 uint32_t k1a_steps(unsigned long long n_ops) { return (uint32_t)((n_ops + K1A_STEP_OPS - 1) / K1A_STEP_OPS); }
 
-void launch_k1a(const DevBatch& B, const DevParams& P, unsigned long long n_ops, cudaStream_t st)
+void launch_k1a(const DevBatch& B, const DevParams& P, unsigned long long n_ops, bool sums, cudaStream_t st)
 {
     const uint32_t steps = k1a_steps(n_ops);
     uint32_t grid = (steps + K1A_THREADS / 32 - 1) / (K1A_THREADS / 32);
     const uint32_t cap = (uint32_t)sm_count() * (uint32_t)g_k1a_ctas_per_sm;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    k1a_screen<<<grid, K1A_THREADS, 0, st>>>(B, P, n_ops);
+    if (sums) k1a_screen<true><<<grid, K1A_THREADS, 0, st>>>(B, P, n_ops);
+    else k1a_screen<false><<<grid, K1A_THREADS, 0, st>>>(B, P, n_ops);
 }
 
 void launch_k1b(const DevBatch& B, const DevParams& P, unsigned long long n_ops, bool use_k1c, cudaStream_t st)

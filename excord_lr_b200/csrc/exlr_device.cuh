@@ -101,6 +101,8 @@ struct DevBatch {
     uint32_t* short_list;   // [R] k1b_claim: claimed records walked by one thread each, any order (ctrl->n_short entries)
     uint32_t* warp_list;    // [R] k1b_claim: claimed records of medium length, scanned by one warp each (ctrl->n_warp entries)
     uint32_t* long_list;    // [R] kernel 1b: claimed records too long for one thread, any order (ctrl->n_long entries)
+    uint32_t* step_sum;     // [max_ops/512 + 1] kernel 1a<SUMS>: reference-consuming length of every 512-op step (long-record batches)
+    uint8_t* step_flag;     // [max_ops/512 + 1] kernel 1a<SUMS>: the step holds an event candidate
     uint32_t* step_list;    // [max_ops/512 + 1] kernel 1a: the 512-op steps of the CIGAR stream that hold an event candidate, any order
     uint32_t raw_cap, prim_slots, capt_log2, slab;
     exlr_event* sa_ev;      // [max_events] SA-derived events, per record contiguous
@@ -140,7 +142,8 @@ void launch_k0(const DevBatch& B, const DevParams& P, cudaStream_t st);
 void plan_k1(DevBatch& B, int variant, uint32_t rpc, uint32_t* tiles_out);
 void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc, cudaStream_t st);
 uint32_t k1a_steps(unsigned long long n_ops);
-void launch_k1a(const DevBatch& B, const DevParams& P, unsigned long long n_ops, cudaStream_t st);
+void launch_k1a(const DevBatch& B, const DevParams& P, unsigned long long n_ops, bool sums, cudaStream_t st);
+void launch_k1d(const DevBatch& B, const DevParams& P, cudaStream_t st);
 void launch_k1b(const DevBatch& B, const DevParams& P, unsigned long long n_ops, bool use_k1c, cudaStream_t st);
 void launch_k1c(const DevBatch& B, const DevParams& P, cudaStream_t st);
 void launch_k3a(const DevBatch& B, const DevParams& P, uint32_t mean_ops, cudaStream_t st);

@@ -168,6 +168,9 @@ typedef struct exlr_batch exlr_batch;
                                      k3b, k4a, k4b per CTA {start, mid, end}, 7 = timeline: entry k = {~first start, last end, -, CTAs} of kernel k */
 #define EXLR_OPT_STAGE_TIMING 6   /* 1 (default) = CUDA events between the kernels, so exlr_get_timing has per-stage times */
 #define EXLR_OPT_K1_WAVES 5       /* kernel 1 grid = SMs x CTAs/SM x waves (default 3) */
+#define EXLR_OPT_LONG_RECORDS 10   /* screened CIGAR path, records of more than 256 ops: 0 = auto (by the batch's mean CIGAR length),
+                                     1 = a warp of kernel 1b each, 2 = kernel 1c (flat block scan of the listed records),
+                                     3 = kernel 1d (from the per-step sums of kernel 1a, no rescan) */
 #define EXLR_OPT_K1A_CTAS_PER_SM 9 /* resident CTAs of kernel 1a per SM, 1..8 (default 8) */
 #define EXLR_OPT_DEVICE_FORMAT 8  /* 1 = batches allocated from now on also format the non-verbose output lines on the device
                                      (kernels 5a/5b, utils.rs:225-236, 269-280); read them with exlr_wait_text */

@@ -60,6 +60,6 @@ def check_result(hb: HostBatch, p: ExlrParams, res, text: bytes, verbose=False, 
     return want
 
 
-def gpu_check(hb: HostBatch, p: ExlrParams, cigar_kernel=0, reads_per_cta=0, verbose=False, label="", max_events=0):
-    res, text = api.extract(hb, p, 0, cigar_kernel, reads_per_cta, verbose, max_events, device_format=True)
+def gpu_check(hb: HostBatch, p: ExlrParams, cigar_kernel=0, reads_per_cta=0, verbose=False, label="", max_events=0, long_records=0):
+    res, text = api.extract(hb, p, 0, cigar_kernel, reads_per_cta, verbose, max_events, device_format=True, long_records=long_records)
     return check_result(hb, p, res, text, verbose, label), res

@@ -68,6 +68,27 @@ def test_dense_events_and_merge_rules(variant):
         gpu_check(hb, p, *variant, label=f"dense i{p.indel_min} m{p.merge_min} {variant}")
 
 
+@pytest.mark.parametrize("long_records", [1, 2, 3])
+def test_long_record_paths_behind_the_screen(long_records):
+    # records of more than 256 ops behind the event screen: a warp of kernel 1b each (1), kernel 1c = flat block scan of the
+    # listed records (2), kernel 1d = from the per-step sums of kernel 1a without rescanning (3)
+    import random
+    rng = random.Random(4242)
+    recs = []
+    for i in range(300):
+        n = rng.choice([1, 2, 3, 8, 40, 300, 1200, 3000])
+        recs.append(dict(tid=rng.randrange(len(RREF)), pos=rng.randint(0, 10 ** 8), flag=rng.choice([0, 16, 0, 256]), mapq=rng.choice([60, 60, 0]),
+                         cigar=clustered_dels(rng, n, rng.choice([0, 1, 4, 5, 6, 30, 600]), min_len=rng.choice([1, 50, 50]))))
+    hb = pack_records(recs, RREF)
+    for p in (ExlrParams.make(indel_min=50, merge_min=5), ExlrParams.make(indel_min=1, merge_min=5), ExlrParams.make(indel_min=80, merge_min=0),
+              ExlrParams.make(indel_min=50, merge_min=100)):
+        gpu_check(hb, p, 3, 0, label=f"long{long_records} i{p.indel_min} m{p.merge_min}", long_records=long_records)
+    for seed in (7, 8, 9):
+        gpu_check(rand_batch(seed, 300), rand_params(seed), 3, 0, label=f"long{long_records} seed{seed}", long_records=long_records)
+    hb = synth.config(2, 0.004)
+    gpu_check(hb, ExlrParams.make(**synth.CONFIGS[2]["params"]), 3, 0, label=f"long{long_records} ont", long_records=long_records)
+
+
 def test_empty_and_degenerate_batches():
     p = ExlrParams.make()
     # zero records
