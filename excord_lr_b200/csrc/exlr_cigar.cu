@@ -645,7 +645,8 @@ __device__ __forceinline__ uint32_t k1b_find_read(const unsigned long long* off,
 // walking inside the per-step warps ran at a third of the warp width, since most of a step's records belong to a neighbour).
 // ======================================================================================
 static constexpr int K1B_THREADS = 256;
-static constexpr uint32_t K1B_LONG = 256;              // ops; longer records are scanned by kernel 1c or by a warp
+static constexpr uint32_t K1B_LONG = 256;              // ops; longer records are scanned by kernel 1c / 1d or by a warp
+static constexpr uint32_t K1B_LONG_BATCH_CUT = 64;     // the same cut in a batch of long records (kernels 1c / 1d take the rest)
 static constexpr uint32_t K1B_EV = 4;                  // events per record parked in shared memory during the walk
 static constexpr int K1B_VEC = 4;                      // 128-bit loads in flight per walking thread
 
@@ -688,7 +689,9 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_claim(DevBatch B, DevParams P
             // launched.  (Measured on the ONT config: a warp per 3k-op record is latency-bound at ~1.8 us per 32 ops -- 1.1 ms for
             // the 58k records kernel 1c scans in 0.5 ms.)
             const unsigned long long len = o1 - o0;
-            const bool c_long = mine && len > K1B_LONG && use_k1c, c_warp = mine && len > K1B_LONG && !use_k1c, c_short = mine && len <= K1B_LONG;
+            // (in a batch of long records the thread walk is kept for really short ones: a 256-op walk is 16 dependent load rounds)
+            const uint32_t cut = use_k1c ? K1B_LONG_BATCH_CUT : K1B_LONG;
+            const bool c_long = mine && len > cut && use_k1c, c_warp = mine && len > cut && !use_k1c, c_short = mine && len <= cut;
             const uint32_t sm = __ballot_sync(0xffffffffu, c_short), wm = __ballot_sync(0xffffffffu, c_warp), lm = __ballot_sync(0xffffffffu, c_long);
             uint32_t base = 0;
             if (lane == 0 && sm) base = atomicAdd(&B.ctrl->n_short, (uint32_t)__popc(sm));

@@ -12,7 +12,7 @@ ex.set_option(api.EXLR_OPT_DEVICE_FORMAT, 1)
 ex.lib.exlr_get_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
 b = ex.batch_for(hb); b.upload()
 flush = torch.zeros(256 << 20, dtype=torch.uint8, device='cuda')
-names = {2: "k0_classify", 8: "k1a_screen", 9: "k1b_claim", 10: "k1b_walk", 11: "k1c/k1_flat", 3: "k3a_sa_cigar", 4: "k3b_sa_events",
+names = {2: "k0_classify", 8: "k1a_screen", 9: "k1b_claim", 10: "k1b_walk", 11: "k1c/k1d/k1_flat", 3: "k3a_sa_cigar", 4: "k3b_sa_events",
          5: "k4a_line_scan", 6: "k4b_place", 12: "k5a_line_bytes", 13: "k5b_format"}
 ex.set_option(api.EXLR_OPT_STAGE_TIMING, 0)
 ex.set_option(api.EXLR_OPT_TRACE, 7)
@@ -28,4 +28,4 @@ for overlap, k1a_ctas in ((1, 8), (1, 6), (1, 4), (0, 8)):
     t0 = min(r[0] for r in rows)
     print(f"overlap={overlap} k1a CTAs/SM {k1a_ctas}: kernels_ms {b.timing().kernels_ms * 1e3:.1f} us (first kernel start -> last kernel end, CUDA events)")
     for s, e, n, name in sorted(rows):
-        print(f"   {name:16s} CTAs {n:5d}  start {(s - t0) / 1e3:7.1f}  end {(e - t0) / 1e3:7.1f}  span {(e - s) / 1e3:6.1f} us")
+        print(f"   {name:18s} CTAs {n:5d}  start {(s - t0) / 1e3:7.1f}  end {(e - t0) / 1e3:7.1f}  span {(e - s) / 1e3:6.1f} us")
