@@ -325,7 +325,7 @@ def main():
     if rank == 0:
         peak, peak_src = load_peaks()
         # The CIGAR path is kernel 1a (streaming event screen: reads every op once, writes every record's 8-byte summary and the
-        # list of 512-op steps that hold an event candidate) followed by kernels 1b/1c on the records around those steps;
+        # list of 512-op steps that hold an event candidate) followed by kernels 1b/1d on the records around those steps;
         # event-dense batches get kernel 1 (flat block scan of everything) instead.  The roofline entry is the kernel that moves
         # the bytes: 1a reads 4 B/op of the 4 B/op + 28 B/record the whole step reads.  Its peak is the measured COPY bandwidth
         # (read + write); a read-mostly stream can exceed that figure, so frac may come out slightly above 1 on long-record batches.
@@ -353,8 +353,8 @@ def main():
             "config": {"workload": c["name"], "records_per_gpu": R, "cigar_ops_per_gpu": Cops, "sa_bytes_per_gpu": A,
                        "lines_per_gpu": n_events, "params": c["params"], "parallelism": f"dp{world} (record shards, no collective)",
                        "l2": "flushed (256 MB read) before every timed step; inputs are also larger than L2",
-                       "cigar_kernel": {0: "auto: streaming event screen (1a), then only the records around a candidate are scanned (1b thread per record, 1c flat block scan of long records)",
-                                        1: "warp per record", 2: "flat TMA-staged block scan of everything", 3: "screen + 1b + 1c (forced)"}[args.cigar_kernel]},
+                       "cigar_kernel": {0: "auto: streaming event screen (1a), then only the records around a candidate are scanned (1b: thread per short record; 1d: long records from 1a's per-step sums)",
+                                        1: "warp per record", 2: "flat TMA-staged block scan of everything", 3: "the screened path (forced)"}[args.cigar_kernel]},
             "e2e": {"value": e2e_value, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms_max / args.steps, "pipeline_parts": len(parts),
                     "h2d_gbs": h2d * args.steps / (e2e_ms_max / 1e3) / 1e9, "pcie_h2d_peak_gbs": pcie_h2d,
@@ -365,7 +365,7 @@ def main():
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k1_bytes, "avg_launch_ms": k1_avg_s * 1e3,
                          "measured": "live CUDA events in bench.py, same-stream steps (the kernel alone on the GPU)",
-                         "cigar_path": {"kernels": "k1a_screen + k1b_claim + k1b_walk + k1c (k1_flat over the listed long records)" if screened else rk_name,
+                         "cigar_path": {"kernels": "k1a_screen + k1b_claim + k1b_walk (+ k1d_long in long-record batches)" if screened else rk_name,
                                         "algorithmic_bytes": path_bytes, "ms": path_s * 1e3,
                                         "achieved": path_bytes / path_s / 1e9 if path_s > 0 else 0.0,
                                         "frac": (path_bytes / path_s / 1e9 / peak) if path_s > 0 else 0.0,

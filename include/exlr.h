@@ -158,9 +158,9 @@ typedef struct exlr_batch exlr_batch;
 
 /* options for exlr_set_option */
 #define EXLR_OPT_CIGAR_KERNEL 1  /* kernel 1 strategy.  0 = auto (default): a streaming event screen over the CIGAR array (kernel 1a), then only the
-                                    records around a candidate are scanned (1b: one thread per short record, 1c: flat block scan of
-                                    the long ones); event-dense batches fall back to 2.  Forced: 1 = warp per record;
-                                    2 = flat TMA-staged block scan of everything; 3 = screen + 1b + 1c */
+                                    records around a candidate are scanned (1b: one thread per short record; long ones by 1d from
+                                    the per-step sums of 1a, see EXLR_OPT_LONG_RECORDS); event-dense batches fall back to 2.
+                                    Forced: 1 = warp per record; 2 = flat TMA-staged block scan of everything; 3 = the screened path */
 #define EXLR_OPT_READS_PER_CTA 2 /* 0 = auto */
 #define EXLR_OPT_OVERLAP 3       /* 1 (default) = kernel 1 runs on a second stream beside kernels 0/3a/3b */
 #define EXLR_OPT_K1_CTAS_PER_SM 4 /* 1..4 CTAs of kernel 1 per SM; 0 (default) = 3 when overlapping, else 4 */
