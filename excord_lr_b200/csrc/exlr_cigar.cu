@@ -818,20 +818,23 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_walk(DevBatch B, DevParams P)
 // (main.rs:523-600, 612-635, 673-678).  Measured on the ONT config: the flat block scan of the same records (kernel 1c) took 527 us.
 // ======================================================================================
 struct K1dState { uint32_t cnt, info, has_prev, pL, pn, pdel; };   // warp-uniform: events so far, flags, the previous event
+// what a step scan needs of the batch, by value (the scan is out of line to bound the kernel's registers; a reference to the
+// kernel's whole parameter block would make every thread copy it to its stack)
+struct K1dArgs { const uint32_t* cigar; RawEv* raw; Ctrl* ctrl; uint32_t prim_slots, raw_cap, merge_min, imin16; };
 
 // Scan the part of step `s` that lies inside the record's ops [o0, o1).  Lane l holds ops s*512 + 16 l .. + 15.
 // Returns the reference-consuming length of that part.  EMIT: also writes the raw events of the part, in order, with
 // `carry` = left_consume at the part's first op.
 template <bool EMIT>
-__device__ __noinline__ uint32_t k1d_scan_step(const DevBatch& B, const DevParams& P, uint32_t imin16, uint32_t s, unsigned long long o0,
-                                                  unsigned long long o1, uint32_t carry, uint32_t pos2, uint32_t r, K1dState& S)
+__device__ __noinline__ uint32_t k1d_scan_step(const K1dArgs A, uint32_t s, unsigned long long o0, unsigned long long o1, uint32_t carry,
+                                               uint32_t pos2, uint32_t r, K1dState& S)
 {
     const uint32_t lane = threadIdx.x & 31;
     const unsigned long long sb = (unsigned long long)s * K1A_STEP_OPS;                       // the step's first op
     // the record's part of the step as op numbers inside the step, [lo, hi) within 0..512
     const uint32_t lo = o0 > sb ? (uint32_t)(o0 - sb) : 0u, hi = o1 < sb + K1A_STEP_OPS ? (uint32_t)(o1 - sb) : K1A_STEP_OPS;
     const uint32_t e0 = lane * 16u;                                                             // my first op inside the step
-    const uint4* c4 = reinterpret_cast<const uint4*>(B.cigar) + (sb >> 2) + lane * 4u;
+    const uint4* c4 = reinterpret_cast<const uint4*>(A.cigar) + (sb >> 2) + lane * 4u;
     uint32_t v[16];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -847,14 +850,14 @@ __device__ __noinline__ uint32_t k1d_scan_step(const DevBatch& B, const DevParam
         asm("prmt.b32 %0, %1, %2, %3;" : "=r"(f) : "r"(K1_LUT_LO), "r"(K1_LUT_HI), "r"(v[i]));
         flags |= f;
         tot += (f & 1u) ? (v[i] >> 4) : 0u;
-        if ((f & 2u) && v[i] >= imin16) evm |= 1u << i;
+        if ((f & 2u) && v[i] >= A.imin16) evm |= 1u << i;
     }
     uint32_t incl = tot;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
     const uint32_t part = __shfl_sync(0xffffffffu, incl, 31);
     if (!EMIT) return part;
-    if (__any_sync(0xffffffffu, (flags & 0x40u) != 0u)) { if (flags & 0x40u) report(B.ctrl, r, RANK_CIGAR_OP); }   // rust-htslib panics on an unknown op
+    if (__any_sync(0xffffffffu, (flags & 0x40u) != 0u)) { if (flags & 0x40u) report(A.ctrl, r, RANK_CIGAR_OP); }   // rust-htslib panics on an unknown op
     const uint32_t em = __ballot_sync(0xffffffffu, evm != 0u);
     if (!em) return part;
     // ranks and raw slots
@@ -864,8 +867,8 @@ __device__ __noinline__ uint32_t k1d_scan_step(const DevBatch& B, const DevParam
     for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, rincl, d); if (lane >= (uint32_t)d) rincl += o; }
     const uint32_t n_ev = __shfl_sync(0xffffffffu, rincl, 31);
     uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&B.ctrl->n_raw, n_ev);
-    base = B.prim_slots + __shfl_sync(0xffffffffu, base, 0) + rincl - mine;
+    if (lane == 0) base = atomicAdd(&A.ctrl->n_raw, n_ev);
+    base = A.prim_slots + __shfl_sync(0xffffffffu, base, 0) + rincl - mine;
     // first walk: my last event, for the lane above me; second walk: emit with the previous-event chain
     uint32_t L = carry + incl - tot, lL = 0, ln = 0, ldel = 0;
 #pragma unroll
@@ -889,14 +892,14 @@ __device__ __noinline__ uint32_t k1d_scan_step(const DevBatch& B, const DevParam
         if (evm & (1u << i)) {
             const uint32_t len = v[i] >> 4, del = (v[i] & 15u) == 2u;
             if (has_prev && del && pdel) {
-                if (seq == 1u && abs_diff(pos2 + L, pos2 + pL + pn) < P.merge_min) info |= K1_PAIR_MERGE;   // main.rs:615
-                if (abs_diff(pos2 + pL, pos2 + L + len) < P.merge_min) info |= K1_FAR_HIT;                  // main.rs:673-678
+                if (seq == 1u && abs_diff(pos2 + L, pos2 + pL + pn) < A.merge_min) info |= K1_PAIR_MERGE;   // main.rs:615
+                if (abs_diff(pos2 + pL, pos2 + L + len) < A.merge_min) info |= K1_FAR_HIT;                  // main.rs:673-678
             }
-            if (slot < B.raw_cap) {
-                uint4* d = reinterpret_cast<uint4*>(B.raw + slot);
+            if (slot < A.raw_cap) {
+                uint4* d = reinterpret_cast<uint4*>(A.raw + slot);
                 d[0] = make_uint4(r, seq, L, len | (del << 31));
                 d[1] = make_uint4(has_prev ? pL : 0u, 0u, 0u, 0u);
-            } else B.ctrl->overflow = 1;
+            } else A.ctrl->overflow = 1;
             pL = L; pn = len; pdel = del; has_prev = true; seq++; slot++;
         }
         L += (f & 1u) ? (v[i] >> 4) : 0u;
@@ -916,7 +919,7 @@ __global__ void __launch_bounds__(256, 3) k1d_long(DevBatch B, DevParams P)
     griddep_launch();
     CtaTrace tr(B, 11);
     const uint32_t n_list = B.ctrl->n_long, nw = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t imin16 = P.indel_min >= (1u << 28) ? 0xffffffffu : (P.indel_min << 4);
+    const K1dArgs A{B.cigar, B.raw, B.ctrl, B.prim_slots, B.raw_cap, P.merge_min, P.indel_min >= (1u << 28) ? 0xffffffffu : (P.indel_min << 4)};
     for (uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; li < n_list; li += nw) {
         const uint32_t r = B.long_list[li];
         const unsigned long long o0 = B.cigar_off[r], o1 = B.cigar_off[r + 1];
@@ -924,10 +927,10 @@ __global__ void __launch_bounds__(256, 3) k1d_long(DevBatch B, DevParams P)
         const uint32_t s0 = (uint32_t)(o0 / K1A_STEP_OPS), s1 = (uint32_t)((o1 - 1ull) / K1A_STEP_OPS);       // o1 > o0: long records are not empty
         K1dState S{0u, 0u, 0u, 0u, 0u, 0u};
         uint32_t T;
-        if (s0 == s1) T = k1d_scan_step<true>(B, P, imin16, s0, o0, o1, 0u, pos2, r, S);
+        if (s0 == s1) T = k1d_scan_step<true>(A, s0, o0, o1, 0u, pos2, r, S);
         else {
-            const uint32_t first = k1d_scan_step<false>(B, P, imin16, s0, o0, o1, 0u, pos2, r, S);
-            const uint32_t last = k1d_scan_step<false>(B, P, imin16, s1, o0, o1, 0u, pos2, r, S);
+            const uint32_t first = k1d_scan_step<false>(A, s0, o0, o1, 0u, pos2, r, S);
+            const uint32_t last = k1d_scan_step<false>(A, s1, o0, o1, 0u, pos2, r, S);
             uint32_t carry = 0;
             for (uint32_t w0 = s0; w0 <= s1; w0 += 32u) {                                        // the record's steps, 32 at a time
                 const uint32_t s = w0 + lane;
@@ -940,7 +943,7 @@ __global__ void __launch_bounds__(256, 3) k1d_long(DevBatch B, DevParams P)
                 for (uint32_t m = __ballot_sync(0xffffffffu, flagged); m; m &= m - 1u) {            // only the flagged steps are looked at
                     const int b = __ffs((int)m) - 1;
                     const uint32_t at = carry + __shfl_sync(0xffffffffu, incl - val, b);
-                    k1d_scan_step<true>(B, P, imin16, w0 + (uint32_t)b, o0, o1, at, pos2, r, S);
+                    k1d_scan_step<true>(A, w0 + (uint32_t)b, o0, o1, at, pos2, r, S);
                 }
                 carry += __shfl_sync(0xffffffffu, incl, 31);
                 if (w0 + 32u < w0) break;                                                        // (u32 wrap guard)
