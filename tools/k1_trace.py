@@ -1,12 +1,14 @@
+"""Per-CTA timeline of k1_flat (EXLR_OPT_TRACE = 1, flat block scan of every tile) for 1 and 3 waves of CTAs."""
 import sys, ctypes as C
 sys.path.insert(0,'/root/repo')
 import numpy as np, torch
 from excord_lr_b200 import api, synth
 from excord_lr_b200.batch import ExlrParams
 hb=synth.config(1,1.0); p=ExlrParams.make(**synth.CONFIGS[1]['params'])
-ex=api.Extractor(p,hb.ref_names,0); ex.set_option(3,0); ex.set_option(7,1)
+ex=api.Extractor(p,hb.ref_names,0); ex.set_option(api.EXLR_OPT_OVERLAP,0); ex.set_option(api.EXLR_OPT_TRACE,1)
+ex.set_option(api.EXLR_OPT_CIGAR_KERNEL, api.CIGAR_KERNEL_FLAT)      # the per-CTA trace of k1_flat (flat block scan of every tile)
 for waves in (1,3):
-    ex.set_option(5,waves)
+    ex.set_option(api.EXLR_OPT_K1_WAVES,waves)
     b=ex.batch_for(hb); b.upload()
     flush=torch.zeros(256<<20,dtype=torch.uint8,device='cuda')
     for i in range(4):
