@@ -282,9 +282,12 @@ __device__ __forceinline__ bool dev_parse_piece_fast(const uint8_t* p /* staged 
     const uint32_t sc = i < e ? (uint32_t)p[i] : 0u, sc2 = i + 1u < e ? (uint32_t)p[i + 1] : 0u;   // strand
     ok &= (sc == '+' || sc == '-') && sc2 == ',';
     i += 2;
-    // CIGAR text (utils.rs:88-117, 12-42): the same step for every byte up to the comma
-    uint32_t sS = 0, sH = 0, sD = 0, sM = 0, sE = 0, sX = 0, nops = 0, n = 0, bad = 0;
-    unsigned long long key = 0; bool seenM = false;
+    // CIGAR text (utils.rs:88-117, 12-42): the same step for every byte up to the comma.  The op branch is taken by a few lanes
+    // at a time, so it is kept short: the op letter selects its classes from bit masks indexed by (c - '='), lengths are
+    // multiplied by the class bit.  With at most 15 ops of less than 2^28 each no sum can wrap a u32, so one accumulator
+    // serves D + M + = + X (split_read_event.rs:23-28); longer CIGARs or lengths take the exact parser.
+    //   = D H I M N P S X  ->  c - '=' = 0 7 11 12 16 17 19 22 27
+    uint32_t ref = 0, sS = 0, sH = 0, key = 0, seenM = 0, nops = 0, n = 0, bad = 0, big = 0;
     nd = 0;
     while (i < e) {
         const uint32_t c = p[i];
@@ -292,18 +295,20 @@ __device__ __forceinline__ bool dev_parse_piece_fast(const uint8_t* p /* staged 
         const uint32_t d = c - '0';
         if (d <= 9u) { n = n * 10u + d; nd++; }
         else {
-            const uint32_t x = c - '=';                                         // = D H I M N P S X  ->  0 7 11 12 16 17 19 22 27
-            bad |= (x >= 28u || !((0x84B1881u >> (x & 31u)) & 1u) || nd - 1u >= 9u) ? 1u : 0u;
-            sM += c == 'M' ? n : 0u; sS += c == 'S' ? n : 0u; sD += c == 'D' ? n : 0u;
-            sH += c == 'H' ? n : 0u; sE += c == '=' ? n : 0u; sX += c == 'X' ? n : 0u;
-            if (!seenM && x < 28u && ((0x8401001u >> x) & 1u)) key += n;        // = I S X before the first M (utils.rs:33)
-            seenM |= c == 'M';
+            const uint32_t x = c - '=', xs = x & 31u, in = x < 28u ? 1u : 0u;   // `in` voids the class bits of bytes beyond 'X'
+            bad |= (((0x84B1881u >> xs) & in) ^ 1u) | (nd - 1u >= 9u ? 1u : 0u);
+            big |= n;
+            ref += n * ((0x8010081u >> xs) & in);                               // = D M X
+            sS += n * ((0x0400000u >> xs) & in);
+            sH += n * ((0x0000800u >> xs) & in);
+            key += n * ((0x8401001u >> xs) & in & (seenM ^ 1u));                // = I S X before the first M (utils.rs:33)
+            seenM |= (0x0010000u >> xs) & in;
             n = 0; nd = 0; nops++;
         }
         i++;
     }
     __syncwarp(m);
-    ok &= !bad && nd == 0u && nops != 0u && i < e;                             // ends at the comma, right after an op
+    ok &= !bad && nd == 0u && nops - 1u < 15u && (big >> 28) == 0u && i < e;   // ends at the comma, right after an op
     i++;
     uint32_t mq = 0;                                                           // mapq: u8
     nd = 0;
@@ -321,7 +326,7 @@ __device__ __forceinline__ bool dev_parse_piece_fast(const uint8_t* p /* staged 
     out->chrom_ref = 0x80000000u | (cb + bias);
     out->chrom_len = ce - cb;
     out->start = (int64_t)pos - 1;
-    out->end = out->start + (int64_t)sD + (int64_t)sM + (int64_t)sE + (int64_t)sX;
+    out->end = out->start + (int64_t)ref;
     out->key = (int64_t)key;
     out->clip_big = (sS > P.ins_clip_min || sH > P.ins_clip_min) ? 1u : 0u;
     out->strand_neg = sc == '-';
