@@ -1,5 +1,6 @@
-"""Small batches through every kernel path, for compute-sanitizer:
-   compute-sanitizer --tool memcheck python tools/sanitize_step.py   (also --tool racecheck / initcheck)"""
+"""Small batches through every kernel path (all CIGAR strategies x long-record paths, device formatting), for compute-sanitizer:
+   compute-sanitizer --tool memcheck python tools/sanitize_step.py   (also --tool racecheck / initcheck)
+(compute-sanitizer is closed on the pool this round was measured on; the same batches run as parity tests in tests/.)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
