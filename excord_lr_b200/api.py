@@ -57,7 +57,7 @@ class _Views(C.Structure):
 class _Result(C.Structure):
     _fields_ = [("status", C.c_int32), ("err_read", C.c_uint32), ("n_reads", C.c_uint64), ("n_events", C.c_uint64),
                 ("events", C.c_void_p), ("line_off", C.c_void_p), ("n_kept", C.c_uint64), ("n_sa_reads", C.c_uint64),
-                ("n_cap_dropped", C.c_uint64), ("n_ops", C.c_uint64)]
+                ("n_cap_dropped", C.c_uint64), ("n_ops", C.c_uint64), ("n_err_lines", C.c_uint64)]
 
 
 class Timing(C.Structure):
@@ -127,6 +127,7 @@ class Result:
         self.n_reads, self.n_events = int(raw.n_reads), int(raw.n_events)
         self.n_kept, self.n_sa_reads = int(raw.n_kept), int(raw.n_sa_reads)
         self.n_cap_dropped, self.n_ops = int(raw.n_cap_dropped), int(raw.n_ops)
+        self.n_err_lines = int(raw.n_err_lines)
         self._raw = raw
         if resident:
             self.events, self.line_off = None, None
@@ -136,6 +137,14 @@ class Result:
         lo = np.frombuffer((C.c_char * ((self.n_reads + 1) * 4)).from_address(raw.line_off), np.uint32)
         self.events = ev.copy() if copy else ev
         self.line_off = lo.copy() if copy else lo
+
+
+    def n_valid_lines(self) -> int:
+        """Lines the reference writes for this batch: all of them, or on a per-record panic (status <= -10) the lines of
+        the records before err_read plus the ones that record itself had written by then."""
+        if self.status > -10:
+            return self.n_events
+        return int(self.line_off[self.err_read]) + self.n_err_lines
 
 
 class DeviceBatch:
@@ -316,7 +325,7 @@ def extract(hb: HostBatch, params: ExlrParams, device: int = 0, cigar_kernel: in
                     continue
                 k = res.n_events
                 if res.status <= -10:
-                    k = int(res.line_off[res.err_read])     # lines of the records before the failing one
+                    k = res.n_valid_lines()                 # lines the reference had written when it panicked
                 text = b.format_lines(res, verbose, hb.qnames, 0, k)
                 return res, text
             finally:

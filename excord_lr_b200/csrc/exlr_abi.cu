@@ -45,6 +45,7 @@ struct exlr_ctx {
     int device_format = 0;                     // EXLR_OPT_DEVICE_FORMAT: kernels 5a/5b write the output lines; read with exlr_wait_text
     int long_records = 0;                      // EXLR_OPT_LONG_RECORDS: 0 auto (by mean CIGAR length), 1 never, 2 kernel 1c, 3 kernel 1d
     int skip_screen = 0;                       // auto mode: batches left to run without the screen pass (the last screened one was event-dense)
+    bool far_mode = false;                     // merge_min > 2 * indel_min: the >2 merge loop (main.rs:636-742) can change the events, kernels 4a/4b run their FAR variants
 };
 
 struct exlr_batch {
@@ -65,6 +66,7 @@ struct exlr_batch {
     size_t ctrl_bytes = 0;                     // ctrl + both scan status arrays (one memset)
     uint64_t n_reads = 0, n_ops = 0;
     bool submitted = false, resident_uploaded = false, have_timing = false, stage_timed = false;
+    bool far_ran = false;                      // the last submit ran the FAR variants of kernels 4a/4b
     uint32_t launches = 0;
     unsigned long long* d_dbg = nullptr;
 };
@@ -122,7 +124,7 @@ const char* exlr_strerror(int s)
     case EXLR_ERR_SA_CIGAR: return "SA CIGAR is malformed or outside [0-9MIDNSHP=X]";
     case EXLR_ERR_SA_MAPQ: return "SA mapq is not a u8 (reference panics)";
     case EXLR_ERR_SA_NM: return "SA NM is not an integer (reference panics)";
-    case EXLR_ERR_MERGE_DOMAIN: return "more than two indel events with merge_min reaching across them: the reference panics or duplicates events here";
+    case EXLR_ERR_MERGE_DOMAIN: return "more than two indel events with merge_min reaching across them: the merge loop of the reference indexes out of bounds and panics";
     case EXLR_ERR_SPLIT_COUNT: return "more than 2^24 segments in one record";
     case EXLR_ERR_TEXT_CAPACITY: return "formatted lines exceed the batch's text buffer; use exlr_wait + exlr_format_lines";
     default: return "unknown status";
@@ -152,6 +154,7 @@ int exlr_create(const exlr_params* p, int device, const char* const* ref_names, 
     d.exclude_unmapped = p->exclude_unmapped; d.split_only = p->split_only; d.indel_min = p->indel_min;
     d.merge_min = p->merge_min; d.ins_clip_min = p->ins_clip_min; d.max_pct_overlap = p->max_pct_overlap;
     d.max_supp_alignm = p->max_supp_alignm;
+    c->far_mode = (uint64_t)p->merge_min > 2ull * p->indel_min;
     std::vector<uint32_t> off(n_ref + 1, 0);
     std::string bytes;
     for (int i = 0; i < n_ref; i++) {
@@ -265,7 +268,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     const size_t d_ctrl = dcarve(sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes + (size_t)ttiles * 8);   // ctrl | scan_a | scan_b | dirty_bits | scan_c : one memset
     const size_t d_cigar = dcarve((max_ops + 4) * 4 + 16), d_coff = dcarve((R + 1) * 8), d_pos = dcarve(R * 4), d_tid = dcarve(R * 4),
                  d_flag = dcarve(R * 2), d_mapq = dcarve(R), d_kind = dcarve(R), d_soff = dcarve((R + 1) * 4), d_sab = dcarve(max_sa_bytes + 16),
-                 d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_slist = dcarve((max_ops / 512 + 16) * 4), d_ssum = dcarve((max_ops / 512 + 16) * 4), d_sflag = dcarve(max_ops / 512 + 16), d_llist = dcarve(R * 4), d_shlist = dcarve(R * 4), d_wlist = dcarve(R * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
+                 d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_slist = dcarve((max_ops / 512 + 16) * 4), d_ssum = dcarve((max_ops / 512 + 16) * 4), d_sflag = dcarve(max_ops / 512 + 16), d_llist = dcarve(R * 4), d_far = dcarve(R * 8), d_shlist = dcarve(R * 4), d_wlist = dcarve(R * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
                  d_raw = dcarve((max_events + kRawHeadroom) * sizeof(RawEv)), d_saev = dcarve(max_events * sizeof(exlr_event)),
                  d_pool = dcarve(pool_cap * sizeof(Seg)), d_dbg = dcarve(8192 * 32), d_toff = dcarve(c->device_format ? (max_events + 1) * 4 : 0), d_text = dcarve(text_cap + 16), d_loff = dcarve((R + 1) * 4), d_ev = dcarve(max_events * sizeof(exlr_event));
     e = cudaMalloc(&b->d_slab, dof);
@@ -274,7 +277,7 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     DevBatch& v = b->dv;
     v.ctrl = (Ctrl*)(ds + d_ctrl);
     v.scan_a = (unsigned long long*)(ds + d_ctrl + sizeof(Ctrl)); v.scan_b = v.scan_a + tiles;
-    v.dirty_bits = (uint32_t*)(v.scan_b + tiles); v.step_list = (uint32_t*)(ds + d_slist); v.step_sum = (uint32_t*)(ds + d_ssum); v.step_flag = (uint8_t*)(ds + d_sflag); v.long_list = (uint32_t*)(ds + d_llist); v.short_list = (uint32_t*)(ds + d_shlist); v.warp_list = (uint32_t*)(ds + d_wlist);
+    v.dirty_bits = (uint32_t*)(v.scan_b + tiles); v.step_list = (uint32_t*)(ds + d_slist); v.step_sum = (uint32_t*)(ds + d_ssum); v.step_flag = (uint8_t*)(ds + d_sflag); v.long_list = (uint32_t*)(ds + d_llist); v.far_list = (uint2*)(ds + d_far); v.short_list = (uint32_t*)(ds + d_shlist); v.warp_list = (uint32_t*)(ds + d_wlist);
     v.scan_c = (unsigned long long*)((char*)v.dirty_bits + bits_bytes);
     v.text_off = c->device_format ? (uint32_t*)(ds + d_toff) : nullptr; v.text = (uint8_t*)(ds + d_text); v.text_cap = (uint32_t)text_cap;
     b->ctrl_bytes = sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes + (size_t)ttiles * 8;
@@ -413,12 +416,13 @@ static int run_kernels(exlr_batch* b)
     launch_k3b(d, c->dparams, st); b->launches++;
     if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K3B], st));
     if (overlap) CK(cudaStreamWaitEvent(st, b->ev_k1_end, 0));
-    launch_k4a(d, c->dparams, st); b->launches++;
+    launch_k4a(d, c->dparams, c->far_mode, st); b->launches++;
     if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K4A], st));
-    launch_k4b(d, c->dparams, st); b->launches++;
+    launch_k4b(d, c->dparams, c->far_mode, st); b->launches++;
     b->formatted = d.text_off != nullptr;
     if (b->formatted) { launch_k5(d, st); b->launches += 2; }      // (no event in between: 5a is placed while 4b drains)
     launch_header(d, b->h_ctrl_dev, st); b->launches++;            // the result header, stored straight into pinned host memory
+    b->far_ran = c->far_mode;
     CK(cudaEventRecord(b->ev[EV_K4B], st));
     CK(cudaEventRecord(b->ev[EV_D2H], st));
     CK(cudaGetLastError());
@@ -492,6 +496,19 @@ static int finish(exlr_batch* b, exlr_result* res, bool fetch)
     if (b->n_reads == 0) { res->status = EXLR_OK; return EXLR_OK; }
     CK(cudaSetDevice(b->ctx->device));
     CK(cudaStreamSynchronize(b->stream));
+    if (b->h_ctrl->need_far && !b->far_ran) {
+        // a record for the literal >2 merge loop in a batch whose parameters rule it out short of a u32 wrap (see k4a_line_scan):
+        // the tail of the pipeline runs again with the loop compiled in
+        exlr_ctx* cx = b->ctx; cudaStream_t st = b->stream;
+        launch_reset_tail(b->dv, st);
+        launch_k4a(b->dv, cx->dparams, true, st);
+        launch_k4b(b->dv, cx->dparams, true, st);
+        if (b->formatted) launch_k5(b->dv, st);
+        launch_header(b->dv, b->h_ctrl_dev, st);
+        b->far_ran = true; b->launches += b->formatted ? 6 : 4;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));
+    }
     const Ctrl& c = *b->h_ctrl;
     if (b->screened && (uint64_t)c.n_flagged * 2 > (uint64_t)k1a_steps(b->n_ops)) b->ctx->skip_screen = 8;   // event-dense: see run_kernels
     res->n_events = c.n_events; res->n_kept = c.n_kept; res->n_sa_reads = c.n_sa; res->n_cap_dropped = c.n_dropped;
@@ -510,6 +527,7 @@ static int finish(exlr_batch* b, exlr_result* res, bool fetch)
         const unsigned long long key = ~c.err_key;
         res->err_read = (uint32_t)(key >> 8);
         res->status = status_of_rank((uint32_t)(key & 0xff));
+        res->n_err_lines = c.err_lines;
     }
     return res->status;
 }
@@ -527,11 +545,12 @@ int exlr_wait_text(exlr_batch* b, exlr_result* res, const char** text, uint64_t*
     if (c.text_bytes > b->dv.text_cap) return EXLR_ERR_TEXT_CAPACITY;    // exlr_wait + exlr_format_lines still work
     uint64_t nb = c.text_bytes;
     if (rc <= -10) {
-        // a record on which the reference panics: the lines of the records before it stand (its BufWriter is flushed on unwind)
+        // a record on which the reference panics: the lines of the records before it stand (its BufWriter is flushed on unwind),
+        // and so do the lines the record itself had written by then
         uint32_t first_line = 0, off = 0;
         CK(cudaMemcpyAsync(&first_line, b->dv.line_off + res->err_read, 4, cudaMemcpyDeviceToHost, b->stream));
         CK(cudaStreamSynchronize(b->stream));
-        CK(cudaMemcpyAsync(&off, b->dv.text_off + first_line, 4, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaMemcpyAsync(&off, b->dv.text_off + first_line + (uint32_t)res->n_err_lines, 4, cudaMemcpyDeviceToHost, b->stream));
         CK(cudaStreamSynchronize(b->stream));
         nb = off;
     }

@@ -37,7 +37,10 @@ struct Ctrl {
     uint32_t ticket_c;              // dynamic tile ids of kernel 5a's chained scan
     uint32_t text_bytes;            // kernel 5a: bytes of the formatted lines
     uint32_t n_warp;                // records kernel 1b scans with a warp each (length of warp_list)
-    uint32_t pad[14];
+    uint32_t n_far;                 // records whose >2-event merge loop (main.rs:636-742) changed the event list (length of far_list)
+    uint32_t err_lines;             // lines the failing record had written before it panicked (result header, set by the last kernel)
+    uint32_t need_far;              // kernel 4a<false> met a record for the literal merge loop: the host re-runs kernels 4a<true>.. (exlr_abi.cu)
+    uint32_t pad[11];
 };
 static_assert(sizeof(Ctrl) == 128, "Ctrl is the 128-byte result header");
 
@@ -54,6 +57,7 @@ static_assert(sizeof(RawEv) == 32, "RawEv");
 
 // per-record summary written by kernel 1:  x = total_consume (main.rs:528-545), y = info
 static constexpr uint32_t K1_CNT_MASK = 0x0fffffffu;   // number of indel events of the record
+static constexpr uint32_t K1_MERGED = 1u << 29;        // set by kernel 4a: the record's lines come from the literal merge loop (far_list), not from its raw events
 static constexpr uint32_t K1_PAIR_MERGE = 1u << 30;    // 2nd event merges with the 1st (near-edge rule, main.rs:615)
 static constexpr uint32_t K1_FAR_HIT = 1u << 31;       // some adjacent pair satisfies the far-edge rule (main.rs:673-678)
 
@@ -100,6 +104,7 @@ struct DevBatch {
     uint32_t* dirty_bits;   // [R/32] one bit per record: claimed by a thread of kernel 1b (zeroed with ctrl)
     uint32_t* short_list;   // [R] k1b_claim: claimed records walked by one thread each, any order (ctrl->n_short entries)
     uint32_t* warp_list;    // [R] k1b_claim: claimed records of medium length, scanned by one warp each (ctrl->n_warp entries)
+    uint2* far_list;        // [R] kernel 4a: {record, rounds of the merge loop to apply} for records the literal >2 merge loop changes
     uint32_t* long_list;    // [R] kernel 1b: claimed records too long for one thread, any order (ctrl->n_long entries)
     uint32_t* step_sum;     // [max_ops/512 + 1] kernel 1a<SUMS>: reference-consuming length of every 512-op step (long-record batches)
     uint8_t* step_flag;     // [max_ops/512 + 1] kernel 1a<SUMS>: the step holds an event candidate
@@ -148,7 +153,8 @@ void launch_k1b(const DevBatch& B, const DevParams& P, unsigned long long n_ops,
 void launch_k1c(const DevBatch& B, const DevParams& P, cudaStream_t st);
 void launch_k3a(const DevBatch& B, const DevParams& P, uint32_t mean_ops, cudaStream_t st);
 void launch_k3b(const DevBatch& B, const DevParams& P, cudaStream_t st);
-void launch_k4a(const DevBatch& B, const DevParams& P, cudaStream_t st);
-void launch_k4b(const DevBatch& B, const DevParams& P, cudaStream_t st);
+void launch_k4a(const DevBatch& B, const DevParams& P, bool far, cudaStream_t st);
+void launch_reset_tail(const DevBatch& B, cudaStream_t st);
+void launch_k4b(const DevBatch& B, const DevParams& P, bool far, cudaStream_t st);
 
 }  // namespace exlr

@@ -86,14 +86,137 @@ __device__ __forceinline__ uint32_t indel_lines(uint32_t info)
     return (cnt == 2u && (info & K1_PAIR_MERGE)) ? 1u : cnt;                  // main.rs:612-635
 }
 
-__device__ __forceinline__ uint32_t record_lines(const DevBatch& B, uint32_t r, uint32_t csa, uint32_t info)
+// ---- the literal merge loop for more than two events (main.rs:636-742) ------------------------------------------------
+// The loop is the identity unless some adjacent pair of Dels satisfies the far-edge predicate (main.rs:673-678), which needs
+// merge_min > 2 * indel_min; kernel 1 flags such records (K1_FAR_HIT) and only those come here -- a rare path, run by the one
+// thread that owns the record in kernel 4a (line count) and again in kernel 4b (the lines themselves).
+// A round reads merge1 through a three-element window (prv, target, nxt) and appends to merge2, and the next round reads
+// what this one appended: the (at most five) rounds are run as a pipeline of window stages fed one event at a time, so no
+// event list is ever stored.  Pass 1 counts what every round emits; the lengths decide at which round the reference stops
+// (`merge1.len() == merge2.len()` or five rounds) or panics (a round that starts with fewer than two events indexes out of
+// bounds, main.rs:664-671); pass 2 re-runs the pipeline up to that round and writes its output.
+struct MEv { uint32_t lend, rstart, rend, del; };                             // lstart = record.pos() for every event of a record
+struct MStage { MEv a, b; uint32_t n_in, n_out; };
+struct MEmit {                                                                // where the last round's events go (null: count only)
+    exlr_event* dst; uint32_t n, cap, pos2, r, tid, neg;
+    __device__ __forceinline__ void operator()(const MEv& e)
+    {
+        if (dst && n < cap)
+            store_event(dst + n, (int64_t)pos2, (int64_t)e.lend, (int64_t)e.rstart, (int64_t)e.rend, r, tid, tid, EXLR_EV_META(1u, EXLR_KIND_INDEL, neg, neg));
+        n++;
+    }
+};
+static constexpr int kMergeRounds = 5;                                        // iter_times, main.rs:638
+
+template <int K>
+struct MFeed {
+    // event e arrives as element n_in of round K+1's input; out-of-line so that the six call sites per round do not multiply
+    static __device__ __noinline__ void push(MStage* st, uint32_t merge_min, int rounds, MEv e, MEmit* emit)
+    {
+        if (K >= rounds) { (*emit)(e); return; }
+        MStage& s = st[K];
+        s.n_in++;
+        if (s.n_in >= 3u) {                                                   // idx = n_in - 2 (main.rs:662-671)
+            const MEv P = s.a, T = s.b;
+            const bool mp = P.del && T.del && abs_diff(P.lend, T.rstart) < merge_min;      // main.rs:673-675
+            const bool mn = T.del && e.del && abs_diff(T.lend, e.rstart) < merge_min;      // main.rs:676-678
+            if (mp || mn) {
+                if (mp) { s.n_out++; MFeed<K + 1>::push(st, merge_min, rounds, MEv{P.lend, T.rstart, T.rend, 1u}, emit); }
+                if (mn) { s.n_out++; MFeed<K + 1>::push(st, merge_min, rounds, MEv{T.lend, e.rstart, e.rend, 1u}, emit); }
+            } else if (s.n_in == 3u) {                                        // idx == 1: prv, target, nxt (main.rs:724-727)
+                s.n_out += 3u;
+                MFeed<K + 1>::push(st, merge_min, rounds, P, emit);
+                MFeed<K + 1>::push(st, merge_min, rounds, T, emit);
+                MFeed<K + 1>::push(st, merge_min, rounds, e, emit);
+            } else { s.n_out++; MFeed<K + 1>::push(st, merge_min, rounds, e, emit); }
+        }
+        s.a = s.b; s.b = e;
+    }
+};
+template <>
+struct MFeed<kMergeRounds> {
+    static __device__ __forceinline__ void push(MStage*, uint32_t, int, MEv e, MEmit* emit) { (*emit)(e); }
+};
+
+// what the loop needs of one record, by value (a reference to the kernel's parameter block would make every thread of the
+// kernel copy the block to its stack)
+struct MArgs { const uint32_t* cigar; unsigned long long o0, o1; uint32_t pos2, total_consume, indel_min, merge_min; };
+
+__device__ __forceinline__ MArgs merge_args(const DevBatch& B, const DevParams& P, uint32_t r, uint32_t total_consume)
+{
+    return MArgs{B.cigar, B.cigar_off[r], B.cigar_off[r + 1], (uint32_t)B.pos[r], total_consume, P.indel_min, P.merge_min};
+}
+
+// the record's indel events in CIGAR order (main.rs:549-600) through `rounds` rounds of the loop
+static __device__ __noinline__ void merge_rounds(const MArgs A, int rounds, MStage* st, MEmit* emit)
+{
+    for (int k = 0; k < kMergeRounds; k++) { st[k].n_in = 0; st[k].n_out = 0; }
+    uint32_t L = 0;
+    for (unsigned long long o = A.o0; o < A.o1; o++) {
+        const uint32_t v = __ldg(A.cigar + o), op = v & 15u, n = v >> 4;
+        if (op == 2u) {
+            if (n >= A.indel_min) MFeed<0>::push(st, A.merge_min, rounds, MEv{A.pos2 + L, A.pos2 + L + n, A.pos2 + A.total_consume, 1u}, emit);
+            L += n;
+        } else if (op == 1u) {
+            if (n >= A.indel_min) MFeed<0>::push(st, A.merge_min, rounds, MEv{A.pos2 + L, A.pos2 + L, A.pos2 + L + n, 0u}, emit);
+        } else if (op <= 8u && consumes_ref(op)) L += n;
+    }
+}
+
+// Pass 1.  Returns lines | rounds << 28: the number of lines the loop leaves for the record and the round it stops at;
+// 0xffffffff = the reference panics.
+static __device__ __noinline__ uint32_t merge_plan(const MArgs A, uint32_t cnt)
+{
+    MStage st[kMergeRounds];
+    MEmit none{nullptr, 0u, 0u, 0u, 0u, 0u, 0u};
+    merge_rounds(A, kMergeRounds, st, &none);
+    uint32_t in = cnt, lines = 0, rounds = 0;
+    for (int k = 1; k <= kMergeRounds; k++) {
+        if (in < 2u) return 0xffffffffu;                                      // merge1.len() - 2 wraps, merge1[idx] is out of bounds
+        const uint32_t out = st[k - 1].n_out;                                 // (in == 2: no window, merge2 stays empty)
+        lines = out; rounds = (uint32_t)k;
+        if (in == out || k == kMergeRounds) break;                            // main.rs:733-737
+        in = out;
+    }
+    return lines >= (1u << 28) ? 0xfffffffeu : (lines | (rounds << 28));
+}
+
+// Lines of one record without the >2 merge loop; *far is set when the loop has to decide (K1_FAR_HIT and more than two events).
+__device__ __forceinline__ uint32_t record_lines(uint32_t csa, uint32_t info, bool* far)
 {
     if (csa & CSA_DROP) return 0u;                                            // -k cap: no lines at all (main.rs:311-313)
-    if ((info & K1_CNT_MASK) > 2u && (info & K1_FAR_HIT)) report(B.ctrl, r, RANK_MERGE_DOMAIN);
+    if (info & K1_MERGED) return (csa & CSA_CNT_MASK) + (info & K1_CNT_MASK);  // second pass: the loop's own line count
+    if ((info & K1_CNT_MASK) > 2u && (info & K1_FAR_HIT)) *far = true;
     return (csa & CSA_CNT_MASK) + indel_lines(info);
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k4a_line_scan(DevBatch B, DevParams P)
+// The rare path of kernel 4a, out of line (its call chain must not shape the register allocation of the scan around it):
+// plans the literal merge loop for record r and leaves the number of indel lines it produces in the record's summary
+// (K1_MERGED | lines: kernel 4a's second pass counts those, kernel 4b skips the record's raw events).
+struct FarArgs { uint2* k1; uint2* far_list; Ctrl* ctrl; MArgs m; uint32_t r; };
+static __device__ __noinline__ void far_record_plan(const FarArgs F)
+{
+    const uint2 k1 = F.k1[F.r];
+    MArgs m = F.m; m.total_consume = k1.x;
+    const uint32_t plan = merge_plan(m, k1.y & K1_CNT_MASK);
+    uint32_t lines = 0;
+    if (plan == 0xffffffffu) {
+        // the reference panics here, after the SA arm of the same record has written its lines (main.rs:395-515 vs :664)
+        report(F.ctrl, F.r, RANK_MERGE_DOMAIN);
+    } else if (plan == 0xfffffffeu) F.ctrl->overflow = 1;                     // 2^28 lines from one record: no buffer holds that
+    else {
+        F.far_list[atomicAdd(&F.ctrl->n_far, 1u)] = make_uint2(F.r, plan >> 28);
+        lines = plan & K1_CNT_MASK;
+    }
+    F.k1[F.r] = make_uint2(k1.x, K1_MERGED | lines);
+}
+
+// FAR = false is the kernel of every ordinary batch: the far-edge predicate cannot fire unless merge_min > 2 * indel_min (two
+// Dels of at least indel_min lie between the edges it compares) or a coordinate wraps around 2^32, so the host launches this
+// lean variant, whose registers are not shaped by the merge loop's call chain; should it meet such a record after all, it
+// only raises need_far and the host runs the tail of the pipeline again with FAR = true.
+template <bool FAR>
+__global__ void __launch_bounds__(SCAN_THREADS, FAR ? 4 : 1) k4a_line_scan(DevBatch B, DevParams P)
 {
     __shared__ uint32_t s_tile, s_warp[16];
     griddep_launch();                                  // kernel 4b may be placed; it waits for this grid before it reads anything
@@ -102,37 +225,59 @@ __global__ void __launch_bounds__(SCAN_THREADS) k4a_line_scan(DevBatch B, DevPar
     __syncthreads();
     const uint32_t tile = s_tile, n = B.n_reads;
     const uint32_t r0 = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    uint32_t c[SCAN_ITEMS], mine = 0;
+    uint32_t c[SCAN_ITEMS], mine, farmask;
     const bool full = r0 + SCAN_ITEMS <= n;
-    if (full && B.k1_gated) {
-        // screened CIGAR path: a record has an indel summary only if kernel 1b claimed it (its bit in the claim bitmap);
-        // everything else is "no event" without ever having been written -- 16 records share one 16-bit slice of the bitmap
-        union { uint4 v[4]; uint32_t u[16]; } cs;
+    for (;;) {
+        mine = 0; farmask = 0;
+        if (full && B.k1_gated) {
+            // screened CIGAR path: a record has an indel summary only if kernel 1b claimed it (its bit in the claim bitmap);
+            // everything else is "no event" without ever having been written -- 16 records share one 16-bit slice of the bitmap
+            union { uint4 v[4]; uint32_t u[16]; } cs;
 #pragma unroll
-        for (int k = 0; k < 4; k++) cs.v[k] = reinterpret_cast<const uint4*>(B.csa + r0)[k];
-        const uint32_t bits = (B.dirty_bits[r0 >> 5] >> (r0 & 31u)) & 0xffffu;
+            for (int k = 0; k < 4; k++) cs.v[k] = reinterpret_cast<const uint4*>(B.csa + r0)[k];
+            const uint32_t bits = (B.dirty_bits[r0 >> 5] >> (r0 & 31u)) & 0xffffu;
 #pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++) {
-            const uint32_t info = (bits >> i) & 1u ? B.k1[r0 + i].y : 0u;
-            c[i] = record_lines(B, r0 + i, cs.u[i], info); mine += c[i];
+            for (int i = 0; i < SCAN_ITEMS; i++) {
+                const uint32_t info = (bits >> i) & 1u ? B.k1[r0 + i].y : 0u;
+                bool far = false;
+                c[i] = record_lines(cs.u[i], info, &far); mine += c[i];
+                farmask |= far ? 1u << i : 0u;
+            }
+        } else if (full) {
+            union { uint4 v[4]; uint32_t u[16]; } cs;
+            union { uint4 v[8]; uint2 p[16]; } k1;
+#pragma unroll
+            for (int k = 0; k < 4; k++) cs.v[k] = reinterpret_cast<const uint4*>(B.csa + r0)[k];
+#pragma unroll
+            for (int k = 0; k < 8; k++) k1.v[k] = reinterpret_cast<const uint4*>(B.k1 + r0)[k];
+#pragma unroll
+            for (int i = 0; i < SCAN_ITEMS; i++) {
+                bool far = false;
+                c[i] = record_lines(cs.u[i], k1.p[i].y, &far); mine += c[i];
+                farmask |= far ? 1u << i : 0u;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < SCAN_ITEMS; i++) {
+                const uint32_t r = r0 + i;
+                uint32_t info = 0;
+                if (r < n && (!B.k1_gated || ((B.dirty_bits[r >> 5] >> (r & 31u)) & 1u))) info = B.k1[r].y;
+                bool far = false;
+                c[i] = r < n ? record_lines(B.csa[r], info, &far) : 0u;
+                mine += c[i];
+                farmask |= far ? 1u << i : 0u;
+            }
         }
-    } else if (full) {
-        union { uint4 v[4]; uint32_t u[16]; } cs;
-        union { uint4 v[8]; uint2 p[16]; } k1;
-#pragma unroll
-        for (int k = 0; k < 4; k++) cs.v[k] = reinterpret_cast<const uint4*>(B.csa + r0)[k];
-#pragma unroll
-        for (int k = 0; k < 8; k++) k1.v[k] = reinterpret_cast<const uint4*>(B.k1 + r0)[k];
-#pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++) { c[i] = record_lines(B, r0 + i, cs.u[i], k1.p[i].y); mine += c[i]; }
-    } else {
-#pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++) {
-            const uint32_t r = r0 + i;
-            uint32_t info = 0;
-            if (r < n && (!B.k1_gated || ((B.dirty_bits[r >> 5] >> (r & 31u)) & 1u))) info = B.k1[r].y;
-            c[i] = r < n ? record_lines(B, r, B.csa[r], info) : 0u;
-            mine += c[i];
+        if (!farmask) break;
+        if (!FAR) { B.ctrl->need_far = 1u; break; }
+        // rare: records whose >2 merge loop is not the identity (main.rs:636-742).  The plan lands in the record's summary and
+        // the counts are taken again (no dynamically indexed update of c[], which would move the array to local memory).
+        if (FAR) {
+            while (farmask) {
+                const uint32_t r = r0 + (uint32_t)(__ffs((int)farmask) - 1);
+                farmask &= farmask - 1u;
+                far_record_plan(FarArgs{B.k1, B.far_list, B.ctrl, merge_args(B, P, r, 0u), r});
+            }
         }
     }
     uint32_t grand;
@@ -169,6 +314,7 @@ __device__ __forceinline__ void k4b_indel(const DevBatch& B, const RawEv* src)
     const uint32_t csa = B.csa[r];
     if (csa & CSA_DROP) return;
     const uint2 k1 = B.k1[r];
+    if (k1.y & K1_MERGED) return;                                             // its lines come from the literal merge loop (far_list)
     const uint32_t cnt = k1.y & K1_CNT_MASK;
     const bool merged = cnt == 2u && (k1.y & K1_PAIR_MERGE);
     uint32_t seq = a.y;
@@ -191,14 +337,15 @@ __device__ __forceinline__ void k4b_indel(const DevBatch& B, const RawEv* src)
 // One thread per raw slot / overflow entry / SA record.  The overflow and SA-record counts live on the device, so the grid
 // is one resident wave striding over the largest of the three ranges (measured: a grid sized for the worst case launched
 // 7-9k CTAs, most of them empty, and the launch alone took ~15 us).
-__global__ void __launch_bounds__(256) k4b_place(DevBatch B, DevParams P)
+template <bool FAR>
+__global__ void __launch_bounds__(256, FAR ? 6 : 1) k4b_place(DevBatch B, DevParams P)
 {
     griddep_wait();                                    // kernel 4a's line offsets
     griddep_launch();
     CtaTrace tr(B, 6);
-    const uint32_t room = B.raw_cap - B.prim_slots, n_ovf = min(B.ctrl->n_raw, room), n_sa = B.ctrl->n_sa;
+    const uint32_t room = B.raw_cap - B.prim_slots, n_ovf = min(B.ctrl->n_raw, room), n_sa = B.ctrl->n_sa, n_far = FAR ? B.ctrl->n_far : 0u;
     tr.mid();
-    const uint32_t limit = max(B.prim_slots, max(n_ovf, n_sa)), stride = gridDim.x * blockDim.x;
+    const uint32_t limit = max(max(B.prim_slots, n_far), max(n_ovf, n_sa)), stride = gridDim.x * blockDim.x;
     for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < limit; x += stride) {
         // indel events, per-tile slices first (slice of tile i = raw[i << capt_log2 ..], tile_cnt[i] entries used) ...
         if (x < B.prim_slots && (x & ((1u << B.capt_log2) - 1u)) < B.tile_cnt[x >> B.capt_log2]) k4b_indel(B, B.raw + x);
@@ -215,6 +362,14 @@ __global__ void __launch_bounds__(256) k4b_place(DevBatch B, DevParams P)
             uint4* d = reinterpret_cast<uint4*>(B.events + dst);
             for (uint32_t k = 0; k < cnt * 3; k++) d[k] = src[k];
         }
+    }
+    // records the literal merge loop changed (rare): pass 2 writes the lines of the round kernel 4a found the loop stops at
+    if constexpr (FAR) for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < n_far; x += stride) {
+        const uint2 f = B.far_list[x];
+        const uint32_t r = f.x, at = B.line_off[r] + (B.csa[r] & CSA_CNT_MASK);
+        MStage st[kMergeRounds];
+        MEmit emit{B.events + at, 0u, at < B.max_events ? B.max_events - at : 0u, (uint32_t)B.pos[r], r, (uint32_t)B.tid[r], (B.flag[r] >> 4) & 1u};
+        merge_rounds(merge_args(B, P, r, B.k1[r].x), (int)f.y, st, &emit);
     }
     tr.end();
 }
@@ -360,9 +515,16 @@ __global__ void __launch_bounds__(256) k5b_format(DevBatch B)
 // result header: the 128-byte control block goes to (mapped, pinned) host memory by eight 16-byte stores of one warp, placed
 // while the last kernel drains -- a cudaMemcpyAsync of 128 bytes costs ~9 us of stream time, this ~3
 // ======================================================================================
-__global__ void __launch_bounds__(32) k6_header(const Ctrl* ctrl, Ctrl* host_ctrl)
+__global__ void __launch_bounds__(32) k6_header(Ctrl* ctrl, Ctrl* host_ctrl, const uint32_t* line_off)
 {
     griddep_wait();
+    if (threadIdx.x == 0 && ctrl->err_key) {
+        // a panic in the indel arm comes after the SA arm's writes of the same record: kernel 4a counted exactly those lines for it
+        const unsigned long long key = ~ctrl->err_key;
+        const uint32_t r = (uint32_t)(key >> 8);
+        ctrl->err_lines = (key & 0xffull) == RANK_MERGE_DOMAIN ? line_off[r + 1] - line_off[r] : 0u;
+    }
+    __syncwarp();
     if (threadIdx.x < sizeof(Ctrl) / 16) reinterpret_cast<uint4*>(host_ctrl)[threadIdx.x] = reinterpret_cast<const uint4*>(ctrl)[threadIdx.x];
     __threadfence_system();
 }
@@ -393,23 +555,39 @@ void launch_k0(const DevBatch& B, const DevParams& P, cudaStream_t st)
     k0_classify<<<tiles, SCAN_THREADS, 0, st>>>(B, P);
 }
 
-void launch_k4a(const DevBatch& B, const DevParams& P, cudaStream_t st)
+void launch_k4a(const DevBatch& B, const DevParams& P, bool far, cudaStream_t st)
 {
     const uint32_t tiles = (B.n_reads + SCAN_TILE - 1) / SCAN_TILE;
-    k4a_line_scan<<<tiles, SCAN_THREADS, 0, st>>>(B, P);
+    if (far) k4a_line_scan<true><<<tiles, SCAN_THREADS, 0, st>>>(B, P);
+    else k4a_line_scan<false><<<tiles, SCAN_THREADS, 0, st>>>(B, P);
 }
 
-void launch_k4b(const DevBatch& B, const DevParams& P, cudaStream_t st)
+// before kernels 4a.. run a second time on the same batch (need_far): their tickets, scan status words and counters
+__global__ void k_reset_tail(DevBatch B, uint32_t tiles_b, uint32_t tiles_c)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (uint32_t k = i; k < tiles_b; k += stride) B.scan_b[k] = 0ull;
+    for (uint32_t k = i; k < tiles_c; k += stride) B.scan_c[k] = 0ull;
+    if (i == 0) { Ctrl* c = B.ctrl; c->ticket_b = 0; c->ticket_c = 0; c->n_events = 0; c->text_bytes = 0; c->n_far = 0; c->need_far = 0; c->err_lines = 0; }
+}
+
+void launch_reset_tail(const DevBatch& B, cudaStream_t st)
+{
+    k_reset_tail<<<64, 256, 0, st>>>(B, scan_tiles(B.n_reads), B.text_off ? text_scan_tiles(B.max_events) : 0u);
+}
+
+void launch_k4b(const DevBatch& B, const DevParams& P, bool far, cudaStream_t st)
 {
     // the overflow count and the SA-record count live on the device: cover the largest they can be, capped at one resident wave
     uint32_t n = B.prim_slots > B.n_reads ? B.prim_slots : B.n_reads;
     const uint32_t room = B.raw_cap - B.prim_slots;
     if (room > n) n = room;
     const uint32_t grid = min((n + 255u) / 256u, (uint32_t)sm_count() * 8u);
-    launch_dependent(k4b_place, grid ? grid : 1u, 256, 0, st, B, P);
+    if (far) launch_dependent(k4b_place<true>, grid ? grid : 1u, 256, 0, st, B, P);
+    else launch_dependent(k4b_place<false>, grid ? grid : 1u, 256, 0, st, B, P);
 }
 
-void launch_header(const DevBatch& B, Ctrl* host_ctrl_dev, cudaStream_t st) { launch_dependent(k6_header, 1u, 32u, 0, st, (const Ctrl*)B.ctrl, host_ctrl_dev); }
+void launch_header(const DevBatch& B, Ctrl* host_ctrl_dev, cudaStream_t st) { launch_dependent(k6_header, 1u, 32u, 0, st, B.ctrl, host_ctrl_dev, (const uint32_t*)B.line_off); }
 
 uint32_t scan_tiles(uint32_t n_reads) { return (n_reads + SCAN_TILE - 1) / SCAN_TILE; }
 uint32_t text_scan_tiles(uint32_t max_events) { return (max_events + SCAN_THREADS - 1) / SCAN_THREADS + 1; }

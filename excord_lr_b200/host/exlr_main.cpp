@@ -222,7 +222,7 @@ int main(int argc, char** argv)
             if (st != 0 && st > -10) { fprintf(stderr, "exlr_wait: %s (%s)\n", exlr_strerror(st), exlr_last_cuda_error()); std::lock_guard<std::mutex> lk(mu); fatal = 3; cv.notify_all(); return; }
             uint64_t n_ev = res.n_events;
             if (host_format) {
-                if (st <= -10) n_ev = res.line_off[res.err_read];        // the lines of the records before the failing one
+                if (st <= -10) n_ev = res.line_off[res.err_read] + res.n_err_lines;   // what the reference had written when it panicked
                 const char* qn = cli.verbose ? s.pk.qnames.data() : nullptr;
                 static const char kEmpty = 0;
                 if (cli.verbose && !qn) qn = &kEmpty;

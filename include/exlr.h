@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define EXLR_ABI_VERSION 1
+#define EXLR_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------- */
 #define EXLR_OK                 0
@@ -41,7 +41,8 @@ extern "C" {
 #define EXLR_ERR_STATE         -5   /* call sequence error (wait without submit, ...)                */
 #define EXLR_ERR_TEXT_CAPACITY -6   /* exlr_wait_text: the lines need more than the batch's text buffer; format on the host */
 /* Per-record conditions on which the reference panics (exit 101).  exlr_result.err_read holds the
- * smallest offending record index of the batch; events of records < err_read are valid. */
+ * smallest offending record index of the batch; the lines the reference had written by then are valid:
+ * events [0, line_off[err_read] + n_err_lines). */
 #define EXLR_ERR_TID          -10   /* kept record with tid<0 or tid>=n_ref (main.rs:198, contig() panics)      */
 #define EXLR_ERR_CIGAR_OP     -11   /* BAM CIGAR op code > 8 (rust-htslib Cigar decode panics; main.rs:243,525) */
 #define EXLR_ERR_SA_FIELDS    -12   /* SA piece with < 6 ','-separated fields (utils.rs:121-130 index panic)    */
@@ -51,8 +52,9 @@ extern "C" {
                                        [0-9MIDNSHP=X] (outside the supported domain)             */
 #define EXLR_ERR_SA_MAPQ      -16   /* SA mapq not a u8 (utils.rs:129)                                          */
 #define EXLR_ERR_SA_NM        -17   /* SA NM not an i64 (utils.rs:130)                                          */
-#define EXLR_ERR_MERGE_DOMAIN -20   /* >2 indel events and the far-edge merge predicate fires (main.rs:673-678):
-                                       the reference panics or duplicates events there           */
+#define EXLR_ERR_MERGE_DOMAIN -20   /* the >2-event merge loop indexes out of bounds (main.rs:664-671): the reference
+                                       panics AFTER the SA arm of the same record wrote its lines (n_err_lines).  Where the loop
+                                       merges or duplicates events without panicking, the library emits what the reference prints */
 #define EXLR_ERR_SPLIT_COUNT  -21   /* more than 2^24 segments in one record (meta field overflow)              */
 
 /* ---- parameters: the Cli fields read inside the loop (main.rs:47-96) ------------------ */
@@ -136,6 +138,8 @@ typedef struct exlr_result {
     uint64_t n_sa_reads;      /* kept records with an SA aux                                        */
     uint64_t n_cap_dropped;   /* kept records skipped by the -k cap (main.rs:311-313)               */
     uint64_t n_ops;           /* CIGAR ops in the batch                                             */
+    uint64_t n_err_lines;     /* status <= -10: lines of record err_read itself that the reference had written before it
+                                 panicked (its SA-arm lines when the indel arm panics, main.rs:395-515 vs :523-742), else 0 */
 } exlr_result;
 
 /* per-stage device times of the last submit, from CUDA events on the batch's stream (ms) */

@@ -63,6 +63,8 @@ typedef struct exlr_oracle_out {
     int32_t status;
     uint32_t err_read;
     uint64_t n_kept, n_sa_reads, n_cap_dropped, n_ops;
+    uint64_t n_err_lines;   /* lines the failing record had already written when it panicked (its SA-arm lines when the
+                               indel arm panics: f.write at main.rs:395-515 precedes main.rs:523-742) */
 } exlr_oracle_out;
 
 static void push_event(exlr_oracle_out* o, const exlr_event* e)
@@ -328,10 +330,9 @@ static void emit_aev(exlr_oracle_out* o, uint32_t read, uint32_t lchrom, uint32_
 }
 
 /*
- * merge_mode 0: product domain — any record whose >2 merge loop is not the identity reports
- *               EXLR_ERR_MERGE_DOMAIN (what libexlr_cuda does).
- * merge_mode 1: literal — non-identity results are emitted as the reference would print
- *               them; only the panic case reports EXLR_ERR_MERGE_DOMAIN.
+ * The >2 merge loop is literal (main.rs:636-742): non-identity results are emitted as the reference prints
+ * them; only the panic case (index out of bounds) reports EXLR_ERR_MERGE_DOMAIN.  `merge_mode` is kept in the
+ * signature for callers of round 1 and ignored.
  */
 int exlr_oracle_run(const exlr_params* P, const char* const* ref_names, int n_ref,
                     uint64_t n_reads, const uint32_t* cigar, const uint64_t* cigar_off,
@@ -506,7 +507,8 @@ int exlr_oracle_run(const exlr_params* P, const char* const* ref_names, int n_re
             } else if (ev.n > 2) {
                 int changed = 0;
                 int panic = merge_loop(&ev, P->merge_min, &merged, &changed);
-                if (panic || (changed && merge_mode == 0)) FAIL(EXLR_ERR_MERGE_DOMAIN);
+                (void)changed; (void)merge_mode;
+                if (panic) FAIL(EXLR_ERR_MERGE_DOMAIN);
             } else if (ev.n == 1) {
                 aev_push(&merged, ev.v[0]);
             }
@@ -518,9 +520,14 @@ int exlr_oracle_run(const exlr_params* P, const char* const* ref_names, int n_re
 done:
     {
         uint64_t stop = (o->status == EXLR_OK) ? r_end : (uint64_t)o->err_read;
-        /* a failing record contributes no lines: drop what its SA arm may have emitted */
-        if (o->status != EXLR_OK) o->n_events = o->line_off[stop - r_begin];
-        for (uint64_t r = stop; r <= r_end; r++) o->line_off[r - r_begin] = (uint32_t)o->n_events;
+        /* The lines a failing record wrote before it panicked stay in the BufWriter and are flushed on unwind.  Only a
+         * panic in the indel arm comes after any write of the same record (the SA arm's lines, main.rs:395-515); every
+         * other panic (contig(), the CIGAR decode at :243, the SA parse at :315-320) precedes the record's first write. */
+        if (o->status != EXLR_OK) {
+            if (o->status == EXLR_ERR_MERGE_DOMAIN) o->n_err_lines = o->n_events - o->line_off[stop - r_begin];
+            else o->n_events = o->line_off[stop - r_begin];
+        }
+        for (uint64_t r = stop + (o->status != EXLR_OK ? 1 : 0); r <= r_end; r++) o->line_off[r - r_begin] = (uint32_t)o->n_events;
     }
     free(segs); free(ev.v); free(merged.v); free(first_cigar_str);
     return o->status;

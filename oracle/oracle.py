@@ -350,7 +350,12 @@ def process_record(rec: Record, P: Params) -> List[str]:
             elif c in "MN=":
                 left = (left + n) & U32
                 right = (right - n) & U32
-        for x in merge_events(ev, P.merge_min):
+        try:
+            merged = merge_events(ev, P.merge_min)
+        except ReferencePanic as e:
+            e.written = "".join(out)        # the SA arm's lines of this record are already in the BufWriter (main.rs:395-515)
+            raise
+        for x in merged:
             out.append(_fmt_aev(x, P, rec, strand, "excord-lr-alignment-event"))
     return out
 
@@ -363,6 +368,6 @@ def run(records: Sequence[Record], P: Params) -> str:
             parts.extend(process_record(r, P))
         except ReferencePanic as e:
             e.read = i
-            e.partial = "".join(parts)
+            e.partial = "".join(parts) + getattr(e, "written", "")
             raise
     return "".join(parts)

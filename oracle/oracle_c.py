@@ -24,7 +24,8 @@ _SRC = os.path.join(_HERE, "exlr_oracle.c")
 class _Out(C.Structure):
     _fields_ = [("events", C.c_void_p), ("n_events", C.c_uint64), ("cap_events", C.c_uint64),
                 ("line_off", C.POINTER(C.c_uint32)), ("status", C.c_int32), ("err_read", C.c_uint32),
-                ("n_kept", C.c_uint64), ("n_sa_reads", C.c_uint64), ("n_cap_dropped", C.c_uint64), ("n_ops", C.c_uint64)]
+                ("n_kept", C.c_uint64), ("n_sa_reads", C.c_uint64), ("n_cap_dropped", C.c_uint64), ("n_ops", C.c_uint64),
+                ("n_err_lines", C.c_uint64)]
 
 
 def build(force: bool = False) -> str:
@@ -61,12 +62,16 @@ def _names(ref_names):
 
 
 class OracleResult:
-    def __init__(self, status, err_read, events, line_off, n_kept, n_sa_reads, n_cap_dropped, n_ops):
+    """events: every line the reference writes, i.e. for a failing run the lines of the records before err_read plus the
+    n_err_lines lines the failing record itself had written before it panicked."""
+
+    def __init__(self, status, err_read, events, line_off, n_kept, n_sa_reads, n_cap_dropped, n_ops, n_err_lines=0):
         self.status, self.err_read, self.events, self.line_off = status, err_read, events, line_off
         self.n_kept, self.n_sa_reads, self.n_cap_dropped, self.n_ops = n_kept, n_sa_reads, n_cap_dropped, n_ops
+        self.n_err_lines = n_err_lines
 
 
-def run(hb: HostBatch, params: ExlrParams, merge_mode: int = 0, r_begin: int = 0, r_end: int | None = None) -> OracleResult:
+def run(hb: HostBatch, params: ExlrParams, merge_mode: int = 1, r_begin: int = 0, r_end: int | None = None) -> OracleResult:
     lib = _load()
     n = hb.n_reads
     r_end = n if r_end is None else r_end
@@ -85,7 +90,7 @@ def run(hb: HostBatch, params: ExlrParams, merge_mode: int = 0, r_begin: int = 0
             C.memmove(ev.ctypes.data, o.events, ne * EVENT_DTYPE.itemsize)
         lo = np.ctypeslib.as_array(o.line_off, shape=(r_end - r_begin + 1,)).copy()
         return OracleResult(int(o.status), int(o.err_read), ev, lo, int(o.n_kept), int(o.n_sa_reads),
-                            int(o.n_cap_dropped), int(o.n_ops))
+                            int(o.n_cap_dropped), int(o.n_ops), int(o.n_err_lines))
     finally:
         lib.exlr_oracle_free(C.byref(o))
 

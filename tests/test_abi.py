@@ -24,12 +24,12 @@ def test_header_symbols_exported():
     assert len(syms) >= 18
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/exlr.h but not exported"
-    assert lib.exlr_abi_version() == 1
+    assert lib.exlr_abi_version() == 2
 
 
 def test_struct_layouts():
     assert C.sizeof(ExlrParams) == 40 and EVENT_DTYPE.itemsize == 48
-    assert C.sizeof(api._Result) == 72 and C.sizeof(api.Timing) == 44 and C.sizeof(api._Views) == 104
+    assert C.sizeof(api._Result) == 80 and C.sizeof(api.Timing) == 44 and C.sizeof(api._Views) == 104
     lib = api.load_library()
     p = ExlrParams()
     lib.exlr_params_default(C.byref(p))

@@ -68,6 +68,37 @@ def test_dense_events_and_merge_rules(variant):
         gpu_check(hb, p, *variant, label=f"dense i{p.indel_min} m{p.merge_min} {variant}")
 
 
+def test_literal_merge_loop_lines_and_panics():
+    # main.rs:636-742 run literally on the device: merged / duplicated / multiplied events where the loop changes the list,
+    # EXLR_ERR_MERGE_DOMAIN only where it indexes out of bounds -- and then the record's own SA-arm lines (already written,
+    # main.rs:395-515) stay
+    M = "268435455M"
+    recs = [dict(tid=0, pos=1000, flag=0, mapq=60, cigar="100M60D2M60D2M60D2M60D100M"),                # -m 200: [ab, bc, bc, cd]
+            dict(tid=1, pos=7000, flag=16, mapq=60, cigar="100M60D2M60D500M70D400M80D900M90D100M"),   # -m 200: [ab, d, e] (c is lost)
+            dict(tid=2, pos=50, flag=0, mapq=60, cigar="5M60I60D2M60D2M60I60D2M60D2M60D2M60D7M"),     # Ins between the Dels
+            dict(tid=3, pos=9, flag=0, mapq=60, cigar="".join("3M%dD" % (50 + k) for k in range(40)) + "8M"),   # -m 1000: 40 events -> 996 lines
+            # the far-edge predicate through a u32 wrap: reachable with the default -i 50 -m 5 (kernel 4a<false> asks for the re-run)
+            dict(tid=0, pos=77, flag=0, mapq=60, cigar="10M60D" + M * 15 + "268435413D5M70D700M80D900M90D10M")]
+    hb = pack_records(recs, RREF)
+    n_lines = {}
+    for p in (ExlrParams.make(merge_min=200), ExlrParams.make(), ExlrParams.make(indel_min=1, merge_min=130), ExlrParams.make(merge_min=125)):
+        for ck, rpc in VARIANTS:
+            want, res = gpu_check(hb, p, ck, rpc, label=f"literal merge m{p.merge_min} i{p.indel_min} k{ck}")
+            assert res.status == 0
+            n_lines[p.merge_min] = np.diff(res.line_off.astype(np.int64)).tolist()
+    assert n_lines[200] == [4, 3, 8, 462, 3] and n_lines[5] == [4, 5, 8, 40, 3]
+    want, res = gpu_check(pack_records(recs[:4], RREF), ExlrParams.make(indel_min=55, merge_min=1000), label="literal merge m1000")
+    assert res.status == 0 and res.n_events > 900
+    want, res = gpu_check(hb, ExlrParams.make(indel_min=55, merge_min=1000), label="literal merge m1000 wrap panic")
+    assert res.status == -20 and res.err_read == 4 and res.n_err_lines == 0
+    bad = dict(tid=1, pos=5000, flag=0, mapq=60, cigar="10M60D2M60D2M60D10M3000S", sa="chr2,7001,+,3000S500M,60,1;chr1,99,-,20M,60,0;")
+    for at in (0, 3, 5):
+        hbad = pack_records(recs[:at] + [bad] + recs[at:], RREF)
+        want, res = gpu_check(hbad, ExlrParams.make(merge_min=200), label=f"merge panic keeps SA lines @{at}")
+        assert res.status == -20 and res.err_read == at and res.n_err_lines == 2
+        want, res = gpu_check(hbad, ExlrParams.make(merge_min=200), verbose=True, label=f"merge panic keeps SA lines @{at} -v")
+
+
 @pytest.mark.parametrize("long_records", [1, 2, 3])
 def test_long_record_paths_behind_the_screen(long_records):
     # records of more than 256 ops behind the event screen: a warp of kernel 1b each (1), kernel 1c = flat block scan of the
@@ -214,8 +245,8 @@ def test_batch_reuse_and_two_in_flight():
         b1.fill(x); b2.fill(y)
         b1.submit(); b2.submit()
         r1, r2 = b1.wait(), b2.wait()
-        check_result(x, p, r1, b1.format_lines(r1, False, None, 0, r1.n_events if r1.status == 0 else int(r1.line_off[r1.err_read])), label=f"reuse{rnd}a")
-        check_result(y, p, r2, b2.format_lines(r2, False, None, 0, r2.n_events if r2.status == 0 else int(r2.line_off[r2.err_read])), label=f"reuse{rnd}b")
+        check_result(x, p, r1, b1.format_lines(r1, False, None, 0, r1.n_valid_lines()), label=f"reuse{rnd}a")
+        check_result(y, p, r2, b2.format_lines(r2, False, None, 0, r2.n_valid_lines()), label=f"reuse{rnd}b")
         t = b1.timing()
         # kernels 0, 3a, 3b, 4a, 4b, header + either the screened CIGAR path (1a, 1b claim, 1b walk) or, after an event-dense batch, kernel 1
         assert t.launches in (7, 9) and t.kernels_ms > 0 and (t.screen_ms > 0) == (t.launches == 9)

@@ -12,7 +12,7 @@ EXLR_ERR_MERGE_DOMAIN = -20
 
 def _compare(hb, p, verbose=False):
     text, err = py_run(hb, p, verbose)
-    r = oracle_c.run(hb, p, merge_mode=1)           # literal merge, like the Python restatement
+    r = oracle_c.run(hb, p)
     got = oracle_c.format_lines(hb, r.events, verbose).decode()
     if err is None:
         assert r.status == 0, (r.status, r.err_read)
@@ -34,20 +34,37 @@ def test_random_params(seed):
     _compare(rand_batch(seed, 150, qnames=True), rand_params(seed), verbose=(seed % 7 == 0))
 
 
-def test_merge_domain_flagged_exactly():
-    # merge_mode 0 must flag exactly the records where the literal >2 loop is not the identity
-    n_flag = 0
+def test_literal_merge_loop_beyond_the_identity():
+    # merge_min > 2 * indel_min: the >2 loop (main.rs:636-742) merges, duplicates or panics; both restatements run it literally
+    n_panic = n_changed = 0
     for seed in range(200, 260):
         hb = rand_batch(seed, 60)
         p = ExlrParams.make(indel_min=1, merge_min=150, exclude_flag=0, mapq=0)
-        lit = oracle_c.run(hb, p, merge_mode=1)
-        dom = oracle_c.run(hb, p, merge_mode=0)
-        if dom.status == EXLR_ERR_MERGE_DOMAIN:
-            n_flag += 1
-            assert lit.status != 0 and lit.err_read >= dom.err_read or lit.status == 0 or lit.err_read >= dom.err_read
-            k = int(dom.err_read)
-            assert (dom.events["read_idx"] < k).all()
-    assert n_flag > 10
+        r = _compare(hb, p)
+        n_panic += r.status == EXLR_ERR_MERGE_DOMAIN
+        n_changed += r.status == 0
+    assert n_panic > 5 and n_changed >= 1
+    # four close Dels -> [ab, bc, bc, cd]: duplicates, no panic
+    from excord_lr_b200.batch import pack_records
+    from randrec import REF_NAMES
+    hb = pack_records([dict(tid=0, pos=1000, flag=0, mapq=60, cigar="100M60D2M60D2M60D2M60D100M")], REF_NAMES)
+    r = _compare(hb, ExlrParams.make(merge_min=200))
+    assert r.status == 0 and len(r.events) == 4
+    assert r.events["lend"].tolist() == [1100, 1162, 1162, 1224] and r.events["rstart"].tolist() == [1222, 1284, 1284, 1346]
+
+
+def test_indel_arm_panic_keeps_the_sa_arm_lines():
+    # the SA arm's f.write calls (main.rs:395-515) precede the indel arm (main.rs:523-742): when the merge loop panics the
+    # record's split / large-INS lines are already in the BufWriter and reach the file on unwind
+    from excord_lr_b200.batch import pack_records
+    from randrec import REF_NAMES
+    recs = [dict(tid=0, pos=100, flag=0, mapq=60, cigar="100M60D200M"),
+            dict(tid=1, pos=5000, flag=0, mapq=60, cigar="10M60D2M60D2M60D10M3000S", sa="chr2,7001,+,3000S500M,60,1;"),
+            dict(tid=0, pos=900, flag=0, mapq=60, cigar="100M60D200M")]
+    hb = pack_records(recs, REF_NAMES)
+    r = _compare(hb, ExlrParams.make(merge_min=200))
+    assert r.status == EXLR_ERR_MERGE_DOMAIN and r.err_read == 1 and r.n_err_lines == 1 and len(r.events) == 2
+    assert r.line_off.tolist() == [0, 1, 2, 2]
 
 
 def test_synth_c1_small():
