@@ -63,7 +63,8 @@ class _Result(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("classify_ms", C.c_float), ("cigar_ms", C.c_float), ("sa_cigar_ms", C.c_float),
                 ("sa_parse_ms", C.c_float), ("scan_ms", C.c_float), ("place_ms", C.c_float), ("kernels_ms", C.c_float),
-                ("d2h_ms", C.c_float), ("launches", C.c_uint32), ("screen_ms", C.c_float)]
+                ("d2h_ms", C.c_float), ("launches", C.c_uint32), ("screen_ms", C.c_float),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -91,6 +92,7 @@ def load_library() -> C.CDLL:
     lib.exlr_batch_alloc.argtypes = [vp, u64, u64, u64, u64, C.POINTER(vp)]
     lib.exlr_batch_free.argtypes = [vp]
     lib.exlr_batch_get_views.argtypes = [vp, C.POINTER(_Views)]
+    lib.exlr_batch_grow.argtypes = [vp, u64]
     lib.exlr_submit.argtypes = [vp, u64]
     lib.exlr_upload.argtypes = [vp, u64]
     lib.exlr_submit_resident.argtypes = [vp]
@@ -103,7 +105,7 @@ def load_library() -> C.CDLL:
     lib.exlr_strerror.restype = C.c_char_p
     lib.exlr_strerror.argtypes = [i32]
     lib.exlr_last_cuda_error.restype = C.c_char_p
-    for f in ("exlr_create", "exlr_set_option", "exlr_batch_alloc", "exlr_batch_get_views", "exlr_submit", "exlr_upload",
+    for f in ("exlr_create", "exlr_set_option", "exlr_batch_alloc", "exlr_batch_get_views", "exlr_batch_grow", "exlr_submit", "exlr_upload",
               "exlr_submit_resident", "exlr_wait", "exlr_wait_resident", "exlr_wait_text", "exlr_get_timing"):
         getattr(lib, f).restype = i32
     _lib = lib
@@ -191,6 +193,11 @@ class DeviceBatch:
         self.n_reads = n
         self._qn = None
         return self
+
+    def grow(self, max_events: int):
+        """Larger event buffers, same packed records: the answer to ExlrCapacityError (then submit again)."""
+        _check(self.lib.exlr_batch_grow(self.handle, max_events))
+        self.max_events = max(self.max_events, max_events)
 
     def submit(self, n_reads: Optional[int] = None):
         _check(self.lib.exlr_submit(self.handle, self.n_reads if n_reads is None else n_reads))
@@ -310,9 +317,9 @@ def extract(hb: HostBatch, params: ExlrParams, device: int = 0, cigar_kernel: in
         ex.set_option(EXLR_OPT_READS_PER_CTA, reads_per_cta)
         ex.set_option(EXLR_OPT_DEVICE_FORMAT, int(device_format))
         ex.set_option(EXLR_OPT_LONG_RECORDS, long_records)
-        for attempt in range(5):
-            b = ex.batch_for(hb, max_events)
-            try:
+        b = ex.batch_for(hb, max_events)
+        try:
+            for attempt in range(5):
                 b.submit()
                 try:
                     dtext = b.wait_text()[1] if device_format else None
@@ -321,14 +328,11 @@ def extract(hb: HostBatch, params: ExlrParams, device: int = 0, cigar_kernel: in
                 except ExlrCapacityError as e:
                     if not grow or attempt == 4:
                         raise
-                    max_events = e.needed + 16
+                    b.grow(e.needed + 16)                   # same packed records, larger event buffers
                     continue
-                k = res.n_events
-                if res.status <= -10:
-                    k = res.n_valid_lines()                 # lines the reference had written when it panicked
-                text = b.format_lines(res, verbose, hb.qnames, 0, k)
+                text = b.format_lines(res, verbose, hb.qnames, 0, res.n_valid_lines())
                 return res, text
-            finally:
-                b.free()
+        finally:
+            b.free()
     finally:
         ex.close()

@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <new>
 #include <string>
@@ -41,10 +42,13 @@ struct exlr_ctx {
     int trace = 0;                             // EXLR_OPT_TRACE: kernel 1 writes a per-CTA timeline (debug)
     int stage_timing = 1;                      // EXLR_OPT_STAGE_TIMING: CUDA events between the kernels (exlr_timing per stage)
     int k1_ctas = 0;                           // EXLR_OPT_K1_CTAS_PER_SM (0 = 3 when overlapping, which leaves room for the SA branch, else 4)
+    int k1a_ctas = 8, k1_waves = 3, sms = 148; // EXLR_OPT_K1A_CTAS_PER_SM, EXLR_OPT_K1_WAVES; multiprocessors of `device`
     uint32_t reads_per_cta = 0;                // EXLR_OPT_READS_PER_CTA (0 = auto)
     int device_format = 0;                     // EXLR_OPT_DEVICE_FORMAT: kernels 5a/5b write the output lines; read with exlr_wait_text
     int long_records = 0;                      // EXLR_OPT_LONG_RECORDS: 0 auto (by mean CIGAR length), 1 never, 2 kernel 1c, 3 kernel 1d
-    int skip_screen = 0;                       // auto mode: batches left to run without the screen pass (the last screened one was event-dense)
+    std::atomic<int> skip_screen{0};           // auto mode: batches left to run without the screen pass (the last screened one was event-dense);
+                                               // written by whoever waits a batch, read by whoever submits the next (two threads in the CLI)
+    std::atomic<uint64_t> ev_hint{0}, text_hint{0};   // events / text bytes of the last waited batch: how much exlr_submit copies back speculatively
     bool far_mode = false;                     // merge_min > 2 * indel_min: the >2 merge loop (main.rs:636-742) can change the events, kernels 4a/4b run their FAR variants
 };
 
@@ -56,14 +60,20 @@ struct exlr_batch {
     bool screened = false;                     // the last submit ran kernels 1a + 1b instead of kernel 1
     exlr_batch_views hv{};                     // pinned host views
     void* h_slab = nullptr;                    // pinned: inputs
-    void* h_out = nullptr;                     // pinned: ctrl + line_off + events
+    void* h_out = nullptr;                     // pinned: ctrl + line_off
+    void* d_evslab = nullptr;                  // device: everything sized by max_events (raw, sa_ev, events, text); exlr_batch_grow replaces it
+    uint64_t d2h_events = 0, d2h_text = 0;     // events / text bytes the last submit copied back behind its kernels (speculative, see run_kernels)
+    bool have_line_off = false;                // ... and the line offsets
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;     // bytes the last submit + wait moved over PCIe
     Ctrl* h_ctrl = nullptr; uint32_t* h_line_off = nullptr; exlr_event* h_events = nullptr;
     Ctrl* h_ctrl_dev = nullptr;                // device address of h_ctrl (mapped pinned memory): the result header is stored there by a kernel
     char* h_text = nullptr;                    // pinned: formatted lines (allocated with the batch when EXLR_OPT_DEVICE_FORMAT is set)
     bool formatted = false;                    // the last submit ran kernels 5a/5b
+    bool device_format = false;                // EXLR_OPT_DEVICE_FORMAT was set when the batch was allocated
     void* d_slab = nullptr;                    // one device allocation, carved up below
     DevBatch dv{};
     size_t ctrl_bytes = 0;                     // ctrl + both scan status arrays (one memset)
+    size_t scan_c_bytes = 0;                   // kernel 5a's scan status words (second memset, only with EXLR_OPT_DEVICE_FORMAT)
     uint64_t n_reads = 0, n_ops = 0;
     bool submitted = false, resident_uploaded = false, have_timing = false, stage_timed = false;
     bool far_ran = false;                      // the last submit ran the FAR variants of kernels 4a/4b
@@ -79,6 +89,44 @@ static constexpr size_t kRawHeadroom = 256 * 1024;
 static constexpr size_t kTextBytesPerLine = 96;
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Everything whose size follows max_events: the raw / SA / final event buffers, the text buffers of kernels 5a/5b with their
+// scan status words, and the pinned host copies.  Separate from the input + per-record slab so that exlr_batch_grow can
+// replace it while the packed records stay where they are.
+static void free_event_buffers(exlr_batch* b)
+{
+    cudaFree(b->d_evslab); b->d_evslab = nullptr;
+    cudaFreeHost(b->h_events); b->h_events = nullptr;
+    cudaFreeHost(b->h_text); b->h_text = nullptr;
+}
+
+static int alloc_event_buffers(exlr_batch* b, uint64_t max_events)
+{
+    if (max_events == 0 || max_events >= 0xfff00000ull) return EXLR_ERR_ARG;
+    const bool fmt = b->device_format;
+    const size_t text_cap = fmt ? max_events * kTextBytesPerLine : 0;
+    if (text_cap >= 0xfffffff0ull) return EXLR_ERR_ARG;
+    const uint32_t ttiles = fmt ? text_scan_tiles((uint32_t)max_events) : 0;
+    size_t dof = 0;
+    auto dcarve = [&](size_t bytes) { size_t at = dof; dof = align_up(dof + bytes, 256); return at; };
+    const size_t d_scan = dcarve((size_t)ttiles * 8), d_raw = dcarve((max_events + kRawHeadroom) * sizeof(RawEv)),
+                 d_saev = dcarve(max_events * sizeof(exlr_event)), d_toff = dcarve(fmt ? (max_events + 1) * 4 : 0),
+                 d_text = dcarve(text_cap + 16), d_ev = dcarve(max_events * sizeof(exlr_event));
+    cudaError_t e = cudaMalloc(&b->d_evslab, dof);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_events, max_events * sizeof(exlr_event), cudaHostAllocDefault);
+    if (e == cudaSuccess && fmt) e = cudaHostAlloc((void**)&b->h_text, text_cap + 16, cudaHostAllocDefault);
+    if (e != cudaSuccess) { free_event_buffers(b); return cuda_fail(e, "event buffers"); }
+    char* ds = (char*)b->d_evslab;
+    DevBatch& v = b->dv;
+    v.scan_c = (unsigned long long*)(ds + d_scan); b->scan_c_bytes = (size_t)ttiles * 8;
+    v.raw = (RawEv*)(ds + d_raw); v.raw_cap = (uint32_t)(max_events + kRawHeadroom);
+    v.sa_ev = (exlr_event*)(ds + d_saev);
+    v.text_off = fmt ? (uint32_t*)(ds + d_toff) : nullptr; v.text = (uint8_t*)(ds + d_text); v.text_cap = (uint32_t)text_cap;
+    v.events = (exlr_event*)(ds + d_ev);
+    v.max_events = (uint32_t)max_events;
+    b->hv.max_events = max_events;
+    return EXLR_OK;
+}
 
 extern "C" {
 
@@ -145,10 +193,11 @@ int exlr_create(const exlr_params* p, int device, const char* const* ref_names, 
         return EXLR_ERR_CUDA;
     }
     CK(cudaSetDevice(device));
-    CK(configure_kernels(device));
+    int sms = 0;
+    CK(configure_kernels(device, &sms));
     exlr_ctx* c = new (std::nothrow) exlr_ctx();
     if (!c) return EXLR_ERR_NOMEM;
-    c->device = device; c->params = *p; c->n_ref = n_ref;
+    c->device = device; c->params = *p; c->n_ref = n_ref; c->sms = sms;
     DevParams& d = c->dparams;
     d.mapq = p->mapq; d.exclude_flag = p->exclude_flag; d.exclude_secondary = p->exclude_secondary;
     d.exclude_unmapped = p->exclude_unmapped; d.split_only = p->split_only; d.indel_min = p->indel_min;
@@ -191,10 +240,10 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
     case EXLR_OPT_OVERLAP: c->overlap = value != 0; return EXLR_OK;
     case EXLR_OPT_DEVICE_FORMAT: c->device_format = value != 0; return EXLR_OK;
     case EXLR_OPT_LONG_RECORDS: if (value < 0 || value > 3) return EXLR_ERR_ARG; c->long_records = (int)value; return EXLR_OK;
-    case EXLR_OPT_K1A_CTAS_PER_SM: if (value < 1 || value > 8) return EXLR_ERR_ARG; set_k1a_ctas_per_sm((int)value); return EXLR_OK;
+    case EXLR_OPT_K1A_CTAS_PER_SM: if (value < 1 || value > 8) return EXLR_ERR_ARG; c->k1a_ctas = (int)value; return EXLR_OK;
     case EXLR_OPT_TRACE: if (value < 0 || value > 7) return EXLR_ERR_ARG; c->trace = (int)value; return EXLR_OK;
     case EXLR_OPT_STAGE_TIMING: c->stage_timing = value != 0; return EXLR_OK;
-    case EXLR_OPT_K1_WAVES: if (value < 1 || value > 16) return EXLR_ERR_ARG; set_k1_waves((int)value); return EXLR_OK;
+    case EXLR_OPT_K1_WAVES: if (value < 1 || value > 16) return EXLR_ERR_ARG; c->k1_waves = (int)value; return EXLR_OK;
     case EXLR_OPT_K1_CTAS_PER_SM: if (value < 0 || value > 4) return EXLR_ERR_ARG; c->k1_ctas = (int)value; return EXLR_OK;
     default: return EXLR_ERR_ARG;
     }
@@ -212,8 +261,8 @@ void exlr_batch_free(exlr_batch* b)
     if (b->ev_k1_end) cudaEventDestroy(b->ev_k1_end);
     if (b->stream2) cudaStreamDestroy(b->stream2);
     if (b->stream) cudaStreamDestroy(b->stream);
-    cudaFree(b->d_slab);
-    cudaFreeHost(b->h_slab); cudaFreeHost(b->h_out); cudaFreeHost(b->h_text);
+    cudaFree(b->d_slab); cudaFree(b->d_evslab);
+    cudaFreeHost(b->h_slab); cudaFreeHost(b->h_out); cudaFreeHost(b->h_events); cudaFreeHost(b->h_text);
     delete b;
 }
 
@@ -244,17 +293,13 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     // ---- pinned host output slab
     size_t oo = 0;
     auto ocarve = [&](size_t bytes) { size_t at = oo; oo = align_up(oo + bytes, A); return at; };
-    const size_t o_ctrl = ocarve(sizeof(Ctrl)), o_loff = ocarve((R + 1) * 4), o_ev = ocarve(max_events * sizeof(exlr_event));
+    const size_t o_ctrl = ocarve(sizeof(Ctrl)), o_loff = ocarve((R + 1) * 4);
     e = cudaHostAlloc(&b->h_out, oo, cudaHostAllocMapped);
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostAlloc(outputs)"); }
     b->h_ctrl = (Ctrl*)((char*)b->h_out + o_ctrl); b->h_line_off = (uint32_t*)((char*)b->h_out + o_loff);
-    b->h_events = (exlr_event*)((char*)b->h_out + o_ev);
     e = cudaHostGetDevicePointer((void**)&b->h_ctrl_dev, b->h_ctrl, 0);
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostGetDevicePointer"); }
-    if (c->device_format) {
-        e = cudaHostAlloc((void**)&b->h_text, max_events * kTextBytesPerLine + 16, cudaHostAllocDefault);
-        if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostAlloc(text)"); }
-    }
+    b->device_format = c->device_format != 0;
     // ---- device slab
     const uint32_t tiles = scan_tiles((uint32_t)R);
     const bool need_pool = c->params.max_supp_alignm + 1 > (uint64_t)kLocalSegs;
@@ -262,15 +307,11 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     size_t dof = 0;
     auto dcarve = [&](size_t bytes) { size_t at = dof; dof = align_up(dof + bytes, A); return at; };
     const size_t bits_bytes = align_up((R + 31) / 32 * 4, 16);
-    const uint32_t ttiles = c->device_format ? text_scan_tiles((uint32_t)max_events) : 0;
-    const size_t text_cap = c->device_format ? max_events * kTextBytesPerLine : 0;
-    if (text_cap >= 0xfffffff0ull) { exlr_batch_free(b); return EXLR_ERR_ARG; }
-    const size_t d_ctrl = dcarve(sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes + (size_t)ttiles * 8);   // ctrl | scan_a | scan_b | dirty_bits | scan_c : one memset
+    const size_t d_ctrl = dcarve(sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes);   // ctrl | scan_a | scan_b | dirty_bits : one memset (scan_c lives with the event buffers)
     const size_t d_cigar = dcarve((max_ops + 4) * 4 + 16), d_coff = dcarve((R + 1) * 8), d_pos = dcarve(R * 4), d_tid = dcarve(R * 4),
                  d_flag = dcarve(R * 2), d_mapq = dcarve(R), d_kind = dcarve(R), d_soff = dcarve((R + 1) * 4), d_sab = dcarve(max_sa_bytes + 16),
                  d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_slist = dcarve((max_ops / 512 + 16) * 4), d_ssum = dcarve((max_ops / 512 + 16) * 4), d_sflag = dcarve(max_ops / 512 + 16), d_llist = dcarve(R * 4), d_far = dcarve(R * 8), d_shlist = dcarve(R * 4), d_wlist = dcarve(R * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
-                 d_raw = dcarve((max_events + kRawHeadroom) * sizeof(RawEv)), d_saev = dcarve(max_events * sizeof(exlr_event)),
-                 d_pool = dcarve(pool_cap * sizeof(Seg)), d_dbg = dcarve(8192 * 32), d_toff = dcarve(c->device_format ? (max_events + 1) * 4 : 0), d_text = dcarve(text_cap + 16), d_loff = dcarve((R + 1) * 4), d_ev = dcarve(max_events * sizeof(exlr_event));
+                 d_pool = dcarve(pool_cap * sizeof(Seg)), d_dbg = dcarve(8192 * 32), d_loff = dcarve((R + 1) * 4);
     e = cudaMalloc(&b->d_slab, dof);
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaMalloc(batch)"); }
     char* ds = (char*)b->d_slab;
@@ -278,20 +319,19 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     v.ctrl = (Ctrl*)(ds + d_ctrl);
     v.scan_a = (unsigned long long*)(ds + d_ctrl + sizeof(Ctrl)); v.scan_b = v.scan_a + tiles;
     v.dirty_bits = (uint32_t*)(v.scan_b + tiles); v.step_list = (uint32_t*)(ds + d_slist); v.step_sum = (uint32_t*)(ds + d_ssum); v.step_flag = (uint8_t*)(ds + d_sflag); v.long_list = (uint32_t*)(ds + d_llist); v.far_list = (uint2*)(ds + d_far); v.short_list = (uint32_t*)(ds + d_shlist); v.warp_list = (uint32_t*)(ds + d_wlist);
-    v.scan_c = (unsigned long long*)((char*)v.dirty_bits + bits_bytes);
-    v.text_off = c->device_format ? (uint32_t*)(ds + d_toff) : nullptr; v.text = (uint8_t*)(ds + d_text); v.text_cap = (uint32_t)text_cap;
-    b->ctrl_bytes = sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes + (size_t)ttiles * 8;
+    b->ctrl_bytes = sizeof(Ctrl) + (size_t)tiles * 16 + bits_bytes;
     v.cigar = (uint32_t*)(ds + d_cigar); v.cigar_off = (unsigned long long*)(ds + d_coff); v.pos = (int32_t*)(ds + d_pos);
     v.tid = (int32_t*)(ds + d_tid); v.flag = (uint16_t*)(ds + d_flag); v.mapq = (uint8_t*)(ds + d_mapq); v.sa_kind = (uint8_t*)(ds + d_kind);
     v.sa_off = (uint32_t*)(ds + d_soff); v.sa_bytes = (uint8_t*)(ds + d_sab);
     v.ref_bytes = c->d_ref_bytes; v.ref_off = c->d_ref_off; v.n_ref = c->n_ref;
-    v.tile_cnt = (uint32_t*)(ds + d_tcnt); v.raw_cap = (uint32_t)(max_events + kRawHeadroom);
+    v.tile_cnt = (uint32_t*)(ds + d_tcnt);
     v.k1 = (uint2*)(ds + d_k1); v.csa = (uint32_t*)(ds + d_csa); v.sa_list = (uint32_t*)(ds + d_list); v.sa_base = (uint32_t*)(ds + d_base);
-    v.sa_sum = (SaSum*)(ds + d_sum); v.raw = (RawEv*)(ds + d_raw); v.sa_ev = (exlr_event*)(ds + d_saev);
+    v.sa_sum = (SaSum*)(ds + d_sum);
     v.seg_pool = (Seg*)(ds + d_pool); v.seg_pool_cap = (uint32_t)pool_cap;
     b->d_dbg = (unsigned long long*)(ds + d_dbg); v.dbg = nullptr;
-    v.line_off = (uint32_t*)(ds + d_loff); v.events = (exlr_event*)(ds + d_ev);
-    v.n_reads = 0; v.max_events = (uint32_t)max_events;
+    v.line_off = (uint32_t*)(ds + d_loff);
+    v.n_reads = 0;
+    { const int rc = alloc_event_buffers(b, max_events); if (rc) { exlr_batch_free(b); return rc; } }
     // the SA branch (kernels 0, 3a, 3b) is the longer chain: its stream gets the higher priority so its CTAs are placed first
     // whenever kernel 1 (stream2) frees a slot
     int prio_lo = 0, prio_hi = 0;
@@ -306,6 +346,18 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "stream/event creation"); }
     *out = b;
     return EXLR_OK;
+}
+
+int exlr_batch_grow(exlr_batch* b, uint64_t max_events)
+{
+    if (!b) return EXLR_ERR_ARG;
+    if (max_events <= b->hv.max_events) return EXLR_OK;
+    CK(cudaSetDevice(b->ctx->device));
+    CK(cudaStreamSynchronize(b->stream));
+    if (b->stream2) CK(cudaStreamSynchronize(b->stream2));
+    free_event_buffers(b);
+    b->submitted = false; b->have_timing = false;
+    return alloc_event_buffers(b, max_events);
 }
 
 int exlr_batch_get_views(exlr_batch* b, exlr_batch_views* v)
@@ -327,6 +379,7 @@ static int copy_inputs(exlr_batch* b, uint64_t n)
 {
     const exlr_batch_views& h = b->hv; DevBatch& d = b->dv; cudaStream_t st = b->stream;
     const uint64_t ops = h.cigar_off[n], sab = h.sa_off[n];
+    b->h2d_bytes = ops * 4 + sab + n * 24 + 12;
     if (ops) CK(cudaMemcpyAsync((void*)d.cigar, h.cigar, ops * 4, cudaMemcpyHostToDevice, st));
     if (n == h.max_reads) {
         // a full batch: cigar_off .. sa_off are carved back to back with the same relative offsets on both sides, one copy moves them all
@@ -360,17 +413,26 @@ static uint32_t auto_rpc(uint64_t n_reads, uint64_t n_ops)
     return (uint32_t)rpc;
 }
 
-static int run_kernels(exlr_batch* b)
+// How many events / text bytes a submit copies back behind its kernels without knowing the real count: a little more than the
+// last waited batch of this context produced.  exlr_wait then needs one synchronisation; what the guess missed is fetched after it.
+static uint64_t guess_with_margin(uint64_t hint, uint64_t first_guess, uint64_t cap)
+{
+    const uint64_t g = hint ? hint + hint / 8 + 1024 : first_guess;
+    return g < cap ? g : cap;
+}
+
+static int run_kernels(exlr_batch* b, bool prefetch_results)
 {
     exlr_ctx* c = b->ctx; cudaStream_t st = b->stream; DevBatch& d = b->dv;
     b->launches = 0; b->stage_timed = c->stage_timing != 0;
     d.dbg = c->trace ? b->d_dbg : nullptr; d.dbg_sel = (uint32_t)c->trace;
     if (c->trace) CK(cudaMemsetAsync(b->d_dbg, 0, 8192 * 32, st));
     CK(cudaMemsetAsync(d.ctrl, 0, b->ctrl_bytes, st));
+    if (b->scan_c_bytes) CK(cudaMemsetAsync(d.scan_c, 0, b->scan_c_bytes, st));
     // kernel 1 needs nothing from kernel 0, so it runs on a second stream beside the SA branch (0 -> 3a -> 3b); 4a joins them
     d.prim_slots = 0; d.capt_log2 = 0; d.k1_gated = 0;
     const bool overlap = c->overlap && !c->params.split_only;
-    set_k1_ctas_per_sm(c->k1_ctas ? c->k1_ctas : (overlap ? 3 : 4));
+    d.hc = HostCfg{c->sms, c->k1_ctas ? c->k1_ctas : (overlap ? 3 : 4), c->k1a_ctas, c->k1_waves};
     uint32_t rpc = 0;
     const int variant = c->cigar_kernel == 1 ? 1 : 0;
     b->screened = false;
@@ -382,7 +444,7 @@ static int run_kernels(exlr_batch* b)
         // everything: after such a batch the next few run unscreened, then the screen is tried again.
         // (kernel 1a indexes the CIGAR array by 32-bit vector numbers)
         bool want = c->cigar_kernel == 3;
-        if (c->cigar_kernel == 0) { if (c->skip_screen > 0) c->skip_screen--; else want = true; }
+        if (c->cigar_kernel == 0) { if (c->skip_screen.load() > 0) c->skip_screen.fetch_sub(1); else want = true; }
         b->screened = want && b->n_ops < (1ull << 33) && b->n_ops > 0;
         uint32_t n_tiles = 0;
         d.k1_gated = b->screened ? 1u : 0u;
@@ -424,6 +486,22 @@ static int run_kernels(exlr_batch* b)
     launch_header(d, b->h_ctrl_dev, st); b->launches++;            // the result header, stored straight into pinned host memory
     b->far_ran = c->far_mode;
     CK(cudaEventRecord(b->ev[EV_K4B], st));
+    b->d2h_events = 0; b->d2h_text = 0; b->have_line_off = false; b->d2h_bytes = sizeof(Ctrl);
+    if (prefetch_results) {
+        // results follow the kernels on the same stream, sized by a guess (the counts live on the device): lines when the batch
+        // formats them (exlr_wait_text), else line offsets + events (exlr_wait)
+        if (b->formatted) {
+            b->d2h_text = guess_with_margin(c->text_hint.load(), b->n_reads * 16 + 65536, d.text_cap);
+            if (b->d2h_text) CK(cudaMemcpyAsync(b->h_text, d.text, b->d2h_text, cudaMemcpyDeviceToHost, st));
+            b->d2h_bytes += b->d2h_text;
+        } else {
+            CK(cudaMemcpyAsync(b->h_line_off, d.line_off, (b->n_reads + 1) * 4, cudaMemcpyDeviceToHost, st));
+            b->have_line_off = true;
+            b->d2h_events = guess_with_margin(c->ev_hint.load(), b->n_reads / 4 + 4096, d.max_events);
+            CK(cudaMemcpyAsync(b->h_events, d.events, b->d2h_events * sizeof(exlr_event), cudaMemcpyDeviceToHost, st));
+            b->d2h_bytes += (b->n_reads + 1) * 4 + b->d2h_events * sizeof(exlr_event);
+        }
+    }
     CK(cudaEventRecord(b->ev[EV_D2H], st));
     CK(cudaGetLastError());
     return EXLR_OK;
@@ -442,7 +520,7 @@ int exlr_submit(exlr_batch* b, uint64_t n_reads)
     rc = copy_inputs(b, n_reads);
     if (rc) return rc;
     CK(cudaEventRecord(b->ev[EV_H2D], b->stream));
-    rc = run_kernels(b);
+    rc = run_kernels(b, true);
     if (rc) return rc;
     b->submitted = true; b->have_timing = true;
     return EXLR_OK;
@@ -470,7 +548,7 @@ int exlr_submit_resident(exlr_batch* b)
     CK(cudaSetDevice(b->ctx->device));
     CK(cudaEventRecord(b->ev[EV_START], b->stream));
     CK(cudaEventRecord(b->ev[EV_H2D], b->stream));
-    int rc = run_kernels(b);
+    int rc = run_kernels(b, false);
     if (rc) return rc;
     b->submitted = true; b->have_timing = true;
     return EXLR_OK;
@@ -506,11 +584,12 @@ static int finish(exlr_batch* b, exlr_result* res, bool fetch)
         if (b->formatted) launch_k5(b->dv, st);
         launch_header(b->dv, b->h_ctrl_dev, st);
         b->far_ran = true; b->launches += b->formatted ? 6 : 4;
+        b->d2h_events = 0; b->d2h_text = 0; b->have_line_off = false;      // what was copied back before is stale
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(st));
     }
     const Ctrl& c = *b->h_ctrl;
-    if (b->screened && (uint64_t)c.n_flagged * 2 > (uint64_t)k1a_steps(b->n_ops)) b->ctx->skip_screen = 8;   // event-dense: see run_kernels
+    if (b->screened && (uint64_t)c.n_flagged * 2 > (uint64_t)k1a_steps(b->n_ops)) b->ctx->skip_screen.store(8);   // event-dense: see run_kernels
     res->n_events = c.n_events; res->n_kept = c.n_kept; res->n_sa_reads = c.n_sa; res->n_cap_dropped = c.n_dropped;
     if (c.overflow) {
         // n_events = the max_events that would have sufficed (all three counters keep counting past the capacity)
@@ -518,10 +597,20 @@ static int finish(exlr_batch* b, exlr_result* res, bool fetch)
         if (c.n_raw) { const uint64_t r = (uint64_t)b->dv.raw_cap + 2ull * c.n_raw; if (r > need) need = r; }
         res->status = EXLR_ERR_CAPACITY; res->n_events = need; return res->status;
     }
+    b->ctx->ev_hint.store(c.n_events); b->ctx->text_hint.store(c.text_bytes);
     if (fetch) {
-        CK(cudaMemcpyAsync(b->h_line_off, b->dv.line_off, (b->n_reads + 1) * 4, cudaMemcpyDeviceToHost, b->stream));
-        if (c.n_events) CK(cudaMemcpyAsync(b->h_events, b->dv.events, (size_t)c.n_events * sizeof(exlr_event), cudaMemcpyDeviceToHost, b->stream));
-        CK(cudaStreamSynchronize(b->stream));
+        // usually everything is here already (copied behind the kernels by exlr_submit); fetch what the guess missed
+        bool more = false;
+        if (!b->have_line_off) {
+            CK(cudaMemcpyAsync(b->h_line_off, b->dv.line_off, (b->n_reads + 1) * 4, cudaMemcpyDeviceToHost, b->stream));
+            b->have_line_off = true; more = true; b->d2h_bytes += (b->n_reads + 1) * 4;
+        }
+        if (c.n_events > b->d2h_events) {
+            const size_t at = (size_t)b->d2h_events, cnt = (size_t)c.n_events - at;
+            CK(cudaMemcpyAsync(b->h_events + at, b->dv.events + at, cnt * sizeof(exlr_event), cudaMemcpyDeviceToHost, b->stream));
+            b->d2h_events = c.n_events; more = true; b->d2h_bytes += cnt * sizeof(exlr_event);
+        }
+        if (more) CK(cudaStreamSynchronize(b->stream));
     }
     if (c.err_key) {
         const unsigned long long key = ~c.err_key;
@@ -554,9 +643,11 @@ int exlr_wait_text(exlr_batch* b, exlr_result* res, const char** text, uint64_t*
         CK(cudaStreamSynchronize(b->stream));
         nb = off;
     }
-    if (nb) {
-        CK(cudaMemcpyAsync(b->h_text, b->dv.text, nb, cudaMemcpyDeviceToHost, b->stream));
+    if (nb > b->d2h_text) {                                              // what the copy behind the kernels did not cover
+        const uint64_t at = b->d2h_text;
+        CK(cudaMemcpyAsync(b->h_text + at, b->dv.text + at, nb - at, cudaMemcpyDeviceToHost, b->stream));
         CK(cudaStreamSynchronize(b->stream));
+        b->d2h_text = nb; b->d2h_bytes += nb - at;
     }
     *text = b->h_text; *n_bytes = nb;
     return rc;
@@ -583,6 +674,7 @@ int exlr_get_timing(exlr_batch* b, exlr_timing* t)
     CK(cudaEventElapsedTime(&t->kernels_ms, b->ev[EV_H2D], b->ev[EV_K4B]));
     CK(cudaEventElapsedTime(&t->d2h_ms, b->ev[EV_K4B], b->ev[EV_D2H]));
     t->launches = b->launches;
+    t->h2d_bytes = b->h2d_bytes; t->d2h_bytes = b->d2h_bytes;
     return EXLR_OK;
 }
 

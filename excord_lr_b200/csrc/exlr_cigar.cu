@@ -958,12 +958,6 @@ __global__ void __launch_bounds__(256, 3) k1d_long(DevBatch B, DevParams P)
 // ======================================================================================
 // launchers
 // ======================================================================================
-static int g_k1_ctas_per_sm = 4;
-static int g_k1a_ctas_per_sm = 8;          // resident CTAs of the screen kernel per SM (fewer leave room for the SA branch beside it)
-static int g_k1_waves = 3;                 // grid = SMs x CTAs/SM x waves: > 1 trades prefetch depth for dynamic balance
-void set_k1a_ctas_per_sm(int n) { g_k1a_ctas_per_sm = n < 1 ? 1 : (n > 8 ? 8 : n); }
-void set_k1_waves(int n) { g_k1_waves = n < 1 ? 1 : (n > 16 ? 16 : n); }
-void set_k1_ctas_per_sm(int n) { g_k1_ctas_per_sm = n < 1 ? 1 : (n > 4 ? 4 : n); }
 
 size_t k1_flat_smem_bytes() { return sizeof(K1Smem); }
 cudaError_t configure_cigar_kernels() { return cudaFuncSetAttribute(k1_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)); }
@@ -990,13 +984,13 @@ void plan_k1(DevBatch& B, int variant, uint32_t rpc, uint32_t* tiles_out)
 void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc, cudaStream_t st)
 {
     if (variant == 1) {
-        const uint32_t blocks = min((B.n_reads + 7u) / 8u, (uint32_t)sm_count() * 32u);
+        const uint32_t blocks = min((B.n_reads + 7u) / 8u, (uint32_t)B.hc.sms * 32u);
         k1_warp<<<blocks, 256, 0, st>>>(B, P);
     } else {
         if (rpc < 1) rpc = 1;
         if (rpc > K1_MAX_RPC) rpc = K1_MAX_RPC;
         const uint32_t n_tiles = (B.n_reads + rpc - 1) / rpc;
-        uint32_t grid = min(n_tiles, (uint32_t)sm_count() * (uint32_t)g_k1_ctas_per_sm * (uint32_t)g_k1_waves);
+        uint32_t grid = min(n_tiles, (uint32_t)B.hc.sms * (uint32_t)B.hc.k1_ctas * (uint32_t)B.hc.k1_waves);
         if ((n_tiles + grid - 1) / grid > K1_MAX_TILES) grid = (n_tiles + K1_MAX_TILES - 1) / K1_MAX_TILES;
         k1_flat<<<grid, K1_THREADS, sizeof(K1Smem), st>>>(B, P, rpc, n_tiles, nullptr);
     }
@@ -1007,7 +1001,7 @@ void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc,
 void launch_k1c(const DevBatch& B, const DevParams& P, cudaStream_t st)
 {
     // one resident wave (the list is usually short or empty, and every CTA of a larger grid costs a launch slot just to see that)
-    uint32_t grid = min(B.n_reads, (uint32_t)sm_count() * (uint32_t)g_k1_ctas_per_sm);
+    uint32_t grid = min(B.n_reads, (uint32_t)B.hc.sms * (uint32_t)B.hc.k1_ctas);
     if ((B.n_reads + grid - 1) / grid > K1_MAX_TILES) grid = (B.n_reads + K1_MAX_TILES - 1) / K1_MAX_TILES;
     launch_dependent(k1_flat, grid ? grid : 1u, K1_THREADS, sizeof(K1Smem), st, B, P, 1u, B.n_reads, (const uint32_t*)B.long_list);
 }
@@ -1015,7 +1009,7 @@ void launch_k1c(const DevBatch& B, const DevParams& P, cudaStream_t st)
 // kernel 1d: one warp per listed long record, one resident wave
 void launch_k1d(const DevBatch& B, const DevParams& P, cudaStream_t st)
 {
-    const uint32_t grid = min((B.n_reads + 7u) / 8u, (uint32_t)sm_count() * 8u);
+    const uint32_t grid = min((B.n_reads + 7u) / 8u, (uint32_t)B.hc.sms * 8u);
     launch_dependent(k1d_long, grid ? grid : 1u, 256u, 0, st, B, P);
 }
 
@@ -1026,7 +1020,7 @@ void launch_k1a(const DevBatch& B, const DevParams& P, unsigned long long n_ops,
 {
     const uint32_t steps = k1a_steps(n_ops);
     uint32_t grid = (steps + K1A_THREADS / 32 - 1) / (K1A_THREADS / 32);
-    const uint32_t cap = (uint32_t)sm_count() * (uint32_t)g_k1a_ctas_per_sm;
+    const uint32_t cap = (uint32_t)B.hc.sms * (uint32_t)B.hc.k1a_ctas;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     if (sums) k1a_screen<true><<<grid, K1A_THREADS, 0, st>>>(B, P, n_ops);
@@ -1037,9 +1031,9 @@ void launch_k1b(const DevBatch& B, const DevParams& P, unsigned long long n_ops,
 {
     // the numbers of flagged steps and of claimed records live on the device: one resident wave strides over each list
     const uint32_t steps = k1a_steps(n_ops);
-    const uint32_t g1 = min((steps + K1B_THREADS / 32 - 1) / (K1B_THREADS / 32), (uint32_t)sm_count() * 8u);
+    const uint32_t g1 = min((steps + K1B_THREADS / 32 - 1) / (K1B_THREADS / 32), (uint32_t)B.hc.sms * 8u);
     launch_dependent(k1b_claim, g1 ? g1 : 1u, K1B_THREADS, 0, st, B, P, n_ops, use_k1c ? 1u : 0u);
-    const uint32_t g2 = min((B.n_reads + K1B_THREADS - 1) / K1B_THREADS, (uint32_t)sm_count() * 8u);
+    const uint32_t g2 = min((B.n_reads + K1B_THREADS - 1) / K1B_THREADS, (uint32_t)B.hc.sms * 8u);
     launch_dependent(k1b_walk, g2 ? g2 : 1u, K1B_THREADS, 0, st, B, P);
 }
 

@@ -138,7 +138,6 @@ __device__ __forceinline__ uint32_t tile_excl_scan(unsigned long long* status, u
 }
 
 // ---- host side: launch helpers shared by the launchers of every translation unit -------------------------------------
-int sm_count();                                        // multiprocessors of the configured device (exlr_order.cu)
 
 // Launch with the programmatic-stream-serialization attribute: the kernel may be placed while its predecessor in the stream
 // drains (it calls griddep_wait() before touching memory).  After anything but a kernel the attribute changes nothing.

@@ -84,8 +84,18 @@ struct Seg {
 };
 static constexpr int kLocalSegs = 10;                  // segments kept in local memory (-k 8 fits); more -> global pool
 
+// launch shapes, per context (host side only: the kernels never read them; they ride in the argument block so that every
+// launcher sees the values of the context the batch belongs to -- nothing about a launch is process-global)
+struct HostCfg {
+    int sms;                // multiprocessors of the context's device
+    int k1_ctas;            // persistent CTAs of kernel 1 per SM (1..4)
+    int k1a_ctas;           // resident CTAs of the screen kernel per SM (fewer leave room for the SA branch beside it)
+    int k1_waves;           // kernel 1 grid = SMs x CTAs/SM x waves: > 1 trades prefetch depth for dynamic balance
+};
+
 // ---- kernel argument block ----------------------------------------------------------------
 struct DevBatch {
+    HostCfg hc;
     // inputs
     const uint32_t* cigar; const unsigned long long* cigar_off;
     const int32_t* pos; const int32_t* tid; const uint16_t* flag; const uint8_t* mapq; const uint8_t* sa_kind;
@@ -134,10 +144,7 @@ struct DevParams {
 };
 
 // launchers (exlr_cigar.cu, exlr_sa.cu, exlr_order.cu)
-cudaError_t configure_kernels(int device);
-void set_k1_ctas_per_sm(int n);
-void set_k1_waves(int n);
-void set_k1a_ctas_per_sm(int n);
+cudaError_t configure_kernels(int device, int* sm_count_out);
 size_t k1_flat_smem_bytes();
 uint32_t scan_tiles(uint32_t n_reads);
 uint32_t text_scan_tiles(uint32_t max_events);

@@ -532,18 +532,16 @@ __global__ void __launch_bounds__(32) k6_header(Ctrl* ctrl, Ctrl* host_ctrl, con
 // ======================================================================================
 // launchers
 // ======================================================================================
-static int g_sm_count = 148;
-int sm_count() { return g_sm_count; }
 
 cudaError_t configure_cigar_kernels();
 cudaError_t configure_sa_kernels();
 
-cudaError_t configure_kernels(int device)
+cudaError_t configure_kernels(int device, int* sm_count_out)
 {
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) return e;
-    g_sm_count = prop.multiProcessorCount;
+    *sm_count_out = prop.multiProcessorCount;
     e = configure_cigar_kernels();
     if (e != cudaSuccess) return e;
     return configure_sa_kernels();
@@ -582,7 +580,7 @@ void launch_k4b(const DevBatch& B, const DevParams& P, bool far, cudaStream_t st
     uint32_t n = B.prim_slots > B.n_reads ? B.prim_slots : B.n_reads;
     const uint32_t room = B.raw_cap - B.prim_slots;
     if (room > n) n = room;
-    const uint32_t grid = min((n + 255u) / 256u, (uint32_t)sm_count() * 8u);
+    const uint32_t grid = min((n + 255u) / 256u, (uint32_t)B.hc.sms * 8u);
     if (far) launch_dependent(k4b_place<true>, grid ? grid : 1u, 256, 0, st, B, P);
     else launch_dependent(k4b_place<false>, grid ? grid : 1u, 256, 0, st, B, P);
 }
@@ -595,9 +593,9 @@ uint32_t text_scan_tiles(uint32_t max_events) { return (max_events + SCAN_THREAD
 void launch_k5(const DevBatch& B, cudaStream_t st)
 {
     // the line count lives on the device: both kernels are one resident wave (5a draws its tiles from a ticket)
-    const uint32_t ga = min((B.max_events + SCAN_THREADS - 1) / SCAN_THREADS, (uint32_t)sm_count() * 8u);
+    const uint32_t ga = min((B.max_events + SCAN_THREADS - 1) / SCAN_THREADS, (uint32_t)B.hc.sms * 8u);
     launch_dependent(k5a_line_bytes, ga ? ga : 1u, SCAN_THREADS, 0, st, B);
-    const uint32_t gb = min((B.max_events + 255u) / 256u, (uint32_t)sm_count() * 8u);
+    const uint32_t gb = min((B.max_events + 255u) / 256u, (uint32_t)B.hc.sms * 8u);
     launch_dependent(k5b_format, gb ? gb : 1u, 256, 0, st, B);
 }
 

@@ -643,7 +643,7 @@ void launch_k3a(const DevBatch& B, const DevParams& P, uint32_t mean_ops, cudaSt
 {
     // grid-stride over a device-side count: size for the worst case, cap at one resident wave (spare CTAs cost launch time).
     // Lanes per record by the batch's mean CIGAR length: the more records a warp walks side by side, the fewer waves.
-    const uint32_t cap = (uint32_t)sm_count() * 8u;
+    const uint32_t cap = (uint32_t)B.hc.sms * 8u;
     if (mean_ops <= 16) {
         const uint32_t g = min((B.n_reads + 127u) / 128u, cap);
         launch_dependent(k3a_sa_cigar<2>, g ? g : 1u, 256, 0, st, B, P);
@@ -661,7 +661,7 @@ void launch_k3b(const DevBatch& B, const DevParams& P, cudaStream_t st)
     // tiles of 64 SA records, grid-stride; the SA-record count lives on the device, so the grid is sized from the batch but
     // capped at the CTAs that are resident at once: spare CTAs of an over-sized grid cost a launch slot each just to read the
     // count and leave, and a CTA with a second tile doubles the kernel's span
-    const uint32_t gb = min((B.n_reads + K3B_TILE - 1u) / K3B_TILE, (uint32_t)sm_count() * K3B_CTAS);
+    const uint32_t gb = min((B.n_reads + K3B_TILE - 1u) / K3B_TILE, (uint32_t)B.hc.sms * K3B_CTAS);
     launch_dependent(k3b_sa_events, gb ? gb : 1u, K3B_THREADS, sizeof(K3bSmem), st, B, P);
 }
 

@@ -7,6 +7,7 @@
 #pragma once
 #include <zlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
@@ -34,18 +35,18 @@ public:
     std::vector<int64_t> ref_lens;
     std::string error;
 
-    ~BamReader() { if (fp_) fclose(fp_); }
+    ~BamReader() { if (fp_ && fp_ != stdin) fclose(fp_); }
 
     // BAM, or SAM text (plain or BGZF-compressed): htslib auto-detects the same way and the reference's Makefile feeds it
     // a .sam (reference Makefile:73-74).
     bool open(const std::string& path, int threads)
     {
-        fp_ = fopen(path.c_str(), "rb");
+        fp_ = path == "-" ? stdin : fopen(path.c_str(), "rb");     // "-": a stream (no seeking anywhere in this reader)
         if (!fp_) { error = "cannot open " + path; return false; }
         threads_ = threads < 1 ? 1 : threads;
         uint8_t magic[2] = {0, 0};
         const size_t got = fread(magic, 1, 2, fp_);
-        rewind(fp_);
+        pre_.assign(magic, magic + got);                           // pushed back: the input may be a pipe
         plain_ = !(got == 2 && magic[0] == 31 && magic[1] == 139);
         if (!fill()) { if (error.empty()) error = "empty or truncated input"; return false; }
         if (!plain_ && avail() >= 4 && memcmp(cur(), "BAM\1", 4) == 0) return read_header();
@@ -70,6 +71,19 @@ public:
 private:
     FILE* fp_ = nullptr;
     int threads_ = 1;
+    std::vector<uint8_t> pre_;        // bytes read while sniffing the format, served again by rd()
+
+    size_t rd(void* dst, size_t n)
+    {
+        size_t k = 0;
+        if (!pre_.empty()) {
+            k = std::min(n, pre_.size());
+            memcpy(dst, pre_.data(), k);
+            pre_.erase(pre_.begin(), pre_.begin() + (ptrdiff_t)k);
+            if (k == n) return k;
+        }
+        return k + fread((uint8_t*)dst + k, 1, n - k, fp_);
+    }
     std::vector<uint8_t> buf_;        // decompressed stream window
     size_t off_ = 0;                  // read cursor inside buf_
     bool eof_ = false, plain_ = false, sam_ = false;
@@ -89,7 +103,7 @@ private:
         if (plain_) {
             const size_t base = buf_.size(), chunk = 4u << 20;
             buf_.resize(base + chunk);
-            const size_t n = fread(buf_.data() + base, 1, chunk, fp_);
+            const size_t n = rd(buf_.data() + base, chunk);
             buf_.resize(base + n);
             if (n == 0) { eof_ = true; return false; }
             return true;
@@ -100,7 +114,7 @@ private:
         const size_t kMaxBlocks = 256 * (size_t)threads_;
         while (blks.size() < kMaxBlocks) {
             uint8_t h[18];
-            size_t n = fread(h, 1, 18, fp_);
+            size_t n = rd(h, 18);
             if (n == 0) { eof_ = true; break; }
             if (n < 18 || h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { error = "not a BGZF block"; eof_ = true; break; }
             // extra subfields: find BC
@@ -108,7 +122,7 @@ private:
             if (xlen < 6) { error = "BGZF block without BC field"; eof_ = true; break; }
             std::vector<uint8_t> extra(xlen);
             memcpy(extra.data(), h + 12, xlen < 6 ? xlen : 6);
-            if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, fp_) != (size_t)xlen - 6) { error = "truncated BGZF header"; eof_ = true; break; }
+            if (xlen > 6 && rd(extra.data() + 6, xlen - 6) != (size_t)xlen - 6) { error = "truncated BGZF header"; eof_ = true; break; }
             int bsize = -1;
             for (size_t i = 0; i + 4 <= extra.size();) {
                 uint16_t slen; memcpy(&slen, &extra[i + 2], 2);
@@ -121,7 +135,7 @@ private:
             const size_t body = total - head;                     // deflate data + crc32 + isize
             const size_t at = comp_.size();
             comp_.resize(at + body);
-            if (fread(comp_.data() + at, 1, body, fp_) != body) { error = "truncated BGZF block"; eof_ = true; break; }
+            if (rd(comp_.data() + at, body) != body) { error = "truncated BGZF block"; eof_ = true; break; }
             uint32_t isize; memcpy(&isize, comp_.data() + at + body - 4, 4);
             if (isize > 65536) { error = "corrupt BGZF isize"; eof_ = true; break; }
             blks.push_back({at, body - 8, utotal, isize});
@@ -283,11 +297,12 @@ private:
         const uint32_t l_name = bin_mq_nl & 0xff, n_cigar = flag_nc & 0xffff;
         r.tid = tid; r.pos = pos; r.mapq = (uint8_t)((bin_mq_nl >> 8) & 0xff); r.flag = (uint16_t)(flag_nc >> 16);
         size_t o = 32;
-        const size_t fixed = o + l_name + 4 * (size_t)n_cigar + (l_seq + 1) / 2 + l_seq;
+        const size_t seq_bytes = ((size_t)l_seq + 1) / 2 + (size_t)l_seq;       // size_t: a corrupt l_seq must not wrap into range
+        const size_t fixed = o + l_name + 4 * (size_t)n_cigar + seq_bytes;
         if (fixed > bs || l_name == 0) { error = "corrupt BAM record"; return false; }
         r.qname = (const char*)p + o; r.qname_len = l_name - 1; o += l_name;
         r.cigar = (const uint32_t*)(p + o); r.n_cigar = n_cigar; o += 4 * (size_t)n_cigar;   // 4-byte alignment is not guaranteed: copied below
-        o += (l_seq + 1) / 2 + l_seq;
+        o += seq_bytes;
         // aux walk: SA (first occurrence, like bam_aux_get) and CG
         r.sa_kind = 0; r.sa = nullptr; r.sa_len = 0;
         const uint8_t* cg = nullptr; uint32_t cg_n = 0; bool cg_seen = false;
@@ -312,8 +327,9 @@ private:
         // CIGAR bytes are only 4-byte aligned by luck: always hand out an aligned copy
         const uint8_t* src = (const uint8_t*)r.cigar; uint32_t n = n_cigar;
         // long-CIGAR convention (SAM spec 4.2.2).  Same test as htslib's bam_tag2cigar, which runs inside bam_read1 before the
-        // reference ever sees the record: first op is <l_seq>S, the record is placed, and a CG:B,I (or B,i) aux exists.
-        if (cg && n_cigar > 0 && tid >= 0 && pos >= 0) {
+        // reference ever sees the record: first op is <l_seq>S, the record is placed, a CG:B,I (or B,i) aux exists and its
+        // count is at least n_cigar and below 2^29 (otherwise htslib keeps the CIGAR as it stands).
+        if (cg && n_cigar > 0 && tid >= 0 && pos >= 0 && cg_n >= n_cigar && cg_n < (1u << 29)) {
             uint32_t c0; memcpy(&c0, src, 4);
             if ((c0 & 15) == 4 && (c0 >> 4) == l_seq) { src = cg; n = cg_n; }
         }

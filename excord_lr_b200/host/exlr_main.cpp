@@ -34,14 +34,14 @@ struct Cli {
     bool not_merge = false, debug = false, verbose = false;
     int gpus = 0;                       // 0 = all visible
     bool stats = false;                 // --stats: stage times on stderr
-    unsigned long long batch_reads = 131072, batch_ops = 0, batch_sa = 0;
+    unsigned long long batch_reads = 131072, batch_ops = 0, batch_sa = 0, batch_events = 0;
 };
 
 static void usage(FILE* f)
 {
     fputs("\nExtract Structural Variation Signals from Long-Read BAMs (B200 build of the signal-extraction path)\n\n"
           "Usage: excord-lr-b200 [OPTIONS] --bam <BAM> --out <OUT>\n\nOptions:\n"
-          "  -b, --bam <BAM>                          Path to BAM file\n"
+          "  -b, --bam <BAM>                          Path to BAM file (BAM, or SAM text plain / BGZF; '-' or a pipe streams from stdin)\n"
           "  -r, --reference <REFERENCE>              Path to reference, used for CRAM file\n"
           "  -Q, --mapq <MAPQ>                        Minimal MapQ [default: 1]\n"
           "  -F, --exclude-flag <EXCLUDE_FLAG>        Exclude Flags [default: 1796]\n"
@@ -52,7 +52,7 @@ static void usage(FILE* f)
           "  -m, --merge-min <MERGE_MIN>              Threshold to merge two adjacent events [default: 5]\n"
           "      --ins-clip-min <INS_CLIP_MIN>        Minimal length of hard-clip and soft-clip to define a large insertion signal [default: 1000]\n"
           "  -n, --not-merge                          Not merge (accepted and ignored, as in the reference)\n"
-          "  -o, --out <OUT>                          Output file name\n"
+          "  -o, --out <OUT>                          Output file name ('-' writes to stdout)\n"
           "  -s, --split-only                         Only report split-read event\n"
           "  -p, --max-pct-overlap <MAX_PCT_OVERLAP>  Percent of overlap to discard a potential false positive record [default: 0] (alias: --pct-overlap)\n"
           "  -k, --max-supp-alignm <MAX_SUPP_ALIGNM>  Maximal number of SA to include a record [default: 4]\n"
@@ -60,6 +60,7 @@ static void usage(FILE* f)
           "  -v, --verbose                            Verbose output\n"
           "      --gpus <N>                           GPUs to shard batches over [default: all visible]\n"
           "      --batch-reads <N>                    Records per GPU batch [default: 131072]\n"
+          "      --batch-events <N>                   Output lines a batch has room for at first [default: 4 x batch-reads + 4096]; grown on demand\n"
           "      --stats                              Print stage times to stderr\n"
           "  -h, --help                               Print help\n"
           "  -V, --version                            Print version\n", f);
@@ -111,6 +112,7 @@ static int parse_cli(int argc, char** argv, Cli& c)
         else if (a == "-v" || a == "--verbose") { if (!flagopt(&c.verbose)) return 2; }
         else if (a == "--gpus") { NUM(64); c.gpus = (int)u; }
         else if (a == "--batch-reads") { NUM(1ull << 30); c.batch_reads = u ? u : 1; }
+        else if (a == "--batch-events") { NUM(0xfff00000ull - 1); c.batch_events = u; }
         else if (a == "--stats") { if (!flagopt(&c.stats)) return 2; }
         else if (a == "-h" || a == "--help") { usage(stdout); return -1; }
         else if (a == "-V" || a == "--version") { puts("excord-LR 0.1.17"); return -1; }
@@ -126,9 +128,20 @@ static int parse_cli(int argc, char** argv, Cli& c)
 
 static bool is_file(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode); }
 static bool is_dir(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode); }
+// a FIFO or character device (/dev/stdin, a named pipe, a process substitution): streamed like "-"
+static bool is_stream(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 && (S_ISFIFO(st.st_mode) || S_ISCHR(st.st_mode)); }
 
 struct Slot {
     exlr_batch* b = nullptr; PackedBatch pk; int gpu = 0;
+};
+
+// One GPU of the run: its context and batch slots are created by its own thread, and only once a batch is headed for it
+// (a small input never touches GPUs 1..n-1; a large one brings them all up side by side while GPU 0 already works).
+struct Gpu {
+    exlr_ctx* ctx = nullptr;
+    std::deque<int> freeq;              // slots of this GPU ready to be packed (guarded by the run's mutex)
+    int state = 0;                      // 0 untouched, 1 starting, 2 ready, -1 failed
+    std::thread th;
 };
 
 int main(int argc, char** argv)
@@ -146,9 +159,11 @@ int main(int argc, char** argv)
                cli.p.mapq, cli.p.exclude_flag, cli.p.exclude_secondary ? "true" : "false", cli.p.exclude_unmapped ? "true" : "false", cli.thread,
                cli.p.indel_min, cli.p.merge_min, cli.p.ins_clip_min, cli.not_merge ? "true" : "false", cli.out.c_str(),
                cli.p.split_only ? "true" : "false", cli.p.max_pct_overlap, (unsigned long long)cli.p.max_supp_alignm, cli.verbose ? "true" : "false");
-    // startup checks: messages on stdout, exit 1 (src/main.rs:113-151)
-    if (!is_file(cli.bam)) { printf("Ivalid BAM file path: %s \n", cli.bam.c_str()); return 1; }
-    {
+    // startup checks: messages on stdout, exit 1 (src/main.rs:113-151).  Beyond the reference: "-" (and any FIFO / character
+    // device) streams the input from a pipe, `-o -` writes the lines to stdout -- the reference accepts regular files only.
+    const bool in_stream = cli.bam == "-" || is_stream(cli.bam), out_stdout = cli.out == "-";
+    if (!in_stream && !is_file(cli.bam)) { printf("Ivalid BAM file path: %s \n", cli.bam.c_str()); return 1; }
+    if (!out_stdout) {
         std::string parent;
         size_t sl = cli.out.find_last_of('/');
         parent = sl == std::string::npos ? "" : (sl == 0 ? "/" : cli.out.substr(0, sl));
@@ -156,7 +171,7 @@ int main(int argc, char** argv)
         if (parent.empty() || parent[0] != '/') { char cwd[4096]; if (getcwd(cwd, sizeof cwd)) abs = std::string(cwd) + (parent.empty() ? "" : "/" + parent); }
         if (!is_dir(abs)) { printf("Output directory does not exists: %s \n", abs.c_str()); return 1; }
     }
-    FILE* fo = fopen(cli.out.c_str(), "wb");                 // created before the BAM is opened (src/main.rs:135 vs 137)
+    FILE* fo = out_stdout ? stdout : fopen(cli.out.c_str(), "wb");     // created before the BAM is opened (src/main.rs:135 vs 137)
     if (!fo) { fprintf(stderr, "cannot create %s\n", cli.out.c_str()); return 101; }
     {
         std::string low = cli.bam; std::transform(low.begin(), low.end(), low.begin(), ::tolower);
@@ -168,44 +183,56 @@ int main(int argc, char** argv)
     if (cli.thread == 0) { fputs("thread pool of 0 threads: the reference panics here\n", stderr); return 101; }
 
     BamReader rd;
-    if (!rd.open(cli.bam, (int)std::min<unsigned long long>(cli.thread, 256))) { fprintf(stderr, "%s\n", rd.error.c_str()); return 101; }
+    if (!rd.open(in_stream && cli.bam == "-" ? "-" : cli.bam, (int)std::min<unsigned long long>(cli.thread, 256))) { fprintf(stderr, "%s\n", rd.error.c_str()); return 101; }
 
     int ndev = exlr_device_count();
     if (ndev <= 0) { fprintf(stderr, "no usable B200: %s (%s)\n", exlr_strerror(EXLR_ERR_CUDA), exlr_last_cuda_error()); return 3; }
     if (cli.gpus > 0) ndev = std::min(ndev, cli.gpus);
     std::vector<const char*> names; for (auto& s : rd.ref_names) names.push_back(s.c_str());
-    std::vector<exlr_ctx*> ctx(ndev, nullptr);
-    for (int g = 0; g < ndev; g++) {
-        rc = exlr_create(&cli.p, g, names.data(), (int)names.size(), &ctx[g]);
-        if (rc) { fprintf(stderr, "exlr_create(device %d): %s (%s)\n", g, exlr_strerror(rc), exlr_last_cuda_error()); return 3; }
-        // without -v the lines are formatted on the device (kernels 5a/5b) and the D2H copy carries the final bytes;
-        // -v lines carry the read name, which stays on the host: those are formatted here
-        exlr_set_option(ctx[g], EXLR_OPT_DEVICE_FORMAT, cli.verbose ? 0 : 1);
-    }
     const unsigned long long R = cli.batch_reads;
     const unsigned long long OPS = cli.batch_ops ? cli.batch_ops : std::max<unsigned long long>(R * 64, 4ull << 20);
     const unsigned long long SAB = cli.batch_sa ? cli.batch_sa : std::max<unsigned long long>(R * 64, 1ull << 20);
+    const unsigned long long EVS = cli.batch_events ? cli.batch_events : 4 * R + 4096;
     const int per_gpu = 3;
     std::vector<Slot> slots((size_t)ndev * per_gpu);
-    for (size_t i = 0; i < slots.size(); i++) {
-        slots[i].gpu = (int)(i % ndev);
-        rc = exlr_batch_alloc(ctx[slots[i].gpu], R, OPS, SAB, 4 * R + 4096, &slots[i].b);
-        if (rc) { fprintf(stderr, "exlr_batch_alloc: %s (%s)\n", exlr_strerror(rc), exlr_last_cuda_error()); return 3; }
-        exlr_batch_get_views(slots[i].b, &slots[i].pk.v);
-        slots[i].pk.keep_qnames = cli.verbose;
-        slots[i].pk.reset();
-    }
+    std::vector<Gpu> gpus(ndev);
 
-    // submitted batches travel to the writer in submission order; free slots travel back
+    // submitted batches travel to the writer in submission order; free slots travel back to their GPU's queue
     std::mutex mu; std::condition_variable cv;
-    std::deque<int> inflight, freeq; bool done = false; int fatal = 0;
-    for (size_t i = 0; i < slots.size(); i++) freeq.push_back((int)i);
+    std::deque<int> inflight; bool done = false; int fatal = 0;
+
+    auto start_gpu = [&](int g) {        // caller holds mu
+        if (gpus[g].state != 0) return;
+        gpus[g].state = 1;
+        gpus[g].th = std::thread([&, g]() {
+            exlr_ctx* ctx = nullptr;
+            int st = exlr_create(&cli.p, g, names.data(), (int)names.size(), &ctx);
+            // without -v the lines are formatted on the device (kernels 5a/5b) and the D2H copy carries the final bytes;
+            // -v lines carry the read name, which stays on the host: those are formatted here
+            if (!st) st = exlr_set_option(ctx, EXLR_OPT_DEVICE_FORMAT, cli.verbose ? 0 : 1);
+            for (int k = 0; k < per_gpu && !st; k++) {
+                Slot& s = slots[(size_t)g * per_gpu + k];
+                s.gpu = g;
+                st = exlr_batch_alloc(ctx, R, OPS, SAB, EVS, &s.b);
+                if (st) break;
+                exlr_batch_get_views(s.b, &s.pk.v);
+                s.pk.keep_qnames = cli.verbose;
+                s.pk.reset();
+            }
+            if (st) fprintf(stderr, "GPU %d: %s (%s)\n", g, exlr_strerror(st), exlr_last_cuda_error());
+            std::lock_guard<std::mutex> lk(mu);
+            gpus[g].ctx = ctx;
+            if (st) { gpus[g].state = -1; fatal = 3; }
+            else { gpus[g].state = 2; for (int k = 0; k < per_gpu; k++) gpus[g].freeq.push_back(g * per_gpu + k); }
+            cv.notify_all();
+        });
+    };
+    { std::lock_guard<std::mutex> lk(mu); start_gpu(0); }
 
     using clk = std::chrono::steady_clock;
     auto secs = [](clk::duration d) { return std::chrono::duration<double>(d).count(); };
     const auto t_begin = clk::now();
-    const double t_setup = secs(t_begin - t_start);
-    double t_wait = 0, t_format = 0, t_write = 0; uint64_t n_lines = 0, n_batches = 0;
+    double t_wait = 0, t_format = 0, t_write = 0; uint64_t n_lines = 0, n_batches = 0, n_regrown = 0;
     std::thread writer([&]() {
         std::vector<char> text;
         for (;;) {
@@ -215,9 +242,20 @@ int main(int argc, char** argv)
             exlr_result res;
             auto t0 = clk::now();
             const char* dtext = nullptr; uint64_t dbytes = 0;
-            int st = cli.verbose ? exlr_wait(s.b, &res) : exlr_wait_text(s.b, &res, &dtext, &dbytes);
             bool host_format = cli.verbose;
-            if (st == EXLR_ERR_TEXT_CAPACITY) { st = exlr_wait(s.b, &res); host_format = true; }   // unusually long lines: format here
+            int st = 0;
+            for (int attempt = 0;; attempt++) {
+                st = cli.verbose ? exlr_wait(s.b, &res) : exlr_wait_text(s.b, &res, &dtext, &dbytes);
+                if (st == EXLR_ERR_TEXT_CAPACITY) { st = exlr_wait(s.b, &res); host_format = true; }   // unusually long lines: format here
+                if (st != EXLR_ERR_CAPACITY || attempt == 4) break;
+                // an event-dense batch (small -i, many split reads at a large -k): the library says how many events it needs;
+                // the packed records are still in the slot's pinned views, so grow the event buffers and run the batch again
+                const uint64_t need = res.n_events + res.n_events / 8 + 4096;
+                int g = exlr_batch_grow(s.b, need);
+                if (!g) g = exlr_submit(s.b, s.pk.n);
+                if (g) { st = g; break; }
+                n_regrown++;
+            }
             t_wait += secs(clk::now() - t0); n_batches++;
             if (st != 0 && st > -10) { fprintf(stderr, "exlr_wait: %s (%s)\n", exlr_strerror(st), exlr_last_cuda_error()); std::lock_guard<std::mutex> lk(mu); fatal = 3; cv.notify_all(); return; }
             uint64_t n_ev = res.n_events;
@@ -227,15 +265,15 @@ int main(int argc, char** argv)
                 static const char kEmpty = 0;
                 if (cli.verbose && !qn) qn = &kEmpty;
                 t0 = clk::now();
-                int64_t need = exlr_format_lines(ctx[s.gpu], s.b, &res, 0, n_ev, cli.verbose, qn, cli.verbose ? s.pk.qname_off.data() : nullptr, nullptr, 0);
+                int64_t need = exlr_format_lines(gpus[s.gpu].ctx, s.b, &res, 0, n_ev, cli.verbose, qn, cli.verbose ? s.pk.qname_off.data() : nullptr, nullptr, 0);
                 if (need > 0) {
                     text.resize((size_t)need);
-                    exlr_format_lines(ctx[s.gpu], s.b, &res, 0, n_ev, cli.verbose, qn, cli.verbose ? s.pk.qname_off.data() : nullptr, text.data(), (uint64_t)need);
+                    exlr_format_lines(gpus[s.gpu].ctx, s.b, &res, 0, n_ev, cli.verbose, qn, cli.verbose ? s.pk.qname_off.data() : nullptr, text.data(), (uint64_t)need);
                     t_format += secs(clk::now() - t0); t0 = clk::now();
                     fwrite(text.data(), 1, (size_t)need, fo);
                     t_write += secs(clk::now() - t0);
                 }
-            } else if (dbytes) {                                          // (on a failing record: already cut to the lines before it)
+            } else if (dbytes) {                                          // (on a failing record: already cut to the lines written before the panic)
                 t0 = clk::now();
                 fwrite(dtext, 1, (size_t)dbytes, fo);
                 t_write += secs(clk::now() - t0);
@@ -246,16 +284,20 @@ int main(int argc, char** argv)
                 fprintf(stderr, "excord-lr-b200: record %u of a batch: %s\n", res.err_read, exlr_strerror(st));
                 std::lock_guard<std::mutex> lk(mu); fatal = 101; cv.notify_all(); return;
             }
-            { std::lock_guard<std::mutex> lk(mu); freeq.push_back(si); }
+            { std::lock_guard<std::mutex> lk(mu); gpus[s.gpu].freeq.push_back(si); }
             cv.notify_all();
         }
     });
 
-    auto acquire = [&]() -> int {
+    // batch `seq` goes to GPU seq % ndev (round robin); the writer re-assembles in submission order
+    auto acquire = [&](uint64_t seq) -> int {
+        const int g = (int)(seq % (uint64_t)ndev);
         std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return !freeq.empty() || fatal; });
+        if (seq == 1) for (int k = 1; k < ndev; k++) start_gpu(k);       // more than one batch: bring the other GPUs up, all at once
+        start_gpu(g);
+        cv.wait(lk, [&] { return !gpus[g].freeq.empty() || fatal; });
         if (fatal) return -1;
-        int si = freeq.front(); freeq.pop_front(); return si;
+        int si = gpus[g].freeq.front(); gpus[g].freeq.pop_front(); return si;
     };
     auto submit = [&](int si) -> bool {
         Slot& s = slots[si];
@@ -266,8 +308,9 @@ int main(int argc, char** argv)
         return true;
     };
 
-    // free slots come back in submission order, and slot i always belongs to GPU i % ndev: batches alternate over the GPUs
-    int cur = acquire();
+    uint64_t seq = 0;
+    int cur = acquire(seq);
+    const double t_setup = secs(clk::now() - t_start);                   // CUDA context + buffers of the first GPU, BAM header
     BamRecordView r;
     uint64_t n_rec = 0;
     while (cur >= 0 && rd.next(r)) {
@@ -276,7 +319,7 @@ int main(int argc, char** argv)
         if (!pk->fits(r)) {
             if (pk->n == 0 || !pk->can_ever_fit(r)) { fprintf(stderr, "record %llu does not fit a batch (CIGAR ops %u, SA bytes %u): raise --batch-reads\n", (unsigned long long)n_rec, r.n_cigar, r.sa_len); std::lock_guard<std::mutex> lk(mu); fatal = 3; break; }
             if (!submit(cur)) break;
-            cur = acquire();
+            cur = acquire(++seq);
             if (cur < 0) break;
             pk = &slots[cur].pk; pk->reset();
         }
@@ -286,13 +329,17 @@ int main(int argc, char** argv)
     { std::lock_guard<std::mutex> lk(mu); done = true; }
     cv.notify_all();
     writer.join();
-    fclose(fo);
+    for (auto& g : gpus) if (g.th.joinable()) g.th.join();
+    if (out_stdout) fflush(fo); else fclose(fo);
+    int n_used = 0; for (auto& g : gpus) n_used += g.state == 2;
     if (cli.stats)
-        fprintf(stderr, "excord-lr-b200: %llu records, %llu lines, %llu batches on %d GPU(s); setup (CUDA context, pinned + device buffers, BAM header) %.3f s; "
+        fprintf(stderr, "excord-lr-b200: %llu records, %llu lines, %llu batches (%llu re-run with larger event buffers) on %d of %d GPU(s); setup (CUDA context, "
+                "pinned + device buffers of the first GPU, BAM header) %.3f s; "
                 "stream %.3f s (writer thread: waiting for the GPU %.3f s, formatting %.3f s, writing %.3f s; the reader thread inflates, parses and packs "
                 "for the whole stream)\n",
-                (unsigned long long)n_rec, (unsigned long long)n_lines, (unsigned long long)n_batches, ndev, t_setup, secs(clk::now() - t_begin), t_wait, t_format, t_write);
-    for (auto& s : slots) exlr_batch_free(s.b);
-    for (auto c : ctx) exlr_destroy(c);
+                (unsigned long long)n_rec, (unsigned long long)n_lines, (unsigned long long)n_batches, (unsigned long long)n_regrown, n_used, ndev, t_setup,
+                secs(clk::now() - t_begin), t_wait, t_format, t_write);
+    for (auto& s : slots) if (s.b) exlr_batch_free(s.b);
+    for (auto& g : gpus) if (g.ctx) exlr_destroy(g.ctx);
     return fatal;
 }

@@ -155,6 +155,9 @@ typedef struct exlr_timing {
     float d2h_ms;       /* what the stream still does after the last kernel (nothing but the closing event since the header is a kernel) */
     uint32_t launches;  /* kernels launched by this submit                      */
     float screen_ms;    /* kernel 1a (event screen in front of kernel 1), part of cigar_ms; 0 when it did not run */
+    uint64_t h2d_bytes; /* bytes the last exlr_submit copied to the device                                        */
+    uint64_t d2h_bytes; /* bytes the last submit + wait copied back (result header, and the events / line offsets /
+                           lines copied behind the kernels: sized by a guess, so a little more than the result needs) */
 } exlr_timing;
 
 typedef struct exlr_ctx exlr_ctx;
@@ -195,6 +198,10 @@ int  exlr_batch_alloc(exlr_ctx* ctx, uint64_t max_reads, uint64_t max_ops, uint6
                       uint64_t max_events, exlr_batch** out);
 void exlr_batch_free(exlr_batch* b);
 int  exlr_batch_get_views(exlr_batch* b, exlr_batch_views* v);
+/* Replaces the batch's event / text buffers by larger ones (max_events entries); the packed records in the pinned views stay.
+ * The answer to EXLR_ERR_CAPACITY: grow to exlr_result.n_events (or more) and submit the same records again.  The batch must
+ * not be in flight. */
+int  exlr_batch_grow(exlr_batch* b, uint64_t max_events);
 
 /* Asynchronous: H2D of the first n_reads records of the pinned views, kernels, result
  * header D2H, all on the batch's stream.  The views must not be modified until exlr_wait. */
@@ -203,9 +210,10 @@ int  exlr_submit(exlr_batch* b, uint64_t n_reads);
  * the device (synchronous); exlr_submit_resident runs the kernels on the resident copy. */
 int  exlr_upload(exlr_batch* b, uint64_t n_reads);
 int  exlr_submit_resident(exlr_batch* b);
-/* Blocks until the batch is done, copies events + line offsets to pinned host memory and
- * fills *res (pointers valid until the next submit/free of this batch).  Returns
- * res->status. */
+/* Blocks until the batch is done and fills *res with the events + line offsets in pinned host memory (pointers valid until
+ * the next submit/grow/free of this batch).  exlr_submit already copied them back behind the kernels, sized by the previous
+ * batch's count, so this is normally ONE stream synchronisation; only what that guess missed is fetched afterwards.
+ * Returns res->status. */
 int  exlr_wait(exlr_batch* b, exlr_result* res);
 /* With EXLR_OPT_DEVICE_FORMAT: blocks until the batch is done and copies the formatted lines (no -v columns) to pinned host
  * memory: *text / *n_bytes are exactly the bytes the reference writes for this batch (for a record the reference panics on:

@@ -29,7 +29,7 @@ def test_header_symbols_exported():
 
 def test_struct_layouts():
     assert C.sizeof(ExlrParams) == 40 and EVENT_DTYPE.itemsize == 48
-    assert C.sizeof(api._Result) == 80 and C.sizeof(api.Timing) == 44 and C.sizeof(api._Views) == 104
+    assert C.sizeof(api._Result) == 80 and C.sizeof(api.Timing) == 64 and C.sizeof(api._Views) == 104
     lib = api.load_library()
     p = ExlrParams()
     lib.exlr_params_default(C.byref(p))

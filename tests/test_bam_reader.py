@@ -83,3 +83,36 @@ def test_sam_text_input(tmp_path):
         for f in ("cigar", "cigar_off", "pos", "tid", "flag", "mapq", "sa_kind", "sa_off", "sa_bytes"):
             assert np.array_equal(getattr(got, f), getattr(h, f)), f
         assert got.qnames == h.qnames and got.ref_names == h.ref_names
+
+
+def test_stream_from_stdin(tmp_path):
+    # "-" reads a pipe: the format sniff pushes its bytes back instead of seeking (BAM and SAM alike)
+    _build()
+    hb = synth.with_qnames(synth.config(0, 0.1))
+    bam, sam = str(tmp_path / "s.bam"), str(tmp_path / "s.sam")
+    bamio.write_bam(hb, bam, seq_len=9)
+    bamio.write_sam(hb, sam)
+    for src in (bam, sam):
+        out = str(tmp_path / "s.bin")
+        with open(src, "rb") as f:
+            subprocess.check_call([DUMP, "-", out, "3"], stdin=f)
+        got = bamio.load_dump(out)
+        for f in ("cigar", "cigar_off", "pos", "tid", "flag", "mapq", "sa_kind", "sa_off", "sa_bytes"):
+            assert np.array_equal(getattr(got, f), getattr(hb, f)), f
+
+
+def test_cg_tag_guards_like_htslib(tmp_path):
+    # bam_tag2cigar (inside htslib's bam_read1) swaps the CIGAR in only if CG:B,I holds at least n_cigar ops (and < 2^29):
+    # a <l_seq>S first op with a shorter CG array keeps the CIGAR as stored
+    import struct
+    hb = pack_records([dict(tid=0, pos=100, flag=0, mapq=60, cigar="5S10M"), dict(tid=1, pos=7, flag=16, mapq=1, cigar="5S3M")], REF_NAMES)
+    short_cg = b"CGBI" + struct.pack("<II", 1, (7 << 4) | 0)
+    got = _roundtrip(hb, tmp_path, seq_len=5, extra_aux=short_cg)
+    assert got.cigar.tolist() == hb.cigar.tolist()
+    # ... and with enough ops it is swapped in (2 >= n_cigar = 2)
+    long_cg = b"CGBI" + struct.pack("<III", 2, (7 << 4) | 0, (9 << 4) | 2)
+    bam, out = str(tmp_path / "cg.bam"), str(tmp_path / "cg.bin")
+    bamio.write_bam(hb, bam, seq_len=5, extra_aux=long_cg)
+    subprocess.check_call([DUMP, bam, out, "1"])
+    got = bamio.load_dump(out)
+    assert got.cigar.tolist() == [(7 << 4) | 0, (9 << 4) | 2] * 2

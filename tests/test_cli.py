@@ -90,3 +90,83 @@ def test_reference_panic_gives_partial_output_and_exit_101(tmp_path):
     want_r, want = _expect(hb, ExlrParams.make())
     assert want_r.status == -14 and want_r.err_read == 321
     assert open(out, "rb").read() == want
+
+
+def _n_devices():
+    try:
+        from excord_lr_b200 import api
+        return api.load_library().exlr_device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not gpu_available(), reason="needs a B200")
+def test_sam_text_to_event_file(tmp_path):
+    # the reference's Makefile feeds it a .sam (Makefile:73-74): same bytes out as for the BAM
+    hb = synth.with_qnames(synth.config(0, 0.3))
+    sam, out = str(tmp_path / "c1.sam"), str(tmp_path / "c1.txt")
+    bamio.write_sam(hb, sam, ref_lens=synth.ref_lens())
+    for extra, params, verbose in ((["-p", "0.8"], dict(max_pct_overlap=0.8), False), (["-v", "-i", "30"], dict(indel_min=30), True)):
+        r = run(["-b", sam, "-o", out] + extra)
+        assert r.returncode == 0, r.stderr
+        want_r, want = _expect(hb, ExlrParams.make(**params), verbose)
+        assert want_r.status == 0 and len(want) > 500
+        assert open(out, "rb").read() == want
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not gpu_available(), reason="needs a B200")
+def test_stdin_to_stdout_streaming(tmp_path):
+    # `-b -` / `-o -` (beyond the reference, which insists on regular files): BAM in through a pipe, lines out through a pipe
+    hb = synth.with_qnames(synth.config(0, 0.3))
+    bam = str(tmp_path / "c1.bam")
+    bamio.write_bam(hb, bam, ref_lens=synth.ref_lens(), seq_len=7)
+    want_r, want = _expect(hb, ExlrParams.make(max_pct_overlap=0.8))
+    with open(bam, "rb") as f:
+        r = subprocess.run([EXE, "-b", "-", "-o", "-", "-p", "0.8", "--batch-reads", "500"], stdin=f, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == want
+    with open(bam, "rb") as f:
+        r = subprocess.run([EXE, "-b", "/dev/stdin", "-o", str(tmp_path / "o.txt"), "-p", "0.8"], stdin=f, capture_output=True)
+    assert r.returncode == 0 and open(tmp_path / "o.txt", "rb").read() == want
+    # a path that does not exist still gets the reference's message
+    r = run(["-b", str(tmp_path / "nope.bam"), "-o", "-"])
+    assert r.returncode == 1 and r.stdout.startswith("Ivalid BAM file path")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not gpu_available(), reason="needs a B200")
+def test_event_buffers_grow_instead_of_failing(tmp_path):
+    # an event-dense input overflows the batch's event buffers: the CLI grows them and runs the batch again (the reference has
+    # no such limit, so the run must complete with identical bytes)
+    hb = synth.with_qnames(synth.config(0, 0.5))
+    bam, out = str(tmp_path / "c1.bam"), str(tmp_path / "c1.txt")
+    bamio.write_bam(hb, bam, ref_lens=synth.ref_lens())
+    for extra, params, verbose in ((["-i", "1", "--batch-events", "64", "--stats"], dict(indel_min=1), False),
+                                   (["-i", "1", "-v", "--batch-events", "64", "--batch-reads", "999", "--stats"], dict(indel_min=1), True),
+                                   (["-i", "2", "-m", "5", "--batch-events", "100", "--stats"], dict(indel_min=2, merge_min=5), False)):
+        r = run(["-b", bam, "-o", out] + extra)
+        assert r.returncode == 0, r.stderr
+        assert "re-run with larger event buffers" in r.stderr and " (0 re-run" not in r.stderr
+        want_r, want = _expect(hb, ExlrParams.make(**params), verbose)
+        assert want_r.status == 0 and len(want) > 100000
+        assert open(out, "rb").read() == want
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_n_devices() < 2, reason="needs two B200s")
+def test_two_gpus_round_robin_same_bytes(tmp_path):
+    # in-process sharding: batch k on GPU k % 2, re-assembled in order by the writer thread
+    hb = synth.with_qnames(synth.config(0, 1.0))
+    bam, out = str(tmp_path / "c1.bam"), str(tmp_path / "c1.txt")
+    bamio.write_bam(hb, bam, ref_lens=synth.ref_lens())
+    want_r, want = _expect(hb, ExlrParams.make(max_pct_overlap=0.8))
+    for extra in (["--gpus", "2", "--batch-reads", "700"], ["--gpus", "2", "--batch-reads", "700", "-t", "2"], ["--batch-reads", "333"]):
+        r = run(["-b", bam, "-o", out, "-p", "0.8", "--stats"] + extra)
+        assert r.returncode == 0, r.stderr
+        assert open(out, "rb").read() == want
+        assert "on 2 of" in r.stderr or "--gpus" not in extra
+    want_r, want = _expect(hb, ExlrParams.make(max_pct_overlap=0.8), True)
+    r = run(["-b", bam, "-o", out, "-p", "0.8", "-v", "--gpus", "2", "--batch-reads", "1000"])
+    assert r.returncode == 0 and open(out, "rb").read() == want
