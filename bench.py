@@ -1,15 +1,18 @@
 #!/usr/bin/env python
 """bench.py — alignments/s and CIGAR ops/s of the signal-extraction hot path on N B200s.
 
-A step = one pass of the hot path (kernels 0-4) over one batch: BASELINE.json configs[1], 1M simulated HiFi
-molecules (~1.04M alignment records, ~5 % carrying SA tags), default parameters + -p 0.8.
+A step = one pass of the hot path (kernels 0-4 + the result header) over one batch: BASELINE.json configs[1], 1M simulated
+HiFi molecules (~1.04M alignment records, ~5 % carrying SA tags), default parameters + -p 0.8.
 
   value        alignments/s, inputs resident in HBM, every step timed on the device with the library's CUDA events
                on the stream its kernels run on (L2 flushed before each step); max over ranks, summed over ranks.
-  e2e          the same metric through the public API with HOST buffers: pinned SoA views -> exlr_submit (H2D +
-               kernels) -> exlr_wait (D2H of events + line offsets), sub-batches pipelined over several streams.
-  roofline     kernel 1 (CIGAR scan), algorithmic bytes 4 B/op + 11 B/record, against the measured HBM copy peak.
+  e2e          the same metric through the public API with HOST buffers: pinned SoA views -> exlr_submit (H2D + kernels +
+               results copied back behind them) -> exlr_wait, sub-batches pipelined over several streams.
+  roofline     the byte-dominant kernel (1a, the streaming CIGAR screen) against the measured HBM copy peak, plus a table
+               of EVERY kernel of the step (time, algorithmic bytes, fraction of the peak) naming the time-dominant one.
   cpu_baseline the CPU oracle (a port of the reference loop; the Rust reference cannot be built here) on the same batch.
+  strong_c5    (N > 1) BASELINE.json configs[4]: ONE 6M-record set cut into 64k-record batches dealt round robin to the
+               ranks, the same two measurements, next to rank 0 running the whole set alone.
 
 `--impl reference` times that CPU port with every host core (records sharded over threads) instead of the GPU.
 Multi-GPU: reads are independent, so each rank processes its own shard (weak scaling, no collective on the data
@@ -36,13 +39,13 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic(kernel):
-    """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), if any."""
+def load_traffic():
+    """dram bytes per launch of every kernel from the committed ncu --set full capture (profiles/traffic.json), if any."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(kernel)
+            return json.load(f)
     except Exception:
-        return None
+        return {}
 
 
 class ClockSampler(threading.Thread):
@@ -96,12 +99,21 @@ def make_workload(config_id, scale, rank, world=1, strong=False):
     from excord_lr_b200.batch import HostBatch
     c = synth.CONFIGS[config_id]
     n = max(1, int(c["n"] * scale))
-    if strong and world > 1:
+    if strong:
         hb = synth.generate(c["profile"], c["seed"], n, c["chr20"], c["ultra"] if scale >= 1 else 0)
+        if world == 1:
+            return hb, c, hb
         mine = shard.rank_batches(shard.plan_batches(hb.n_reads, 65536), rank, world)
-        return HostBatch.concat([hb.slice(a, b) for _, a, b in mine]), c
+        return HostBatch.concat([hb.slice(a, b) for _, a, b in mine]), c, hb
     hb = synth.generate(c["profile"], c["seed"] + 7919 * rank, n, c["chr20"], c["ultra"] if scale >= 1 else 0)
-    return hb, c
+    return hb, c, hb
+
+
+def config_dict(c, hb):
+    """The workload as both arms state it (identical keys and values in the GPU arm and in `--impl reference`)."""
+    return {"workload": c["name"], "records_per_gpu": hb.n_reads, "cigar_ops_per_gpu": hb.n_ops, "sa_bytes_per_gpu": hb.n_sa_bytes,
+            "params": c["params"], "parallelism": "record shards, one per GPU, no collective",
+            "l2": "GPU arm: L2 flushed (256 MB read) before every timed step, inputs also larger than L2; CPU arm: not applicable"}
 
 
 def split_for_pipeline(hb, parts):
@@ -117,7 +129,7 @@ def run_reference(args, rank, world):
     from excord_lr_b200.batch import ExlrParams
     if rank != 0:
         return
-    hb, c = make_workload(args.config, args.scale, 0)
+    hb, c, _ = make_workload(args.config, args.scale, 0)
     p = ExlrParams.make(**c["params"])
     cores = os.cpu_count() or 1
     for _ in range(args.warmup):
@@ -132,13 +144,203 @@ def run_reference(args, rank, world):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "cigar_ops_per_sec": hb.n_ops / dt,
-            "config": {"workload": c["name"], "records": hb.n_reads, "cigar_ops": hb.n_ops, "sa_bytes": hb.n_sa_bytes,
-                       "params": c["params"]},
+            "config": config_dict(c, hb),
             "cpu_baseline": {"value": v, "unit": "alignments/s", "cores": cores, "kind": "port",
                              "sample": f"whole workload ({hb.n_reads} records) per step, records sharded over {cores} threads; "
                                        "the reference's own loop is single-threaded (src/main.rs:158)"},
             "e2e": {"value": v, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+class Dist:
+    """barrier / reductions over the ranks (torch.distributed over NCCL; nothing on the data path)."""
+
+    def __init__(self, world, local_rank):
+        import torch
+        self.torch, self.world = torch, world
+        if world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # NCCL would print its version banner on stdout, next to the JSON line
+                os.environ["NCCL_DEBUG"] = "WARN"
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, vals, op):
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op={"max": self.dist.ReduceOp.MAX, "sum": self.dist.ReduceOp.SUM, "min": self.dist.ReduceOp.MIN}[op])
+        return t.tolist()
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+class Flusher:
+    def __init__(self, torch):
+        self.torch = torch
+        self.buf = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+
+    def __call__(self):
+        self.buf.sum()                  # READ 256 MB: evicts the batch from L2 and leaves only clean lines behind
+        self.torch.cuda.synchronize()
+
+
+def measure_resident(big, flush, steps, warmup, D):
+    """K timed steps on the device-resident batch: (sum of step ms, launches, lines per step)."""
+    def step():
+        flush()
+        big.submit_resident()
+        r = big.wait_resident()
+        return r, big.timing()
+    for _ in range(warmup):
+        r, _t = step()
+    assert r.status == 0, f"status {r.status}"
+    D.barrier()
+    ms, launches = [], 0
+    for _ in range(steps):
+        r, t = step()
+        ms.append(t.kernels_ms + t.d2h_ms)                                # first kernel start -> result header on the host
+        launches += t.launches
+    D.barrier()
+    return float(np.sum(ms)), launches, r.n_events, step
+
+
+def measure_e2e(ex, hb, n_parts, steps, warmup, n_events, D):
+    """The same steps through exlr_submit / exlr_wait the way a streaming caller (the CLI) uses them: a ring of sub-batches, each
+    waited (events + line offsets on the host) right before its buffers are re-submitted with the next step's records, so the
+    H2D engine never idles between steps.  Every step's inputs cross PCIe and every step's result is read back.
+    -> (seconds, h2d bytes per step, d2h bytes per step) -- the byte counts are the library's own (exlr_timing)."""
+    torch = D.torch
+    parts = split_for_pipeline(hb, max(1, n_parts))
+    pb = [ex.batch_for(h) for h in parts]                                  # pinned views already hold the packed records
+
+    def run(k):
+        tot, busy = 0, [False] * len(pb)
+        for _ in range(k):
+            for i, b in enumerate(pb):
+                if busy[i]:
+                    tot += b.wait(copy=False).n_events
+                b.submit()
+                busy[i] = True
+        for i, b in enumerate(pb):
+            if busy[i]:
+                tot += b.wait(copy=False).n_events
+        return tot
+    ne = run(warmup)
+    assert ne == n_events * warmup, f"pipelined run produced {ne} lines, resident run {n_events} per step"
+    D.barrier()
+    t0 = time.perf_counter()
+    ne = run(steps)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    D.barrier()
+    assert ne == n_events * steps
+    h2d = sum(int(b.timing().h2d_bytes) for b in pb)
+    d2h = sum(int(b.timing().d2h_bytes) for b in pb)
+    for b in pb:
+        b.free()
+    return dt, h2d, d2h, len(parts)
+
+
+def pcie_probe(D, concurrent):
+    """Pinned host -> device copy rate of this rank: one 256 MB copy, best of 10.  concurrent=True: every rank copies at the same
+    time (barrier-aligned rounds), which is what the ranks' e2e loops do to the box's host memory and PCIe root."""
+    torch = D.torch
+    pin = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    dev = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rates = []
+    for _ in range(10):
+        if concurrent:
+            D.barrier()
+        e0.record(); dev.copy_(pin, non_blocking=True); e1.record(); torch.cuda.synchronize()
+        rates.append((256 << 20) / (e0.elapsed_time(e1) / 1e3) / 1e9)
+    del pin, dev
+    rates.sort()
+    return rates[-1] if not concurrent else rates[len(rates) // 2]       # alone: best; together: the median round
+
+
+def kernel_table(hb, p, solo, cnt, n_events, peak, traffic):
+    """Every kernel of a step: same-stream stage time (the kernel alone on the GPU, CUDA events between the kernels), the
+    algorithmic bytes it has to move, and what fraction of the HBM peak that is."""
+    R, C, A = hb.n_reads, hb.n_ops, hb.n_sa_bytes
+    has_sa = hb.sa_kind != 0
+    S = int(has_sa.sum())
+    sa_ops = int(np.diff(hb.cigar_off.astype(np.int64))[has_sa].sum())
+    claimed = cnt["claimed_short"] + cnt["claimed_warp"] + cnt["claimed_long"]
+    raw, sa_ev, E = cnt["raw_events"], cnt["sa_events"], n_events
+    rows = [("k0_classify", solo["classify_ms"], 8 * R + 4 * R + 4 * S, "flag 2 + mapq 1 + sa_kind 1 + tid 4 read, 4 B/record + 4 B/SA record written"),
+            ("k1a_screen", solo["screen_ms"], 4 * C, "every CIGAR op read once")]
+    if not p.split_only:
+        rows.append(("k1b_claim+k1b_walk", solo["cigar_ms"] - solo["screen_ms"], 2048 * cnt["flagged_steps"] + 19 * claimed + 32 * raw,
+                     "the flagged 512-op steps read again, 19 B per claimed record, 32 B per raw event written"))
+    rows += [("k3a_sa_cigar", solo["sa_cigar_ms"], 4 * sa_ops + 12 * S + 32 * S, "4 B/op of the SA records' own CIGARs, 32 B summary written"),
+             ("k3b_sa_events", solo["sa_parse_ms"], A + 32 * S + 16 * S + 48 * sa_ev, "SA bytes + 32 B summary + 16 B/record read, 48 B/line written"),
+             ("k4a_line_scan", solo["scan_ms"], 4 * R + R // 8 + 8 * claimed + 4 * R, "4 B/record + claim bit + 8 B/claimed record read, 4 B/record written"),
+             ("k4b_place(+k5a,k5b)+k6_header", solo["place_ms"], 32 * raw + 48 * sa_ev + 48 * E + 128, "raw + SA events read, 48 B/line written")]
+    out = []
+    for name, ms, b, what in rows:
+        if ms <= 0:
+            continue
+        tr = (traffic.get(name.split("+")[0].split("(")[0]) or {}).get("dram_bytes_per_launch")
+        out.append({"name": name, "avg_ms": ms, "algorithmic_bytes": int(b), "achieved_gbs": b / (ms / 1e3) / 1e9,
+                    "frac": b / (ms / 1e3) / 1e9 / peak, "traffic": tr, "bytes": what})
+    return out
+
+
+def strong_c5(args, ex_opts, D, rank, local_rank, world, peak):
+    """BASELINE.json configs[4] (6M HiFi records) sharded round robin in 64k-record batches over the ranks: fixed total work."""
+    from excord_lr_b200 import api
+    from excord_lr_b200.batch import ExlrParams
+    torch = D.torch
+    hb, c, whole = make_workload(4, args.strong_scale, rank, world, strong=True)
+    p = ExlrParams.make(**c["params"])
+    steps, warmup = min(args.steps, 5), 3
+    flush = Flusher(torch)
+
+    def one(h, barrier_obj):
+        ex = api.Extractor(p, h.ref_names, local_rank)
+        for k, v in ex_opts:
+            ex.set_option(k, v)
+        ex.set_option(api.EXLR_OPT_STAGE_TIMING, 0)
+        big = ex.batch_for(h)
+        big.upload()
+        tot, _l, ne, _ = measure_resident(big, flush, steps, warmup, barrier_obj)
+        big.free()
+        dt, h2d, d2h, _n = measure_e2e(ex, h, args.pipeline_parts, steps, warmup, ne, barrier_obj)
+        ex.close()
+        return tot, dt, h2d, d2h
+    tot, dt, h2d, d2h = one(hb, D)
+    tot_max, e2e_max = D.reduce([tot, dt * 1e3], "max")
+    R_all = whole.n_reads
+    out = {"workload": c["name"], "records_total": R_all, "cigar_ops_total": whole.n_ops, "batch_records": 65536, "scaling": "strong",
+           "steps": steps, "warmup": warmup,
+           "value": R_all / (tot_max / 1e3) * steps, "ms_per_step": tot_max / steps,
+           "e2e": {"value": R_all / (e2e_max / 1e3) * steps, "ms_per_step": e2e_max / steps,
+                   "h2d_bytes_per_step_rank0": h2d, "d2h_bytes_per_step_rank0": d2h}}
+    if world > 1:
+        # the same set on ONE GPU (rank 0, the others wait): what the N-GPU numbers are to be compared with
+        class Solo:
+            torch = D.torch
+
+            def barrier(self):
+                torch.cuda.synchronize()
+        if rank == 0:
+            t1, d1, _h, _d = one(whole, Solo())
+            out["single_gpu"] = {"value": R_all / (t1 / 1e3) * steps, "ms_per_step": t1 / steps,
+                                 "e2e_value": R_all / d1 * steps, "e2e_ms_per_step": d1 * 1e3 / steps}
+            out["efficiency"] = out["value"] / (world * out["single_gpu"]["value"])
+            out["e2e_efficiency"] = out["e2e"]["value"] / (world * out["single_gpu"]["e2e_value"])
+        D.barrier()
+    return out
 
 
 def main():
@@ -153,7 +355,9 @@ def main():
     ap.add_argument("--reads-per-cta", type=int, default=0)
     ap.add_argument("--pipeline-parts", type=int, default=3, help="sub-batches in flight for the e2e measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--strong", action="store_true", help="one dataset sharded round robin over the ranks instead of one batch per rank")
+    ap.add_argument("--strong", action="store_true", help="the headline workload itself sharded round robin over the ranks (instead of one batch per rank)")
+    ap.add_argument("--no-strong-c5", action="store_true", help="skip the strong_c5 block (N > 1)")
+    ap.add_argument("--strong-scale", type=float, default=1.0, help="scale of configs[4] in the strong_c5 block")
     ap.add_argument("--no-overlap", action="store_true", help="run kernel 1 on the same stream as the SA branch")
     ap.add_argument("--k1-ctas", type=int, default=0, help="persistent CTAs of kernel 1 per SM (1..4)")
     ap.add_argument("--k1-waves", type=int, default=0)
@@ -169,68 +373,40 @@ def main():
         return
 
     import torch
-    import torch.distributed as dist
     from excord_lr_b200 import api
     from excord_lr_b200.batch import ExlrParams
 
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # NCCL would print its version banner on stdout, next to the JSON line
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    D = Dist(world, local_rank)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    hb, c = make_workload(args.config, args.scale, rank, world, args.strong)
+    hb, c, _whole = make_workload(args.config, args.scale, rank, world, args.strong)
     p = ExlrParams.make(**c["params"])
     R, Cops, A = hb.n_reads, hb.n_ops, hb.n_sa_bytes
 
-    ex = api.Extractor(p, hb.ref_names, local_rank)
-    ex.set_option(api.EXLR_OPT_CIGAR_KERNEL, args.cigar_kernel)
-    ex.set_option(api.EXLR_OPT_READS_PER_CTA, args.reads_per_cta)
+    ex_opts = [(api.EXLR_OPT_CIGAR_KERNEL, args.cigar_kernel), (api.EXLR_OPT_READS_PER_CTA, args.reads_per_cta)]
     if args.no_overlap:
-        ex.set_option(api.EXLR_OPT_OVERLAP, 0)
+        ex_opts.append((api.EXLR_OPT_OVERLAP, 0))
     if args.k1_ctas:
-        ex.set_option(api.EXLR_OPT_K1_CTAS_PER_SM, args.k1_ctas)
+        ex_opts.append((api.EXLR_OPT_K1_CTAS_PER_SM, args.k1_ctas))
     if args.k1_waves:
-        ex.set_option(api.EXLR_OPT_K1_WAVES, args.k1_waves)
+        ex_opts.append((api.EXLR_OPT_K1_WAVES, args.k1_waves))
+    ex = api.Extractor(p, hb.ref_names, local_rank)
+    for k, v in ex_opts:
+        ex.set_option(k, v)
 
     # ---------------- device-resident: value + roofline ----------------
     big = ex.batch_for(hb)
     big.upload()
-    flush = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
-
-    def resident_step():
-        flush.sum()                     # READ 256 MB: evicts the batch from L2 and leaves only clean lines behind
-        torch.cuda.synchronize()
-        big.submit_resident()
-        r = big.wait_resident()
-        return r, big.timing()
-
+    flush = Flusher(torch)
     # the timed steps run without the per-stage events (they cost a few microseconds of launch gap each); stage times and the
-    # roofline kernel's duration are taken in extra, untimed-for-`value` steps below
+    # per-kernel durations are taken in extra steps below
     ex.set_option(api.EXLR_OPT_STAGE_TIMING, 0)
-    for _ in range(args.warmup):
-        r, _t = resident_step()
-    assert r.status == 0, f"status {r.status}"
-    n_events = r.n_events
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    step_ms, launches = [], 0
     wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        r, t = resident_step()
-        step_ms.append(t.kernels_ms + t.d2h_ms)                            # first kernel start -> result header on the host
-        launches += t.launches
-    barrier()
+    total_ms, launches, n_events, resident_step = measure_resident(big, flush, args.steps, args.warmup, D)
     wall_resident = time.perf_counter() - wall0
-    total_ms = float(np.sum(step_ms))
+    counters = big.counters().as_dict()
 
     def diag(n):
         acc, k1, k1a = {}, [], []
@@ -247,7 +423,7 @@ def main():
     nd = min(args.steps, 20)
     stage_ms, k1_beside, _ = diag(nd)                                      # as configured (kernel 1 beside the SA branch)
     k1_overlapped_ms = float(np.mean(k1_beside)) if k1_beside else float("nan")
-    # the dominant kernel on its own: every kernel on one stream, so kernel 1's launch duration is not stretched by the SA branch
+    # every kernel on its own: all on one stream, so no launch duration is stretched by the other branch
     if not args.no_overlap and not c["params"].get("split_only"):
         ex.set_option(api.EXLR_OPT_OVERLAP, 0)
         solo_stage, k1_ms, k1a_ms = diag(nd)
@@ -256,57 +432,18 @@ def main():
         solo_stage, k1_ms, k1a_ms = dict(stage_ms), k1_beside, [0.0]
     ex.set_option(api.EXLR_OPT_STAGE_TIMING, 0)
     clocks = sampler.stop()
+    big.free()
 
-    # ---------------- PCIe ceiling: one pinned 256 MB host->device copy, best of 10 ----------------
-    pin = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
-    dev = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pcie_h2d = 0.0
-    for _ in range(10):
-        e0.record(); dev.copy_(pin, non_blocking=True); e1.record(); torch.cuda.synchronize()
-        pcie_h2d = max(pcie_h2d, (256 << 20) / (e0.elapsed_time(e1) / 1e3) / 1e9)
-    del pin, dev
+    # ---------------- PCIe ceiling: alone, and with every rank copying at once ----------------
+    pcie_alone = pcie_probe(D, False)
+    pcie_together = pcie_probe(D, True) if world > 1 else pcie_alone
 
     # ---------------- end to end through the public API, host buffers ----------------
-    parts = split_for_pipeline(hb, max(1, args.pipeline_parts))
-    pbatches = [ex.batch_for(h) for h in parts]                              # pinned views already hold the packed records
-
-    def e2e_steps(k):
-        """k steps through exlr_submit / exlr_wait the way a streaming caller (the CLI) uses them: a ring of sub-batches, each
-        waited (events + line offsets read back to the host) right before its buffers are re-submitted with the next step's
-        records, so the H2D engine never idles between steps.  Every step's inputs cross PCIe and every step's result is read."""
-        tot, busy = 0, [False] * len(pbatches)
-        for _ in range(k):
-            for i, b in enumerate(pbatches):
-                if busy[i]:
-                    tot += b.wait(copy=False).n_events
-                b.submit()
-                busy[i] = True
-        for i, b in enumerate(pbatches):
-            if busy[i]:
-                tot += b.wait(copy=False).n_events
-        return tot
-
-    ne = e2e_steps(args.warmup)
-    assert ne == n_events * args.warmup, f"pipelined run produced {ne} lines, resident run {n_events} per step"
-    barrier()
-    t0 = time.perf_counter()
-    ne = e2e_steps(args.steps)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0)
-    barrier()
-    assert ne == n_events * args.steps
-    h2d = 4 * Cops + A + R * (8 + 4 + 4 + 2 + 1 + 1 + 4) + len(parts) * 12
-    d2h = len(parts) * 64 + 4 * (R + len(parts)) + 48 * n_events
+    e2e_s, h2d, d2h, n_parts = measure_e2e(ex, hb, args.pipeline_parts, args.steps, args.warmup, n_events, D)
 
     # ---------------- reduce over ranks ----------------
-    tt = torch.tensor([total_ms, e2e_s * 1e3, float(np.sum(k1_ms)), float(np.sum(k1a_ms))], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([R, Cops, n_events], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    total_ms_max, e2e_ms_max, k1_ms_max, k1a_ms_max = tt.tolist()
-    R_all, C_all, E_all = cnt.tolist()
+    total_ms_max, e2e_ms_max, k1_ms_max, k1a_ms_max = D.reduce([total_ms, e2e_s * 1e3, float(np.sum(k1_ms)), float(np.sum(k1a_ms))], "max")
+    R_all, C_all, E_all, pcie_sum, h2d_all = D.reduce([R, Cops, n_events, pcie_together, h2d], "sum")
 
     # ---------------- cpu baseline (rank 0, N=1 only) ----------------
     cpu = None
@@ -317,18 +454,23 @@ def main():
         t0 = time.perf_counter()
         want = oracle_c.run(hb, p)
         dt = time.perf_counter() - t0
-        assert want.status == 0 and want.n_events if hasattr(want, "n_events") else True
+        assert want.status == 0
         cpu = {"value": R / dt, "unit": "alignments/s", "cores": 1, "kind": "port",
                "sample": f"the whole workload once ({R} records, {Cops} CIGAR ops, {dt:.2f} s), single thread like the reference loop",
                "lines": int(len(want.events)), "matches_gpu_line_count": bool(len(want.events) == n_events)}
 
+    strong = None
+    if world > 1 and not args.no_strong_c5 and not args.strong:
+        strong = strong_c5(args, ex_opts, D, rank, local_rank, world, load_peaks()[0])
+
     if rank == 0:
         peak, peak_src = load_peaks()
-        # The CIGAR path is kernel 1a (streaming event screen: reads every op once, writes every record's 8-byte summary and the
-        # list of 512-op steps that hold an event candidate) followed by kernels 1b/1d on the records around those steps;
-        # event-dense batches get kernel 1 (flat block scan of everything) instead.  The roofline entry is the kernel that moves
-        # the bytes: 1a reads 4 B/op of the 4 B/op + 28 B/record the whole step reads.  Its peak is the measured COPY bandwidth
-        # (read + write); a read-mostly stream can exceed that figure, so frac may come out slightly above 1 on long-record batches.
+        traffic = load_traffic()
+        # The CIGAR path is kernel 1a (streaming event screen: reads every op once and lists the 512-op steps that hold an event
+        # candidate) followed by kernels 1b/1d on the records around those steps; event-dense batches get kernel 1 (flat block
+        # scan of everything) instead.  The headline roofline entry is the kernel that moves the bytes: 1a reads 4 B/op of the
+        # 4 B/op + 28 B/record the whole step reads.  Its peak is the measured COPY bandwidth (read + write); a read-mostly
+        # stream can exceed that figure, so frac may come out slightly above 1 on long-record batches.
         screened = bool(k1a_ms) and float(np.mean(k1a_ms)) > 0
         path_bytes = 4.0 * Cops + 11.0 * R                                # 4 B/op + offset 8 + flag 2 + mapq 1 per record
         path_s = float(np.mean(k1_ms)) / 1e3 if k1_ms else float("nan")
@@ -340,26 +482,32 @@ def main():
             rk_name = "k1_flat" if args.cigar_kernel != 1 else "k1_warp"
             k1_bytes, k1_avg_s = path_bytes, path_s
         achieved = k1_bytes / k1_avg_s / 1e9 if k1_avg_s > 0 else 0.0
-        traffic = load_traffic(rk_name)
+        kernels = kernel_table(hb, p, solo_stage, counters, n_events, peak, traffic) if screened or c["params"].get("split_only") else []
+        dominant = max(kernels, key=lambda k: k["avg_ms"]) if kernels else None
         pipe_bytes = 24.0 * R + 4.0 * Cops + A + 4.0 * R + 48.0 * n_events
         ms_per_step = total_ms_max / args.steps
         value = R_all / (total_ms_max / 1e3) * args.steps
         e2e_value = R_all / (e2e_ms_max / 1e3) * args.steps
+        h2d_rate = h2d * args.steps / (e2e_ms_max / 1e3) / 1e9             # this rank's bytes over the slowest rank's time
         line = {
             "metric": "alignments_per_sec", "value": value, "unit": "alignments/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "cigar_ops_per_sec": C_all / (total_ms_max / 1e3) * args.steps,
-            "config": {"workload": c["name"], "records_per_gpu": R, "cigar_ops_per_gpu": Cops, "sa_bytes_per_gpu": A,
-                       "lines_per_gpu": n_events, "params": c["params"], "parallelism": f"dp{world} (record shards, no collective)",
-                       "l2": "flushed (256 MB read) before every timed step; inputs are also larger than L2",
-                       "cigar_kernel": {0: "auto: streaming event screen (1a), then only the records around a candidate are scanned (1b: thread per short record; 1d: long records from 1a's per-step sums)",
-                                        1: "warp per record", 2: "flat TMA-staged block scan of everything", 3: "the screened path (forced)"}[args.cigar_kernel]},
+            "config": config_dict(c, hb),
+            "run": {"lines_per_gpu": n_events, "n_gpus": world,
+                    "cigar_kernel": {0: "auto: streaming event screen (1a), then only the records around a candidate are scanned (1b: thread per short record; 1d: long records from 1a's per-step sums)",
+                                     1: "warp per record", 2: "flat TMA-staged block scan of everything", 3: "the screened path (forced)"}[args.cigar_kernel],
+                    "counters": counters},
             "e2e": {"value": e2e_value, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms_max / args.steps, "pipeline_parts": len(parts),
-                    "h2d_gbs": h2d * args.steps / (e2e_ms_max / 1e3) / 1e9, "pcie_h2d_peak_gbs": pcie_h2d,
-                    "frac_of_pcie": (h2d * args.steps / (e2e_ms_max / 1e3) / 1e9) / pcie_h2d if pcie_h2d else None,
-                    "cigar_ops_per_sec": C_all / (e2e_ms_max / 1e3) * args.steps},
+                    "ms_per_step": e2e_ms_max / args.steps, "pipeline_parts": n_parts,
+                    "h2d_gbs": h2d_rate, "h2d_gbs_all_gpus": h2d_all * args.steps / (e2e_ms_max / 1e3) / 1e9,
+                    "pcie_h2d_peak_gbs": pcie_alone,
+                    "pcie_h2d_peak_gbs_all_ranks_copying": pcie_together, "pcie_h2d_box_aggregate_gbs": pcie_sum,
+                    "frac_of_pcie": h2d_rate / pcie_alone if pcie_alone else None,
+                    "frac_of_box_aggregate": (h2d_all * args.steps / (e2e_ms_max / 1e3) / 1e9) / pcie_sum if pcie_sum else None,
+                    "cigar_ops_per_sec": C_all / (e2e_ms_max / 1e3) * args.steps,
+                    "note": "the packer is outside the timed region (the pinned views are pre-filled); every step's inputs cross PCIe and every result is read back"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": rk_name, "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
@@ -370,7 +518,10 @@ def main():
                                         "achieved": path_bytes / path_s / 1e9 if path_s > 0 else 0.0,
                                         "frac": (path_bytes / path_s / 1e9 / peak) if path_s > 0 else 0.0,
                                         "ms_beside_sa_branch": k1_overlapped_ms},
-                         "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                         "traffic": (traffic.get(rk_name) or {}).get("dram_bytes_per_launch"),
+                         "kernels": kernels,
+                         "time_dominant_kernel": dominant["name"] if dominant else None,
+                         "time_dominant_frac": dominant["frac"] if dominant else None,
                          "pipeline_achieved_gbs": pipe_bytes / (ms_per_step / 1e3) / 1e9,
                          "pipeline_frac": pipe_bytes / (ms_per_step / 1e3) / 1e9 / peak},
             "stage_ms": stage_ms, "stage_ms_same_stream": solo_stage,
@@ -379,14 +530,12 @@ def main():
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if strong:
+            line["strong_c5"] = strong
         print(json.dumps(line), flush=True)
 
-    for b in pbatches:
-        b.free()
-    big.free()
     ex.close()
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
 if __name__ == "__main__":

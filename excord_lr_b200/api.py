@@ -70,6 +70,14 @@ class Timing(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("flagged_steps", "claimed_short", "claimed_warp", "claimed_long", "raw_events",
+                                          "sa_events", "far_records", "text_bytes")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
 _lib = None
 
 
@@ -100,6 +108,8 @@ def load_library() -> C.CDLL:
     lib.exlr_wait_resident.argtypes = [vp, C.POINTER(_Result)]
     lib.exlr_wait_text.argtypes = [vp, C.POINTER(_Result), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.exlr_get_timing.argtypes = [vp, C.POINTER(Timing)]
+    lib.exlr_get_counters.argtypes = [vp, C.POINTER(Counters)]
+    lib.exlr_get_counters.restype = i32
     lib.exlr_format_lines.restype = C.c_int64
     lib.exlr_format_lines.argtypes = [vp, vp, C.POINTER(_Result), u64, u64, i32, C.c_char_p, vp, vp, u64]
     lib.exlr_strerror.restype = C.c_char_p
@@ -238,6 +248,11 @@ class DeviceBatch:
         t = Timing()
         _check(self.lib.exlr_get_timing(self.handle, C.byref(t)))
         return t
+
+    def counters(self) -> Counters:
+        c = Counters()
+        _check(self.lib.exlr_get_counters(self.handle, C.byref(c)))
+        return c
 
     def format_lines(self, res: Result, verbose: bool = False, qnames: Optional[Sequence[str]] = None,
                      ev_begin: int = 0, ev_end: Optional[int] = None) -> bytes:

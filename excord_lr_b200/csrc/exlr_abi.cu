@@ -678,6 +678,18 @@ int exlr_get_timing(exlr_batch* b, exlr_timing* t)
     return EXLR_OK;
 }
 
+int exlr_get_counters(exlr_batch* b, exlr_counters* out)
+{
+    if (!b || !out) return EXLR_ERR_ARG;
+    if (!b->submitted) return EXLR_ERR_STATE;
+    CK(cudaSetDevice(b->ctx->device));
+    CK(cudaStreamSynchronize(b->stream));
+    const Ctrl& c = *b->h_ctrl;
+    const uint32_t room = b->dv.raw_cap - b->dv.prim_slots;
+    *out = exlr_counters{c.n_flagged, c.n_short, c.n_warp, c.n_long, b->screened ? (c.n_raw < room ? c.n_raw : room) : 0ull, c.n_saev, c.n_far, c.text_bytes};
+    return EXLR_OK;
+}
+
 int exlr_get_trace(exlr_batch* b, unsigned long long* out, uint32_t n_ctas)
 {
     if (!b || !out || n_ctas > 8192) return EXLR_ERR_ARG;

@@ -223,6 +223,17 @@ int  exlr_wait_text(exlr_batch* b, exlr_result* res, const char** text, uint64_t
 /* Like exlr_wait but leaves events on the device (only the result header is read). */
 int  exlr_wait_resident(exlr_batch* b, exlr_result* res);
 int  exlr_get_timing(exlr_batch* b, exlr_timing* t);
+/* Device-side work counters of the last waited batch (diagnostics; what the per-kernel roofline figures of bench.py are
+ * computed from). */
+typedef struct exlr_counters {
+    uint64_t flagged_steps;   /* 512-op steps of the CIGAR stream in which kernel 1a found an event candidate            */
+    uint64_t claimed_short, claimed_warp, claimed_long;   /* records kernel 1b claimed, by the kernel that scans them     */
+    uint64_t raw_events;      /* indel events before the merge (main.rs:549-600)                                         */
+    uint64_t sa_events;       /* lines of the SA arm (main.rs:340-516)                                                   */
+    uint64_t far_records;     /* records whose >2-event merge loop changed the event list (main.rs:636-742)              */
+    uint64_t text_bytes;      /* bytes of the device-formatted lines (EXLR_OPT_DEVICE_FORMAT)                            */
+} exlr_counters;
+int  exlr_get_counters(exlr_batch* b, exlr_counters* c);
 /* debug (EXLR_OPT_TRACE): 4 x u64 per CTA of kernel 1 {globaltimer at start, at first data, at end, tiles | scanned tiles << 32} */
 int  exlr_get_trace(exlr_batch* b, unsigned long long* out, uint32_t n_ctas);
 

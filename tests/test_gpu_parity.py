@@ -291,3 +291,8 @@ def test_full_size_configs_bit_exact(cfg):
     want, res = gpu_check(hb, p, 0, 0, label=f"config{cfg} full size")
     assert res.status == 0 and res.line_off[-1] == res.n_events == len(want.events)
     assert (np.diff(res.events["read_idx"].astype(np.int64)) >= 0).all()
+    if cfg == 3:
+        # BASELINE.json configs[3] names both -k 4 and -k 8: the second half at full size too (more records pass the cap,
+        # up to 9 segments each; the event buffers grow to what the device asks for)
+        want8, res8 = gpu_check(hb, ExlrParams.make(split_only=True, max_supp_alignm=8), 0, 0, label="config3 -k 8 full size")
+        assert res8.status == 0 and res8.n_events == len(want8.events) > res.n_events and res8.n_cap_dropped < res.n_cap_dropped
