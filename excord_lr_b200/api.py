@@ -78,6 +78,22 @@ class Counters(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class BgzfBlock(C.Structure):
+    _fields_ = [("comp_off", C.c_uint32), ("comp_len", C.c_uint32), ("ulen", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class _BamViews(C.Structure):
+    _fields_ = [("comp", C.c_void_p), ("blocks", C.c_void_p), ("max_comp_bytes", C.c_uint64), ("max_blocks", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class BamInfo(C.Structure):
+    _fields_ = [("status", C.c_int32), ("bad_block", C.c_int32), ("n_blocks", C.c_uint32), ("reserved", C.c_uint32),
+                ("n_reads", C.c_uint64), ("n_ops", C.c_uint64), ("n_sa_bytes", C.c_uint64), ("tail_off", C.c_uint64),
+                ("u_bytes", C.c_uint64), ("comp_bytes", C.c_uint64), ("h2d_ms", C.c_float), ("inflate_ms", C.c_float),
+                ("walk_ms", C.c_float), ("reserved2", C.c_float)]
+
+
 _lib = None
 
 
@@ -110,6 +126,14 @@ def load_library() -> C.CDLL:
     lib.exlr_get_timing.argtypes = [vp, C.POINTER(Timing)]
     lib.exlr_get_counters.argtypes = [vp, C.POINTER(Counters)]
     lib.exlr_get_counters.restype = i32
+    lib.exlr_bam_batch_alloc.argtypes = [vp, u64, C.c_uint32, u64, C.POINTER(vp)]
+    lib.exlr_bam_get_views.argtypes = [vp, C.POINTER(_BamViews)]
+    lib.exlr_bam_submit.argtypes = [vp, u64, C.c_uint32]
+    lib.exlr_bam_walk.argtypes = [vp, u64]
+    lib.exlr_bam_extract.argtypes = [vp, C.POINTER(BamInfo)]
+    lib.exlr_bam_download.argtypes = [vp, C.POINTER(_Views), vp, u64, vp]
+    for f in ("exlr_bam_batch_alloc", "exlr_bam_get_views", "exlr_bam_submit", "exlr_bam_walk", "exlr_bam_extract", "exlr_bam_download"):
+        getattr(lib, f).restype = i32
     lib.exlr_format_lines.restype = C.c_int64
     lib.exlr_format_lines.argtypes = [vp, vp, C.POINTER(_Result), u64, u64, i32, C.c_char_p, vp, vp, u64]
     lib.exlr_strerror.restype = C.c_char_p
@@ -285,6 +309,83 @@ class DeviceBatch:
             self.free()
         except Exception:
             pass
+
+
+def bgzf_blocks(data: bytes):
+    """The host's whole share of reading a BGZF file: hop over the block headers.  -> [(comp_off, comp_len, ulen)] of the
+    complete blocks in `data`, and the number of bytes they span (SAMv1 4.1: gzip header with the BC extra subfield)."""
+    out, at, n = [], 0, len(data)
+    while at + 18 <= n:
+        if data[at] != 31 or data[at + 1] != 139 or data[at + 2] != 8 or not (data[at + 3] & 4):
+            raise ExlrError(-7, "not a BGZF block")
+        xlen = int.from_bytes(data[at + 10:at + 12], "little")
+        if at + 12 + xlen > n:
+            break
+        bsize, i = -1, at + 12
+        while i + 4 <= at + 12 + xlen:
+            slen = int.from_bytes(data[i + 2:i + 4], "little")
+            if data[i] == 66 and data[i + 1] == 67 and slen == 2:
+                bsize = int.from_bytes(data[i + 4:i + 6], "little")
+            i += 4 + slen
+        if bsize < 0:
+            raise ExlrError(-7, "BGZF block without BC field")
+        total = bsize + 1
+        if at + total > n:
+            break
+        out.append((at + 12 + xlen, total - xlen - 20, int.from_bytes(data[at + total - 4:at + total], "little")))
+        at += total
+    return out, at
+
+
+class BamBatch(DeviceBatch):
+    """A batch whose records come from BGZF-compressed BAM bytes decoded on the device (exlr_bam_*)."""
+
+    def __init__(self, ex: "Extractor", max_comp_bytes: int, max_blocks: int, max_events: int = 0):
+        self.ex, self.lib = ex, ex.lib
+        h = C.c_void_p()
+        _check(self.lib.exlr_bam_batch_alloc(ex.handle, max_comp_bytes, max_blocks, max_events, C.byref(h)))
+        self.handle = h
+        v = _BamViews()
+        _check(self.lib.exlr_bam_get_views(h, C.byref(v)))
+        self.max_comp, self.max_blocks = int(v.max_comp_bytes), int(v.max_blocks)
+        self.comp = np.frombuffer((C.c_char * self.max_comp).from_address(v.comp), np.uint8)
+        self.blocks = (BgzfBlock * self.max_blocks).from_address(v.blocks)
+        self.n_reads = 0
+
+    def load(self, data: bytes, blocks):
+        """Chunk bytes + their block table (bgzf_blocks) into the pinned views, then H2D + inflate (asynchronous)."""
+        self.comp[:len(data)] = np.frombuffer(data, np.uint8)
+        for i, (co, cl, ul) in enumerate(blocks):
+            self.blocks[i] = BgzfBlock(co, cl, ul, 0)
+        _check(self.lib.exlr_bam_submit(self.handle, len(data), len(blocks)))
+
+    def walk(self, start_off: int):
+        _check(self.lib.exlr_bam_walk(self.handle, start_off))
+
+    def extract(self) -> BamInfo:
+        info = BamInfo()
+        rc = self.lib.exlr_bam_extract(self.handle, C.byref(info))
+        if rc not in (0, -7, -8):
+            _check(rc)
+        self.n_reads = int(info.n_reads)
+        return info
+
+    def download(self, ref_names, max_reads, max_ops, max_sa) -> HostBatch:
+        """The decoded records as a HostBatch (for comparison with what the host reader packs)."""
+        n, c, a = max(1, max_reads), max(1, max_ops), max(1, max_sa)
+        arr = dict(cigar=np.zeros(c, np.uint32), cigar_off=np.zeros(n + 1, np.uint64), pos=np.zeros(n, np.int32),
+                   tid=np.zeros(n, np.int32), flag=np.zeros(n, np.uint16), mapq=np.zeros(n, np.uint8), sa_kind=np.zeros(n, np.uint8),
+                   sa_off=np.zeros(n + 1, np.uint32), sa_bytes=np.zeros(a, np.uint8))
+        v = _Views(*[arr[k].ctypes.data for k in ("cigar", "cigar_off", "pos", "tid", "flag", "mapq", "sa_kind", "sa_off", "sa_bytes")],
+                   n, c, a, 0)
+        qn = np.zeros(256 * n, np.uint8)
+        qo = np.zeros(n + 1, np.uint32)
+        _check(self.lib.exlr_bam_download(self.handle, C.byref(v), qn.ctypes.data, qn.size, qo.ctypes.data))
+        k = max_reads
+        names = [qn[int(qo[i]):int(qo[i + 1])].tobytes().decode("latin-1") for i in range(k)]
+        return HostBatch(arr["cigar"][:int(arr["cigar_off"][k])], arr["cigar_off"][:k + 1], arr["pos"][:k], arr["tid"][:k],
+                         arr["flag"][:k], arr["mapq"][:k], arr["sa_kind"][:k], arr["sa_off"][:k + 1],
+                         arr["sa_bytes"][:int(arr["sa_off"][k])], list(ref_names), names)
 
 
 class Extractor:

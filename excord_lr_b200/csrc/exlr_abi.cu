@@ -79,6 +79,15 @@ struct exlr_batch {
     bool far_ran = false;                      // the last submit ran the FAR variants of kernels 4a/4b
     uint32_t launches = 0;
     unsigned long long* d_dbg = nullptr;
+    // ---- BAM input decoded on the device (exlr_bam_*): compressed chunk + block table in pinned memory, the rest on the device
+    bool is_bam = false;
+    uint8_t* h_comp = nullptr; exlr_bgzf_block* h_blocks = nullptr; BgzfBlock* h_btab = nullptr; BamCtrl* h_bctrl = nullptr;
+    void* d_bam = nullptr; DevBam db{};
+    size_t bam_zero_bytes = 0;                 // BamCtrl + the three scan status arrays (one memset per submit)
+    uint64_t max_comp = 0, u_cap = 0; uint32_t max_blocks = 0;
+    int bam_state = 0;                         // 0 idle, 1 exlr_bam_submit done, 2 exlr_bam_walk done, 3 exlr_bam_extract done
+    uint64_t bam_comp_bytes = 0;
+    cudaEvent_t ev_bam[4] = {};                // start, after H2D, after inflate, after walk + gather
 };
 
 // kernel 1 reserves overflow slabs of 128 raw slots ahead of use (one spare per persistent CTA, see k1_flush): room for
@@ -174,6 +183,8 @@ const char* exlr_strerror(int s)
     case EXLR_ERR_SA_NM: return "SA NM is not an integer (reference panics)";
     case EXLR_ERR_MERGE_DOMAIN: return "more than two indel events with merge_min reaching across them: the merge loop of the reference indexes out of bounds and panics";
     case EXLR_ERR_SPLIT_COUNT: return "more than 2^24 segments in one record";
+    case EXLR_ERR_BGZF: return "corrupt BGZF block (bad header, or a deflate stream that does not inflate to its ISIZE)";
+    case EXLR_ERR_BAM_RECORD: return "corrupt BAM record (block_size or auxiliary data run past the record)";
     case EXLR_ERR_TEXT_CAPACITY: return "formatted lines exceed the batch's text buffer; use exlr_wait + exlr_format_lines";
     default: return "unknown status";
     }
@@ -261,12 +272,14 @@ void exlr_batch_free(exlr_batch* b)
     if (b->ev_k1_end) cudaEventDestroy(b->ev_k1_end);
     if (b->stream2) cudaStreamDestroy(b->stream2);
     if (b->stream) cudaStreamDestroy(b->stream);
+    for (auto& e : b->ev_bam) if (e) cudaEventDestroy(e);
+    cudaFree(b->d_bam); cudaFreeHost(b->h_comp); cudaFreeHost(b->h_blocks); cudaFreeHost(b->h_btab); cudaFreeHost(b->h_bctrl);
     cudaFree(b->d_slab); cudaFree(b->d_evslab);
     cudaFreeHost(b->h_slab); cudaFreeHost(b->h_out); cudaFreeHost(b->h_events); cudaFreeHost(b->h_text);
     delete b;
 }
 
-int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t max_sa_bytes, uint64_t max_events, exlr_batch** out)
+static int batch_alloc_impl(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t max_sa_bytes, uint64_t max_events, bool host_inputs, exlr_batch** out)
 {
     if (!c || !out) return EXLR_ERR_ARG;
     *out = nullptr;
@@ -282,14 +295,17 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     auto hcarve = [&](size_t bytes) { size_t at = ho; ho = align_up(ho + bytes, A); return at; };
     const size_t h_cigar = hcarve((max_ops + 4) * 4), h_coff = hcarve((R + 1) * 8), h_pos = hcarve(R * 4), h_tid = hcarve(R * 4),
                  h_flag = hcarve(R * 2), h_mapq = hcarve(R), h_kind = hcarve(R), h_soff = hcarve((R + 1) * 4), h_sab = hcarve(max_sa_bytes + 16);
-    cudaError_t e = cudaHostAlloc(&b->h_slab, ho, cudaHostAllocDefault);
-    if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostAlloc(inputs)"); }
-    char* hs = (char*)b->h_slab;
-    b->hv.cigar = (uint32_t*)(hs + h_cigar); b->hv.cigar_off = (uint64_t*)(hs + h_coff); b->hv.pos = (int32_t*)(hs + h_pos);
-    b->hv.tid = (int32_t*)(hs + h_tid); b->hv.flag = (uint16_t*)(hs + h_flag); b->hv.mapq = (uint8_t*)(hs + h_mapq);
-    b->hv.sa_kind = (uint8_t*)(hs + h_kind); b->hv.sa_off = (uint32_t*)(hs + h_soff); b->hv.sa_bytes = (uint8_t*)(hs + h_sab);
+    cudaError_t e = cudaSuccess;
     b->hv.max_reads = max_reads; b->hv.max_ops = max_ops; b->hv.max_sa_bytes = max_sa_bytes; b->hv.max_events = max_events;
-    b->hv.cigar_off[0] = 0; b->hv.sa_off[0] = 0;
+    if (host_inputs) {                         // (a BAM batch gets its records from the device-side decoder: no pinned input views)
+        e = cudaHostAlloc(&b->h_slab, ho, cudaHostAllocDefault);
+        if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostAlloc(inputs)"); }
+        char* hs = (char*)b->h_slab;
+        b->hv.cigar = (uint32_t*)(hs + h_cigar); b->hv.cigar_off = (uint64_t*)(hs + h_coff); b->hv.pos = (int32_t*)(hs + h_pos);
+        b->hv.tid = (int32_t*)(hs + h_tid); b->hv.flag = (uint16_t*)(hs + h_flag); b->hv.mapq = (uint8_t*)(hs + h_mapq);
+        b->hv.sa_kind = (uint8_t*)(hs + h_kind); b->hv.sa_off = (uint32_t*)(hs + h_soff); b->hv.sa_bytes = (uint8_t*)(hs + h_sab);
+        b->hv.cigar_off[0] = 0; b->hv.sa_off[0] = 0;
+    }
     // ---- pinned host output slab
     size_t oo = 0;
     auto ocarve = [&](size_t bytes) { size_t at = oo; oo = align_up(oo + bytes, A); return at; };
@@ -348,6 +364,11 @@ int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t
     return EXLR_OK;
 }
 
+int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t max_sa_bytes, uint64_t max_events, exlr_batch** out)
+{
+    return batch_alloc_impl(c, max_reads, max_ops, max_sa_bytes, max_events, true, out);
+}
+
 int exlr_batch_grow(exlr_batch* b, uint64_t max_events)
 {
     if (!b) return EXLR_ERR_ARG;
@@ -363,6 +384,7 @@ int exlr_batch_grow(exlr_batch* b, uint64_t max_events)
 int exlr_batch_get_views(exlr_batch* b, exlr_batch_views* v)
 {
     if (!b || !v) return EXLR_ERR_ARG;
+    if (b->is_bam) return EXLR_ERR_STATE;      // a BAM batch has no host-side record views
     *v = b->hv;
     return EXLR_OK;
 }
@@ -510,6 +532,7 @@ static int run_kernels(exlr_batch* b, bool prefetch_results)
 int exlr_submit(exlr_batch* b, uint64_t n_reads)
 {
     if (!b) return EXLR_ERR_ARG;
+    if (b->is_bam) return EXLR_ERR_STATE;
     int rc = check_sizes(b, n_reads);
     if (rc) return rc;
     CK(cudaSetDevice(b->ctx->device));
@@ -529,6 +552,7 @@ int exlr_submit(exlr_batch* b, uint64_t n_reads)
 int exlr_upload(exlr_batch* b, uint64_t n_reads)
 {
     if (!b) return EXLR_ERR_ARG;
+    if (b->is_bam) return EXLR_ERR_STATE;
     int rc = check_sizes(b, n_reads);
     if (rc) return rc;
     if (n_reads == 0) return EXLR_ERR_ARG;
@@ -678,6 +702,173 @@ int exlr_get_timing(exlr_batch* b, exlr_timing* t)
     return EXLR_OK;
 }
 
+// ---- BAM input decoded on the device ---------------------------------------------------------------------------------------
+int exlr_bam_batch_alloc(exlr_ctx* c, uint64_t max_comp_bytes, uint32_t max_blocks, uint64_t max_events, exlr_batch** out)
+{
+    if (!c || !out || max_comp_bytes == 0 || max_blocks == 0 || max_blocks > 32000u || max_comp_bytes >= 0xfff00000ull) return EXLR_ERR_ARG;
+    // what a chunk of max_blocks BGZF blocks (64 KB of BAM each at most) can hold: every bound is exact, so no chunk overflows its batch
+    const uint64_t u_cap = (uint64_t)max_blocks * 65536ull;
+    const uint64_t R = u_cap / 36 + 1, OPS = u_cap / 4 + 4, SAB = u_cap;
+    if (max_events == 0) max_events = R / 8 + 65536;
+    const bool fmt = c->device_format != 0;
+    c->device_format = 1;                      // the lines of a BAM batch are always formatted on the device (exlr_wait_text)
+    exlr_batch* b = nullptr;
+    const int rc = batch_alloc_impl(c, R, OPS, SAB, max_events, false, &b);
+    c->device_format = fmt;
+    if (rc) return rc;
+    b->is_bam = true; b->max_comp = max_comp_bytes; b->max_blocks = max_blocks; b->u_cap = u_cap;
+    cudaError_t e = cudaHostAlloc((void**)&b->h_comp, max_comp_bytes + 512, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_blocks, (size_t)max_blocks * sizeof(exlr_bgzf_block), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_btab, (size_t)max_blocks * sizeof(BgzfBlock), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_bctrl, sizeof(BamCtrl), cudaHostAllocMapped);
+    if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostAlloc(BAM chunk)"); }
+    memset(b->h_bctrl, 0, sizeof(BamCtrl));
+    const uint32_t tiles = bam_scan_tiles((uint32_t)R);
+    size_t dof = 0;
+    auto dcarve = [&](size_t bytes) { size_t at = dof; dof = align_up(dof + bytes, 256); return at; };
+    const size_t d_ctrl = dcarve(sizeof(BamCtrl) + (size_t)tiles * 24), d_comp = dcarve(max_comp_bytes + 1024), d_tab = dcarve((size_t)max_blocks * sizeof(BgzfBlock)),
+                 d_u = dcarve(u_cap + 256), d_blk = dcarve((size_t)max_blocks * 4 * 6), d_rec = dcarve(R * 4), d_per = dcarve(R * 4 * 5),
+                 d_qoff = dcarve((R + 1) * 4), d_qn = dcarve(u_cap + 16);
+    e = cudaMalloc(&b->d_bam, dof);
+    if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaMalloc(BAM chunk)"); }
+    char* ds = (char*)b->d_bam;
+    DevBam& D = b->db;
+    D.ctrl = (BamCtrl*)(ds + d_ctrl);
+    D.scan_x = (unsigned long long*)(ds + d_ctrl + sizeof(BamCtrl)); D.scan_y = D.scan_x + tiles; D.scan_z = D.scan_y + tiles;
+    b->bam_zero_bytes = sizeof(BamCtrl) + (size_t)tiles * 24;
+    D.comp = (const uint8_t*)(ds + d_comp); D.blocks = (const BgzfBlock*)(ds + d_tab); D.U = (uint8_t*)(ds + d_u);
+    uint32_t* pb = (uint32_t*)(ds + d_blk);
+    D.spec = pb; D.cnt = pb + max_blocks; D.exitp = pb + 2 * (size_t)max_blocks; D.kind = pb + 3 * (size_t)max_blocks;
+    D.blk_start = pb + 4 * (size_t)max_blocks; D.blk_base = pb + 5 * (size_t)max_blocks;
+    D.rec_start = (uint32_t*)(ds + d_rec);
+    uint32_t* pr = (uint32_t*)(ds + d_per);
+    D.ncig = pr; D.salen = pr + R; D.qlen = pr + 2 * R; D.cig_src = pr + 3 * R; D.sa_src = pr + 4 * R;
+    D.qname_off = (uint32_t*)(ds + d_qoff); D.qnames = (uint8_t*)(ds + d_qn);
+    D.max_reads = (uint32_t)R; D.n_ref = c->n_ref;
+    e = cudaHostGetDevicePointer((void**)&D.host_ctrl, b->h_bctrl, 0);
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&b->ev_bam[i]);
+    if (e == cudaSuccess) e = cudaMemset(D.U, 0, u_cap + 256);
+    if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "BAM chunk setup"); }
+    *out = b;
+    return EXLR_OK;
+}
+
+int exlr_bam_get_views(exlr_batch* b, exlr_bam_views* v)
+{
+    if (!b || !v || !b->is_bam) return EXLR_ERR_ARG;
+    v->comp = b->h_comp; v->blocks = b->h_blocks; v->max_comp_bytes = b->max_comp; v->max_blocks = b->max_blocks; v->reserved = 0;
+    return EXLR_OK;
+}
+
+int exlr_bam_submit(exlr_batch* b, uint64_t comp_bytes, uint32_t n_blocks)
+{
+    if (!b || !b->is_bam) return EXLR_ERR_ARG;
+    if (comp_bytes > b->max_comp || n_blocks > b->max_blocks) return EXLR_ERR_CAPACITY;
+    CK(cudaSetDevice(b->ctx->device));
+    uint64_t u = 0;
+    for (uint32_t i = 0; i < n_blocks; i++) {                  // where every block inflates to: the prefix sum of the ISIZEs
+        const exlr_bgzf_block& k = b->h_blocks[i];
+        if ((uint64_t)k.comp_off + k.comp_len > comp_bytes || k.ulen > 65536u) return EXLR_ERR_BGZF;
+        b->h_btab[i] = BgzfBlock{k.comp_off, k.comp_len, (uint32_t)u, k.ulen};
+        u += k.ulen;
+    }
+    cudaStream_t st = b->stream;
+    DevBam& D = b->db;
+    D.n_blocks = n_blocks; D.u_total = (uint32_t)u; D.start_off = 0;
+    b->bam_comp_bytes = comp_bytes; b->submitted = false; b->have_timing = false;
+    CK(cudaEventRecord(b->ev_bam[0], st));
+    CK(cudaMemsetAsync(D.ctrl, 0, b->bam_zero_bytes, st));
+    if (comp_bytes) CK(cudaMemcpyAsync((void*)D.comp, b->h_comp, comp_bytes, cudaMemcpyHostToDevice, st));
+    if (n_blocks) CK(cudaMemcpyAsync((void*)D.blocks, b->h_btab, (size_t)n_blocks * sizeof(BgzfBlock), cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(b->ev_bam[1], st));
+    launch_bam_inflate(D, st);
+    CK(cudaEventRecord(b->ev_bam[2], st));
+    CK(cudaGetLastError());
+    b->bam_state = 1;
+    return EXLR_OK;
+}
+
+int exlr_bam_walk(exlr_batch* b, uint64_t start_off)
+{
+    if (!b || !b->is_bam) return EXLR_ERR_ARG;
+    if (b->bam_state != 1) return EXLR_ERR_STATE;
+    if (start_off > b->db.u_total) return EXLR_ERR_ARG;
+    CK(cudaSetDevice(b->ctx->device));
+    b->db.start_off = (uint32_t)start_off;
+    b->dv.hc = HostCfg{b->ctx->sms, 4, b->ctx->k1a_ctas, b->ctx->k1_waves};
+    launch_bam_walk(b->db, b->dv, b->stream);
+    CK(cudaEventRecord(b->ev_bam[3], b->stream));
+    CK(cudaGetLastError());
+    b->bam_state = 2;
+    return EXLR_OK;
+}
+
+int exlr_bam_extract(exlr_batch* b, exlr_bam_info* info)
+{
+    if (!b || !info || !b->is_bam) return EXLR_ERR_ARG;
+    if (b->bam_state != 2 && b->bam_state != 3) return EXLR_ERR_STATE;      // (3: again, after exlr_batch_grow)
+    memset(info, 0, sizeof(*info));
+    CK(cudaSetDevice(b->ctx->device));
+    CK(cudaStreamSynchronize(b->stream));                       // the decode header is in mapped pinned memory now
+    const BamCtrl& c = *b->h_bctrl;
+    info->n_blocks = b->db.n_blocks; info->u_bytes = b->db.u_total; info->comp_bytes = b->bam_comp_bytes;
+    info->bad_block = -1;
+    CK(cudaEventElapsedTime(&info->h2d_ms, b->ev_bam[0], b->ev_bam[1]));
+    CK(cudaEventElapsedTime(&info->inflate_ms, b->ev_bam[1], b->ev_bam[2]));
+    CK(cudaEventElapsedTime(&info->walk_ms, b->ev_bam[2], b->ev_bam[3]));
+    b->bam_state = 3;
+    if (c.bad_block) { info->bad_block = (int32_t)~c.bad_block; info->status = EXLR_ERR_BGZF; return info->status; }
+    uint64_t n = c.n_rec;
+    info->tail_off = c.tail_off;
+    if (c.capped) { info->status = EXLR_ERR_CAPACITY; return info->status; }
+    if (c.bad_rec) {                                            // records before the corrupt one stand; the stream ends there
+        n = (uint32_t)~c.bad_rec; info->status = EXLR_ERR_BAM_RECORD;
+    } else if (c.corrupt) info->status = EXLR_ERR_BAM_RECORD;
+    info->n_reads = n; info->n_ops = c.n_ops; info->n_sa_bytes = c.n_sa;
+    // the records sit in the batch's device arrays exactly as exlr_upload would have left them: run the event kernels on them
+    b->n_reads = n; b->dv.n_reads = (uint32_t)n; b->resident_uploaded = false; b->have_timing = false;
+    if (c.bad_rec && n) {
+        // (the offsets of the kept prefix are valid; its op / byte totals are read back from the device)
+        unsigned long long ops = 0; uint32_t sab = 0;
+        CK(cudaMemcpy(&ops, b->dv.cigar_off + n, 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&sab, b->dv.sa_off + n, 4, cudaMemcpyDeviceToHost));
+        info->n_ops = ops; info->n_sa_bytes = sab;
+    }
+    b->n_ops = info->n_ops;
+    if (n == 0) { memset(b->h_ctrl, 0, sizeof(Ctrl)); b->h_line_off[0] = 0; b->submitted = true; b->formatted = true; return info->status; }
+    CK(cudaEventRecord(b->ev[EV_START], b->stream));
+    CK(cudaEventRecord(b->ev[EV_H2D], b->stream));
+    b->h2d_bytes = b->bam_comp_bytes + (uint64_t)b->db.n_blocks * sizeof(BgzfBlock);
+    const int rc = run_kernels(b, true);
+    if (rc) return rc;
+    b->submitted = true; b->have_timing = true;
+    return info->status;
+}
+
+int exlr_bam_download(exlr_batch* b, const exlr_batch_views* out, char* qnames, uint64_t qnames_cap, uint32_t* qname_off)
+{
+    if (!b || !out || !b->is_bam) return EXLR_ERR_ARG;
+    if (b->bam_state < 2) return EXLR_ERR_STATE;
+    CK(cudaSetDevice(b->ctx->device));
+    CK(cudaStreamSynchronize(b->stream));
+    const BamCtrl& c = *b->h_bctrl;
+    const uint64_t n = c.n_rec, ops = c.n_ops, sab = c.n_sa, qn = c.n_qn;
+    if (n > out->max_reads || ops > out->max_ops || sab > out->max_sa_bytes || (qnames && qn > qnames_cap)) return EXLR_ERR_CAPACITY;
+    const DevBatch& d = b->dv;
+    if (ops) CK(cudaMemcpy(out->cigar, d.cigar, ops * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out->cigar_off, d.cigar_off, (n + 1) * 8, cudaMemcpyDeviceToHost));
+    if (n) {
+        CK(cudaMemcpy(out->pos, d.pos, n * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(out->tid, d.tid, n * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(out->flag, d.flag, n * 2, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(out->mapq, d.mapq, n, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(out->sa_kind, d.sa_kind, n, cudaMemcpyDeviceToHost));
+    }
+    CK(cudaMemcpy(out->sa_off, d.sa_off, (n + 1) * 4, cudaMemcpyDeviceToHost));
+    if (sab) CK(cudaMemcpy(out->sa_bytes, d.sa_bytes, sab, cudaMemcpyDeviceToHost));
+    if (qnames && qn) CK(cudaMemcpy(qnames, b->db.qnames, qn, cudaMemcpyDeviceToHost));
+    if (qname_off) CK(cudaMemcpy(qname_off, b->db.qname_off, (n + 1) * 4, cudaMemcpyDeviceToHost));
+    return EXLR_OK;
+}
+
 int exlr_get_counters(exlr_batch* b, exlr_counters* out)
 {
     if (!b || !out) return EXLR_ERR_ARG;
@@ -718,6 +909,7 @@ int64_t exlr_format_lines(const exlr_ctx* c, const exlr_batch* b, const exlr_res
                           int verbose, const char* qnames, const uint32_t* qname_off, char* out, uint64_t out_cap)
 {
     if (!c || !b || !res || ev_begin > ev_end || ev_end > res->n_events) return EXLR_ERR_ARG;
+    if (b->is_bam) return EXLR_ERR_STATE;      // the records of a BAM batch never reach the host: its lines are formatted on the device
     if (verbose && (!qnames || !qname_off)) return EXLR_ERR_ARG;
     const uint8_t* sa = b->hv.sa_bytes;
     uint64_t w = 0;

@@ -143,6 +143,39 @@ struct DevParams {
     unsigned long long max_supp_alignm;
 };
 
+// ---- BAM input decoded on the device (exlr_bam.cu) -----------------------------------------
+static constexpr uint32_t KI_NONE = 0xffffffffu;
+struct BgzfBlock { uint32_t coff, clen, uoff, ulen; };    // deflate data = comp[coff, coff+clen) -> U[uoff, uoff+ulen)
+
+struct BamCtrl {                   // device-side control block of the BAM stages (zeroed per submit)
+    uint32_t bad_block;            // ~(smallest block index whose deflate stream is corrupt), 0 = none (atomicMax)
+    uint32_t n_rec, corrupt;       // records found by the walk; 1 = the chain hit a corrupt record header at tail_off
+    uint32_t tail_off;             // first byte of the stream the walk did not consume (a partial record, or the end)
+    uint32_t n_ops, n_sa, n_qn;    // totals of the gathered batch
+    uint32_t bad_rec;              // ~(smallest record index with corrupt aux data), 0 = none
+    uint32_t ticket[3];
+    uint32_t capped;               // 1 = more records than the batch holds (cannot happen with the bounds of exlr_bam_batch_alloc)
+    uint32_t pad[4];
+};
+static_assert(sizeof(BamCtrl) == 64, "BamCtrl");
+
+struct DevBam {
+    const uint8_t* comp; const BgzfBlock* blocks; uint32_t n_blocks;
+    uint8_t* U; uint32_t u_total, start_off; int32_t n_ref;
+    uint32_t *spec, *cnt, *exitp, *kind;            // per block: speculated first record, records owned, where the chain leaves, how it stopped
+    uint32_t *blk_start, *blk_base;                 // per block, verified: first record (KI_NONE: none) and index of its first record
+    uint32_t* rec_start;                            // [max_reads] offset of every record's block_size word
+    uint32_t *ncig, *salen, *qlen, *cig_src, *sa_src;   // per record
+    uint32_t* qname_off; uint8_t* qnames;           // gathered read names (for -v and for inspection)
+    unsigned long long *scan_x, *scan_y, *scan_z;   // chained-scan status words
+    BamCtrl* ctrl; BamCtrl* host_ctrl;              // device block and its mirror in mapped pinned memory
+    uint32_t max_reads;
+};
+
+void launch_bam_inflate(const DevBam& B, cudaStream_t st);
+void launch_bam_walk(const DevBam& B, const DevBatch& D, cudaStream_t st);
+uint32_t bam_scan_tiles(uint32_t max_reads);
+
 // launchers (exlr_cigar.cu, exlr_sa.cu, exlr_order.cu)
 cudaError_t configure_kernels(int device, int* sm_count_out);
 size_t k1_flat_smem_bytes();

@@ -231,7 +231,6 @@ int main(int argc, char** argv)
 
     using clk = std::chrono::steady_clock;
     auto secs = [](clk::duration d) { return std::chrono::duration<double>(d).count(); };
-    const auto t_begin = clk::now();
     double t_wait = 0, t_format = 0, t_write = 0; uint64_t n_lines = 0, n_batches = 0, n_regrown = 0;
     std::thread writer([&]() {
         std::vector<char> text;
@@ -310,7 +309,8 @@ int main(int argc, char** argv)
 
     uint64_t seq = 0;
     int cur = acquire(seq);
-    const double t_setup = secs(clk::now() - t_start);                   // CUDA context + buffers of the first GPU, BAM header
+    const auto t_begin = clk::now();
+    const double t_setup = secs(t_begin - t_start);                      // CUDA context + buffers of the first GPU, BAM header
     BamRecordView r;
     uint64_t n_rec = 0;
     while (cur >= 0 && rd.next(r)) {

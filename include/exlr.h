@@ -39,6 +39,8 @@ extern "C" {
 #define EXLR_ERR_NOMEM         -3   /* host or device allocation failed                              */
 #define EXLR_ERR_CAPACITY      -4   /* batch larger than its allocation, or event buffer overflow    */
 #define EXLR_ERR_STATE         -5   /* call sequence error (wait without submit, ...)                */
+#define EXLR_ERR_BGZF          -7   /* exlr_bam_*: corrupt BGZF block (the reference's reader returns an error there and the loop stops quietly, main.rs:165-168) */
+#define EXLR_ERR_BAM_RECORD    -8   /* exlr_bam_*: corrupt BAM record in the inflated stream (same: the records before it stand)        */
 #define EXLR_ERR_TEXT_CAPACITY -6   /* exlr_wait_text: the lines need more than the batch's text buffer; format on the host */
 /* Per-record conditions on which the reference panics (exit 101).  exlr_result.err_read holds the
  * smallest offending record index of the batch; the lines the reference had written by then are valid:
@@ -236,6 +238,58 @@ typedef struct exlr_counters {
 int  exlr_get_counters(exlr_batch* b, exlr_counters* c);
 /* debug (EXLR_OPT_TRACE): 4 x u64 per CTA of kernel 1 {globaltimer at start, at first data, at end, tiles | scanned tiles << 32} */
 int  exlr_get_trace(exlr_batch* b, unsigned long long* out, uint32_t n_ctas);
+
+/* ---- BAM input decoded on the device ---------------------------------------------------------
+ * Replaces, for BGZF-compressed BAM, what htslib does for the reference between the file and the record loop
+ * (bam::Reader::from_path, set_threads, bam.read(&mut record): main.rs:137,155,158): the host only hops over the BGZF block
+ * headers of a chunk of the file (gzip header with the BC extra field, 18 bytes; ISIZE in the last 4 bytes of the block) and
+ * hands the compressed bytes over; DEFLATE, the BAM record walk (with htslib's CG:B,I long-CIGAR restore), the SA aux
+ * lookup and the packing into the structure-of-arrays batch all run as kernels, and the event kernels follow on the same
+ * device arrays.  A chunk is a run of whole BGZF blocks; records may straddle chunks:
+ *
+ *   exlr_bam_submit(b, bytes, n_blocks)   async: H2D of the chunk + inflate
+ *   exlr_bam_walk(b, start_off)           async: records from uncompressed offset start_off on (the end of the BAM header for
+ *                                         the first chunk; for the next one, where the previous chunk's tail record begins
+ *                                         inside the blocks the caller repeated at the front of this chunk)
+ *   exlr_bam_extract(b, &info)            waits for the walk, reports the chunk (records, tail_off = first byte not consumed:
+ *                                         a partial record or the end of the chunk) and starts the event kernels
+ *   exlr_wait_text(b, ...)                the lines, exactly as for exlr_submit with EXLR_OPT_DEVICE_FORMAT
+ */
+typedef struct exlr_bgzf_block {
+    uint32_t comp_off;    /* offset of the block's DEFLATE data (after the gzip header + extra field) in the chunk */
+    uint32_t comp_len;    /* its length: BSIZE + 1 - XLEN - 20                                                     */
+    uint32_t ulen;        /* ISIZE: bytes the block inflates to (<= 65536)                                         */
+    uint32_t reserved;
+} exlr_bgzf_block;
+
+typedef struct exlr_bam_views {
+    uint8_t* comp;             /* [max_comp_bytes] pinned: the caller reads the file straight into it */
+    exlr_bgzf_block* blocks;   /* [max_blocks] pinned                                                 */
+    uint64_t max_comp_bytes;
+    uint32_t max_blocks, reserved;
+} exlr_bam_views;
+
+typedef struct exlr_bam_info {
+    int32_t  status;           /* EXLR_OK, EXLR_ERR_BGZF (bad_block set), EXLR_ERR_BAM_RECORD (n_reads = the records before it) */
+    int32_t  bad_block;        /* first block whose DEFLATE stream is corrupt, else -1                                        */
+    uint32_t n_blocks, reserved;
+    uint64_t n_reads, n_ops, n_sa_bytes;
+    uint64_t tail_off;         /* uncompressed offset inside this chunk of the first byte the walk did not consume            */
+    uint64_t u_bytes, comp_bytes;
+    float    h2d_ms, inflate_ms, walk_ms;   /* device times of the decode stages (CUDA events on the batch's stream)          */
+    float    reserved2;
+} exlr_bam_info;
+
+/* A batch for chunks of at most max_blocks BGZF blocks / max_comp_bytes compressed bytes; its record capacity is the most
+ * such a chunk can hold, so no chunk overflows it.  Lines are always formatted on the device. */
+int  exlr_bam_batch_alloc(exlr_ctx* ctx, uint64_t max_comp_bytes, uint32_t max_blocks, uint64_t max_events, exlr_batch** out);
+int  exlr_bam_get_views(exlr_batch* b, exlr_bam_views* v);
+int  exlr_bam_submit(exlr_batch* b, uint64_t comp_bytes, uint32_t n_blocks);
+int  exlr_bam_walk(exlr_batch* b, uint64_t start_off);
+int  exlr_bam_extract(exlr_batch* b, exlr_bam_info* info);
+/* Inspection / tests: copies the decoded structure-of-arrays batch of the last walked chunk into caller memory (`out` holds
+ * caller-allocated arrays and their capacities; qnames / qname_off may be NULL). */
+int  exlr_bam_download(exlr_batch* b, const exlr_batch_views* out, char* qnames, uint64_t qnames_cap, uint32_t* qname_off);
 
 /* ---- host formatter: utils.rs:196-283 ------------------------------------------------- */
 /* Writes the lines of events [ev_begin, ev_end) of `res` into out (capacity out_cap) and

@@ -1,0 +1,148 @@
+"""BAM input decoded on the device (exlr_bam_*): BGZF inflate, record walk, SA / CG aux lookup and packing as kernels.
+The checker is the batch the BAM was written from -- exactly what the host reader (bam_reader.hpp, tests/test_bam_reader.py)
+hands the packer for the same file -- and, end to end, the oracle's lines."""
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle_c
+from excord_lr_b200 import api, bamio, synth
+from excord_lr_b200.batch import ExlrParams, pack_records
+from gpu_helpers import gpu_available
+from randrec import rand_batch, REF_NAMES
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not gpu_available(), reason="needs a B200")]
+FIELDS = ("cigar", "cigar_off", "pos", "tid", "flag", "mapq", "sa_kind", "sa_off", "sa_bytes")
+
+
+def _header_end(data, blocks):
+    """Uncompressed offset of the first record (the host's zlib-side job in the CLI)."""
+    u = b"".join(zlib.decompress(data[co:co + cl], -15) for co, cl, _ in blocks[:64])
+    l_text, = struct.unpack_from("<i", u, 4)
+    n_ref, = struct.unpack_from("<i", u, 8 + l_text)
+    o = 12 + l_text
+    for _ in range(n_ref):
+        l_name, = struct.unpack_from("<i", u, o)
+        o += 8 + l_name
+    return o
+
+
+def _decode(path, params=None, ref_names=REF_NAMES):
+    data = open(path, "rb").read()
+    blocks, used = api.bgzf_blocks(data)
+    p = params or ExlrParams.make()
+    ex = api.Extractor(p, ref_names)
+    bb = api.BamBatch(ex, len(data) + 64, max(1, len(blocks)))
+    bb.load(data[:used], blocks)
+    bb.walk(_header_end(data, blocks))
+    info = bb.extract()
+    return ex, bb, info
+
+
+def _same(got, hb, n=None):
+    n = hb.n_reads if n is None else n
+    for f in FIELDS:
+        a, b = getattr(got, f), getattr(hb, f)
+        if f in ("cigar_off", "sa_off"):
+            b = b[:n + 1]
+        elif f == "cigar":
+            b = b[:int(hb.cigar_off[n])]
+        elif f == "sa_bytes":
+            b = b[:int(hb.sa_off[n])]
+        else:
+            b = b[:n]
+        assert np.array_equal(a, b), f
+
+
+@pytest.mark.parametrize("level,block,seq_len", [(1, 0xFF00, 11), (6, 0xFF00, 0), (9, 3000, 37), (0, 0xFF00, 5), (6, 200, 3), (1, 65280, 300)])
+def test_decode_matches_the_batch_it_was_written_from(tmp_path, level, block, seq_len):
+    # compression levels 0 (stored blocks) .. 9, tiny blocks (fixed Huffman codes, records straddling many blocks), SEQ/QUAL to skip
+    hb = synth.with_qnames(synth.config(0, 0.3))
+    bam = str(tmp_path / "x.bam")
+    bamio.write_bam(hb, bam, ref_lens=synth.ref_lens(), level=level, block=block, seq_len=seq_len)
+    ex, bb, info = _decode(bam, ref_names=hb.ref_names)
+    assert info.status == 0 and info.n_reads == hb.n_reads and info.n_ops == hb.n_ops and info.n_sa_bytes == hb.n_sa_bytes
+    assert info.tail_off == info.u_bytes
+    got = bb.download(hb.ref_names, hb.n_reads, hb.n_ops, hb.n_sa_bytes)
+    _same(got, hb)
+    assert got.qnames == hb.qnames
+    bb.free(); ex.close()
+
+
+def test_random_records_and_long_cigars(tmp_path):
+    hb = rand_batch(11, 400, qnames=True)
+    hb.tid[hb.tid >= len(REF_NAMES)] = 0
+    rng = np.random.default_rng(3)
+    ops = ((rng.integers(1, 30, 70000).astype(np.uint32) << 4) | rng.choice([0, 1, 2], 70000).astype(np.uint32)).tolist()
+    big = pack_records([dict(tid=0, pos=100, flag=0, mapq=60, cigar=ops, sa="chr1,5,+,10M,3,0;"), dict(tid=1, pos=7, flag=16, mapq=1, cigar="5S10M")], REF_NAMES)
+    for h, kw in ((hb, dict(seq_len=37, block=4000)), (hb, dict(seq_len=0, level=6)), (big, dict()), (big, dict(seq_len=9, block=1000))):
+        bam = str(tmp_path / "r.bam")
+        bamio.write_bam(h, bam, **kw)
+        ex, bb, info = _decode(bam)
+        assert info.status == 0 and info.n_reads == h.n_reads
+        _same(bb.download(REF_NAMES, h.n_reads, h.n_ops, h.n_sa_bytes), h)
+        bb.free(); ex.close()
+
+
+def test_lines_from_compressed_bytes_match_the_oracle(tmp_path):
+    # compressed BAM bytes in, the reference's lines out: nothing but block-header hopping happens on the host
+    for cfg, scale, seq_len in ((0, 1.0, 20), (1, 0.02, 0), (3, 0.01, 4)):
+        hb = synth.config(cfg, scale)
+        p = ExlrParams.make(**synth.CONFIGS[cfg]["params"])
+        bam = str(tmp_path / "c.bam")
+        bamio.write_bam(hb, bam, ref_lens=synth.ref_lens(), seq_len=seq_len, level=6)
+        ex, bb, info = _decode(bam, p, hb.ref_names)
+        assert info.status == 0 and info.n_reads == hb.n_reads
+        res, text = bb.wait_text()
+        want = oracle_c.run(hb, p)
+        assert res.status == want.status == 0 and res.n_events == len(want.events)
+        assert text == oracle_c.format_lines(hb, want.events)
+        bb.free(); ex.close()
+
+
+def test_partial_record_at_the_end_is_the_tail(tmp_path):
+    # a chunk that ends inside a record: every whole record is decoded, tail_off names the first byte of the partial one
+    hb = synth.config(0, 0.2)
+    bam = str(tmp_path / "t.bam")
+    bamio.write_bam(hb, bam, ref_lens=synth.ref_lens(), block=5000, seq_len=50)
+    data = open(bam, "rb").read()
+    blocks, used = api.bgzf_blocks(data)
+    keep = len(blocks) * 2 // 3
+    ex = api.Extractor(ExlrParams.make(), hb.ref_names)
+    bb = api.BamBatch(ex, len(data), len(blocks))
+    bb.load(data[:used], blocks[:keep])
+    bb.walk(_header_end(data, blocks))
+    info = bb.extract()
+    assert info.status == 0 and 0 < info.n_reads < hb.n_reads and info.tail_off < info.u_bytes
+    n = int(info.n_reads)
+    _same(bb.download(hb.ref_names, n, int(info.n_ops), int(info.n_sa_bytes)), hb, n)
+    # the next chunk repeats the blocks from the tail's block on and starts its walk at the tail
+    u_off = np.concatenate([[0], np.cumsum([b[2] for b in blocks])])
+    first = int(np.searchsorted(u_off, info.tail_off, side="right") - 1)
+    bb.load(data[:used], blocks[first:])
+    bb.walk(int(info.tail_off - u_off[first]))
+    info2 = bb.extract()
+    assert info2.status == 0 and info2.n_reads == hb.n_reads - n and info2.tail_off == info2.u_bytes
+    rest = bb.download(hb.ref_names, int(info2.n_reads), int(info2.n_ops), int(info2.n_sa_bytes))
+    assert np.array_equal(rest.pos, hb.pos[n:]) and np.array_equal(rest.cigar, hb.cigar[int(hb.cigar_off[n]):])
+    bb.free(); ex.close()
+
+
+def test_corrupt_block_is_reported(tmp_path):
+    hb = synth.config(0, 0.1)
+    bam = str(tmp_path / "b.bam")
+    bamio.write_bam(hb, bam, ref_lens=synth.ref_lens(), block=8000, level=6)
+    data = bytearray(open(bam, "rb").read())
+    blocks, used = api.bgzf_blocks(bytes(data))
+    co, cl, _ = blocks[5]
+    for k in range(co + 2, co + min(cl, 40)):
+        data[k] ^= 0x5A
+    ex = api.Extractor(ExlrParams.make(), hb.ref_names)
+    bb = api.BamBatch(ex, len(data), len(blocks))
+    bb.load(bytes(data[:used]), blocks)
+    bb.walk(0)
+    info = bb.extract()
+    assert info.status == -7 and info.bad_block == 5
+    bb.free(); ex.close()
