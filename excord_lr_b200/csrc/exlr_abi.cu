@@ -45,6 +45,7 @@ struct exlr_ctx {
     int k1a_ctas = 8, k1_waves = 3, sms = 148; // EXLR_OPT_K1A_CTAS_PER_SM, EXLR_OPT_K1_WAVES; multiprocessors of `device`
     uint32_t reads_per_cta = 0;                // EXLR_OPT_READS_PER_CTA (0 = auto)
     int device_format = 0;                     // EXLR_OPT_DEVICE_FORMAT: kernels 5a/5b write the output lines; read with exlr_wait_text
+    int verbose_text = 0;                      // EXLR_OPT_VERBOSE_TEXT: BAM batches format the -v columns too (the read names are on the device there)
     int long_records = 0;                      // EXLR_OPT_LONG_RECORDS: 0 auto (by mean CIGAR length), 1 never, 2 kernel 1c, 3 kernel 1d
     std::atomic<int> skip_screen{0};           // auto mode: batches left to run without the screen pass (the last screened one was event-dense);
                                                // written by whoever waits a batch, read by whoever submits the next (two threads in the CLI)
@@ -70,6 +71,7 @@ struct exlr_batch {
     char* h_text = nullptr;                    // pinned: formatted lines (allocated with the batch when EXLR_OPT_DEVICE_FORMAT is set)
     bool formatted = false;                    // the last submit ran kernels 5a/5b
     bool device_format = false;                // EXLR_OPT_DEVICE_FORMAT was set when the batch was allocated
+    bool verbose_text = false;                 // a BAM batch allocated with EXLR_OPT_VERBOSE_TEXT: its device-formatted lines carry the -v columns
     void* d_slab = nullptr;                    // one device allocation, carved up below
     DevBatch dv{};
     size_t ctrl_bytes = 0;                     // ctrl + both scan status arrays (one memset)
@@ -96,6 +98,7 @@ static constexpr size_t kRawHeadroom = 256 * 1024;
 // EXLR_OPT_DEVICE_FORMAT: room for the formatted lines, per max_events entry (a typical line is 40-60 bytes; when a batch needs
 // more, exlr_wait_text says so and the caller formats on the host)
 static constexpr size_t kTextBytesPerLine = 96;
+static constexpr size_t kTextBytesPerVerboseLine = 288;    // -v lines carry a tag of up to 50 bytes and the read name (BAM batches)
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -113,7 +116,7 @@ static int alloc_event_buffers(exlr_batch* b, uint64_t max_events)
 {
     if (max_events == 0 || max_events >= 0xfff00000ull) return EXLR_ERR_ARG;
     const bool fmt = b->device_format;
-    const size_t text_cap = fmt ? max_events * kTextBytesPerLine : 0;
+    const size_t text_cap = fmt ? max_events * (b->verbose_text ? kTextBytesPerVerboseLine : kTextBytesPerLine) : 0;
     if (text_cap >= 0xfffffff0ull) return EXLR_ERR_ARG;
     const uint32_t ttiles = fmt ? text_scan_tiles((uint32_t)max_events) : 0;
     size_t dof = 0;
@@ -250,6 +253,7 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
     case EXLR_OPT_READS_PER_CTA: if (value < 0 || value > 128) return EXLR_ERR_ARG; c->reads_per_cta = (uint32_t)value; return EXLR_OK;
     case EXLR_OPT_OVERLAP: c->overlap = value != 0; return EXLR_OK;
     case EXLR_OPT_DEVICE_FORMAT: c->device_format = value != 0; return EXLR_OK;
+    case EXLR_OPT_VERBOSE_TEXT: c->verbose_text = value != 0; return EXLR_OK;
     case EXLR_OPT_LONG_RECORDS: if (value < 0 || value > 3) return EXLR_ERR_ARG; c->long_records = (int)value; return EXLR_OK;
     case EXLR_OPT_K1A_CTAS_PER_SM: if (value < 1 || value > 8) return EXLR_ERR_ARG; c->k1a_ctas = (int)value; return EXLR_OK;
     case EXLR_OPT_TRACE: if (value < 0 || value > 7) return EXLR_ERR_ARG; c->trace = (int)value; return EXLR_OK;
@@ -279,7 +283,7 @@ void exlr_batch_free(exlr_batch* b)
     delete b;
 }
 
-static int batch_alloc_impl(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t max_sa_bytes, uint64_t max_events, bool host_inputs, exlr_batch** out)
+static int batch_alloc_impl(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t max_sa_bytes, uint64_t max_events, bool host_inputs, bool verbose_text, exlr_batch** out)
 {
     if (!c || !out) return EXLR_ERR_ARG;
     *out = nullptr;
@@ -315,7 +319,7 @@ static int batch_alloc_impl(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, u
     b->h_ctrl = (Ctrl*)((char*)b->h_out + o_ctrl); b->h_line_off = (uint32_t*)((char*)b->h_out + o_loff);
     e = cudaHostGetDevicePointer((void**)&b->h_ctrl_dev, b->h_ctrl, 0);
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostGetDevicePointer"); }
-    b->device_format = c->device_format != 0;
+    b->device_format = c->device_format != 0; b->verbose_text = verbose_text;
     // ---- device slab
     const uint32_t tiles = scan_tiles((uint32_t)R);
     const bool need_pool = c->params.max_supp_alignm + 1 > (uint64_t)kLocalSegs;
@@ -366,7 +370,7 @@ static int batch_alloc_impl(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, u
 
 int exlr_batch_alloc(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t max_sa_bytes, uint64_t max_events, exlr_batch** out)
 {
-    return batch_alloc_impl(c, max_reads, max_ops, max_sa_bytes, max_events, true, out);
+    return batch_alloc_impl(c, max_reads, max_ops, max_sa_bytes, max_events, true, false, out);
 }
 
 int exlr_batch_grow(exlr_batch* b, uint64_t max_events)
@@ -504,6 +508,8 @@ static int run_kernels(exlr_batch* b, bool prefetch_results)
     if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K4A], st));
     launch_k4b(d, c->dparams, c->far_mode, st); b->launches++;
     b->formatted = d.text_off != nullptr;
+    d.qnames = b->is_bam ? b->db.qnames : nullptr; d.qname_off = b->is_bam ? b->db.qname_off : nullptr;
+    d.verbose = b->is_bam && b->verbose_text ? 1u : 0u;
     if (b->formatted) { launch_k5(d, st); b->launches += 2; }      // (no event in between: 5a is placed while 4b drains)
     launch_header(d, b->h_ctrl_dev, st); b->launches++;            // the result header, stored straight into pinned host memory
     b->far_ran = c->far_mode;
@@ -713,7 +719,7 @@ int exlr_bam_batch_alloc(exlr_ctx* c, uint64_t max_comp_bytes, uint32_t max_bloc
     const bool fmt = c->device_format != 0;
     c->device_format = 1;                      // the lines of a BAM batch are always formatted on the device (exlr_wait_text)
     exlr_batch* b = nullptr;
-    const int rc = batch_alloc_impl(c, R, OPS, SAB, max_events, false, &b);
+    const int rc = batch_alloc_impl(c, R, OPS, SAB, max_events, false, c->verbose_text != 0, &b);
     c->device_format = fmt;
     if (rc) return rc;
     b->is_bam = true; b->max_comp = max_comp_bytes; b->max_blocks = max_blocks; b->u_cap = u_cap;

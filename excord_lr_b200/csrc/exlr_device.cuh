@@ -128,6 +128,8 @@ struct DevBatch {
     // outputs
     uint32_t* line_off;     // [R+1]
     exlr_event* events;     // [max_events]
+    const uint8_t* qnames; const uint32_t* qname_off;   // read names on the device (BAM batches only, else null)
+    uint32_t verbose;       // 1 = kernels 5a/5b add the -v columns (utils.rs:205-223, 252-267); needs qnames
     uint32_t* text_off;     // [max_events+1] byte offset of every line (kernel 5a); null unless EXLR_OPT_DEVICE_FORMAT
     uint8_t* text;          // [text_cap] the formatted lines (kernel 5b)
     uint32_t text_cap;

@@ -418,6 +418,17 @@ __device__ __forceinline__ const uint8_t* chrom_name(const DevBatch& B, uint32_t
     return B.ref_bytes + a;
 }
 
+// the -v columns: "\t{tag}\t{qname}\tstrand:{record strand}\tflag:{flags}" (utils.rs:205-223, 252-267); the tag names the f.write site
+__constant__ char kTagText[5][56] = {"excord-lr-alignment-event", "excord-lr-alignment-event-large-ins", "excord-lr-alignment-event-large-ins-one-alignments",
+                                     "excord-lr-alignment-event-large-ins-two-alignments", "excord-lr-split-read"};
+__constant__ uint32_t kTagLen[5] = {25, 35, 50, 50, 20};
+
+__device__ __forceinline__ uint32_t verbose_len(const DevBatch& B, const exlr_event& e)
+{
+    const uint32_t r = e.read_idx, kind = min(EXLR_EV_KIND(e.meta), 4u), flag = B.flag[r];
+    return 1u + kTagLen[kind] + 1u + (B.qname_off[r + 1] - B.qname_off[r]) + 8u + ((flag & 0x10u) ? 2u : 1u) + 6u + dec_len((int64_t)flag);
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS) k5a_line_bytes(DevBatch B)
 {
     __shared__ uint32_t s_tile, s_warp[16];
@@ -440,6 +451,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k5a_line_bytes(DevBatch B)
             len = a + b + dec_len(e.lstart) + dec_len(e.lend) + dec_len(e.rstart) + dec_len(e.rend)
                   + (EXLR_EV_LSTRAND(e.meta) < 0 ? 2u : 1u) + (EXLR_EV_RSTRAND(e.meta) < 0 ? 2u : 1u)
                   + dec_len((int64_t)EXLR_EV_NUM(e.meta)) + 9u;                 // 8 tabs and the newline
+            if (B.verbose) len += verbose_len(B, e);
         }
         uint32_t grand;
         const uint32_t at = tile_excl_scan(B.scan_c, tile, len, s_warp, &grand);
@@ -462,7 +474,21 @@ __device__ __forceinline__ uint8_t* k5_put_line(const DevBatch& B, const exlr_ev
     for (uint32_t k = 0; k < len; k++) *p++ = nm[k];
     *p++ = '\t'; p = put_dec(p, e.rstart); *p++ = '\t'; p = put_dec(p, e.rend); *p++ = '\t';
     p = put_dec(p, EXLR_EV_RSTRAND(e.meta)); *p++ = '\t';
-    p = put_dec(p, (int64_t)EXLR_EV_NUM(e.meta)); *p++ = '\n';
+    p = put_dec(p, (int64_t)EXLR_EV_NUM(e.meta));
+    if (B.verbose) {
+        const uint32_t r = e.read_idx, kind = min(EXLR_EV_KIND(e.meta), 4u), flag = B.flag[r];
+        *p++ = '\t';
+        for (uint32_t k = 0; k < kTagLen[kind]; k++) *p++ = (uint8_t)kTagText[kind][k];
+        *p++ = '\t';
+        for (uint32_t k = B.qname_off[r]; k < B.qname_off[r + 1]; k++) *p++ = B.qnames[k];
+        const char* s1 = "\tstrand:";
+        for (int k = 0; k < 8; k++) *p++ = (uint8_t)s1[k];
+        p = put_dec(p, (flag & 0x10u) ? -1 : 1);
+        const char* s2 = "\tflag:";
+        for (int k = 0; k < 6; k++) *p++ = (uint8_t)s2[k];
+        p = put_dec(p, (int64_t)flag);
+    }
+    *p++ = '\n';
     return p;
 }
 

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "../../include/exlr.h"
+#include "bam_chunker.hpp"
 #include "bam_reader.hpp"
 #include "packer.hpp"
 
@@ -35,6 +36,8 @@ struct Cli {
     int gpus = 0;                       // 0 = all visible
     bool stats = false;                 // --stats: stage times on stderr
     unsigned long long batch_reads = 131072, batch_ops = 0, batch_sa = 0, batch_events = 0;
+    bool host_reader = false;           // --host-reader: inflate + parse BAM on host threads (zlib) even when the GPU decoder applies
+    unsigned long long chunk_mb = 64, chunk_blocks = 0;   // GPU decoder: compressed bytes / BGZF blocks per chunk
 };
 
 static void usage(FILE* f)
@@ -61,6 +64,9 @@ static void usage(FILE* f)
           "      --gpus <N>                           GPUs to shard batches over [default: all visible]\n"
           "      --batch-reads <N>                    Records per GPU batch [default: 131072]\n"
           "      --batch-events <N>                   Output lines a batch has room for at first [default: 4 x batch-reads + 4096]; grown on demand\n"
+          "      --host-reader                        Inflate and parse BAM on host threads (-t) instead of on the GPU\n"
+          "      --chunk-mb <N>                       GPU BAM decoder: compressed megabytes per chunk [default: 64]\n"
+          "      --chunk-blocks <N>                   GPU BAM decoder: BGZF blocks per chunk [default: by --chunk-mb]\n"
           "      --stats                              Print stage times to stderr\n"
           "  -h, --help                               Print help\n"
           "  -V, --version                            Print version\n", f);
@@ -113,6 +119,9 @@ static int parse_cli(int argc, char** argv, Cli& c)
         else if (a == "--gpus") { NUM(64); c.gpus = (int)u; }
         else if (a == "--batch-reads") { NUM(1ull << 30); c.batch_reads = u ? u : 1; }
         else if (a == "--batch-events") { NUM(0xfff00000ull - 1); c.batch_events = u; }
+        else if (a == "--host-reader") { if (!flagopt(&c.host_reader)) return 2; }
+        else if (a == "--chunk-mb") { NUM(2048); c.chunk_mb = u ? u : 1; }
+        else if (a == "--chunk-blocks") { NUM(30000); c.chunk_blocks = u; }
         else if (a == "--stats") { if (!flagopt(&c.stats)) return 2; }
         else if (a == "-h" || a == "--help") { usage(stdout); return -1; }
         else if (a == "-V" || a == "--version") { puts("excord-LR 0.1.17"); return -1; }
@@ -133,6 +142,8 @@ static bool is_stream(const std::string& p) { struct stat st; return stat(p.c_st
 
 struct Slot {
     exlr_batch* b = nullptr; PackedBatch pk; int gpu = 0;
+    // GPU BAM decoder: the chunk this slot holds
+    exlr_bam_views bv{}; std::vector<uint64_t> u_off; uint32_t n_blocks = 0; uint64_t walk_start = 0, comp_bytes = 0; exlr_bam_info info{};
 };
 
 // One GPU of the run: its context and batch slots are created by its own thread, and only once a batch is headed for it
@@ -182,17 +193,31 @@ int main(int argc, char** argv)
     }
     if (cli.thread == 0) { fputs("thread pool of 0 threads: the reference panics here\n", stderr); return 101; }
 
+    // BGZF-compressed BAM in a regular file: the GPU inflates it and walks the records (exlr_bam_*), the host only hops over
+    // block headers.  Everything else (SAM text, pipes, --host-reader) goes through the host reader and the packer.
+    BgzfBamStream bs;
+    const bool device_bam = !cli.host_reader && !in_stream && bs.open(cli.bam);
+    if (!device_bam && !bs.error.empty() && !cli.host_reader && !in_stream) { fprintf(stderr, "%s\n", bs.error.c_str()); return 101; }
     BamReader rd;
-    if (!rd.open(in_stream && cli.bam == "-" ? "-" : cli.bam, (int)std::min<unsigned long long>(cli.thread, 256))) { fprintf(stderr, "%s\n", rd.error.c_str()); return 101; }
+    if (!device_bam && !rd.open(in_stream && cli.bam == "-" ? "-" : cli.bam, (int)std::min<unsigned long long>(cli.thread, 256))) { fprintf(stderr, "%s\n", rd.error.c_str()); return 101; }
+    const std::vector<std::string>& ref_names = device_bam ? bs.ref_names : rd.ref_names;
 
     int ndev = exlr_device_count();
     if (ndev <= 0) { fprintf(stderr, "no usable B200: %s (%s)\n", exlr_strerror(EXLR_ERR_CUDA), exlr_last_cuda_error()); return 3; }
     if (cli.gpus > 0) ndev = std::min(ndev, cli.gpus);
-    std::vector<const char*> names; for (auto& s : rd.ref_names) names.push_back(s.c_str());
+    std::vector<const char*> names; for (auto& s : ref_names) names.push_back(s.c_str());
     const unsigned long long R = cli.batch_reads;
     const unsigned long long OPS = cli.batch_ops ? cli.batch_ops : std::max<unsigned long long>(R * 64, 4ull << 20);
     const unsigned long long SAB = cli.batch_sa ? cli.batch_sa : std::max<unsigned long long>(R * 64, 1ull << 20);
-    const unsigned long long EVS = cli.batch_events ? cli.batch_events : 4 * R + 4096;
+    const unsigned long long EVS = cli.batch_events ? cli.batch_events : (device_bam ? 0 : 4 * R + 4096);
+    // GPU decoder: chunk geometry.  A chunk never needs more than the file holds; some blocks are kept free for the blocks of the
+    // previous chunk that are repeated in front (from the one its last, partial record begins in)
+    unsigned long long file_bytes = 0;
+    { struct stat st; if (device_bam && stat(cli.bam.c_str(), &st) == 0) file_bytes = (unsigned long long)st.st_size; }
+    const unsigned long long chunk_bytes = std::min<unsigned long long>(cli.chunk_mb << 20, file_bytes + 65536) + (1u << 20);
+    const uint32_t chunk_blocks = (uint32_t)(cli.chunk_blocks ? cli.chunk_blocks : std::min<unsigned long long>(30000, std::max<unsigned long long>(chunk_bytes / 12288, 64)));
+    const uint32_t over_blocks = std::max<uint32_t>(chunk_blocks / 4, std::min<uint32_t>(chunk_blocks - 1, 8));
+    const unsigned long long over_bytes = std::min<unsigned long long>((unsigned long long)over_blocks * 65536ull, chunk_bytes / 2);
     const int per_gpu = 3;
     std::vector<Slot> slots((size_t)ndev * per_gpu);
     std::vector<Gpu> gpus(ndev);
@@ -209,10 +234,16 @@ int main(int argc, char** argv)
             int st = exlr_create(&cli.p, g, names.data(), (int)names.size(), &ctx);
             // without -v the lines are formatted on the device (kernels 5a/5b) and the D2H copy carries the final bytes;
             // -v lines carry the read name, which stays on the host: those are formatted here
-            if (!st) st = exlr_set_option(ctx, EXLR_OPT_DEVICE_FORMAT, cli.verbose ? 0 : 1);
+            if (!st) st = exlr_set_option(ctx, EXLR_OPT_DEVICE_FORMAT, (cli.verbose && !device_bam) ? 0 : 1);
+            if (!st && device_bam) st = exlr_set_option(ctx, EXLR_OPT_VERBOSE_TEXT, cli.verbose ? 1 : 0);   // the read names are on the device there
             for (int k = 0; k < per_gpu && !st; k++) {
                 Slot& s = slots[(size_t)g * per_gpu + k];
                 s.gpu = g;
+                if (device_bam) {
+                    st = exlr_bam_batch_alloc(ctx, chunk_bytes, chunk_blocks, EVS, &s.b);
+                    if (!st) st = exlr_bam_get_views(s.b, &s.bv);
+                    continue;
+                }
                 st = exlr_batch_alloc(ctx, R, OPS, SAB, EVS, &s.b);
                 if (st) break;
                 exlr_batch_get_views(s.b, &s.pk.v);
@@ -241,17 +272,21 @@ int main(int argc, char** argv)
             exlr_result res;
             auto t0 = clk::now();
             const char* dtext = nullptr; uint64_t dbytes = 0;
-            bool host_format = cli.verbose;
+            bool host_format = cli.verbose && !device_bam;
             int st = 0;
+            uint64_t cap_now = 0;
             for (int attempt = 0;; attempt++) {
-                st = cli.verbose ? exlr_wait(s.b, &res) : exlr_wait_text(s.b, &res, &dtext, &dbytes);
-                if (st == EXLR_ERR_TEXT_CAPACITY) { st = exlr_wait(s.b, &res); host_format = true; }   // unusually long lines: format here
-                if (st != EXLR_ERR_CAPACITY || attempt == 4) break;
+                st = host_format ? exlr_wait(s.b, &res) : exlr_wait_text(s.b, &res, &dtext, &dbytes);
+                if (st == EXLR_ERR_TEXT_CAPACITY && !device_bam) { st = exlr_wait(s.b, &res); host_format = true; }   // unusually long lines: format here
+                if ((st != EXLR_ERR_CAPACITY && st != EXLR_ERR_TEXT_CAPACITY) || attempt == 6) break;
                 // an event-dense batch (small -i, many split reads at a large -k): the library says how many events it needs;
-                // the packed records are still in the slot's pinned views, so grow the event buffers and run the batch again
-                const uint64_t need = res.n_events + res.n_events / 8 + 4096;
+                // the records are still in the slot (pinned views, or on the device for a decoded BAM chunk), so grow the event
+                // buffers and run the batch again.  (Lines too long for the text buffer of a BAM chunk: the same, doubled.)
+                uint64_t need = res.n_events + res.n_events / 8 + 4096;
+                if (st == EXLR_ERR_TEXT_CAPACITY) need = std::max<uint64_t>(cap_now * 2, 2 * need);
+                cap_now = need;
                 int g = exlr_batch_grow(s.b, need);
-                if (!g) g = exlr_submit(s.b, s.pk.n);
+                if (!g) { if (device_bam) { exlr_bam_info again; g = exlr_bam_extract(s.b, &again); if (g == EXLR_ERR_BAM_RECORD) g = 0; } else g = exlr_submit(s.b, s.pk.n); }
                 if (g) { st = g; break; }
                 n_regrown++;
             }
@@ -313,6 +348,80 @@ int main(int argc, char** argv)
     const double t_setup = secs(t_begin - t_start);                      // CUDA context + buffers of the first GPU, BAM header
     BamRecordView r;
     uint64_t n_rec = 0;
+    double t_read = 0, t_settle = 0, dev_h2d_ms = 0, dev_inflate_ms = 0, dev_walk_ms = 0; uint64_t u_bytes_total = 0, n_chunks = 0;
+    if (device_bam) {
+        // ---- GPU decoder: chunk k = [blocks of chunk k-1 from its partial last record on] + [new blocks]
+        auto fail = [&](const char* what, int st) { fprintf(stderr, "%s: %s (%s)\n", what, exlr_strerror(st), exlr_last_cuda_error()); std::lock_guard<std::mutex> lk(mu); fatal = 3; cv.notify_all(); };
+        auto hand_over = [&](int si) { { std::lock_guard<std::mutex> lk(mu); inflight.push_back(si); } cv.notify_all(); };
+        // waits for chunk `si`'s record walk and starts its event kernels; false = stop reading (error, or the stream ends here)
+        auto settle = [&](int si) -> bool {
+            Slot& s = slots[si];
+            auto t0 = clk::now();
+            int st = exlr_bam_extract(s.b, &s.info);
+            if (st == EXLR_ERR_BGZF && s.info.bad_block > 0) {
+                // a block that does not inflate: like the reference's reader error, the stream ends there and the records before it stand
+                const uint32_t keep = (uint32_t)s.info.bad_block;
+                st = exlr_bam_submit(s.b, s.comp_bytes, keep);
+                if (!st) st = exlr_bam_walk(s.b, s.walk_start);
+                if (!st) st = exlr_bam_extract(s.b, &s.info);
+                if (st == 0 || st == EXLR_ERR_BAM_RECORD) { s.info.status = EXLR_ERR_BGZF; st = EXLR_ERR_BGZF; }
+            }
+            t_settle += secs(clk::now() - t0);
+            dev_h2d_ms += s.info.h2d_ms; dev_inflate_ms += s.info.inflate_ms; dev_walk_ms += s.info.walk_ms; u_bytes_total += s.info.u_bytes; n_chunks++;
+            if (st != 0 && st != EXLR_ERR_BGZF && st != EXLR_ERR_BAM_RECORD) { fail("exlr_bam_extract", st); return false; }
+            if (st == EXLR_ERR_BGZF && s.info.bad_block <= 0) return false;         // nothing usable in this chunk
+            n_rec += s.info.n_reads;
+            hand_over(si);
+            return st == 0;
+        };
+        std::vector<exlr_bgzf_block> newtab(chunk_blocks);
+        int prev = -1;
+        uint64_t start = bs.first_record_off;
+        while (cur >= 0) {
+            Slot& s = slots[cur];
+            auto t0 = clk::now();
+            size_t new_bytes = 0;
+            const size_t nb = bs.read_blocks(s.bv.comp, (size_t)(s.bv.max_comp_bytes - over_bytes), newtab.data(), chunk_blocks - over_blocks, &new_bytes);
+            t_read += secs(clk::now() - t0);
+            // where does the previous chunk's last, partial record begin?  Its blocks from there on are repeated in front of this chunk
+            uint32_t n_over = 0; size_t total_bytes = new_bytes;
+            bool go_on = true;
+            if (prev >= 0) {
+                Slot& q = slots[prev];
+                go_on = settle(prev);
+                const int was = prev; prev = -1;
+                if (go_on && q.info.tail_off < q.info.u_bytes) {
+                    uint32_t j = (uint32_t)(std::upper_bound(q.u_off.begin(), q.u_off.end(), q.info.tail_off) - q.u_off.begin()) - 1u;
+                    n_over = q.n_blocks - j;
+                    start = q.info.tail_off - q.u_off[j];
+                    uint64_t need = 0;
+                    for (uint32_t k = j; k < q.n_blocks; k++) need += q.bv.blocks[k].comp_len;
+                    if (n_over > over_blocks || need > over_bytes) { fprintf(stderr, "a record spans more than %u BGZF blocks: raise --chunk-mb / --chunk-blocks\n", over_blocks); std::lock_guard<std::mutex> lk(mu); fatal = 3; cv.notify_all(); break; }
+                    for (uint32_t k = j; k < q.n_blocks; k++) {
+                        const exlr_bgzf_block& e = q.bv.blocks[k];
+                        memcpy(s.bv.comp + total_bytes, q.bv.comp + e.comp_off, e.comp_len);
+                        s.bv.blocks[k - j] = exlr_bgzf_block{(uint32_t)total_bytes, e.comp_len, e.ulen, 0};
+                        total_bytes += e.comp_len;
+                    }
+                } else start = 0;
+                (void)was;
+            }
+            if (!go_on || nb == 0) {                        // error / end of the stream (a partial record left at the very end is a truncated file: dropped)
+                std::lock_guard<std::mutex> lk(mu); gpus[s.gpu].freeq.push_back(cur); cur = -1; break;
+            }
+            memcpy(s.bv.blocks + n_over, newtab.data(), nb * sizeof(exlr_bgzf_block));
+            s.n_blocks = n_over + (uint32_t)nb; s.walk_start = start; s.comp_bytes = total_bytes;
+            s.u_off.assign(s.n_blocks + 1, 0);
+            for (uint32_t k = 0; k < s.n_blocks; k++) s.u_off[k + 1] = s.u_off[k] + s.bv.blocks[k].ulen;
+            int st = exlr_bam_submit(s.b, total_bytes, s.n_blocks);
+            if (!st) st = exlr_bam_walk(s.b, start);
+            if (st) { fail("exlr_bam_submit", st); break; }
+            prev = cur;
+            cur = acquire(++seq);
+        }
+        if (prev >= 0 && !fatal) settle(prev);
+        cur = -1;
+    }
     while (cur >= 0 && rd.next(r)) {
         n_rec++;
         PackedBatch* pk = &slots[cur].pk;
@@ -332,6 +441,11 @@ int main(int argc, char** argv)
     for (auto& g : gpus) if (g.th.joinable()) g.th.join();
     if (out_stdout) fflush(fo); else fclose(fo);
     int n_used = 0; for (auto& g : gpus) n_used += g.state == 2;
+    if (cli.stats && device_bam)
+        fprintf(stderr, "excord-lr-b200 GPU BAM decoder: %llu chunks, %.1f MB of BGZF -> %.1f MB of BAM; reader thread: reading the file into pinned memory %.3f s, "
+                "waiting for a chunk's record walk %.3f s; device: H2D %.1f ms, inflate %.1f ms (%.1f GB/s of BAM out), record walk + gather %.1f ms\n",
+                (unsigned long long)n_chunks, bs.bytes_read / 1e6, u_bytes_total / 1e6, t_read, t_settle, dev_h2d_ms, dev_inflate_ms,
+                dev_inflate_ms > 0 ? u_bytes_total / 1e6 / dev_inflate_ms : 0.0, dev_walk_ms);
     if (cli.stats)
         fprintf(stderr, "excord-lr-b200: %llu records, %llu lines, %llu batches (%llu re-run with larger event buffers) on %d of %d GPU(s); setup (CUDA context, "
                 "pinned + device buffers of the first GPU, BAM header) %.3f s; "

@@ -184,6 +184,9 @@ typedef struct exlr_batch exlr_batch;
 #define EXLR_OPT_DEVICE_FORMAT 8  /* 1 = batches allocated from now on also format the non-verbose output lines on the device
                                      (kernels 5a/5b, utils.rs:225-236, 269-280); read them with exlr_wait_text */
 
+#define EXLR_OPT_VERBOSE_TEXT 11  /* 1 = BAM batches (exlr_bam_batch_alloc) allocated from now on format the -v columns on the device too
+                                     (tag, read name, strand, flag: utils.rs:205-223, 252-267) -- there the read names are on the device */
+
 /* ---- lifecycle ---------------------------------------------------------------------- */
 int  exlr_abi_version(void);
 /* Number of CUDA devices with compute capability 10.x; <0 on CUDA error. */

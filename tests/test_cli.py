@@ -170,3 +170,46 @@ def test_two_gpus_round_robin_same_bytes(tmp_path):
     want_r, want = _expect(hb, ExlrParams.make(max_pct_overlap=0.8), True)
     r = run(["-b", bam, "-o", out, "-p", "0.8", "-v", "--gpus", "2", "--batch-reads", "1000"])
     assert r.returncode == 0 and open(out, "rb").read() == want
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not gpu_available(), reason="needs a B200")
+def test_gpu_bam_decoder_chunks_and_host_reader_agree(tmp_path):
+    # BGZF BAM in a regular file is inflated and walked on the GPU (exlr_bam_*); --host-reader keeps it on zlib threads.
+    # Small chunks make records straddle chunk boundaries (the tail record's blocks are repeated in front of the next chunk).
+    hb = synth.with_qnames(synth.config(0, 1.0))
+    bam, out = str(tmp_path / "c1.bam"), str(tmp_path / "c1.txt")
+    bamio.write_bam(hb, bam, ref_lens=synth.ref_lens(), seq_len=120, block=6000, level=6)
+    for verbose in (False, True):
+        want_r, want = _expect(hb, ExlrParams.make(max_pct_overlap=0.8), verbose)
+        assert want_r.status == 0
+        for extra in (["--chunk-blocks", "9"], ["--chunk-blocks", "64", "--gpus", "1"], ["--chunk-mb", "1"], [], ["--host-reader", "-t", "3"]):
+            r = run(["-b", bam, "-o", out, "-p", "0.8", "--stats"] + (["-v"] if verbose else []) + extra)
+            assert r.returncode == 0, r.stderr
+            assert open(out, "rb").read() == want, extra
+            assert ("GPU BAM decoder" in r.stderr) == ("--host-reader" not in extra)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not gpu_available(), reason="needs a B200")
+def test_gpu_bam_decoder_damaged_files(tmp_path):
+    # truncated file / corrupt block: the reference's reader returns an error and the loop ends quietly with the lines so far
+    # (src/main.rs:165-168); both readers must stop at the same record
+    hb = synth.with_qnames(synth.config(0, 0.5))
+    bam, out = str(tmp_path / "d.bam"), str(tmp_path / "d.txt")
+    bamio.write_bam(hb, bam, ref_lens=synth.ref_lens(), block=8000)
+    data = open(bam, "rb").read()
+    trunc = str(tmp_path / "t.bam")
+    open(trunc, "wb").write(data[: len(data) * 2 // 3])
+    outs = []
+    for extra in (["--host-reader"], ["--chunk-blocks", "16"], []):
+        r = run(["-b", trunc, "-o", out] + extra)
+        assert r.returncode == 0, r.stderr
+        outs.append(open(out, "rb").read())
+    assert len(outs[0]) > 1000 and outs[0] == outs[1] == outs[2]
+    full_r, full = _expect(hb, ExlrParams.make())
+    assert full.startswith(outs[0]) and len(outs[0]) < len(full)
+    # event-dense chunk: the event buffers of a BAM chunk grow too
+    r = run(["-b", bam, "-o", out, "-i", "1", "--batch-events", "64", "--stats"])
+    want_r, want = _expect(hb, ExlrParams.make(indel_min=1))
+    assert r.returncode == 0 and open(out, "rb").read() == want and " (0 re-run" not in r.stderr

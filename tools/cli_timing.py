@@ -30,14 +30,21 @@ with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") els
         bamio.write_bam(hb, bam, ref_lens=synth.ref_lens(), seq_len=seq_len, random_seq=seq_len > 0)
         tw = time.time() - t0
         size = os.path.getsize(bam)
-        best = None
-        for _ in range(3):
-            t0 = time.time()
-            r = subprocess.run([exe, "-b", bam, "-o", out, "-p", "0.8", "-t", str(args.threads), "--stats"], capture_output=True, text=True)
-            dt = time.time() - t0
-            assert r.returncode == 0, r.stderr
-            best = dt if best is None or dt < best else best
-            stats = r.stderr.strip().splitlines()[-1]
-        print(f"{name}: {hb.n_reads} records, BAM {size / 1e6:.0f} MB (written in {tw:.0f} s), {args.threads} inflate threads")
-        print(f"  best of 3 wall {best:.3f} s -> {hb.n_reads / best:.3e} alignments/s, {size / best / 1e6:.0f} MB/s of BAM")
-        print(f"  {stats}")
+        print(f"{name}: {hb.n_reads} records, BAM {size / 1e6:.0f} MB (written in {tw:.0f} s)")
+        ref_out = None
+        for mode, extra in (("GPU BAM decoder (default)", []), (f"host reader, {args.threads} zlib threads (--host-reader)", ["--host-reader"])):
+            best, stats = None, []
+            for _ in range(3):
+                t0 = time.time()
+                r = subprocess.run([exe, "-b", bam, "-o", out, "-p", "0.8", "-t", str(args.threads), "--stats"] + extra, capture_output=True, text=True)
+                dt = time.time() - t0
+                assert r.returncode == 0, r.stderr
+                if best is None or dt < best:
+                    best, stats = dt, r.stderr.strip().splitlines()
+            got = open(out, "rb").read()
+            assert ref_out is None or got == ref_out, "the two readers disagree"
+            ref_out = got
+            stream = float(stats[-1].split("stream ")[1].split(" s")[0])
+            print(f"  {mode}: best of 3 wall {best:.3f} s; stream (after setup) {stream:.3f} s -> {hb.n_reads / stream:.3e} alignments/s, {size / stream / 1e9:.2f} GB/s of BAM file")
+            for ln in stats[-2:]:
+                print(f"    {ln}")
