@@ -106,7 +106,8 @@ __device__ __forceinline__ bool build_table(InflWarp& S, const uint8_t* lens, ui
             sym[S.so[l] + rank] = (uint16_t)s;
             if (l <= bits) {
                 const uint32_t rev = __brev(c) >> (32u - l);                 // the stream carries Huffman codes most significant bit first
-                for (uint32_t k = rev; k < (1u << bits); k += 1u << l) lut[k] = (uint16_t)((s << 4) | l);
+                const uint16_t ent = (uint16_t)((s << 4) | l | (s < 256u ? 0x2000u : 0u));   // bit 13: a literal (only ever tested in the literal/length table)
+                for (uint32_t k = rev; k < (1u << bits); k += 1u << l) lut[k] = ent;
             }
         }
         __syncwarp();
@@ -120,7 +121,7 @@ __device__ __forceinline__ bool build_table(InflWarp& S, const uint8_t* lens, ui
 __device__ __forceinline__ bool decode_sym(BitReader& br, const uint16_t* lut, uint32_t bits, const uint16_t* sym, const uint16_t* cnt, uint32_t* out)
 {
     const uint32_t e = lut[br.peek(bits)];
-    if (e) { br.drop(e & 15u); *out = e >> 4; return true; }
+    if (e) { br.drop(e & 15u); *out = (e >> 4) & 0x1ffu; return true; }
     uint32_t code = 0, first = 0, index = 0;
     for (uint32_t l = 1; l <= 15; l++) {
         code |= (uint32_t)(br.bb >> (l - 1)) & 1u;
@@ -148,12 +149,12 @@ __global__ void __launch_bounds__(KI_WARPS * 32) kb_inflate(const uint8_t* __res
     const uint32_t ulen = blk.ulen;
     BitReader br; br.init(comp + blk.coff);
     uint32_t o = 0, ps = 0, pend = 0;                                        // output position; pending literals are [ps, o), one per lane
+    const uint32_t oa = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 31u);  // (oa + o) & 31 = the lane that holds output byte o
     bool ok = true;
     // pending literal bytes sit in the lane (address & 31) of their 32-byte window and go out as one 32-byte store
     auto flush = [&]() {
-        const uintptr_t a0 = reinterpret_cast<uintptr_t>(out) + ps;
-        const uintptr_t mine = (a0 & ~(uintptr_t)31) + lane;
-        if (mine >= a0 && mine < reinterpret_cast<uintptr_t>(out) + o) *reinterpret_cast<uint8_t*>(mine) = (uint8_t)pend;
+        const uint32_t w0 = (oa + ps) & ~31u, mine = w0 + lane;             // window and my byte, counted from out - oa
+        if (mine >= oa + ps && mine < oa + o && o <= ulen) (out - oa)[mine] = (uint8_t)pend;
         ps = o;
     };
     for (bool last = false; ok && !last;) {
@@ -219,13 +220,22 @@ __global__ void __launch_bounds__(KI_WARPS * 32) kb_inflate(const uint8_t* __res
         __syncwarp();
         for (;;) {                                                           // the symbols of this deflate block
             br.refill();
+            {   // literals, the common case, straight from the table: one look-up, the byte parks in its lane
+                const uint32_t e = S.ll[br.peek(KI_LL_BITS)];
+                if (e & 0x2000u) {
+                    br.drop(e & 15u);
+                    if (lane == ((oa + o) & 31u)) pend = e >> 4;
+                    o++;
+                    if (((oa + o) & 31u) == 0u) { if (o > ulen) { ok = false; break; } flush(); }
+                    continue;
+                }
+            }
             uint32_t sym;
             if (!decode_sym(br, S.ll, KI_LL_BITS, S.ll_sym, S.ll_cnt, &sym)) { ok = false; break; }
-            if (sym < 256u) {                                                // literal
-                if (o >= ulen) { ok = false; break; }
-                if (lane == (uint32_t)((reinterpret_cast<uintptr_t>(out) + o) & 31)) pend = sym;
+            if (sym < 256u) {                                                // literal with a code longer than the table
+                if (lane == ((oa + o) & 31u)) pend = sym;
                 o++;
-                if (((reinterpret_cast<uintptr_t>(out) + o) & 31) == 0) flush();
+                if (((oa + o) & 31u) == 0u) { if (o > ulen) { ok = false; break; } flush(); }
                 continue;
             }
             if (sym == 256u) break;                                          // end of block
@@ -253,7 +263,7 @@ __global__ void __launch_bounds__(KI_WARPS * 32) kb_inflate(const uint8_t* __res
             o += len; ps = o;
         }
     }
-    flush();
+    flush();                                                                 // (stores nothing once o is past ulen)
     if (!ok || o != ulen) { if (lane == 0) atomicMax(&ctrl->bad_block, ~b); }
 }
 

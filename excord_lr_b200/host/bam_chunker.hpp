@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/exlr.h"
@@ -24,6 +25,7 @@ public:
     std::string error;
     uint64_t first_record_off = 0;     // uncompressed offset of the first record inside the first block read_blocks() returns
     uint64_t bytes_read = 0;
+    int threads = 8;                   // parallel pread()s per chunk: one thread copies page cache -> pinned memory at a few GB/s only
 
     ~BgzfBamStream() { if (fd_ >= 0) close(fd_); }
 
@@ -86,17 +88,16 @@ public:
     size_t read_blocks(uint8_t* dst, size_t cap_bytes, exlr_bgzf_block* tab, size_t cap_blocks, size_t* bytes_out)
     {
         size_t have = 0, nb = 0, scanned = 0;
-        // what open() left in its buffer goes first
-        if (at_ < buf_.size()) {
-            have = std::min(buf_.size() - at_, cap_bytes);
-            memcpy(dst, buf_.data() + at_, have);
-            at_ += have;
-            if (at_ == buf_.size()) { buf_.clear(); buf_.shrink_to_fit(); at_ = 0; }
+        if (carry_.size()) {                        // what the previous call read but could not return (a partial block, or blocks beyond its block capacity)
+            if (carry_.size() > cap_bytes) { error = "chunk buffer too small"; *bytes_out = 0; return 0; }
+            memcpy(dst, carry_.data(), carry_.size());
+            have = carry_.size(); carry_.clear();
         }
-        if (carry_.size()) {                        // the partial block the previous call could not return
-            if (carry_.size() > cap_bytes - have) { error = "chunk buffer too small"; *bytes_out = 0; return 0; }
-            memmove(dst + carry_.size(), dst, have); memcpy(dst, carry_.data(), carry_.size());
-            have += carry_.size(); carry_.clear();
+        if (at_ < buf_.size()) {                    // then what open() left in its buffer
+            const size_t k = std::min(buf_.size() - at_, cap_bytes - have);
+            memcpy(dst + have, buf_.data() + at_, k);
+            at_ += k; have += k;
+            if (at_ == buf_.size()) { buf_.clear(); buf_.shrink_to_fit(); at_ = 0; }
         }
         for (;;) {
             // hop over the complete blocks that are here
@@ -108,12 +109,11 @@ public:
                 tab[nb++] = exlr_bgzf_block{(uint32_t)(scanned + off), clen, ulen, 0};
                 scanned += total;
             }
-            if (eof_ || nb == cap_blocks || have == cap_bytes) break;
-            // read on, straight into the caller's (pinned) buffer
-            const size_t want = std::min<size_t>(cap_bytes - have, 8u << 20);
-            const ssize_t n = ::read(fd_, dst + have, want);
-            if (n <= 0) { eof_ = true; break; }
-            have += (size_t)n; bytes_read += (size_t)n;
+            if (eof_ || nb == cap_blocks || have == cap_bytes || at_ < buf_.size()) break;
+            // read on, straight into the caller's (pinned) buffer: the rest of its capacity, cut into slices read side by side
+            const size_t n = read_parallel(dst + have, cap_bytes - have);
+            if (n == 0) { eof_ = true; break; }
+            have += n;
         }
         if (have > scanned && !bad_) carry_.assign(dst + scanned, dst + have);     // starts the next chunk (at the end of the file: a truncated block, never completed)
         *bytes_out = scanned;
@@ -125,6 +125,7 @@ private:
     int fd_ = -1;
     std::vector<uint8_t> buf_, carry_;
     size_t at_ = 0;
+    uint64_t fpos_ = 0;
     bool eof_ = false, bad_ = false;
     int stage_ = 0; size_t pos_ = 0, name_len_ = 0; int64_t n_ref_ = 0;
 
@@ -135,10 +136,40 @@ private:
         while (buf_.size() < want && !eof_) {
             const size_t base = buf_.size();
             buf_.resize(base + (1u << 20));
-            const ssize_t n = ::read(fd_, buf_.data() + base, 1u << 20);
+            const ssize_t n = ::pread(fd_, buf_.data() + base, 1u << 20, (off_t)fpos_);
             buf_.resize(base + (n > 0 ? (size_t)n : 0));
-            if (n <= 0) eof_ = true; else bytes_read += (size_t)n;
+            if (n <= 0) eof_ = true; else { bytes_read += (size_t)n; fpos_ += (size_t)n; }
         }
+    }
+
+    // up to `want` bytes from the file position on; short only at the end of the file
+    size_t read_parallel(uint8_t* dst, size_t want)
+    {
+        const size_t kSlice = 4u << 20;
+        const int nt = (int)std::min<size_t>((size_t)std::max(threads, 1), (want + kSlice - 1) / kSlice);
+        std::vector<size_t> got((size_t)std::max(nt, 1), 0);
+        auto work = [&](int t) {
+            const size_t a = want * (size_t)t / (size_t)nt, b = want * (size_t)(t + 1) / (size_t)nt;
+            size_t done = 0;
+            while (a + done < b) {
+                const ssize_t n = ::pread(fd_, dst + a + done, b - a - done, (off_t)(fpos_ + a + done));
+                if (n <= 0) break;
+                done += (size_t)n;
+            }
+            got[(size_t)t] = done;
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+        size_t total = 0;
+        for (int t = 0; t < nt; t++) {                       // contiguous prefix (a short slice means the file ended inside it)
+            const size_t a = want * (size_t)t / (size_t)nt, b = want * (size_t)(t + 1) / (size_t)nt;
+            total += got[(size_t)t];
+            if (got[(size_t)t] < b - a) break;
+        }
+        fpos_ += total; bytes_read += total;
+        return total;
     }
 
     // 1: a complete block at p (offset / length of its DEFLATE data, ISIZE, total size); 0: not all there yet; -1: not BGZF

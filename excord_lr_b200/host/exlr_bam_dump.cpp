@@ -3,8 +3,10 @@
 //   exlr_bam_dump in.bam out.bin [threads]
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
+#include "bam_chunker.hpp"
 #include "bam_reader.hpp"
 
 using namespace exlr_host;
@@ -13,6 +15,26 @@ template <class T> static void put(FILE* f, const std::vector<T>& v) { uint64_t 
 
 int main(int argc, char** argv)
 {
+    if (argc >= 3 && std::string(argv[1]) == "--chunker") {
+        // the host side of the GPU BAM decoder (bam_chunker.hpp): prints what it sees, chunk by chunk
+        //   exlr_bam_dump --chunker in.bam [cap_bytes] [cap_blocks] [threads]
+        BgzfBamStream bs;
+        const size_t cap = argc > 3 ? (size_t)atoll(argv[3]) : (8u << 20), capb = argc > 4 ? (size_t)atoll(argv[4]) : 4096;
+        bs.threads = argc > 5 ? atoi(argv[5]) : 4;
+        if (!bs.open(argv[2])) { printf("not-bgzf-bam %s\n", bs.error.c_str()); return 1; }
+        printf("refs %zu first_record_off %llu\n", bs.ref_names.size(), (unsigned long long)bs.first_record_off);
+        std::vector<uint8_t> buf(cap); std::vector<exlr_bgzf_block> tab(capb);
+        unsigned long long nb_total = 0, u_total = 0, c_total = 0, crc = 0;
+        for (;;) {
+            size_t bytes = 0;
+            const size_t nb = bs.read_blocks(buf.data(), cap, tab.data(), capb, &bytes);
+            if (!nb) break;
+            for (size_t i = 0; i < nb; i++) { u_total += tab[i].ulen; c_total += tab[i].comp_len; for (uint32_t k = 0; k < tab[i].comp_len; k += 97) crc = crc * 131 + buf[tab[i].comp_off + k]; }
+            nb_total += nb;
+        }
+        printf("blocks %llu ulen %llu clen %llu sample %llu\n", nb_total, u_total, c_total, crc);
+        return 0;
+    }
     if (argc < 3) { fputs("usage: exlr_bam_dump in.bam out.bin [threads]\n", stderr); return 2; }
     BamReader rd;
     if (!rd.open(argv[1], argc > 3 ? atoi(argv[3]) : 4)) { fprintf(stderr, "%s\n", rd.error.c_str()); return 1; }

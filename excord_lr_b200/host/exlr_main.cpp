@@ -37,7 +37,7 @@ struct Cli {
     bool stats = false;                 // --stats: stage times on stderr
     unsigned long long batch_reads = 131072, batch_ops = 0, batch_sa = 0, batch_events = 0;
     bool host_reader = false;           // --host-reader: inflate + parse BAM on host threads (zlib) even when the GPU decoder applies
-    unsigned long long chunk_mb = 64, chunk_blocks = 0;   // GPU decoder: compressed bytes / BGZF blocks per chunk
+    unsigned long long chunk_mb = 128, chunk_blocks = 0;   // GPU decoder: compressed bytes / BGZF blocks per chunk
 };
 
 static void usage(FILE* f)
@@ -65,7 +65,7 @@ static void usage(FILE* f)
           "      --batch-reads <N>                    Records per GPU batch [default: 131072]\n"
           "      --batch-events <N>                   Output lines a batch has room for at first [default: 4 x batch-reads + 4096]; grown on demand\n"
           "      --host-reader                        Inflate and parse BAM on host threads (-t) instead of on the GPU\n"
-          "      --chunk-mb <N>                       GPU BAM decoder: compressed megabytes per chunk [default: 64]\n"
+          "      --chunk-mb <N>                       GPU BAM decoder: compressed megabytes per chunk [default: 128]\n"
           "      --chunk-blocks <N>                   GPU BAM decoder: BGZF blocks per chunk [default: by --chunk-mb]\n"
           "      --stats                              Print stage times to stderr\n"
           "  -h, --help                               Print help\n"
@@ -196,6 +196,7 @@ int main(int argc, char** argv)
     // BGZF-compressed BAM in a regular file: the GPU inflates it and walks the records (exlr_bam_*), the host only hops over
     // block headers.  Everything else (SAM text, pipes, --host-reader) goes through the host reader and the packer.
     BgzfBamStream bs;
+    bs.threads = (int)std::min<unsigned long long>(cli.thread, 64);
     const bool device_bam = !cli.host_reader && !in_stream && bs.open(cli.bam);
     if (!device_bam && !bs.error.empty() && !cli.host_reader && !in_stream) { fprintf(stderr, "%s\n", bs.error.c_str()); return 101; }
     BamReader rd;
@@ -215,9 +216,9 @@ int main(int argc, char** argv)
     unsigned long long file_bytes = 0;
     { struct stat st; if (device_bam && stat(cli.bam.c_str(), &st) == 0) file_bytes = (unsigned long long)st.st_size; }
     const unsigned long long chunk_bytes = std::min<unsigned long long>(cli.chunk_mb << 20, file_bytes + 65536) + (1u << 20);
-    const uint32_t chunk_blocks = (uint32_t)(cli.chunk_blocks ? cli.chunk_blocks : std::min<unsigned long long>(30000, std::max<unsigned long long>(chunk_bytes / 12288, 64)));
-    const uint32_t over_blocks = std::max<uint32_t>(chunk_blocks / 4, std::min<uint32_t>(chunk_blocks - 1, 8));
-    const unsigned long long over_bytes = std::min<unsigned long long>((unsigned long long)over_blocks * 65536ull, chunk_bytes / 2);
+    const uint32_t chunk_blocks = (uint32_t)(cli.chunk_blocks ? cli.chunk_blocks : std::min<unsigned long long>(30000, std::max<unsigned long long>(chunk_bytes / 16384, 64)));
+    const uint32_t over_blocks = std::max<uint32_t>(std::min<uint32_t>(chunk_blocks / 4, 256), std::min<uint32_t>(chunk_blocks - 1, 8));
+    const unsigned long long over_bytes = std::min<unsigned long long>((unsigned long long)over_blocks * 65536ull, chunk_bytes / 4);
     const int per_gpu = 3;
     std::vector<Slot> slots((size_t)ndev * per_gpu);
     std::vector<Gpu> gpus(ndev);

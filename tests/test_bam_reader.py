@@ -116,3 +116,38 @@ def test_cg_tag_guards_like_htslib(tmp_path):
     subprocess.check_call([DUMP, bam, out, "1"])
     got = bamio.load_dump(out)
     assert got.cigar.tolist() == [(7 << 4) | 0, (9 << 4) | 2] * 2
+
+
+def test_chunker_sees_every_block(tmp_path):
+    # the host side of the GPU BAM decoder: whatever the chunk geometry, the same blocks in the same order (checked against
+    # the Python header hop of excord_lr_b200.api.bgzf_blocks), and the BAM header parsed with zlib
+    import struct
+    import zlib
+    from excord_lr_b200 import api
+    _build()
+    hb = synth.with_qnames(synth.config(0, 0.3))
+    bam = str(tmp_path / "k.bam")
+    bamio.write_bam(hb, bam, ref_lens=synth.ref_lens(), seq_len=40, block=3000)
+    data = open(bam, "rb").read()
+    blocks, used = api.bgzf_blocks(data)
+    assert used == len(data)
+    u = b"".join(zlib.decompress(data[co:co + cl], -15) for co, cl, _ in blocks[:40])
+    l_text, = struct.unpack_from("<i", u, 4)
+    o = 12 + l_text
+    for _ in range(len(hb.ref_names)):
+        o += 8 + struct.unpack_from("<i", u, o)[0]
+    uoff = np.concatenate([[0], np.cumsum([b[2] for b in blocks])])
+    first = int(np.searchsorted(uoff, o, side="right") - 1)
+    outs = set()
+    for cap, capb, th in ((8 << 20, 4096, 4), (70000, 4096, 1), (1 << 20, 7, 3), (200000, 2, 2)):
+        r = subprocess.run([DUMP, "--chunker", bam, str(cap), str(capb), str(th)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        l1, l2 = r.stdout.strip().splitlines()
+        assert l1 == f"refs {len(hb.ref_names)} first_record_off {o - uoff[first]}"
+        outs.add(l2)
+    want_blocks = blocks[first:]
+    assert len(outs) == 1
+    assert outs.pop().startswith(f"blocks {len(want_blocks)} ulen {sum(b[2] for b in want_blocks)} clen {sum(b[1] for b in want_blocks)} ")
+    sam = str(tmp_path / "k.sam")
+    bamio.write_sam(hb, sam)
+    assert subprocess.run([DUMP, "--chunker", sam], capture_output=True, text=True).returncode == 1
