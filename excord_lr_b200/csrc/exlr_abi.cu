@@ -84,7 +84,8 @@ struct exlr_batch {
     // ---- BAM input decoded on the device (exlr_bam_*): compressed chunk + block table in pinned memory, the rest on the device
     bool is_bam = false;
     uint8_t* h_comp = nullptr; exlr_bgzf_block* h_blocks = nullptr; BgzfBlock* h_btab = nullptr; BamCtrl* h_bctrl = nullptr;
-    void* d_bam = nullptr; DevBam db{};
+    void* d_bam = nullptr; DevBam db{}; BgzfBlock* d_btab = nullptr;
+    uint64_t max_front_bytes = 0, front_u = 0, bam_u_end = 0, bam_origin = 0; uint32_t max_front_blocks = 0, bam_n_new = 0, bam_n_front = 0;
     size_t bam_zero_bytes = 0;                 // BamCtrl + the three scan status arrays (one memset per submit)
     uint64_t max_comp = 0, u_cap = 0; uint32_t max_blocks = 0;
     int bam_state = 0;                         // 0 idle, 1 exlr_bam_submit done, 2 exlr_bam_walk done, 3 exlr_bam_extract done
@@ -319,6 +320,7 @@ static int batch_alloc_impl(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, u
     b->h_ctrl = (Ctrl*)((char*)b->h_out + o_ctrl); b->h_line_off = (uint32_t*)((char*)b->h_out + o_loff);
     e = cudaHostGetDevicePointer((void**)&b->h_ctrl_dev, b->h_ctrl, 0);
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostGetDevicePointer"); }
+    b->dv.host_ctrl = b->h_ctrl_dev;
     b->device_format = c->device_format != 0; b->verbose_text = verbose_text;
     // ---- device slab
     const uint32_t tiles = scan_tiles((uint32_t)R);
@@ -511,7 +513,6 @@ static int run_kernels(exlr_batch* b, bool prefetch_results)
     d.qnames = b->is_bam ? b->db.qnames : nullptr; d.qname_off = b->is_bam ? b->db.qname_off : nullptr;
     d.verbose = b->is_bam && b->verbose_text ? 1u : 0u;
     if (b->formatted) { launch_k5(d, st); b->launches += 2; }      // (no event in between: 5a is placed while 4b drains)
-    launch_header(d, b->h_ctrl_dev, st); b->launches++;            // the result header, stored straight into pinned host memory
     b->far_ran = c->far_mode;
     CK(cudaEventRecord(b->ev[EV_K4B], st));
     b->d2h_events = 0; b->d2h_text = 0; b->have_line_off = false; b->d2h_bytes = sizeof(Ctrl);
@@ -612,8 +613,7 @@ static int finish(exlr_batch* b, exlr_result* res, bool fetch)
         launch_k4a(b->dv, cx->dparams, true, st);
         launch_k4b(b->dv, cx->dparams, true, st);
         if (b->formatted) launch_k5(b->dv, st);
-        launch_header(b->dv, b->h_ctrl_dev, st);
-        b->far_ran = true; b->launches += b->formatted ? 6 : 4;
+        b->far_ran = true; b->launches += b->formatted ? 5 : 3;
         b->d2h_events = 0; b->d2h_text = 0; b->have_line_off = false;      // what was copied back before is stale
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(st));
@@ -709,11 +709,14 @@ int exlr_get_timing(exlr_batch* b, exlr_timing* t)
 }
 
 // ---- BAM input decoded on the device ---------------------------------------------------------------------------------------
-int exlr_bam_batch_alloc(exlr_ctx* c, uint64_t max_comp_bytes, uint32_t max_blocks, uint64_t max_events, exlr_batch** out)
+int exlr_bam_batch_alloc(exlr_ctx* c, uint64_t max_comp_bytes, uint32_t max_blocks, uint64_t max_front_bytes, uint32_t max_front_blocks,
+                         uint64_t max_events, exlr_batch** out)
 {
-    if (!c || !out || max_comp_bytes == 0 || max_blocks == 0 || max_blocks > 32000u || max_comp_bytes >= 0xfff00000ull) return EXLR_ERR_ARG;
-    // what a chunk of max_blocks BGZF blocks (64 KB of BAM each at most) can hold: every bound is exact, so no chunk overflows its batch
-    const uint64_t u_cap = (uint64_t)max_blocks * 65536ull;
+    if (!c || !out || max_comp_bytes == 0 || max_blocks == 0 || max_blocks > 32000u || max_front_blocks > 8000u ||
+        max_comp_bytes >= 0xf0000000ull || max_front_bytes >= 0x0ff00000ull) return EXLR_ERR_ARG;
+    // what a chunk of that many BGZF blocks (64 KB of BAM each at most) can hold: every bound is exact, so no chunk overflows its batch
+    const uint64_t front_u = (uint64_t)max_front_blocks * 65536ull;
+    const uint64_t u_cap = (uint64_t)max_blocks * 65536ull + front_u;
     const uint64_t R = u_cap / 36 + 1, OPS = u_cap / 4 + 4, SAB = u_cap;
     if (max_events == 0) max_events = R / 8 + 65536;
     const bool fmt = c->device_format != 0;
@@ -723,17 +726,19 @@ int exlr_bam_batch_alloc(exlr_ctx* c, uint64_t max_comp_bytes, uint32_t max_bloc
     c->device_format = fmt;
     if (rc) return rc;
     b->is_bam = true; b->max_comp = max_comp_bytes; b->max_blocks = max_blocks; b->u_cap = u_cap;
-    cudaError_t e = cudaHostAlloc((void**)&b->h_comp, max_comp_bytes + 512, cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_blocks, (size_t)max_blocks * sizeof(exlr_bgzf_block), cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_btab, (size_t)max_blocks * sizeof(BgzfBlock), cudaHostAllocDefault);
+    b->max_front_bytes = max_front_bytes; b->max_front_blocks = max_front_blocks; b->front_u = front_u;
+    const size_t tab_n = (size_t)max_front_blocks + max_blocks;
+    cudaError_t e = cudaHostAlloc((void**)&b->h_comp, max_comp_bytes + max_front_bytes + 512, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_blocks, tab_n * sizeof(exlr_bgzf_block), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_btab, tab_n * sizeof(BgzfBlock), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_bctrl, sizeof(BamCtrl), cudaHostAllocMapped);
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostAlloc(BAM chunk)"); }
     memset(b->h_bctrl, 0, sizeof(BamCtrl));
     const uint32_t tiles = bam_scan_tiles((uint32_t)R);
     size_t dof = 0;
     auto dcarve = [&](size_t bytes) { size_t at = dof; dof = align_up(dof + bytes, 256); return at; };
-    const size_t d_ctrl = dcarve(sizeof(BamCtrl) + (size_t)tiles * 24), d_comp = dcarve(max_comp_bytes + 1024), d_tab = dcarve((size_t)max_blocks * sizeof(BgzfBlock)),
-                 d_u = dcarve(u_cap + 256), d_blk = dcarve((size_t)max_blocks * 4 * 6), d_rec = dcarve(R * 4), d_per = dcarve(R * 4 * 5),
+    const size_t d_ctrl = dcarve(sizeof(BamCtrl) + (size_t)tiles * 24), d_comp = dcarve(max_comp_bytes + max_front_bytes + 1024), d_tab = dcarve(tab_n * sizeof(BgzfBlock)),
+                 d_u = dcarve(u_cap + 256), d_blk = dcarve(tab_n * 4 * 6), d_rec = dcarve(R * 4), d_per = dcarve(R * 4 * 5),
                  d_qoff = dcarve((R + 1) * 4), d_qn = dcarve(u_cap + 16);
     e = cudaMalloc(&b->d_bam, dof);
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaMalloc(BAM chunk)"); }
@@ -742,10 +747,10 @@ int exlr_bam_batch_alloc(exlr_ctx* c, uint64_t max_comp_bytes, uint32_t max_bloc
     D.ctrl = (BamCtrl*)(ds + d_ctrl);
     D.scan_x = (unsigned long long*)(ds + d_ctrl + sizeof(BamCtrl)); D.scan_y = D.scan_x + tiles; D.scan_z = D.scan_y + tiles;
     b->bam_zero_bytes = sizeof(BamCtrl) + (size_t)tiles * 24;
-    D.comp = (const uint8_t*)(ds + d_comp); D.blocks = (const BgzfBlock*)(ds + d_tab); D.U = (uint8_t*)(ds + d_u);
+    D.comp = (const uint8_t*)(ds + d_comp); b->d_btab = (BgzfBlock*)(ds + d_tab); D.U = (uint8_t*)(ds + d_u);
     uint32_t* pb = (uint32_t*)(ds + d_blk);
-    D.spec = pb; D.cnt = pb + max_blocks; D.exitp = pb + 2 * (size_t)max_blocks; D.kind = pb + 3 * (size_t)max_blocks;
-    D.blk_start = pb + 4 * (size_t)max_blocks; D.blk_base = pb + 5 * (size_t)max_blocks;
+    D.spec = pb; D.cnt = pb + tab_n; D.exitp = pb + 2 * tab_n; D.kind = pb + 3 * tab_n;
+    D.blk_start = pb + 4 * tab_n; D.blk_base = pb + 5 * tab_n;
     D.rec_start = (uint32_t*)(ds + d_rec);
     uint32_t* pr = (uint32_t*)(ds + d_per);
     D.ncig = pr; D.salen = pr + R; D.qlen = pr + 2 * R; D.cig_src = pr + 3 * R; D.sa_src = pr + 4 * R;
@@ -762,31 +767,38 @@ int exlr_bam_batch_alloc(exlr_ctx* c, uint64_t max_comp_bytes, uint32_t max_bloc
 int exlr_bam_get_views(exlr_batch* b, exlr_bam_views* v)
 {
     if (!b || !v || !b->is_bam) return EXLR_ERR_ARG;
-    v->comp = b->h_comp; v->blocks = b->h_blocks; v->max_comp_bytes = b->max_comp; v->max_blocks = b->max_blocks; v->reserved = 0;
+    v->comp = b->h_comp; v->blocks = b->h_blocks; v->max_comp_bytes = b->max_comp; v->max_blocks = b->max_blocks;
+    v->front_comp = b->h_comp + b->max_comp; v->front_blocks = b->h_blocks + b->max_blocks;
+    v->max_front_bytes = b->max_front_bytes; v->max_front_blocks = b->max_front_blocks;
     return EXLR_OK;
 }
 
+// Layout on the device: the chunk's own blocks inflate to U[front_u + ...) and have the table entries [max_front_blocks, ...);
+// the blocks repeated from the previous chunk (known only once that chunk's walk is done) go right in front of both, so the
+// walk sees one ascending table and one contiguous stream -- and the chunk's own blocks can be inflated before that is known.
 int exlr_bam_submit(exlr_batch* b, uint64_t comp_bytes, uint32_t n_blocks)
 {
     if (!b || !b->is_bam) return EXLR_ERR_ARG;
     if (comp_bytes > b->max_comp || n_blocks > b->max_blocks) return EXLR_ERR_CAPACITY;
     CK(cudaSetDevice(b->ctx->device));
-    uint64_t u = 0;
+    uint64_t u = b->front_u;
+    BgzfBlock* tab = b->h_btab + b->max_front_blocks;
     for (uint32_t i = 0; i < n_blocks; i++) {                  // where every block inflates to: the prefix sum of the ISIZEs
         const exlr_bgzf_block& k = b->h_blocks[i];
         if ((uint64_t)k.comp_off + k.comp_len > comp_bytes || k.ulen > 65536u) return EXLR_ERR_BGZF;
-        b->h_btab[i] = BgzfBlock{k.comp_off, k.comp_len, (uint32_t)u, k.ulen};
+        tab[i] = BgzfBlock{k.comp_off, k.comp_len, (uint32_t)u, k.ulen};
         u += k.ulen;
     }
     cudaStream_t st = b->stream;
     DevBam& D = b->db;
-    D.n_blocks = n_blocks; D.u_total = (uint32_t)u; D.start_off = 0;
+    b->bam_n_new = n_blocks; b->bam_u_end = u;
     b->bam_comp_bytes = comp_bytes; b->submitted = false; b->have_timing = false;
     CK(cudaEventRecord(b->ev_bam[0], st));
     CK(cudaMemsetAsync(D.ctrl, 0, b->bam_zero_bytes, st));
     if (comp_bytes) CK(cudaMemcpyAsync((void*)D.comp, b->h_comp, comp_bytes, cudaMemcpyHostToDevice, st));
-    if (n_blocks) CK(cudaMemcpyAsync((void*)D.blocks, b->h_btab, (size_t)n_blocks * sizeof(BgzfBlock), cudaMemcpyHostToDevice, st));
+    if (n_blocks) CK(cudaMemcpyAsync(b->d_btab + b->max_front_blocks, tab, (size_t)n_blocks * sizeof(BgzfBlock), cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(b->ev_bam[1], st));
+    D.blocks = b->d_btab + b->max_front_blocks; D.n_blocks = n_blocks; D.block_index_base = b->max_front_blocks;
     launch_bam_inflate(D, st);
     CK(cudaEventRecord(b->ev_bam[2], st));
     CK(cudaGetLastError());
@@ -794,16 +806,37 @@ int exlr_bam_submit(exlr_batch* b, uint64_t comp_bytes, uint32_t n_blocks)
     return EXLR_OK;
 }
 
-int exlr_bam_walk(exlr_batch* b, uint64_t start_off)
+int exlr_bam_walk(exlr_batch* b, uint64_t front_bytes, uint32_t n_front, uint64_t start_off)
 {
     if (!b || !b->is_bam) return EXLR_ERR_ARG;
     if (b->bam_state != 1) return EXLR_ERR_STATE;
-    if (start_off > b->db.u_total) return EXLR_ERR_ARG;
+    if (front_bytes > b->max_front_bytes || n_front > b->max_front_blocks) return EXLR_ERR_CAPACITY;
     CK(cudaSetDevice(b->ctx->device));
-    b->db.start_off = (uint32_t)start_off;
+    cudaStream_t st = b->stream;
+    DevBam& D = b->db;
+    // the repeated blocks: table entries and stream positions right in front of the chunk's own
+    uint64_t fu = 0;
+    const exlr_bgzf_block* fb = b->h_blocks + b->max_blocks;
+    for (uint32_t i = 0; i < n_front; i++) { if ((uint64_t)fb[i].comp_off + fb[i].comp_len > front_bytes || fb[i].ulen > 65536u) return EXLR_ERR_BGZF; fu += fb[i].ulen; }
+    const uint32_t first = b->max_front_blocks - n_front;
+    uint64_t u = b->front_u - fu;
+    if (start_off > fu + (b->bam_u_end - b->front_u)) return EXLR_ERR_ARG;
+    for (uint32_t i = 0; i < n_front; i++) {
+        b->h_btab[first + i] = BgzfBlock{(uint32_t)(b->max_comp + fb[i].comp_off), fb[i].comp_len, (uint32_t)u, fb[i].ulen};
+        u += fb[i].ulen;
+    }
+    b->bam_n_front = n_front; b->bam_origin = b->front_u - fu;
+    if (n_front) {
+        CK(cudaMemcpyAsync((void*)(D.comp + b->max_comp), b->h_comp + b->max_comp, front_bytes, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->d_btab + first, b->h_btab + first, (size_t)n_front * sizeof(BgzfBlock), cudaMemcpyHostToDevice, st));
+        D.blocks = b->d_btab + first; D.n_blocks = n_front; D.block_index_base = first;
+        launch_bam_inflate(D, st);
+    }
+    D.blocks = b->d_btab + first; D.n_blocks = n_front + b->bam_n_new; D.block_index_base = first;
+    D.u_begin = (uint32_t)b->bam_origin; D.u_total = (uint32_t)b->bam_u_end; D.start_off = (uint32_t)(b->bam_origin + start_off);
     b->dv.hc = HostCfg{b->ctx->sms, 4, b->ctx->k1a_ctas, b->ctx->k1_waves};
-    launch_bam_walk(b->db, b->dv, b->stream);
-    CK(cudaEventRecord(b->ev_bam[3], b->stream));
+    launch_bam_walk(D, b->dv, st);
+    CK(cudaEventRecord(b->ev_bam[3], st));
     CK(cudaGetLastError());
     b->bam_state = 2;
     return EXLR_OK;
@@ -817,15 +850,16 @@ int exlr_bam_extract(exlr_batch* b, exlr_bam_info* info)
     CK(cudaSetDevice(b->ctx->device));
     CK(cudaStreamSynchronize(b->stream));                       // the decode header is in mapped pinned memory now
     const BamCtrl& c = *b->h_bctrl;
-    info->n_blocks = b->db.n_blocks; info->u_bytes = b->db.u_total; info->comp_bytes = b->bam_comp_bytes;
+    info->n_blocks = b->db.n_blocks; info->u_bytes = b->bam_u_end - b->bam_origin; info->comp_bytes = b->bam_comp_bytes;
     info->bad_block = -1;
     CK(cudaEventElapsedTime(&info->h2d_ms, b->ev_bam[0], b->ev_bam[1]));
     CK(cudaEventElapsedTime(&info->inflate_ms, b->ev_bam[1], b->ev_bam[2]));
     CK(cudaEventElapsedTime(&info->walk_ms, b->ev_bam[2], b->ev_bam[3]));
     b->bam_state = 3;
-    if (c.bad_block) { info->bad_block = (int32_t)~c.bad_block; info->status = EXLR_ERR_BGZF; return info->status; }
+    // (block indices and stream offsets as the caller counts them: the repeated blocks first, then the chunk's own)
+    if (c.bad_block) { info->bad_block = (int32_t)(~c.bad_block - (b->max_front_blocks - b->bam_n_front)); info->status = EXLR_ERR_BGZF; return info->status; }
     uint64_t n = c.n_rec;
-    info->tail_off = c.tail_off;
+    info->tail_off = c.tail_off - b->bam_origin;
     if (c.capped) { info->status = EXLR_ERR_CAPACITY; return info->status; }
     if (c.bad_rec) {                                            // records before the corrupt one stand; the stream ends there
         n = (uint32_t)~c.bad_rec; info->status = EXLR_ERR_BAM_RECORD;
@@ -844,7 +878,7 @@ int exlr_bam_extract(exlr_batch* b, exlr_bam_info* info)
     if (n == 0) { memset(b->h_ctrl, 0, sizeof(Ctrl)); b->h_line_off[0] = 0; b->submitted = true; b->formatted = true; return info->status; }
     CK(cudaEventRecord(b->ev[EV_START], b->stream));
     CK(cudaEventRecord(b->ev[EV_H2D], b->stream));
-    b->h2d_bytes = b->bam_comp_bytes + (uint64_t)b->db.n_blocks * sizeof(BgzfBlock);
+    b->h2d_bytes = b->bam_comp_bytes + (uint64_t)b->db.n_blocks * sizeof(BgzfBlock);     // (+ the repeated blocks, a few per chunk)
     const int rc = run_kernels(b, true);
     if (rc) return rc;
     b->submitted = true; b->have_timing = true;

@@ -136,7 +136,7 @@ __device__ __forceinline__ bool decode_sym(BitReader& br, const uint16_t* lut, u
 __constant__ uint8_t kClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 __global__ void __launch_bounds__(KI_WARPS * 32) kb_inflate(const uint8_t* __restrict__ comp, const BgzfBlock* __restrict__ blocks, uint32_t n_blocks,
-                                                             uint8_t* U, BamCtrl* ctrl)
+                                                             uint32_t index_base, uint8_t* U, BamCtrl* ctrl)
 {
     __shared__ InflWarp s_all[KI_WARPS];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(KI_WARPS * 32) kb_inflate(const uint8_t* __res
         }
     }
     flush();                                                                 // (stores nothing once o is past ulen)
-    if (!ok || o != ulen) { if (lane == 0) atomicMax(&ctrl->bad_block, ~b); }
+    if (!ok || o != ulen) { if (lane == 0) atomicMax(&ctrl->bad_block, ~(index_base + b)); }
 }
 
 // ======================================================================================
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(32) kb_header(DevBam B)
 void launch_bam_inflate(const DevBam& B, cudaStream_t st)
 {
     if (!B.n_blocks) return;
-    kb_inflate<<<(B.n_blocks + KI_WARPS - 1) / KI_WARPS, KI_WARPS * 32, 0, st>>>(B.comp, B.blocks, B.n_blocks, B.U, B.ctrl);
+    kb_inflate<<<(B.n_blocks + KI_WARPS - 1) / KI_WARPS, KI_WARPS * 32, 0, st>>>(B.comp, B.blocks, B.n_blocks, B.block_index_base, B.U, B.ctrl);
 }
 
 void launch_bam_walk(const DevBam& B, const DevBatch& D, cudaStream_t st)
@@ -529,7 +529,7 @@ void launch_bam_walk(const DevBam& B, const DevBatch& D, cudaStream_t st)
     kb_emit<<<(nb + 127) / 128, 128, 0, st>>>(B);
     // the record count lives on the device: the grids cover what the chunk can hold at most, capped at a few resident waves
     const uint32_t cap = (uint32_t)D.hc.sms * 8u;
-    const uint32_t bound = min(B.max_reads, B.u_total / 36u + 1u);
+    const uint32_t bound = min(B.max_reads, (B.u_total - B.u_begin) / 36u + 1u);
     kb_fields<<<(bound + 255) / 256, 256, 0, st>>>(B, D);
     kb_offsets<<<(bound + SCAN_TILE - 1) / SCAN_TILE, SCAN_THREADS, 0, st>>>(B, D);
     kb_copy<<<min((bound + 7u) / 8u, cap * 4u), 256, 0, st>>>(B, D);

@@ -40,7 +40,8 @@ struct Ctrl {
     uint32_t n_far;                 // records whose >2-event merge loop (main.rs:636-742) changed the event list (length of far_list)
     uint32_t err_lines;             // lines the failing record had written before it panicked (result header, set by the last kernel)
     uint32_t need_far;              // kernel 4a<false> met a record for the literal merge loop: the host re-runs kernels 4a<true>.. (exlr_abi.cu)
-    uint32_t pad[11];
+    uint32_t ticket_d;              // CTAs of the step's last kernel that are done: the last one stores the result header
+    uint32_t pad[10];
 };
 static_assert(sizeof(Ctrl) == 128, "Ctrl is the 128-byte result header");
 
@@ -125,6 +126,7 @@ struct DevBatch {
     unsigned long long* scan_a; unsigned long long* scan_b;   // chained-scan tile status
     unsigned long long* scan_c;                                // ... of kernel 5a (one word per 256 events)
     Ctrl* ctrl;
+    Ctrl* host_ctrl;        // the result header in mapped pinned host memory: stored by the last CTA of the step's last kernel
     // outputs
     uint32_t* line_off;     // [R+1]
     exlr_event* events;     // [max_events]
@@ -162,8 +164,8 @@ struct BamCtrl {                   // device-side control block of the BAM stage
 static_assert(sizeof(BamCtrl) == 64, "BamCtrl");
 
 struct DevBam {
-    const uint8_t* comp; const BgzfBlock* blocks; uint32_t n_blocks;
-    uint8_t* U; uint32_t u_total, start_off; int32_t n_ref;
+    const uint8_t* comp; const BgzfBlock* blocks; uint32_t n_blocks, block_index_base;   // (index of blocks[0] in the batch's table: error reports)
+    uint8_t* U; uint32_t u_begin, u_total, start_off; int32_t n_ref;    // the stream is U[u_begin, u_total); the walk starts at start_off
     uint32_t *spec, *cnt, *exitp, *kind;            // per block: speculated first record, records owned, where the chain leaves, how it stopped
     uint32_t *blk_start, *blk_base;                 // per block, verified: first record (KI_NONE: none) and index of its first record
     uint32_t* rec_start;                            // [max_reads] offset of every record's block_size word
@@ -184,7 +186,6 @@ size_t k1_flat_smem_bytes();
 uint32_t scan_tiles(uint32_t n_reads);
 uint32_t text_scan_tiles(uint32_t max_events);
 void launch_k5(const DevBatch& B, cudaStream_t st);
-void launch_header(const DevBatch& B, Ctrl* host_ctrl_dev, cudaStream_t st);
 void launch_k0(const DevBatch& B, const DevParams& P, cudaStream_t st);
 void plan_k1(DevBatch& B, int variant, uint32_t rpc, uint32_t* tiles_out);
 void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc, cudaStream_t st);

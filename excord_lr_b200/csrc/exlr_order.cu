@@ -303,6 +303,36 @@ __global__ void __launch_bounds__(SCAN_THREADS, FAR ? 4 : 1) k4a_line_scan(DevBa
 
 
 // ======================================================================================
+// result header: the 128-byte control block goes to (mapped, pinned) host memory by eight 16-byte stores -- from the last CTA
+// to finish of whichever kernel ends the step (4b, or 5b when the lines are formatted on the device).  A cudaMemcpyAsync of
+// 128 bytes costs ~9 us of stream time, a kernel of its own ~4; this costs a ticket.  Call with the whole CTA, at its very end.
+// ======================================================================================
+__device__ __forceinline__ void finish_step(const DevBatch& B)
+{
+    __shared__ uint32_t s_last;
+    __syncthreads();                                   // every thread of this CTA has issued its stores
+    if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(&B.ctrl->ticket_d, 1u) == gridDim.x - 1u; }
+    __syncthreads();
+    if (!s_last || threadIdx.x >= 32) return;
+    __threadfence();                                   // ... and the other CTAs' are visible here
+    Ctrl* ctrl = B.ctrl;
+    if (threadIdx.x == 0) {
+        const unsigned long long ek = __ldcg(&ctrl->err_key);
+        if (ek) {
+            // a panic in the indel arm comes after the SA arm's writes of the same record: kernel 4a counted exactly those lines for it
+            const unsigned long long key = ~ek;
+            const uint32_t r = (uint32_t)(key >> 8);
+            ctrl->err_lines = (key & 0xffull) == RANK_MERGE_DOMAIN ? B.line_off[r + 1] - B.line_off[r] : 0u;
+        }
+        ctrl->ticket_d = 0;
+        __threadfence();
+    }
+    __syncwarp();
+    if (threadIdx.x < sizeof(Ctrl) / 16) reinterpret_cast<uint4*>(B.host_ctrl)[threadIdx.x] = __ldcg(reinterpret_cast<const uint4*>(ctrl) + threadIdx.x);
+    __threadfence_system();
+}
+
+// ======================================================================================
 // kernel 4b: ordered compaction into the output event buffer
 // ======================================================================================
 // one raw indel event -> its output line (AlignmentEvent::new, aligments_event.rs:28-57; pair merge main.rs:612-635)
@@ -372,6 +402,7 @@ __global__ void __launch_bounds__(256, FAR ? 6 : 1) k4b_place(DevBatch B, DevPar
         merge_rounds(merge_args(B, P, r, B.k1[r].x), (int)f.y, st, &emit);
     }
     tr.end();
+    if (!B.text_off) finish_step(B);                   // (with device formatting kernel 5b ends the step)
 }
 
 // ======================================================================================
@@ -506,8 +537,8 @@ __global__ void __launch_bounds__(256) k5b_format(DevBatch B)
     CtaTrace tr(B, 13);
     const uint32_t n = min(B.ctrl->n_events, B.max_events), lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
-    if (B.ctrl->text_bytes > B.text_cap) return;        // the host falls back to its own formatter
-    for (uint32_t i0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; i0 < n; i0 += nw * 32u) {
+    const bool fits = B.ctrl->text_bytes <= B.text_cap;  // else the host falls back to its own formatter (or grows the batch)
+    for (uint32_t i0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; fits && i0 < n; i0 += nw * 32u) {
         const uint32_t i = i0 + lane, i1 = min(i0 + 32u, n);
         const uint32_t lo = B.text_off[i0], hi = B.text_off[i1];          // the warp's byte range
         const uint32_t skew = lo & 15u;
@@ -535,24 +566,7 @@ __global__ void __launch_bounds__(256) k5b_format(DevBatch B)
         }
     }
     tr.end();
-}
-
-// ======================================================================================
-// result header: the 128-byte control block goes to (mapped, pinned) host memory by eight 16-byte stores of one warp, placed
-// while the last kernel drains -- a cudaMemcpyAsync of 128 bytes costs ~9 us of stream time, this ~3
-// ======================================================================================
-__global__ void __launch_bounds__(32) k6_header(Ctrl* ctrl, Ctrl* host_ctrl, const uint32_t* line_off)
-{
-    griddep_wait();
-    if (threadIdx.x == 0 && ctrl->err_key) {
-        // a panic in the indel arm comes after the SA arm's writes of the same record: kernel 4a counted exactly those lines for it
-        const unsigned long long key = ~ctrl->err_key;
-        const uint32_t r = (uint32_t)(key >> 8);
-        ctrl->err_lines = (key & 0xffull) == RANK_MERGE_DOMAIN ? line_off[r + 1] - line_off[r] : 0u;
-    }
-    __syncwarp();
-    if (threadIdx.x < sizeof(Ctrl) / 16) reinterpret_cast<uint4*>(host_ctrl)[threadIdx.x] = reinterpret_cast<const uint4*>(ctrl)[threadIdx.x];
-    __threadfence_system();
+    finish_step(B);
 }
 
 // ======================================================================================
@@ -611,7 +625,6 @@ void launch_k4b(const DevBatch& B, const DevParams& P, bool far, cudaStream_t st
     else launch_dependent(k4b_place<false>, grid ? grid : 1u, 256, 0, st, B, P);
 }
 
-void launch_header(const DevBatch& B, Ctrl* host_ctrl_dev, cudaStream_t st) { launch_dependent(k6_header, 1u, 32u, 0, st, B.ctrl, host_ctrl_dev, (const uint32_t*)B.line_off); }
 
 uint32_t scan_tiles(uint32_t n_reads) { return (n_reads + SCAN_TILE - 1) / SCAN_TILE; }
 uint32_t text_scan_tiles(uint32_t max_events) { return (max_events + SCAN_THREADS - 1) / SCAN_THREADS + 1; }

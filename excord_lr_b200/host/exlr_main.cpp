@@ -143,7 +143,7 @@ static bool is_stream(const std::string& p) { struct stat st; return stat(p.c_st
 struct Slot {
     exlr_batch* b = nullptr; PackedBatch pk; int gpu = 0;
     // GPU BAM decoder: the chunk this slot holds
-    exlr_bam_views bv{}; std::vector<uint64_t> u_off; uint32_t n_blocks = 0; uint64_t walk_start = 0, comp_bytes = 0; exlr_bam_info info{};
+    exlr_bam_views bv{}; std::vector<uint64_t> u_off; uint32_t n_blocks = 0, n_front = 0; uint64_t walk_start = 0, comp_bytes = 0, front_bytes = 0; exlr_bam_info info{};
 };
 
 // One GPU of the run: its context and batch slots are created by its own thread, and only once a batch is headed for it
@@ -217,8 +217,8 @@ int main(int argc, char** argv)
     { struct stat st; if (device_bam && stat(cli.bam.c_str(), &st) == 0) file_bytes = (unsigned long long)st.st_size; }
     const unsigned long long chunk_bytes = std::min<unsigned long long>(cli.chunk_mb << 20, file_bytes + 65536) + (1u << 20);
     const uint32_t chunk_blocks = (uint32_t)(cli.chunk_blocks ? cli.chunk_blocks : std::min<unsigned long long>(30000, std::max<unsigned long long>(chunk_bytes / 16384, 64)));
-    const uint32_t over_blocks = std::max<uint32_t>(std::min<uint32_t>(chunk_blocks / 4, 256), std::min<uint32_t>(chunk_blocks - 1, 8));
-    const unsigned long long over_bytes = std::min<unsigned long long>((unsigned long long)over_blocks * 65536ull, chunk_bytes / 4);
+    const uint32_t over_blocks = std::min<uint32_t>(std::max<uint32_t>(chunk_blocks / 4, 16), 512);       // a record of up to ~32 MB
+    const unsigned long long over_bytes = (unsigned long long)over_blocks * 65536ull + 65536ull;
     const int per_gpu = 3;
     std::vector<Slot> slots((size_t)ndev * per_gpu);
     std::vector<Gpu> gpus(ndev);
@@ -241,7 +241,7 @@ int main(int argc, char** argv)
                 Slot& s = slots[(size_t)g * per_gpu + k];
                 s.gpu = g;
                 if (device_bam) {
-                    st = exlr_bam_batch_alloc(ctx, chunk_bytes, chunk_blocks, EVS, &s.b);
+                    st = exlr_bam_batch_alloc(ctx, chunk_bytes, chunk_blocks, over_bytes, over_blocks, EVS, &s.b);
                     if (!st) st = exlr_bam_get_views(s.b, &s.bv);
                     continue;
                 }
@@ -359,64 +359,69 @@ int main(int argc, char** argv)
             Slot& s = slots[si];
             auto t0 = clk::now();
             int st = exlr_bam_extract(s.b, &s.info);
-            if (st == EXLR_ERR_BGZF && s.info.bad_block > 0) {
+            if (st == EXLR_ERR_BGZF && s.info.bad_block > (int32_t)s.n_front) {
                 // a block that does not inflate: like the reference's reader error, the stream ends there and the records before it stand
-                const uint32_t keep = (uint32_t)s.info.bad_block;
+                const uint32_t keep = (uint32_t)s.info.bad_block - s.n_front;
                 st = exlr_bam_submit(s.b, s.comp_bytes, keep);
-                if (!st) st = exlr_bam_walk(s.b, s.walk_start);
+                if (!st) st = exlr_bam_walk(s.b, s.front_bytes, s.n_front, s.walk_start);
                 if (!st) st = exlr_bam_extract(s.b, &s.info);
                 if (st == 0 || st == EXLR_ERR_BAM_RECORD) { s.info.status = EXLR_ERR_BGZF; st = EXLR_ERR_BGZF; }
             }
             t_settle += secs(clk::now() - t0);
             dev_h2d_ms += s.info.h2d_ms; dev_inflate_ms += s.info.inflate_ms; dev_walk_ms += s.info.walk_ms; u_bytes_total += s.info.u_bytes; n_chunks++;
             if (st != 0 && st != EXLR_ERR_BGZF && st != EXLR_ERR_BAM_RECORD) { fail("exlr_bam_extract", st); return false; }
-            if (st == EXLR_ERR_BGZF && s.info.bad_block <= 0) return false;         // nothing usable in this chunk
+            if (st == EXLR_ERR_BGZF && s.info.status != EXLR_ERR_BGZF) return false;
+            if (st == EXLR_ERR_BGZF && s.info.bad_block >= 0) return false;         // (bad_block stays set only when nothing of this chunk is usable)
             n_rec += s.info.n_reads;
             hand_over(si);
             return st == 0;
         };
-        std::vector<exlr_bgzf_block> newtab(chunk_blocks);
         int prev = -1;
         uint64_t start = bs.first_record_off;
         while (cur >= 0) {
             Slot& s = slots[cur];
             auto t0 = clk::now();
             size_t new_bytes = 0;
-            const size_t nb = bs.read_blocks(s.bv.comp, (size_t)(s.bv.max_comp_bytes - over_bytes), newtab.data(), chunk_blocks - over_blocks, &new_bytes);
+            const size_t nb = bs.read_blocks(s.bv.comp, (size_t)s.bv.max_comp_bytes, s.bv.blocks, s.bv.max_blocks, &new_bytes);
             t_read += secs(clk::now() - t0);
+            // the chunk's own blocks go to the device and are inflated right away, beside the previous chunk's
+            if (nb) {
+                const int st = exlr_bam_submit(s.b, new_bytes, (uint32_t)nb);
+                if (st) { fail("exlr_bam_submit", st); break; }
+            }
             // where does the previous chunk's last, partial record begin?  Its blocks from there on are repeated in front of this chunk
-            uint32_t n_over = 0; size_t total_bytes = new_bytes;
+            uint32_t n_over = 0; uint64_t front_bytes = 0;
             bool go_on = true;
             if (prev >= 0) {
                 Slot& q = slots[prev];
                 go_on = settle(prev);
-                const int was = prev; prev = -1;
+                prev = -1;
+                start = 0;
                 if (go_on && q.info.tail_off < q.info.u_bytes) {
-                    uint32_t j = (uint32_t)(std::upper_bound(q.u_off.begin(), q.u_off.end(), q.info.tail_off) - q.u_off.begin()) - 1u;
+                    // (q's stream = its repeated blocks, then its own)
+                    const uint32_t j = (uint32_t)(std::upper_bound(q.u_off.begin(), q.u_off.end(), q.info.tail_off) - q.u_off.begin()) - 1u;
                     n_over = q.n_blocks - j;
                     start = q.info.tail_off - q.u_off[j];
+                    auto blk = [&](uint32_t k) -> const exlr_bgzf_block& { return k < q.n_front ? q.bv.front_blocks[k] : q.bv.blocks[k - q.n_front]; };
                     uint64_t need = 0;
-                    for (uint32_t k = j; k < q.n_blocks; k++) need += q.bv.blocks[k].comp_len;
-                    if (n_over > over_blocks || need > over_bytes) { fprintf(stderr, "a record spans more than %u BGZF blocks: raise --chunk-mb / --chunk-blocks\n", over_blocks); std::lock_guard<std::mutex> lk(mu); fatal = 3; cv.notify_all(); break; }
+                    for (uint32_t k = j; k < q.n_blocks; k++) need += blk(k).comp_len;
+                    if (n_over > s.bv.max_front_blocks || need > s.bv.max_front_bytes) { fprintf(stderr, "a record spans more than %u BGZF blocks: raise --chunk-mb / --chunk-blocks\n", s.bv.max_front_blocks); std::lock_guard<std::mutex> lk(mu); fatal = 3; cv.notify_all(); break; }
                     for (uint32_t k = j; k < q.n_blocks; k++) {
-                        const exlr_bgzf_block& e = q.bv.blocks[k];
-                        memcpy(s.bv.comp + total_bytes, q.bv.comp + e.comp_off, e.comp_len);
-                        s.bv.blocks[k - j] = exlr_bgzf_block{(uint32_t)total_bytes, e.comp_len, e.ulen, 0};
-                        total_bytes += e.comp_len;
+                        const exlr_bgzf_block& e = blk(k);
+                        memcpy(s.bv.front_comp + front_bytes, (k < q.n_front ? q.bv.front_comp : q.bv.comp) + e.comp_off, e.comp_len);
+                        s.bv.front_blocks[k - j] = exlr_bgzf_block{(uint32_t)front_bytes, e.comp_len, e.ulen, 0};
+                        front_bytes += e.comp_len;
                     }
-                } else start = 0;
-                (void)was;
+                }
             }
             if (!go_on || nb == 0) {                        // error / end of the stream (a partial record left at the very end is a truncated file: dropped)
                 std::lock_guard<std::mutex> lk(mu); gpus[s.gpu].freeq.push_back(cur); cur = -1; break;
             }
-            memcpy(s.bv.blocks + n_over, newtab.data(), nb * sizeof(exlr_bgzf_block));
-            s.n_blocks = n_over + (uint32_t)nb; s.walk_start = start; s.comp_bytes = total_bytes;
+            s.n_front = n_over; s.n_blocks = n_over + (uint32_t)nb; s.walk_start = start; s.comp_bytes = new_bytes; s.front_bytes = front_bytes;
             s.u_off.assign(s.n_blocks + 1, 0);
-            for (uint32_t k = 0; k < s.n_blocks; k++) s.u_off[k + 1] = s.u_off[k] + s.bv.blocks[k].ulen;
-            int st = exlr_bam_submit(s.b, total_bytes, s.n_blocks);
-            if (!st) st = exlr_bam_walk(s.b, start);
-            if (st) { fail("exlr_bam_submit", st); break; }
+            for (uint32_t k = 0; k < s.n_blocks; k++) s.u_off[k + 1] = s.u_off[k] + (k < n_over ? s.bv.front_blocks[k] : s.bv.blocks[k - n_over]).ulen;
+            const int st = exlr_bam_walk(s.b, front_bytes, n_over, start);
+            if (st) { fail("exlr_bam_walk", st); break; }
             prev = cur;
             cur = acquire(++seq);
         }

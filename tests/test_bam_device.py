@@ -111,18 +111,25 @@ def test_partial_record_at_the_end_is_the_tail(tmp_path):
     blocks, used = api.bgzf_blocks(data)
     keep = len(blocks) * 2 // 3
     ex = api.Extractor(ExlrParams.make(), hb.ref_names)
-    bb = api.BamBatch(ex, len(data), len(blocks))
+    bb = api.BamBatch(ex, len(data), len(blocks), 0, 1 << 20, 64)
     bb.load(data[:used], blocks[:keep])
     bb.walk(_header_end(data, blocks))
     info = bb.extract()
     assert info.status == 0 and 0 < info.n_reads < hb.n_reads and info.tail_off < info.u_bytes
     n = int(info.n_reads)
     _same(bb.download(hb.ref_names, n, int(info.n_ops), int(info.n_sa_bytes)), hb, n)
-    # the next chunk repeats the blocks from the tail's block on and starts its walk at the tail
-    u_off = np.concatenate([[0], np.cumsum([b[2] for b in blocks])])
+    # the next chunk: its own blocks are inflated at once; the blocks of the previous one from the tail's block on go in front
+    u_off = np.concatenate([[0], np.cumsum([b[2] for b in blocks[:keep]])])
     first = int(np.searchsorted(u_off, info.tail_off, side="right") - 1)
-    bb.load(data[:used], blocks[first:])
-    bb.walk(int(info.tail_off - u_off[first]))
+    rest_blocks = blocks[keep:]
+    base = rest_blocks[0][0]
+    bb.load(data[base:used], [(co - base, cl, ul) for co, cl, ul in rest_blocks])
+    front = blocks[first:keep]
+    fdata, ftab = b"", []
+    for co, cl, ul in front:
+        ftab.append((len(fdata), cl, ul))
+        fdata += data[co:co + cl]
+    bb.walk(int(info.tail_off - u_off[first]), (fdata, ftab))
     info2 = bb.extract()
     assert info2.status == 0 and info2.n_reads == hb.n_reads - n and info2.tail_off == info2.u_bytes
     rest = bb.download(hb.ref_names, int(info2.n_reads), int(info2.n_ops), int(info2.n_sa_bytes))
