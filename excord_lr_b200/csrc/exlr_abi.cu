@@ -50,6 +50,7 @@ struct exlr_ctx {
     std::atomic<int> skip_screen{0};           // auto mode: batches left to run without the screen pass (the last screened one was event-dense);
                                                // written by whoever waits a batch, read by whoever submits the next (two threads in the CLI)
     std::atomic<uint64_t> ev_hint{0}, text_hint{0};   // events / text bytes of the last waited batch: how much exlr_submit copies back speculatively
+    int k3_fold = 1;                           // EXLR_OPT_K3_FOLD: 0 = kernel 3a always runs on its own (A/B measurement)
     bool far_mode = false;                     // merge_min > 2 * indel_min: the >2 merge loop (main.rs:636-742) can change the events, kernels 4a/4b run their FAR variants
 };
 
@@ -255,6 +256,7 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
     case EXLR_OPT_OVERLAP: c->overlap = value != 0; return EXLR_OK;
     case EXLR_OPT_DEVICE_FORMAT: c->device_format = value != 0; return EXLR_OK;
     case EXLR_OPT_VERBOSE_TEXT: c->verbose_text = value != 0; return EXLR_OK;
+    case EXLR_OPT_K3_FOLD: c->k3_fold = value != 0; return EXLR_OK;
     case EXLR_OPT_LONG_RECORDS: if (value < 0 || value > 3) return EXLR_ERR_ARG; c->long_records = (int)value; return EXLR_OK;
     case EXLR_OPT_K1A_CTAS_PER_SM: if (value < 1 || value > 8) return EXLR_ERR_ARG; c->k1a_ctas = (int)value; return EXLR_OK;
     case EXLR_OPT_TRACE: if (value < 0 || value > 7) return EXLR_ERR_ARG; c->trace = (int)value; return EXLR_OK;
@@ -501,9 +503,11 @@ static int run_kernels(exlr_batch* b, bool prefetch_results)
         CK(cudaEventRecord(b->ev_k1_end, s1));
     }
     if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K1], st));
-    launch_k3a(d, c->dparams, (uint32_t)(b->n_reads ? b->n_ops / b->n_reads : 0), st); b->launches++;
+    const uint32_t mean_ops = (uint32_t)(b->n_reads ? b->n_ops / b->n_reads : 0);
+    const bool fold = k3_fold(mean_ops) && c->k3_fold;               // short CIGARs: kernel 3b walks the SA records' own CIGARs itself
+    if (!fold) { launch_k3a(d, c->dparams, mean_ops, st); b->launches++; }
     if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K3A], st));
-    launch_k3b(d, c->dparams, st); b->launches++;
+    launch_k3b(d, c->dparams, fold, st); b->launches++;
     if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K3B], st));
     if (overlap) CK(cudaStreamWaitEvent(st, b->ev_k1_end, 0));
     launch_k4a(d, c->dparams, c->far_mode, st); b->launches++;

@@ -195,7 +195,8 @@ void launch_k1d(const DevBatch& B, const DevParams& P, cudaStream_t st);
 void launch_k1b(const DevBatch& B, const DevParams& P, unsigned long long n_ops, bool use_k1c, cudaStream_t st);
 void launch_k1c(const DevBatch& B, const DevParams& P, cudaStream_t st);
 void launch_k3a(const DevBatch& B, const DevParams& P, uint32_t mean_ops, cudaStream_t st);
-void launch_k3b(const DevBatch& B, const DevParams& P, cudaStream_t st);
+void launch_k3b(const DevBatch& B, const DevParams& P, bool fold, cudaStream_t st);
+bool k3_fold(uint32_t mean_ops);
 void launch_k4a(const DevBatch& B, const DevParams& P, bool far, cudaStream_t st);
 void launch_reset_tail(const DevBatch& B, cudaStream_t st);
 void launch_k4b(const DevBatch& B, const DevParams& P, bool far, cudaStream_t st);

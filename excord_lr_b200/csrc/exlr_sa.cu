@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) k3a_sa_cigar(DevBatch B, DevParams P)
 // ======================================================================================
 static constexpr int K3B_THREADS = 192;                 // the usual tile (64 records, ~140 pieces + 64 own segments) parses in one round
 static constexpr int K3B_TILE = 64;                     // SA records per tile (pieces are then spread over all threads)
-static constexpr int K3B_CTAS = 7;                      // CTAs per SM: 30 KB of shared memory and 48 registers x 192 threads each
+static constexpr int K3B_CTAS = 6;                      // CTAs per SM: 30 KB of shared memory and 48 registers x 192 threads each
 static constexpr uint32_t K3B_STAGE_BYTES = 12 * 1024;
 static constexpr uint32_t K3B_SEMI = 8;                // ';' positions kept per record by phase 1; more -> phase 1b rescans
 static constexpr uint32_t K3B_MAXP = 320;              // segments (records + SA pieces) per tile in the staged layout
@@ -450,19 +450,50 @@ __device__ __forceinline__ void k3b_finish(const DevBatch& B, const DevParams& P
 }
 
 // the record's own alignment as segment 0 (main.rs:299-306)
+__device__ __forceinline__ void seg_from_sums(const DevBatch& B, const DevParams& P, uint32_t r, uint32_t sS, uint32_t sH, int64_t refspan, int64_t ffm, Seg* out)
+{
+    const int32_t tid = B.tid[r];
+    out->chrom_ref = (uint32_t)tid; out->chrom_len = B.ref_off[tid + 1] - B.ref_off[tid];
+    out->start = (int64_t)B.pos[r]; out->end = out->start + refspan; out->key = ffm;
+    out->clip_big = (sS > P.ins_clip_min || sH > P.ins_clip_min) ? 1u : 0u;
+    out->strand_neg = (B.flag[r] & 0x10u) ? 1u : 0u;
+}
+
 __device__ __forceinline__ void k3b_record_seg(const DevBatch& B, const DevParams& P, uint32_t j, uint32_t r, Seg* out)
 {
     const SaSum sum = B.sa_sum[j];
-    const int32_t tid = B.tid[r];
-    out->chrom_ref = (uint32_t)tid; out->chrom_len = B.ref_off[tid + 1] - B.ref_off[tid];
-    out->start = (int64_t)B.pos[r]; out->end = out->start + sum.refspan; out->key = sum.ffm;
-    out->clip_big = (sum.S > P.ins_clip_min || sum.H > P.ins_clip_min) ? 1u : 0u;
-    out->strand_neg = (B.flag[r] & 0x10u) ? 1u : 0u;
+    seg_from_sums(B, P, r, sum.S, sum.H, sum.refspan, sum.ffm, out);
+}
+
+// The same segment straight from the record's CIGAR, walked by one thread (kernel 3a folded into kernel 3b: batches of short
+// CIGARs, where a launch of its own costs more than the walk): per-op-type wrapping sums (main.rs:243-296), reference span
+// D + M + = + X (split_read_event.rs:23-28), first-match offset (utils.rs:12-42).
+__device__ __forceinline__ void k3b_own_seg(const DevBatch& B, const DevParams& P, uint32_t r, Seg* out)
+{
+    const unsigned long long o0 = B.cigar_off[r], o1 = B.cigar_off[r + 1];
+    uint32_t sS = 0, sH = 0, sD = 0, sM = 0, sE = 0, sX = 0, bad = 0;
+    unsigned long long ffm = 0; bool seenM = false;
+    for (unsigned long long o = o0; o < o1; o += 4) {
+        uint32_t vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) vv[u] = o + u < o1 ? __ldg(B.cigar + o + u) : 0xfu;       // 0xf: not an op
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t v = vv[u], op = v & 15u, len = v >> 4;
+            if (o + u < o1 && op > 8u) bad = 1;
+            sM += op == 0u ? len : 0u; sD += op == 2u ? len : 0u; sS += op == 4u ? len : 0u;
+            sH += op == 5u ? len : 0u; sE += op == 7u ? len : 0u; sX += op == 8u ? len : 0u;
+            if (op == 0u) seenM = true;                                                       // utils.rs:28-29 stops at the first M
+            if (!seenM && (op == 4u || op == 1u || op == 8u || op == 7u)) ffm += len;         // S I X =  (utils.rs:33)
+        }
+    }
+    if (bad) report(B.ctrl, r, RANK_CIGAR_OP);
+    seg_from_sums(B, P, r, sS, sH, (int64_t)sD + (int64_t)sM + (int64_t)sE + (int64_t)sX, (int64_t)ffm, out);
 }
 
 // Fallback: one SA record parsed start to finish by one thread (used when a tile's SA bytes or segment count do
 // not fit the staged layout, e.g. -k far above the default).  Must be called by every lane of the warp.
-template <class Bytes>
+template <bool FOLD, class Bytes>
 __device__ __forceinline__ void k3b_record(const DevBatch& B, const DevParams& P, const Bytes& s, uint32_t j, bool active, Seg* local_segs)
 {
     uint32_t r = 0, nseg = 0, err = 0;
@@ -484,7 +515,7 @@ __device__ __forceinline__ void k3b_record(const DevBatch& B, const DevParams& P
             else { B.ctrl->overflow = 1; dropped = true; }
         }
         if (!dropped) {
-            k3b_record_seg(B, P, j, r, &segs[0]);
+            if (FOLD) k3b_own_seg(B, P, r, &segs[0]); else k3b_record_seg(B, P, j, r, &segs[0]);
             nseg = 1;
             if (is_str) {
                 uint32_t pb = b0;
@@ -518,14 +549,19 @@ struct __align__(16) K3bSmem {
     uint32_t rerr[K3B_TILE];
     uint32_t semi[K3B_TILE][K3B_SEMI];                 // positions of the first ';' of every record (phase 1 -> 1b)
     uint32_t wsum[K3B_THREADS / 32];
+    uint32_t rrec[K3B_TILE], rslot[K3B_TILE];          // the tile's records and their first segment slot (FOLD: the piece threads walk their CIGARs)
     uint8_t pread[K3B_MAXP];
+    uint8_t rlong[K3B_TILE];                           // FOLD: the record's CIGAR is long, a whole warp walks it
 };
 
+// FOLD: kernel 3a's work is done here (the host folds it in for batches of short CIGARs): the thread that owns a record's slot
+// in phase 2 walks the record's CIGAR while the other threads parse SA pieces.
+template <bool FOLD>
 __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch B, DevParams P)
 {
     extern __shared__ __align__(16) unsigned char k3b_smem_raw[];
     K3bSmem& S = *reinterpret_cast<K3bSmem*>(k3b_smem_raw);
-    griddep_wait();                                    // kernel 3a's summaries
+    griddep_wait();                                    // kernel 3a's summaries (FOLD: kernel 0's list)
     CtaTrace tr(B, 4);
     const uint32_t n_sa = B.ctrl->n_sa;
     const uint32_t n_tiles = (n_sa + K3B_TILE - 1) / K3B_TILE;
@@ -541,7 +577,7 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
         __syncthreads();                                                      // the previous tile's readers are done
         if (!staged) {
             GlobalBytes s{B.sa_bytes};
-            k3b_record(B, P, s, j, active, local_segs);
+            k3b_record<FOLD>(B, P, s, j, active, local_segs);
             continue;
         }
         for (uint32_t o = a0 + t * 16u; o < span_e; o += K3B_THREADS * 16u)
@@ -574,6 +610,7 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
             }
             slots = dropped ? 0u : 1u + nonempty;
             S.rerr[t] = 0xffffffffu;
+            S.rrec[t] = r; S.rlong[t] = 0;
         }
         uint32_t incl = slots;
 #pragma unroll
@@ -584,12 +621,12 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
 #pragma unroll
         for (int k = 0; k < K3B_THREADS / 32; k++) { const uint32_t x = S.wsum[k]; if ((uint32_t)k < w) sb += x; total += x; }
         if (total > K3B_MAXP) {                                               // block-uniform: too many segments for the staged layout
-            k3b_record(B, P, s, j, active, local_segs);
+            k3b_record<FOLD>(B, P, s, j, active, local_segs);
             continue;
         }
         // phase 1b: piece list
         if (active && !dropped) {
-            S.pb[sb] = 0xffffffffu; S.pread[sb] = (uint8_t)t;                 // slot 0 of the record: its own alignment
+            S.pb[sb] = 0xffffffffu; S.pread[sb] = (uint8_t)t; S.rslot[t] = sb;   // slot 0 of the record: its own alignment
             if (is_str) {
                 uint32_t at = sb + 1, pbeg = b0;
                 auto piece_end = [&](uint32_t i) {
@@ -613,6 +650,11 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
             const uint32_t pbeg = x < total ? S.pb[x] : 0xffffffffu;
             const bool has = pbeg != 0xffffffffu;
             const uint32_t m = __ballot_sync(0xffffffffu, has);
+            if (FOLD && x < total && !has) {                                  // slot 0 of a record: its own alignment, from its CIGAR
+                const uint32_t tr_ = S.pread[x], rr = S.rrec[tr_];
+                if (B.cigar_off[rr + 1] - B.cigar_off[rr] > K3A_LONG) S.rlong[tr_] = 1;
+                else k3b_own_seg(B, P, rr, &S.segs[x]);
+            }
             if (!has) continue;
             const uint32_t pend = S.pe[x];
             if (dev_parse_piece_fast(S.bytes, a0, pbeg, pend, P, &S.segs[x], m)) continue;
@@ -620,6 +662,15 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
             if (err) atomicMin(&S.rerr[S.pread[x]], (x << 8) | err);          // the first failing piece in SA order wins
         }
         __syncthreads();
+        if (FOLD) {                                                           // the odd long CIGAR of a short-CIGAR batch: a warp each
+            for (uint32_t k = w; k < K3B_TILE; k += K3B_THREADS / 32) {
+                if (j0 + k >= j1 || !S.rlong[k]) continue;                    // warp-uniform
+                const uint32_t rr = S.rrec[k];
+                const K3aAcc a = k3a_walk<32>(B, rr, B.cigar_off[rr], B.cigar_off[rr + 1], 0xffffffffu, 0);
+                if (lane == 0) seg_from_sums(B, P, rr, a.S, a.H, (int64_t)a.D + (int64_t)a.M + (int64_t)a.E + (int64_t)a.X, (int64_t)a.ffm, &S.segs[S.rslot[k]]);
+            }
+            __syncthreads();
+        }
         tr.mid();
         // phase 3: one thread per record
         uint32_t nseg = 0;
@@ -627,7 +678,7 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
             uint32_t err = S.rerr[t];
             nseg = slots;
             if (err != 0xffffffffu) { report(B.ctrl, r, err & 0xffu); nseg = 0; }
-            else k3b_record_seg(B, P, j, r, &S.segs[sb]);
+            else if (!FOLD) k3b_record_seg(B, P, j, r, &S.segs[sb]);           // (FOLD: phase 2 left it there)
         }
         k3b_finish(B, P, s, j, active, r, dropped, &S.segs[sb < K3B_MAXP ? sb : 0], nseg);
     }
@@ -637,7 +688,15 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
 // ======================================================================================
 // launchers
 // ======================================================================================
-cudaError_t configure_sa_kernels() { return cudaFuncSetAttribute(k3b_sa_events, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3bSmem)); }
+cudaError_t configure_sa_kernels()
+{
+    cudaError_t e = cudaFuncSetAttribute(k3b_sa_events<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3bSmem));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k3b_sa_events<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3bSmem));
+}
+
+// batches whose CIGARs are short get kernel 3a's work done inside kernel 3b (one launch less on the SA chain)
+bool k3_fold(uint32_t mean_ops) { return mean_ops <= 64u; }
 
 void launch_k3a(const DevBatch& B, const DevParams& P, uint32_t mean_ops, cudaStream_t st)
 {
@@ -656,13 +715,14 @@ void launch_k3a(const DevBatch& B, const DevParams& P, uint32_t mean_ops, cudaSt
     }
 }
 
-void launch_k3b(const DevBatch& B, const DevParams& P, cudaStream_t st)
+void launch_k3b(const DevBatch& B, const DevParams& P, bool fold, cudaStream_t st)
 {
     // tiles of 64 SA records, grid-stride; the SA-record count lives on the device, so the grid is sized from the batch but
     // capped at the CTAs that are resident at once: spare CTAs of an over-sized grid cost a launch slot each just to read the
     // count and leave, and a CTA with a second tile doubles the kernel's span
     const uint32_t gb = min((B.n_reads + K3B_TILE - 1u) / K3B_TILE, (uint32_t)B.hc.sms * K3B_CTAS);
-    launch_dependent(k3b_sa_events, gb ? gb : 1u, K3B_THREADS, sizeof(K3bSmem), st, B, P);
+    if (fold) launch_dependent(k3b_sa_events<true>, gb ? gb : 1u, K3B_THREADS, sizeof(K3bSmem), st, B, P);
+    else launch_dependent(k3b_sa_events<false>, gb ? gb : 1u, K3B_THREADS, sizeof(K3bSmem), st, B, P);
 }
 
 }  // namespace exlr
