@@ -37,7 +37,7 @@ struct Cli {
     bool stats = false;                 // --stats: stage times on stderr
     unsigned long long batch_reads = 131072, batch_ops = 0, batch_sa = 0, batch_events = 0;
     bool host_reader = false;           // --host-reader: inflate + parse BAM on host threads (zlib) even when the GPU decoder applies
-    unsigned long long chunk_mb = 128, chunk_blocks = 0;   // GPU decoder: compressed bytes / BGZF blocks per chunk
+    unsigned long long chunk_mb = 96, chunk_blocks = 0;   // GPU decoder: compressed bytes / BGZF blocks per chunk
 };
 
 static void usage(FILE* f)
@@ -65,7 +65,7 @@ static void usage(FILE* f)
           "      --batch-reads <N>                    Records per GPU batch [default: 131072]\n"
           "      --batch-events <N>                   Output lines a batch has room for at first [default: 4 x batch-reads + 4096]; grown on demand\n"
           "      --host-reader                        Inflate and parse BAM on host threads (-t) instead of on the GPU\n"
-          "      --chunk-mb <N>                       GPU BAM decoder: compressed megabytes per chunk [default: 128]\n"
+          "      --chunk-mb <N>                       GPU BAM decoder: compressed megabytes per chunk [default: 96]\n"
           "      --chunk-blocks <N>                   GPU BAM decoder: BGZF blocks per chunk [default: by --chunk-mb]\n"
           "      --stats                              Print stage times to stderr\n"
           "  -h, --help                               Print help\n"
@@ -143,7 +143,7 @@ static bool is_stream(const std::string& p) { struct stat st; return stat(p.c_st
 struct Slot {
     exlr_batch* b = nullptr; PackedBatch pk; int gpu = 0;
     // GPU BAM decoder: the chunk this slot holds
-    exlr_bam_views bv{}; std::vector<uint64_t> u_off; uint32_t n_blocks = 0, n_front = 0; uint64_t walk_start = 0, comp_bytes = 0, front_bytes = 0; exlr_bam_info info{};
+    exlr_bam_views bv{}; std::vector<uint64_t> u_off; uint32_t n_blocks = 0, n_front = 0, n_new = 0; uint64_t walk_start = 0, comp_bytes = 0, front_bytes = 0; exlr_bam_info info{};
 };
 
 // One GPU of the run: its context and batch slots are created by its own thread, and only once a batch is headed for it
@@ -219,7 +219,7 @@ int main(int argc, char** argv)
     const uint32_t chunk_blocks = (uint32_t)(cli.chunk_blocks ? cli.chunk_blocks : std::min<unsigned long long>(30000, std::max<unsigned long long>(chunk_bytes / 16384, 64)));
     const uint32_t over_blocks = std::min<uint32_t>(std::max<uint32_t>(chunk_blocks / 4, 16), 512);       // a record of up to ~32 MB
     const unsigned long long over_bytes = (unsigned long long)over_blocks * 65536ull + 65536ull;
-    const int per_gpu = 3;
+    const int per_gpu = device_bam ? 4 : 3;
     std::vector<Slot> slots((size_t)ndev * per_gpu);
     std::vector<Gpu> gpus(ndev);
 
@@ -355,8 +355,11 @@ int main(int argc, char** argv)
         auto fail = [&](const char* what, int st) { fprintf(stderr, "%s: %s (%s)\n", what, exlr_strerror(st), exlr_last_cuda_error()); std::lock_guard<std::mutex> lk(mu); fatal = 3; cv.notify_all(); };
         auto hand_over = [&](int si) { { std::lock_guard<std::mutex> lk(mu); inflight.push_back(si); } cv.notify_all(); };
         // waits for chunk `si`'s record walk and starts its event kernels; false = stop reading (error, or the stream ends here)
+        bool settled_ok = false;                            // the last settle() left a usable result in its slot
+        auto release_slot = [&](int si) { std::lock_guard<std::mutex> lk(mu); gpus[slots[si].gpu].freeq.push_back(si); };
         auto settle = [&](int si) -> bool {
             Slot& s = slots[si];
+            settled_ok = false;
             auto t0 = clk::now();
             int st = exlr_bam_extract(s.b, &s.info);
             if (st == EXLR_ERR_BGZF && s.info.bad_block > (int32_t)s.n_front) {
@@ -373,59 +376,87 @@ int main(int argc, char** argv)
             if (st == EXLR_ERR_BGZF && s.info.status != EXLR_ERR_BGZF) return false;
             if (st == EXLR_ERR_BGZF && s.info.bad_block >= 0) return false;         // (bad_block stays set only when nothing of this chunk is usable)
             n_rec += s.info.n_reads;
-            hand_over(si);
+            settled_ok = true;
             return st == 0;
         };
-        int prev = -1;
+        auto hand_over_settled = [&](int si) { if (settled_ok) hand_over(si); else release_slot(si); settled_ok = false; };
+        // The reader runs ahead: it reads and submits (H2D + inflate) chunks as long as slots are free, so that several chunks'
+        // inflate kernels share the GPU (one chunk alone leaves most warp slots empty and DEFLATE is latency-bound per block),
+        // while the chain walk(k) -> settle(k) -> walk(k+1) advances one chunk at a time behind it.
+        std::deque<int> pend;                               // submitted, not yet walked (in order)
+        int walked = -1;                                    // walked, not yet settled
+        std::vector<uint8_t> front_data; std::vector<exlr_bgzf_block> front_tab;    // the previous chunk's blocks from its partial last record on
         uint64_t start = bs.first_record_off;
-        while (cur >= 0) {
-            Slot& s = slots[cur];
-            auto t0 = clk::now();
-            size_t new_bytes = 0;
-            const size_t nb = bs.read_blocks(s.bv.comp, (size_t)s.bv.max_comp_bytes, s.bv.blocks, s.bv.max_blocks, &new_bytes);
-            t_read += secs(clk::now() - t0);
-            // the chunk's own blocks go to the device and are inflated right away, beside the previous chunk's
-            if (nb) {
+        bool input_done = false;
+        auto try_acquire = [&](uint64_t sq) -> int {        // a free slot of the GPU chunk sq goes to, if there is one right now
+            const int g = (int)(sq % (uint64_t)ndev);
+            std::lock_guard<std::mutex> lk(mu);
+            if (sq == 1) for (int k = 1; k < ndev; k++) start_gpu(k);
+            start_gpu(g);
+            if (fatal || gpus[g].freeq.empty()) return -1;
+            const int si = gpus[g].freeq.front(); gpus[g].freeq.pop_front(); return si;
+        };
+        auto release = [&](int si) { std::lock_guard<std::mutex> lk(mu); gpus[slots[si].gpu].freeq.push_back(si); };
+        int have = cur;                                     // the slot acquired above, for chunk 0
+        cur = -1;
+        for (;;) {
+            // 1. run ahead
+            while (!input_done && !fatal) {
+                int si = have;
+                have = -1;
+                if (si < 0) si = (pend.empty() && walked < 0) ? acquire(seq) : try_acquire(seq);
+                if (si < 0) break;
+                Slot& s = slots[si];
+                auto t0 = clk::now();
+                size_t new_bytes = 0;
+                const size_t nb = bs.read_blocks(s.bv.comp, (size_t)s.bv.max_comp_bytes, s.bv.blocks, s.bv.max_blocks, &new_bytes);
+                t_read += secs(clk::now() - t0);
+                if (nb == 0) { input_done = true; release(si); break; }
+                s.comp_bytes = new_bytes; s.n_new = (uint32_t)nb;
                 const int st = exlr_bam_submit(s.b, new_bytes, (uint32_t)nb);
-                if (st) { fail("exlr_bam_submit", st); break; }
+                if (st) { fail("exlr_bam_submit", st); release(si); input_done = true; break; }
+                pend.push_back(si);
+                seq++;
             }
-            // where does the previous chunk's last, partial record begin?  Its blocks from there on are repeated in front of this chunk
-            uint32_t n_over = 0; uint64_t front_bytes = 0;
-            bool go_on = true;
-            if (prev >= 0) {
-                Slot& q = slots[prev];
-                go_on = settle(prev);
-                prev = -1;
-                start = 0;
+            if (fatal) break;
+            // 2. advance the chain by one chunk
+            if (walked >= 0) {
+                Slot& q = slots[walked];
+                const bool go_on = settle(walked);
+                front_data.clear(); front_tab.clear(); start = 0;
                 if (go_on && q.info.tail_off < q.info.u_bytes) {
-                    // (q's stream = its repeated blocks, then its own)
+                    // where its last, partial record begins: the blocks from there on are repeated in front of the next chunk
+                    // (q's stream = its repeated blocks, then its own); copied now, q's buffers go back to the pool
                     const uint32_t j = (uint32_t)(std::upper_bound(q.u_off.begin(), q.u_off.end(), q.info.tail_off) - q.u_off.begin()) - 1u;
-                    n_over = q.n_blocks - j;
                     start = q.info.tail_off - q.u_off[j];
-                    auto blk = [&](uint32_t k) -> const exlr_bgzf_block& { return k < q.n_front ? q.bv.front_blocks[k] : q.bv.blocks[k - q.n_front]; };
-                    uint64_t need = 0;
-                    for (uint32_t k = j; k < q.n_blocks; k++) need += blk(k).comp_len;
-                    if (n_over > s.bv.max_front_blocks || need > s.bv.max_front_bytes) { fprintf(stderr, "a record spans more than %u BGZF blocks: raise --chunk-mb / --chunk-blocks\n", s.bv.max_front_blocks); std::lock_guard<std::mutex> lk(mu); fatal = 3; cv.notify_all(); break; }
                     for (uint32_t k = j; k < q.n_blocks; k++) {
-                        const exlr_bgzf_block& e = blk(k);
-                        memcpy(s.bv.front_comp + front_bytes, (k < q.n_front ? q.bv.front_comp : q.bv.comp) + e.comp_off, e.comp_len);
-                        s.bv.front_blocks[k - j] = exlr_bgzf_block{(uint32_t)front_bytes, e.comp_len, e.ulen, 0};
-                        front_bytes += e.comp_len;
+                        const exlr_bgzf_block& e = k < q.n_front ? q.bv.front_blocks[k] : q.bv.blocks[k - q.n_front];
+                        const uint8_t* src = (k < q.n_front ? q.bv.front_comp : q.bv.comp) + e.comp_off;
+                        front_tab.push_back(exlr_bgzf_block{(uint32_t)front_data.size(), e.comp_len, e.ulen, 0});
+                        front_data.insert(front_data.end(), src, src + e.comp_len);
                     }
                 }
+                hand_over_settled(walked);
+                walked = -1;
+                if (!go_on) { input_done = true; for (int si : pend) release(si); pend.clear(); break; }
             }
-            if (!go_on || nb == 0) {                        // error / end of the stream (a partial record left at the very end is a truncated file: dropped)
-                std::lock_guard<std::mutex> lk(mu); gpus[s.gpu].freeq.push_back(cur); cur = -1; break;
+            if (pend.empty()) { if (input_done) break; else continue; }
+            const int si = pend.front(); pend.pop_front();
+            Slot& s = slots[si];
+            if (front_tab.size() > s.bv.max_front_blocks || front_data.size() > s.bv.max_front_bytes) {
+                fprintf(stderr, "a record spans more than %u BGZF blocks: raise --chunk-mb / --chunk-blocks\n", s.bv.max_front_blocks);
+                std::lock_guard<std::mutex> lk(mu); fatal = 3; cv.notify_all(); break;
             }
-            s.n_front = n_over; s.n_blocks = n_over + (uint32_t)nb; s.walk_start = start; s.comp_bytes = new_bytes; s.front_bytes = front_bytes;
+            if (!front_data.empty()) memcpy(s.bv.front_comp, front_data.data(), front_data.size());
+            if (!front_tab.empty()) memcpy(s.bv.front_blocks, front_tab.data(), front_tab.size() * sizeof(exlr_bgzf_block));
+            s.n_front = (uint32_t)front_tab.size(); s.n_blocks = s.n_front + s.n_new; s.walk_start = start; s.front_bytes = front_data.size();
             s.u_off.assign(s.n_blocks + 1, 0);
-            for (uint32_t k = 0; k < s.n_blocks; k++) s.u_off[k + 1] = s.u_off[k] + (k < n_over ? s.bv.front_blocks[k] : s.bv.blocks[k - n_over]).ulen;
-            const int st = exlr_bam_walk(s.b, front_bytes, n_over, start);
+            for (uint32_t k = 0; k < s.n_blocks; k++) s.u_off[k + 1] = s.u_off[k] + (k < s.n_front ? s.bv.front_blocks[k] : s.bv.blocks[k - s.n_front]).ulen;
+            const int st = exlr_bam_walk(s.b, s.front_bytes, s.n_front, start);
             if (st) { fail("exlr_bam_walk", st); break; }
-            prev = cur;
-            cur = acquire(++seq);
+            walked = si;
         }
-        if (prev >= 0 && !fatal) settle(prev);
+        // (a partial record left at the very end of the input is a truncated file: dropped, like a read error in the reference)
         cur = -1;
     }
     while (cur >= 0 && rd.next(r)) {
