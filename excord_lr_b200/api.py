@@ -86,14 +86,14 @@ class BgzfBlock(C.Structure):
 
 class _BamViews(C.Structure):
     _fields_ = [("comp", C.c_void_p), ("blocks", C.c_void_p), ("max_comp_bytes", C.c_uint64), ("max_blocks", C.c_uint32),
-                ("max_front_blocks", C.c_uint32), ("front_comp", C.c_void_p), ("front_blocks", C.c_void_p), ("max_front_bytes", C.c_uint64)]
+                ("reserved", C.c_uint32), ("max_tail_bytes", C.c_uint64)]
 
 
 class BamInfo(C.Structure):
     _fields_ = [("status", C.c_int32), ("bad_block", C.c_int32), ("n_blocks", C.c_uint32), ("reserved", C.c_uint32),
                 ("n_reads", C.c_uint64), ("n_ops", C.c_uint64), ("n_sa_bytes", C.c_uint64), ("tail_off", C.c_uint64),
                 ("u_bytes", C.c_uint64), ("comp_bytes", C.c_uint64), ("h2d_ms", C.c_float), ("inflate_ms", C.c_float),
-                ("walk_ms", C.c_float), ("reserved2", C.c_float)]
+                ("walk_ms", C.c_float), ("reserved2", C.c_float), ("t_ms", C.c_float * 4)]
 
 
 _lib = None
@@ -128,10 +128,10 @@ def load_library() -> C.CDLL:
     lib.exlr_get_timing.argtypes = [vp, C.POINTER(Timing)]
     lib.exlr_get_counters.argtypes = [vp, C.POINTER(Counters)]
     lib.exlr_get_counters.restype = i32
-    lib.exlr_bam_batch_alloc.argtypes = [vp, u64, C.c_uint32, u64, C.c_uint32, u64, C.POINTER(vp)]
+    lib.exlr_bam_batch_alloc.argtypes = [vp, u64, C.c_uint32, u64, u64, C.POINTER(vp)]
     lib.exlr_bam_get_views.argtypes = [vp, C.POINTER(_BamViews)]
     lib.exlr_bam_submit.argtypes = [vp, u64, C.c_uint32]
-    lib.exlr_bam_walk.argtypes = [vp, u64, C.c_uint32, u64]
+    lib.exlr_bam_walk.argtypes = [vp, vp, u64]
     lib.exlr_bam_extract.argtypes = [vp, C.POINTER(BamInfo)]
     lib.exlr_bam_download.argtypes = [vp, C.POINTER(_Views), vp, u64, vp]
     for f in ("exlr_bam_batch_alloc", "exlr_bam_get_views", "exlr_bam_submit", "exlr_bam_walk", "exlr_bam_extract", "exlr_bam_download"):
@@ -342,20 +342,16 @@ def bgzf_blocks(data: bytes):
 class BamBatch(DeviceBatch):
     """A batch whose records come from BGZF-compressed BAM bytes decoded on the device (exlr_bam_*)."""
 
-    def __init__(self, ex: "Extractor", max_comp_bytes: int, max_blocks: int, max_events: int = 0, max_front_bytes: int = 0,
-                 max_front_blocks: int = 0):
+    def __init__(self, ex: "Extractor", max_comp_bytes: int, max_blocks: int, max_events: int = 0, max_tail_bytes: int = 1 << 20):
         self.ex, self.lib = ex, ex.lib
         h = C.c_void_p()
-        _check(self.lib.exlr_bam_batch_alloc(ex.handle, max_comp_bytes, max_blocks, max_front_bytes, max_front_blocks, max_events, C.byref(h)))
+        _check(self.lib.exlr_bam_batch_alloc(ex.handle, max_comp_bytes, max_blocks, max_tail_bytes, max_events, C.byref(h)))
         self.handle = h
         v = _BamViews()
         _check(self.lib.exlr_bam_get_views(h, C.byref(v)))
         self.max_comp, self.max_blocks = int(v.max_comp_bytes), int(v.max_blocks)
         self.comp = np.frombuffer((C.c_char * self.max_comp).from_address(v.comp), np.uint8)
         self.blocks = (BgzfBlock * self.max_blocks).from_address(v.blocks)
-        self.max_front, self.max_front_blocks = int(v.max_front_bytes), int(v.max_front_blocks)
-        self.front_comp = np.frombuffer((C.c_char * max(1, self.max_front)).from_address(v.front_comp), np.uint8) if self.max_front else None
-        self.front_blocks = (BgzfBlock * max(1, self.max_front_blocks)).from_address(v.front_blocks) if self.max_front_blocks else None
         self.n_reads = 0
 
     def load(self, data: bytes, blocks):
@@ -365,17 +361,10 @@ class BamBatch(DeviceBatch):
             self.blocks[i] = BgzfBlock(co, cl, ul, 0)
         _check(self.lib.exlr_bam_submit(self.handle, len(data), len(blocks)))
 
-    def walk(self, start_off: int, front=None):
-        """Record walk + gather (asynchronous).  front = (bytes, blocks): the DEFLATE data of the previous chunk's blocks from its
-        partial last record on, with their (comp_off, comp_len, ulen) relative to those bytes; start_off then counts from there."""
-        nb, nf = 0, 0
-        if front is not None:
-            data, blocks = front
-            nb, nf = len(data), len(blocks)
-            self.front_comp[:nb] = np.frombuffer(data, np.uint8)
-            for i, (co, cl, ul) in enumerate(blocks):
-                self.front_blocks[i] = BgzfBlock(co, cl, ul, 0)
-        _check(self.lib.exlr_bam_walk(self.handle, nb, nf, start_off))
+    def walk(self, start_off: int = 0, prev: "BamBatch" = None):
+        """Record walk + gather (asynchronous).  prev: the batch of the previous chunk (already extracted): the bytes its walk left
+        over -- its partial last record -- are copied in front of this chunk's on the device; start_off counts from there."""
+        _check(self.lib.exlr_bam_walk(self.handle, prev.handle if prev is not None else None, start_off))
 
     def extract(self) -> BamInfo:
         info = BamInfo()

@@ -51,6 +51,7 @@ struct exlr_ctx {
                                                // written by whoever waits a batch, read by whoever submits the next (two threads in the CLI)
     std::atomic<uint64_t> ev_hint{0}, text_hint{0};   // events / text bytes of the last waited batch: how much exlr_submit copies back speculatively
     int k3_fold = 1;                           // EXLR_OPT_K3_FOLD: 0 = kernel 3a always runs on its own (A/B measurement)
+    cudaEvent_t ev_origin = nullptr;           // recorded at exlr_create: the context's clock for exlr_bam_info.t_ms
     bool far_mode = false;                     // merge_min > 2 * indel_min: the >2 merge loop (main.rs:636-742) can change the events, kernels 4a/4b run their FAR variants
 };
 
@@ -86,7 +87,8 @@ struct exlr_batch {
     bool is_bam = false;
     uint8_t* h_comp = nullptr; exlr_bgzf_block* h_blocks = nullptr; BgzfBlock* h_btab = nullptr; BamCtrl* h_bctrl = nullptr;
     void* d_bam = nullptr; DevBam db{}; BgzfBlock* d_btab = nullptr;
-    uint64_t max_front_bytes = 0, front_u = 0, bam_u_end = 0, bam_origin = 0; uint32_t max_front_blocks = 0, bam_n_new = 0, bam_n_front = 0;
+    uint64_t front_u = 0, bam_u_end = 0, bam_origin = 0, bam_info_tail = 0; uint32_t bam_n_new = 0, bam_n_front = 0;
+    cudaEvent_t ev_tail_read = nullptr; bool tail_reader_pending = false;   // the next chunk's copy of this chunk's tail out of U (exlr_bam_walk)
     size_t bam_zero_bytes = 0;                 // BamCtrl + the three scan status arrays (one memset per submit)
     uint64_t max_comp = 0, u_cap = 0; uint32_t max_blocks = 0;
     int bam_state = 0;                         // 0 idle, 1 exlr_bam_submit done, 2 exlr_bam_walk done, 3 exlr_bam_extract done
@@ -234,6 +236,8 @@ int exlr_create(const exlr_params* p, int device, const char* const* ref_names, 
     if (e == cudaSuccess) e = cudaMalloc(&c->d_ref_off, off.size() * 4);
     if (e == cudaSuccess && !bytes.empty()) e = cudaMemcpy(c->d_ref_bytes, bytes.data(), bytes.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(c->d_ref_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_origin);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_origin, 0);
     if (e != cudaSuccess) { exlr_destroy(c); return cuda_fail(e, "reference name table"); }
     *out = c;
     return EXLR_OK;
@@ -244,6 +248,7 @@ void exlr_destroy(exlr_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaFree(c->d_ref_bytes); cudaFree(c->d_ref_off);
+    if (c->ev_origin) cudaEventDestroy(c->ev_origin);
     delete c;
 }
 
@@ -280,6 +285,7 @@ void exlr_batch_free(exlr_batch* b)
     if (b->stream2) cudaStreamDestroy(b->stream2);
     if (b->stream) cudaStreamDestroy(b->stream);
     for (auto& e : b->ev_bam) if (e) cudaEventDestroy(e);
+    if (b->ev_tail_read) cudaEventDestroy(b->ev_tail_read);
     cudaFree(b->d_bam); cudaFreeHost(b->h_comp); cudaFreeHost(b->h_blocks); cudaFreeHost(b->h_btab); cudaFreeHost(b->h_bctrl);
     cudaFree(b->d_slab); cudaFree(b->d_evslab);
     cudaFreeHost(b->h_slab); cudaFreeHost(b->h_out); cudaFreeHost(b->h_events); cudaFreeHost(b->h_text);
@@ -713,13 +719,12 @@ int exlr_get_timing(exlr_batch* b, exlr_timing* t)
 }
 
 // ---- BAM input decoded on the device ---------------------------------------------------------------------------------------
-int exlr_bam_batch_alloc(exlr_ctx* c, uint64_t max_comp_bytes, uint32_t max_blocks, uint64_t max_front_bytes, uint32_t max_front_blocks,
-                         uint64_t max_events, exlr_batch** out)
+int exlr_bam_batch_alloc(exlr_ctx* c, uint64_t max_comp_bytes, uint32_t max_blocks, uint64_t max_tail_bytes, uint64_t max_events, exlr_batch** out)
 {
-    if (!c || !out || max_comp_bytes == 0 || max_blocks == 0 || max_blocks > 32000u || max_front_blocks > 8000u ||
-        max_comp_bytes >= 0xf0000000ull || max_front_bytes >= 0x0ff00000ull) return EXLR_ERR_ARG;
-    // what a chunk of that many BGZF blocks (64 KB of BAM each at most) can hold: every bound is exact, so no chunk overflows its batch
-    const uint64_t front_u = (uint64_t)max_front_blocks * 65536ull;
+    if (!c || !out || max_comp_bytes == 0 || max_blocks == 0 || max_blocks > 32000u || max_comp_bytes >= 0xf0000000ull || max_tail_bytes >= 0x40000000ull) return EXLR_ERR_ARG;
+    // what a chunk of that many BGZF blocks (64 KB of BAM each at most) plus the previous chunk's tail can hold: every bound is
+    // exact, so no chunk overflows its batch
+    const uint64_t front_u = align_up(max_tail_bytes, 256);
     const uint64_t u_cap = (uint64_t)max_blocks * 65536ull + front_u;
     const uint64_t R = u_cap / 36 + 1, OPS = u_cap / 4 + 4, SAB = u_cap;
     if (max_events == 0) max_events = R / 8 + 65536;
@@ -729,19 +734,18 @@ int exlr_bam_batch_alloc(exlr_ctx* c, uint64_t max_comp_bytes, uint32_t max_bloc
     const int rc = batch_alloc_impl(c, R, OPS, SAB, max_events, false, c->verbose_text != 0, &b);
     c->device_format = fmt;
     if (rc) return rc;
-    b->is_bam = true; b->max_comp = max_comp_bytes; b->max_blocks = max_blocks; b->u_cap = u_cap;
-    b->max_front_bytes = max_front_bytes; b->max_front_blocks = max_front_blocks; b->front_u = front_u;
-    const size_t tab_n = (size_t)max_front_blocks + max_blocks;
-    cudaError_t e = cudaHostAlloc((void**)&b->h_comp, max_comp_bytes + max_front_bytes + 512, cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_blocks, tab_n * sizeof(exlr_bgzf_block), cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_btab, tab_n * sizeof(BgzfBlock), cudaHostAllocDefault);
+    b->is_bam = true; b->max_comp = max_comp_bytes; b->max_blocks = max_blocks; b->u_cap = u_cap; b->front_u = front_u;
+    cudaError_t e = cudaHostAlloc((void**)&b->h_comp, max_comp_bytes + 512, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_blocks, (size_t)max_blocks * sizeof(exlr_bgzf_block), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_btab, ((size_t)max_blocks + 1) * sizeof(BgzfBlock), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_bctrl, sizeof(BamCtrl), cudaHostAllocMapped);
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostAlloc(BAM chunk)"); }
     memset(b->h_bctrl, 0, sizeof(BamCtrl));
     const uint32_t tiles = bam_scan_tiles((uint32_t)R);
+    const size_t tab_n = (size_t)max_blocks + 1;               // entry 0: the previous chunk's tail, as one pseudo block
     size_t dof = 0;
     auto dcarve = [&](size_t bytes) { size_t at = dof; dof = align_up(dof + bytes, 256); return at; };
-    const size_t d_ctrl = dcarve(sizeof(BamCtrl) + (size_t)tiles * 24), d_comp = dcarve(max_comp_bytes + max_front_bytes + 1024), d_tab = dcarve(tab_n * sizeof(BgzfBlock)),
+    const size_t d_ctrl = dcarve(sizeof(BamCtrl) + (size_t)tiles * 24), d_comp = dcarve(max_comp_bytes + 1024), d_tab = dcarve(tab_n * sizeof(BgzfBlock)),
                  d_u = dcarve(u_cap + 256), d_blk = dcarve(tab_n * 4 * 6), d_rec = dcarve(R * 4), d_per = dcarve(R * 4 * 5),
                  d_qoff = dcarve((R + 1) * 4), d_qn = dcarve(u_cap + 16);
     e = cudaMalloc(&b->d_bam, dof);
@@ -762,6 +766,7 @@ int exlr_bam_batch_alloc(exlr_ctx* c, uint64_t max_comp_bytes, uint32_t max_bloc
     D.max_reads = (uint32_t)R; D.n_ref = c->n_ref;
     e = cudaHostGetDevicePointer((void**)&D.host_ctrl, b->h_bctrl, 0);
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&b->ev_bam[i]);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_tail_read, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMemset(D.U, 0, u_cap + 256);
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "BAM chunk setup"); }
     *out = b;
@@ -771,22 +776,21 @@ int exlr_bam_batch_alloc(exlr_ctx* c, uint64_t max_comp_bytes, uint32_t max_bloc
 int exlr_bam_get_views(exlr_batch* b, exlr_bam_views* v)
 {
     if (!b || !v || !b->is_bam) return EXLR_ERR_ARG;
-    v->comp = b->h_comp; v->blocks = b->h_blocks; v->max_comp_bytes = b->max_comp; v->max_blocks = b->max_blocks;
-    v->front_comp = b->h_comp + b->max_comp; v->front_blocks = b->h_blocks + b->max_blocks;
-    v->max_front_bytes = b->max_front_bytes; v->max_front_blocks = b->max_front_blocks;
+    v->comp = b->h_comp; v->blocks = b->h_blocks; v->max_comp_bytes = b->max_comp; v->max_blocks = b->max_blocks; v->reserved = 0;
+    v->max_tail_bytes = b->front_u;
     return EXLR_OK;
 }
 
-// Layout on the device: the chunk's own blocks inflate to U[front_u + ...) and have the table entries [max_front_blocks, ...);
-// the blocks repeated from the previous chunk (known only once that chunk's walk is done) go right in front of both, so the
-// walk sees one ascending table and one contiguous stream -- and the chunk's own blocks can be inflated before that is known.
+// Layout on the device: the chunk's own blocks inflate to U[front_u + ...); the bytes the previous chunk's walk did not consume
+// (its partial last record) are copied right in front of them once that walk is done, device to device -- so a chunk's blocks
+// are inflated before the previous chunk's tail is known, and nothing is inflated twice.
 int exlr_bam_submit(exlr_batch* b, uint64_t comp_bytes, uint32_t n_blocks)
 {
     if (!b || !b->is_bam) return EXLR_ERR_ARG;
     if (comp_bytes > b->max_comp || n_blocks > b->max_blocks) return EXLR_ERR_CAPACITY;
     CK(cudaSetDevice(b->ctx->device));
     uint64_t u = b->front_u;
-    BgzfBlock* tab = b->h_btab + b->max_front_blocks;
+    BgzfBlock* tab = b->h_btab + 1;
     for (uint32_t i = 0; i < n_blocks; i++) {                  // where every block inflates to: the prefix sum of the ISIZEs
         const exlr_bgzf_block& k = b->h_blocks[i];
         if ((uint64_t)k.comp_off + k.comp_len > comp_bytes || k.ulen > 65536u) return EXLR_ERR_BGZF;
@@ -797,12 +801,13 @@ int exlr_bam_submit(exlr_batch* b, uint64_t comp_bytes, uint32_t n_blocks)
     DevBam& D = b->db;
     b->bam_n_new = n_blocks; b->bam_u_end = u;
     b->bam_comp_bytes = comp_bytes; b->submitted = false; b->have_timing = false;
+    if (b->tail_reader_pending) { CK(cudaStreamWaitEvent(st, b->ev_tail_read, 0)); b->tail_reader_pending = false; }   // the next chunk still copies this one's old tail
     CK(cudaEventRecord(b->ev_bam[0], st));
     CK(cudaMemsetAsync(D.ctrl, 0, b->bam_zero_bytes, st));
     if (comp_bytes) CK(cudaMemcpyAsync((void*)D.comp, b->h_comp, comp_bytes, cudaMemcpyHostToDevice, st));
-    if (n_blocks) CK(cudaMemcpyAsync(b->d_btab + b->max_front_blocks, tab, (size_t)n_blocks * sizeof(BgzfBlock), cudaMemcpyHostToDevice, st));
+    if (n_blocks) CK(cudaMemcpyAsync(b->d_btab + 1, tab, (size_t)n_blocks * sizeof(BgzfBlock), cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(b->ev_bam[1], st));
-    D.blocks = b->d_btab + b->max_front_blocks; D.n_blocks = n_blocks; D.block_index_base = b->max_front_blocks;
+    D.blocks = b->d_btab + 1; D.n_blocks = n_blocks; D.block_index_base = 0;
     launch_bam_inflate(D, st);
     CK(cudaEventRecord(b->ev_bam[2], st));
     CK(cudaGetLastError());
@@ -810,33 +815,36 @@ int exlr_bam_submit(exlr_batch* b, uint64_t comp_bytes, uint32_t n_blocks)
     return EXLR_OK;
 }
 
-int exlr_bam_walk(exlr_batch* b, uint64_t front_bytes, uint32_t n_front, uint64_t start_off)
+int exlr_bam_walk(exlr_batch* b, exlr_batch* prev, uint64_t start_off)
 {
-    if (!b || !b->is_bam) return EXLR_ERR_ARG;
-    if (b->bam_state != 1) return EXLR_ERR_STATE;
-    if (front_bytes > b->max_front_bytes || n_front > b->max_front_blocks) return EXLR_ERR_CAPACITY;
+    if (!b || !b->is_bam || (prev && (!prev->is_bam || prev == b))) return EXLR_ERR_ARG;
+    if (b->bam_state != 1 || (prev && prev->bam_state != 3)) return EXLR_ERR_STATE;
     CK(cudaSetDevice(b->ctx->device));
     cudaStream_t st = b->stream;
     DevBam& D = b->db;
-    // the repeated blocks: table entries and stream positions right in front of the chunk's own
-    uint64_t fu = 0;
-    const exlr_bgzf_block* fb = b->h_blocks + b->max_blocks;
-    for (uint32_t i = 0; i < n_front; i++) { if ((uint64_t)fb[i].comp_off + fb[i].comp_len > front_bytes || fb[i].ulen > 65536u) return EXLR_ERR_BGZF; fu += fb[i].ulen; }
-    const uint32_t first = b->max_front_blocks - n_front;
-    uint64_t u = b->front_u - fu;
-    if (start_off > fu + (b->bam_u_end - b->front_u)) return EXLR_ERR_ARG;
-    for (uint32_t i = 0; i < n_front; i++) {
-        b->h_btab[first + i] = BgzfBlock{(uint32_t)(b->max_comp + fb[i].comp_off), fb[i].comp_len, (uint32_t)u, fb[i].ulen};
-        u += fb[i].ulen;
+    // the previous chunk's unconsumed tail goes right in front of this chunk's own bytes (its extract has synchronised its stream)
+    uint64_t tail = 0;
+    if (prev) {
+        const uint64_t p_end = prev->bam_u_end, p_tail = prev->bam_origin + prev->bam_info_tail;
+        tail = p_end > p_tail ? p_end - p_tail : 0;
+        if (tail > b->front_u) return EXLR_ERR_CAPACITY;        // a record larger than max_tail_bytes
+        if (tail) {
+            if (prev->ctx->device == b->ctx->device) CK(cudaMemcpyAsync(D.U + b->front_u - tail, prev->db.U + p_tail, tail, cudaMemcpyDeviceToDevice, st));
+            else CK(cudaMemcpyPeerAsync(D.U + b->front_u - tail, b->ctx->device, prev->db.U + p_tail, prev->ctx->device, tail, st));
+            CK(cudaEventRecord(prev->ev_tail_read, st));
+            prev->tail_reader_pending = true;
+        }
     }
-    b->bam_n_front = n_front; b->bam_origin = b->front_u - fu;
-    if (n_front) {
-        CK(cudaMemcpyAsync((void*)(D.comp + b->max_comp), b->h_comp + b->max_comp, front_bytes, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(b->d_btab + first, b->h_btab + first, (size_t)n_front * sizeof(BgzfBlock), cudaMemcpyHostToDevice, st));
-        D.blocks = b->d_btab + first; D.n_blocks = n_front; D.block_index_base = first;
-        launch_bam_inflate(D, st);
+    if (start_off > tail + (b->bam_u_end - b->front_u)) return EXLR_ERR_ARG;
+    b->bam_origin = b->front_u - tail;
+    // (the tail is entry 0 of the block table: a pseudo block that is already "inflated")
+    const uint32_t first = tail ? 0u : 1u;
+    if (tail) {
+        b->h_btab[0] = BgzfBlock{0u, 0u, (uint32_t)b->bam_origin, (uint32_t)tail};
+        CK(cudaMemcpyAsync(b->d_btab, b->h_btab, sizeof(BgzfBlock), cudaMemcpyHostToDevice, st));
     }
-    D.blocks = b->d_btab + first; D.n_blocks = n_front + b->bam_n_new; D.block_index_base = first;
+    b->bam_n_front = tail ? 1u : 0u;
+    D.blocks = b->d_btab + first; D.n_blocks = b->bam_n_front + b->bam_n_new; D.block_index_base = first;
     D.u_begin = (uint32_t)b->bam_origin; D.u_total = (uint32_t)b->bam_u_end; D.start_off = (uint32_t)(b->bam_origin + start_off);
     b->dv.hc = HostCfg{b->ctx->sms, 4, b->ctx->k1a_ctas, b->ctx->k1_waves};
     launch_bam_walk(D, b->dv, st);
@@ -859,11 +867,12 @@ int exlr_bam_extract(exlr_batch* b, exlr_bam_info* info)
     CK(cudaEventElapsedTime(&info->h2d_ms, b->ev_bam[0], b->ev_bam[1]));
     CK(cudaEventElapsedTime(&info->inflate_ms, b->ev_bam[1], b->ev_bam[2]));
     CK(cudaEventElapsedTime(&info->walk_ms, b->ev_bam[2], b->ev_bam[3]));
+    for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(&info->t_ms[i], b->ctx->ev_origin, b->ev_bam[i]));
     b->bam_state = 3;
-    // (block indices and stream offsets as the caller counts them: the repeated blocks first, then the chunk's own)
-    if (c.bad_block) { info->bad_block = (int32_t)(~c.bad_block - (b->max_front_blocks - b->bam_n_front)); info->status = EXLR_ERR_BGZF; return info->status; }
+    // (stream offsets as the caller counts them: from the first byte of the previous chunk's tail, if any, else of this chunk)
+    if (c.bad_block) { info->bad_block = (int32_t)~c.bad_block; info->status = EXLR_ERR_BGZF; return info->status; }
     uint64_t n = c.n_rec;
-    info->tail_off = c.tail_off - b->bam_origin;
+    info->tail_off = c.tail_off - b->bam_origin; b->bam_info_tail = info->tail_off;
     if (c.capped) { info->status = EXLR_ERR_CAPACITY; return info->status; }
     if (c.bad_rec) {                                            // records before the corrupt one stand; the stream ends there
         n = (uint32_t)~c.bad_rec; info->status = EXLR_ERR_BAM_RECORD;
@@ -882,7 +891,7 @@ int exlr_bam_extract(exlr_batch* b, exlr_bam_info* info)
     if (n == 0) { memset(b->h_ctrl, 0, sizeof(Ctrl)); b->h_line_off[0] = 0; b->submitted = true; b->formatted = true; return info->status; }
     CK(cudaEventRecord(b->ev[EV_START], b->stream));
     CK(cudaEventRecord(b->ev[EV_H2D], b->stream));
-    b->h2d_bytes = b->bam_comp_bytes + (uint64_t)b->db.n_blocks * sizeof(BgzfBlock);     // (+ the repeated blocks, a few per chunk)
+    b->h2d_bytes = b->bam_comp_bytes + (uint64_t)b->db.n_blocks * sizeof(BgzfBlock);
     const int rc = run_kernels(b, true);
     if (rc) return rc;
     b->submitted = true; b->have_timing = true;

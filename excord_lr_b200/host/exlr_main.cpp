@@ -37,7 +37,7 @@ struct Cli {
     bool stats = false;                 // --stats: stage times on stderr
     unsigned long long batch_reads = 131072, batch_ops = 0, batch_sa = 0, batch_events = 0;
     bool host_reader = false;           // --host-reader: inflate + parse BAM on host threads (zlib) even when the GPU decoder applies
-    unsigned long long chunk_mb = 96, chunk_blocks = 0;   // GPU decoder: compressed bytes / BGZF blocks per chunk
+    unsigned long long chunk_mb = 96, chunk_blocks = 0, max_record_mb = 64;   // GPU decoder: compressed bytes / BGZF blocks per chunk
 };
 
 static void usage(FILE* f)
@@ -67,6 +67,7 @@ static void usage(FILE* f)
           "      --host-reader                        Inflate and parse BAM on host threads (-t) instead of on the GPU\n"
           "      --chunk-mb <N>                       GPU BAM decoder: compressed megabytes per chunk [default: 96]\n"
           "      --chunk-blocks <N>                   GPU BAM decoder: BGZF blocks per chunk [default: by --chunk-mb]\n"
+          "      --max-record-mb <N>                  GPU BAM decoder: largest BAM record, in megabytes [default: 64]\n"
           "      --stats                              Print stage times to stderr\n"
           "  -h, --help                               Print help\n"
           "  -V, --version                            Print version\n", f);
@@ -122,6 +123,7 @@ static int parse_cli(int argc, char** argv, Cli& c)
         else if (a == "--host-reader") { if (!flagopt(&c.host_reader)) return 2; }
         else if (a == "--chunk-mb") { NUM(2048); c.chunk_mb = u ? u : 1; }
         else if (a == "--chunk-blocks") { NUM(30000); c.chunk_blocks = u; }
+        else if (a == "--max-record-mb") { NUM(1023); c.max_record_mb = u ? u : 1; }
         else if (a == "--stats") { if (!flagopt(&c.stats)) return 2; }
         else if (a == "-h" || a == "--help") { usage(stdout); return -1; }
         else if (a == "-V" || a == "--version") { puts("excord-LR 0.1.17"); return -1; }
@@ -143,7 +145,7 @@ static bool is_stream(const std::string& p) { struct stat st; return stat(p.c_st
 struct Slot {
     exlr_batch* b = nullptr; PackedBatch pk; int gpu = 0;
     // GPU BAM decoder: the chunk this slot holds
-    exlr_bam_views bv{}; std::vector<uint64_t> u_off; uint32_t n_blocks = 0, n_front = 0, n_new = 0; uint64_t walk_start = 0, comp_bytes = 0, front_bytes = 0; exlr_bam_info info{};
+    exlr_bam_views bv{}; uint32_t n_new = 0; uint64_t walk_start = 0, comp_bytes = 0; exlr_bam_info info{}; int prev_slot = -1;
 };
 
 // One GPU of the run: its context and batch slots are created by its own thread, and only once a batch is headed for it
@@ -217,8 +219,7 @@ int main(int argc, char** argv)
     { struct stat st; if (device_bam && stat(cli.bam.c_str(), &st) == 0) file_bytes = (unsigned long long)st.st_size; }
     const unsigned long long chunk_bytes = std::min<unsigned long long>(cli.chunk_mb << 20, file_bytes + 65536) + (1u << 20);
     const uint32_t chunk_blocks = (uint32_t)(cli.chunk_blocks ? cli.chunk_blocks : std::min<unsigned long long>(30000, std::max<unsigned long long>(chunk_bytes / 16384, 64)));
-    const uint32_t over_blocks = std::min<uint32_t>(std::max<uint32_t>(chunk_blocks / 4, 16), 512);       // a record of up to ~32 MB
-    const unsigned long long over_bytes = (unsigned long long)over_blocks * 65536ull + 65536ull;
+    const unsigned long long tail_bytes = std::min<unsigned long long>(cli.max_record_mb << 20, (unsigned long long)chunk_blocks * 65536ull);   // the largest record a chunk can inherit
     const int per_gpu = device_bam ? 4 : 3;
     std::vector<Slot> slots((size_t)ndev * per_gpu);
     std::vector<Gpu> gpus(ndev);
@@ -241,7 +242,7 @@ int main(int argc, char** argv)
                 Slot& s = slots[(size_t)g * per_gpu + k];
                 s.gpu = g;
                 if (device_bam) {
-                    st = exlr_bam_batch_alloc(ctx, chunk_bytes, chunk_blocks, over_bytes, over_blocks, EVS, &s.b);
+                    st = exlr_bam_batch_alloc(ctx, chunk_bytes, chunk_blocks, tail_bytes, EVS, &s.b);
                     if (!st) st = exlr_bam_get_views(s.b, &s.bv);
                     continue;
                 }
@@ -362,15 +363,16 @@ int main(int argc, char** argv)
             settled_ok = false;
             auto t0 = clk::now();
             int st = exlr_bam_extract(s.b, &s.info);
-            if (st == EXLR_ERR_BGZF && s.info.bad_block > (int32_t)s.n_front) {
+            if (st == EXLR_ERR_BGZF && s.info.bad_block > 0) {
                 // a block that does not inflate: like the reference's reader error, the stream ends there and the records before it stand
-                const uint32_t keep = (uint32_t)s.info.bad_block - s.n_front;
+                const uint32_t keep = (uint32_t)s.info.bad_block;
                 st = exlr_bam_submit(s.b, s.comp_bytes, keep);
-                if (!st) st = exlr_bam_walk(s.b, s.front_bytes, s.n_front, s.walk_start);
+                if (!st) st = exlr_bam_walk(s.b, s.prev_slot >= 0 ? slots[s.prev_slot].b : nullptr, s.walk_start);
                 if (!st) st = exlr_bam_extract(s.b, &s.info);
                 if (st == 0 || st == EXLR_ERR_BAM_RECORD) { s.info.status = EXLR_ERR_BGZF; st = EXLR_ERR_BGZF; }
             }
             t_settle += secs(clk::now() - t0);
+            if (getenv("EXLR_BAM_TRACE")) fprintf(stderr, "chunk %llu gpu %d: start %.2f h2d-done %.2f inflate-done %.2f walk-done %.2f ms; settled at host %.2f ms\n", (unsigned long long)n_chunks, s.gpu, s.info.t_ms[0], s.info.t_ms[1], s.info.t_ms[2], s.info.t_ms[3], secs(clk::now() - t_begin) * 1e3);
             dev_h2d_ms += s.info.h2d_ms; dev_inflate_ms += s.info.inflate_ms; dev_walk_ms += s.info.walk_ms; u_bytes_total += s.info.u_bytes; n_chunks++;
             if (st != 0 && st != EXLR_ERR_BGZF && st != EXLR_ERR_BAM_RECORD) { fail("exlr_bam_extract", st); return false; }
             if (st == EXLR_ERR_BGZF && s.info.status != EXLR_ERR_BGZF) return false;
@@ -385,7 +387,7 @@ int main(int argc, char** argv)
         // while the chain walk(k) -> settle(k) -> walk(k+1) advances one chunk at a time behind it.
         std::deque<int> pend;                               // submitted, not yet walked (in order)
         int walked = -1;                                    // walked, not yet settled
-        std::vector<uint8_t> front_data; std::vector<exlr_bgzf_block> front_tab;    // the previous chunk's blocks from its partial last record on
+        int held = -1;                                      // settled, its leftover not yet handed to the next chunk
         uint64_t start = bs.first_record_off;
         bool input_done = false;
         auto try_acquire = [&](uint64_t sq) -> int {        // a free slot of the GPU chunk sq goes to, if there is one right now
@@ -421,38 +423,21 @@ int main(int argc, char** argv)
             if (fatal) break;
             // 2. advance the chain by one chunk
             if (walked >= 0) {
-                Slot& q = slots[walked];
                 const bool go_on = settle(walked);
-                front_data.clear(); front_tab.clear(); start = 0;
-                if (go_on && q.info.tail_off < q.info.u_bytes) {
-                    // where its last, partial record begins: the blocks from there on are repeated in front of the next chunk
-                    // (q's stream = its repeated blocks, then its own); copied now, q's buffers go back to the pool
-                    const uint32_t j = (uint32_t)(std::upper_bound(q.u_off.begin(), q.u_off.end(), q.info.tail_off) - q.u_off.begin()) - 1u;
-                    start = q.info.tail_off - q.u_off[j];
-                    for (uint32_t k = j; k < q.n_blocks; k++) {
-                        const exlr_bgzf_block& e = k < q.n_front ? q.bv.front_blocks[k] : q.bv.blocks[k - q.n_front];
-                        const uint8_t* src = (k < q.n_front ? q.bv.front_comp : q.bv.comp) + e.comp_off;
-                        front_tab.push_back(exlr_bgzf_block{(uint32_t)front_data.size(), e.comp_len, e.ulen, 0});
-                        front_data.insert(front_data.end(), src, src + e.comp_len);
-                    }
-                }
-                hand_over_settled(walked);
+                start = 0;
+                // its leftover (a partial last record) is copied in front of the next chunk on the device: the slot goes to the
+                // writer only once that copy is in the next chunk's stream (the library orders the slot's reuse behind it)
+                held = walked;
                 walked = -1;
-                if (!go_on) { input_done = true; for (int si : pend) release(si); pend.clear(); break; }
+                if (!go_on) { hand_over_settled(held); held = -1; input_done = true; for (int si : pend) release(si); pend.clear(); break; }
             }
-            if (pend.empty()) { if (input_done) break; else continue; }
+            if (pend.empty()) { if (input_done) { if (held >= 0) hand_over_settled(held); held = -1; break; } else continue; }
             const int si = pend.front(); pend.pop_front();
             Slot& s = slots[si];
-            if (front_tab.size() > s.bv.max_front_blocks || front_data.size() > s.bv.max_front_bytes) {
-                fprintf(stderr, "a record spans more than %u BGZF blocks: raise --chunk-mb / --chunk-blocks\n", s.bv.max_front_blocks);
-                std::lock_guard<std::mutex> lk(mu); fatal = 3; cv.notify_all(); break;
-            }
-            if (!front_data.empty()) memcpy(s.bv.front_comp, front_data.data(), front_data.size());
-            if (!front_tab.empty()) memcpy(s.bv.front_blocks, front_tab.data(), front_tab.size() * sizeof(exlr_bgzf_block));
-            s.n_front = (uint32_t)front_tab.size(); s.n_blocks = s.n_front + s.n_new; s.walk_start = start; s.front_bytes = front_data.size();
-            s.u_off.assign(s.n_blocks + 1, 0);
-            for (uint32_t k = 0; k < s.n_blocks; k++) s.u_off[k + 1] = s.u_off[k] + (k < s.n_front ? s.bv.front_blocks[k] : s.bv.blocks[k - s.n_front]).ulen;
-            const int st = exlr_bam_walk(s.b, s.front_bytes, s.n_front, start);
+            s.walk_start = start; s.prev_slot = held;
+            const int st = exlr_bam_walk(s.b, held >= 0 ? slots[held].b : nullptr, start);
+            if (held >= 0) { hand_over_settled(held); held = -1; }
+            if (st == EXLR_ERR_CAPACITY) fprintf(stderr, "a BAM record is larger than --max-record-mb (%llu MB)\n", cli.max_record_mb);
             if (st) { fail("exlr_bam_walk", st); break; }
             walked = si;
         }

@@ -252,16 +252,14 @@ int  exlr_get_trace(exlr_batch* b, unsigned long long* out, uint32_t n_ctas);
  * lookup and the packing into the structure-of-arrays batch all run as kernels, and the event kernels follow on the same
  * device arrays.  A chunk is a run of whole BGZF blocks; records may straddle chunks:
  *
- *   exlr_bam_submit(b, bytes, n_blocks)   async: H2D of the chunk's own blocks + inflate (needs nothing from the previous chunk,
- *                                         so the inflate kernels of consecutive chunks overlap on the device)
- *   exlr_bam_walk(b, fbytes, n_front, start_off)
- *                                         async: the caller has put the blocks of the previous chunk from the one its last, partial
- *                                         record begins in (front_comp / front_blocks) -- they are inflated in front of the chunk's
- *                                         own; then the records from uncompressed offset start_off on, counted from the first
- *                                         repeated block (first chunk: no repeated blocks, start_off = the end of the BAM header)
- *   exlr_bam_extract(b, &info)            waits for the walk, reports the chunk (records, tail_off = first byte not consumed:
- *                                         a partial record or the end of the chunk; counted like start_off) and starts the event
- *                                         kernels
+ *   exlr_bam_submit(b, bytes, n_blocks)   async: H2D of the chunk's blocks + inflate (needs nothing from the previous chunk, so
+ *                                         the inflate kernels of consecutive chunks share the device)
+ *   exlr_bam_walk(b, prev, start_off)     async: the bytes the previous chunk's walk left over (its partial last record; prev must
+ *                                         have been through exlr_bam_extract; NULL for the first chunk) are copied in front of this
+ *                                         chunk's, device to device; then the records from uncompressed offset start_off on,
+ *                                         counted from the first of those bytes (first chunk: the end of the BAM header; else 0)
+ *   exlr_bam_extract(b, &info)            waits for the walk, reports the chunk (records; tail_off = first byte not consumed, a
+ *                                         partial record or the chunk's end, counted like start_off) and starts the event kernels
  *   exlr_wait_text(b, ...)                the lines, exactly as for exlr_submit with EXLR_OPT_DEVICE_FORMAT
  */
 typedef struct exlr_bgzf_block {
@@ -275,10 +273,8 @@ typedef struct exlr_bam_views {
     uint8_t* comp;             /* [max_comp_bytes] pinned: the caller reads the file straight into it */
     exlr_bgzf_block* blocks;   /* [max_blocks] pinned                                                 */
     uint64_t max_comp_bytes;
-    uint32_t max_blocks, max_front_blocks;
-    uint8_t* front_comp;       /* [max_front_bytes] pinned: DEFLATE data of the blocks repeated from the previous chunk */
-    exlr_bgzf_block* front_blocks;   /* [max_front_blocks] pinned: comp_off relative to front_comp                     */
-    uint64_t max_front_bytes;
+    uint32_t max_blocks, reserved;
+    uint64_t max_tail_bytes;   /* the longest leftover of a previous chunk (= the largest record) the batch has room for */
 } exlr_bam_views;
 
 typedef struct exlr_bam_info {
@@ -290,16 +286,17 @@ typedef struct exlr_bam_info {
     uint64_t u_bytes, comp_bytes;
     float    h2d_ms, inflate_ms, walk_ms;   /* device times of the decode stages (CUDA events on the batch's stream)          */
     float    reserved2;
+    float    t_ms[4];          /* the same events on the context's clock (ms since exlr_create): chunk start, H2D done, inflate done,
+                                  walk + gather done -- shows how the chunks of a stream overlap on the device                */
 } exlr_bam_info;
 
-/* A batch for chunks of at most max_blocks BGZF blocks / max_comp_bytes compressed bytes, plus max_front_blocks /
- * max_front_bytes repeated from the previous chunk; its record capacity is the most such a chunk can hold, so no chunk
- * overflows it.  Lines are always formatted on the device. */
-int  exlr_bam_batch_alloc(exlr_ctx* ctx, uint64_t max_comp_bytes, uint32_t max_blocks, uint64_t max_front_bytes, uint32_t max_front_blocks,
-                          uint64_t max_events, exlr_batch** out);
+/* A batch for chunks of at most max_blocks BGZF blocks / max_comp_bytes compressed bytes, plus max_tail_bytes left over from
+ * the previous chunk; its record capacity is the most such a chunk can hold, so no chunk overflows it.  Lines are always
+ * formatted on the device. */
+int  exlr_bam_batch_alloc(exlr_ctx* ctx, uint64_t max_comp_bytes, uint32_t max_blocks, uint64_t max_tail_bytes, uint64_t max_events, exlr_batch** out);
 int  exlr_bam_get_views(exlr_batch* b, exlr_bam_views* v);
 int  exlr_bam_submit(exlr_batch* b, uint64_t comp_bytes, uint32_t n_blocks);
-int  exlr_bam_walk(exlr_batch* b, uint64_t front_bytes, uint32_t n_front, uint64_t start_off);
+int  exlr_bam_walk(exlr_batch* b, exlr_batch* prev, uint64_t start_off);
 int  exlr_bam_extract(exlr_batch* b, exlr_bam_info* info);
 /* Inspection / tests: copies the decoded structure-of-arrays batch of the last walked chunk into caller memory (`out` holds
  * caller-allocated arrays and their capacities; qnames / qname_off may be NULL). */

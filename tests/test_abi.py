@@ -30,7 +30,7 @@ def test_header_symbols_exported():
 def test_struct_layouts():
     assert C.sizeof(ExlrParams) == 40 and EVENT_DTYPE.itemsize == 48
     assert C.sizeof(api._Result) == 80 and C.sizeof(api.Timing) == 64 and C.sizeof(api._Views) == 104
-    assert C.sizeof(api.BamInfo) == 80 and C.sizeof(api.BgzfBlock) == 16 and C.sizeof(api._BamViews) == 56 and C.sizeof(api.Counters) == 64
+    assert C.sizeof(api.BamInfo) == 96 and C.sizeof(api.BgzfBlock) == 16 and C.sizeof(api._BamViews) == 40 and C.sizeof(api.Counters) == 64
     lib = api.load_library()
     p = ExlrParams()
     lib.exlr_params_default(C.byref(p))

@@ -111,30 +111,25 @@ def test_partial_record_at_the_end_is_the_tail(tmp_path):
     blocks, used = api.bgzf_blocks(data)
     keep = len(blocks) * 2 // 3
     ex = api.Extractor(ExlrParams.make(), hb.ref_names)
-    bb = api.BamBatch(ex, len(data), len(blocks), 0, 1 << 20, 64)
+    bb = api.BamBatch(ex, len(data), len(blocks))
     bb.load(data[:used], blocks[:keep])
     bb.walk(_header_end(data, blocks))
     info = bb.extract()
     assert info.status == 0 and 0 < info.n_reads < hb.n_reads and info.tail_off < info.u_bytes
     n = int(info.n_reads)
     _same(bb.download(hb.ref_names, n, int(info.n_ops), int(info.n_sa_bytes)), hb, n)
-    # the next chunk: its own blocks are inflated at once; the blocks of the previous one from the tail's block on go in front
-    u_off = np.concatenate([[0], np.cumsum([b[2] for b in blocks[:keep]])])
-    first = int(np.searchsorted(u_off, info.tail_off, side="right") - 1)
+    # the next chunk: its own blocks are inflated at once; what the previous walk left over is copied in front on the device
     rest_blocks = blocks[keep:]
     base = rest_blocks[0][0]
-    bb.load(data[base:used], [(co - base, cl, ul) for co, cl, ul in rest_blocks])
-    front = blocks[first:keep]
-    fdata, ftab = b"", []
-    for co, cl, ul in front:
-        ftab.append((len(fdata), cl, ul))
-        fdata += data[co:co + cl]
-    bb.walk(int(info.tail_off - u_off[first]), (fdata, ftab))
+    b2 = api.BamBatch(ex, len(data), len(blocks))
+    b2.load(data[base:used], [(co - base, cl, ul) for co, cl, ul in rest_blocks])
+    b2.walk(0, bb)
+    bb, old = b2, bb
     info2 = bb.extract()
     assert info2.status == 0 and info2.n_reads == hb.n_reads - n and info2.tail_off == info2.u_bytes
     rest = bb.download(hb.ref_names, int(info2.n_reads), int(info2.n_ops), int(info2.n_sa_bytes))
     assert np.array_equal(rest.pos, hb.pos[n:]) and np.array_equal(rest.cigar, hb.cigar[int(hb.cigar_off[n]):])
-    bb.free(); ex.close()
+    old.free(); bb.free(); ex.close()
 
 
 def test_corrupt_block_is_reported(tmp_path):
@@ -153,3 +148,41 @@ def test_corrupt_block_is_reported(tmp_path):
     info = bb.extract()
     assert info.status == -7 and info.bad_block == 5
     bb.free(); ex.close()
+
+
+@pytest.mark.parametrize("per_chunk,seq_len,block", [(3, 4000, 3000), (1, 4000, 3000), (7, 150, 700), (40, 9000, 0xFF00)])
+def test_records_spanning_blocks_and_chunks(tmp_path, per_chunk, seq_len, block):
+    # records several BGZF blocks long, chunks of a few blocks: a record can start in one chunk and end two chunks later; the
+    # leftover of every walk is handed to the next chunk on the device
+    hb = synth.with_qnames(synth.config(0, 0.06))
+    bam = str(tmp_path / "s.bam")
+    bamio.write_bam(hb, bam, ref_lens=synth.ref_lens(), seq_len=seq_len, block=block, random_seq=True)
+    data = open(bam, "rb").read()
+    blocks, used = api.bgzf_blocks(data)
+    ex = api.Extractor(ExlrParams.make(), hb.ref_names)
+    batches = [api.BamBatch(ex, 1 << 22, per_chunk + 1, 0, 1 << 20) for _ in range(3)]
+    got_pos, got_cig, got_sa, got_qn, n_chunks = [], [], [], [], 0
+    prev, start = None, _header_end(data, blocks)
+    for i in range(0, len(blocks), per_chunk):
+        bb = batches[n_chunks % 3]
+        part = blocks[i:i + per_chunk]
+        base = part[0][0]
+        end = part[-1][0] + part[-1][1]
+        bb.load(data[base:end], [(co - base, cl, ul) for co, cl, ul in part])
+        if prev is None:
+            first_u = sum(b[2] for b in blocks[:i])
+            bb.walk(max(0, start - first_u))
+        else:
+            bb.walk(0, prev)
+        info = bb.extract()
+        assert info.status == 0
+        if info.n_reads:
+            h = bb.download(hb.ref_names, int(info.n_reads), int(info.n_ops), int(info.n_sa_bytes))
+            got_pos.append(h.pos); got_cig.append(h.cigar); got_sa.append(h.sa_bytes); got_qn += h.qnames
+        prev, n_chunks = bb, n_chunks + 1
+    assert info.tail_off == info.u_bytes
+    assert np.array_equal(np.concatenate(got_pos), hb.pos) and np.array_equal(np.concatenate(got_cig), hb.cigar)
+    assert np.array_equal(np.concatenate(got_sa), hb.sa_bytes) and got_qn == hb.qnames
+    for b in batches:
+        b.free()
+    ex.close()
