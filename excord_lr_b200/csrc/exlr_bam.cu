@@ -25,6 +25,7 @@ namespace exlr {
 static constexpr int KI_WARPS = 8;             // BGZF blocks in flight per CTA
 static constexpr int KI_LL_BITS = 10;          // literal/length codes up to this many bits resolve with one table look-up
 static constexpr int KI_D_BITS = 9;
+static constexpr uint32_t KI_RING_LINES = 4;   // 128-byte lines of compressed input held per warp
 
 struct __align__(16) InflWarp {
     uint16_t ll[1 << KI_LL_BITS];              // (symbol << 4) | code length, indexed by the next bits of the stream; 0 = longer code
@@ -35,35 +36,51 @@ struct __align__(16) InflWarp {
     uint16_t cl_sym[20], cl_cnt[16];
     uint32_t nc[16], so[16], cw[16];           // table building scratch: next code / sorted offset / count per length
     uint8_t lens[320];
+    uint32_t ring[KI_RING_LINES * 32];         // the compressed stream, prefetched (BitReader)
 };
 
 // All 32 lanes of the warp run the decoder redundantly (same data, same control flow: one instruction stream); what differs per
-// lane is the prefetched input (each lane holds one word of the current and of the next 128-byte line of the compressed stream)
-// and the byte it holds of the pending output.
+// lane is the byte it holds of the pending output.  The compressed stream is prefetched into a small per-warp ring in shared
+// memory with cp.async (four 128-byte lines: the line being read and three ahead), so no register ever waits for global memory:
+// a line is requested ~384 bytes of input before it is read.
 struct BitReader {
     const uint32_t* line0;                     // 128-byte aligned start of the stream's first line
-    uint32_t line, widx, cur, nxt, bc;
+    uint32_t* ring;                            // [KI_RING_LINES * 32] words in shared memory
+    uint32_t line, widx, bc;                   // current line, next word in it, valid bits in bb
     unsigned long long bb;
-    __device__ __forceinline__ void init(const uint8_t* p)
+    __device__ __forceinline__ void fetch_line(uint32_t l)     // every lane copies one word of line l into its ring slot
     {
         const uint32_t lane = threadIdx.x & 31;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (l % KI_RING_LINES) * 32 + lane);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n\tcp.async.commit_group;" ::"r"(dst), "l"(line0 + (size_t)l * 32 + lane) : "memory");
+    }
+    __device__ __forceinline__ void init(const uint8_t* p)
+    {
         const uintptr_t a = reinterpret_cast<uintptr_t>(p);
         line0 = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)127);
         line = 0; widx = (uint32_t)(a & 127) >> 2; bb = 0; bc = 0;
-        cur = __ldg(line0 + lane); nxt = __ldg(line0 + 32 + lane);
-        refill();
+        __syncwarp();                                          // (a re-init: nobody still reads the ring)
+#pragma unroll
+        for (uint32_t l = 0; l < KI_RING_LINES; l++) fetch_line(l);
+        asm volatile("cp.async.wait_group %0;" ::"n"(KI_RING_LINES - 1) : "memory");
+        __syncwarp();
+        refill(); refill();
         const uint32_t skip = (uint32_t)(a & 3) * 8u;
         bb >>= skip; bc -= skip;
         refill();
     }
-    __device__ __forceinline__ void refill()    // afterwards bc >= 33
+    __device__ __forceinline__ void refill()    // one word if there is room for it; afterwards bc >= 33 (callers consume < 32 bits between calls)
     {
-        while (bc <= 32u) {
-            const uint32_t w = __shfl_sync(0xffffffffu, cur, widx);
+        if (bc <= 32u) {
+            const uint32_t w = ring[(line % KI_RING_LINES) * 32 + widx];
             bb |= (unsigned long long)w << bc; bc += 32u;
             if (++widx == 32u) {
-                cur = nxt; line++; widx = 0;
-                nxt = __ldg(line0 + (size_t)(line + 1) * 32 + (threadIdx.x & 31));
+                // the line just finished frees its slot: request the line KI_RING_LINES ahead there, then make sure the next one landed
+                __syncwarp();
+                fetch_line(line + KI_RING_LINES);
+                line++; widx = 0;
+                asm volatile("cp.async.wait_group %0;" ::"n"(KI_RING_LINES - 1) : "memory");
+                __syncwarp();
             }
         }
     }
@@ -147,9 +164,10 @@ __global__ void __launch_bounds__(KI_WARPS * 32) kb_inflate(const uint8_t* __res
     if (blk.ulen == 0) return;                                               // (the EOF marker block)
     uint8_t* out = U + blk.uoff;
     const uint32_t ulen = blk.ulen;
-    BitReader br; br.init(comp + blk.coff);
+    BitReader br; br.ring = S.ring; br.init(comp + blk.coff);
     uint32_t o = 0, ps = 0, pend = 0;                                        // output position; pending literals are [ps, o), one per lane
     const uint32_t oa = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 31u);  // (oa + o) & 31 = the lane that holds output byte o
+    const uint32_t my_o = (lane - oa) & 31u, wend = (32u - oa) & 31u;       // ... i.e. o & 31 == my_o; a 32-byte window ends where o & 31 == wend
     bool ok = true;
     // pending literal bytes sit in the lane (address & 31) of their 32-byte window and go out as one 32-byte store
     auto flush = [&]() {
@@ -164,7 +182,9 @@ __global__ void __launch_bounds__(KI_WARPS * 32) kb_inflate(const uint8_t* __res
         if (type == 0) {                                                     // stored
             br.drop(br.bc & 7u);
             br.refill();
-            const uint32_t len = br.get(16), nlen = br.get(16);
+            const uint32_t len = br.get(16);
+            br.refill();
+            const uint32_t nlen = br.get(16);
             if ((len ^ 0xffffu) != nlen || o + len > ulen) { ok = false; break; }
             flush();
             const uint8_t* src = br.byte_ptr();
@@ -224,9 +244,9 @@ __global__ void __launch_bounds__(KI_WARPS * 32) kb_inflate(const uint8_t* __res
                 const uint32_t e = S.ll[br.peek(KI_LL_BITS)];
                 if (e & 0x2000u) {
                     br.drop(e & 15u);
-                    if (lane == ((oa + o) & 31u)) pend = e >> 4;
+                    if ((o & 31u) == my_o) pend = e >> 4;
                     o++;
-                    if (((oa + o) & 31u) == 0u) { if (o > ulen) { ok = false; break; } flush(); }
+                    if ((o & 31u) == wend) { if (o > ulen) { ok = false; break; } flush(); }
                     continue;
                 }
             }
