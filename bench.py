@@ -343,6 +343,55 @@ def strong_c5(args, ex_opts, D, rank, local_rank, world, peak):
     return out
 
 
+def e2e_bam(args, pcie_gbs):
+    """BAM bytes in -> event bytes out, through the CLI (excord_lr_b200/host/excord-lr-b200): the file is read into pinned memory,
+    inflated and walked on the GPU (exlr_bam_*), and the lines come back formatted.  Workload: BASELINE.json configs[1] molecules
+    with 15 kb of random SEQ/QUAL per record (what makes a real HiFi BAM big); the same run with --host-reader (zlib on every host
+    core) beside it.  Times are the CLI's own `stream` figure (after process setup: CUDA context, buffers), best of 3."""
+    import re
+    import subprocess
+    import tempfile
+    from excord_lr_b200 import bamio, synth
+    exe = os.path.join(ROOT, "excord_lr_b200", "host", "excord-lr-b200")
+    if not os.path.exists(exe):
+        return {"unavailable": "host/excord-lr-b200 not built"}
+    hb = synth.config(1, args.bam_scale)
+    cores = os.cpu_count() or 1
+    out = {"workload": f"c2_hifi molecules x {args.bam_scale}, 15 kb random SEQ/QUAL per record, BGZF level 1", "records": hb.n_reads}
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+        bam, txt = os.path.join(d, "x.bam"), os.path.join(d, "x.txt")
+        bamio.write_bam(hb, bam, ref_lens=synth.ref_lens(), seq_len=15000, random_seq=True)
+        size = os.path.getsize(bam)
+        out["bam_bytes"] = size
+        ref = None
+        for key, extra in (("gpu_decoder", []), ("host_reader", ["--host-reader"])):
+            best, wall, detail = None, None, ""
+            for _ in range(3):
+                t0 = time.perf_counter()
+                r = subprocess.run([exe, "-b", bam, "-o", txt, "-p", "0.8", "-t", str(cores), "--stats"] + extra, capture_output=True, text=True)
+                w = time.perf_counter() - t0
+                if r.returncode != 0:
+                    return {"unavailable": r.stderr[-300:]}
+                m = re.search(r"stream ([0-9.]+) s", r.stderr)
+                st = float(m.group(1)) if m else w
+                if best is None or st < best:
+                    best, wall = st, w
+                    dm = re.search(r"GPU BAM decoder: (.*)", r.stderr)
+                    detail = dm.group(1) if dm else ""
+            got = open(txt, "rb").read()
+            if ref is not None and got != ref:
+                return {"unavailable": "the GPU decoder and the host reader wrote different files"}
+            ref = got
+            out[key] = {"stream_s": best, "wall_s_with_process_setup": wall, "alignments_per_sec": hb.n_reads / best, "bam_gbs": size / best / 1e9,
+                        "frac_of_pcie_h2d": size / best / 1e9 / pcie_gbs if pcie_gbs else None}
+            if detail:
+                out[key]["stages"] = detail
+        out["host_reader"]["threads"] = cores
+        out["output_bytes"] = len(ref)
+        out["speedup_over_host_reader"] = out["host_reader"]["stream_s"] / out["gpu_decoder"]["stream_s"]
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -358,6 +407,8 @@ def main():
     ap.add_argument("--strong", action="store_true", help="the headline workload itself sharded round robin over the ranks (instead of one batch per rank)")
     ap.add_argument("--no-strong-c5", action="store_true", help="skip the strong_c5 block (N > 1)")
     ap.add_argument("--strong-scale", type=float, default=1.0, help="scale of configs[4] in the strong_c5 block")
+    ap.add_argument("--no-e2e-bam", action="store_true", help="skip the e2e_bam block (BAM file -> event file through the CLI, N = 1)")
+    ap.add_argument("--bam-scale", type=float, default=0.03, help="molecules of configs[1] in the e2e_bam BAM (0.03 -> ~31k records, ~580 MB)")
     ap.add_argument("--no-overlap", action="store_true", help="run kernel 1 on the same stream as the SA branch")
     ap.add_argument("--k1-ctas", type=int, default=0, help="persistent CTAs of kernel 1 per SM (1..4)")
     ap.add_argument("--k1-waves", type=int, default=0)
@@ -459,6 +510,13 @@ def main():
                "sample": f"the whole workload once ({R} records, {Cops} CIGAR ops, {dt:.2f} s), single thread like the reference loop",
                "lines": int(len(want.events)), "matches_gpu_line_count": bool(len(want.events) == n_events)}
 
+    bam_block = None
+    if rank == 0 and world == 1 and not args.no_e2e_bam:
+        ex.close()
+        ex = None
+        torch.cuda.synchronize()
+        bam_block = e2e_bam(args, pcie_alone)
+
     strong = None
     if world > 1 and not args.no_strong_c5 and not args.strong:
         strong = strong_c5(args, ex_opts, D, rank, local_rank, world, load_peaks()[0])
@@ -532,9 +590,12 @@ def main():
             line["cpu_baseline"] = cpu
         if strong:
             line["strong_c5"] = strong
+        if bam_block:
+            line["e2e_bam"] = bam_block
         print(json.dumps(line), flush=True)
 
-    ex.close()
+    if ex is not None:
+        ex.close()
     D.close()
 
 
