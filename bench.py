@@ -409,6 +409,7 @@ def main():
     ap.add_argument("--strong-scale", type=float, default=1.0, help="scale of configs[4] in the strong_c5 block")
     ap.add_argument("--no-e2e-bam", action="store_true", help="skip the e2e_bam block (BAM file -> event file through the CLI, N = 1)")
     ap.add_argument("--bam-scale", type=float, default=0.03, help="molecules of configs[1] in the e2e_bam BAM (0.03 -> ~31k records, ~580 MB)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel of every step directly (default: repeated shapes replay a CUDA graph)")
     ap.add_argument("--no-overlap", action="store_true", help="run kernel 1 on the same stream as the SA branch")
     ap.add_argument("--k1-ctas", type=int, default=0, help="persistent CTAs of kernel 1 per SM (1..4)")
     ap.add_argument("--k1-waves", type=int, default=0)
@@ -437,6 +438,8 @@ def main():
     ex_opts = [(api.EXLR_OPT_CIGAR_KERNEL, args.cigar_kernel), (api.EXLR_OPT_READS_PER_CTA, args.reads_per_cta)]
     if args.no_overlap:
         ex_opts.append((api.EXLR_OPT_OVERLAP, 0))
+    if args.no_graph:
+        ex_opts.append((api.EXLR_OPT_GRAPH, 0))
     if args.k1_ctas:
         ex_opts.append((api.EXLR_OPT_K1_CTAS_PER_SM, args.k1_ctas))
     if args.k1_waves:
@@ -554,6 +557,7 @@ def main():
             "cigar_ops_per_sec": C_all / (total_ms_max / 1e3) * args.steps,
             "config": config_dict(c, hb),
             "run": {"lines_per_gpu": n_events, "n_gpus": world,
+                    "launch": "direct launches" if args.no_graph else "the step's kernels replay as one CUDA graph (same shape every step); PDL edges and the two-stream fork/join are part of the graph",
                     "cigar_kernel": {0: "auto: streaming event screen (1a), then only the records around a candidate are scanned (1b: thread per short record; 1d: long records from 1a's per-step sums)",
                                      1: "warp per record", 2: "flat TMA-staged block scan of everything", 3: "the screened path (forced)"}[args.cigar_kernel],
                     "counters": counters},

@@ -50,9 +50,23 @@ struct exlr_ctx {
     std::atomic<int> skip_screen{0};           // auto mode: batches left to run without the screen pass (the last screened one was event-dense);
                                                // written by whoever waits a batch, read by whoever submits the next (two threads in the CLI)
     std::atomic<uint64_t> ev_hint{0}, text_hint{0};   // events / text bytes of the last waited batch: how much exlr_submit copies back speculatively
+    int graph = 1;                             // EXLR_OPT_GRAPH: repeated shapes run as one CUDA graph launch
     int k3_fold = 1;                           // EXLR_OPT_K3_FOLD: 0 = kernel 3a always runs on its own (A/B measurement)
     cudaEvent_t ev_origin = nullptr;           // recorded at exlr_create: the context's clock for exlr_bam_info.t_ms
     bool far_mode = false;                     // merge_min > 2 * indel_min: the >2 merge loop (main.rs:636-742) can change the events, kernels 4a/4b run their FAR variants
+};
+
+// What a submit is going to launch: decided on the host before anything is enqueued (and part of the identity of a captured graph).
+struct StepPlan {
+    bool overlap, screened, long_batch, two_level, fold, far, formatted;
+    int variant; uint32_t rpc;
+    unsigned long long n_reads, n_ops;
+    const void* events;                        // (exlr_batch_grow moves the event buffers: a graph captured before it is stale)
+    bool operator==(const StepPlan& o) const
+    {
+        return overlap == o.overlap && screened == o.screened && long_batch == o.long_batch && two_level == o.two_level && fold == o.fold &&
+               far == o.far && formatted == o.formatted && variant == o.variant && rpc == o.rpc && n_reads == o.n_reads && n_ops == o.n_ops && events == o.events;
+    }
 };
 
 struct exlr_batch {
@@ -81,6 +95,8 @@ struct exlr_batch {
     uint64_t n_reads = 0, n_ops = 0;
     bool submitted = false, resident_uploaded = false, have_timing = false, stage_timed = false;
     bool far_ran = false;                      // the last submit ran the FAR variants of kernels 4a/4b
+    cudaGraphExec_t gexec = nullptr;           // the step as a CUDA graph, once the same shape has been submitted twice in a row
+    StepPlan gplan{}, last_plan{}; bool have_last_plan = false; uint32_t glaunches = 0;
     uint32_t launches = 0;
     unsigned long long* d_dbg = nullptr;
     // ---- BAM input decoded on the device (exlr_bam_*): compressed chunk + block table in pinned memory, the rest on the device
@@ -105,6 +121,13 @@ static constexpr size_t kTextBytesPerLine = 96;
 static constexpr size_t kTextBytesPerVerboseLine = 288;    // -v lines carry a tag of up to 50 bytes and the read name (BAM batches)
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static void drop_graph(exlr_batch* b)
+{
+    if (b->gexec) { cudaGraphExecDestroy(b->gexec); b->gexec = nullptr; }
+    b->have_last_plan = false;
+}
+
 
 // Everything whose size follows max_events: the raw / SA / final event buffers, the text buffers of kernels 5a/5b with their
 // scan status words, and the pinned host copies.  Separate from the input + per-record slab so that exlr_batch_grow can
@@ -262,6 +285,7 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
     case EXLR_OPT_DEVICE_FORMAT: c->device_format = value != 0; return EXLR_OK;
     case EXLR_OPT_VERBOSE_TEXT: c->verbose_text = value != 0; return EXLR_OK;
     case EXLR_OPT_K3_FOLD: c->k3_fold = value != 0; return EXLR_OK;
+    case EXLR_OPT_GRAPH: c->graph = value != 0; return EXLR_OK;
     case EXLR_OPT_LONG_RECORDS: if (value < 0 || value > 3) return EXLR_ERR_ARG; c->long_records = (int)value; return EXLR_OK;
     case EXLR_OPT_K1A_CTAS_PER_SM: if (value < 1 || value > 8) return EXLR_ERR_ARG; c->k1a_ctas = (int)value; return EXLR_OK;
     case EXLR_OPT_TRACE: if (value < 0 || value > 7) return EXLR_ERR_ARG; c->trace = (int)value; return EXLR_OK;
@@ -287,6 +311,7 @@ void exlr_batch_free(exlr_batch* b)
     for (auto& e : b->ev_bam) if (e) cudaEventDestroy(e);
     if (b->ev_tail_read) cudaEventDestroy(b->ev_tail_read);
     cudaFree(b->d_bam); cudaFreeHost(b->h_comp); cudaFreeHost(b->h_blocks); cudaFreeHost(b->h_btab); cudaFreeHost(b->h_bctrl);
+    if (b->gexec) cudaGraphExecDestroy(b->gexec);
     cudaFree(b->d_slab); cudaFree(b->d_evslab);
     cudaFreeHost(b->h_slab); cudaFreeHost(b->h_out); cudaFreeHost(b->h_events); cudaFreeHost(b->h_text);
     delete b;
@@ -391,6 +416,7 @@ int exlr_batch_grow(exlr_batch* b, uint64_t max_events)
     CK(cudaStreamSynchronize(b->stream));
     if (b->stream2) CK(cudaStreamSynchronize(b->stream2));
     free_event_buffers(b);
+    drop_graph(b);
     b->submitted = false; b->have_timing = false;
     return alloc_event_buffers(b, max_events);
 }
@@ -457,23 +483,15 @@ static uint64_t guess_with_margin(uint64_t hint, uint64_t first_guess, uint64_t 
     return g < cap ? g : cap;
 }
 
-static int run_kernels(exlr_batch* b, bool prefetch_results)
+static void plan_step(exlr_batch* b, StepPlan* p)
 {
-    exlr_ctx* c = b->ctx; cudaStream_t st = b->stream; DevBatch& d = b->dv;
-    b->launches = 0; b->stage_timed = c->stage_timing != 0;
-    d.dbg = c->trace ? b->d_dbg : nullptr; d.dbg_sel = (uint32_t)c->trace;
-    if (c->trace) CK(cudaMemsetAsync(b->d_dbg, 0, 8192 * 32, st));
-    CK(cudaMemsetAsync(d.ctrl, 0, b->ctrl_bytes, st));
-    if (b->scan_c_bytes) CK(cudaMemsetAsync(d.scan_c, 0, b->scan_c_bytes, st));
-    // kernel 1 needs nothing from kernel 0, so it runs on a second stream beside the SA branch (0 -> 3a -> 3b); 4a joins them
-    d.prim_slots = 0; d.capt_log2 = 0; d.k1_gated = 0;
-    const bool overlap = c->overlap && !c->params.split_only;
-    d.hc = HostCfg{c->sms, c->k1_ctas ? c->k1_ctas : (overlap ? 3 : 4), c->k1a_ctas, c->k1_waves};
-    uint32_t rpc = 0;
-    const int variant = c->cigar_kernel == 1 ? 1 : 0;
-    b->screened = false;
+    exlr_ctx* c = b->ctx;
+    memset(p, 0, sizeof(*p));
+    p->n_reads = b->n_reads; p->n_ops = b->n_ops; p->events = b->dv.events;
+    p->overlap = c->overlap && !c->params.split_only;
+    p->variant = c->cigar_kernel == 1 ? 1 : 0;
     if (!c->params.split_only) {
-        rpc = c->reads_per_cta ? c->reads_per_cta : auto_rpc(b->n_reads, b->n_ops);
+        p->rpc = c->reads_per_cta ? c->reads_per_cta : auto_rpc(b->n_reads, b->n_ops);
         // Events (I/D >= indel_min) are sparse in HiFi and ONT batches alike (~10 % of the records hold one), so by default the
         // CIGAR stream is screened at streaming speed (kernel 1a) and only the records around an event candidate are scanned
         // (kernels 1b, 1c).  A batch where most 512-op steps held a candidate (e.g. -i 1) is better off with the flat scan of
@@ -481,49 +499,104 @@ static int run_kernels(exlr_batch* b, bool prefetch_results)
         // (kernel 1a indexes the CIGAR array by 32-bit vector numbers)
         bool want = c->cigar_kernel == 3;
         if (c->cigar_kernel == 0) { if (c->skip_screen.load() > 0) c->skip_screen.fetch_sub(1); else want = true; }
-        b->screened = want && b->n_ops < (1ull << 33) && b->n_ops > 0;
+        p->screened = want && b->n_ops < (1ull << 33) && b->n_ops > 0;
+        // Batches of long records (ONT-like): kernel 1a also leaves per-step sums, and the long records behind it are resolved by
+        // kernel 1d from those sums (EXLR_OPT_LONG_RECORDS=2: by kernel 1c, the flat block scan of the listed records).  In a
+        // batch of short records the odd long one is scanned by a warp of kernel 1b, and the chain is one launch shorter.
+        p->long_batch = p->screened && (c->long_records ? c->long_records >= 2 : b->n_ops / b->n_reads > kLongRecordMeanOps);
+        p->two_level = p->long_batch && c->long_records != 2;
+    }
+    const uint32_t mean_ops = (uint32_t)(b->n_reads ? b->n_ops / b->n_reads : 0);
+    p->fold = k3_fold(mean_ops) && c->k3_fold;                        // short CIGARs: kernel 3b walks the SA records' own CIGARs itself
+    p->far = c->far_mode;
+    p->formatted = b->dv.text_off != nullptr;
+}
+
+// The step itself: two memsets and the kernels, on the batch's two streams.  `timed`: CUDA events between the kernels
+// (exlr_timing per stage); never while the step is being captured into a graph.
+static int enqueue_step(exlr_batch* b, const StepPlan& p, bool timed)
+{
+    exlr_ctx* c = b->ctx; cudaStream_t st = b->stream; DevBatch& d = b->dv;
+    b->launches = 0;
+    d.dbg = c->trace ? b->d_dbg : nullptr; d.dbg_sel = (uint32_t)c->trace;
+    if (c->trace) CK(cudaMemsetAsync(b->d_dbg, 0, 8192 * 32, st));
+    CK(cudaMemsetAsync(d.ctrl, 0, b->ctrl_bytes, st));
+    if (b->scan_c_bytes) CK(cudaMemsetAsync(d.scan_c, 0, b->scan_c_bytes, st));
+    // kernel 1 needs nothing from kernel 0, so it runs on a second stream beside the SA branch (0 -> 3a -> 3b); 4a joins them
+    d.prim_slots = 0; d.capt_log2 = 0;
+    d.hc = HostCfg{c->sms, c->k1_ctas ? c->k1_ctas : (p.overlap ? 3 : 4), c->k1a_ctas, c->k1_waves};
+    d.k1_gated = p.screened ? 1u : 0u;
+    d.qnames = b->is_bam ? b->db.qnames : nullptr; d.qname_off = b->is_bam ? b->db.qname_off : nullptr;
+    d.verbose = b->is_bam && b->verbose_text ? 1u : 0u;
+    if (!c->params.split_only) {
         uint32_t n_tiles = 0;
-        d.k1_gated = b->screened ? 1u : 0u;
-        plan_k1(d, b->screened ? 1 : variant, rpc, &n_tiles);               // screened: raw events all go to the atomically allocated region
-        if (overlap) CK(cudaEventRecord(b->ev_fork, st));                  // after the memset
+        plan_k1(d, p.screened ? 1 : p.variant, p.rpc, &n_tiles);         // screened: raw events all go to the atomically allocated region
+        if (p.overlap) CK(cudaEventRecord(b->ev_fork, st));               // after the memset
     }
     launch_k0(d, c->dparams, st); b->launches++;
-    if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K0], st));
+    if (timed) CK(cudaEventRecord(b->ev[EV_K0], st));
     if (!c->params.split_only) {
-        cudaStream_t s1 = overlap ? b->stream2 : st;
-        if (overlap) CK(cudaStreamWaitEvent(s1, b->ev_fork, 0));
-        if (c->stage_timing) CK(cudaEventRecord(b->ev_k1_begin, s1));
-        if (b->screened) {
-            // Batches of long records (ONT-like): kernel 1a also leaves per-step sums, and the long records behind it are resolved by
-            // kernel 1d from those sums (EXLR_OPT_LONG_RECORDS=2: by kernel 1c, the flat block scan of the listed records).  In a
-            // batch of short records the odd long one is scanned by a warp of kernel 1b, and the chain is one launch shorter.
-            const bool long_batch = c->long_records ? c->long_records >= 2 : b->n_ops / b->n_reads > kLongRecordMeanOps;
-            const bool two_level = long_batch && c->long_records != 2;
-            launch_k1a(d, c->dparams, b->n_ops, two_level, s1); b->launches++;
-            if (c->stage_timing) CK(cudaEventRecord(b->ev_k1_mid, s1));
-            launch_k1b(d, c->dparams, b->n_ops, long_batch, s1); b->launches += 2;
-            if (long_batch) { if (two_level) launch_k1d(d, c->dparams, s1); else launch_k1c(d, c->dparams, s1); b->launches++; }
+        cudaStream_t s1 = p.overlap ? b->stream2 : st;
+        if (p.overlap) CK(cudaStreamWaitEvent(s1, b->ev_fork, 0));
+        if (timed) CK(cudaEventRecord(b->ev_k1_begin, s1));
+        if (p.screened) {
+            launch_k1a(d, c->dparams, b->n_ops, p.two_level, s1); b->launches++;
+            if (timed) CK(cudaEventRecord(b->ev_k1_mid, s1));
+            launch_k1b(d, c->dparams, b->n_ops, p.long_batch, s1); b->launches += 2;
+            if (p.long_batch) { if (p.two_level) launch_k1d(d, c->dparams, s1); else launch_k1c(d, c->dparams, s1); b->launches++; }
         } else {
-            launch_k1(d, c->dparams, variant, rpc, s1); b->launches++;
+            launch_k1(d, c->dparams, p.variant, p.rpc, s1); b->launches++;
         }
         CK(cudaEventRecord(b->ev_k1_end, s1));
     }
-    if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K1], st));
-    const uint32_t mean_ops = (uint32_t)(b->n_reads ? b->n_ops / b->n_reads : 0);
-    const bool fold = k3_fold(mean_ops) && c->k3_fold;               // short CIGARs: kernel 3b walks the SA records' own CIGARs itself
-    if (!fold) { launch_k3a(d, c->dparams, mean_ops, st); b->launches++; }
-    if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K3A], st));
-    launch_k3b(d, c->dparams, fold, st); b->launches++;
-    if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K3B], st));
-    if (overlap) CK(cudaStreamWaitEvent(st, b->ev_k1_end, 0));
-    launch_k4a(d, c->dparams, c->far_mode, st); b->launches++;
-    if (c->stage_timing) CK(cudaEventRecord(b->ev[EV_K4A], st));
-    launch_k4b(d, c->dparams, c->far_mode, st); b->launches++;
-    b->formatted = d.text_off != nullptr;
-    d.qnames = b->is_bam ? b->db.qnames : nullptr; d.qname_off = b->is_bam ? b->db.qname_off : nullptr;
-    d.verbose = b->is_bam && b->verbose_text ? 1u : 0u;
-    if (b->formatted) { launch_k5(d, st); b->launches += 2; }      // (no event in between: 5a is placed while 4b drains)
-    b->far_ran = c->far_mode;
+    if (timed) CK(cudaEventRecord(b->ev[EV_K1], st));
+    if (!p.fold) { launch_k3a(d, c->dparams, (uint32_t)(b->n_reads ? b->n_ops / b->n_reads : 0), st); b->launches++; }
+    if (timed) CK(cudaEventRecord(b->ev[EV_K3A], st));
+    launch_k3b(d, c->dparams, p.fold, st); b->launches++;
+    if (timed) CK(cudaEventRecord(b->ev[EV_K3B], st));
+    if (p.overlap) CK(cudaStreamWaitEvent(st, b->ev_k1_end, 0));
+    launch_k4a(d, c->dparams, p.far, st); b->launches++;
+    if (timed) CK(cudaEventRecord(b->ev[EV_K4A], st));
+    launch_k4b(d, c->dparams, p.far, st); b->launches++;
+    if (p.formatted) { launch_k5(d, st); b->launches += 2; }       // (no event in between: 5a is placed while 4b drains)
+    CK(cudaGetLastError());
+    return EXLR_OK;
+}
+
+static int run_kernels(exlr_batch* b, bool prefetch_results)
+{
+    exlr_ctx* c = b->ctx; cudaStream_t st = b->stream; DevBatch& d = b->dv;
+    StepPlan plan;
+    plan_step(b, &plan);
+    b->screened = plan.screened; b->formatted = plan.formatted;
+    b->stage_timed = c->stage_timing != 0;
+    // A caller that submits the same shape again and again (a resident batch re-run, a ring of equal sub-batches) gets the step
+    // as ONE CUDA graph launch from the third time on: the chain of 5-9 small kernels is then scheduled by the device, not
+    // paced by this thread's launch calls (which jitter when several processes share the host).  The graph keeps the two-stream
+    // fork/join and the programmatic-dependent-launch edges.  Varying shapes (a streamed BAM) launch directly, as before.
+    const bool graph_ok = c->graph && !c->stage_timing && !c->trace;
+    if (graph_ok && b->gexec && plan == b->gplan) {
+        CK(cudaGraphLaunch(b->gexec, st));
+        b->launches = b->glaunches;
+    } else {
+        bool captured = false;
+        if (graph_ok && b->have_last_plan && plan == b->last_plan) {
+            drop_graph(b);
+            cudaGraph_t g = nullptr;
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int rc = enqueue_step(b, plan, false);
+                const cudaError_t e = cudaStreamEndCapture(st, &g);
+                if (rc == EXLR_OK && e == cudaSuccess && g && cudaGraphInstantiate(&b->gexec, g, 0) == cudaSuccess) {
+                    b->gplan = plan; b->glaunches = b->launches; captured = true;
+                } else { b->gexec = nullptr; c->graph = 0; cudaGetLastError(); }     // this driver cannot capture the step: never try again
+                if (g) cudaGraphDestroy(g);
+            } else { c->graph = 0; cudaGetLastError(); }
+            if (captured) CK(cudaGraphLaunch(b->gexec, st));
+        }
+        if (!captured) { const int rc = enqueue_step(b, plan, c->stage_timing != 0); if (rc) return rc; }
+    }
+    b->last_plan = plan; b->have_last_plan = true;
+    b->far_ran = plan.far;
     CK(cudaEventRecord(b->ev[EV_K4B], st));
     b->d2h_events = 0; b->d2h_text = 0; b->have_line_off = false; b->d2h_bytes = sizeof(Ctrl);
     if (prefetch_results) {

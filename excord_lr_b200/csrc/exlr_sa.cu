@@ -552,6 +552,7 @@ struct __align__(16) K3bSmem {
     uint32_t rrec[K3B_TILE], rslot[K3B_TILE];          // the tile's records and their first segment slot (FOLD: the piece threads walk their CIGARs)
     uint8_t pread[K3B_MAXP];
     uint8_t rlong[K3B_TILE];                           // FOLD: the record's CIGAR is long, a whole warp walks it
+    SaSum sum[K3B_TILE];                               // FOLD: what kernel 3a would have left in sa_sum, per record of the tile
 };
 
 // FOLD: kernel 3a's work is done here (the host folds it in for batches of short CIGARs): the thread that owns a record's slot
@@ -582,6 +583,22 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
         }
         for (uint32_t o = a0 + t * 16u; o < span_e; o += K3B_THREADS * 16u)
             *reinterpret_cast<uint4*>(S.bytes + (o - a0)) = __ldg(reinterpret_cast<const uint4*>(B.sa_bytes + o));
+        if (FOLD) {
+            // kernel 3a's work (main.rs:214-306, utils.rs:12-42): a pair of lanes walks the CIGAR of each of the tile's records --
+            // its loads are in flight while the SA bytes are staged
+            static_assert(K3B_THREADS >= 2 * K3B_TILE, "two lanes per record");
+            const uint32_t k = t >> 1;
+            const bool mine = t < 2 * K3B_TILE && j0 + k < j1;
+            uint32_t rr = 0; unsigned long long o0 = 0, o1 = 0;
+            if (mine) { rr = B.sa_list[j0 + k]; o0 = B.cigar_off[rr]; o1 = B.cigar_off[rr + 1]; }
+            const bool is_long = mine && o1 - o0 > K3A_LONG;
+            const uint32_t pm = __ballot_sync(0xffffffffu, mine && !is_long);
+            if (mine && !is_long) {
+                const K3aAcc a = k3a_walk<2>(B, rr, o0, o1, pm & (3u << (lane & ~1u)), lane & ~1u);
+                if ((t & 1u) == 0u) { SaSum sm; sm.S = a.S; sm.H = a.H; sm.refspan = (int64_t)a.D + (int64_t)a.M + (int64_t)a.E + (int64_t)a.X; sm.ffm = (int64_t)a.ffm; sm.pad[0] = sm.pad[1] = 0; S.sum[k] = sm; }
+            }
+            if (mine && (t & 1u) == 0u) { S.rrec[k] = rr; S.rlong[k] = is_long ? 1 : 0; }
+        }
         // phase 1: pieces per record
         uint32_t r = 0, b0 = 0, e0 = 0, slots = 0;
         bool dropped = false, is_str = false;
@@ -610,7 +627,6 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
             }
             slots = dropped ? 0u : 1u + nonempty;
             S.rerr[t] = 0xffffffffu;
-            S.rrec[t] = r; S.rlong[t] = 0;
         }
         uint32_t incl = slots;
 #pragma unroll
@@ -650,11 +666,6 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
             const uint32_t pbeg = x < total ? S.pb[x] : 0xffffffffu;
             const bool has = pbeg != 0xffffffffu;
             const uint32_t m = __ballot_sync(0xffffffffu, has);
-            if (FOLD && x < total && !has) {                                  // slot 0 of a record: its own alignment, from its CIGAR
-                const uint32_t tr_ = S.pread[x], rr = S.rrec[tr_];
-                if (B.cigar_off[rr + 1] - B.cigar_off[rr] > K3A_LONG) S.rlong[tr_] = 1;
-                else k3b_own_seg(B, P, rr, &S.segs[x]);
-            }
             if (!has) continue;
             const uint32_t pend = S.pe[x];
             if (dev_parse_piece_fast(S.bytes, a0, pbeg, pend, P, &S.segs[x], m)) continue;
@@ -667,7 +678,7 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
                 if (j0 + k >= j1 || !S.rlong[k]) continue;                    // warp-uniform
                 const uint32_t rr = S.rrec[k];
                 const K3aAcc a = k3a_walk<32>(B, rr, B.cigar_off[rr], B.cigar_off[rr + 1], 0xffffffffu, 0);
-                if (lane == 0) seg_from_sums(B, P, rr, a.S, a.H, (int64_t)a.D + (int64_t)a.M + (int64_t)a.E + (int64_t)a.X, (int64_t)a.ffm, &S.segs[S.rslot[k]]);
+                if (lane == 0) { SaSum sm; sm.S = a.S; sm.H = a.H; sm.refspan = (int64_t)a.D + (int64_t)a.M + (int64_t)a.E + (int64_t)a.X; sm.ffm = (int64_t)a.ffm; sm.pad[0] = sm.pad[1] = 0; S.sum[k] = sm; }
             }
             __syncthreads();
         }
@@ -678,7 +689,8 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
             uint32_t err = S.rerr[t];
             nseg = slots;
             if (err != 0xffffffffu) { report(B.ctrl, r, err & 0xffu); nseg = 0; }
-            else if (!FOLD) k3b_record_seg(B, P, j, r, &S.segs[sb]);           // (FOLD: phase 2 left it there)
+            else if (!FOLD) k3b_record_seg(B, P, j, r, &S.segs[sb]);
+            else { const SaSum sm = S.sum[t]; seg_from_sums(B, P, r, sm.S, sm.H, sm.refspan, sm.ffm, &S.segs[sb]); }
         }
         k3b_finish(B, P, s, j, active, r, dropped, &S.segs[sb < K3B_MAXP ? sb : 0], nseg);
     }

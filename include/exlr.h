@@ -189,6 +189,8 @@ typedef struct exlr_batch exlr_batch;
 
 #define EXLR_OPT_K3_FOLD 12       /* 1 (default) = in batches of short CIGARs kernel 3b does kernel 3a's work itself; 0 = kernel 3a always runs */
 
+#define EXLR_OPT_GRAPH 13         /* 1 (default) = a batch submitted with the same shape again and again runs its kernels as one CUDA graph launch */
+
 /* ---- lifecycle ---------------------------------------------------------------------- */
 int  exlr_abi_version(void);
 /* Number of CUDA devices with compute capability 10.x; <0 on CUDA error. */
