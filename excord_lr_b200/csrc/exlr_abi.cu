@@ -51,7 +51,7 @@ struct exlr_ctx {
                                                // written by whoever waits a batch, read by whoever submits the next (two threads in the CLI)
     std::atomic<uint64_t> ev_hint{0}, text_hint{0};   // events / text bytes of the last waited batch: how much exlr_submit copies back speculatively
     int graph = 1;                             // EXLR_OPT_GRAPH: repeated shapes run as one CUDA graph launch
-    int k3_fold = 1;                           // EXLR_OPT_K3_FOLD: 0 = kernel 3a always runs on its own (A/B measurement)
+    int k3_fold = 0;                           // EXLR_OPT_K3_FOLD: 1 = kernel 3b does kernel 3a's work itself in batches of short CIGARs (measured slower: off)
     cudaEvent_t ev_origin = nullptr;           // recorded at exlr_create: the context's clock for exlr_bam_info.t_ms
     bool far_mode = false;                     // merge_min > 2 * indel_min: the >2 merge loop (main.rs:636-742) can change the events, kernels 4a/4b run their FAR variants
 };

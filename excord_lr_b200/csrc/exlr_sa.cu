@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) k3a_sa_cigar(DevBatch B, DevParams P)
 // ======================================================================================
 static constexpr int K3B_THREADS = 192;                 // the usual tile (64 records, ~140 pieces + 64 own segments) parses in one round
 static constexpr int K3B_TILE = 64;                     // SA records per tile (pieces are then spread over all threads)
-static constexpr int K3B_CTAS = 6;                      // CTAs per SM: 30 KB of shared memory and 48 registers x 192 threads each
+static constexpr int K3B_CTAS = 7;                      // CTAs per SM: 30 KB of shared memory and 48 registers x 192 threads each
 static constexpr uint32_t K3B_STAGE_BYTES = 12 * 1024;
 static constexpr uint32_t K3B_SEMI = 8;                // ';' positions kept per record by phase 1; more -> phase 1b rescans
 static constexpr uint32_t K3B_MAXP = 320;              // segments (records + SA pieces) per tile in the staged layout

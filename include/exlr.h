@@ -187,7 +187,8 @@ typedef struct exlr_batch exlr_batch;
 #define EXLR_OPT_VERBOSE_TEXT 11  /* 1 = BAM batches (exlr_bam_batch_alloc) allocated from now on format the -v columns on the device too
                                      (tag, read name, strand, flag: utils.rs:205-223, 252-267) -- there the read names are on the device */
 
-#define EXLR_OPT_K3_FOLD 12       /* 1 (default) = in batches of short CIGARs kernel 3b does kernel 3a's work itself; 0 = kernel 3a always runs */
+#define EXLR_OPT_K3_FOLD 12       /* 1 = in batches of short CIGARs kernel 3b does kernel 3a's work itself (one launch less; measured slower than the
+                                     two kernels -- 53 vs 17 + 31 us on configs[1] -- so the default is 0: kernel 3a always runs) */
 
 #define EXLR_OPT_GRAPH 13         /* 1 (default) = a batch submitted with the same shape again and again runs its kernels as one CUDA graph launch */
 

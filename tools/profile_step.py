@@ -16,6 +16,7 @@ ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--cigar-kernel", type=int, default=0)
 ap.add_argument("--overlap", type=int, default=0)
+ap.add_argument("--graph", type=int, default=1)
 a = ap.parse_args()
 c = synth.CONFIGS[a.config]
 hb = synth.config(a.config, a.scale)
@@ -23,6 +24,7 @@ ex = api.Extractor(ExlrParams.make(**c["params"]), hb.ref_names, 0)
 ex.set_option(api.EXLR_OPT_CIGAR_KERNEL, a.cigar_kernel)
 ex.set_option(api.EXLR_OPT_OVERLAP, a.overlap)
 ex.set_option(api.EXLR_OPT_STAGE_TIMING, 0)
+ex.set_option(api.EXLR_OPT_GRAPH, a.graph)
 b = ex.batch_for(hb)
 b.upload()
 flush = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")
