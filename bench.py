@@ -409,6 +409,7 @@ def main():
     ap.add_argument("--strong-scale", type=float, default=1.0, help="scale of configs[4] in the strong_c5 block")
     ap.add_argument("--no-e2e-bam", action="store_true", help="skip the e2e_bam block (BAM file -> event file through the CLI, N = 1)")
     ap.add_argument("--bam-scale", type=float, default=0.03, help="molecules of configs[1] in the e2e_bam BAM (0.03 -> ~31k records, ~580 MB)")
+    ap.add_argument("--wc-input", action="store_true", help="write-combined pinned input views (A/B for the e2e figure)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of every step directly (default: repeated shapes replay a CUDA graph)")
     ap.add_argument("--no-overlap", action="store_true", help="run kernel 1 on the same stream as the SA branch")
     ap.add_argument("--k1-ctas", type=int, default=0, help="persistent CTAs of kernel 1 per SM (1..4)")
@@ -440,6 +441,8 @@ def main():
         ex_opts.append((api.EXLR_OPT_OVERLAP, 0))
     if args.no_graph:
         ex_opts.append((api.EXLR_OPT_GRAPH, 0))
+    if args.wc_input:
+        ex_opts.append((api.EXLR_OPT_WC_INPUT, 1))
     if args.k1_ctas:
         ex_opts.append((api.EXLR_OPT_K1_CTAS_PER_SM, args.k1_ctas))
     if args.k1_waves:

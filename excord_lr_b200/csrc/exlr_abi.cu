@@ -50,6 +50,7 @@ struct exlr_ctx {
     std::atomic<int> skip_screen{0};           // auto mode: batches left to run without the screen pass (the last screened one was event-dense);
                                                // written by whoever waits a batch, read by whoever submits the next (two threads in the CLI)
     std::atomic<uint64_t> ev_hint{0}, text_hint{0};   // events / text bytes of the last waited batch: how much exlr_submit copies back speculatively
+    int wc_input = 0;                          // EXLR_OPT_WC_INPUT: pinned input views allocated write-combined
     int graph = 1;                             // EXLR_OPT_GRAPH: repeated shapes run as one CUDA graph launch
     int k3_fold = 0;                           // EXLR_OPT_K3_FOLD: 1 = kernel 3b does kernel 3a's work itself in batches of short CIGARs (measured slower: off)
     cudaEvent_t ev_origin = nullptr;           // recorded at exlr_create: the context's clock for exlr_bam_info.t_ms
@@ -286,6 +287,7 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
     case EXLR_OPT_VERBOSE_TEXT: c->verbose_text = value != 0; return EXLR_OK;
     case EXLR_OPT_K3_FOLD: c->k3_fold = value != 0; return EXLR_OK;
     case EXLR_OPT_GRAPH: c->graph = value != 0; return EXLR_OK;
+    case EXLR_OPT_WC_INPUT: c->wc_input = value != 0; return EXLR_OK;
     case EXLR_OPT_LONG_RECORDS: if (value < 0 || value > 3) return EXLR_ERR_ARG; c->long_records = (int)value; return EXLR_OK;
     case EXLR_OPT_K1A_CTAS_PER_SM: if (value < 1 || value > 8) return EXLR_ERR_ARG; c->k1a_ctas = (int)value; return EXLR_OK;
     case EXLR_OPT_TRACE: if (value < 0 || value > 7) return EXLR_ERR_ARG; c->trace = (int)value; return EXLR_OK;
@@ -336,7 +338,9 @@ static int batch_alloc_impl(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, u
     cudaError_t e = cudaSuccess;
     b->hv.max_reads = max_reads; b->hv.max_ops = max_ops; b->hv.max_sa_bytes = max_sa_bytes; b->hv.max_events = max_events;
     if (host_inputs) {                         // (a BAM batch gets its records from the device-side decoder: no pinned input views)
-        e = cudaHostAlloc(&b->h_slab, ho, cudaHostAllocDefault);
+        // (write-combined: the host only ever writes these views front to back; EXLR_OPT_WC_INPUT, off by default -- the host formatter
+        // and check_sizes read a few words of them back, which is slow on write-combined memory but rare)
+        e = cudaHostAlloc(&b->h_slab, ho, c->wc_input ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
         if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostAlloc(inputs)"); }
         char* hs = (char*)b->h_slab;
         b->hv.cigar = (uint32_t*)(hs + h_cigar); b->hv.cigar_off = (uint64_t*)(hs + h_coff); b->hv.pos = (int32_t*)(hs + h_pos);

@@ -1009,7 +1009,7 @@ void launch_k1c(const DevBatch& B, const DevParams& P, cudaStream_t st)
 // kernel 1d: one warp per listed long record, one resident wave
 void launch_k1d(const DevBatch& B, const DevParams& P, cudaStream_t st)
 {
-    const uint32_t grid = min((B.n_reads + 7u) / 8u, (uint32_t)B.hc.sms * 8u);
+    const uint32_t grid = min((B.n_reads + 7u) / 8u, (uint32_t)B.hc.sms * EXLR_RESIDENT_PER_SM(k1d_long, 256, 0));
     launch_dependent(k1d_long, grid ? grid : 1u, 256u, 0, st, B, P);
 }
 
@@ -1031,9 +1031,9 @@ void launch_k1b(const DevBatch& B, const DevParams& P, unsigned long long n_ops,
 {
     // the numbers of flagged steps and of claimed records live on the device: one resident wave strides over each list
     const uint32_t steps = k1a_steps(n_ops);
-    const uint32_t g1 = min((steps + K1B_THREADS / 32 - 1) / (K1B_THREADS / 32), (uint32_t)B.hc.sms * 8u);
+    const uint32_t g1 = min((steps + K1B_THREADS / 32 - 1) / (K1B_THREADS / 32), (uint32_t)B.hc.sms * EXLR_RESIDENT_PER_SM(k1b_claim, K1B_THREADS, 0));
     launch_dependent(k1b_claim, g1 ? g1 : 1u, K1B_THREADS, 0, st, B, P, n_ops, use_k1c ? 1u : 0u);
-    const uint32_t g2 = min((B.n_reads + K1B_THREADS - 1) / K1B_THREADS, (uint32_t)B.hc.sms * 8u);
+    const uint32_t g2 = min((B.n_reads + K1B_THREADS - 1) / K1B_THREADS, (uint32_t)B.hc.sms * EXLR_RESIDENT_PER_SM(k1b_walk, K1B_THREADS, 0));
     launch_dependent(k1b_walk, g2 ? g2 : 1u, K1B_THREADS, 0, st, B, P);
 }
 

@@ -368,7 +368,7 @@ __device__ __forceinline__ void k4b_indel(const DevBatch& B, const RawEv* src)
 // is one resident wave striding over the largest of the three ranges (measured: a grid sized for the worst case launched
 // 7-9k CTAs, most of them empty, and the launch alone took ~15 us).
 template <bool FAR>
-__global__ void __launch_bounds__(256, FAR ? 6 : 1) k4b_place(DevBatch B, DevParams P)
+__global__ void __launch_bounds__(256, 6) k4b_place(DevBatch B, DevParams P)
 {
     griddep_wait();                                    // kernel 4a's line offsets
     griddep_launch();
@@ -620,7 +620,8 @@ void launch_k4b(const DevBatch& B, const DevParams& P, bool far, cudaStream_t st
     uint32_t n = B.prim_slots > B.n_reads ? B.prim_slots : B.n_reads;
     const uint32_t room = B.raw_cap - B.prim_slots;
     if (room > n) n = room;
-    const uint32_t grid = min((n + 255u) / 256u, (uint32_t)B.hc.sms * 8u);
+    const uint32_t per_sm = far ? EXLR_RESIDENT_PER_SM(k4b_place<true>, 256, 0) : EXLR_RESIDENT_PER_SM(k4b_place<false>, 256, 0);
+    const uint32_t grid = min((n + 255u) / 256u, (uint32_t)B.hc.sms * per_sm);
     if (far) launch_dependent(k4b_place<true>, grid ? grid : 1u, 256, 0, st, B, P);
     else launch_dependent(k4b_place<false>, grid ? grid : 1u, 256, 0, st, B, P);
 }
@@ -632,9 +633,9 @@ uint32_t text_scan_tiles(uint32_t max_events) { return (max_events + SCAN_THREAD
 void launch_k5(const DevBatch& B, cudaStream_t st)
 {
     // the line count lives on the device: both kernels are one resident wave (5a draws its tiles from a ticket)
-    const uint32_t ga = min((B.max_events + SCAN_THREADS - 1) / SCAN_THREADS, (uint32_t)B.hc.sms * 8u);
+    const uint32_t ga = min((B.max_events + SCAN_THREADS - 1) / SCAN_THREADS, (uint32_t)B.hc.sms * EXLR_RESIDENT_PER_SM(k5a_line_bytes, SCAN_THREADS, 0));
     launch_dependent(k5a_line_bytes, ga ? ga : 1u, SCAN_THREADS, 0, st, B);
-    const uint32_t gb = min((B.max_events + 255u) / 256u, (uint32_t)B.hc.sms * 8u);
+    const uint32_t gb = min((B.max_events + 255u) / 256u, (uint32_t)B.hc.sms * EXLR_RESIDENT_PER_SM(k5b_format, 256, 0));
     launch_dependent(k5b_format, gb ? gb : 1u, 256, 0, st, B);
 }
 

@@ -549,10 +549,14 @@ struct __align__(16) K3bSmem {
     uint32_t rerr[K3B_TILE];
     uint32_t semi[K3B_TILE][K3B_SEMI];                 // positions of the first ';' of every record (phase 1 -> 1b)
     uint32_t wsum[K3B_THREADS / 32];
-    uint32_t rrec[K3B_TILE], rslot[K3B_TILE];          // the tile's records and their first segment slot (FOLD: the piece threads walk their CIGARs)
     uint8_t pread[K3B_MAXP];
-    uint8_t rlong[K3B_TILE];                           // FOLD: the record's CIGAR is long, a whole warp walks it
-    SaSum sum[K3B_TILE];                               // FOLD: what kernel 3a would have left in sa_sum, per record of the tile
+};
+// FOLD only (kept out of the plain layout: 2.6 KB more per CTA cost kernel 3b its seventh CTA per SM, and a grid sized for seven
+// then ran a second, nearly empty wave -- 1.03 ms instead of 0.61 ms on configs[3])
+struct __align__(16) K3bFoldSmem {
+    SaSum sum[K3B_TILE];                               // what kernel 3a would have left in sa_sum, per record of the tile
+    uint32_t rrec[K3B_TILE];                           // the tile's records
+    uint8_t rlong[K3B_TILE];                           // the record's CIGAR is long: a whole warp walks it
 };
 
 // FOLD: kernel 3a's work is done here (the host folds it in for batches of short CIGARs): the thread that owns a record's slot
@@ -562,6 +566,7 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
 {
     extern __shared__ __align__(16) unsigned char k3b_smem_raw[];
     K3bSmem& S = *reinterpret_cast<K3bSmem*>(k3b_smem_raw);
+    K3bFoldSmem& F = *reinterpret_cast<K3bFoldSmem*>(k3b_smem_raw + sizeof(K3bSmem));     // (only allocated for FOLD)
     griddep_wait();                                    // kernel 3a's summaries (FOLD: kernel 0's list)
     CtaTrace tr(B, 4);
     const uint32_t n_sa = B.ctrl->n_sa;
@@ -595,9 +600,9 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
             const uint32_t pm = __ballot_sync(0xffffffffu, mine && !is_long);
             if (mine && !is_long) {
                 const K3aAcc a = k3a_walk<2>(B, rr, o0, o1, pm & (3u << (lane & ~1u)), lane & ~1u);
-                if ((t & 1u) == 0u) { SaSum sm; sm.S = a.S; sm.H = a.H; sm.refspan = (int64_t)a.D + (int64_t)a.M + (int64_t)a.E + (int64_t)a.X; sm.ffm = (int64_t)a.ffm; sm.pad[0] = sm.pad[1] = 0; S.sum[k] = sm; }
+                if ((t & 1u) == 0u) { SaSum sm; sm.S = a.S; sm.H = a.H; sm.refspan = (int64_t)a.D + (int64_t)a.M + (int64_t)a.E + (int64_t)a.X; sm.ffm = (int64_t)a.ffm; sm.pad[0] = sm.pad[1] = 0; F.sum[k] = sm; }
             }
-            if (mine && (t & 1u) == 0u) { S.rrec[k] = rr; S.rlong[k] = is_long ? 1 : 0; }
+            if (mine && (t & 1u) == 0u) { F.rrec[k] = rr; F.rlong[k] = is_long ? 1 : 0; }
         }
         // phase 1: pieces per record
         uint32_t r = 0, b0 = 0, e0 = 0, slots = 0;
@@ -642,7 +647,7 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
         }
         // phase 1b: piece list
         if (active && !dropped) {
-            S.pb[sb] = 0xffffffffu; S.pread[sb] = (uint8_t)t; S.rslot[t] = sb;   // slot 0 of the record: its own alignment
+            S.pb[sb] = 0xffffffffu; S.pread[sb] = (uint8_t)t;                 // slot 0 of the record: its own alignment
             if (is_str) {
                 uint32_t at = sb + 1, pbeg = b0;
                 auto piece_end = [&](uint32_t i) {
@@ -675,10 +680,10 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
         __syncthreads();
         if (FOLD) {                                                           // the odd long CIGAR of a short-CIGAR batch: a warp each
             for (uint32_t k = w; k < K3B_TILE; k += K3B_THREADS / 32) {
-                if (j0 + k >= j1 || !S.rlong[k]) continue;                    // warp-uniform
-                const uint32_t rr = S.rrec[k];
+                if (j0 + k >= j1 || !F.rlong[k]) continue;                    // warp-uniform
+                const uint32_t rr = F.rrec[k];
                 const K3aAcc a = k3a_walk<32>(B, rr, B.cigar_off[rr], B.cigar_off[rr + 1], 0xffffffffu, 0);
-                if (lane == 0) { SaSum sm; sm.S = a.S; sm.H = a.H; sm.refspan = (int64_t)a.D + (int64_t)a.M + (int64_t)a.E + (int64_t)a.X; sm.ffm = (int64_t)a.ffm; sm.pad[0] = sm.pad[1] = 0; S.sum[k] = sm; }
+                if (lane == 0) { SaSum sm; sm.S = a.S; sm.H = a.H; sm.refspan = (int64_t)a.D + (int64_t)a.M + (int64_t)a.E + (int64_t)a.X; sm.ffm = (int64_t)a.ffm; sm.pad[0] = sm.pad[1] = 0; F.sum[k] = sm; }
             }
             __syncthreads();
         }
@@ -690,7 +695,7 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
             nseg = slots;
             if (err != 0xffffffffu) { report(B.ctrl, r, err & 0xffu); nseg = 0; }
             else if (!FOLD) k3b_record_seg(B, P, j, r, &S.segs[sb]);
-            else { const SaSum sm = S.sum[t]; seg_from_sums(B, P, r, sm.S, sm.H, sm.refspan, sm.ffm, &S.segs[sb]); }
+            else { const SaSum sm = F.sum[t]; seg_from_sums(B, P, r, sm.S, sm.H, sm.refspan, sm.ffm, &S.segs[sb]); }
         }
         k3b_finish(B, P, s, j, active, r, dropped, &S.segs[sb < K3B_MAXP ? sb : 0], nseg);
     }
@@ -700,11 +705,19 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
 // ======================================================================================
 // launchers
 // ======================================================================================
+static int g_k3b_resident[2] = {K3B_CTAS, K3B_CTAS - 1};      // CTAs of kernel 3b that fit an SM at once: plain, FOLD (asked of the runtime below)
+
 cudaError_t configure_sa_kernels()
 {
-    cudaError_t e = cudaFuncSetAttribute(k3b_sa_events<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3bSmem));
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k3b_sa_events<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3bSmem));
+    const int bytes[2] = {(int)sizeof(K3bSmem), (int)(sizeof(K3bSmem) + sizeof(K3bFoldSmem))};
+    cudaError_t e = cudaFuncSetAttribute(k3b_sa_events<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes[0]);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3b_sa_events<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes[1]);
+    int n = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k3b_sa_events<false>, K3B_THREADS, bytes[0]);
+    if (e == cudaSuccess && n > 0) g_k3b_resident[0] = n;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k3b_sa_events<true>, K3B_THREADS, bytes[1]);
+    if (e == cudaSuccess && n > 0) g_k3b_resident[1] = n;
+    return e;
 }
 
 // batches whose CIGARs are short get kernel 3a's work done inside kernel 3b (one launch less on the SA chain)
@@ -714,15 +727,15 @@ void launch_k3a(const DevBatch& B, const DevParams& P, uint32_t mean_ops, cudaSt
 {
     // grid-stride over a device-side count: size for the worst case, cap at one resident wave (spare CTAs cost launch time).
     // Lanes per record by the batch's mean CIGAR length: the more records a warp walks side by side, the fewer waves.
-    const uint32_t cap = (uint32_t)B.hc.sms * 8u;
+    const uint32_t sms = (uint32_t)B.hc.sms;
     if (mean_ops <= 16) {
-        const uint32_t g = min((B.n_reads + 127u) / 128u, cap);
+        const uint32_t g = min((B.n_reads + 127u) / 128u, sms * EXLR_RESIDENT_PER_SM(k3a_sa_cigar<2>, 256, 0));
         launch_dependent(k3a_sa_cigar<2>, g ? g : 1u, 256, 0, st, B, P);
     } else if (mean_ops <= 48) {
-        const uint32_t g = min((B.n_reads + 63u) / 64u, cap);
+        const uint32_t g = min((B.n_reads + 63u) / 64u, sms * EXLR_RESIDENT_PER_SM(k3a_sa_cigar<4>, 256, 0));
         launch_dependent(k3a_sa_cigar<4>, g ? g : 1u, 256, 0, st, B, P);
     } else {
-        const uint32_t g = min((B.n_reads + 31u) / 32u, cap);
+        const uint32_t g = min((B.n_reads + 31u) / 32u, sms * EXLR_RESIDENT_PER_SM(k3a_sa_cigar<8>, 256, 0));
         launch_dependent(k3a_sa_cigar<8>, g ? g : 1u, 256, 0, st, B, P);
     }
 }
@@ -732,8 +745,9 @@ void launch_k3b(const DevBatch& B, const DevParams& P, bool fold, cudaStream_t s
     // tiles of 64 SA records, grid-stride; the SA-record count lives on the device, so the grid is sized from the batch but
     // capped at the CTAs that are resident at once: spare CTAs of an over-sized grid cost a launch slot each just to read the
     // count and leave, and a CTA with a second tile doubles the kernel's span
-    const uint32_t gb = min((B.n_reads + K3B_TILE - 1u) / K3B_TILE, (uint32_t)B.hc.sms * K3B_CTAS);
-    if (fold) launch_dependent(k3b_sa_events<true>, gb ? gb : 1u, K3B_THREADS, sizeof(K3bSmem), st, B, P);
+    // (a grid larger than what is resident at once would run a second wave whose CTAs start when the first ones finish)
+    const uint32_t gb = min((B.n_reads + K3B_TILE - 1u) / K3B_TILE, (uint32_t)B.hc.sms * (uint32_t)g_k3b_resident[fold ? 1 : 0]);
+    if (fold) launch_dependent(k3b_sa_events<true>, gb ? gb : 1u, K3B_THREADS, sizeof(K3bSmem) + sizeof(K3bFoldSmem), st, B, P);
     else launch_dependent(k3b_sa_events<false>, gb ? gb : 1u, K3B_THREADS, sizeof(K3bSmem), st, B, P);
 }
 

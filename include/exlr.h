@@ -192,6 +192,8 @@ typedef struct exlr_batch exlr_batch;
 
 #define EXLR_OPT_GRAPH 13         /* 1 (default) = a batch submitted with the same shape again and again runs its kernels as one CUDA graph launch */
 
+#define EXLR_OPT_WC_INPUT 14      /* 1 = batches allocated from now on get write-combined pinned input views (A/B for multi-GPU H2D; default 0) */
+
 /* ---- lifecycle ---------------------------------------------------------------------- */
 int  exlr_abi_version(void);
 /* Number of CUDA devices with compute capability 10.x; <0 on CUDA error. */

@@ -213,3 +213,43 @@ def test_gpu_bam_decoder_damaged_files(tmp_path):
     r = run(["-b", bam, "-o", out, "-i", "1", "--batch-events", "64", "--stats"])
     want_r, want = _expect(hb, ExlrParams.make(indel_min=1))
     assert r.returncode == 0 and open(out, "rb").read() == want and " (0 re-run" not in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not gpu_available(), reason="needs a B200")
+def test_gpu_bam_decoder_odd_files(tmp_path):
+    # header-only BAM, a header larger than a BGZF block, records several blocks long (ONT-sized SEQ/QUAL), unplaced records
+    from excord_lr_b200.batch import HostBatch
+    import numpy as np
+    out = str(tmp_path / "o.txt")
+    # 1. no records at all
+    hb = synth.config(0, 0.01)
+    empty = hb.slice(0, 0)
+    bam = str(tmp_path / "empty.bam")
+    bamio.write_bam(empty, bam, ref_lens=synth.ref_lens())
+    for extra in ([], ["--host-reader"]):
+        r = run(["-b", bam, "-o", out] + extra)
+        assert r.returncode == 0, r.stderr
+        assert open(out, "rb").read() == b""
+    # 2. 3 000 contigs: the header spans several BGZF blocks and ends inside one
+    names = ["chr%d_random_contig_with_a_long_name_%d" % (i, i * 7919) for i in range(3000)]
+    recs = [dict(tid=i * 37 % 3000, pos=1000 + i, flag=0, mapq=60, cigar="100M60D200M%dS" % (2000 + i),
+                 sa="%s,%d,+,2000S300M,60,1;" % (names[(i * 11) % 3000], 5000 + i), qname="q%d" % i) for i in range(400)]
+    big = pack_records(recs, names)
+    bam = str(tmp_path / "bighdr.bam")
+    bamio.write_bam(big, bam, seq_len=33)
+    want_r, want = _expect(big, ExlrParams.make())
+    assert want_r.status == 0 and len(want) > 10000
+    for extra in ([], ["--chunk-blocks", "5"], ["--host-reader"]):
+        r = run(["-b", bam, "-o", out] + extra)
+        assert r.returncode == 0, r.stderr
+        assert open(out, "rb").read() == want, extra
+    # 3. records of ~300 KB (five BGZF blocks each), chunks smaller than a record's span
+    hb = synth.with_qnames(synth.config(0, 0.01))
+    bam = str(tmp_path / "long.bam")
+    bamio.write_bam(hb, bam, ref_lens=synth.ref_lens(), seq_len=200_000, random_seq=True)
+    want_r, want = _expect(hb, ExlrParams.make(max_pct_overlap=0.8), True)
+    for extra in ([], ["--chunk-blocks", "3"], ["--chunk-blocks", "16", "--max-record-mb", "1"]):
+        r = run(["-b", bam, "-o", out, "-p", "0.8", "-v"] + extra)
+        assert r.returncode == 0, r.stderr
+        assert open(out, "rb").read() == want, extra
