@@ -219,7 +219,7 @@ int main(int argc, char** argv)
     { struct stat st; if (device_bam && stat(cli.bam.c_str(), &st) == 0) file_bytes = (unsigned long long)st.st_size; }
     const unsigned long long chunk_bytes = std::min<unsigned long long>(cli.chunk_mb << 20, file_bytes + 65536) + (1u << 20);
     const uint32_t chunk_blocks = (uint32_t)(cli.chunk_blocks ? cli.chunk_blocks : std::min<unsigned long long>(30000, std::max<unsigned long long>(chunk_bytes / 16384, 64)));
-    const unsigned long long tail_bytes = std::min<unsigned long long>(cli.max_record_mb << 20, (unsigned long long)chunk_blocks * 65536ull);   // the largest record a chunk can inherit
+    const unsigned long long tail_bytes = cli.max_record_mb << 20;      // the longest leftover a chunk can inherit: one record, however many chunks it spans
     const int per_gpu = device_bam ? 4 : 3;
     std::vector<Slot> slots((size_t)ndev * per_gpu);
     std::vector<Gpu> gpus(ndev);
