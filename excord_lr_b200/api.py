@@ -33,6 +33,7 @@ EXLR_OPT_VERBOSE_TEXT = 11
 EXLR_OPT_K3_FOLD = 12
 EXLR_OPT_GRAPH = 13
 EXLR_OPT_WC_INPUT = 14
+EXLR_OPT_K0_WALK = 15
 # see EXLR_OPT_CIGAR_KERNEL in include/exlr.h
 CIGAR_KERNEL_AUTO, CIGAR_KERNEL_WARP, CIGAR_KERNEL_FLAT, CIGAR_KERNEL_SCREEN = 0, 1, 2, 3
 

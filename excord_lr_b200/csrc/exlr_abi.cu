@@ -50,6 +50,7 @@ struct exlr_ctx {
     std::atomic<int> skip_screen{0};           // auto mode: batches left to run without the screen pass (the last screened one was event-dense);
                                                // written by whoever waits a batch, read by whoever submits the next (two threads in the CLI)
     std::atomic<uint64_t> ev_hint{0}, text_hint{0};   // events / text bytes of the last waited batch: how much exlr_submit copies back speculatively
+    int k0_walk = 1;                           // EXLR_OPT_K0_WALK: kernel 0 does kernel 3a's work in batches of short CIGARs
     int wc_input = 0;                          // EXLR_OPT_WC_INPUT: pinned input views allocated write-combined
     int graph = 1;                             // EXLR_OPT_GRAPH: repeated shapes run as one CUDA graph launch
     int k3_fold = 0;                           // EXLR_OPT_K3_FOLD: 1 = kernel 3b does kernel 3a's work itself in batches of short CIGARs (measured slower: off)
@@ -59,13 +60,13 @@ struct exlr_ctx {
 
 // What a submit is going to launch: decided on the host before anything is enqueued (and part of the identity of a captured graph).
 struct StepPlan {
-    bool overlap, screened, long_batch, two_level, fold, far, formatted;
+    bool overlap, screened, long_batch, two_level, fold, k0_walk, far, formatted;
     int variant; uint32_t rpc;
     unsigned long long n_reads, n_ops;
     const void* events;                        // (exlr_batch_grow moves the event buffers: a graph captured before it is stale)
     bool operator==(const StepPlan& o) const
     {
-        return overlap == o.overlap && screened == o.screened && long_batch == o.long_batch && two_level == o.two_level && fold == o.fold &&
+        return overlap == o.overlap && screened == o.screened && long_batch == o.long_batch && two_level == o.two_level && fold == o.fold && k0_walk == o.k0_walk &&
                far == o.far && formatted == o.formatted && variant == o.variant && rpc == o.rpc && n_reads == o.n_reads && n_ops == o.n_ops && events == o.events;
     }
 };
@@ -288,6 +289,7 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
     case EXLR_OPT_K3_FOLD: c->k3_fold = value != 0; return EXLR_OK;
     case EXLR_OPT_GRAPH: c->graph = value != 0; return EXLR_OK;
     case EXLR_OPT_WC_INPUT: c->wc_input = value != 0; return EXLR_OK;
+    case EXLR_OPT_K0_WALK: c->k0_walk = value != 0; return EXLR_OK;
     case EXLR_OPT_LONG_RECORDS: if (value < 0 || value > 3) return EXLR_ERR_ARG; c->long_records = (int)value; return EXLR_OK;
     case EXLR_OPT_K1A_CTAS_PER_SM: if (value < 1 || value > 8) return EXLR_ERR_ARG; c->k1a_ctas = (int)value; return EXLR_OK;
     case EXLR_OPT_TRACE: if (value < 0 || value > 7) return EXLR_ERR_ARG; c->trace = (int)value; return EXLR_OK;
@@ -511,7 +513,8 @@ static void plan_step(exlr_batch* b, StepPlan* p)
         p->two_level = p->long_batch && c->long_records != 2;
     }
     const uint32_t mean_ops = (uint32_t)(b->n_reads ? b->n_ops / b->n_reads : 0);
-    p->fold = k3_fold(mean_ops) && c->k3_fold;                        // short CIGARs: kernel 3b walks the SA records' own CIGARs itself
+    p->fold = k3_fold(mean_ops) && c->k3_fold;                        // short CIGARs: kernel 3b walks the SA records' own CIGARs itself (off by default)
+    p->k0_walk = !p->fold && k3_fold(mean_ops) && c->k0_walk;         // short CIGARs: kernel 0 does, for the records it lists
     p->far = c->far_mode;
     p->formatted = b->dv.text_off != nullptr;
 }
@@ -537,7 +540,7 @@ static int enqueue_step(exlr_batch* b, const StepPlan& p, bool timed)
         plan_k1(d, p.screened ? 1 : p.variant, p.rpc, &n_tiles);         // screened: raw events all go to the atomically allocated region
         if (p.overlap) CK(cudaEventRecord(b->ev_fork, st));               // after the memset
     }
-    launch_k0(d, c->dparams, st); b->launches++;
+    launch_k0(d, c->dparams, p.k0_walk, st); b->launches++;
     if (timed) CK(cudaEventRecord(b->ev[EV_K0], st));
     if (!c->params.split_only) {
         cudaStream_t s1 = p.overlap ? b->stream2 : st;
@@ -554,7 +557,7 @@ static int enqueue_step(exlr_batch* b, const StepPlan& p, bool timed)
         CK(cudaEventRecord(b->ev_k1_end, s1));
     }
     if (timed) CK(cudaEventRecord(b->ev[EV_K1], st));
-    if (!p.fold) { launch_k3a(d, c->dparams, (uint32_t)(b->n_reads ? b->n_ops / b->n_reads : 0), st); b->launches++; }
+    if (!p.fold && !p.k0_walk) { launch_k3a(d, c->dparams, (uint32_t)(b->n_reads ? b->n_ops / b->n_reads : 0), st); b->launches++; }
     if (timed) CK(cudaEventRecord(b->ev[EV_K3A], st));
     launch_k3b(d, c->dparams, p.fold, st); b->launches++;
     if (timed) CK(cudaEventRecord(b->ev[EV_K3B], st));

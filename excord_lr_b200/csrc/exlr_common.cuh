@@ -47,6 +47,33 @@ __device__ __forceinline__ void store_event(exlr_event* dst, int64_t ls, int64_t
     d[2] = make_uint4(read, lc, rc, meta);
 }
 
+// Kernel 3a's work for one record by one thread: per-op-type wrapping sums of the record's own CIGAR (main.rs:243-296), reference
+// span D + M + = + X (split_read_event.rs:23-28), first-match offset (utils.rs:12-42).  For batches of short CIGARs, where kernel 0
+// does this for the few SA records it lists instead of a launch of its own.
+__device__ __forceinline__ void sa_cigar_sums_serial(const DevBatch& B, uint32_t r, SaSum* out)
+{
+    const unsigned long long o0 = B.cigar_off[r], o1 = B.cigar_off[r + 1];
+    uint32_t sS = 0, sH = 0, sD = 0, sM = 0, sE = 0, sX = 0, bad = 0;
+    unsigned long long ffm = 0; bool seenM = false;
+    for (unsigned long long o = o0; o < o1; o += 8) {
+        uint32_t vv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) vv[u] = o + u < o1 ? __ldg(B.cigar + o + u) : 0xfu;       // 0xf: not an op
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t v = vv[u], op = v & 15u, len = v >> 4;
+            if (o + u < o1 && op > 8u) bad = 1;                                               // rust-htslib panics on an unknown op (main.rs:243)
+            sM += op == 0u ? len : 0u; sD += op == 2u ? len : 0u; sS += op == 4u ? len : 0u;
+            sH += op == 5u ? len : 0u; sE += op == 7u ? len : 0u; sX += op == 8u ? len : 0u;
+            if (op == 0u) seenM = true;                                                       // utils.rs:28-29 stops at the first M
+            if (!seenM && (op == 4u || op == 1u || op == 8u || op == 7u)) ffm += len;         // S I X =  (utils.rs:33)
+        }
+    }
+    if (bad) report(B.ctrl, r, RANK_CIGAR_OP);
+    out->S = sS; out->H = sH; out->refspan = (int64_t)sD + (int64_t)sM + (int64_t)sE + (int64_t)sX; out->ffm = (int64_t)ffm;
+    out->pad[0] = out->pad[1] = 0;
+}
+
 // EXLR_OPT_TRACE for the small kernels: {CTA start, a mid point, CTA end} by thread 0, entry blockIdx.x (mod 8192).
 // EXLR_OPT_TRACE = 7 is the timeline mode: every kernel folds its CTAs' start / end into entry `id` with atomicMin / atomicMax
 // ({~first CTA start, last CTA end, -, CTAs}; the buffer is zeroed per submit), which shows the gaps and overlaps of a whole step

@@ -186,7 +186,7 @@ size_t k1_flat_smem_bytes();
 uint32_t scan_tiles(uint32_t n_reads);
 uint32_t text_scan_tiles(uint32_t max_events);
 void launch_k5(const DevBatch& B, cudaStream_t st);
-void launch_k0(const DevBatch& B, const DevParams& P, cudaStream_t st);
+void launch_k0(const DevBatch& B, const DevParams& P, bool walk, cudaStream_t st);
 void plan_k1(DevBatch& B, int variant, uint32_t rpc, uint32_t* tiles_out);
 void launch_k1(const DevBatch& B, const DevParams& P, int variant, uint32_t rpc, cudaStream_t st);
 uint32_t k1a_steps(unsigned long long n_ops);

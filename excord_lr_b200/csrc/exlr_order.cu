@@ -15,6 +15,9 @@ namespace exlr {
 // ======================================================================================
 // kernel 0: filter + tid check + ordered SA-record list
 // ======================================================================================
+// WALK: batches of short CIGARs -- the thread that lists an SA record also walks its CIGAR (kernel 3a's work: 5 % of the records,
+// ~30 ops each), which takes kernel 3a's launch off the SA chain.
+template <bool WALK>
 __global__ void __launch_bounds__(SCAN_THREADS) k0_classify(DevBatch B, DevParams P)
 {
     __shared__ uint32_t s_tile, s_warp[16];
@@ -68,11 +71,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) k0_classify(DevBatch B, DevParam
     uint32_t grand;
     tr.mid();
     uint32_t at = tile_excl_scan(B.scan_a, tile, (uint32_t)__popc(sa_mask), s_warp, &grand);
+    const uint32_t at0 = at, listed = sa_mask;
     while (sa_mask) { const int i = __ffs(sa_mask) - 1; sa_mask &= sa_mask - 1; B.sa_list[at++] = r0 + i; }
     // kept counter: one atomic per warp
     for (int d = 16; d; d >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, d);
     if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&B.ctrl->n_kept, kept);
     if (threadIdx.x == 0 && tile == (n + SCAN_TILE - 1) / SCAN_TILE - 1) B.ctrl->n_sa = grand;
+    if (WALK) {
+        uint32_t j = at0;
+        for (uint32_t m = listed; m; m &= m - 1u) { SaSum sm; sa_cigar_sums_serial(B, r0 + (uint32_t)(__ffs((int)m) - 1), &sm); B.sa_sum[j++] = sm; }
+    }
     tr.end();
 }
 
@@ -587,10 +595,11 @@ cudaError_t configure_kernels(int device, int* sm_count_out)
     return configure_sa_kernels();
 }
 
-void launch_k0(const DevBatch& B, const DevParams& P, cudaStream_t st)
+void launch_k0(const DevBatch& B, const DevParams& P, bool walk, cudaStream_t st)
 {
     const uint32_t tiles = (B.n_reads + SCAN_TILE - 1) / SCAN_TILE;
-    k0_classify<<<tiles, SCAN_THREADS, 0, st>>>(B, P);
+    if (walk) k0_classify<true><<<tiles, SCAN_THREADS, 0, st>>>(B, P);
+    else k0_classify<false><<<tiles, SCAN_THREADS, 0, st>>>(B, P);
 }
 
 void launch_k4a(const DevBatch& B, const DevParams& P, bool far, cudaStream_t st)

@@ -121,21 +121,22 @@ def test_long_record_paths_behind_the_screen(long_records):
 
 
 def test_folded_sa_cigar_walk_and_graph_replay():
-    # EXLR_OPT_K3_FOLD: kernel 3b walks the SA records' own CIGARs itself (a pair of lanes each, a warp for the odd long one);
+    # EXLR_OPT_K0_WALK / EXLR_OPT_K3_FOLD: kernel 0 or kernel 3b does kernel 3a's work (the SA records' own CIGARs);
     # EXLR_OPT_GRAPH: the third submit of the same shape replays a CUDA graph -- both must leave every byte as it was
     for seed, n in ((21, 700), (22, 300)):
         hb = rand_batch(seed, n)
         p = rand_params(seed)
         want = oracle_c.run(hb, p)
-        for fold, graph in ((1, 1), (1, 0), (0, 1)):
+        for fold, graph, k0w in ((1, 1, 1), (1, 0, 0), (0, 1, 1), (0, 1, 0), (0, 0, 1)):
             ex = api.Extractor(p, hb.ref_names)
             ex.set_option(api.EXLR_OPT_K3_FOLD, fold)
             ex.set_option(api.EXLR_OPT_GRAPH, graph)
+            ex.set_option(api.EXLR_OPT_K0_WALK, k0w)
             b = ex.batch_for(hb, 40000)
             for rnd in range(4):
                 b.submit()
                 res = b.wait()
-                check_result(hb, p, res, b.format_lines(res, False, None, 0, res.n_valid_lines()), label=f"fold{fold} graph{graph} round{rnd}")
+                check_result(hb, p, res, b.format_lines(res, False, None, 0, res.n_valid_lines()), label=f"fold{fold} graph{graph} k0walk{k0w} round{rnd}")
             b.upload()
             for rnd in range(4):
                 b.submit_resident()
@@ -280,9 +281,9 @@ def test_batch_reuse_and_two_in_flight():
         check_result(x, p, r1, b1.format_lines(r1, False, None, 0, r1.n_valid_lines()), label=f"reuse{rnd}a")
         check_result(y, p, r2, b2.format_lines(r2, False, None, 0, r2.n_valid_lines()), label=f"reuse{rnd}b")
         t = b1.timing()
-        # kernels 0, 3a, 3b, 4a, 4b (its last CTA stores the result header) + either the screened CIGAR path (1a, 1b claim, 1b walk)
-        # or, after an event-dense batch, kernel 1
-        assert t.launches in (6, 8) and t.kernels_ms > 0 and (t.screen_ms > 0) == (t.launches == 8)
+        # kernels 0 (short CIGARs: it does kernel 3a's work too), 3b, 4a, 4b (its last CTA stores the result header) + either the
+        # screened CIGAR path (1a, 1b claim, 1b walk) or, after an event-dense batch, kernel 1
+        assert t.launches in (5, 7) and t.kernels_ms > 0 and (t.screen_ms > 0) == (t.launches == 7)
     # resident path gives the same header
     b1.fill(a); b1.upload(); b1.submit_resident()
     rr = b1.wait_resident()
