@@ -50,7 +50,7 @@ struct exlr_ctx {
     std::atomic<int> skip_screen{0};           // auto mode: batches left to run without the screen pass (the last screened one was event-dense);
                                                // written by whoever waits a batch, read by whoever submits the next (two threads in the CLI)
     std::atomic<uint64_t> ev_hint{0}, text_hint{0};   // events / text bytes of the last waited batch: how much exlr_submit copies back speculatively
-    int k0_walk = 1;                           // EXLR_OPT_K0_WALK: kernel 0 does kernel 3a's work in batches of short CIGARs
+    int k0_walk = 0;                           // EXLR_OPT_K0_WALK: kernel 0 does kernel 3a's work in batches of short CIGARs (measured slower: off)
     int wc_input = 0;                          // EXLR_OPT_WC_INPUT: pinned input views allocated write-combined
     int graph = 1;                             // EXLR_OPT_GRAPH: repeated shapes run as one CUDA graph launch
     int k3_fold = 0;                           // EXLR_OPT_K3_FOLD: 1 = kernel 3b does kernel 3a's work itself in batches of short CIGARs (measured slower: off)

@@ -194,8 +194,9 @@ typedef struct exlr_batch exlr_batch;
 
 #define EXLR_OPT_WC_INPUT 14      /* 1 = batches allocated from now on get write-combined pinned input views (A/B for multi-GPU H2D; default 0) */
 
-#define EXLR_OPT_K0_WALK 15       /* 1 (default) = in batches of short CIGARs kernel 0 walks the CIGARs of the SA records it lists (kernel 3a's work);
-                                     0 = kernel 3a always runs */
+#define EXLR_OPT_K0_WALK 15       /* 1 = in batches of short CIGARs kernel 0 walks the CIGARs of the SA records it lists (kernel 3a's work) -- measured
+                                     slower (SA records cluster, so a few threads walk a dozen CIGARs one after the other: 45 vs 23 + 17 us);
+                                     default 0: kernel 3a always runs */
 
 /* ---- lifecycle ---------------------------------------------------------------------- */
 int  exlr_abi_version(void);
