@@ -106,7 +106,8 @@ struct exlr_batch {
     uint8_t* h_comp = nullptr; exlr_bgzf_block* h_blocks = nullptr; BgzfBlock* h_btab = nullptr; BamCtrl* h_bctrl = nullptr;
     void* d_bam = nullptr; DevBam db{}; BgzfBlock* d_btab = nullptr;
     uint64_t front_u = 0, bam_u_end = 0, bam_origin = 0, bam_info_tail = 0; uint32_t bam_n_new = 0, bam_n_front = 0;
-    cudaEvent_t ev_tail_read = nullptr; bool tail_reader_pending = false;   // the next chunk's copy of this chunk's tail out of U (exlr_bam_walk)
+    cudaEvent_t ev_tail_copied = nullptr;      // recorded on this batch's stream once it has copied the previous chunk's tail out of that batch's U
+    cudaEvent_t tail_reader = nullptr;         // ... and, in that previous batch: the event its next submit has to wait for (it may live on another GPU)
     size_t bam_zero_bytes = 0;                 // BamCtrl + the three scan status arrays (one memset per submit)
     uint64_t max_comp = 0, u_cap = 0; uint32_t max_blocks = 0;
     int bam_state = 0;                         // 0 idle, 1 exlr_bam_submit done, 2 exlr_bam_walk done, 3 exlr_bam_extract done
@@ -313,7 +314,7 @@ void exlr_batch_free(exlr_batch* b)
     if (b->stream2) cudaStreamDestroy(b->stream2);
     if (b->stream) cudaStreamDestroy(b->stream);
     for (auto& e : b->ev_bam) if (e) cudaEventDestroy(e);
-    if (b->ev_tail_read) cudaEventDestroy(b->ev_tail_read);
+    if (b->ev_tail_copied) cudaEventDestroy(b->ev_tail_copied);
     cudaFree(b->d_bam); cudaFreeHost(b->h_comp); cudaFreeHost(b->h_blocks); cudaFreeHost(b->h_btab); cudaFreeHost(b->h_bctrl);
     if (b->gexec) cudaGraphExecDestroy(b->gexec);
     cudaFree(b->d_slab); cudaFree(b->d_evslab);
@@ -846,7 +847,7 @@ int exlr_bam_batch_alloc(exlr_ctx* c, uint64_t max_comp_bytes, uint32_t max_bloc
     D.max_reads = (uint32_t)R; D.n_ref = c->n_ref;
     e = cudaHostGetDevicePointer((void**)&D.host_ctrl, b->h_bctrl, 0);
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&b->ev_bam[i]);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_tail_read, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_tail_copied, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMemset(D.U, 0, u_cap + 256);
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "BAM chunk setup"); }
     *out = b;
@@ -881,7 +882,7 @@ int exlr_bam_submit(exlr_batch* b, uint64_t comp_bytes, uint32_t n_blocks)
     DevBam& D = b->db;
     b->bam_n_new = n_blocks; b->bam_u_end = u;
     b->bam_comp_bytes = comp_bytes; b->submitted = false; b->have_timing = false;
-    if (b->tail_reader_pending) { CK(cudaStreamWaitEvent(st, b->ev_tail_read, 0)); b->tail_reader_pending = false; }   // the next chunk still copies this one's old tail
+    if (b->tail_reader) { CK(cudaStreamWaitEvent(st, b->tail_reader, 0)); b->tail_reader = nullptr; }   // the next chunk may still be copying this one's old tail
     CK(cudaEventRecord(b->ev_bam[0], st));
     CK(cudaMemsetAsync(D.ctrl, 0, b->bam_zero_bytes, st));
     if (comp_bytes) CK(cudaMemcpyAsync((void*)D.comp, b->h_comp, comp_bytes, cudaMemcpyHostToDevice, st));
@@ -911,8 +912,8 @@ int exlr_bam_walk(exlr_batch* b, exlr_batch* prev, uint64_t start_off)
         if (tail) {
             if (prev->ctx->device == b->ctx->device) CK(cudaMemcpyAsync(D.U + b->front_u - tail, prev->db.U + p_tail, tail, cudaMemcpyDeviceToDevice, st));
             else CK(cudaMemcpyPeerAsync(D.U + b->front_u - tail, b->ctx->device, prev->db.U + p_tail, prev->ctx->device, tail, st));
-            CK(cudaEventRecord(prev->ev_tail_read, st));
-            prev->tail_reader_pending = true;
+            CK(cudaEventRecord(b->ev_tail_copied, st));        // (an event of this batch's device; prev's stream can wait for it across devices)
+            prev->tail_reader = b->ev_tail_copied;
         }
     }
     if (start_off > tail + (b->bam_u_end - b->front_u)) return EXLR_ERR_ARG;
