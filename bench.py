@@ -285,7 +285,7 @@ def kernel_table(hb, p, solo, cnt, n_events, peak, traffic):
     rows += [("k3a_sa_cigar", solo["sa_cigar_ms"], 4 * sa_ops + 12 * S + 32 * S, "4 B/op of the SA records' own CIGARs, 32 B summary written"),
              ("k3b_sa_events", solo["sa_parse_ms"], A + 32 * S + 16 * S + 48 * sa_ev, "SA bytes + 32 B summary + 16 B/record read, 48 B/line written"),
              ("k4a_line_scan", solo["scan_ms"], 4 * R + R // 8 + 8 * claimed + 4 * R, "4 B/record + claim bit + 8 B/claimed record read, 4 B/record written"),
-             ("k4b_place(+k5a,k5b)+k6_header", solo["place_ms"], 32 * raw + 48 * sa_ev + 48 * E + 128, "raw + SA events read, 48 B/line written")]
+             ("k4b_place", solo["place_ms"], 32 * raw + 48 * sa_ev + 48 * E + 128, "raw + SA events read, 48 B/line written; its last CTA stores the 128-byte result header")]
     out = []
     for name, ms, b, what in rows:
         if ms <= 0:

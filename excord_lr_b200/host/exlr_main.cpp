@@ -471,10 +471,10 @@ int main(int argc, char** argv)
     if (cli.stats)
         fprintf(stderr, "excord-lr-b200: %llu records, %llu lines, %llu batches (%llu re-run with larger event buffers) on %d of %d GPU(s); setup (CUDA context, "
                 "pinned + device buffers of the first GPU, BAM header) %.3f s; "
-                "stream %.3f s (writer thread: waiting for the GPU %.3f s, formatting %.3f s, writing %.3f s; the reader thread inflates, parses and packs "
+                "stream %.3f s (writer thread: waiting for the GPU %.3f s, formatting %.3f s, writing %.3f s; the reader thread %s "
                 "for the whole stream)\n",
                 (unsigned long long)n_rec, (unsigned long long)n_lines, (unsigned long long)n_batches, (unsigned long long)n_regrown, n_used, ndev, t_setup,
-                secs(clk::now() - t_begin), t_wait, t_format, t_write);
+                secs(clk::now() - t_begin), t_wait, t_format, t_write, device_bam ? "reads the file and drives the GPU decoder" : "inflates, parses and packs");
     for (auto& s : slots) if (s.b) exlr_batch_free(s.b);
     for (auto& g : gpus) if (g.ctx) exlr_destroy(g.ctx);
     return fatal;
