@@ -501,6 +501,7 @@ def main():
     # ---------------- reduce over ranks ----------------
     total_ms_max, e2e_ms_max, k1_ms_max, k1a_ms_max = D.reduce([total_ms, e2e_s * 1e3, float(np.sum(k1_ms)), float(np.sum(k1a_ms))], "max")
     R_all, C_all, E_all, pcie_sum, h2d_all = D.reduce([R, Cops, n_events, pcie_together, h2d], "sum")
+    pcie_slowest, = D.reduce([pcie_together], "min")
 
     # ---------------- cpu baseline (rank 0, N=1 only) ----------------
     cpu = None
@@ -571,6 +572,9 @@ def main():
                     "pcie_h2d_peak_gbs_all_ranks_copying": pcie_together, "pcie_h2d_box_aggregate_gbs": pcie_sum,
                     "frac_of_pcie": h2d_rate / pcie_alone if pcie_alone else None,
                     "frac_of_box_aggregate": (h2d_all * args.steps / (e2e_ms_max / 1e3) / 1e9) / pcie_sum if pcie_sum else None,
+                    # the e2e time is the slowest rank's: its own ceiling is what that rank's copies reach while all ranks copy
+                    "pcie_h2d_slowest_rank_gbs_all_ranks_copying": pcie_slowest,
+                    "frac_of_slowest_rank_ceiling": h2d_rate / pcie_slowest if pcie_slowest else None,
                     "cigar_ops_per_sec": C_all / (e2e_ms_max / 1e3) * args.steps,
                     "note": "the packer is outside the timed region (the pinned views are pre-filled); every step's inputs cross PCIe and every result is read back"},
             "gpu_launches": int(launches),
