@@ -137,6 +137,8 @@ def load_library() -> C.CDLL:
     lib.exlr_bam_walk.argtypes = [vp, vp, u64]
     lib.exlr_bam_extract.argtypes = [vp, C.POINTER(BamInfo)]
     lib.exlr_bam_download.argtypes = [vp, C.POINTER(_Views), vp, u64, vp]
+    lib.exlr_bam_download_stream.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    lib.exlr_bam_download_stream.restype = i32
     for f in ("exlr_bam_batch_alloc", "exlr_bam_get_views", "exlr_bam_submit", "exlr_bam_walk", "exlr_bam_extract", "exlr_bam_download"):
         getattr(lib, f).restype = i32
     lib.exlr_format_lines.restype = C.c_int64
@@ -376,6 +378,14 @@ class BamBatch(DeviceBatch):
             _check(rc)
         self.n_reads = int(info.n_reads)
         return info
+
+    def inflated(self) -> bytes:
+        """The chunk's inflated byte stream (raises ExlrError -7 if a block did not inflate)."""
+        n = C.c_uint64()
+        _check(self.lib.exlr_bam_download_stream(self.handle, None, 0, C.byref(n)))
+        buf = np.zeros(max(1, n.value), np.uint8)
+        _check(self.lib.exlr_bam_download_stream(self.handle, buf.ctypes.data, buf.size, C.byref(n)))
+        return buf[:n.value].tobytes()
 
     def download(self, ref_names, max_reads, max_ops, max_sa) -> HostBatch:
         """The decoded records as a HostBatch (for comparison with what the host reader packs)."""

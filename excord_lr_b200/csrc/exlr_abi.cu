@@ -979,6 +979,23 @@ int exlr_bam_extract(exlr_batch* b, exlr_bam_info* info)
     return info->status;
 }
 
+int exlr_bam_download_stream(exlr_batch* b, uint8_t* dst, uint64_t cap, uint64_t* n_bytes)
+{
+    if (!b || !n_bytes || !b->is_bam) return EXLR_ERR_ARG;
+    if (b->bam_state < 1) return EXLR_ERR_STATE;
+    CK(cudaSetDevice(b->ctx->device));
+    CK(cudaStreamSynchronize(b->stream));
+    // state 1: the chunk's own inflated bytes; after exlr_bam_walk also the previous chunk's leftover in front of them
+    const uint64_t from = b->bam_state >= 2 ? b->bam_origin : b->front_u, n = b->bam_u_end - from;
+    *n_bytes = n;
+    BamCtrl c;
+    CK(cudaMemcpy(&c, b->db.ctrl, sizeof c, cudaMemcpyDeviceToHost));
+    if (c.bad_block) return EXLR_ERR_BGZF;
+    if (!dst || n > cap) return n > cap ? EXLR_ERR_CAPACITY : EXLR_OK;
+    if (n) CK(cudaMemcpy(dst, b->db.U + from, n, cudaMemcpyDeviceToHost));
+    return EXLR_OK;
+}
+
 int exlr_bam_download(exlr_batch* b, const exlr_batch_views* out, char* qnames, uint64_t qnames_cap, uint32_t* qname_off)
 {
     if (!b || !out || !b->is_bam) return EXLR_ERR_ARG;

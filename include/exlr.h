@@ -310,6 +310,9 @@ int  exlr_bam_extract(exlr_batch* b, exlr_bam_info* info);
 /* Inspection / tests: copies the decoded structure-of-arrays batch of the last walked chunk into caller memory (`out` holds
  * caller-allocated arrays and their capacities; qnames / qname_off may be NULL). */
 int  exlr_bam_download(exlr_batch* b, const exlr_batch_views* out, char* qnames, uint64_t qnames_cap, uint32_t* qname_off);
+/* Inspection / tests: the inflated byte stream of the chunk (after exlr_bam_walk: with the previous chunk's leftover in front).
+ * *n_bytes = its length; EXLR_ERR_BGZF if a block did not inflate; dst may be NULL to ask for the length only. */
+int  exlr_bam_download_stream(exlr_batch* b, uint8_t* dst, uint64_t cap, uint64_t* n_bytes);
 
 /* ---- host formatter: utils.rs:196-283 ------------------------------------------------- */
 /* Writes the lines of events [ev_begin, ev_end) of `res` into out (capacity out_cap) and

@@ -186,3 +186,70 @@ def test_records_spanning_blocks_and_chunks(tmp_path, per_chunk, seq_len, block)
     for b in batches:
         b.free()
     ex.close()
+
+
+def _bgzf(payloads):
+    """BGZF blocks around ready-made raw DEFLATE streams: [(deflate bytes, uncompressed bytes)] -> file bytes."""
+    out = b""
+    for comp, raw in payloads:
+        out += (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25) + comp +
+                struct.pack("<II", zlib.crc32(raw) & 0xFFFFFFFF, len(raw)))
+    return out
+
+
+def test_inflate_against_zlib_on_every_kind_of_deflate_stream():
+    # the DEFLATE kernel alone, on streams no BAM writer would bother to produce: every zlib strategy and level, fixed Huffman
+    # codes, RLE (distance 1), Huffman-only, stored blocks, sync-flushed streams (empty stored blocks between deflate blocks),
+    # maximal matches at maximal distance, incompressible bytes, a single byte, 15-bit codes from a skewed alphabet
+    rng = np.random.default_rng(12)
+    text = (b"chr2,9877576,+,51421S1538M14S,60,191;" * 700)[:60000]
+    skew = bytes(rng.choice(256, 65000, p=np.r_[[0.5, 0.25, 0.125], np.full(253, 0.125 / 253)]).astype(np.uint8))
+    far = bytes(rng.integers(0, 256, 300, dtype=np.uint8)) + bytes(32600) + bytes(rng.integers(0, 256, 300, dtype=np.uint8))
+    far = (far[:300] + bytes(32468) + far[:300] + far[:258] * 3)[:65536]
+    datas = [text, skew, far, bytes(rng.integers(0, 256, 65536, dtype=np.uint8)), b"\x00" * 65536, b"ab" * 32768, b"x",
+             bytes(rng.integers(65, 69, 65536, dtype=np.uint8)), bytes(rng.integers(0, 256, 7, dtype=np.uint8)) * 9000]
+    payloads = []
+    for raw in datas:
+        for level, strategy in ((1, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY), (0, zlib.Z_DEFAULT_STRATEGY),
+                                (6, zlib.Z_FIXED), (6, zlib.Z_RLE), (6, zlib.Z_HUFFMAN_ONLY), (9, zlib.Z_FILTERED)):
+            co = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+            payloads.append((co.compress(raw) + co.flush(), raw))
+        # several deflate blocks per BGZF block, separated by sync / full flushes (each leaves an empty stored block)
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        comp = b""
+        for k in range(0, len(raw), 9000):
+            comp += co.compress(raw[k:k + 9000]) + co.flush(zlib.Z_SYNC_FLUSH if (k // 9000) % 2 else zlib.Z_FULL_FLUSH)
+        payloads.append((comp + co.flush(), raw))
+    payloads = [p for p in payloads if len(p[0]) < 65000]
+    data = _bgzf(payloads)
+    blocks, used = api.bgzf_blocks(data)
+    assert used == len(data) and len(blocks) == len(payloads)
+    ex = api.Extractor(ExlrParams.make(), REF_NAMES)
+    bb = api.BamBatch(ex, len(data) + 64, len(blocks))
+    bb.load(data, blocks)
+    got = bb.inflated()
+    want = b"".join(p[1] for p in payloads)
+    assert len(got) == len(want)
+    if got != want:
+        at, k = 0, 0
+        for comp, raw in payloads:
+            assert got[at:at + len(raw)] == raw, f"block {k} ({len(raw)} bytes from {len(comp)}) inflated wrong"
+            at, k = at + len(raw), k + 1
+    # and streams that must be refused: a reserved block type, a stored block whose NLEN does not match, an over-subscribed code,
+    # a distance beyond the start of the output, output longer / shorter than ISIZE
+    good = zlib.compressobj(6, zlib.DEFLATED, -15)
+    gz = good.compress(text) + good.flush()
+    bad_streams = [b"\x07" + gz[1:], b"\x01\x05\x00\x00\x00hello", gz[:len(gz) // 2], b"\x03\x02\x00"]
+    for i, comp in enumerate(bad_streams):
+        d = _bgzf([(comp, text)])
+        bl, _ = api.bgzf_blocks(d)
+        bb.load(d, bl)
+        with pytest.raises(api.ExlrError) as e:
+            bb.inflated()
+        assert e.value.status == -7, i
+    d = _bgzf([(gz, text + b"!")]) + _bgzf([(gz, text[:-1])])
+    bl, _ = api.bgzf_blocks(d)
+    bb.load(d, bl)
+    with pytest.raises(api.ExlrError):
+        bb.inflated()
+    bb.free(); ex.close()
