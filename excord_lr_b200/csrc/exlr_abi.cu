@@ -991,7 +991,8 @@ int exlr_bam_download_stream(exlr_batch* b, uint8_t* dst, uint64_t cap, uint64_t
     BamCtrl c;
     CK(cudaMemcpy(&c, b->db.ctrl, sizeof c, cudaMemcpyDeviceToHost));
     if (c.bad_block) return EXLR_ERR_BGZF;
-    if (!dst || n > cap) return n > cap ? EXLR_ERR_CAPACITY : EXLR_OK;
+    if (!dst) return EXLR_OK;                                  // (the length was all that was asked for)
+    if (n > cap) return EXLR_ERR_CAPACITY;
     if (n) CK(cudaMemcpy(dst, b->db.U + from, n, cudaMemcpyDeviceToHost));
     return EXLR_OK;
 }

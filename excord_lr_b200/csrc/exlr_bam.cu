@@ -59,7 +59,10 @@ struct BitReader {
         const uintptr_t a = reinterpret_cast<uintptr_t>(p);
         line0 = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)127);
         line = 0; widx = (uint32_t)(a & 127) >> 2; bb = 0; bc = 0;
-        __syncwarp();                                          // (a re-init: nobody still reads the ring)
+        // (a re-init behind a stored block: lines requested for the old position may still be in flight to the same ring slots, and
+        // two cp.async writes to one address have no order of their own -- drain them before the ring is filled again)
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
 #pragma unroll
         for (uint32_t l = 0; l < KI_RING_LINES; l++) fetch_line(l);
         asm volatile("cp.async.wait_group %0;" ::"n"(KI_RING_LINES - 1) : "memory");

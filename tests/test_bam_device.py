@@ -213,27 +213,41 @@ def test_inflate_against_zlib_on_every_kind_of_deflate_stream():
         for level, strategy in ((1, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY), (0, zlib.Z_DEFAULT_STRATEGY),
                                 (6, zlib.Z_FIXED), (6, zlib.Z_RLE), (6, zlib.Z_HUFFMAN_ONLY), (9, zlib.Z_FILTERED)):
             co = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
-            payloads.append((co.compress(raw) + co.flush(), raw))
+            payloads.append((co.compress(raw) + co.flush(), raw, f"data{datas.index(raw)} level{level} strategy{strategy}"))
         # several deflate blocks per BGZF block, separated by sync / full flushes (each leaves an empty stored block)
         co = zlib.compressobj(6, zlib.DEFLATED, -15)
         comp = b""
         for k in range(0, len(raw), 9000):
             comp += co.compress(raw[k:k + 9000]) + co.flush(zlib.Z_SYNC_FLUSH if (k // 9000) % 2 else zlib.Z_FULL_FLUSH)
-        payloads.append((comp + co.flush(), raw))
+        payloads.append((comp + co.flush(), raw, f"data{datas.index(raw)} flushed"))
     payloads = [p for p in payloads if len(p[0]) < 65000]
-    data = _bgzf(payloads)
+    data = _bgzf([p[:2] for p in payloads])
     blocks, used = api.bgzf_blocks(data)
     assert used == len(data) and len(blocks) == len(payloads)
     ex = api.Extractor(ExlrParams.make(), REF_NAMES)
     bb = api.BamBatch(ex, len(data) + 64, len(blocks))
     bb.load(data, blocks)
-    got = bb.inflated()
+    try:
+        got = bb.inflated()
+    except api.ExlrError:
+        bad = []
+        for comp, raw, label in payloads:                   # which ones?
+            d1 = _bgzf([(comp, raw)])
+            b1, _ = api.bgzf_blocks(d1)
+            bb.load(d1, b1)
+            try:
+                ok = bb.inflated() == raw
+            except api.ExlrError:
+                ok = False
+            if not ok:
+                bad.append(label)
+        raise AssertionError(f"refused or wrong: {bad}")
     want = b"".join(p[1] for p in payloads)
     assert len(got) == len(want)
     if got != want:
         at, k = 0, 0
-        for comp, raw in payloads:
-            assert got[at:at + len(raw)] == raw, f"block {k} ({len(raw)} bytes from {len(comp)}) inflated wrong"
+        for comp, raw, label in payloads:
+            assert got[at:at + len(raw)] == raw, f"block {k} ({label}: {len(raw)} bytes from {len(comp)}) inflated wrong"
             at, k = at + len(raw), k + 1
     # and streams that must be refused: a reserved block type, a stored block whose NLEN does not match, an over-subscribed code,
     # a distance beyond the start of the output, output longer / shorter than ISIZE
