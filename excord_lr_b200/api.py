@@ -34,6 +34,7 @@ EXLR_OPT_K3_FOLD = 12
 EXLR_OPT_GRAPH = 13
 EXLR_OPT_WC_INPUT = 14
 EXLR_OPT_K0_WALK = 15
+EXLR_OPT_BGZF_CRC = 16
 # see EXLR_OPT_CIGAR_KERNEL in include/exlr.h
 CIGAR_KERNEL_AUTO, CIGAR_KERNEL_WARP, CIGAR_KERNEL_FLAT, CIGAR_KERNEL_SCREEN = 0, 1, 2, 3
 
@@ -84,7 +85,7 @@ class Counters(C.Structure):
 
 
 class BgzfBlock(C.Structure):
-    _fields_ = [("comp_off", C.c_uint32), ("comp_len", C.c_uint32), ("ulen", C.c_uint32), ("reserved", C.c_uint32)]
+    _fields_ = [("comp_off", C.c_uint32), ("comp_len", C.c_uint32), ("ulen", C.c_uint32), ("crc32", C.c_uint32)]
 
 
 class _BamViews(C.Structure):
@@ -363,7 +364,9 @@ class BamBatch(DeviceBatch):
         """Chunk bytes + their block table (bgzf_blocks) into the pinned views, then H2D + inflate (asynchronous)."""
         self.comp[:len(data)] = np.frombuffer(data, np.uint8)
         for i, (co, cl, ul) in enumerate(blocks):
-            self.blocks[i] = BgzfBlock(co, cl, ul, 0)
+            if co + cl + 4 > len(data):
+                raise ExlrError(-1, "the chunk must hold whole BGZF blocks, footers included (CRC32)")
+            self.blocks[i] = BgzfBlock(co, cl, ul, int.from_bytes(data[co + cl:co + cl + 4], "little"))
         _check(self.lib.exlr_bam_submit(self.handle, len(data), len(blocks)))
 
     def walk(self, start_off: int = 0, prev: "BamBatch" = None):

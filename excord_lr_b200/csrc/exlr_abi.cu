@@ -50,6 +50,7 @@ struct exlr_ctx {
     std::atomic<int> skip_screen{0};           // auto mode: batches left to run without the screen pass (the last screened one was event-dense);
                                                // written by whoever waits a batch, read by whoever submits the next (two threads in the CLI)
     std::atomic<uint64_t> ev_hint{0}, text_hint{0};   // events / text bytes of the last waited batch: how much exlr_submit copies back speculatively
+    int bgzf_crc = 1;                          // EXLR_OPT_BGZF_CRC: kb_inflate verifies the CRC-32 of every BGZF block
     int k0_walk = 0;                           // EXLR_OPT_K0_WALK: kernel 0 does kernel 3a's work in batches of short CIGARs (measured slower: off)
     int wc_input = 0;                          // EXLR_OPT_WC_INPUT: pinned input views allocated write-combined
     int graph = 1;                             // EXLR_OPT_GRAPH: repeated shapes run as one CUDA graph launch
@@ -291,6 +292,7 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
     case EXLR_OPT_GRAPH: c->graph = value != 0; return EXLR_OK;
     case EXLR_OPT_WC_INPUT: c->wc_input = value != 0; return EXLR_OK;
     case EXLR_OPT_K0_WALK: c->k0_walk = value != 0; return EXLR_OK;
+    case EXLR_OPT_BGZF_CRC: c->bgzf_crc = value != 0; return EXLR_OK;
     case EXLR_OPT_LONG_RECORDS: if (value < 0 || value > 3) return EXLR_ERR_ARG; c->long_records = (int)value; return EXLR_OK;
     case EXLR_OPT_K1A_CTAS_PER_SM: if (value < 1 || value > 8) return EXLR_ERR_ARG; c->k1a_ctas = (int)value; return EXLR_OK;
     case EXLR_OPT_TRACE: if (value < 0 || value > 7) return EXLR_ERR_ARG; c->trace = (int)value; return EXLR_OK;
@@ -875,7 +877,7 @@ int exlr_bam_submit(exlr_batch* b, uint64_t comp_bytes, uint32_t n_blocks)
     for (uint32_t i = 0; i < n_blocks; i++) {                  // where every block inflates to: the prefix sum of the ISIZEs
         const exlr_bgzf_block& k = b->h_blocks[i];
         if ((uint64_t)k.comp_off + k.comp_len > comp_bytes || k.ulen > 65536u) return EXLR_ERR_BGZF;
-        tab[i] = BgzfBlock{k.comp_off, k.comp_len, (uint32_t)u, k.ulen};
+        tab[i] = BgzfBlock{k.comp_off, k.comp_len, (uint32_t)u, k.ulen, k.crc32, {0u, 0u, 0u}};
         u += k.ulen;
     }
     cudaStream_t st = b->stream;
@@ -888,7 +890,7 @@ int exlr_bam_submit(exlr_batch* b, uint64_t comp_bytes, uint32_t n_blocks)
     if (comp_bytes) CK(cudaMemcpyAsync((void*)D.comp, b->h_comp, comp_bytes, cudaMemcpyHostToDevice, st));
     if (n_blocks) CK(cudaMemcpyAsync(b->d_btab + 1, tab, (size_t)n_blocks * sizeof(BgzfBlock), cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(b->ev_bam[1], st));
-    D.blocks = b->d_btab + 1; D.n_blocks = n_blocks; D.block_index_base = 0;
+    D.blocks = b->d_btab + 1; D.n_blocks = n_blocks; D.block_index_base = 0; D.check_crc = b->ctx->bgzf_crc ? 1u : 0u;
     launch_bam_inflate(D, st);
     CK(cudaEventRecord(b->ev_bam[2], st));
     CK(cudaGetLastError());
@@ -921,7 +923,7 @@ int exlr_bam_walk(exlr_batch* b, exlr_batch* prev, uint64_t start_off)
     // (the tail is entry 0 of the block table: a pseudo block that is already "inflated")
     const uint32_t first = tail ? 0u : 1u;
     if (tail) {
-        b->h_btab[0] = BgzfBlock{0u, 0u, (uint32_t)b->bam_origin, (uint32_t)tail};
+        b->h_btab[0] = BgzfBlock{0u, 0u, (uint32_t)b->bam_origin, (uint32_t)tail, 0u, {0u, 0u, 0u}};
         CK(cudaMemcpyAsync(b->d_btab, b->h_btab, sizeof(BgzfBlock), cudaMemcpyHostToDevice, st));
     }
     b->bam_n_front = tail ? 1u : 0u;

@@ -155,10 +155,39 @@ __device__ __forceinline__ bool decode_sym(BitReader& br, const uint16_t* lut, u
 // order in which the code length code lengths are stored (RFC 1951 3.2.7)
 __constant__ uint8_t kClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
+// ---- CRC-32 of a block's output (gzip / BGZF footer; htslib's bgzf_read_block verifies it and the reference's reader then
+// returns an error).  Every lane takes the CRC of one slice of the output with the byte table; the slices are combined the
+// way zlib's crc32_combine does: crc(A || B) = crc(A) * x^(8 |B|) + crc(B) over GF(2)[x] mod the CRC polynomial.
+static constexpr uint32_t KI_CRC_POLY = 0xedb88320u;
+__device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b)      // a * b mod P, bit 31 = x^0 (zlib multmodp)
+{
+    uint32_t p = 0;
+    for (uint32_t m = 0x80000000u; m; m >>= 1) {
+        if (a & m) p ^= b;
+        b = (b & 1u) ? (b >> 1) ^ KI_CRC_POLY : b >> 1;
+    }
+    return p;
+}
+// x^(8 n) mod P from the table of x^(2^k) (zlib x2nmodp with k = 3)
+__device__ __forceinline__ uint32_t gf2_x8n(const uint32_t* x2n, uint32_t n)
+{
+    uint32_t p = 0x80000000u;
+    for (uint32_t k = 3; n; n >>= 1, k++) if (n & 1u) p = gf2_mulmod(x2n[k & 31u], p);
+    return p;
+}
+
 __global__ void __launch_bounds__(KI_WARPS * 32) kb_inflate(const uint8_t* __restrict__ comp, const BgzfBlock* __restrict__ blocks, uint32_t n_blocks,
-                                                             uint32_t index_base, uint8_t* U, BamCtrl* ctrl)
+                                                             uint32_t index_base, uint8_t* U, BamCtrl* ctrl, uint32_t check_crc)
 {
     __shared__ InflWarp s_all[KI_WARPS];
+    __shared__ uint32_t s_crc_tab[256], s_x2n[32];
+    if (check_crc) {                                                     // (block-uniform)
+        uint32_t c = threadIdx.x;
+        for (int k = 0; k < 8; k++) c = (c & 1u) ? (c >> 1) ^ KI_CRC_POLY : c >> 1;
+        if (threadIdx.x < 256) s_crc_tab[threadIdx.x] = c;
+        if (threadIdx.x == 0) { uint32_t p = 0x40000000u; s_x2n[0] = p; for (int n = 1; n < 32; n++) s_x2n[n] = p = gf2_mulmod(p, p); }
+        __syncthreads();
+    }
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     InflWarp& S = s_all[w];
     const uint32_t b = blockIdx.x * KI_WARPS + w;
@@ -287,6 +316,17 @@ __global__ void __launch_bounds__(KI_WARPS * 32) kb_inflate(const uint8_t* __res
         }
     }
     flush();                                                                 // (stores nothing once o is past ulen)
+    if (ok && o == ulen && check_crc) {
+        __syncwarp();
+        const uint32_t L = (ulen + 31u) / 32u, a0 = min(lane * L, ulen), a1 = min(a0 + L, ulen);
+        uint32_t c = 0xffffffffu;
+        for (uint32_t i = a0; i < a1; i++) c = s_crc_tab[(c ^ out[i]) & 0xffu] ^ (c >> 8);
+        c = a1 > a0 ? ~c : 0u;                                               // crc32 of my slice (of nothing: 0)
+        const uint32_t g = gf2_x8n(s_x2n, a1 - a0);                          // x^(8 |slice|)
+        uint32_t acc = 0;
+        for (int i = 0; i < 32; i++) acc = gf2_mulmod(__shfl_sync(0xffffffffu, g, i), acc) ^ __shfl_sync(0xffffffffu, c, i);
+        if (acc != blk.crc) ok = false;
+    }
     if (!ok || o != ulen) { if (lane == 0) atomicMax(&ctrl->bad_block, ~(index_base + b)); }
 }
 
@@ -541,7 +581,7 @@ __global__ void __launch_bounds__(32) kb_header(DevBam B)
 void launch_bam_inflate(const DevBam& B, cudaStream_t st)
 {
     if (!B.n_blocks) return;
-    kb_inflate<<<(B.n_blocks + KI_WARPS - 1) / KI_WARPS, KI_WARPS * 32, 0, st>>>(B.comp, B.blocks, B.n_blocks, B.block_index_base, B.U, B.ctrl);
+    kb_inflate<<<(B.n_blocks + KI_WARPS - 1) / KI_WARPS, KI_WARPS * 32, 0, st>>>(B.comp, B.blocks, B.n_blocks, B.block_index_base, B.U, B.ctrl, B.check_crc);
 }
 
 void launch_bam_walk(const DevBam& B, const DevBatch& D, cudaStream_t st)

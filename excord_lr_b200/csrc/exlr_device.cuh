@@ -149,7 +149,8 @@ struct DevParams {
 
 // ---- BAM input decoded on the device (exlr_bam.cu) -----------------------------------------
 static constexpr uint32_t KI_NONE = 0xffffffffu;
-struct BgzfBlock { uint32_t coff, clen, uoff, ulen; };    // deflate data = comp[coff, coff+clen) -> U[uoff, uoff+ulen)
+struct BgzfBlock { uint32_t coff, clen, uoff, ulen, crc, pad[3]; };    // deflate data = comp[coff, coff+clen) -> U[uoff, uoff+ulen); CRC-32 of the output
+static_assert(sizeof(BgzfBlock) == 32, "BgzfBlock");
 
 struct BamCtrl {                   // device-side control block of the BAM stages (zeroed per submit)
     uint32_t bad_block;            // ~(smallest block index whose deflate stream is corrupt), 0 = none (atomicMax)
@@ -164,6 +165,7 @@ struct BamCtrl {                   // device-side control block of the BAM stage
 static_assert(sizeof(BamCtrl) == 64, "BamCtrl");
 
 struct DevBam {
+    uint32_t check_crc;     // 1 = kb_inflate verifies every block's CRC-32 (htslib does: a mismatch is a read error there)
     const uint8_t* comp; const BgzfBlock* blocks; uint32_t n_blocks, block_index_base;   // (index of blocks[0] in the batch's table: error reports)
     uint8_t* U; uint32_t u_begin, u_total, start_off; int32_t n_ref;    // the stream is U[u_begin, u_total); the walk starts at start_off
     uint32_t *spec, *cnt, *exitp, *kind;            // per block: speculated first record, records owned, where the chain leaves, how it stopped

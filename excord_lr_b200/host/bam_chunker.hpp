@@ -106,7 +106,8 @@ public:
                 const int k = parse_block(dst + scanned, have - scanned, &off, &clen, &ulen, &total);
                 if (k < 0) { error = "not a BGZF block"; eof_ = true; bad_ = true; have = scanned; break; }
                 if (k == 0) break;
-                tab[nb++] = exlr_bgzf_block{(uint32_t)(scanned + off), clen, ulen, 0};
+                uint32_t crc; memcpy(&crc, dst + scanned + total - 8, 4);
+                tab[nb++] = exlr_bgzf_block{(uint32_t)(scanned + off), clen, ulen, crc};
                 scanned += total;
             }
             if (eof_ || nb == cap_blocks || have == cap_bytes || at_ < buf_.size()) break;

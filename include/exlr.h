@@ -198,6 +198,9 @@ typedef struct exlr_batch exlr_batch;
                                      slower (SA records cluster, so a few threads walk a dozen CIGARs one after the other: 45 vs 23 + 17 us);
                                      default 0: kernel 3a always runs */
 
+#define EXLR_OPT_BGZF_CRC 16      /* 1 (default) = exlr_bam_submit verifies the CRC-32 of every BGZF block on the device, like htslib's bgzf reader:
+                                     a mismatch is EXLR_ERR_BGZF with bad_block set */
+
 /* ---- lifecycle ---------------------------------------------------------------------- */
 int  exlr_abi_version(void);
 /* Number of CUDA devices with compute capability 10.x; <0 on CUDA error. */
@@ -275,7 +278,7 @@ typedef struct exlr_bgzf_block {
     uint32_t comp_off;    /* offset of the block's DEFLATE data (after the gzip header + extra field) in the chunk */
     uint32_t comp_len;    /* its length: BSIZE + 1 - XLEN - 20                                                     */
     uint32_t ulen;        /* ISIZE: bytes the block inflates to (<= 65536)                                         */
-    uint32_t reserved;
+    uint32_t crc32;       /* CRC32 field of the block's footer: verified on the device (EXLR_OPT_BGZF_CRC, default 1)  */
 } exlr_bgzf_block;
 
 typedef struct exlr_bam_views {

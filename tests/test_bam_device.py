@@ -147,6 +147,24 @@ def test_corrupt_block_is_reported(tmp_path):
     bb.walk(0)
     info = bb.extract()
     assert info.status == -7 and info.bad_block == 5
+    # a block that inflates fine to the right length but to the wrong bytes: only the CRC-32 tells (htslib checks it too)
+    data = bytearray(open(bam, "rb").read())
+    raw = zlib.decompress(bytes(data[blocks[7][0]:blocks[7][0] + blocks[7][1]]), -15)
+    wrong = bytearray(raw); wrong[100] ^= 1
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    comp2 = co.compress(bytes(wrong)) + co.flush()
+    pre = bytes(data[:blocks[7][0] - 18])
+    post = bytes(data[blocks[7][0] + blocks[7][1] + 8:])
+    hdr = b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp2) + 25)
+    forged = pre + hdr + comp2 + struct.pack("<II", zlib.crc32(raw) & 0xFFFFFFFF, len(raw)) + post
+    bl2, used2 = api.bgzf_blocks(forged)
+    bb.load(forged[:used2], bl2)
+    bb.walk(0)
+    info = bb.extract()
+    assert info.status == -7 and info.bad_block == 7
+    ex.set_option(api.EXLR_OPT_BGZF_CRC, 0)
+    bb.load(forged[:used2], bl2)
+    assert len(bb.inflated()) == sum(b[2] for b in bl2)          # unchecked, the forged block goes through
     bb.free(); ex.close()
 
 
@@ -167,7 +185,7 @@ def test_records_spanning_blocks_and_chunks(tmp_path, per_chunk, seq_len, block)
         bb = batches[n_chunks % 3]
         part = blocks[i:i + per_chunk]
         base = part[0][0]
-        end = part[-1][0] + part[-1][1]
+        end = part[-1][0] + part[-1][1] + 8                 # (the footer belongs to the block: CRC32, ISIZE)
         bb.load(data[base:end], [(co - base, cl, ul) for co, cl, ul in part])
         if prev is None:
             first_u = sum(b[2] for b in blocks[:i])
