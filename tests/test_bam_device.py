@@ -86,6 +86,22 @@ def test_random_records_and_long_cigars(tmp_path):
         bb.free(); ex.close()
 
 
+@pytest.mark.parametrize("seed", range(30, 42))
+def test_random_bams_decode_to_what_was_written(tmp_path, seed):
+    rng = np.random.default_rng(seed)
+    hb = rand_batch(seed, int(rng.integers(1, 900)), qnames=True)
+    hb.tid[hb.tid >= len(REF_NAMES)] = 0
+    bam = str(tmp_path / "f.bam")
+    bamio.write_bam(hb, bam, level=int(rng.integers(0, 10)), block=int(rng.choice([300, 2000, 20000, 0xFF00])), seq_len=int(rng.choice([0, 1, 33, 700])),
+                    random_seq=bool(rng.integers(0, 2)))
+    ex, bb, info = _decode(bam)
+    assert info.status == 0 and info.n_reads == hb.n_reads
+    got = bb.download(REF_NAMES, hb.n_reads, hb.n_ops, hb.n_sa_bytes)
+    _same(got, hb)
+    assert got.qnames == hb.qnames
+    bb.free(); ex.close()
+
+
 def test_lines_from_compressed_bytes_match_the_oracle(tmp_path):
     # compressed BAM bytes in, the reference's lines out: nothing but block-header hopping happens on the host
     for cfg, scale, seq_len in ((0, 1.0, 20), (1, 0.02, 0), (3, 0.01, 4)):
@@ -142,7 +158,7 @@ def test_corrupt_block_is_reported(tmp_path):
     for k in range(co + 2, co + min(cl, 40)):
         data[k] ^= 0x5A
     ex = api.Extractor(ExlrParams.make(), hb.ref_names)
-    bb = api.BamBatch(ex, len(data), len(blocks))
+    bb = api.BamBatch(ex, len(data) + 65536, len(blocks) + 4)
     bb.load(bytes(data[:used]), blocks)
     bb.walk(0)
     info = bb.extract()

@@ -52,6 +52,19 @@ def test_random_params(seed):
     gpu_check(hb, rand_params(seed), ck, rpc, label=f"seed{seed} k{ck} rpc{rpc}")
 
 
+@pytest.mark.parametrize("seed", range(160, 300))
+def test_random_params_larger_batches(seed):
+    # more of the same, larger and with the literal merge loop in reach (merge_min up to hundreds at small indel_min)
+    hb = rand_batch(seed, 700, qnames=(seed % 3 == 0))
+    p = rand_params(seed)
+    if seed % 5 == 0:
+        p = ExlrParams.make(indel_min=1 + seed % 7, merge_min=20 + seed % 300, max_supp_alignm=seed % 9, ins_clip_min=seed % 50,
+                            max_pct_overlap=(seed % 10) / 10.0, mapq=0, exclude_flag=0 if seed % 2 else 1796)
+        hb.tid[hb.tid < 0] = 0
+    ck, rpc = VARIANTS[seed % len(VARIANTS)]
+    gpu_check(hb, p, ck, rpc, verbose=(seed % 3 == 0), label=f"seed{seed} k{ck} rpc{rpc}")
+
+
 @pytest.mark.parametrize("variant", VARIANTS)
 def test_dense_events_and_merge_rules(variant):
     # -i 1: every small indel is an event (thousands per CTA: exercises the staged-flush rounds), merge rules at all gaps
