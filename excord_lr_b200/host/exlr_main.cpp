@@ -37,7 +37,7 @@ struct Cli {
     bool stats = false;                 // --stats: stage times on stderr
     unsigned long long batch_reads = 131072, batch_ops = 0, batch_sa = 0, batch_events = 0;
     bool host_reader = false;           // --host-reader: inflate + parse BAM on host threads (zlib) even when the GPU decoder applies
-    unsigned long long chunk_mb = 96, chunk_blocks = 0, max_record_mb = 64;   // GPU decoder: compressed bytes / BGZF blocks per chunk
+    unsigned long long chunk_mb = 128, chunk_blocks = 0, max_record_mb = 64, slots = 0;   // GPU decoder: compressed bytes / BGZF blocks per chunk
 };
 
 static void usage(FILE* f)
@@ -65,9 +65,10 @@ static void usage(FILE* f)
           "      --batch-reads <N>                    Records per GPU batch [default: 131072]\n"
           "      --batch-events <N>                   Output lines a batch has room for at first [default: 4 x batch-reads + 4096]; grown on demand\n"
           "      --host-reader                        Inflate and parse BAM on host threads (-t) instead of on the GPU\n"
-          "      --chunk-mb <N>                       GPU BAM decoder: compressed megabytes per chunk [default: 96]\n"
+          "      --chunk-mb <N>                       GPU BAM decoder: compressed megabytes per chunk [default: 128]\n"
           "      --chunk-blocks <N>                   GPU BAM decoder: BGZF blocks per chunk [default: by --chunk-mb]\n"
           "      --max-record-mb <N>                  GPU BAM decoder: largest BAM record, in megabytes [default: 64]\n"
+          "      --slots <N>                          Batches in flight per GPU [default: 5 with the GPU BAM decoder, else 3]\n"
           "      --stats                              Print stage times to stderr\n"
           "  -h, --help                               Print help\n"
           "  -V, --version                            Print version\n", f);
@@ -124,6 +125,7 @@ static int parse_cli(int argc, char** argv, Cli& c)
         else if (a == "--chunk-mb") { NUM(2048); c.chunk_mb = u ? u : 1; }
         else if (a == "--chunk-blocks") { NUM(30000); c.chunk_blocks = u; }
         else if (a == "--max-record-mb") { NUM(1023); c.max_record_mb = u ? u : 1; }
+        else if (a == "--slots") { NUM(16); c.slots = u; }
         else if (a == "--stats") { if (!flagopt(&c.stats)) return 2; }
         else if (a == "-h" || a == "--help") { usage(stdout); return -1; }
         else if (a == "-V" || a == "--version") { puts("excord-LR 0.1.17"); return -1; }
@@ -220,7 +222,7 @@ int main(int argc, char** argv)
     const unsigned long long chunk_bytes = std::min<unsigned long long>(cli.chunk_mb << 20, file_bytes + 65536) + (1u << 20);
     const uint32_t chunk_blocks = (uint32_t)(cli.chunk_blocks ? cli.chunk_blocks : std::min<unsigned long long>(30000, std::max<unsigned long long>(chunk_bytes / 16384, 64)));
     const unsigned long long tail_bytes = cli.max_record_mb << 20;      // the longest leftover a chunk can inherit: one record, however many chunks it spans
-    const int per_gpu = device_bam ? 4 : 3;
+    const int per_gpu = cli.slots ? (int)std::max<unsigned long long>(cli.slots, 2) : (device_bam ? 5 : 3);
     std::vector<Slot> slots((size_t)ndev * per_gpu);
     std::vector<Gpu> gpus(ndev);
 
