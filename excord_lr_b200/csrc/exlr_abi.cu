@@ -5,7 +5,9 @@
 // batches can be in flight (H2D of one overlapping the kernels / D2H of another).
 // There is no CPU fallback anywhere in this file: without a usable sm_100 device every
 // compute entry point returns EXLR_ERR_CUDA.
+#include <algorithm>
 #include <cstdint>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <atomic>
@@ -28,6 +30,20 @@ static int cuda_fail(cudaError_t e, const char* what)
     return EXLR_ERR_CUDA;
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+
+// EXLR_ALLOC_TRACE=1 in the environment: every buffer allocation reports its size and duration on stderr (setup-time profiling)
+static bool alloc_trace() { static const bool on = getenv("EXLR_ALLOC_TRACE") != nullptr; return on; }
+template <class F>
+static cudaError_t traced(const char* what, size_t bytes, F f)
+{
+    if (!alloc_trace()) return f();
+    const auto t0 = std::chrono::steady_clock::now();
+    const cudaError_t e = f();
+    fprintf(stderr, "exlr alloc: %-28s %10.1f MB %8.2f ms\n", what, bytes / 1e6, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    return e;
+}
+static cudaError_t dev_alloc(void** p, size_t bytes, const char* what) { return traced(what, bytes, [&] { return cudaMalloc(p, bytes); }); }
+static cudaError_t host_alloc(void** p, size_t bytes, unsigned flags, const char* what) { return traced(what, bytes, [&] { return cudaHostAlloc(p, bytes, flags); }); }
 
 enum { EV_START = 0, EV_H2D, EV_K0, EV_K1, EV_K3A, EV_K3B, EV_K4A, EV_K4B, EV_D2H, EV_COUNT };
 
@@ -88,6 +104,11 @@ struct exlr_batch {
     Ctrl* h_ctrl = nullptr; uint32_t* h_line_off = nullptr; exlr_event* h_events = nullptr;
     Ctrl* h_ctrl_dev = nullptr;                // device address of h_ctrl (mapped pinned memory): the result header is stored there by a kernel
     char* h_text = nullptr;                    // pinned: formatted lines (allocated with the batch when EXLR_OPT_DEVICE_FORMAT is set)
+    uint64_t h_text_cap = 0;                   // its size: dv.text_cap, or less for a lean batch (grown on demand by exlr_wait_text)
+    bool lean_host = false;                    // a BAM batch: its results normally leave as formatted text, so the pinned copies of the
+                                               // events and line offsets (sized by the worst-case record count) are only allocated when
+                                               // exlr_wait is actually called, and the pinned text buffer starts small
+    uint32_t* h_loff_full = nullptr;           // lean batch: the line offsets, once exlr_wait has asked for them
     bool formatted = false;                    // the last submit ran kernels 5a/5b
     bool device_format = false;                // EXLR_OPT_DEVICE_FORMAT was set when the batch was allocated
     bool verbose_text = false;                 // a BAM batch allocated with EXLR_OPT_VERBOSE_TEXT: its device-formatted lines carry the -v columns
@@ -136,6 +157,8 @@ static void drop_graph(exlr_batch* b)
 // Everything whose size follows max_events: the raw / SA / final event buffers, the text buffers of kernels 5a/5b with their
 // scan status words, and the pinned host copies.  Separate from the input + per-record slab so that exlr_batch_grow can
 // replace it while the packed records stay where they are.
+static constexpr size_t kLeanTextBytes = 16u << 20;     // pinned text buffer a lean batch starts with
+
 static void free_event_buffers(exlr_batch* b)
 {
     cudaFree(b->d_evslab); b->d_evslab = nullptr;
@@ -155,9 +178,10 @@ static int alloc_event_buffers(exlr_batch* b, uint64_t max_events)
     const size_t d_scan = dcarve((size_t)ttiles * 8), d_raw = dcarve((max_events + kRawHeadroom) * sizeof(RawEv)),
                  d_saev = dcarve(max_events * sizeof(exlr_event)), d_toff = dcarve(fmt ? (max_events + 1) * 4 : 0),
                  d_text = dcarve(text_cap + 16), d_ev = dcarve(max_events * sizeof(exlr_event));
-    cudaError_t e = cudaMalloc(&b->d_evslab, dof);
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_events, max_events * sizeof(exlr_event), cudaHostAllocDefault);
-    if (e == cudaSuccess && fmt) e = cudaHostAlloc((void**)&b->h_text, text_cap + 16, cudaHostAllocDefault);
+    cudaError_t e = dev_alloc(&b->d_evslab, dof, "device events+text");
+    if (e == cudaSuccess && !b->lean_host) e = host_alloc((void**)&b->h_events, max_events * sizeof(exlr_event), cudaHostAllocDefault, "pinned events");
+    b->h_text_cap = b->lean_host ? std::min<size_t>(text_cap, kLeanTextBytes) : text_cap;
+    if (e == cudaSuccess && fmt) e = host_alloc((void**)&b->h_text, b->h_text_cap + 16, cudaHostAllocDefault, "pinned text");
     if (e != cudaSuccess) { free_event_buffers(b); return cuda_fail(e, "event buffers"); }
     char* ds = (char*)b->d_evslab;
     DevBatch& v = b->dv;
@@ -169,6 +193,19 @@ static int alloc_event_buffers(exlr_batch* b, uint64_t max_events)
     v.max_events = (uint32_t)max_events;
     b->hv.max_events = max_events;
     return EXLR_OK;
+}
+
+// exlr_wait on a lean batch: the pinned copies it hands out are allocated now
+static int ensure_fetch_buffers(exlr_batch* b)
+{
+    if (!b->lean_host) return EXLR_OK;
+    cudaError_t e = cudaSuccess;
+    if (!b->h_events) e = host_alloc((void**)&b->h_events, b->hv.max_events * sizeof(exlr_event), cudaHostAllocDefault, "pinned events (on demand)");
+    if (e == cudaSuccess && !b->h_loff_full) {
+        e = host_alloc((void**)&b->h_loff_full, (b->hv.max_reads + 1) * 4, cudaHostAllocDefault, "pinned line_off (on demand)");
+        if (e == cudaSuccess) { b->h_loff_full[0] = 0; b->h_line_off = b->h_loff_full; }
+    }
+    return e == cudaSuccess ? EXLR_OK : cuda_fail(e, "pinned result buffers");
 }
 
 extern "C" {
@@ -229,7 +266,7 @@ int exlr_create(const exlr_params* p, int device, const char* const* ref_names, 
     if (!p || !out || n_ref < 0 || (n_ref > 0 && !ref_names)) return EXLR_ERR_ARG;
     *out = nullptr;
     int ndev = 0;
-    CK(cudaGetDeviceCount(&ndev));
+    CK(traced("driver init + device count", 0, [&] { return cudaGetDeviceCount(&ndev); }));
     if (device < 0 || device >= ndev) return EXLR_ERR_ARG;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -237,9 +274,9 @@ int exlr_create(const exlr_params* p, int device, const char* const* ref_names, 
         snprintf(g_cuda_err, sizeof g_cuda_err, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
         return EXLR_ERR_CUDA;
     }
-    CK(cudaSetDevice(device));
+    CK(traced("context (cudaSetDevice + cudaFree(0))", 0, [&] { cudaError_t e = cudaSetDevice(device); return e == cudaSuccess ? cudaFree(nullptr) : e; }));
     int sms = 0;
-    CK(configure_kernels(device, &sms));
+    CK(traced("module load + kernel attributes", 0, [&] { return configure_kernels(device, &sms); }));
     exlr_ctx* c = new (std::nothrow) exlr_ctx();
     if (!c) return EXLR_ERR_NOMEM;
     c->device = device; c->params = *p; c->n_ref = n_ref; c->sms = sms;
@@ -320,11 +357,11 @@ void exlr_batch_free(exlr_batch* b)
     cudaFree(b->d_bam); cudaFreeHost(b->h_comp); cudaFreeHost(b->h_blocks); cudaFreeHost(b->h_btab); cudaFreeHost(b->h_bctrl);
     if (b->gexec) cudaGraphExecDestroy(b->gexec);
     cudaFree(b->d_slab); cudaFree(b->d_evslab);
-    cudaFreeHost(b->h_slab); cudaFreeHost(b->h_out); cudaFreeHost(b->h_events); cudaFreeHost(b->h_text);
+    cudaFreeHost(b->h_slab); cudaFreeHost(b->h_out); cudaFreeHost(b->h_events); cudaFreeHost(b->h_text); cudaFreeHost(b->h_loff_full);
     delete b;
 }
 
-static int batch_alloc_impl(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t max_sa_bytes, uint64_t max_events, bool host_inputs, bool verbose_text, exlr_batch** out)
+static int batch_alloc_impl(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, uint64_t max_sa_bytes, uint64_t max_events, bool host_inputs, bool verbose_text, exlr_batch** out)   // host_inputs = false: a BAM batch (no pinned input views, lean pinned results)
 {
     if (!c || !out) return EXLR_ERR_ARG;
     *out = nullptr;
@@ -345,7 +382,7 @@ static int batch_alloc_impl(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, u
     if (host_inputs) {                         // (a BAM batch gets its records from the device-side decoder: no pinned input views)
         // (write-combined: the host only ever writes these views front to back; EXLR_OPT_WC_INPUT, off by default -- the host formatter
         // and check_sizes read a few words of them back, which is slow on write-combined memory but rare)
-        e = cudaHostAlloc(&b->h_slab, ho, c->wc_input ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+        e = host_alloc(&b->h_slab, ho, c->wc_input ? cudaHostAllocWriteCombined : cudaHostAllocDefault, "pinned input views");
         if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostAlloc(inputs)"); }
         char* hs = (char*)b->h_slab;
         b->hv.cigar = (uint32_t*)(hs + h_cigar); b->hv.cigar_off = (uint64_t*)(hs + h_coff); b->hv.pos = (int32_t*)(hs + h_pos);
@@ -356,8 +393,9 @@ static int batch_alloc_impl(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, u
     // ---- pinned host output slab
     size_t oo = 0;
     auto ocarve = [&](size_t bytes) { size_t at = oo; oo = align_up(oo + bytes, A); return at; };
-    const size_t o_ctrl = ocarve(sizeof(Ctrl)), o_loff = ocarve((R + 1) * 4);
-    e = cudaHostAlloc(&b->h_out, oo, cudaHostAllocMapped);
+    b->lean_host = !host_inputs;
+    const size_t o_ctrl = ocarve(sizeof(Ctrl)), o_loff = ocarve(b->lean_host ? 4 : (R + 1) * 4);   // (lean: line_off[0] only, see ensure_fetch_buffers)
+    e = host_alloc(&b->h_out, oo, cudaHostAllocMapped, "pinned header+line_off");
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostAlloc(outputs)"); }
     b->h_ctrl = (Ctrl*)((char*)b->h_out + o_ctrl); b->h_line_off = (uint32_t*)((char*)b->h_out + o_loff);
     e = cudaHostGetDevicePointer((void**)&b->h_ctrl_dev, b->h_ctrl, 0);
@@ -376,7 +414,7 @@ static int batch_alloc_impl(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, u
                  d_flag = dcarve(R * 2), d_mapq = dcarve(R), d_kind = dcarve(R), d_soff = dcarve((R + 1) * 4), d_sab = dcarve(max_sa_bytes + 16),
                  d_k1 = dcarve(R * 8), d_tcnt = dcarve(R * 4), d_slist = dcarve((max_ops / 512 + 16) * 4), d_ssum = dcarve((max_ops / 512 + 16) * 4), d_sflag = dcarve(max_ops / 512 + 16), d_llist = dcarve(R * 4), d_far = dcarve(R * 8), d_shlist = dcarve(R * 4), d_wlist = dcarve(R * 4), d_csa = dcarve(R * 4), d_list = dcarve(R * 4), d_base = dcarve(R * 4), d_sum = dcarve(R * sizeof(SaSum)),
                  d_pool = dcarve(pool_cap * sizeof(Seg)), d_dbg = dcarve(8192 * 32), d_loff = dcarve((R + 1) * 4);
-    e = cudaMalloc(&b->d_slab, dof);
+    e = dev_alloc(&b->d_slab, dof, "device batch");
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaMalloc(batch)"); }
     char* ds = (char*)b->d_slab;
     DevBatch& v = b->dv;
@@ -613,10 +651,11 @@ static int run_kernels(exlr_batch* b, bool prefetch_results)
         // results follow the kernels on the same stream, sized by a guess (the counts live on the device): lines when the batch
         // formats them (exlr_wait_text), else line offsets + events (exlr_wait)
         if (b->formatted) {
-            b->d2h_text = guess_with_margin(c->text_hint.load(), b->n_reads * 16 + 65536, d.text_cap);
+            b->d2h_text = guess_with_margin(c->text_hint.load(), b->n_reads * 16 + 65536, std::min<uint64_t>(d.text_cap, b->h_text_cap));
             if (b->d2h_text) CK(cudaMemcpyAsync(b->h_text, d.text, b->d2h_text, cudaMemcpyDeviceToHost, st));
             b->d2h_bytes += b->d2h_text;
         } else {
+            { const int rc = ensure_fetch_buffers(b); if (rc) return rc; }
             CK(cudaMemcpyAsync(b->h_line_off, d.line_off, (b->n_reads + 1) * 4, cudaMemcpyDeviceToHost, st));
             b->have_line_off = true;
             b->d2h_events = guess_with_margin(c->ev_hint.load(), b->n_reads / 4 + 4096, d.max_events);
@@ -722,6 +761,7 @@ static int finish(exlr_batch* b, exlr_result* res, bool fetch)
     }
     b->ctx->ev_hint.store(c.n_events); b->ctx->text_hint.store(c.text_bytes);
     if (fetch) {
+        { const int rc = ensure_fetch_buffers(b); if (rc) return rc; res->events = b->h_events; res->line_off = b->h_line_off; }
         // usually everything is here already (copied behind the kernels by exlr_submit); fetch what the guess missed
         bool more = false;
         if (!b->have_line_off) {
@@ -765,6 +805,12 @@ int exlr_wait_text(exlr_batch* b, exlr_result* res, const char** text, uint64_t*
         CK(cudaMemcpyAsync(&off, b->dv.text_off + first_line + (uint32_t)res->n_err_lines, 4, cudaMemcpyDeviceToHost, b->stream));
         CK(cudaStreamSynchronize(b->stream));
         nb = off;
+    }
+    if (nb > b->h_text_cap) {                                            // lean batch: more text than its pinned buffer holds yet
+        cudaFreeHost(b->h_text); b->h_text = nullptr; b->d2h_text = 0;
+        b->h_text_cap = std::min<uint64_t>(b->dv.text_cap, nb + nb / 2);
+        const cudaError_t e = host_alloc((void**)&b->h_text, b->h_text_cap + 16, cudaHostAllocDefault, "pinned text (grown)");
+        if (e != cudaSuccess) { b->h_text_cap = 0; return cuda_fail(e, "pinned text"); }
     }
     if (nb > b->d2h_text) {                                              // what the copy behind the kernels did not cover
         const uint64_t at = b->d2h_text;
@@ -818,7 +864,7 @@ int exlr_bam_batch_alloc(exlr_ctx* c, uint64_t max_comp_bytes, uint32_t max_bloc
     c->device_format = fmt;
     if (rc) return rc;
     b->is_bam = true; b->max_comp = max_comp_bytes; b->max_blocks = max_blocks; b->u_cap = u_cap; b->front_u = front_u;
-    cudaError_t e = cudaHostAlloc((void**)&b->h_comp, max_comp_bytes + 512, cudaHostAllocDefault);
+    cudaError_t e = host_alloc((void**)&b->h_comp, max_comp_bytes + 512, cudaHostAllocDefault, "pinned BGZF chunk");
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_blocks, (size_t)max_blocks * sizeof(exlr_bgzf_block), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_btab, ((size_t)max_blocks + 1) * sizeof(BgzfBlock), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_bctrl, sizeof(BamCtrl), cudaHostAllocMapped);
@@ -831,7 +877,7 @@ int exlr_bam_batch_alloc(exlr_ctx* c, uint64_t max_comp_bytes, uint32_t max_bloc
     const size_t d_ctrl = dcarve(sizeof(BamCtrl) + (size_t)tiles * 24), d_comp = dcarve(max_comp_bytes + 1024), d_tab = dcarve(tab_n * sizeof(BgzfBlock)),
                  d_u = dcarve(u_cap + 256), d_blk = dcarve(tab_n * 4 * 6), d_rec = dcarve(R * 4), d_per = dcarve(R * 4 * 5),
                  d_qoff = dcarve((R + 1) * 4), d_qn = dcarve(u_cap + 16);
-    e = cudaMalloc(&b->d_bam, dof);
+    e = dev_alloc(&b->d_bam, dof, "device BAM chunk");
     if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaMalloc(BAM chunk)"); }
     char* ds = (char*)b->d_bam;
     DevBam& D = b->db;

@@ -5,6 +5,7 @@
 //   kernel 3b k3b_sa_events  SA parse (utils.rs:88-139), -k cap (main.rs:311), stable segment sort
 //                            (main.rs:322), large-INS rules (:340-486), split pairs (:488-516)
 #include "exlr_common.cuh"
+#include "exlr_sa_parse.cuh"
 
 namespace exlr {
 
@@ -110,11 +111,10 @@ __global__ void __launch_bounds__(256) k3a_sa_cigar(DevBatch B, DevParams P)
 // 128-bit loads and each thread then parses its own record's string out of shared memory
 // (falls back to reading global memory when the range does not fit).
 // ======================================================================================
-static constexpr int K3B_THREADS = 192;                 // the usual tile (64 records, ~140 pieces + 64 own segments) parses in one round
+static constexpr int K3B_THREADS = 192;                 // the usual tile (64 records, ~140 SA pieces) parses in one round
 static constexpr int K3B_TILE = 64;                     // SA records per tile (pieces are then spread over all threads)
-static constexpr int K3B_CTAS = 7;                      // CTAs per SM: 30 KB of shared memory and 48 registers x 192 threads each
+static constexpr int K3B_CTAS = 7;                      // CTAs per SM: 29 KB of shared memory and 48 registers x 192 threads each
 static constexpr uint32_t K3B_STAGE_BYTES = 12 * 1024;
-static constexpr uint32_t K3B_SEMI = 8;                // ';' positions kept per record by phase 1; more -> phase 1b rescans
 static constexpr uint32_t K3B_MAXP = 320;              // segments (records + SA pieces) per tile in the staged layout
 
 struct SmemBytes {            // byte i of sa_bytes, served from the staged copy (bias is a multiple of 16)
@@ -137,6 +137,8 @@ __device__ __forceinline__ uint32_t swar_eq(uint32_t x, uint32_t c4)
     const uint32_t y = x ^ c4;
     return ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y | 0x7f7f7f7fu);
 }
+// the four "byte == ';'" flags of a word as a nibble (bit k: byte k)
+__device__ __forceinline__ uint32_t semi_bits(uint32_t w) { return (((swar_eq(w, 0x3b3b3b3bu) >> 7) * 0x00204081u) >> 21) & 0xfu; }
 // keep only the flag bits of the bytes whose absolute index is in [lo, hi); w0 = absolute index of the word's byte 0
 __device__ __forceinline__ uint32_t swar_clip(uint32_t z, uint32_t w0, uint32_t lo, uint32_t hi)
 {
@@ -255,97 +257,23 @@ __device__ uint32_t dev_parse_piece(const Bytes& s, uint32_t b, uint32_t e, cons
     return 0;
 }
 
-// Fast path of parse_supplementary_alignment (utils.rs:119-139) for the regular form every aligner writes,
-//     chrom,<1-9 digits>,<+|->,(<1-9 digits><op>)+,<1-3 digits <= 255>,<1-9 digits>
-// in ONE pass over the bytes.  Anything else -- signs, longer numbers, missing or extra fields, odd bytes, trailing digits in
-// the CIGAR -- returns false and the caller runs the exact dev_parse_piece above, which also yields the reference's panics.
-// For the accepted form both produce the same Seg: same field boundaries, u32-wrapping sums, u64 key.
-// Written for warp convergence: one simple loop per field, no early exit (a failed check only clears `ok`), and the lanes
-// of `m` (the lanes of the warp that hold a piece) re-join after every loop -- with early returns and nested digit loops
-// the lanes drifted apart and the parser ran at a quarter of the warp width.
+// Fast path of parse_supplementary_alignment (utils.rs:119-139) for the regular form every aligner writes: sa_parse_fast
+// (exlr_sa_parse.cuh) on the staged bytes.  Anything else -- signs, longer numbers, missing or extra fields, odd bytes, trailing
+// digits in the CIGAR -- returns false and the caller runs the exact dev_parse_piece above, which also yields the reference's
+// panics.  For the accepted form both produce the same Seg: same field boundaries, u32-wrapping sums, u64 key.
 __device__ __forceinline__ bool dev_parse_piece_fast(const uint8_t* p /* staged bytes */, uint32_t bias /* sa offset of p[0] */,
-                                                     uint32_t b, uint32_t e, const DevParams& P, Seg* out, uint32_t m)
+                                                     uint32_t b /* offsets into p */, uint32_t e, const DevParams& P, Seg* out, uint32_t m)
 {
-    b -= bias; e -= bias;
-    bool ok = true;
-    uint32_t i = b;
-    while (i < e && p[i] != ',') i++;                                          // chrom
-    __syncwarp(m);
-    const uint32_t ce = i;
-    ok &= i < e;
-    i++;
-    uint32_t pos = 0, nd = 0;                                                  // pos
-    while (i < e) { const uint32_t d = (uint32_t)p[i] - '0'; if (d > 9u) break; pos = pos * 10u + d; nd++; i++; }
-    __syncwarp(m);
-    ok &= nd - 1u < 9u && i < e && p[min(i, e - 1u)] == ',';
-    i++;
-    const uint32_t sc = i < e ? (uint32_t)p[i] : 0u, sc2 = i + 1u < e ? (uint32_t)p[i + 1] : 0u;   // strand
-    ok &= (sc == '+' || sc == '-') && sc2 == ',';
-    i += 2;
-    // CIGAR text (utils.rs:88-117, 12-42): the same step for every byte up to the comma.  The op branch is taken by a few lanes
-    // at a time, so it is kept short: the op letter selects its classes from bit masks indexed by (c - '='), lengths are
-    // multiplied by the class bit.  With at most 15 ops of less than 2^28 each no sum can wrap a u32, so one accumulator
-    // serves D + M + = + X (split_read_event.rs:23-28); longer CIGARs or lengths take the exact parser.
-    //   = D H I M N P S X  ->  c - '=' = 0 7 11 12 16 17 19 22 27
-    uint32_t ref = 0, sS = 0, sH = 0, key = 0, seenM = 0, nops = 0, n = 0, bad = 0, big = 0;
-    nd = 0;
-    while (i < e) {
-        const uint32_t c = p[i];
-        if (c == ',') break;
-        const uint32_t d = c - '0';
-        if (d <= 9u) { n = n * 10u + d; nd++; }
-        else {
-            const uint32_t x = c - '=', xs = x & 31u, in = x < 28u ? 1u : 0u;   // `in` voids the class bits of bytes beyond 'X'
-            bad |= (((0x84B1881u >> xs) & in) ^ 1u) | (nd - 1u >= 9u ? 1u : 0u);
-            big |= n;
-            ref += n * ((0x8010081u >> xs) & in);                               // = D M X
-            sS += n * ((0x0400000u >> xs) & in);
-            sH += n * ((0x0000800u >> xs) & in);
-            key += n * ((0x8401001u >> xs) & in & (seenM ^ 1u));                // = I S X before the first M (utils.rs:33)
-            seenM |= (0x0010000u >> xs) & in;
-            n = 0; nd = 0; nops++;
-        }
-        i++;
-    }
-    __syncwarp(m);
-    ok &= !bad && nd == 0u && nops - 1u < 15u && (big >> 28) == 0u && i < e;   // ends at the comma, right after an op
-    i++;
-    uint32_t mq = 0;                                                           // mapq: u8
-    nd = 0;
-    while (i < e) { const uint32_t d = (uint32_t)p[i] - '0'; if (d > 9u) break; mq = mq * 10u + d; nd++; i++; }
-    __syncwarp(m);
-    ok &= nd - 1u < 3u && mq <= 255u && i < e && p[min(i, e - 1u)] == ',';
-    i++;
-    nd = 0;                                                                    // NM: parsed, value unused (utils.rs:135)
-    while (i < e) { if ((uint32_t)p[i] - '0' > 9u) break; nd++; i++; }
-    __syncwarp(m);
-    ok &= nd - 1u < 9u && i == e;
-    if (!ok) return false;
-    uint32_t cb = b;
-    if (ce - cb >= 3u && p[cb] == 'c' && p[cb + 1] == 'h' && p[cb + 2] == 'r') cb += 3;
-    out->chrom_ref = 0x80000000u | (cb + bias);
-    out->chrom_len = ce - cb;
-    out->start = (int64_t)pos - 1;
-    out->end = out->start + (int64_t)ref;
-    out->key = (int64_t)key;
-    out->clip_big = (sS > P.ins_clip_min || sH > P.ins_clip_min) ? 1u : 0u;
-    out->strand_neg = sc == '-';
+    SaFast f;
+    if (!sa_parse_fast(p, b, e, &f, m)) return false;
+    out->chrom_ref = 0x80000000u | (f.cb + bias);
+    out->chrom_len = f.chrom_len;
+    out->start = (int64_t)f.pos - 1;
+    out->end = out->start + (int64_t)f.ref;
+    out->key = (int64_t)f.key;
+    out->clip_big = (f.clipS > P.ins_clip_min || f.clipH > P.ins_clip_min) ? 1u : 0u;
+    out->strand_neg = f.strand_neg;
     return true;
-}
-
-// Calls f(w0, z) for every aligned word of bytes [b0, e0): z has 0x80 in each byte that equals the byte replicated in c4,
-// bytes outside the range masked off (only the first and the last word pay for the masking).
-template <class F>
-__device__ __forceinline__ void swar_scan(const SmemBytes& s, uint32_t b0, uint32_t e0, uint32_t c4, F f)
-{
-    if (b0 >= e0) return;
-    uint32_t w0 = b0 & ~3u;
-    const uint32_t last = (e0 - 1u) & ~3u;
-    uint32_t z = swar_eq(s.word(w0), c4) & (0xffffffffu << (8u * (b0 - w0)));
-    if (w0 == last) { f(w0, z & (0xffffffffu >> (8u * (w0 + 4u - e0)))); return; }
-    f(w0, z);
-    for (w0 += 4u; w0 < last; w0 += 4u) f(w0, swar_eq(s.word(w0), c4));
-    f(last, swar_eq(s.word(last), c4) & (0xffffffffu >> (8u * (last + 4u - e0))));
 }
 
 template <class Bytes>
@@ -536,21 +464,24 @@ __device__ __forceinline__ void k3b_record(const DevBatch& B, const DevParams& P
     k3b_finish(B, P, s, j, active, r, dropped, segs, nseg);
 }
 
-// Fast path layout: the tile's SA bytes, its piece list and its segments all live in shared memory, and the work
-// is re-flattened between phases so that the lanes of a warp always run the same loop:
-//   phase 1  thread per record : count ';' (the -k cap) and non-empty pieces          -> slots per record, block scan
-//   phase 1b thread per record : write the [begin,end) of every piece into the piece list
-//   phase 2  thread per PIECE  : parse_supplementary_alignment on homogeneous pieces   -> Seg
-//   phase 3  thread per record : record segment, sort, rules, emit
+// Fast path layout: the tile's SA bytes, a bit mask of their ';', the piece list and the segments all live in shared memory,
+// and the work is re-flattened between phases so that the lanes of a warp always run the same code:
+//   staging  thread per 16 bytes: copy to shared memory, one mask bit per byte that is ';'
+//   phase 1  thread per record  : count ';' (the -k cap) and non-empty pieces from the mask     -> slots per record, block scan
+//   phase 1b thread per record  : write the [begin,end) of every non-empty piece into the piece list
+//   phase 2  thread per PIECE   : parse_supplementary_alignment from 8-byte windows (exlr_sa_parse.cuh) -> Seg
+//   phase 3  thread per record  : record segment, sort, rules, emit
 struct __align__(16) K3bSmem {
-    uint8_t bytes[K3B_STAGE_BYTES];
-    Seg segs[K3B_MAXP];
-    uint32_t pb[K3B_MAXP], pe[K3B_MAXP];
+    uint8_t bytes[K3B_STAGE_BYTES + 16];               // (+16: the parser's windows read up to 11 bytes past a piece)
+    uint32_t msemi[K3B_STAGE_BYTES / 32 + 4];          // bit i: staged byte i is ';'
+    Seg segs[K3B_MAXP];                                // per record: its own alignment, then its pieces in SA order
+    uint16_t pb[K3B_MAXP], pe[K3B_MAXP];               // piece list: [begin, end) as offsets into bytes[]
+    uint16_t pslot[K3B_MAXP];                          // the piece's slot in segs[]
+    uint8_t pread[K3B_MAXP];                           // the piece's record (index in the tile)
     uint32_t rerr[K3B_TILE];
-    uint32_t semi[K3B_TILE][K3B_SEMI];                 // positions of the first ';' of every record (phase 1 -> 1b)
     uint32_t wsum[K3B_THREADS / 32];
-    uint8_t pread[K3B_MAXP];
 };
+static_assert(offsetof(K3bSmem, segs) % 8 == 0, "Seg holds 64-bit fields");
 // FOLD only (kept out of the plain layout: 2.6 KB more per CTA cost kernel 3b its seventh CTA per SM, and a grid sized for seven
 // then ran a second, nearly empty wave -- 1.03 ms instead of 0.61 ms on configs[3])
 struct __align__(16) K3bFoldSmem {
@@ -567,7 +498,11 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
     extern __shared__ __align__(16) unsigned char k3b_smem_raw[];
     K3bSmem& S = *reinterpret_cast<K3bSmem*>(k3b_smem_raw);
     K3bFoldSmem& F = *reinterpret_cast<K3bFoldSmem*>(k3b_smem_raw + sizeof(K3bSmem));     // (only allocated for FOLD)
-    griddep_wait();                                    // kernel 3a's summaries (FOLD: kernel 0's list)
+    // FOLD: the predecessor is kernel 0, whose list everything below reads.  Otherwise it is kernel 3a, whose CTAs trigger this
+    // launch only after their own wait on kernel 0 has returned: kernel 0's list and count are complete and visible to any CTA
+    // of this grid that runs, and kernel 3a's summaries are read in phase 3 only -- the wait is there, and staging, the piece
+    // list and the parse run beside kernel 3a (which is bound by the latency of its CIGAR loads and leaves the issue slots idle).
+    if (FOLD) griddep_wait();
     CtaTrace tr(B, 4);
     const uint32_t n_sa = B.ctrl->n_sa;
     const uint32_t n_tiles = (n_sa + K3B_TILE - 1) / K3B_TILE;
@@ -583,11 +518,16 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
         __syncthreads();                                                      // the previous tile's readers are done
         if (!staged) {
             GlobalBytes s{B.sa_bytes};
+            griddep_wait();
             k3b_record<FOLD>(B, P, s, j, active, local_segs);
             continue;
         }
-        for (uint32_t o = a0 + t * 16u; o < span_e; o += K3B_THREADS * 16u)
-            *reinterpret_cast<uint4*>(S.bytes + (o - a0)) = __ldg(reinterpret_cast<const uint4*>(B.sa_bytes + o));
+        for (uint32_t o = a0 + t * 16u; o < span_e; o += K3B_THREADS * 16u) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(B.sa_bytes + o));
+            *reinterpret_cast<uint4*>(S.bytes + (o - a0)) = v;
+            reinterpret_cast<uint16_t*>(S.msemi)[(o - a0) >> 4] =
+                (uint16_t)(semi_bits(v.x) | (semi_bits(v.y) << 4) | (semi_bits(v.z) << 8) | (semi_bits(v.w) << 12));
+        }
         if (FOLD) {
             // kernel 3a's work (main.rs:214-306, utils.rs:12-42): a pair of lanes walks the CIGAR of each of the tile's records --
             // its loads are in flight while the SA bytes are staged
@@ -605,76 +545,80 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
             if (mine && (t & 1u) == 0u) { F.rrec[k] = rr; F.rlong[k] = is_long ? 1 : 0; }
         }
         // phase 1: pieces per record
-        uint32_t r = 0, b0 = 0, e0 = 0, slots = 0;
+        uint32_t r = 0, b0 = 0, e0 = 0, slots = 0, npieces = 0;
         bool dropped = false, is_str = false;
-        if (active) { r = B.sa_list[j]; b0 = B.sa_off[r]; e0 = B.sa_off[r + 1]; is_str = B.sa_kind[r] == EXLR_SA_STRING; }
+        int32_t own_tid = 0, own_pos = 0; uint32_t own_flag = 0;              // the record's own alignment: asked for now, used in phase 3
+        if (active) {
+            r = B.sa_list[j]; b0 = B.sa_off[r]; e0 = B.sa_off[r + 1]; is_str = B.sa_kind[r] == EXLR_SA_STRING;
+            own_tid = B.tid[r]; own_pos = B.pos[r]; own_flag = B.flag[r];
+        }
         __syncthreads();
         SmemBytes s{S.bytes, a0};
-        uint32_t nsemi = 0;
+        const uint32_t rb = b0 - a0, re = e0 - a0;                             // the record's string as offsets into bytes[]
+        const bool scan = active && is_str && re > rb;
+        const uint32_t k_first = rb >> 5, k_last = (re - 1u) >> 5;
         if (active) {
-            uint32_t nonempty = 0;
-            if (is_str) {
-                // one pass, four bytes per step: every ';' closes a piece (empty when it directly follows the previous ';' or the
-                // start of the string); the last piece runs to the end of the string.  pieces = #';' + 1 (main.rs:309).
-                uint32_t pbeg = b0;
-                swar_scan(s, b0, e0, 0x3b3b3b3bu, [&](uint32_t w0, uint32_t z) {
-                    while (z) {
-                        const uint32_t i = w0 + ((uint32_t)(__ffs((int)z) - 1) >> 3);
-                        z &= z - 1u;
-                        if (nsemi < K3B_SEMI) S.semi[t][nsemi] = i;
-                        nsemi++;
-                        nonempty += i > pbeg;
-                        pbeg = i + 1u;
-                    }
-                });
-                nonempty += e0 > pbeg;
-                if ((unsigned long long)nsemi + 1ull > P.max_supp_alignm) dropped = true;   // main.rs:311-313
+            // every ';' closes a piece, empty when it directly follows the previous ';' or the start of the string; the last
+            // piece runs to the end of the string.  pieces = #';' + 1 (main.rs:309), non-empty ones get a slot (main.rs:315).
+            uint32_t nsemi = 0, nonempty = 0;
+            if (scan) {
+                uint32_t carry = 1u;                                           // "the byte before is a ';' or the start"
+                for (uint32_t k = k_first; k <= k_last; k++) {
+                    uint32_t z = S.msemi[k];
+                    if (k == k_first) z &= 0xffffffffu << (rb & 31u);
+                    if (k == k_last) z &= 0xffffffffu >> (31u - ((re - 1u) & 31u));
+                    uint32_t prev = (z << 1) | carry;
+                    if (k == k_first) prev = (z << 1) | (1u << (rb & 31u));
+                    nsemi += __popc(z);
+                    nonempty += __popc(z & ~prev);
+                    carry = z >> 31;
+                }
+                nonempty += ((S.msemi[k_last] >> ((re - 1u) & 31u)) & 1u) ^ 1u;   // the string does not end in ';': one more piece
             }
+            if (is_str && (unsigned long long)nsemi + 1ull > P.max_supp_alignm) dropped = true;   // main.rs:311-313
             slots = dropped ? 0u : 1u + nonempty;
+            npieces = dropped ? 0u : nonempty;
             S.rerr[t] = 0xffffffffu;
         }
-        uint32_t incl = slots;
+        uint32_t incl = slots | (npieces << 16);                              // both running sums in one scan
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
         if (lane == 31) S.wsum[w] = incl;
         __syncthreads();
-        uint32_t sb = incl - slots, total = 0;
+        uint32_t excl = incl - (slots | (npieces << 16)), total2 = 0;
 #pragma unroll
-        for (int k = 0; k < K3B_THREADS / 32; k++) { const uint32_t x = S.wsum[k]; if ((uint32_t)k < w) sb += x; total += x; }
+        for (int k = 0; k < K3B_THREADS / 32; k++) { const uint32_t x = S.wsum[k]; if ((uint32_t)k < w) excl += x; total2 += x; }
+        const uint32_t sb = excl & 0xffffu, total = total2 & 0xffffu, total_pieces = total2 >> 16;
         if (total > K3B_MAXP) {                                               // block-uniform: too many segments for the staged layout
+            griddep_wait();
             k3b_record<FOLD>(B, P, s, j, active, local_segs);
             continue;
         }
         // phase 1b: piece list
-        if (active && !dropped) {
-            S.pb[sb] = 0xffffffffu; S.pread[sb] = (uint8_t)t;                 // slot 0 of the record: its own alignment
-            if (is_str) {
-                uint32_t at = sb + 1, pbeg = b0;
-                auto piece_end = [&](uint32_t i) {
-                    if (i > pbeg) { S.pb[at] = pbeg; S.pe[at] = i; S.pread[at] = (uint8_t)t; at++; }   // filter(|x| x.len() > 0), main.rs:315
-                    pbeg = i + 1u;
-                };
-                if (nsemi <= K3B_SEMI) {
-                    for (uint32_t k = 0; k < nsemi; k++) piece_end(S.semi[t][k]);
-                } else {                                                       // more ';' than phase 1 kept (large -k): rescan
-                    swar_scan(s, b0, e0, 0x3b3b3b3bu, [&](uint32_t w0, uint32_t z) {
-                        while (z) { piece_end(w0 + ((uint32_t)(__ffs((int)z) - 1) >> 3)); z &= z - 1u; }
-                    });
-                }
-                if (e0 > pbeg) piece_end(e0);
+        if (scan && !dropped) {
+            uint32_t at = excl >> 16, slot = sb + 1u, pbeg = rb;
+            auto piece_end = [&](uint32_t i) {
+                if (i > pbeg) { S.pb[at] = (uint16_t)pbeg; S.pe[at] = (uint16_t)i; S.pslot[at] = (uint16_t)slot; S.pread[at] = (uint8_t)t; at++; slot++; }
+                pbeg = i + 1u;
+            };
+            for (uint32_t k = k_first; k <= k_last; k++) {
+                uint32_t z = S.msemi[k];
+                if (k == k_first) z &= 0xffffffffu << (rb & 31u);
+                if (k == k_last) z &= 0xffffffffu >> (31u - ((re - 1u) & 31u));
+                while (z) { piece_end(k * 32u + (uint32_t)__ffs((int)z) - 1u); z &= z - 1u; }
             }
+            if (re > pbeg) piece_end(re);
         }
         __syncthreads();
         // phase 2: one thread per piece
-        for (uint32_t x0 = 0; x0 < total; x0 += K3B_THREADS) {               // block-uniform trip count
+        for (uint32_t x0 = 0; x0 < total_pieces; x0 += K3B_THREADS) {        // block-uniform trip count
             const uint32_t x = x0 + t;
-            const uint32_t pbeg = x < total ? S.pb[x] : 0xffffffffu;
-            const bool has = pbeg != 0xffffffffu;
+            const bool has = x < total_pieces;
             const uint32_t m = __ballot_sync(0xffffffffu, has);
             if (!has) continue;
-            const uint32_t pend = S.pe[x];
-            if (dev_parse_piece_fast(S.bytes, a0, pbeg, pend, P, &S.segs[x], m)) continue;
-            const uint32_t err = dev_parse_piece(s, pbeg, pend, P, &S.segs[x]);   // irregular piece: the exact parser decides
+            const uint32_t pbeg = S.pb[x], pend = S.pe[x], slot = S.pslot[x];
+            if (dev_parse_piece_fast(S.bytes, a0, pbeg, pend, P, &S.segs[slot], m)) continue;
+            const uint32_t err = dev_parse_piece(s, pbeg + a0, pend + a0, P, &S.segs[slot]);   // irregular piece: the exact parser decides
             if (err) atomicMin(&S.rerr[S.pread[x]], (x << 8) | err);          // the first failing piece in SA order wins
         }
         __syncthreads();
@@ -689,13 +633,23 @@ __global__ void __launch_bounds__(K3B_THREADS, K3B_CTAS) k3b_sa_events(DevBatch 
         }
         tr.mid();
         // phase 3: one thread per record
+        uint32_t own_clen = 0;
+        if (active && !dropped) own_clen = B.ref_off[own_tid + 1] - B.ref_off[own_tid];
+        if (!FOLD) griddep_wait();                                            // kernel 3a's summaries
         uint32_t nseg = 0;
         if (active && !dropped) {
             uint32_t err = S.rerr[t];
             nseg = slots;
             if (err != 0xffffffffu) { report(B.ctrl, r, err & 0xffu); nseg = 0; }
-            else if (!FOLD) k3b_record_seg(B, P, j, r, &S.segs[sb]);
-            else { const SaSum sm = F.sum[t]; seg_from_sums(B, P, r, sm.S, sm.H, sm.refspan, sm.ffm, &S.segs[sb]); }
+            else {
+                SaSum sm;
+                if (!FOLD) sm = B.sa_sum[j]; else sm = F.sum[t];
+                Seg& g = S.segs[sb];                                          // the record's own alignment as segment 0 (main.rs:299-306)
+                g.chrom_ref = (uint32_t)own_tid; g.chrom_len = own_clen;
+                g.start = (int64_t)own_pos; g.end = g.start + sm.refspan; g.key = sm.ffm;
+                g.clip_big = (sm.S > P.ins_clip_min || sm.H > P.ins_clip_min) ? 1u : 0u;
+                g.strand_neg = (own_flag & 0x10u) ? 1u : 0u;
+            }
         }
         k3b_finish(B, P, s, j, active, r, dropped, &S.segs[sb < K3B_MAXP ? sb : 0], nseg);
     }

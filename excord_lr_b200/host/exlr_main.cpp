@@ -222,7 +222,11 @@ int main(int argc, char** argv)
     const unsigned long long chunk_bytes = std::min<unsigned long long>(cli.chunk_mb << 20, file_bytes + 65536) + (1u << 20);
     const uint32_t chunk_blocks = (uint32_t)(cli.chunk_blocks ? cli.chunk_blocks : std::min<unsigned long long>(30000, std::max<unsigned long long>(chunk_bytes / 16384, 64)));
     const unsigned long long tail_bytes = cli.max_record_mb << 20;      // the longest leftover a chunk can inherit: one record, however many chunks it spans
-    const int per_gpu = cli.slots ? (int)std::max<unsigned long long>(cli.slots, 2) : (device_bam ? 5 : 3);
+    int per_gpu = cli.slots ? (int)std::max<unsigned long long>(cli.slots, 2) : (device_bam ? 5 : 3);
+    if (device_bam && !cli.slots) {     // a file of few chunks never fills five slots per GPU: do not allocate (and pin) what cannot be used
+        const unsigned long long est = file_bytes / std::max<unsigned long long>(cli.chunk_mb << 20, 1) + 1;
+        per_gpu = (int)std::min<unsigned long long>(per_gpu, std::max<unsigned long long>(2, (est + ndev - 1) / ndev + 1));
+    }
     std::vector<Slot> slots((size_t)ndev * per_gpu);
     std::vector<Gpu> gpus(ndev);
 
@@ -240,26 +244,33 @@ int main(int argc, char** argv)
             // -v lines carry the read name, which stays on the host: those are formatted here
             if (!st) st = exlr_set_option(ctx, EXLR_OPT_DEVICE_FORMAT, (cli.verbose && !device_bam) ? 0 : 1);
             if (!st && device_bam) st = exlr_set_option(ctx, EXLR_OPT_VERBOSE_TEXT, cli.verbose ? 1 : 0);   // the read names are on the device there
+            { std::lock_guard<std::mutex> lk(mu); gpus[g].ctx = ctx; }
+            // each slot is handed to the reader as soon as it exists: the first chunk is on its way while the others' buffers
+            // are still being allocated and pinned
             for (int k = 0; k < per_gpu && !st; k++) {
                 Slot& s = slots[(size_t)g * per_gpu + k];
                 s.gpu = g;
                 if (device_bam) {
                     st = exlr_bam_batch_alloc(ctx, chunk_bytes, chunk_blocks, tail_bytes, EVS, &s.b);
                     if (!st) st = exlr_bam_get_views(s.b, &s.bv);
-                    continue;
+                } else {
+                    st = exlr_batch_alloc(ctx, R, OPS, SAB, EVS, &s.b);
+                    if (st) break;
+                    exlr_batch_get_views(s.b, &s.pk.v);
+                    s.pk.keep_qnames = cli.verbose;
+                    s.pk.reset();
                 }
-                st = exlr_batch_alloc(ctx, R, OPS, SAB, EVS, &s.b);
                 if (st) break;
-                exlr_batch_get_views(s.b, &s.pk.v);
-                s.pk.keep_qnames = cli.verbose;
-                s.pk.reset();
+                std::lock_guard<std::mutex> lk(mu);
+                gpus[g].state = 2; gpus[g].freeq.push_back(g * per_gpu + k);
+                cv.notify_all();
             }
-            if (st) fprintf(stderr, "GPU %d: %s (%s)\n", g, exlr_strerror(st), exlr_last_cuda_error());
-            std::lock_guard<std::mutex> lk(mu);
-            gpus[g].ctx = ctx;
-            if (st) { gpus[g].state = -1; fatal = 3; }
-            else { gpus[g].state = 2; for (int k = 0; k < per_gpu; k++) gpus[g].freeq.push_back(g * per_gpu + k); }
-            cv.notify_all();
+            if (st) {
+                fprintf(stderr, "GPU %d: %s (%s)\n", g, exlr_strerror(st), exlr_last_cuda_error());
+                std::lock_guard<std::mutex> lk(mu);
+                gpus[g].state = -1; fatal = 3;
+                cv.notify_all();
+            }
         });
     };
     { std::lock_guard<std::mutex> lk(mu); start_gpu(0); }

@@ -118,6 +118,32 @@ def test_lines_from_compressed_bytes_match_the_oracle(tmp_path):
         bb.free(); ex.close()
 
 
+def test_events_of_a_bam_batch_and_text_beyond_the_first_pinned_buffer(tmp_path):
+    # a BAM batch keeps no pinned copies of events / line offsets until exlr_wait asks for them, and its pinned text buffer
+    # starts at 16 MB: both paths give what the oracle gives
+    hb = synth.config(3, 0.15)                                  # split-heavy: ~0.4 M lines, > 16 MB of text
+    p = ExlrParams.make(**synth.CONFIGS[3]["params"])
+    bam = str(tmp_path / "d.bam")
+    bamio.write_bam(hb, bam, ref_lens=synth.ref_lens(), seq_len=0, level=1)
+    data = open(bam, "rb").read()
+    blocks, used = api.bgzf_blocks(data)
+    ex = api.Extractor(p, hb.ref_names)
+    bb = api.BamBatch(ex, len(data) + 64, len(blocks), max_events=2 * hb.n_reads)
+    bb.load(data[:used], blocks)
+    bb.walk(_header_end(data, blocks))
+    info = bb.extract()
+    assert info.status == 0 and info.n_reads == hb.n_reads
+    want = oracle_c.run(hb, p)
+    res, text = bb.wait_text()
+    assert res.status == want.status == 0 and res.n_events == len(want.events)
+    assert len(text) > (16 << 20)
+    assert text == oracle_c.format_lines(hb, want.events)
+    r = bb.wait()
+    assert r.n_events == len(want.events) and r.events.tobytes() == want.events.tobytes()
+    assert np.array_equal(r.line_off, want.line_off)
+    bb.free(); ex.close()
+
+
 def test_partial_record_at_the_end_is_the_tail(tmp_path):
     # a chunk that ends inside a record: every whole record is decoded, tail_off names the first byte of the partial one
     hb = synth.config(0, 0.2)
