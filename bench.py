@@ -347,7 +347,7 @@ def e2e_bam(args, pcie_gbs):
     """BAM bytes in -> event bytes out, through the CLI (excord_lr_b200/host/excord-lr-b200): the file is read into pinned memory,
     inflated and walked on the GPU (exlr_bam_*), and the lines come back formatted.  Workload: BASELINE.json configs[1] molecules
     with 15 kb of random SEQ/QUAL per record (what makes a real HiFi BAM big); the same run with --host-reader (zlib on every host
-    core) beside it.  Times are the CLI's own `stream` figure (after process setup: CUDA context, buffers), best of 3."""
+    core) beside it.  stream_s is the CLI's own `stream` figure (after process setup: CUDA context, buffers), wall_s the whole process."""
     import re
     import subprocess
     import tempfile
@@ -365,17 +365,24 @@ def e2e_bam(args, pcie_gbs):
         out["bam_bytes"] = size
         ref = None
         for key, extra in (("gpu_decoder", []), ("host_reader", ["--host-reader"])):
+            # stream_s: the CLI's own `stream` figure with every batch in place before the input is read (--eager-alloc) -- the rate a
+            # large file sees; wall_s: the whole process as a user starts it (CUDA context, batches allocated while the first ones
+            # already work), best of 3 each
             best, wall, detail = None, None, ""
-            for _ in range(3):
+            for eager in (True, True, True, False, False, False):
                 t0 = time.perf_counter()
-                r = subprocess.run([exe, "-b", bam, "-o", txt, "-p", "0.8", "-t", str(cores), "--stats"] + extra, capture_output=True, text=True)
+                r = subprocess.run([exe, "-b", bam, "-o", txt, "-p", "0.8", "-t", str(cores), "--stats"] + extra + (["--eager-alloc"] if eager else []),
+                                   capture_output=True, text=True)
                 w = time.perf_counter() - t0
                 if r.returncode != 0:
                     return {"unavailable": r.stderr[-300:]}
+                if not eager:
+                    wall = w if wall is None else min(wall, w)
+                    continue
                 m = re.search(r"stream ([0-9.]+) s", r.stderr)
                 st = float(m.group(1)) if m else w
                 if best is None or st < best:
-                    best, wall = st, w
+                    best = st
                     dm = re.search(r"GPU BAM decoder: (.*)", r.stderr)
                     detail = dm.group(1) if dm else ""
             got = open(txt, "rb").read()
@@ -389,6 +396,7 @@ def e2e_bam(args, pcie_gbs):
         out["host_reader"]["threads"] = cores
         out["output_bytes"] = len(ref)
         out["speedup_over_host_reader"] = out["host_reader"]["stream_s"] / out["gpu_decoder"]["stream_s"]
+        out["wall_speedup_over_host_reader"] = out["host_reader"]["wall_s_with_process_setup"] / out["gpu_decoder"]["wall_s_with_process_setup"]
     return out
 
 
@@ -412,6 +420,9 @@ def main():
     ap.add_argument("--wc-input", action="store_true", help="write-combined pinned input views (A/B for the e2e figure)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of every step directly (default: repeated shapes replay a CUDA graph)")
     ap.add_argument("--no-overlap", action="store_true", help="run kernel 1 on the same stream as the SA branch")
+    ap.add_argument("--fork-late", action="store_true", help="A/B: start the CIGAR path once kernel 0 is done (EXLR_OPT_OVERLAP = 2)")
+    ap.add_argument("--k3-fold", action="store_true", help="A/B: kernel 3a's work inside kernel 3b for short-CIGAR batches (EXLR_OPT_K3_FOLD)")
+    ap.add_argument("--k0-walk", action="store_true", help="A/B: kernel 3a's work inside kernel 0 for short-CIGAR batches (EXLR_OPT_K0_WALK)")
     ap.add_argument("--k1-ctas", type=int, default=0, help="persistent CTAs of kernel 1 per SM (1..4)")
     ap.add_argument("--k1-waves", type=int, default=0)
     args = ap.parse_args()
@@ -439,6 +450,12 @@ def main():
     ex_opts = [(api.EXLR_OPT_CIGAR_KERNEL, args.cigar_kernel), (api.EXLR_OPT_READS_PER_CTA, args.reads_per_cta)]
     if args.no_overlap:
         ex_opts.append((api.EXLR_OPT_OVERLAP, 0))
+    if args.fork_late:
+        ex_opts.append((api.EXLR_OPT_OVERLAP, 2))
+    if args.k3_fold:
+        ex_opts.append((api.EXLR_OPT_K3_FOLD, 1))
+    if args.k0_walk:
+        ex_opts.append((api.EXLR_OPT_K0_WALK, 1))
     if args.no_graph:
         ex_opts.append((api.EXLR_OPT_GRAPH, 0))
     if args.wc_input:
@@ -484,7 +501,7 @@ def main():
     if not args.no_overlap and not c["params"].get("split_only"):
         ex.set_option(api.EXLR_OPT_OVERLAP, 0)
         solo_stage, k1_ms, k1a_ms = diag(nd)
-        ex.set_option(api.EXLR_OPT_OVERLAP, 1)
+        ex.set_option(api.EXLR_OPT_OVERLAP, 2 if args.fork_late else 1)
     else:
         solo_stage, k1_ms, k1a_ms = dict(stage_ms), k1_beside, [0.0]
     ex.set_option(api.EXLR_OPT_STAGE_TIMING, 0)

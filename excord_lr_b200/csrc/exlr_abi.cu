@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 
+#include <sys/mman.h>
 #include <cuda_runtime.h>
 
 #include "exlr_device.cuh"
@@ -44,6 +45,39 @@ static cudaError_t traced(const char* what, size_t bytes, F f)
 }
 static cudaError_t dev_alloc(void** p, size_t bytes, const char* what) { return traced(what, bytes, [&] { return cudaMalloc(p, bytes); }); }
 static cudaError_t host_alloc(void** p, size_t bytes, unsigned flags, const char* what) { return traced(what, bytes, [&] { return cudaHostAlloc(p, bytes, flags); }); }
+
+// A large pinned buffer.  cudaHostAlloc pins 4 KB pages one by one inside the driver (~0.45 ms per MB measured, and kernel launches
+// of other threads wait behind it); an anonymous mapping backed by transparent huge pages, faulted in here and then registered,
+// costs a third of that and only the short cudaHostRegister runs inside the driver (tools/exp/pin_bench.cu: 128 MB in 22 ms instead
+// of 57 ms, same 55 GB/s H2D).  Falls back to cudaHostAlloc wherever any step of that is refused.
+struct Pinned { void* p = nullptr; void* map = nullptr; size_t map_bytes = 0; };
+static cudaError_t pinned_alloc(Pinned* out, size_t bytes, const char* what)
+{
+    *out = Pinned{};
+    return traced(what, bytes, [&]() -> cudaError_t {
+        constexpr size_t kHuge = 2u << 20;
+        static const bool no_thp = getenv("EXLR_NO_THP") != nullptr;
+        if (bytes >= (8u << 20) && !no_thp) {
+            const size_t body = (bytes + kHuge - 1) / kHuge * kHuge, len = body + kHuge;
+            void* q = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+            if (q != MAP_FAILED) {
+                char* a = (char*)(((uintptr_t)q + kHuge - 1) / kHuge * kHuge);
+                madvise(a, body, MADV_HUGEPAGE);
+                for (size_t o = 0; o < bytes; o += 4096) ((volatile char*)a)[o] = 0;      // the page faults happen here, outside the driver
+                if (cudaHostRegister(a, bytes, cudaHostRegisterDefault) == cudaSuccess) { out->p = a; out->map = q; out->map_bytes = len; return cudaSuccess; }
+                cudaGetLastError();
+                munmap(q, len);
+            }
+        }
+        return cudaHostAlloc(&out->p, bytes, cudaHostAllocDefault);
+    });
+}
+static void pinned_free(Pinned* b)
+{
+    if (b->map) { cudaHostUnregister(b->p); munmap(b->map, b->map_bytes); }
+    else if (b->p) cudaFreeHost(b->p);
+    *b = Pinned{};
+}
 
 enum { EV_START = 0, EV_H2D, EV_K0, EV_K1, EV_K3A, EV_K3B, EV_K4A, EV_K4B, EV_D2H, EV_COUNT };
 
@@ -77,14 +111,14 @@ struct exlr_ctx {
 
 // What a submit is going to launch: decided on the host before anything is enqueued (and part of the identity of a captured graph).
 struct StepPlan {
-    bool overlap, screened, long_batch, two_level, fold, k0_walk, far, formatted;
-    int variant; uint32_t rpc;
+    bool overlap, fork_late, screened, long_batch, two_level, fold, k0_walk, far, formatted;
+    int variant, trace; uint32_t rpc;
     unsigned long long n_reads, n_ops;
     const void* events;                        // (exlr_batch_grow moves the event buffers: a graph captured before it is stale)
     bool operator==(const StepPlan& o) const
     {
-        return overlap == o.overlap && screened == o.screened && long_batch == o.long_batch && two_level == o.two_level && fold == o.fold && k0_walk == o.k0_walk &&
-               far == o.far && formatted == o.formatted && variant == o.variant && rpc == o.rpc && n_reads == o.n_reads && n_ops == o.n_ops && events == o.events;
+        return overlap == o.overlap && fork_late == o.fork_late && screened == o.screened && long_batch == o.long_batch && two_level == o.two_level && fold == o.fold && k0_walk == o.k0_walk &&
+               far == o.far && formatted == o.formatted && variant == o.variant && trace == o.trace && rpc == o.rpc && n_reads == o.n_reads && n_ops == o.n_ops && events == o.events;
     }
 };
 
@@ -109,6 +143,7 @@ struct exlr_batch {
                                                // events and line offsets (sized by the worst-case record count) are only allocated when
                                                // exlr_wait is actually called, and the pinned text buffer starts small
     uint32_t* h_loff_full = nullptr;           // lean batch: the line offsets, once exlr_wait has asked for them
+    Pinned pin_slab, pin_events, pin_text, pin_loff, pin_comp;   // how h_slab, h_events, h_text, h_loff_full, h_comp were pinned
     bool formatted = false;                    // the last submit ran kernels 5a/5b
     bool device_format = false;                // EXLR_OPT_DEVICE_FORMAT was set when the batch was allocated
     bool verbose_text = false;                 // a BAM batch allocated with EXLR_OPT_VERBOSE_TEXT: its device-formatted lines carry the -v columns
@@ -162,8 +197,8 @@ static constexpr size_t kLeanTextBytes = 16u << 20;     // pinned text buffer a 
 static void free_event_buffers(exlr_batch* b)
 {
     cudaFree(b->d_evslab); b->d_evslab = nullptr;
-    cudaFreeHost(b->h_events); b->h_events = nullptr;
-    cudaFreeHost(b->h_text); b->h_text = nullptr;
+    pinned_free(&b->pin_events); b->h_events = nullptr;
+    pinned_free(&b->pin_text); b->h_text = nullptr;
 }
 
 static int alloc_event_buffers(exlr_batch* b, uint64_t max_events)
@@ -179,9 +214,9 @@ static int alloc_event_buffers(exlr_batch* b, uint64_t max_events)
                  d_saev = dcarve(max_events * sizeof(exlr_event)), d_toff = dcarve(fmt ? (max_events + 1) * 4 : 0),
                  d_text = dcarve(text_cap + 16), d_ev = dcarve(max_events * sizeof(exlr_event));
     cudaError_t e = dev_alloc(&b->d_evslab, dof, "device events+text");
-    if (e == cudaSuccess && !b->lean_host) e = host_alloc((void**)&b->h_events, max_events * sizeof(exlr_event), cudaHostAllocDefault, "pinned events");
+    if (e == cudaSuccess && !b->lean_host) { e = pinned_alloc(&b->pin_events, max_events * sizeof(exlr_event), "pinned events"); b->h_events = (exlr_event*)b->pin_events.p; }
     b->h_text_cap = b->lean_host ? std::min<size_t>(text_cap, kLeanTextBytes) : text_cap;
-    if (e == cudaSuccess && fmt) e = host_alloc((void**)&b->h_text, b->h_text_cap + 16, cudaHostAllocDefault, "pinned text");
+    if (e == cudaSuccess && fmt) { e = pinned_alloc(&b->pin_text, b->h_text_cap + 16, "pinned text"); b->h_text = (char*)b->pin_text.p; }
     if (e != cudaSuccess) { free_event_buffers(b); return cuda_fail(e, "event buffers"); }
     char* ds = (char*)b->d_evslab;
     DevBatch& v = b->dv;
@@ -200,9 +235,10 @@ static int ensure_fetch_buffers(exlr_batch* b)
 {
     if (!b->lean_host) return EXLR_OK;
     cudaError_t e = cudaSuccess;
-    if (!b->h_events) e = host_alloc((void**)&b->h_events, b->hv.max_events * sizeof(exlr_event), cudaHostAllocDefault, "pinned events (on demand)");
+    if (!b->h_events) { e = pinned_alloc(&b->pin_events, b->hv.max_events * sizeof(exlr_event), "pinned events (on demand)"); b->h_events = (exlr_event*)b->pin_events.p; }
     if (e == cudaSuccess && !b->h_loff_full) {
-        e = host_alloc((void**)&b->h_loff_full, (b->hv.max_reads + 1) * 4, cudaHostAllocDefault, "pinned line_off (on demand)");
+        e = pinned_alloc(&b->pin_loff, (b->hv.max_reads + 1) * 4, "pinned line_off (on demand)");
+        b->h_loff_full = (uint32_t*)b->pin_loff.p;
         if (e == cudaSuccess) { b->h_loff_full[0] = 0; b->h_line_off = b->h_loff_full; }
     }
     return e == cudaSuccess ? EXLR_OK : cuda_fail(e, "pinned result buffers");
@@ -322,7 +358,7 @@ int exlr_set_option(exlr_ctx* c, int option, int64_t value)
     switch (option) {
     case EXLR_OPT_CIGAR_KERNEL: if (value < 0 || value > 3) return EXLR_ERR_ARG; c->cigar_kernel = (int)value; return EXLR_OK;
     case EXLR_OPT_READS_PER_CTA: if (value < 0 || value > 128) return EXLR_ERR_ARG; c->reads_per_cta = (uint32_t)value; return EXLR_OK;
-    case EXLR_OPT_OVERLAP: c->overlap = value != 0; return EXLR_OK;
+    case EXLR_OPT_OVERLAP: if (value < 0 || value > 2) return EXLR_ERR_ARG; c->overlap = (int)value; return EXLR_OK;
     case EXLR_OPT_DEVICE_FORMAT: c->device_format = value != 0; return EXLR_OK;
     case EXLR_OPT_VERBOSE_TEXT: c->verbose_text = value != 0; return EXLR_OK;
     case EXLR_OPT_K3_FOLD: c->k3_fold = value != 0; return EXLR_OK;
@@ -354,10 +390,10 @@ void exlr_batch_free(exlr_batch* b)
     if (b->stream) cudaStreamDestroy(b->stream);
     for (auto& e : b->ev_bam) if (e) cudaEventDestroy(e);
     if (b->ev_tail_copied) cudaEventDestroy(b->ev_tail_copied);
-    cudaFree(b->d_bam); cudaFreeHost(b->h_comp); cudaFreeHost(b->h_blocks); cudaFreeHost(b->h_btab); cudaFreeHost(b->h_bctrl);
+    cudaFree(b->d_bam); pinned_free(&b->pin_comp); cudaFreeHost(b->h_blocks); cudaFreeHost(b->h_btab); cudaFreeHost(b->h_bctrl);
     if (b->gexec) cudaGraphExecDestroy(b->gexec);
     cudaFree(b->d_slab); cudaFree(b->d_evslab);
-    cudaFreeHost(b->h_slab); cudaFreeHost(b->h_out); cudaFreeHost(b->h_events); cudaFreeHost(b->h_text); cudaFreeHost(b->h_loff_full);
+    pinned_free(&b->pin_slab); cudaFreeHost(b->h_out); pinned_free(&b->pin_events); pinned_free(&b->pin_text); pinned_free(&b->pin_loff);
     delete b;
 }
 
@@ -382,7 +418,9 @@ static int batch_alloc_impl(exlr_ctx* c, uint64_t max_reads, uint64_t max_ops, u
     if (host_inputs) {                         // (a BAM batch gets its records from the device-side decoder: no pinned input views)
         // (write-combined: the host only ever writes these views front to back; EXLR_OPT_WC_INPUT, off by default -- the host formatter
         // and check_sizes read a few words of them back, which is slow on write-combined memory but rare)
-        e = host_alloc(&b->h_slab, ho, c->wc_input ? cudaHostAllocWriteCombined : cudaHostAllocDefault, "pinned input views");
+        if (c->wc_input) { e = host_alloc(&b->pin_slab.p, ho, cudaHostAllocWriteCombined, "pinned input views (write-combined)"); }
+        else e = pinned_alloc(&b->pin_slab, ho, "pinned input views");
+        b->h_slab = b->pin_slab.p;
         if (e != cudaSuccess) { exlr_batch_free(b); return cuda_fail(e, "cudaHostAlloc(inputs)"); }
         char* hs = (char*)b->h_slab;
         b->hv.cigar = (uint32_t*)(hs + h_cigar); b->hv.cigar_off = (uint64_t*)(hs + h_coff); b->hv.pos = (int32_t*)(hs + h_pos);
@@ -534,8 +572,9 @@ static void plan_step(exlr_batch* b, StepPlan* p)
 {
     exlr_ctx* c = b->ctx;
     memset(p, 0, sizeof(*p));
-    p->n_reads = b->n_reads; p->n_ops = b->n_ops; p->events = b->dv.events;
+    p->n_reads = b->n_reads; p->n_ops = b->n_ops; p->events = b->dv.events; p->trace = c->trace;
     p->overlap = c->overlap && !c->params.split_only;
+    p->fork_late = p->overlap && c->overlap == 2;
     p->variant = c->cigar_kernel == 1 ? 1 : 0;
     if (!c->params.split_only) {
         p->rpc = c->reads_per_cta ? c->reads_per_cta : auto_rpc(b->n_reads, b->n_ops);
@@ -579,9 +618,10 @@ static int enqueue_step(exlr_batch* b, const StepPlan& p, bool timed)
     if (!c->params.split_only) {
         uint32_t n_tiles = 0;
         plan_k1(d, p.screened ? 1 : p.variant, p.rpc, &n_tiles);         // screened: raw events all go to the atomically allocated region
-        if (p.overlap) CK(cudaEventRecord(b->ev_fork, st));               // after the memset
+        if (p.overlap && !p.fork_late) CK(cudaEventRecord(b->ev_fork, st));   // after the memset
     }
     launch_k0(d, c->dparams, p.k0_walk, st); b->launches++;
+    if (p.fork_late) CK(cudaEventRecord(b->ev_fork, st));                 // EXLR_OPT_OVERLAP = 2: the CIGAR path starts once kernel 0 is done
     if (timed) CK(cudaEventRecord(b->ev[EV_K0], st));
     if (!c->params.split_only) {
         cudaStream_t s1 = p.overlap ? b->stream2 : st;
@@ -622,7 +662,7 @@ static int run_kernels(exlr_batch* b, bool prefetch_results)
     // as ONE CUDA graph launch from the third time on: the chain of 5-9 small kernels is then scheduled by the device, not
     // paced by this thread's launch calls (which jitter when several processes share the host).  The graph keeps the two-stream
     // fork/join and the programmatic-dependent-launch edges.  Varying shapes (a streamed BAM) launch directly, as before.
-    const bool graph_ok = c->graph && !c->stage_timing && !c->trace;
+    const bool graph_ok = c->graph && !c->stage_timing;
     if (graph_ok && b->gexec && plan == b->gplan) {
         CK(cudaGraphLaunch(b->gexec, st));
         b->launches = b->glaunches;
@@ -807,9 +847,10 @@ int exlr_wait_text(exlr_batch* b, exlr_result* res, const char** text, uint64_t*
         nb = off;
     }
     if (nb > b->h_text_cap) {                                            // lean batch: more text than its pinned buffer holds yet
-        cudaFreeHost(b->h_text); b->h_text = nullptr; b->d2h_text = 0;
+        pinned_free(&b->pin_text); b->h_text = nullptr; b->d2h_text = 0;
         b->h_text_cap = std::min<uint64_t>(b->dv.text_cap, nb + nb / 2);
-        const cudaError_t e = host_alloc((void**)&b->h_text, b->h_text_cap + 16, cudaHostAllocDefault, "pinned text (grown)");
+        const cudaError_t e = pinned_alloc(&b->pin_text, b->h_text_cap + 16, "pinned text (grown)");
+        b->h_text = (char*)b->pin_text.p;
         if (e != cudaSuccess) { b->h_text_cap = 0; return cuda_fail(e, "pinned text"); }
     }
     if (nb > b->d2h_text) {                                              // what the copy behind the kernels did not cover
@@ -864,7 +905,8 @@ int exlr_bam_batch_alloc(exlr_ctx* c, uint64_t max_comp_bytes, uint32_t max_bloc
     c->device_format = fmt;
     if (rc) return rc;
     b->is_bam = true; b->max_comp = max_comp_bytes; b->max_blocks = max_blocks; b->u_cap = u_cap; b->front_u = front_u;
-    cudaError_t e = host_alloc((void**)&b->h_comp, max_comp_bytes + 512, cudaHostAllocDefault, "pinned BGZF chunk");
+    cudaError_t e = pinned_alloc(&b->pin_comp, max_comp_bytes + 512, "pinned BGZF chunk");
+    b->h_comp = (uint8_t*)b->pin_comp.p;
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_blocks, (size_t)max_blocks * sizeof(exlr_bgzf_block), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_btab, ((size_t)max_blocks + 1) * sizeof(BgzfBlock), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&b->h_bctrl, sizeof(BamCtrl), cudaHostAllocMapped);

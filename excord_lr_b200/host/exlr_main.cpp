@@ -36,6 +36,7 @@ struct Cli {
     int gpus = 0;                       // 0 = all visible
     bool stats = false;                 // --stats: stage times on stderr
     unsigned long long batch_reads = 131072, batch_ops = 0, batch_sa = 0, batch_events = 0;
+    bool eager_alloc = false;           // --eager-alloc: every batch of every GPU exists before the first chunk is read (steady-state timing; slower start)
     bool host_reader = false;           // --host-reader: inflate + parse BAM on host threads (zlib) even when the GPU decoder applies
     unsigned long long chunk_mb = 128, chunk_blocks = 0, max_record_mb = 64, slots = 0;   // GPU decoder: compressed bytes / BGZF blocks per chunk
 };
@@ -69,6 +70,7 @@ static void usage(FILE* f)
           "      --chunk-blocks <N>                   GPU BAM decoder: BGZF blocks per chunk [default: by --chunk-mb]\n"
           "      --max-record-mb <N>                  GPU BAM decoder: largest BAM record, in megabytes [default: 64]\n"
           "      --slots <N>                          Batches in flight per GPU [default: 5 with the GPU BAM decoder, else 3]\n"
+          "      --eager-alloc                        Allocate every batch before the input is read (default: while the first ones work)\n"
           "      --stats                              Print stage times to stderr\n"
           "  -h, --help                               Print help\n"
           "  -V, --version                            Print version\n", f);
@@ -126,6 +128,7 @@ static int parse_cli(int argc, char** argv, Cli& c)
         else if (a == "--chunk-blocks") { NUM(30000); c.chunk_blocks = u; }
         else if (a == "--max-record-mb") { NUM(1023); c.max_record_mb = u ? u : 1; }
         else if (a == "--slots") { NUM(16); c.slots = u; }
+        else if (a == "--eager-alloc") { if (!flagopt(&c.eager_alloc)) return 2; }
         else if (a == "--stats") { if (!flagopt(&c.stats)) return 2; }
         else if (a == "-h" || a == "--help") { usage(stdout); return -1; }
         else if (a == "-V" || a == "--version") { puts("excord-LR 0.1.17"); return -1; }
@@ -273,7 +276,11 @@ int main(int argc, char** argv)
             }
         });
     };
-    { std::lock_guard<std::mutex> lk(mu); start_gpu(0); }
+    { std::lock_guard<std::mutex> lk(mu); start_gpu(0); if (cli.eager_alloc) for (int k = 1; k < ndev; k++) start_gpu(k); }
+    if (cli.eager_alloc) {               // the stream clock below then starts with every batch of every GPU in place
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { if (fatal) return true; for (auto& g : gpus) if ((int)g.freeq.size() < per_gpu) return false; return true; });
+    }
 
     using clk = std::chrono::steady_clock;
     auto secs = [](clk::duration d) { return std::chrono::duration<double>(d).count(); };

@@ -171,7 +171,7 @@ typedef struct exlr_batch exlr_batch;
                                     the per-step sums of 1a, see EXLR_OPT_LONG_RECORDS); event-dense batches fall back to 2.
                                     Forced: 1 = warp per record; 2 = flat TMA-staged block scan of everything; 3 = the screened path */
 #define EXLR_OPT_READS_PER_CTA 2 /* 0 = auto */
-#define EXLR_OPT_OVERLAP 3       /* 1 (default) = kernel 1 runs on a second stream beside kernels 0/3a/3b */
+#define EXLR_OPT_OVERLAP 3       /* 1 (default) = kernel 1 runs on a second stream beside kernels 0/3a/3b; 2 = the same, started once kernel 0 is done; 0 = one stream */
 #define EXLR_OPT_K1_CTAS_PER_SM 4 /* 1..4 CTAs of kernel 1 per SM; 0 (default) = 3 when overlapping, else 4 */
 #define EXLR_OPT_TRACE 7          /* debug: %globaltimer traces, read back with exlr_get_trace.  1 = kernel 1 / 1b per CTA / step, 2..6 = k0, k3a,
                                      k3b, k4a, k4b per CTA {start, mid, end}, 7 = timeline: entry k = {~first start, last end, -, CTAs} of kernel k */

@@ -33,18 +33,25 @@ with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") els
         print(f"{name}: {hb.n_reads} records, BAM {size / 1e6:.0f} MB (written in {tw:.0f} s)")
         ref_out = None
         for mode, extra in (("GPU BAM decoder (default)", []), (f"host reader, {args.threads} zlib threads (--host-reader)", ["--host-reader"])):
-            best, stats = None, []
-            for _ in range(3):
+            # wall: the process as a user starts it (batches are allocated while the first ones already work); stream: the CLI's own
+            # figure with every batch in place before the input is read (--eager-alloc) -- the steady-state rate of a large file
+            best, stats, stream = None, [], None
+            for eager in (False, False, False, True, True, True):
                 t0 = time.time()
-                r = subprocess.run([exe, "-b", bam, "-o", out, "-p", "0.8", "-t", str(args.threads), "--stats"] + extra, capture_output=True, text=True)
+                r = subprocess.run([exe, "-b", bam, "-o", out, "-p", "0.8", "-t", str(args.threads), "--stats"] + extra + (["--eager-alloc"] if eager else []),
+                                   capture_output=True, text=True)
                 dt = time.time() - t0
                 assert r.returncode == 0, r.stderr
-                if best is None or dt < best:
-                    best, stats = dt, r.stderr.strip().splitlines()
+                lines = r.stderr.strip().splitlines()
+                if not eager:
+                    best = dt if best is None else min(best, dt)
+                    continue
+                st = float(lines[-1].split("stream ")[1].split(" s")[0])
+                if stream is None or st < stream:
+                    stream, stats = st, lines
             got = open(out, "rb").read()
             assert ref_out is None or got == ref_out, "the two readers disagree"
             ref_out = got
-            stream = float(stats[-1].split("stream ")[1].split(" s")[0])
-            print(f"  {mode}: best of 3 wall {best:.3f} s; stream (after setup) {stream:.3f} s -> {hb.n_reads / stream:.3e} alignments/s, {size / stream / 1e9:.2f} GB/s of BAM file")
+            print(f"  {mode}: best of 3 wall {best:.3f} s (default start); steady-state stream (--eager-alloc) {stream:.3f} s -> {hb.n_reads / stream:.3e} alignments/s, {size / stream / 1e9:.2f} GB/s of BAM file")
             for ln in stats[-2:]:
                 print(f"    {ln}")
