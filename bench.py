@@ -422,7 +422,6 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="run kernel 1 on the same stream as the SA branch")
     ap.add_argument("--fork-late", action="store_true", help="A/B: start the CIGAR path once kernel 0 is done (EXLR_OPT_OVERLAP = 2)")
     ap.add_argument("--k3-fold", action="store_true", help="A/B: kernel 3a's work inside kernel 3b for short-CIGAR batches (EXLR_OPT_K3_FOLD)")
-    ap.add_argument("--k0-walk", action="store_true", help="A/B: kernel 3a's work inside kernel 0 for short-CIGAR batches (EXLR_OPT_K0_WALK)")
     ap.add_argument("--k1-ctas", type=int, default=0, help="persistent CTAs of kernel 1 per SM (1..4)")
     ap.add_argument("--k1-waves", type=int, default=0)
     args = ap.parse_args()
@@ -454,8 +453,6 @@ def main():
         ex_opts.append((api.EXLR_OPT_OVERLAP, 2))
     if args.k3_fold:
         ex_opts.append((api.EXLR_OPT_K3_FOLD, 1))
-    if args.k0_walk:
-        ex_opts.append((api.EXLR_OPT_K0_WALK, 1))
     if args.no_graph:
         ex_opts.append((api.EXLR_OPT_GRAPH, 0))
     if args.wc_input:
