@@ -9,8 +9,11 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -27,7 +30,13 @@ public:
     uint64_t bytes_read = 0;
     int threads = 8;                   // parallel pread()s per chunk: one thread copies page cache -> pinned memory at a few GB/s only
 
-    ~BgzfBamStream() { if (fd_ >= 0) close(fd_); }
+    ~BgzfBamStream()
+    {
+        { std::lock_guard<std::mutex> lk(pool_mu_); pool_stop_ = true; }
+        pool_cv_.notify_all();
+        for (auto& t : pool_) t.join();
+        if (fd_ >= 0) close(fd_);
+    }
 
     // true: `path` is a BGZF-compressed BAM and its header has been read.  false with an empty `error`: something else
     // (SAM text, plain data): the caller uses the host reader.
@@ -143,31 +152,75 @@ private:
         }
     }
 
-    // up to `want` bytes from the file position on; short only at the end of the file
-    size_t read_parallel(uint8_t* dst, size_t want)
+    // ---- the readers: `threads - 1` workers that live as long as the stream (a chunk is read every few milliseconds: starting
+    // 31 threads per chunk cost a quarter of the read itself) plus the calling thread.  A job is a range of the file cut into
+    // slices; whoever is free takes the next slice.
+    std::vector<std::thread> pool_;
+    std::mutex pool_mu_;
+    std::condition_variable pool_cv_, done_cv_;
+    bool pool_stop_ = false;
+    int pool_busy_ = 0;                   // workers inside read_slices() (guarded by pool_mu_): a new job is only set up at 0
+    uint64_t job_id_ = 0;                 // bumped per job (guarded by pool_mu_)
+    uint8_t* job_dst_ = nullptr; size_t job_want_ = 0, job_slices_ = 0; uint64_t job_fpos_ = 0;
+    std::atomic<size_t> job_next_{0}, job_left_{0};
+    std::vector<size_t> job_got_;
+
+    void read_slices()
     {
-        const size_t kSlice = 4u << 20;
-        const int nt = (int)std::min<size_t>((size_t)std::max(threads, 1), (want + kSlice - 1) / kSlice);
-        std::vector<size_t> got((size_t)std::max(nt, 1), 0);
-        auto work = [&](int t) {
-            const size_t a = want * (size_t)t / (size_t)nt, b = want * (size_t)(t + 1) / (size_t)nt;
+        for (;;) {
+            const size_t t = job_next_.fetch_add(1);
+            if (t >= job_slices_) return;
+            const size_t a = job_want_ * t / job_slices_, b = job_want_ * (t + 1) / job_slices_;
             size_t done = 0;
             while (a + done < b) {
-                const ssize_t n = ::pread(fd_, dst + a + done, b - a - done, (off_t)(fpos_ + a + done));
+                const ssize_t n = ::pread(fd_, job_dst_ + a + done, b - a - done, (off_t)(job_fpos_ + a + done));
                 if (n <= 0) break;
                 done += (size_t)n;
             }
-            got[(size_t)t] = done;
-        };
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; t++) th.emplace_back(work, t);
-        work(0);
-        for (auto& x : th) x.join();
+            job_got_[t] = done;
+            if (job_left_.fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(pool_mu_); done_cv_.notify_all(); }
+        }
+    }
+    void worker()
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(pool_mu_);
+                pool_cv_.wait(lk, [&] { return pool_stop_ || job_id_ != seen; });
+                if (pool_stop_) return;
+                seen = job_id_;
+                pool_busy_++;
+            }
+            read_slices();
+            { std::lock_guard<std::mutex> lk(pool_mu_); pool_busy_--; }
+            done_cv_.notify_all();
+        }
+    }
+
+    // up to `want` bytes from the file position on; short only at the end of the file
+    size_t read_parallel(uint8_t* dst, size_t want)
+    {
+        const size_t kSlice = 2u << 20;
+        const size_t slices = std::max<size_t>(1, (want + kSlice - 1) / kSlice);
+        const int nt = (int)std::min<size_t>((size_t)std::max(threads, 1), slices);
+        while ((int)pool_.size() < nt - 1) pool_.emplace_back([this] { worker(); });
+        {
+            std::unique_lock<std::mutex> lk(pool_mu_);
+            done_cv_.wait(lk, [&] { return pool_busy_ == 0; });     // (a worker of the previous job may still be on its way out)
+            job_dst_ = dst; job_want_ = want; job_slices_ = slices; job_fpos_ = fpos_;
+            job_got_.assign(slices, 0);
+            job_next_.store(0); job_left_.store(slices);
+            job_id_++;
+        }
+        pool_cv_.notify_all();
+        read_slices();
+        { std::unique_lock<std::mutex> lk(pool_mu_); done_cv_.wait(lk, [&] { return job_left_.load() == 0 && pool_busy_ == 0; }); }
         size_t total = 0;
-        for (int t = 0; t < nt; t++) {                       // contiguous prefix (a short slice means the file ended inside it)
-            const size_t a = want * (size_t)t / (size_t)nt, b = want * (size_t)(t + 1) / (size_t)nt;
-            total += got[(size_t)t];
-            if (got[(size_t)t] < b - a) break;
+        for (size_t t = 0; t < slices; t++) {                // contiguous prefix (a short slice means the file ended inside it)
+            const size_t a = want * t / slices, b = want * (t + 1) / slices;
+            total += job_got_[t];
+            if (job_got_[t] < b - a) break;
         }
         fpos_ += total; bytes_read += total;
         return total;

@@ -304,7 +304,9 @@ typedef struct exlr_bam_info {
 
 /* A batch for chunks of at most max_blocks BGZF blocks / max_comp_bytes compressed bytes, plus max_tail_bytes left over from
  * the previous chunk; its record capacity is the most such a chunk can hold, so no chunk overflows it.  Lines are always
- * formatted on the device. */
+ * formatted on the device (exlr_wait_text).  Such a batch keeps no pinned copies of the events and line offsets -- they are sized
+ * by the worst-case record count -- until exlr_wait is first called on it (which then allocates them); its pinned text buffer
+ * starts at 16 MB and grows when a chunk's lines need more. */
 int  exlr_bam_batch_alloc(exlr_ctx* ctx, uint64_t max_comp_bytes, uint32_t max_blocks, uint64_t max_tail_bytes, uint64_t max_events, exlr_batch** out);
 int  exlr_bam_get_views(exlr_batch* b, exlr_bam_views* v);
 int  exlr_bam_submit(exlr_batch* b, uint64_t comp_bytes, uint32_t n_blocks);

@@ -151,3 +151,19 @@ def test_chunker_sees_every_block(tmp_path):
     sam = str(tmp_path / "k.sam")
     bamio.write_sam(hb, sam)
     assert subprocess.run([DUMP, "--chunker", sam], capture_output=True, text=True).returncode == 1
+
+
+def test_chunker_reader_pool_reads_the_same_bytes(tmp_path):
+    # chunks larger than one read slice are read by the stream's worker pool (slices taken by whoever is free, the same workers
+    # chunk after chunk): any thread count and chunk size sees the same blocks, and the sample hash covers their bytes
+    _build()
+    hb = synth.config(1, 0.001)
+    bam = str(tmp_path / "p.bam")
+    bamio.write_bam(hb, bam, ref_lens=synth.ref_lens(), seq_len=15000, random_seq=True, level=1)
+    assert os.path.getsize(bam) > (12 << 20)
+    outs = set()
+    for cap, th in ((5 << 20, 1), (5 << 20, 8), (9 << 20, 32), (64 << 20, 5), (3 << 20, 16)):
+        r = subprocess.run([DUMP, "--chunker", bam, str(cap), "30000", str(th)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.add(r.stdout)
+    assert len(outs) == 1
