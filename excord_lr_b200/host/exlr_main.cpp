@@ -377,7 +377,7 @@ int main(int argc, char** argv)
         auto hand_over = [&](int si) { { std::lock_guard<std::mutex> lk(mu); inflight.push_back(si); } cv.notify_all(); };
         // waits for chunk `si`'s record walk and starts its event kernels; false = stop reading (error, or the stream ends here)
         bool settled_ok = false;                            // the last settle() left a usable result in its slot
-        auto release_slot = [&](int si) { std::lock_guard<std::mutex> lk(mu); gpus[slots[si].gpu].freeq.push_back(si); };
+        auto release_slot = [&](int si) { { std::lock_guard<std::mutex> lk(mu); gpus[slots[si].gpu].freeq.push_back(si); } cv.notify_all(); };
         auto settle = [&](int si) -> bool {
             Slot& s = slots[si];
             settled_ok = false;
@@ -402,65 +402,68 @@ int main(int argc, char** argv)
             return st == 0;
         };
         auto hand_over_settled = [&](int si) { if (settled_ok) hand_over(si); else release_slot(si); settled_ok = false; };
-        // The reader runs ahead: it reads and submits (H2D + inflate) chunks as long as slots are free, so that several chunks'
-        // inflate kernels share the GPU (one chunk alone leaves most warp slots empty and DEFLATE is latency-bound per block),
-        // while the chain walk(k) -> settle(k) -> walk(k+1) advances one chunk at a time behind it.
-        std::deque<int> pend;                               // submitted, not yet walked (in order)
-        int walked = -1;                                    // walked, not yet settled
-        int held = -1;                                      // settled, its leftover not yet handed to the next chunk
-        uint64_t start = bs.first_record_off;
-        bool input_done = false;
-        auto try_acquire = [&](uint64_t sq) -> int {        // a free slot of the GPU chunk sq goes to, if there is one right now
-            const int g = (int)(sq % (uint64_t)ndev);
-            std::lock_guard<std::mutex> lk(mu);
-            if (sq == 1) for (int k = 1; k < ndev; k++) start_gpu(k);
-            start_gpu(g);
-            if (fatal || gpus[g].freeq.empty()) return -1;
-            const int si = gpus[g].freeq.front(); gpus[g].freeq.pop_front(); return si;
-        };
-        auto release = [&](int si) { std::lock_guard<std::mutex> lk(mu); gpus[slots[si].gpu].freeq.push_back(si); };
-        int have = cur;                                     // the slot acquired above, for chunk 0
+        // Two threads share the input side.  The READER reads chunks into free batches and submits them (H2D + inflate) as fast as
+        // batches come back from the writer, so that several chunks' inflate kernels share the GPU(s) (one chunk alone leaves most
+        // warp slots empty and DEFLATE is latency-bound per block).  This thread drives the CHAIN walk(k) -> settle(k) -> walk(k+1)
+        // behind it, one chunk at a time: where chunk k+1's records begin is only known once chunk k has been walked.
+        std::mutex pm; std::condition_variable pcv;
+        std::deque<int> pend;                               // submitted, not yet walked, in order        (guarded by pm)
+        bool input_done = false, stop_reading = false;      // reader has left; chain asks it to leave  (guarded by pm)
+        auto release = [&](int si) { { std::lock_guard<std::mutex> lk(mu); gpus[slots[si].gpu].freeq.push_back(si); } cv.notify_all(); };
+        const int first_slot = cur;                         // the batch acquired above, for chunk 0
         cur = -1;
-        for (;;) {
-            // 1. run ahead
-            while (!input_done && !fatal) {
-                int si = have;
+        std::thread reader([&]() {
+            int have = first_slot;
+            for (uint64_t sq = 0;; sq++) {
+                const int si = have >= 0 ? have : acquire(sq);
                 have = -1;
-                if (si < 0) si = (pend.empty() && walked < 0) ? acquire(seq) : try_acquire(seq);
-                if (si < 0) break;
+                if (si < 0) break;                          // fatal
+                { std::lock_guard<std::mutex> lk(pm); if (stop_reading) { release(si); break; } }
                 Slot& s = slots[si];
                 auto t0 = clk::now();
                 size_t new_bytes = 0;
                 const size_t nb = bs.read_blocks(s.bv.comp, (size_t)s.bv.max_comp_bytes, s.bv.blocks, s.bv.max_blocks, &new_bytes);
                 t_read += secs(clk::now() - t0);
-                if (nb == 0) { input_done = true; release(si); break; }
+                if (nb == 0) { release(si); break; }
                 s.comp_bytes = new_bytes; s.n_new = (uint32_t)nb;
                 const int st = exlr_bam_submit(s.b, new_bytes, (uint32_t)nb);
-                if (st) { fail("exlr_bam_submit", st); release(si); input_done = true; break; }
-                pend.push_back(si);
-                seq++;
+                if (st) { fail("exlr_bam_submit", st); release(si); break; }
+                { std::lock_guard<std::mutex> lk(pm); pend.push_back(si); }
+                pcv.notify_all();
             }
-            if (fatal) break;
-            // 2. advance the chain by one chunk
-            if (walked >= 0) {
-                const bool go_on = settle(walked);
-                start = 0;
-                // its leftover (a partial last record) is copied in front of the next chunk on the device: the slot goes to the
-                // writer only once that copy is in the next chunk's stream (the library orders the slot's reuse behind it)
-                held = walked;
-                walked = -1;
-                if (!go_on) { hand_over_settled(held); held = -1; input_done = true; for (int si : pend) release(si); pend.clear(); break; }
+            { std::lock_guard<std::mutex> lk(pm); input_done = true; }
+            pcv.notify_all();
+        });
+        int held = -1;                                      // settled, its leftover not yet handed to the next chunk
+        uint64_t start = bs.first_record_off;
+        bool stopped = false;                               // the stream ends here: what the reader still submits is dropped
+        for (;;) {
+            int si;
+            {
+                std::unique_lock<std::mutex> lk(pm);
+                pcv.wait(lk, [&] { return !pend.empty() || input_done; });
+                if (pend.empty()) break;
+                si = pend.front(); pend.pop_front();
             }
-            if (pend.empty()) { if (input_done) { if (held >= 0) hand_over_settled(held); held = -1; break; } else continue; }
-            const int si = pend.front(); pend.pop_front();
+            if (stopped || fatal) { release(si); continue; }
             Slot& s = slots[si];
             s.walk_start = start; s.prev_slot = held;
             const int st = exlr_bam_walk(s.b, held >= 0 ? slots[held].b : nullptr, start);
+            // the previous chunk's leftover (a partial last record) is copied in front of this one on the device: its batch goes to
+            // the writer only now that the copy is in this chunk's stream (the library orders the batch's reuse behind it)
             if (held >= 0) { hand_over_settled(held); held = -1; }
             if (st == EXLR_ERR_CAPACITY) fprintf(stderr, "a BAM record is larger than --max-record-mb (%llu MB)\n", cli.max_record_mb);
-            if (st) { fail("exlr_bam_walk", st); break; }
-            walked = si;
+            if (st) { fail("exlr_bam_walk", st); release(si); stopped = true; }
+            else {
+                const bool go_on = settle(si);
+                start = 0;
+                held = si;
+                if (!go_on) { hand_over_settled(held); held = -1; stopped = true; }
+            }
+            if (stopped) { std::lock_guard<std::mutex> lk(pm); stop_reading = true; }
         }
+        if (held >= 0) hand_over_settled(held);
+        reader.join();
         // (a partial record left at the very end of the input is a truncated file: dropped, like a read error in the reference)
         cur = -1;
     }
