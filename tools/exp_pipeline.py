@@ -16,6 +16,9 @@ c = synth.CONFIGS[cfg]
 hb = synth.config(cfg, 1.0)
 ex = api.Extractor(ExlrParams.make(**c["params"]), hb.ref_names, 0)
 ex.set_option(api.EXLR_OPT_STAGE_TIMING, 0)
+for kv in os.environ.get("EXLR_EXP_OPTS", "").split(","):          # e.g. EXLR_EXP_OPTS=9:6  (option 9 = k1a CTAs per SM)
+    if kv:
+        ex.set_option(int(kv.split(":")[0]), int(kv.split(":")[1]))
 flush = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")
 for nb in counts:
     bs = [ex.batch_for(hb) for _ in range(nb)]
