@@ -550,8 +550,11 @@ __device__ __forceinline__ bool k1a_step(uint32_t imin16, uint32_t lut_lo, uint3
     return __any_sync(0xffffffffu, ((sus & 2u) | (flags & 0x40u)) != 0u);
 }
 
-template <bool SUMS>
-__global__ void __launch_bounds__(K1A_THREADS, K1A_CTAS) k1a_screen(DevBatch B, DevParams P, unsigned long long n_ops)
+// DEEP: half the CTAs per SM, two warp steps' loads in flight per thread (the next step is requested before this one is screened):
+// the same bytes in flight per SM from half the thread slots, which leaves the other half to whatever else is resident -- the
+// SA branch beside it, or the kernels of other batches when several steps are in flight (EXLR_OPT_K1A_CTAS_PER_SM <= 4).
+template <bool SUMS, bool DEEP>
+__global__ void __launch_bounds__(K1A_THREADS, DEEP ? 4 : K1A_CTAS) k1a_screen(DevBatch B, DevParams P, unsigned long long n_ops)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t nthreads = gridDim.x * K1A_THREADS, gt = blockIdx.x * K1A_THREADS + threadIdx.x;
@@ -575,10 +578,8 @@ __global__ void __launch_bounds__(K1A_THREADS, K1A_CTAS) k1a_screen(DevBatch B, 
         base = __shfl_sync(0xffffffffu, base, 0);
         if (lane < n) B.step_list[base + lane] = gw + (it0 + __fns(mask, 0, lane + 1)) * nw;
     };
-    uint32_t hitmask = 0, it = 0;
-    for (uint32_t v0 = gw * (32 * K1A_VEC); v0 < nvec; v0 += wstep, it++) {
+    auto load = [&](uint4 (&q)[K1A_VEC], uint32_t v0) {
         const uint4* p = cig + v0 + lane;
-        uint4 q[K1A_VEC];
         if ((unsigned long long)(v0 + 32 * K1A_VEC) * 4ull <= n_ops) {      // every op of the step exists
 #pragma unroll
             for (int k = 0; k < K1A_VEC; k++) q[k] = __ldg(p + 32 * k);
@@ -594,11 +595,36 @@ __global__ void __launch_bounds__(K1A_THREADS, K1A_CTAS) k1a_screen(DevBatch B, 
                 if (e0 + 4 > n_ops) q[k].w = 0u;
             }
         }
+    };
+    uint32_t hitmask = 0, it = 0;
+    auto screen = [&](const uint4 (&q)[K1A_VEC], uint32_t v0) {
         uint32_t ssum = 0;
         const bool hit = k1a_step<SUMS>(imin16, lut_lo, lut_hi, q, &ssum);
         if (SUMS && lane == 0) { const uint32_t st = v0 / (32 * K1A_VEC); B.step_sum[st] = ssum; B.step_flag[st] = hit ? 1 : 0; }
         hitmask |= (hit ? 1u : 0u) << (it & 31u);
         if ((it & 31u) == 31u) { append(hitmask, it - 31u); hitmask = 0; }
+        it++;
+    };
+    if (!DEEP) {
+        for (uint32_t v0 = gw * (32 * K1A_VEC); v0 < nvec; v0 += wstep) {
+            uint4 q[K1A_VEC];
+            load(q, v0);
+            screen(q, v0);
+        }
+    } else {
+        uint4 qa[K1A_VEC], qb[K1A_VEC];
+        uint32_t v0 = gw * (32 * K1A_VEC);
+        if (v0 < nvec) load(qa, v0);
+        while (v0 < nvec) {                                                 // two steps per trip: each is screened while the other's loads fly
+            const uint32_t v1 = v0 + wstep;                                 // (v0 + wstep cannot wrap: nvec < 2^31 and wstep < 2^26)
+            if (v1 < nvec) load(qb, v1);
+            screen(qa, v0);
+            if (v1 >= nvec) break;
+            const uint32_t v2 = v1 + wstep;
+            if (v2 < nvec) load(qa, v2);
+            screen(qb, v1);
+            v0 = v2;
+        }
     }
     append(hitmask, it & ~31u);
     tr.end();
@@ -1023,8 +1049,9 @@ void launch_k1a(const DevBatch& B, const DevParams& P, unsigned long long n_ops,
     const uint32_t cap = (uint32_t)B.hc.sms * (uint32_t)B.hc.k1a_ctas;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    if (sums) k1a_screen<true><<<grid, K1A_THREADS, 0, st>>>(B, P, n_ops);
-    else k1a_screen<false><<<grid, K1A_THREADS, 0, st>>>(B, P, n_ops);
+    const bool deep = B.hc.k1a_ctas <= 4;              // half the thread slots, two steps' loads in flight per thread
+    if (sums) { if (deep) k1a_screen<true, true><<<grid, K1A_THREADS, 0, st>>>(B, P, n_ops); else k1a_screen<true, false><<<grid, K1A_THREADS, 0, st>>>(B, P, n_ops); }
+    else { if (deep) k1a_screen<false, true><<<grid, K1A_THREADS, 0, st>>>(B, P, n_ops); else k1a_screen<false, false><<<grid, K1A_THREADS, 0, st>>>(B, P, n_ops); }
 }
 
 void launch_k1b(const DevBatch& B, const DevParams& P, unsigned long long n_ops, bool use_k1c, cudaStream_t st)

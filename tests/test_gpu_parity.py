@@ -166,6 +166,26 @@ def test_folded_sa_cigar_walk_and_graph_replay():
     b.free(); ex.close()
 
 
+def test_k1a_deep_prefetch_variant():
+    # EXLR_OPT_K1A_CTAS_PER_SM <= 4 selects the screen kernel with two warp steps' loads in flight per thread (half the CTAs per SM):
+    # same step list, same lines -- short batches (one partial step), ragged ends, long-record batches (per-step sums), ONT
+    cases = [(rand_batch(seed, n), rand_params(seed)) for seed, n in ((31, 900), (32, 41), (33, 3000))]
+    cases.append((synth.config(0, 1.0), ExlrParams.make(**synth.CONFIGS[0]["params"])))
+    cases.append((synth.config(1, 0.05), ExlrParams.make(**synth.CONFIGS[1]["params"])))
+    cases.append((synth.config(2, 0.004), ExlrParams.make(**synth.CONFIGS[2]["params"])))
+    for i, (hb, p) in enumerate(cases):
+        for ctas in (4, 2):
+            ex = api.Extractor(p, hb.ref_names)
+            ex.set_option(api.EXLR_OPT_CIGAR_KERNEL, 3)                  # the screened path, whatever the batch looks like
+            ex.set_option(9, ctas)
+            b = ex.batch_for(hb, max(40000, 2 * hb.n_reads))
+            for rnd in range(3):
+                b.submit()
+                res = b.wait()
+                check_result(hb, p, res, b.format_lines(res, False, None, 0, res.n_valid_lines()), label=f"deep k1a case{i} ctas{ctas} round{rnd}")
+            b.free(); ex.close()
+
+
 def test_empty_and_degenerate_batches():
     p = ExlrParams.make()
     # zero records
